@@ -1,0 +1,421 @@
+"""ctypes front-end for the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Loads ``oracle/libt3oracle.so`` (plain-C restatement, ``Oracle``) and, when present,
+``oracle/_ref/libt3ref{,_fixed}.so`` (the reference itself, ``Reference``).  Only tests/,
+``bench.py``'s cpu_baseline / ``--impl reference`` legs and ``__graft_entry__.smoke()``
+may import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RAW_MODE = 0xFF
+P1, P2, P3, P4, P5 = 0, 1, 2, 3, 4
+K_OF_UEP = (24, 22, 20, 18)
+
+
+class Cfg(C.Structure):
+    """Field-for-field mirror of ``t3o_cfg`` (= EncoderConfig, OLD:862-873)."""
+    _fields_ = [
+        ("profile", C.c_uint8), ("uep", C.c_uint8 * 9),
+        ("tile_w", C.c_uint16), ("tile_h", C.c_uint16),
+        ("seed_a", C.c_uint32), ("seed_b", C.c_uint32), ("seed_s0", C.c_uint32),
+        ("beacon_period", C.c_uint32), ("beacon_slot", C.c_uint8), ("beacon_enabled", C.c_uint8),
+        ("subword", C.c_uint8), ("centered", C.c_uint8), ("coset", C.c_uint8), ("pad_", C.c_uint8 * 3),
+        ("superframe_words", C.c_uint32),
+    ]
+
+    def copy(self) -> "Cfg":
+        c = Cfg()
+        C.memmove(C.byref(c), C.byref(self), C.sizeof(Cfg))
+        return c
+
+    def astuple(self):
+        return (self.profile, tuple(self.uep), self.tile_w, self.tile_h, self.seed_a, self.seed_b, self.seed_s0,
+                self.beacon_period, self.beacon_slot, self.beacon_enabled, self.subword, self.centered, self.coset)
+
+
+def make_cfg(profile=P2, uep=1, tile=(0, 0), seed=(1, 1, 1), beacon=(0, 0, False), superframe_words=8192,
+             subword=27, centered=True, coset=0) -> Cfg:
+    """EncoderConfig with the reference defaults (EncoderContext(): uniform UEP index 1 => k=22)."""
+    c = Cfg()
+    c.profile = profile
+    u = [uep] * 9 if isinstance(uep, int) else list(uep)
+    for i in range(9):
+        c.uep[i] = u[i]
+    c.tile_w, c.tile_h = tile
+    c.seed_a, c.seed_b, c.seed_s0 = seed
+    c.beacon_period, c.beacon_slot, c.beacon_enabled = beacon[0], beacon[1], 1 if beacon[2] else 0
+    c.superframe_words = superframe_words
+    c.subword, c.centered, c.coset = subword, 1 if centered else 0, coset
+    return c
+
+
+UEP_LUMA = (2, 1, 1, 2, 1, 1, 2, 1, 1)  # uep_luma_priority, OLD:68-72
+
+PIXEL_DTYPE = np.dtype([("Yq", "<u2"), ("Cbq", "<i2"), ("Crq", "<i2")])
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (always) and the reference shim (when /root/reference exists)."""
+    if force or not os.path.exists(os.path.join(HERE, "libt3oracle.so")) or \
+            os.path.getmtime(os.path.join(HERE, "libt3oracle.so")) < os.path.getmtime(os.path.join(HERE, "t3_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if os.path.exists("/root/reference/old/include/ternary_image_codec_v6_min.hpp"):
+        subprocess.check_call(["make", "-s", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+
+
+class _Lib:
+    """Common numpy-level API over either library; ``pfx`` is the symbol prefix (t3o_/t3r_)."""
+
+    def __init__(self, path: str, pfx: str, fixed: int | None):
+        self.lib = C.CDLL(path)
+        self.pfx = pfx
+        self.fixed = fixed  # None: the library takes a `fixed` argument (oracle); else baked in (reference builds)
+        L = self.lib
+        sz, u8p = C.c_size_t, C.POINTER(C.c_uint8)
+        for name in ("encode_profile", "pack_pixels", "profile_words_bound", "bytes_to_words", "encode_rgb"):
+            if hasattr(L, pfx + name):
+                getattr(L, pfx + name).restype = sz
+        for name in ("gf_add", "gf_sub", "gf_mul", "gf_inv", "gf_pow_alpha", "scramble_symbol", "descramble_symbol", "beacon_symbol"):
+            if hasattr(L, pfx + name):
+                getattr(L, pfx + name).restype = C.c_uint8
+        del u8p
+
+    def f(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+    # --- RS ---
+    def rs_gen(self, k):
+        g = np.zeros(9, np.uint8)
+        n = self.f("rs_gen")(C.c_int(k), _ptr(g))
+        return g[:n].copy()
+
+    def rs_encode_blocks(self, k, data, fixed=0):
+        data, dp = _u8(data)
+        n = data.size // k
+        out = np.zeros((n, 26), np.uint8)
+        if self.fixed is None:
+            self.f("rs_encode_blocks")(C.c_int(k), C.c_int(fixed), dp, C.c_size_t(n), _ptr(out))
+        else:
+            assert fixed == self.fixed
+            self.f("rs_encode_blocks")(C.c_int(k), dp, C.c_size_t(n), _ptr(out))
+        return out
+
+    def rs_decode_blocks(self, k, blocks, fixed=0):
+        """returns (corrected inout [n,26], out [n,k] (zeros when !ok), ok [n])"""
+        io = np.array(blocks, dtype=np.uint8, copy=True).reshape(-1, 26)
+        n = io.shape[0]
+        out = np.zeros((n, k), np.uint8)
+        ok = np.zeros(n, np.uint8)
+        if self.fixed is None:
+            self.f("rs_decode_blocks")(C.c_int(k), C.c_int(fixed), _ptr(io), C.c_size_t(n), _ptr(out), _ptr(ok))
+        else:
+            assert fixed == self.fixed
+            self.f("rs_decode_blocks")(C.c_int(k), _ptr(io), C.c_size_t(n), _ptr(out), _ptr(ok))
+        return io, out, ok
+
+    # --- header ---
+    def crc12(self, trits):
+        t, tp = _u8(trits)
+        out = np.zeros(12, np.uint8)
+        self.f("crc12")(tp, C.c_size_t(t.size), _ptr(out))
+        return out
+
+    def header_pack(self, cfg, frame_seq=0, band_map_hash=0):
+        out = np.zeros(27, np.uint8)
+        self.f("header_pack")(C.byref(cfg), C.c_uint32(frame_seq), C.c_uint32(band_map_hash), _ptr(out))
+        return out
+
+    def header_check(self, sym27):
+        s, sp = _u8(sym27)
+        return bool(self.f("header_check")(sp))
+
+    def header_unpack(self, sym27):
+        s, sp = _u8(sym27)
+        cfg = Cfg()
+        fs, bh, mg, ver = C.c_uint32(), C.c_uint32(), C.c_uint16(), C.c_uint8()
+        self.f("header_unpack")(sp, C.byref(cfg), C.byref(fs), C.byref(bh), C.byref(mg), C.byref(ver))
+        return cfg, fs.value, bh.value, mg.value, ver.value
+
+    # --- pixels ---
+    def pack_pixels(self, px):
+        px = np.ascontiguousarray(px, dtype=PIXEL_DTYPE)
+        nw = (px.size + 1) // 2
+        out = np.zeros((nw, 9), np.uint8)
+        self.f("pack_pixels")(px.ctypes.data_as(C.c_void_p), C.c_size_t(px.size), _ptr(out))
+        return out
+
+    def unpack_pixels(self, words):
+        w, wp = _u8(words)
+        nw = w.size // 9
+        px = np.zeros(2 * nw, PIXEL_DTYPE)
+        self.f("unpack_pixels")(wp, C.c_size_t(nw), px.ctypes.data_as(C.c_void_p))
+        return px
+
+    def rgb_to_quant(self, rgb):
+        r, rp = _u8(rgb)
+        n = r.size // 3
+        px = np.zeros(n, PIXEL_DTYPE)
+        self.f("rgb_to_quant")(rp, C.c_size_t(n), px.ctypes.data_as(C.c_void_p))
+        return px
+
+    def quant_to_rgb(self, px):
+        px = np.ascontiguousarray(px, dtype=PIXEL_DTYPE)
+        out = np.zeros((px.size, 3), np.uint8)
+        self.f("quant_to_rgb")(px.ctypes.data_as(C.c_void_p), C.c_size_t(px.size), _ptr(out))
+        return out
+
+    # --- permutation / scrambler ---
+    def interleave2d(self, sy, w, h, inverse=False):
+        a = np.array(sy, dtype=np.uint8, copy=True)
+        self.f("deinterleave2d" if inverse else "interleave2d")(_ptr(a), C.c_size_t(a.size), C.c_uint(w), C.c_uint(h))
+        return a
+
+    def scramble_stream(self, sy, a, b, s0, inverse=False):
+        out = np.zeros(len(sy), np.uint8)
+        st = C.c_uint32(s0 % 3)
+        fn = self.f("descramble_symbol" if inverse else "scramble_symbol")
+        for i, s in enumerate(sy):
+            out[i] = fn(C.c_uint8(int(s)), C.c_uint32(a), C.c_uint32(b), C.byref(st))
+        return out
+
+    def beacon_symbol(self, profile, seq, health=0):
+        return int(self.f("beacon_symbol")(C.c_uint8(profile), C.c_uint16(seq), C.c_uint8(health)))
+
+    # --- profile codec ---
+    def encode_profile(self, cfg, raw_words, fixed=0, cap=None):
+        raw, rp = _u8(raw_words)
+        n = raw.size // 9
+        if cap is None:
+            cap = 2 * n + 64
+        out = np.zeros((cap, 9), np.uint8)
+        if self.fixed is None:
+            r = self.f("encode_profile")(C.byref(cfg), C.c_int(fixed), rp, C.c_size_t(n), _ptr(out), C.c_size_t(cap))
+        else:
+            assert fixed == self.fixed
+            r = self.f("encode_profile")(C.byref(cfg), rp, C.c_size_t(n), _ptr(out), C.c_size_t(cap))
+        assert r != C.c_size_t(-1).value, "capacity too small"
+        return out[:r].copy()
+
+    def encode_rgb(self, cfg, rgb, fixed=0):
+        r_, rp = _u8(rgb)
+        n = r_.size // 3
+        cap = n + 64
+        out = np.zeros((cap, 9), np.uint8)
+        if self.fixed is None:
+            r = self.f("encode_rgb")(C.byref(cfg), C.c_int(fixed), rp, C.c_size_t(n), _ptr(out), C.c_size_t(cap))
+        else:
+            assert fixed == self.fixed
+            r = self.f("encode_rgb")(C.byref(cfg), rp, C.c_size_t(n), _ptr(out), C.c_size_t(cap))
+        return out[:r].copy()
+
+
+class Oracle(_Lib):
+    def __init__(self):
+        build()
+        super().__init__(os.path.join(HERE, "libt3oracle.so"), "t3o_", None)
+        self.lib.t3o_gf_log.restype = C.c_int
+
+    def words_bound(self, cfg, n_words):
+        return int(self.lib.t3o_profile_words_bound(C.byref(cfg), C.c_size_t(n_words)))
+
+    def decode_profile_ref(self, seen, words):
+        """returns (ok, out_words, seen_after)"""
+        w, wp = _u8(words)
+        n = w.size // 9
+        seen = seen.copy()
+        out = np.zeros((n + 8, 9), np.uint8)
+        n_out = C.c_size_t()
+        ok = self.lib.t3o_decode_profile_ref(C.byref(seen), wp, C.c_size_t(n), _ptr(out), C.c_size_t(n + 8), C.byref(n_out))
+        return bool(ok), out[:n_out.value].copy(), seen
+
+    def decode_profile_fixed(self, cfg, words, n_raw_words=0):
+        """returns (ok, out_words, n_corrected)"""
+        w, wp = _u8(words)
+        n = w.size // 9
+        out = np.zeros((n + 8, 9), np.uint8)
+        n_out, ncorr = C.c_size_t(), C.c_size_t()
+        ok = self.lib.t3o_decode_profile_fixed(C.byref(cfg), C.c_size_t(n_raw_words), wp, C.c_size_t(n), _ptr(out),
+                                               C.c_size_t(n + 8), C.byref(n_out), C.byref(ncorr))
+        return bool(ok), out[:n_out.value].copy(), ncorr.value
+
+    def decode_rgb_fixed(self, cfg, words, n_px):
+        w, wp = _u8(words)
+        n = w.size // 9
+        rgb = np.zeros((n_px, 3), np.uint8)
+        npx, ncorr = C.c_size_t(), C.c_size_t()
+        ok = self.lib.t3o_decode_rgb_fixed(C.byref(cfg), C.c_size_t(n_px), wp, C.c_size_t(n), _ptr(rgb), C.byref(npx), C.byref(ncorr))
+        return bool(ok), rgb[:npx.value].copy(), ncorr.value
+
+    def gf_tables(self):
+        L = self.lib
+        exp = np.array([L.t3o_gf_pow_alpha(C.c_int(i)) for i in range(78)], np.uint8)
+        log = np.array([L.t3o_gf_log(C.c_uint8(i)) for i in range(27)], np.int16)
+        mul = np.array([[L.t3o_gf_mul(C.c_uint8(a), C.c_uint8(b)) for b in range(27)] for a in range(27)], np.uint8).reshape(-1)
+        inv = np.array([L.t3o_gf_inv(C.c_uint8(i)) for i in range(27)], np.uint8)
+        return exp, log, mul, inv
+
+
+class Reference(_Lib):
+    """The reference itself (oracle/_ref/, built from /root/reference); fixed=False: as shipped."""
+
+    def __init__(self, fixed: bool = False):
+        build()
+        path = os.path.join(HERE, "_ref", "libt3ref_fixed.so" if fixed else "libt3ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        super().__init__(path, "t3r_", 1 if fixed else 0)
+
+    @staticmethod
+    def available() -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", "libt3ref.so")) or \
+            os.path.exists("/root/reference/old/include/ternary_image_codec_v6_min.hpp")
+
+    def decode_profile_ref(self, seen, words):
+        w, wp = _u8(words)
+        n = w.size // 9
+        seen = seen.copy()
+        out = np.zeros((n + 8, 9), np.uint8)
+        n_out = C.c_size_t()
+        ok = self.lib.t3r_decode_profile(C.byref(seen), wp, C.c_size_t(n), _ptr(out), C.c_size_t(n + 8), C.byref(n_out))
+        return bool(ok), out[:n_out.value].copy(), seen
+
+    def gf_tables(self):
+        exp, log, mul, inv = np.zeros(78, np.uint8), np.zeros(27, np.int16), np.zeros(729, np.uint8), np.zeros(27, np.uint8)
+        prim = C.c_uint8()
+        self.lib.t3r_gf_tables(_ptr(exp), log.ctypes.data_as(C.c_void_p), _ptr(mul), _ptr(inv), C.byref(prim))
+        return exp, log, mul, inv
+
+    def selftests(self):
+        a, b = C.c_int(), C.c_int()
+        self.lib.t3r_selftests(C.byref(a), C.byref(b))
+        return bool(a.value), bool(b.value)
+
+    def words_to_bytes(self, words):
+        w, wp = _u8(words)
+        out = np.zeros(w.size, np.uint8)
+        self.lib.t3r_words_to_bytes(wp, C.c_size_t(w.size // 9), _ptr(out))
+        return out
+
+    def bytes_to_words(self, b):
+        b, bp = _u8(b)
+        out = np.zeros((b.size // 9 + 1, 9), np.uint8)
+        n = self.lib.t3r_bytes_to_words(bp, C.c_size_t(b.size), _ptr(out))
+        return out[:n].copy()
+
+
+# --------------------------------------------------------------------------------------
+# Deterministic synthetic inputs (counter based: identical on CPU and GPU), SURVEY 8(d).
+# --------------------------------------------------------------------------------------
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def h(seed: int, idx: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        return splitmix64(np.uint64(seed) * np.uint64(0xD1342543DE82EF95) + idx.astype(np.uint64))
+
+
+def synth_rgb(seed: int, n_px: int) -> np.ndarray:
+    return (h(seed, np.arange(3 * n_px, dtype=np.uint64)) & np.uint64(0xFF)).astype(np.uint8).reshape(n_px, 3)
+
+
+def synth_checker(w: int, hgt: int, cell: int = 8) -> np.ndarray:
+    """8x8 checkerboard of (32,200,64)/(200,32,220), src/minitest_codec.cpp:31-42."""
+    yy, xx = np.mgrid[0:hgt, 0:w]
+    m = ((xx // cell + yy // cell) % 2).astype(bool)
+    out = np.empty((hgt, w, 3), np.uint8)
+    out[~m] = (32, 200, 64)
+    out[m] = (200, 32, 220)
+    return out.reshape(-1, 3)
+
+
+def synth_quant(seed: int, n_px: int) -> np.ndarray:
+    r = h(seed, np.arange(3 * n_px, dtype=np.uint64)).reshape(n_px, 3)
+    px = np.zeros(n_px, PIXEL_DTYPE)
+    px["Yq"] = (r[:, 0] % np.uint64(243)).astype(np.uint16)
+    px["Cbq"] = (r[:, 1] % np.uint64(81)).astype(np.int16) - 40
+    px["Crq"] = (r[:, 2] % np.uint64(81)).astype(np.int16) - 40
+    return px
+
+
+def inject_errors(words: np.ndarray, cfg: Cfg, n_raw_words: int, seed: int, gf_add, exact_t: bool = False):
+    """Corrupt e_c <= t_b symbols in every body codeword of an encoder output (no beacon/any k).
+
+    Positions and magnitudes are counter based: for codeword c, e_c = h(seed,c) % (t+1) (or t when
+    exact_t), distinct positions, symbol replaced by gf_add(sym, 1 + h%26).  Works on the wire format
+    (52 header symbols, band-major body, optional beacon expansion).  Returns (corrupted, n_errors).
+    """
+    flat = np.array(words, dtype=np.uint8, copy=True).reshape(-1)
+    n_s = (26 * n_raw_words + 2) // 3
+    period, slot = cfg.beacon_period, cfg.beacon_slot
+    has_b = bool(cfg.beacon_enabled and period > 0 and slot < 9)
+    cw_index = 0
+    total = 0
+    for b in range(9):
+        k = K_OF_UEP[cfg.uep[b] % 4]
+        t = (26 - k) // 2
+        s_b = (n_s - b + 8) // 9 if n_s > b else 0
+        ncw = s_b // k
+        if ncw == 0:
+            continue
+        c_idx = np.arange(cw_index, cw_index + ncw, dtype=np.uint64)
+        e = np.full(ncw, t, np.int64) if exact_t else (h(seed, c_idx) % np.uint64(t + 1)).astype(np.int64)
+        for j in range(t):
+            sel = e > j
+            if not sel.any():
+                continue
+            # distinct positions: j-th element of a per-codeword pseudo-random permutation start/stride
+            start = (h(seed + 1, c_idx) % np.uint64(26)).astype(np.int64)
+            stride = np.array([1, 3, 5, 7, 9, 11, 15, 17, 19, 21, 23, 25], np.int64)[(h(seed + 2, c_idx) % np.uint64(12)).astype(np.int64)]
+            pos = (start + j * stride) % 26
+            mag = (h(seed + 3 + j, c_idx) % np.uint64(26)).astype(np.int64) + 1
+            p = 26 * c_idx.astype(np.int64) + pos  # pre-beacon body index
+            if has_b:
+                q = beacon_expand_index(p, period, slot)
+            else:
+                q = p
+            idx = (52 + q)[sel]
+            flat[idx] = gf_add[flat[idx].astype(np.int64) % 27, mag[sel]]
+            total += int(sel.sum())
+        cw_index += ncw
+    return flat.reshape(-1, 9), total
+
+
+def beacon_expand_index(p, period, slot):
+    """pre-beacon body index p -> index q in the beacon-expanded body (A.5): every `period` words one
+    word carries the beacon in `slot` and only 8 body symbols."""
+    per = 9 * period - 1
+    blk, rem = p // per, p % per
+    first = rem < 8
+    wordoff = np.where(first, 0, 1 + (rem - 8) // 9)
+    slotidx = np.where(first, np.where(rem < slot, rem, rem + 1), (rem - 8) % 9)
+    return 9 * (blk * period + wordoff) + slotidx
+
+
+def gf_add_table() -> np.ndarray:
+    a = np.arange(27)
+    t = np.zeros((27, 27), np.uint8)
+    for x in a:
+        for y in a:
+            t[x, y] = ((x % 3 + y % 3) % 3) + 3 * (((x // 3) % 3 + (y // 3) % 3) % 3) + 9 * (((x // 9) + (y // 9)) % 3)
+    return t
