@@ -1,0 +1,161 @@
+/*
+ * t3c.h -- C ABI of libt3c.so: the B200-native (sm_100a) implementation of the Ternary Image
+ * Codec v6 data-parallel encode/decode path.
+ *
+ * The reference has no FFI layer: the path is a header-only set of inline C++ functions
+ * (old/include/ternary_image_codec_v6_min.hpp, "OLD").  Each entry point below replaces one of
+ * them (cited as OLD:line / IMG:line = old/include/io_image.hpp:line); the C++ shim headers in
+ * this directory (ternary_image_codec_v6_min.hpp, ternary_packing.hpp, io_image_bridge.hpp) keep
+ * the reference's names and types and forward here.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - Word27 = 9 bytes, symbol s at byte s (OLD:666-669); PixelYCbCrQuant = 6 bytes (OLD:670-674);
+ *     RGB8 = 3 bytes interleaved, row-major.  No torch/C++ types cross this boundary.
+ *   - Host-buffer calls copy in/out on the context's stream and return when the result is in
+ *     the caller's buffer.  `_dev` calls take device pointers and a cudaStream_t (as void*), are
+ *     asynchronous and never synchronise, except where a result count must be returned.
+ *   - One t3c_ctx per device; calls on one ctx are serialised by the caller.
+ *   - There is NO CPU fallback: without a CUDA device t3c_create fails with T3C_ERR_NODEVICE.
+ *   - arith: T3C_REF_EXACT reproduces the reference bit for bit, bugs included;
+ *     T3C_FIXED applies the 3-line RS repair and, for decode, inverts the
+ *     encoder's framing.
+ */
+#ifndef T3C_H
+#define T3C_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define T3C_API
+#else
+#define T3C_API __attribute__((visibility("default")))
+#endif
+
+typedef struct t3c_ctx t3c_ctx;
+
+typedef enum {
+    T3C_OK = 0,
+    T3C_ERR_ARG = 1,        /* bad argument (null pointer, invalid k, ...) */
+    T3C_ERR_CUDA = 2,       /* CUDA runtime error, see t3c_last_error */
+    T3C_ERR_CAPACITY = 3,   /* output buffer too small */
+    T3C_ERR_NODEVICE = 4,   /* no CUDA device / driver: there is no CPU fallback */
+    T3C_ERR_UNSUPPORTED = 5
+} t3c_status;
+
+typedef enum { T3C_REF_EXACT = 0, T3C_FIXED = 1 } t3c_arith;
+
+#define T3C_PROFILE_RAW 0xFF /* ProfileID::RAW_MODE, OLD:34 */
+
+/* EncoderConfig (OLD:862-873) / DecoderConfigSeen (OLD:874-884) as plain integers. */
+typedef struct {
+    uint8_t  profile;           /* ProfileID 0..4 = P1..P5, 0xFF = RAW_MODE */
+    uint8_t  uep[9];            /* UEPLayout::band_profile; k = {24,22,20,18}[uep%4]  (OLD:1089-1100) */
+    uint16_t tile_w, tile_h;    /* Tile2D; used only when profile==P5 and both non-zero (OLD:1083) */
+    uint32_t seed_a, seed_b, seed_s0; /* ScramblerSeed */
+    uint32_t beacon_period;     /* SparseBeaconCfg::words_period */
+    uint8_t  beacon_slot;
+    uint8_t  beacon_enabled;
+    uint8_t  subword;           /* SubwordMode 27/24/21/18/15 (header slot 12 only) */
+    uint8_t  centered;
+    uint8_t  coset;             /* CosetID 0..2 (header slot 16 only) */
+    uint8_t  pad_[3];
+    uint32_t superframe_words;  /* only %5 reaches the beacon payload (OLD:1130) */
+} t3c_config;
+
+typedef struct { uint16_t Yq; int16_t Cbq, Crq; } t3c_pixel; /* PixelYCbCrQuant */
+
+/* ---- context ---------------------------------------------------------------------------- */
+T3C_API t3c_status  t3c_create(int device, t3c_ctx** out);      /* EncoderContext()/DecoderContext() ctor work, OLD:885-916 */
+T3C_API void        t3c_destroy(t3c_ctx* ctx);
+T3C_API const char* t3c_last_error(const t3c_ctx* ctx);
+T3C_API int         t3c_version(void);
+T3C_API void        t3c_config_default(t3c_config* cfg);        /* EncoderConfig defaults + uep_uniform(1), OLD:862-873,898 */
+T3C_API void*       t3c_stream(t3c_ctx* ctx);                   /* the context's cudaStream_t */
+T3C_API t3c_status  t3c_sync(t3c_ctx* ctx);
+T3C_API uint64_t    t3c_kernel_launches(const t3c_ctx* ctx);    /* kernels launched by this ctx so far */
+
+/* ---- sizes ------------------------------------------------------------------------------ */
+/* exact number of profile words encode_profile_from_raw emits for n_raw_words */
+T3C_API size_t t3c_profile_words(const t3c_config* cfg, size_t n_raw_words);
+
+/* ---- K1: RGB8 <-> quant <-> Word27 -------------------------------------------------------- */
+/* rgb_to_quant_stream, IMG:156-170 (rgb_to_ycbcr IMG:47-56 + quantize_ycbcr IMG:69-78) */
+T3C_API t3c_status t3c_rgb_to_quant(t3c_ctx*, const uint8_t* rgb, size_t n_px, t3c_pixel* out);
+/* quant_stream_to_rgb, IMG:171-192 */
+T3C_API t3c_status t3c_quant_to_rgb(t3c_ctx*, const t3c_pixel* px, size_t n_px, uint8_t* rgb);
+/* encode_raw_pixels_to_words, OLD:723-734: writes ceil(n_px/2) words */
+T3C_API t3c_status t3c_pack_pixels(t3c_ctx*, const t3c_pixel* px, size_t n_px, uint8_t* words9, size_t* n_words);
+/* decode_raw_words_to_pixels, OLD:735-747: writes 2*n_words pixels */
+T3C_API t3c_status t3c_unpack_pixels(t3c_ctx*, const uint8_t* words9, size_t n_words, t3c_pixel* px);
+/* tpack::words_to_bytes / bytes_to_words, include/ternary_packing.hpp:53-65 (each symbol %27) */
+T3C_API t3c_status t3c_words_to_bytes(t3c_ctx*, const uint8_t* words9, size_t n_words, uint8_t* bytes);
+
+/* ---- stage-level block codecs (parity hooks for OLD:490-663, 749-813, 155-380) ------------- */
+/* RSCodec::encode_block over n_blocks blocks of k symbols -> 26 symbols each, OLD:517-535 */
+T3C_API t3c_status t3c_rs_encode_blocks(t3c_ctx*, int k, int arith, const uint8_t* data, size_t n_blocks, uint8_t* out26);
+/* RSCodec::decode_block, OLD:546-662: inout26 corrected in place, out_k = first k symbols (zeros when !ok) */
+T3C_API t3c_status t3c_rs_decode_blocks(t3c_ctx*, int k, int arith, uint8_t* inout26, size_t n_blocks, uint8_t* out_k, uint8_t* ok);
+/* interleave2D_boustrophedon / deinterleave2D_boustrophedon, OLD:750-813 (in place) */
+T3C_API t3c_status t3c_interleave2d(t3c_ctx*, uint8_t* syms, size_t n, uint16_t w, uint16_t h, int inverse);
+/* HeaderCodec::pack + 2x RS(26,18): the 52 coded header symbols, OLD:1142-1158 (device kernel) */
+T3C_API t3c_status t3c_header_emit(t3c_ctx*, const t3c_config*, int arith, uint8_t hdr27[27], uint8_t coded52[52]);
+/* read_and_decode_header_from_words, OLD:918-937: *ok = RS+CRC verdict */
+T3C_API t3c_status t3c_header_parse(t3c_ctx*, int arith, const uint8_t* words9, size_t n_words, t3c_config* out, int* ok);
+
+/* ---- K2..K5: profile codec ----------------------------------------------------------------- */
+/* encode_profile_from_raw, OLD:1043-1169 */
+T3C_API t3c_status t3c_encode_profile(t3c_ctx*, const t3c_config*, int arith, const uint8_t* raw9, size_t n_words,
+                                      uint8_t* out9, size_t cap_words, size_t* n_out);
+/* decode_profile_to_raw AS SHIPPED, OLD:995-1041: `seen` is DecoderContext::cfg_last_seen (read, then
+ * overwritten from the header); *ok is the reference's bool; on !ok *n_out = 0. */
+T3C_API t3c_status t3c_decode_profile(t3c_ctx*, t3c_config* seen, const uint8_t* in9, size_t n_words,
+                                      uint8_t* out9, size_t cap_words, size_t* n_out, int* ok);
+/* consistent decoder for T3C_FIXED streams.  cfg = the encoder's config (carried out of
+ * band: the 27-symbol header cannot hold tiles >= 27, UEP index 3 or periods > 26, bug B7);
+ * n_raw_words = N_w given to the encoder (0 = infer from n_words; not possible with the 2D interleave).
+ * *n_out = recovered prefix of raw words (the encoder drops < k symbols per band, bug B8). */
+T3C_API t3c_status t3c_decode_profile_fixed(t3c_ctx*, const t3c_config* cfg, size_t n_raw_words, const uint8_t* in9,
+                                            size_t n_words, uint8_t* out9, size_t cap_words, size_t* n_out, int* ok,
+                                            size_t* n_corrected);
+
+/* ---- fused, batched frames (old/src/main.cpp:15-26 as one call) ----------------------------- */
+/* n_frames RGB8 frames of n_px pixels each -> n_frames profile-word streams of *words_per_frame words,
+ * frame f at out9 + f*stride_words*9.  Equal to rgb_to_quant_stream -> encode_raw_pixels_to_words ->
+ * encode_profile_from_raw per frame. */
+T3C_API t3c_status t3c_encode_frames_rgb8(t3c_ctx*, const t3c_config*, int arith, const uint8_t* rgb, size_t n_px,
+                                          size_t n_frames, uint8_t* out9, size_t stride_words, size_t* words_per_frame);
+/* inverse (T3C_FIXED framing): per frame decode -> decode_raw_words_to_pixels -> quant_stream_to_rgb.
+ * ok[f] per frame; pixels past the recovered prefix are left untouched; *px_recovered per frame. */
+T3C_API t3c_status t3c_decode_frames_rgb8(t3c_ctx*, const t3c_config*, const uint8_t* in9, size_t words_per_frame,
+                                          size_t stride_words, size_t n_frames, size_t n_px, uint8_t* rgb,
+                                          uint8_t* ok, size_t* px_recovered, size_t* n_corrected);
+
+/* ---- device-pointer variants (bench / pipelines: PCIe outside the timed region) ------------- */
+T3C_API t3c_status t3c_rgb_to_quant_dev(t3c_ctx*, const uint8_t* d_rgb, size_t n_px, t3c_pixel* d_out, void* stream);
+T3C_API t3c_status t3c_quant_to_rgb_dev(t3c_ctx*, const t3c_pixel* d_px, size_t n_px, uint8_t* d_rgb, void* stream);
+T3C_API t3c_status t3c_pack_pixels_dev(t3c_ctx*, const t3c_pixel* d_px, size_t n_px, uint8_t* d_words9, void* stream);
+T3C_API t3c_status t3c_unpack_pixels_dev(t3c_ctx*, const uint8_t* d_words9, size_t n_words, t3c_pixel* d_px, void* stream);
+T3C_API t3c_status t3c_rs_encode_blocks_dev(t3c_ctx*, int k, int arith, const uint8_t* d_data, size_t n_blocks, uint8_t* d_out26, void* stream);
+T3C_API t3c_status t3c_rs_decode_blocks_dev(t3c_ctx*, int k, int arith, uint8_t* d_inout26, size_t n_blocks, uint8_t* d_out_k, uint8_t* d_ok, void* stream);
+T3C_API t3c_status t3c_encode_profile_dev(t3c_ctx*, const t3c_config*, int arith, const uint8_t* d_raw9, size_t n_words,
+                                          uint8_t* d_out9, size_t cap_words, void* stream);
+/* d_status[0] = ok flag (1/0), d_status[1] = symbols corrected; both written asynchronously */
+T3C_API t3c_status t3c_decode_profile_fixed_dev(t3c_ctx*, const t3c_config*, size_t n_raw_words, const uint8_t* d_in9,
+                                                size_t n_words, uint8_t* d_out9, size_t cap_words, uint32_t* d_status, void* stream);
+T3C_API t3c_status t3c_encode_frames_rgb8_dev(t3c_ctx*, const t3c_config*, int arith, const uint8_t* d_rgb, size_t n_px,
+                                              size_t n_frames, uint8_t* d_out9, size_t stride_words, void* stream);
+/* d_status: 2 uint32 per frame {ok, n_corrected} */
+T3C_API t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx*, const t3c_config*, const uint8_t* d_in9, size_t words_per_frame,
+                                              size_t stride_words, size_t n_frames, size_t n_px, uint8_t* d_rgb,
+                                              uint32_t* d_status, void* stream);
+/* which kernel family the fused calls will use for this config: 1 = tiled fast path, 0 = general path */
+T3C_API int t3c_fast_path_available(const t3c_config* cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T3C_H */

@@ -1,0 +1,624 @@
+// api.cu -- the C ABI of libt3c.so (include/t3c.h): context, device buffers, host<->device staging
+// and dispatch to the kernels.  No CPU implementation of any codec stage lives here: without a CUDA
+// device every entry point fails (T3C_ERR_NODEVICE), loudly.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "launch.h"
+#include "t3c_internal.h"
+
+using namespace t3c;
+static_assert(sizeof(t3c_config) == 44 && sizeof(t3c_pixel) == 6, "ABI struct layout");
+
+struct t3c_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    DevTables tabs{};
+    void* d_tables = nullptr;
+    // grow-only device scratch
+    struct Buf { void* p = nullptr; size_t cap = 0; };
+    Buf buf[6];
+    // small results: device mailbox + pinned host mirror (copied explicitly, MAIL_DOWN)
+    struct Mail { uint32_t status[64]; t3c_config cfg; int ok; uint8_t hdr27[27]; uint8_t coded52[52]; };
+    Mail* h_mail = nullptr;
+    Mail* d_mail = nullptr;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+enum { B_IN = 0, B_OUT = 1, B_TMP = 2, B_TMP2 = 3, B_AUX = 4, B_AUX2 = 5 };
+
+t3c_status fail(t3c_ctx* c, t3c_status s, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    return s;
+}
+#define CU(call)                                                                   \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) return fail(ctx, T3C_ERR_CUDA, #call, e_);          \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int d) { cudaGetDevice(&prev); if (prev != d) cudaSetDevice(d); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+t3c_status reserve(t3c_ctx* ctx, int slot, size_t bytes, void** out)
+{
+    t3c_ctx::Buf& b = ctx->buf[slot];
+    if (bytes + 64 > b.cap) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (b.p) CU(cudaFree(b.p));
+        b.p = nullptr; b.cap = 0;
+        size_t want = bytes + 64 + bytes / 8;
+        CU(cudaMalloc(&b.p, want));
+        b.cap = want;
+    }
+    *out = b.p;
+    return T3C_OK;
+}
+template <class T>
+t3c_status reserve_t(t3c_ctx* ctx, int slot, size_t bytes, T** out)
+{
+    void* p = nullptr;
+    t3c_status s = reserve(ctx, slot, bytes, &p);
+    *out = static_cast<T*>(p);
+    return s;
+}
+t3c_status check_launch(t3c_ctx* ctx, int n)
+{
+    ctx->launches += (uint64_t)n;
+    CU(cudaGetLastError());
+    return T3C_OK;
+}
+#define TRY(expr) do { t3c_status s_ = (expr); if (s_ != T3C_OK) return s_; } while (0)
+
+void ref_dec_geom(const t3c_config& h, size_t n_words, RefDecGeom& g)
+{
+    static const int ks[4] = {24, 22, 20, 18};
+    std::memset(&g, 0, sizeof g);
+    g.n_body_words = n_words - 6;
+    const bool skip = h.beacon_enabled && h.beacon_period > 0; // OLD:952
+    g.period = skip ? h.beacon_period : 0;
+    g.slot = skip ? h.beacon_slot : -1;
+    uint64_t use = 0;
+    for (int b = 0; b < 9; ++b) {
+        g.k[b] = ks[h.uep[b] % 4];
+        uint64_t L = g.n_body_words;
+        if (skip && b == h.beacon_slot) L -= (g.n_body_words + h.beacon_period - 1) / h.beacon_period;
+        g.ncw[b] = L / 26;
+        g.use_base[b] = use;
+        use += g.ncw[b] * (uint64_t)g.k[b];
+    }
+    g.n_use = use;
+    if (h.profile == 4 && h.tile_w && h.tile_h) { g.tile_w = h.tile_w; g.tile_area = (uint64_t)h.tile_w * h.tile_h; } // OLD:1018
+    scrambler_states(h.seed_a, h.seed_b, h.seed_s0, g.st);
+}
+
+// recovered prefix of the regrouped stream for the consistent decoder (A.8): first position of sy
+// (pre-interleave order) that is not covered by a decoded codeword
+uint64_t known_prefix(const t3c_config& c, const Geom& g)
+{
+    uint64_t pfx = g.n_s;
+    for (int b = 0; b < 9; ++b) {
+        const uint64_t first_unknown = 9 * ((uint64_t)g.k[b] * g.ncw[b]) + b;
+        if (first_unknown < pfx) pfx = first_unknown;
+    }
+    if (use_2d(c) && pfx < g.n_s) {
+        const uint64_t A = g.tile_area, base = (pfx / A) * A, off = pfx - base, row = off / c.tile_w;
+        if (row & 1) pfx = base + row * c.tile_w; // a reversed row loses its low end first
+    }
+    return pfx;
+}
+
+} // namespace
+
+extern "C" {
+
+int t3c_version(void) { return 100; }
+
+void t3c_config_default(t3c_config* c)
+{
+    std::memset(c, 0, sizeof *c);
+    c->profile = 1;
+    for (int i = 0; i < 9; ++i) c->uep[i] = 1;
+    c->seed_a = c->seed_b = c->seed_s0 = 1;
+    c->superframe_words = 8192;
+    c->subword = 27;
+    c->centered = 1;
+}
+
+t3c_status t3c_create(int device, t3c_ctx** out)
+{
+    if (!out) return T3C_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return T3C_ERR_NODEVICE;
+    t3c_ctx* ctx = new t3c_ctx();
+    ctx->device = device;
+    DeviceGuard guard(device);
+    HostTables* ht = new HostTables();
+    build_tables(*ht);
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(HostTables));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, ht, sizeof(HostTables), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_mail, sizeof(t3c_ctx::Mail));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_mail, sizeof(t3c_ctx::Mail));
+    if (e == cudaSuccess) e = cudaMemset(ctx->d_mail, 0, sizeof(t3c_ctx::Mail));
+    delete ht;
+    if (e != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
+    ctx->tabs.gf = &static_cast<HostTables*>(ctx->d_tables)->gf;
+    ctx->tabs.rs = &static_cast<HostTables*>(ctx->d_tables)->rs;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->tabs.sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return T3C_OK;
+}
+
+void t3c_destroy(t3c_ctx* ctx)
+{
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->buf) if (b.p) cudaFree(b.p);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
+    if (ctx->d_mail) cudaFree(ctx->d_mail);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* t3c_last_error(const t3c_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+void* t3c_stream(t3c_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t t3c_kernel_launches(const t3c_ctx* ctx) { return ctx ? ctx->launches : 0; }
+t3c_status t3c_sync(t3c_ctx* ctx)
+{
+    if (!ctx) return T3C_ERR_ARG;
+    DeviceGuard guard(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return T3C_OK;
+}
+size_t t3c_profile_words(const t3c_config* cfg, size_t n_raw_words) { return cfg ? profile_words(*cfg, n_raw_words) : 0; }
+int t3c_fast_path_available(const t3c_config* cfg) { return cfg && fast_path_ok(*cfg) ? 1 : 0; }
+
+// =============================================================================================
+// device-pointer API
+// =============================================================================================
+t3c_status t3c_rgb_to_quant_dev(t3c_ctx* ctx, const uint8_t* d_rgb, size_t n_px, t3c_pixel* d_out, void* st)
+{
+    if (!ctx || (n_px && (!d_rgb || !d_out))) return fail(ctx, T3C_ERR_ARG, "rgb_to_quant: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_rgb_to_quant(d_rgb, n_px, d_out, (cudaStream_t)st));
+}
+t3c_status t3c_quant_to_rgb_dev(t3c_ctx* ctx, const t3c_pixel* d_px, size_t n_px, uint8_t* d_rgb, void* st)
+{
+    if (!ctx || (n_px && (!d_rgb || !d_px))) return fail(ctx, T3C_ERR_ARG, "quant_to_rgb: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_quant_to_rgb(d_px, n_px, d_rgb, (cudaStream_t)st));
+}
+t3c_status t3c_pack_pixels_dev(t3c_ctx* ctx, const t3c_pixel* d_px, size_t n_px, uint8_t* d_words, void* st)
+{
+    if (!ctx || (n_px && (!d_px || !d_words))) return fail(ctx, T3C_ERR_ARG, "pack_pixels: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_pack_pixels(d_px, n_px, d_words, (cudaStream_t)st));
+}
+t3c_status t3c_unpack_pixels_dev(t3c_ctx* ctx, const uint8_t* d_words, size_t n_words, t3c_pixel* d_px, void* st)
+{
+    if (!ctx || (n_words && (!d_px || !d_words))) return fail(ctx, T3C_ERR_ARG, "unpack_pixels: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_unpack_pixels(d_words, n_words, d_px, (cudaStream_t)st));
+}
+t3c_status t3c_rs_encode_blocks_dev(t3c_ctx* ctx, int k, int arith, const uint8_t* d_data, size_t n, uint8_t* d_out, void* st)
+{
+    if (!ctx || !k_valid(k) || (n && (!d_data || !d_out))) return fail(ctx, T3C_ERR_ARG, "rs_encode_blocks: bad k or null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_rs_encode_blocks(ctx->tabs, k, arith, d_data, n, d_out, (cudaStream_t)st));
+}
+t3c_status t3c_rs_decode_blocks_dev(t3c_ctx* ctx, int k, int arith, uint8_t* d_inout, size_t n, uint8_t* d_out_k, uint8_t* d_ok, void* st)
+{
+    if (!ctx || !k_valid(k) || (n && (!d_inout || !d_out_k || !d_ok))) return fail(ctx, T3C_ERR_ARG, "rs_decode_blocks: bad k or null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_rs_decode_blocks(ctx->tabs, k, arith, d_inout, n, d_out_k, d_ok, (cudaStream_t)st));
+}
+
+t3c_status t3c_encode_profile_dev(t3c_ctx* ctx, const t3c_config* cfg, int arith, const uint8_t* d_raw, size_t n_words,
+                                  uint8_t* d_out, size_t cap_words, void* st)
+{
+    if (!ctx || !cfg || !d_out || (n_words && !d_raw)) return fail(ctx, T3C_ERR_ARG, "encode_profile: null");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)st;
+    if (cfg->profile == T3C_PROFILE_RAW) { // OLD:1046-1050
+        if (cap_words < n_words) return fail(ctx, T3C_ERR_CAPACITY, "encode_profile: capacity");
+        CU(cudaMemcpyAsync(d_out, d_raw, 9 * n_words, cudaMemcpyDeviceToDevice, s));
+        return T3C_OK;
+    }
+    Geom g;
+    make_geom(*cfg, n_words, arith, g);
+    if (cap_words < g.n_out) return fail(ctx, T3C_ERR_CAPACITY, "encode_profile: capacity");
+    return check_launch(ctx, launch_encode_general(ctx->tabs, *cfg, g, d_raw, d_out, s));
+}
+
+t3c_status t3c_decode_profile_fixed_dev(t3c_ctx* ctx, const t3c_config* cfg, size_t n_raw_words, const uint8_t* d_in, size_t n_words,
+                                        uint8_t* d_out, size_t cap_words, uint32_t* d_status, void* st)
+{
+    if (!ctx || !cfg || !d_in || !d_out || !d_status) return fail(ctx, T3C_ERR_ARG, "decode_profile_fixed: null");
+    if (cfg->profile == T3C_PROFILE_RAW || !n_raw_words) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_profile_fixed_dev: needs n_raw_words and a coded profile");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)st;
+    Geom g;
+    make_geom(*cfg, n_raw_words, 1, g);
+    if (g.n_out != n_words) return fail(ctx, T3C_ERR_ARG, "decode_profile_fixed: n_words does not match the config");
+    uint64_t nw = 3 * known_prefix(*cfg, g) / 26;
+    if (nw > n_raw_words) nw = n_raw_words;
+    if (cap_words < nw) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile_fixed: capacity");
+    uint8_t* sy = nullptr;
+    TRY(reserve_t(ctx, B_TMP, g.n_s + 16, &sy));
+    CU(cudaMemsetAsync(sy, 0, g.n_s + 16, s));
+    int n = launch_init_status(d_status, 1, s);
+    n += launch_decode_fixed_general(ctx->tabs, g, d_in, sy, d_status, s);
+    n += launch_regroup_words(sy, g.n_s, g.tile_area, g.tile_w, d_out, (size_t)nw, s);
+    return check_launch(ctx, n);
+}
+
+t3c_status t3c_encode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, int arith, const uint8_t* d_rgb, size_t n_px, size_t n_frames,
+                                      uint8_t* d_out, size_t stride_words, void* st)
+{
+    if (!ctx || !cfg || !d_rgb || !d_out) return fail(ctx, T3C_ERR_ARG, "encode_frames: null");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)st;
+    const size_t n_words = (n_px + 1) / 2;
+    const size_t n_out = profile_words(*cfg, n_words);
+    if (stride_words < n_out) return fail(ctx, T3C_ERR_CAPACITY, "encode_frames: stride < words per frame");
+    if (cfg->profile != T3C_PROFILE_RAW && fast_path_ok(*cfg)) {
+        Geom g;
+        make_geom(*cfg, n_words, arith, g);
+        return check_launch(ctx, launch_encode_rgb_fast(ctx->tabs, *cfg, g, d_rgb, n_px, n_frames, d_out, stride_words, s));
+    }
+    // general path: per frame K1 (bridge, pack) into scratch, then the general profile encoder
+    t3c_pixel* q = nullptr;
+    uint8_t* raw = nullptr;
+    TRY(reserve_t(ctx, B_AUX, 6 * n_px, &q));
+    TRY(reserve_t(ctx, B_AUX2, 9 * n_words, &raw));
+    for (size_t f = 0; f < n_frames; ++f) {
+        int n = launch_rgb_to_quant(d_rgb + 3 * n_px * f, n_px, q, s);
+        n += launch_pack_pixels(q, n_px, raw, s);
+        TRY(check_launch(ctx, n));
+        TRY(t3c_encode_profile_dev(ctx, cfg, arith, raw, n_words, d_out + 9 * stride_words * f, stride_words, st));
+    }
+    return T3C_OK;
+}
+
+t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, const uint8_t* d_in, size_t words_per_frame, size_t stride_words,
+                                      size_t n_frames, size_t n_px, uint8_t* d_rgb, uint32_t* d_status, void* st)
+{
+    if (!ctx || !cfg || !d_in || !d_rgb || !d_status) return fail(ctx, T3C_ERR_ARG, "decode_frames: null");
+    if (cfg->profile == T3C_PROFILE_RAW) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: RAW profile carries raw words, use unpack_pixels");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = (cudaStream_t)st;
+    const size_t n_words = (n_px + 1) / 2;
+    Geom g;
+    make_geom(*cfg, n_words, 1, g);
+    if (g.n_out != words_per_frame) return fail(ctx, T3C_ERR_ARG, "decode_frames: words_per_frame does not match config and n_px");
+    uint64_t nw = 3 * known_prefix(*cfg, g) / 26;
+    if (nw > n_words) nw = n_words;
+    size_t px_out = 2 * (size_t)nw < n_px ? 2 * (size_t)nw : n_px;
+    TRY(check_launch(ctx, launch_init_status(d_status, n_frames, s)));
+    if (fast_path_ok(*cfg))
+        return check_launch(ctx, launch_decode_rgb_fast(ctx->tabs, *cfg, g, d_in, stride_words, n_frames, n_px, px_out, d_rgb, d_status, s));
+    uint8_t* sy = nullptr;
+    TRY(reserve_t(ctx, B_TMP, g.n_s + 16, &sy));
+    for (size_t f = 0; f < n_frames; ++f) {
+        CU(cudaMemsetAsync(sy, 0, g.n_s + 16, s));
+        int n = launch_decode_fixed_general(ctx->tabs, g, d_in + 9 * stride_words * f, sy, d_status + 2 * f, s);
+        n += launch_regroup_rgb(sy, g.n_s, g.tile_area, g.tile_w, d_rgb + 3 * n_px * f, px_out, s);
+        TRY(check_launch(ctx, n));
+    }
+    return T3C_OK;
+}
+
+// =============================================================================================
+// host-buffer API: stage in, run, stage out
+// =============================================================================================
+#define H2D(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream))
+#define D2H(dst, src, bytes) CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream))
+#define SYNC() CU(cudaStreamSynchronize(ctx->stream))
+#define MAIL_UP() CU(cudaMemcpyAsync(ctx->d_mail, ctx->h_mail, sizeof(t3c_ctx::Mail), cudaMemcpyHostToDevice, ctx->stream))
+#define MAIL_DOWN()                                                                                               \
+    do {                                                                                                          \
+        CU(cudaMemcpyAsync(ctx->h_mail, ctx->d_mail, sizeof(t3c_ctx::Mail), cudaMemcpyDeviceToHost, ctx->stream)); \
+        SYNC();                                                                                                   \
+    } while (0)
+
+t3c_status t3c_rgb_to_quant(t3c_ctx* ctx, const uint8_t* rgb, size_t n_px, t3c_pixel* out)
+{
+    if (!ctx || (n_px && (!rgb || !out))) return fail(ctx, T3C_ERR_ARG, "rgb_to_quant: null");
+    if (!n_px) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t* d_in; t3c_pixel* d_out;
+    TRY(reserve_t(ctx, B_IN, 3 * n_px, &d_in)); TRY(reserve_t(ctx, B_OUT, 6 * n_px, &d_out));
+    H2D(d_in, rgb, 3 * n_px);
+    TRY(t3c_rgb_to_quant_dev(ctx, d_in, n_px, d_out, ctx->stream));
+    D2H(out, d_out, 6 * n_px);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_quant_to_rgb(t3c_ctx* ctx, const t3c_pixel* px, size_t n_px, uint8_t* rgb)
+{
+    if (!ctx || (n_px && (!rgb || !px))) return fail(ctx, T3C_ERR_ARG, "quant_to_rgb: null");
+    if (!n_px) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    t3c_pixel* d_in; uint8_t* d_out;
+    TRY(reserve_t(ctx, B_IN, 6 * n_px, &d_in)); TRY(reserve_t(ctx, B_OUT, 3 * n_px, &d_out));
+    H2D(d_in, px, 6 * n_px);
+    TRY(t3c_quant_to_rgb_dev(ctx, d_in, n_px, d_out, ctx->stream));
+    D2H(rgb, d_out, 3 * n_px);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_pack_pixels(t3c_ctx* ctx, const t3c_pixel* px, size_t n_px, uint8_t* words, size_t* n_words)
+{
+    if (!ctx || (n_px && (!px || !words))) return fail(ctx, T3C_ERR_ARG, "pack_pixels: null");
+    const size_t nw = (n_px + 1) / 2;
+    if (n_words) *n_words = nw;
+    if (!n_px) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    t3c_pixel* d_in; uint8_t* d_out;
+    TRY(reserve_t(ctx, B_IN, 6 * n_px, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * nw, &d_out));
+    H2D(d_in, px, 6 * n_px);
+    TRY(t3c_pack_pixels_dev(ctx, d_in, n_px, d_out, ctx->stream));
+    D2H(words, d_out, 9 * nw);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_unpack_pixels(t3c_ctx* ctx, const uint8_t* words, size_t n_words, t3c_pixel* px)
+{
+    if (!ctx || (n_words && (!px || !words))) return fail(ctx, T3C_ERR_ARG, "unpack_pixels: null");
+    if (!n_words) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t* d_in; t3c_pixel* d_out;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, 12 * n_words, &d_out));
+    H2D(d_in, words, 9 * n_words);
+    TRY(t3c_unpack_pixels_dev(ctx, d_in, n_words, d_out, ctx->stream));
+    D2H(px, d_out, 12 * n_words);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_words_to_bytes(t3c_ctx* ctx, const uint8_t* words, size_t n_words, uint8_t* bytes)
+{
+    if (!ctx || (n_words && (!bytes || !words))) return fail(ctx, T3C_ERR_ARG, "words_to_bytes: null");
+    if (!n_words) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * n_words, &d_out));
+    H2D(d_in, words, 9 * n_words);
+    TRY(check_launch(ctx, launch_mod27(d_in, 9 * n_words, d_out, ctx->stream)));
+    D2H(bytes, d_out, 9 * n_words);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_rs_encode_blocks(t3c_ctx* ctx, int k, int arith, const uint8_t* data, size_t n, uint8_t* out26)
+{
+    if (!ctx || !k_valid(k) || (n && (!data || !out26))) return fail(ctx, T3C_ERR_ARG, "rs_encode_blocks: bad k or null");
+    if (!n) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, n * k, &d_in)); TRY(reserve_t(ctx, B_OUT, n * 26, &d_out));
+    H2D(d_in, data, n * k);
+    TRY(t3c_rs_encode_blocks_dev(ctx, k, arith, d_in, n, d_out, ctx->stream));
+    D2H(out26, d_out, n * 26);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_rs_decode_blocks(t3c_ctx* ctx, int k, int arith, uint8_t* inout26, size_t n, uint8_t* out_k, uint8_t* ok)
+{
+    if (!ctx || !k_valid(k) || (n && (!inout26 || !out_k || !ok))) return fail(ctx, T3C_ERR_ARG, "rs_decode_blocks: bad k or null");
+    if (!n) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_io, *d_out, *d_ok;
+    TRY(reserve_t(ctx, B_IN, n * 26, &d_io)); TRY(reserve_t(ctx, B_OUT, n * k, &d_out)); TRY(reserve_t(ctx, B_TMP, n, &d_ok));
+    H2D(d_io, inout26, n * 26);
+    TRY(t3c_rs_decode_blocks_dev(ctx, k, arith, d_io, n, d_out, d_ok, ctx->stream));
+    D2H(inout26, d_io, n * 26);
+    D2H(out_k, d_out, n * k);
+    D2H(ok, d_ok, n);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_interleave2d(t3c_ctx* ctx, uint8_t* syms, size_t n, uint16_t w, uint16_t h, int inverse)
+{
+    (void)inverse; // the boustrophedon permutation is an involution: one kernel serves both directions
+    if (!ctx || (n && !syms)) return fail(ctx, T3C_ERR_ARG, "interleave2d: null");
+    if (!n || !w || !h) return T3C_OK; // OLD:752
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, n, &d_in)); TRY(reserve_t(ctx, B_OUT, n, &d_out));
+    H2D(d_in, syms, n);
+    TRY(check_launch(ctx, launch_perm2d(d_in, d_out, n, w, h, ctx->stream)));
+    D2H(syms, d_out, n);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_header_emit(t3c_ctx* ctx, const t3c_config* cfg, int arith, uint8_t hdr27[27], uint8_t coded52[52])
+{
+    if (!ctx || !cfg) return fail(ctx, T3C_ERR_ARG, "header_emit: null");
+    DeviceGuard guard(ctx->device);
+    TRY(check_launch(ctx, launch_header_emit(ctx->tabs, *cfg, arith, ctx->d_mail->hdr27, ctx->d_mail->coded52, ctx->stream)));
+    MAIL_DOWN();
+    if (hdr27) std::memcpy(hdr27, ctx->h_mail->hdr27, 27);
+    if (coded52) std::memcpy(coded52, ctx->h_mail->coded52, 52);
+    return T3C_OK;
+}
+t3c_status t3c_header_parse(t3c_ctx* ctx, int arith, const uint8_t* words, size_t n_words, t3c_config* out, int* ok)
+{
+    if (!ctx || !out || !ok || (n_words && !words)) return fail(ctx, T3C_ERR_ARG, "header_parse: null");
+    DeviceGuard guard(ctx->device);
+    *ok = 0;
+    if (n_words < 6) return T3C_OK; // OLD:920
+    uint8_t* d_in;
+    TRY(reserve_t(ctx, B_IN, 54, &d_in));
+    H2D(d_in, words, 54);
+    ctx->h_mail->cfg = *out;
+    ctx->h_mail->ok = 0;
+    MAIL_UP();
+    TRY(check_launch(ctx, launch_header_parse(ctx->tabs, arith, d_in, n_words, &ctx->d_mail->cfg, &ctx->d_mail->ok, ctx->stream)));
+    MAIL_DOWN();
+    *ok = ctx->h_mail->ok;
+    if (*ok) *out = ctx->h_mail->cfg;
+    return T3C_OK;
+}
+
+t3c_status t3c_encode_profile(t3c_ctx* ctx, const t3c_config* cfg, int arith, const uint8_t* raw, size_t n_words, uint8_t* out,
+                              size_t cap_words, size_t* n_out)
+{
+    if (!ctx || !cfg || !out || !n_out || (n_words && !raw)) return fail(ctx, T3C_ERR_ARG, "encode_profile: null");
+    DeviceGuard guard(ctx->device);
+    const size_t no = profile_words(*cfg, n_words);
+    *n_out = 0;
+    if (cap_words < no) return fail(ctx, T3C_ERR_CAPACITY, "encode_profile: capacity");
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * no, &d_out));
+    if (n_words) H2D(d_in, raw, 9 * n_words);
+    TRY(t3c_encode_profile_dev(ctx, cfg, arith, d_in, n_words, d_out, no, ctx->stream));
+    if (no) D2H(out, d_out, 9 * no);
+    SYNC();
+    *n_out = no;
+    return T3C_OK;
+}
+
+t3c_status t3c_decode_profile(t3c_ctx* ctx, t3c_config* seen, const uint8_t* in, size_t n_words, uint8_t* out, size_t cap_words,
+                              size_t* n_out, int* ok)
+{
+    if (!ctx || !seen || !n_out || !ok || (n_words && !in)) return fail(ctx, T3C_ERR_ARG, "decode_profile: null");
+    DeviceGuard guard(ctx->device);
+    *n_out = 0; *ok = 0;
+    if (seen->profile == T3C_PROFILE_RAW) { // stateful passthrough keyed on the PREVIOUS header, OLD:998-1002
+        if (cap_words < n_words) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile: capacity");
+        if (n_words) std::memcpy(out, in, 9 * n_words); // out=in: a host-to-host copy of the caller's own buffers, no codec work
+        *n_out = n_words; *ok = 1;
+        return T3C_OK;
+    }
+    if (n_words < 6) return T3C_OK;
+    uint8_t* d_in;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in));
+    H2D(d_in, in, 9 * n_words);
+    ctx->h_mail->cfg = *seen;
+    ctx->h_mail->ok = 0;
+    MAIL_UP();
+    TRY(check_launch(ctx, launch_header_parse(ctx->tabs, 0, d_in, n_words, &ctx->d_mail->cfg, &ctx->d_mail->ok, ctx->stream)));
+    MAIL_DOWN();
+    if (!ctx->h_mail->ok) return T3C_OK;            // header rejected: cfg_last_seen untouched (OLD:1005)
+    *seen = ctx->h_mail->cfg;                       // OLD:1006-1013, before the body is looked at
+    RefDecGeom g;
+    ref_dec_geom(*seen, n_words, g);
+    const size_t nw = (size_t)(3 * g.n_use / 26);
+    uint8_t *use, *d_out;
+    TRY(reserve_t(ctx, B_TMP, g.n_use + 16, &use)); TRY(reserve_t(ctx, B_OUT, 9 * nw + 16, &d_out));
+    int n = launch_init_status(ctx->d_mail->status, 1, ctx->stream);
+    n += launch_decode_ref_general(ctx->tabs, g, d_in, use, ctx->d_mail->status, ctx->stream);
+    TRY(check_launch(ctx, n));
+    MAIL_DOWN();
+    if (!ctx->h_mail->status[0]) return T3C_OK;     // some block failed: out stays empty (OLD:987,997)
+    if (cap_words < nw) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile: capacity");
+    TRY(check_launch(ctx, launch_regroup_words(use, g.n_use, g.tile_area, g.tile_w, d_out, nw, ctx->stream)));
+    if (nw) D2H(out, d_out, 9 * nw);
+    SYNC();
+    *n_out = nw; *ok = 1;
+    return T3C_OK;
+}
+
+t3c_status t3c_decode_profile_fixed(t3c_ctx* ctx, const t3c_config* cfg, size_t n_raw_words, const uint8_t* in, size_t n_words,
+                                    uint8_t* out, size_t cap_words, size_t* n_out, int* ok, size_t* n_corrected)
+{
+    if (!ctx || !cfg || !n_out || !ok || (n_words && !in)) return fail(ctx, T3C_ERR_ARG, "decode_profile_fixed: null");
+    DeviceGuard guard(ctx->device);
+    *n_out = 0; *ok = 0;
+    if (n_corrected) *n_corrected = 0;
+    if (cfg->profile == T3C_PROFILE_RAW) {
+        if (cap_words < n_words) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile_fixed: capacity");
+        if (n_words) std::memcpy(out, in, 9 * n_words);
+        *n_out = n_words; *ok = 1;
+        return T3C_OK;
+    }
+    Geom g;
+    if (n_raw_words) { make_geom(*cfg, n_raw_words, 1, g); if (g.n_out != n_words) return T3C_OK; }
+    else {
+        if (!geom_from_nout(*cfg, n_words, 1, g)) return T3C_OK;
+        if (use_2d(*cfg) && g.l_body) return T3C_OK; // the last partial tile's permutation depends on N_w
+        n_raw_words = (size_t)g.n_words;
+    }
+    uint64_t nw = 3 * known_prefix(*cfg, g) / 26;
+    if (nw > n_raw_words) nw = n_raw_words;
+    if (cap_words < nw) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile_fixed: capacity");
+    if (!g.n_cw || !nw) { *ok = 1; return T3C_OK; }
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * nw + 16, &d_out));
+    H2D(d_in, in, 9 * n_words);
+    TRY(t3c_decode_profile_fixed_dev(ctx, cfg, n_raw_words, d_in, n_words, d_out, (size_t)nw, ctx->d_mail->status, ctx->stream));
+    D2H(out, d_out, 9 * nw);
+    MAIL_DOWN();
+    if (!ctx->h_mail->status[0]) return T3C_OK;
+    *n_out = (size_t)nw; *ok = 1;
+    if (n_corrected) *n_corrected = ctx->h_mail->status[1];
+    return T3C_OK;
+}
+
+t3c_status t3c_encode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, int arith, const uint8_t* rgb, size_t n_px, size_t n_frames,
+                                  uint8_t* out, size_t stride_words, size_t* words_per_frame)
+{
+    if (!ctx || !cfg || !rgb || !out || !words_per_frame) return fail(ctx, T3C_ERR_ARG, "encode_frames: null");
+    DeviceGuard guard(ctx->device);
+    const size_t no = profile_words(*cfg, (n_px + 1) / 2);
+    *words_per_frame = no;
+    if (stride_words < no) return fail(ctx, T3C_ERR_CAPACITY, "encode_frames: stride");
+    if (!n_frames) return T3C_OK;
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, 3 * n_px * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * stride_words * n_frames, &d_out));
+    H2D(d_in, rgb, 3 * n_px * n_frames);
+    TRY(t3c_encode_frames_rgb8_dev(ctx, cfg, arith, d_in, n_px, n_frames, d_out, stride_words, ctx->stream));
+    D2H(out, d_out, 9 * stride_words * (n_frames - 1) + 9 * no);
+    SYNC();
+    return T3C_OK;
+}
+
+t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uint8_t* in, size_t words_per_frame, size_t stride_words,
+                                  size_t n_frames, size_t n_px, uint8_t* rgb, uint8_t* ok, size_t* px_recovered, size_t* n_corrected)
+{
+    if (!ctx || !cfg || !in || !rgb || !ok) return fail(ctx, T3C_ERR_ARG, "decode_frames: null");
+    if (n_frames > 32) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: at most 32 frames per host-buffer call");
+    DeviceGuard guard(ctx->device);
+    if (n_corrected) *n_corrected = 0;
+    if (px_recovered) *px_recovered = 0;
+    if (!n_frames) return T3C_OK;
+    const size_t n_words = (n_px + 1) / 2;
+    Geom g;
+    make_geom(*cfg, n_words, 1, g);
+    uint64_t nw = 3 * known_prefix(*cfg, g) / 26;
+    if (nw > n_words) nw = n_words;
+    const size_t px_out = 2 * (size_t)nw < n_px ? 2 * (size_t)nw : n_px;
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, 9 * stride_words * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 3 * n_px * n_frames, &d_out));
+    H2D(d_in, in, 9 * stride_words * (n_frames - 1) + 9 * words_per_frame);
+    TRY(t3c_decode_frames_rgb8_dev(ctx, cfg, d_in, words_per_frame, stride_words, n_frames, n_px, d_out, ctx->d_mail->status, ctx->stream));
+    for (size_t f = 0; f < n_frames; ++f) if (px_out) D2H(rgb + 3 * n_px * f, d_out + 3 * n_px * f, 3 * px_out);
+    MAIL_DOWN();
+    for (size_t f = 0; f < n_frames; ++f) {
+        ok[f] = ctx->h_mail->status[2 * f] ? 1 : 0;
+        if (n_corrected) *n_corrected += ctx->h_mail->status[2 * f + 1];
+    }
+    if (px_recovered) *px_recovered = px_out;
+    return T3C_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,241 @@
+// dev.cuh -- device-side building blocks shared by the kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "t3c_internal.h"
+
+namespace t3c {
+
+// ---------------------------------------------------------------------------------------------
+// GF(3)^24 arithmetic on bit planes.  A vector of up to 24 trits lives in two 32-bit registers:
+//   nz  : bit set where the trit is 1 or 2        two : bit set where the trit is 2
+// With this encoding (0->00, 1->10, 2->11) trit-wise addition mod 3 is exactly three LOP3s
+// (found by exhaustive search over 2-level LOP3 networks; checked in tests/test_host_logic.py).
+// ---------------------------------------------------------------------------------------------
+template <int IMM>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(IMM));
+    return r;
+}
+struct Planes { uint32_t nz, two; };
+__device__ __forceinline__ void gf3_add(Planes& a, uint32_t bnz, uint32_t btwo)
+{
+    const uint32_t t = lop3<0x92>(a.nz, a.two, btwo);
+    const uint32_t s0 = lop3<0xE6>(t, a.nz, bnz);
+    const uint32_t s1 = lop3<0x24>(t, a.two, bnz);
+    a.nz = s0;
+    a.two = s1;
+}
+__device__ __forceinline__ void gf3_add(Planes& a, uint64_t e) { gf3_add(a, (uint32_t)e, (uint32_t)(e >> 32)); }
+// four symbols (bytes) from plane bits b0,b1,b2 of each byte: b0 + 3 b1 + 9 b2, trit = nz + two
+__device__ __forceinline__ uint32_t trits_to_sym4(uint32_t y)
+{
+    return y + ((y >> 1) & 0x01010101u) + 5u * ((y >> 2) & 0x01010101u);
+}
+__device__ __forceinline__ uint32_t planes_to_sym4_lo(const Planes& p) // parity symbols 0..3
+{
+    return trits_to_sym4(p.nz & 0x07070707u) + trits_to_sym4(p.two & 0x07070707u);
+}
+__device__ __forceinline__ uint32_t planes_to_sym4_hi(const Planes& p) // parity symbols 4..7
+{
+    return trits_to_sym4((p.nz >> 4) & 0x07070707u) + trits_to_sym4((p.two >> 4) & 0x07070707u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Index maps of the wire format
+// ---------------------------------------------------------------------------------------------
+// scrambler state for pre-beacon body index p (A.4)
+__device__ __forceinline__ uint32_t scr_state(const Geom& g, uint64_t p)
+{
+    return p < 2 ? g.st[p] : g.st[2 + (uint32_t)((p - 2) % 6)];
+}
+// pre-beacon body index p -> index in the beacon-expanded body (A.5)
+__device__ __forceinline__ uint64_t beacon_expand(const Geom& g, uint64_t p)
+{
+    if (g.period == 0 || g.slot < 0) return p;
+    const uint64_t blk = p / g.beacon_per;
+    const uint32_t rem = (uint32_t)(p - blk * g.beacon_per);
+    if (rem < 8) return 9 * (blk * g.period) + (rem < (uint32_t)g.slot ? rem : rem + 1);
+    return 9 * (blk * g.period + 1 + (rem - 8) / 9) + (rem - 8) % 9;
+}
+// 2D boustrophedon: position i of the permuted stream reads position perm2d(i) of the source;
+// the map is an involution, so the same function de-interleaves (A.2, OLD:750-813).
+__device__ __forceinline__ uint64_t perm2d(uint64_t i, uint64_t n, uint64_t area, uint32_t w)
+{
+    if (area == 0) return i;
+    const uint64_t base = (i / area) * area;
+    const uint64_t take = (n - base) < area ? (n - base) : area;
+    const uint64_t off = i - base, r = off / w;
+    if ((r & 1) == 0) return i;
+    const uint64_t rs = r * w;
+    const uint64_t cnt = (take - rs) < w ? (take - rs) : w;
+    return base + rs + (cnt - 1 - (off - rs));
+}
+// symbol j of the regrouped stream (A.1): trits 3j..3j+2 of the 26-trits-per-word stream of `raw`
+__device__ __forceinline__ uint32_t raw_trit(const uint8_t* __restrict__ raw, uint64_t n_words, uint64_t ti)
+{
+    const uint64_t w = ti / 26;
+    if (w >= n_words) return 0;
+    const uint32_t o = (uint32_t)(ti - w * 26);
+    const uint32_t s = raw[9 * w + o / 3];
+    const uint32_t c = o % 3;
+    return c == 0 ? s % 3 : (c == 1 ? (s / 3) % 3 : (s / 9) % 3); // unpack3, OLD:28-31
+}
+__device__ __forceinline__ uint32_t raw_symbol(const uint8_t* __restrict__ raw, uint64_t n_words, uint64_t j)
+{
+    return raw_trit(raw, n_words, 3 * j) + 3 * raw_trit(raw, n_words, 3 * j + 1) + 9 * raw_trit(raw, n_words, 3 * j + 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GF(27) through shared-memory look-ups (general / slow paths)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_gf(GfTables& dst, const GfTables* __restrict__ src)
+{
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+    for (uint32_t i = threadIdx.x; i < sizeof(GfTables) / 4; i += blockDim.x) d[i] = s[i];
+}
+__device__ __forceinline__ uint8_t gmul(const GfTables& g, uint32_t a, uint32_t b) { return g.mul[a * 27 + b]; }
+__device__ __forceinline__ uint8_t gadd(const GfTables& g, uint32_t a, uint32_t b) { return g.add[a * 27 + b]; }
+__device__ __forceinline__ uint8_t gsub(const GfTables& g, uint32_t a, uint32_t b) { return g.add[a * 27 + g.neg[b]]; }
+
+// One thread decodes one RS(26,k) block: syndromes, Berlekamp-Massey, Chien, Forney, exactly as
+// RSCodec::decode_block (OLD:546-662) with the vectors restated as zero-padded fixed arrays (their
+// logical sizes never exceed r+1 <= 9).  fixed selects the Forney sign (bug B2 / Appendix B).
+// c[] is corrected in place in ascending position order, including the partial corrections the
+// reference leaves behind when it bails out on a zero derivative.
+static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t* c, int k, bool fixed)
+{
+    const int r = 26 - k, t = r >> 1;
+    uint8_t S[8];
+    bool all0 = true;
+    for (int j = 0; j < r; ++j) {
+        uint32_t acc = 0, e = 0;
+        for (int i = 0; i < 26; ++i) {
+            acc = gadd(g, acc, gmul(g, c[i], g.exp[e]));
+            e += j + 1;
+            if (e >= 26) e -= 26;
+        }
+        S[j] = (uint8_t)acc;
+        all0 = all0 && acc == 0;
+    }
+    if (all0) return true;
+    uint8_t sg[10], B[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) sg[i] = B[i] = 0;
+    sg[0] = B[0] = 1;
+    int L = 0, m = 1;
+    for (int n = 0; n < r; ++n) {
+        uint32_t delta = S[n];
+        for (int i = 1; i <= L; ++i) delta = gadd(g, delta, gmul(g, sg[i], S[n - i]));
+        if (delta) {
+            uint8_t T[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) T[i] = sg[i];
+            for (int i = m; i < 10; ++i) sg[i] = gsub(g, sg[i], gmul(g, delta, B[i - m]));
+            if (2 * L <= n) {
+                const uint32_t invd = g.inv[delta];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) B[i] = gmul(g, T[i], invd);
+                L = n + 1 - L;
+                m = 1;
+            } else ++m;
+        } else ++m;
+    }
+    uint8_t Om[8];
+    for (int i = 0; i < r; ++i) {
+        uint32_t acc = 0;
+        for (int a = 0; a <= i; ++a) acc = gadd(g, acc, gmul(g, S[a], sg[i - a])); // i-a <= 7 < 10
+        Om[i] = (uint8_t)acc;
+    }
+    uint32_t roots = 0;
+    int nroots = 0;
+    for (int i = 0; i < 26; ++i) {
+        const uint32_t x = g.exp[(26 - i) % 26];
+        uint32_t acc = 0;
+        for (int d = 9; d >= 0; --d) acc = gadd(g, gmul(g, acc, x), sg[d]);
+        if (acc == 0) { roots |= 1u << i; ++nroots; }
+    }
+    if (nroots > t) return false;
+    uint8_t sp[9];
+    for (int i = 1; i < 10; ++i) {
+        const int im = i % 3;
+        sp[i - 1] = im == 0 ? 0 : (im == 1 ? sg[i] : g.neg[sg[i]]); // 2a = -a in characteristic 3
+    }
+    for (int pos = 0; pos < 26; ++pos) {
+        if (!((roots >> pos) & 1)) continue;
+        const uint32_t x = g.exp[(26 - pos) % 26];
+        uint32_t num = 0, den = 0;
+        for (int d = r - 1; d >= 0; --d) num = gadd(g, gmul(g, num, x), Om[d]);
+        for (int d = 8; d >= 0; --d) den = gadd(g, gmul(g, den, x), sp[d]);
+        if (den == 0) return false;
+        const uint32_t mag = gmul(g, g.neg[num], g.inv[den]);
+        c[pos] = fixed ? gsub(g, c[pos], mag) : gadd(g, c[pos], mag);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-pixel arithmetic
+// ---------------------------------------------------------------------------------------------
+// round-half-away for x in [0, 2^21): floor(x + 0.5).  FADD.RM against 2^22+0.5 leaves
+// 2*floor(2x+1)/2 in the mantissa, one rounding only, so there is no double-rounding hazard.
+__device__ __forceinline__ int round_pos(float x)
+{
+    return (__float_as_int(__fadd_rd(x, 4194304.5f)) >> 1) & 0xFFFFF;
+}
+// rgb_to_ycbcr (IMG:47-56): float32, left-to-right, no FMA contraction, round half away, clamp
+__device__ __forceinline__ void rgb_to_ycbcr8(uint32_t R, uint32_t G, uint32_t B, int& Y, int& Cb, int& Cr)
+{
+    const float r = (float)R, g = (float)G, b = (float)B;
+    const float y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+    const float cb = __fadd_rn(__fadd_rn(__fsub_rn(__fmul_rn(-0.168736f, r), __fmul_rn(0.331264f, g)), __fmul_rn(0.5f, b)), 128.0f);
+    const float cr = __fadd_rn(__fsub_rn(__fsub_rn(__fmul_rn(0.5f, r), __fmul_rn(0.418688f, g)), __fmul_rn(0.081312f, b)), 128.0f);
+    // all three are >= 0 for 8-bit inputs (min 128-127.5), so round-half-away == floor(x+0.5)
+    Y = min(round_pos(y), 255);
+    Cb = min(round_pos(fmaxf(cb, 0.0f)), 255);
+    Cr = min(round_pos(fmaxf(cr, 0.0f)), 255);
+}
+// quantize_ycbcr (IMG:69-78) in exact integer form:
+//   Yq = round(Y*242/255): no ties exist (484Y = 510m+255 has no solution), so (484Y+255)/510
+//   Cq = round-half-away((C-128)*5/16) = ((5C + 7 + (C>=128)) >> 4) - 40
+__device__ __forceinline__ int quant_y(int Y) { return (Y * 484 + 255) / 510; }
+__device__ __forceinline__ int quant_c_off(int C) { return (5 * C + 7 + (C >> 7)) >> 4; } // Cq + 40, 0..80
+// dequantize_ycbcr (IMG:79-84) in exact integer form.
+//   Y = clamp(round(Yq*(255.0/242.0))): the only exact tie below the clamp is Yq=121 (127.5), where
+//   the reference's double product is 127.49999999999999 and rounds DOWN; "+241" reproduces that and
+//   is otherwise identical to floor(x+0.5).  C = clamp(round(128 + Cq*3.2)) has no ties.
+__device__ __forceinline__ int dequant_y(int Yq) { return min((Yq * 510 + 241) / 484, 255); }
+__device__ __forceinline__ int dequant_c(int Cq)
+{
+    const int v = 2570 + 64 * Cq; // (128 + 3.2 Cq + 0.5) * 20
+    return v <= 0 ? 0 : min(v / 20, 255);
+}
+// ycbcr_to_rgb (IMG:57-66)
+__device__ __forceinline__ int round_clamp255(float x)
+{
+    // std::round (half away from zero) then clamp to [0,255]; negatives all clamp to 0
+    return x <= 0.0f ? 0 : min(round_pos(fminf(x, 300.0f)), 255);
+}
+__device__ __forceinline__ void ycbcr8_to_rgb(int Y, int Cb, int Cr, int& R, int& G, int& B)
+{
+    const float y = (float)Y, cb = __fsub_rn((float)Cb, 128.0f), cr = __fsub_rn((float)Cr, 128.0f);
+    const float r = __fadd_rn(y, __fmul_rn(1.402f, cr));
+    const float g = __fsub_rn(__fsub_rn(y, __fmul_rn(0.344136f, cb)), __fmul_rn(0.714136f, cr));
+    const float b = __fadd_rn(y, __fmul_rn(1.772f, cb));
+    R = round_clamp255(r);
+    G = round_clamp255(g);
+    B = round_clamp255(b);
+}
+// 13 trits of one pixel as an integer < 3^13: A = Yq%243 + 243*((Cbq+40)%81) + 19683*((Crq+40)%81),
+// the digits i2tr keeps (OLD:675-682,697-702; out-of-range values wrap through the uint32 cast)
+__device__ __forceinline__ uint32_t pixel_value(uint32_t yq, int cbq, int crq)
+{
+    return yq % 243u + 243u * ((uint32_t)(cbq + 40) % 81u) + 19683u * ((uint32_t)(crq + 40) % 81u);
+}
+
+} // namespace t3c

@@ -1,0 +1,584 @@
+// k_general.cu -- stage-level kernels and the general (any-config) profile codec.
+//
+// These kernels are correct for every configuration the reference accepts (mixed-k UEP, 2D
+// interleave with any tile, beacons, odd sizes).  The tiled fused kernels in k_fast.cu cover the
+// headline family (uniform k, 1D, no beacon) at memory-system speed.
+#include "dev.cuh"
+#include "launch.h"
+
+namespace t3c {
+namespace {
+
+constexpr int TPB = 128;
+inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+// ------------------------------------------------------------------------------------------
+// K1: RGB8 <-> quant (IMG:47-84,156-192) and 2 px <-> Word27 (OLD:693-747)
+// ------------------------------------------------------------------------------------------
+__global__ void k_rgb_to_quant(const uint8_t* __restrict__ rgb, size_t n_px, uint16_t* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    int Y, Cb, Cr;
+    rgb_to_ycbcr8(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], Y, Cb, Cr);
+    out[3 * i] = (uint16_t)quant_y(Y);
+    out[3 * i + 1] = (uint16_t)(int16_t)(quant_c_off(Cb) - 40);
+    out[3 * i + 2] = (uint16_t)(int16_t)(quant_c_off(Cr) - 40);
+}
+__global__ void k_quant_to_rgb(const uint16_t* __restrict__ px, size_t n_px, uint8_t* __restrict__ rgb)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const int Yq = px[3 * i], Cbq = (int16_t)px[3 * i + 1], Crq = (int16_t)px[3 * i + 2];
+    int R, G, B;
+    ycbcr8_to_rgb(dequant_y(Yq), dequant_c(Cbq), dequant_c(Crq), R, G, B);
+    rgb[3 * i] = (uint8_t)R;
+    rgb[3 * i + 1] = (uint8_t)G;
+    rgb[3 * i + 2] = (uint8_t)B;
+}
+
+// word = base-27 digits of A_a + 3^13 A_b (26 trits, T[26]=0), split so that everything stays 32-bit:
+//   s0..s3 = digits of A_a;  s4 = trit12(A_a) + 3*(A_b % 9);  s5..s7 = digits of A_b/9;  s8 = A_b / 177147
+__device__ __forceinline__ void word_from_values(uint32_t Aa, uint32_t Ab, uint32_t& w0, uint32_t& w1, uint32_t& w2)
+{
+    const uint32_t q1 = Aa / 27, q2 = Aa / 729, q3 = Aa / 19683, q4 = Aa / 531441;
+    w0 = (Aa - 27 * q1) | ((q1 - 27 * q2) << 8) | ((q2 - 27 * q3) << 16) | ((q3 - 27 * q4) << 24);
+    const uint32_t lo = Ab % 9, h = Ab / 9;
+    const uint32_t h1 = h / 27, h2 = h / 729, h3 = h / 19683;
+    w1 = (q4 + 3 * lo) | ((h - 27 * h1) << 8) | ((h1 - 27 * h2) << 16) | ((h2 - 27 * h3) << 24);
+    w2 = h3;
+}
+// inverse on arbitrary bytes: every symbol contributes its low three trits (unpack3, OLD:28-31)
+__device__ __forceinline__ void values_from_word(const uint8_t* s, uint32_t& Ya, uint32_t& Cba, uint32_t& Cra, uint32_t& Yb, uint32_t& Cbb, uint32_t& Crb)
+{
+    uint32_t v[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v[i] = s[i] % 27u;
+    Ya = v[0] + 27 * (v[1] % 9);
+    Cba = v[1] / 9 + 3 * v[2];
+    Cra = v[3] + 27 * (v[4] % 3);
+    Yb = v[4] / 3 + 9 * v[5];
+    Cbb = v[6] + 27 * (v[7] % 3);
+    Crb = v[7] / 3 + 9 * (v[8] % 9);
+}
+
+constexpr int PACK_PX_PER_THREAD = 8, PACK_TPB = 256, PACK_PX_PER_BLOCK = PACK_PX_PER_THREAD * PACK_TPB;
+// Full tiles: 2048 pixels (12288 B) -> 1024 words (9216 B) staged through shared memory so that both
+// the global loads and stores are 128-bit and fully coalesced.
+__global__ void __launch_bounds__(PACK_TPB) k_pack_pixels(const uint16_t* __restrict__ px, size_t n_px, uint8_t* __restrict__ words)
+{
+    __shared__ __align__(16) uint32_t sin[PACK_PX_PER_BLOCK * 6 / 4];
+    __shared__ __align__(16) uint32_t sout[PACK_PX_PER_BLOCK / 2 * 9 / 4];
+    const size_t p0 = (size_t)blockIdx.x * PACK_PX_PER_BLOCK;
+    const int t = threadIdx.x;
+    if (p0 + PACK_PX_PER_BLOCK <= n_px) {
+        const uint4* src = reinterpret_cast<const uint4*>(px + 3 * p0);
+        uint4* s4 = reinterpret_cast<uint4*>(sin);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s4[t + PACK_TPB * j] = __ldg(src + t + PACK_TPB * j);
+        __syncthreads();
+        const uint16_t* me = reinterpret_cast<const uint16_t*>(sin) + 24 * t;
+        uint4 a = reinterpret_cast<const uint4*>(me)[0], b = reinterpret_cast<const uint4*>(me)[1], c = reinterpret_cast<const uint4*>(me)[2];
+        const uint32_t h[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        uint32_t A[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // pixel i = halfwords 3i, 3i+1, 3i+2
+            auto hw = [&](int k) { return (uint32_t)((h[k >> 1] >> ((k & 1) * 16)) & 0xFFFF); };
+            A[i] = pixel_value(hw(3 * i), (int16_t)hw(3 * i + 1), (int16_t)hw(3 * i + 2));
+        }
+        uint32_t o[9];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t w0, w1, w2;
+            word_from_values(A[2 * w], A[2 * w + 1], w0, w1, w2);
+            // 9 bytes at byte offset 9w of the thread's 36-byte output
+            const int off = 9 * w;
+            uint64_t lo = (uint64_t)w0 | ((uint64_t)w1 << 32);
+#pragma unroll
+            for (int bq = 0; bq < 9; ++bq) {
+                const uint32_t byte = bq < 8 ? (uint32_t)((lo >> (8 * bq)) & 0xFF) : w2;
+                const int pos = off + bq;
+                if (bq == 0 && (pos & 3) == 0) o[pos >> 2] = 0;
+                if ((pos & 3) == 0) o[pos >> 2] = byte; else o[pos >> 2] |= byte << (8 * (pos & 3));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) sout[9 * t + j] = o[j];
+        __syncthreads();
+        uint4* dst = reinterpret_cast<uint4*>(words + 9 * (p0 / 2));
+        const uint4* so4 = reinterpret_cast<const uint4*>(sout);
+        for (int j = t; j < PACK_PX_PER_BLOCK / 2 * 9 / 16; j += PACK_TPB) dst[j] = so4[j];
+    } else { // ragged tail: one word per thread, scalar
+        const size_t n_words = (n_px + 1) / 2;
+        for (size_t w = p0 / 2 + t; w < n_words && w < p0 / 2 + PACK_PX_PER_BLOCK / 2; w += PACK_TPB) {
+            const size_t a = 2 * w, b = 2 * w + 1;
+            const uint32_t Aa = pixel_value(px[3 * a], (int16_t)px[3 * a + 1], (int16_t)px[3 * a + 2]);
+            const uint32_t Ab = b < n_px ? pixel_value(px[3 * b], (int16_t)px[3 * b + 1], (int16_t)px[3 * b + 2])
+                                         : pixel_value(0, 0, 0); // pairs with PixelYCbCrQuant{}, OLD:730
+            uint32_t w0, w1, w2;
+            word_from_values(Aa, Ab, w0, w1, w2);
+            uint8_t* o = words + 9 * w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { o[i] = (uint8_t)(w0 >> (8 * i)); o[4 + i] = (uint8_t)(w1 >> (8 * i)); }
+            o[8] = (uint8_t)w2;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PACK_TPB) k_unpack_pixels(const uint8_t* __restrict__ words, size_t n_words, uint16_t* __restrict__ px)
+{
+    __shared__ __align__(16) uint32_t sin[PACK_PX_PER_BLOCK / 2 * 9 / 4];
+    __shared__ __align__(16) uint32_t sout[PACK_PX_PER_BLOCK * 6 / 4];
+    constexpr int WPB = PACK_PX_PER_BLOCK / 2;
+    const size_t w0 = (size_t)blockIdx.x * WPB;
+    const int t = threadIdx.x;
+    if (w0 + WPB <= n_words) {
+        const uint4* src = reinterpret_cast<const uint4*>(words + 9 * w0);
+        uint4* s4 = reinterpret_cast<uint4*>(sin);
+        for (int j = t; j < WPB * 9 / 16; j += PACK_TPB) s4[j] = __ldg(src + j);
+        __syncthreads();
+        uint32_t in[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) in[j] = sin[9 * t + j];
+        uint16_t* me = reinterpret_cast<uint16_t*>(sout) + 24 * t;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint8_t s[9];
+#pragma unroll
+            for (int bq = 0; bq < 9; ++bq) { const int pos = 9 * w + bq; s[bq] = (uint8_t)(in[pos >> 2] >> (8 * (pos & 3))); }
+            uint32_t Ya, Cba, Cra, Yb, Cbb, Crb;
+            values_from_word(s, Ya, Cba, Cra, Yb, Cbb, Crb);
+            me[6 * w + 0] = (uint16_t)Ya; me[6 * w + 1] = (uint16_t)(int16_t)((int)Cba - 40); me[6 * w + 2] = (uint16_t)(int16_t)((int)Cra - 40);
+            me[6 * w + 3] = (uint16_t)Yb; me[6 * w + 4] = (uint16_t)(int16_t)((int)Cbb - 40); me[6 * w + 5] = (uint16_t)(int16_t)((int)Crb - 40);
+        }
+        __syncthreads();
+        uint4* dst = reinterpret_cast<uint4*>(px + 6 * w0);
+        const uint4* so4 = reinterpret_cast<const uint4*>(sout);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dst[t + PACK_TPB * j] = so4[t + PACK_TPB * j];
+    } else {
+        for (size_t w = w0 + t; w < n_words && w < w0 + WPB; w += PACK_TPB) {
+            uint8_t s[9];
+            for (int i = 0; i < 9; ++i) s[i] = words[9 * w + i];
+            uint32_t Ya, Cba, Cra, Yb, Cbb, Crb;
+            values_from_word(s, Ya, Cba, Cra, Yb, Cbb, Crb);
+            uint16_t* o = px + 6 * w;
+            o[0] = (uint16_t)Ya; o[1] = (uint16_t)(int16_t)((int)Cba - 40); o[2] = (uint16_t)(int16_t)((int)Cra - 40);
+            o[3] = (uint16_t)Yb; o[4] = (uint16_t)(int16_t)((int)Cbb - 40); o[5] = (uint16_t)(int16_t)((int)Crb - 40);
+        }
+    }
+}
+
+__global__ void k_init_status(uint32_t* st, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * n) st[i] = (i & 1) ? 0u : 1u;
+}
+__global__ void k_mod27(const uint8_t* __restrict__ in, size_t n, uint8_t* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] % 27;
+}
+
+// ------------------------------------------------------------------------------------------
+// Block-level RS (RSCodec::encode_block / decode_block), one thread per block
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_rs_encode_blocks(const RowTable* __restrict__ tab, int k, const uint8_t* __restrict__ data,
+                                                          size_t n, uint8_t* __restrict__ out)
+{
+    __shared__ uint64_t row[24 * kVals];
+    for (int i = threadIdx.x; i < k * kVals; i += TPB) row[i] = tab->e[i / kVals][i % kVals];
+    __syncthreads();
+    const size_t blk = (size_t)blockIdx.x * TPB + threadIdx.x;
+    if (blk >= n) return;
+    const int r = 26 - k;
+    Planes acc{0, 0};
+    for (int i = 0; i < k; ++i) {
+        const uint32_t raw = data[blk * k + i];
+        out[blk * 26 + i] = (uint8_t)raw;      // systematic part is copied verbatim (OLD:532)
+        gf3_add(acc, row[i * kVals + raw % 27]);
+    }
+    const uint32_t lo = planes_to_sym4_lo(acc), hi = planes_to_sym4_hi(acc);
+    for (int j = 0; j < r; ++j) out[blk * 26 + k + j] = (uint8_t)((j < 4 ? lo >> (8 * j) : hi >> (8 * (j - 4))) & 0xFF);
+}
+
+__global__ void __launch_bounds__(TPB) k_rs_decode_blocks(const GfTables* __restrict__ gf, int k, int fixed, uint8_t* __restrict__ inout,
+                                                          size_t n, uint8_t* __restrict__ out_k, uint8_t* __restrict__ ok)
+{
+    __shared__ GfTables sg;
+    load_gf(sg, gf);
+    __syncthreads();
+    const size_t blk = (size_t)blockIdx.x * TPB + threadIdx.x;
+    if (blk >= n) return;
+    uint8_t c[26];
+    for (int i = 0; i < 26; ++i) c[i] = inout[blk * 26 + i] % 27;
+    const bool good = rs_decode_thread(sg, c, k, fixed != 0);
+    for (int i = 0; i < 26; ++i) inout[blk * 26 + i] = c[i];
+    for (int i = 0; i < k; ++i) out_k[blk * k + i] = good ? c[i] : 0;
+    ok[blk] = good ? 1 : 0;
+}
+
+__global__ void k_perm2d(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, uint64_t area, uint32_t w)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm2d(i, n, area, w)];
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: super-frame header (OLD:155-380, 1142-1158) -- one warp
+// ------------------------------------------------------------------------------------------
+__device__ void header_symbols(const t3c_config& c, uint32_t frame_seq, uint32_t hash, uint8_t* p)
+{
+    // HeaderCodec::pack, OLD:208-289.  at(i,v) narrows v to uint8 before %27.
+    const uint32_t magic = 0x0A2;
+    for (int i = 0; i < 27; ++i) p[i] = 0;
+    p[0] = magic % 27; p[1] = (magic / 27) % 27; p[2] = 1; p[3] = c.profile % 27;
+    for (int g = 0; g < 3; ++g) p[4 + g] = (uint8_t)(9 * (c.uep[3 * g] % 3) + 3 * (c.uep[3 * g + 1] % 3) + (c.uep[3 * g + 2] % 3));
+    p[7] = c.tile_w % 27; p[8] = c.tile_h % 27;
+    p[9] = c.seed_a % 27; p[10] = c.seed_b % 27; p[11] = c.seed_s0 % 27;
+    const uint32_t sub = c.subword == 24 ? 1 : c.subword == 21 ? 2 : c.subword == 18 ? 3 : c.subword == 15 ? 4 : 0;
+    p[12] = (uint8_t)((sub + 9 * (c.centered ? 1 : 0)) % 27);
+    p[13] = hash % 27; p[14] = (hash / 27) % 27; p[15] = (hash / 729) % 27;
+    p[16] = c.coset % 3;
+    p[17] = frame_seq % 27; p[18] = (frame_seq / 27) % 27; p[19] = (frame_seq / 729) % 27;
+    p[23] = c.beacon_enabled ? 1 : 0; p[24] = c.beacon_slot % 27;
+    p[25] = (uint8_t)(c.beacon_period < 26 ? c.beacon_period : 26);
+}
+__device__ void header_crc(const uint8_t* p, uint8_t* r) // CRC3::rem12 over 69 trits + 12 zeros, OLD:176-205
+{
+    for (int i = 0; i < 12; ++i) r[i] = 0;
+    for (int q = 0; q < 27 + 4; ++q) {          // 23 symbols, then 4 all-zero "symbols" = the 12 flush steps
+        uint32_t s = 0;
+        if (q < 27) { if (q == 20 || q == 21 || q == 22 || q == 26) continue; s = p[q]; }
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t in = c == 0 ? s % 3 : (c == 1 ? (s / 3) % 3 : (s / 9) % 3);
+            const uint32_t fb = (in + r[11]) % 3;
+            uint8_t nx[12] = {(uint8_t)fb, r[0], r[1], (uint8_t)((r[2] + fb) % 3), (uint8_t)((r[3] + fb) % 3), r[4], r[5],
+                              (uint8_t)((r[6] + fb) % 3), r[7], r[8], r[9], r[10]};
+            for (int i = 0; i < 12; ++i) r[i] = nx[i];
+        }
+    }
+}
+// warp-cooperative: lane 0 builds the 27 symbols + CRC, lanes 0..15 each produce one parity symbol
+// of the two RS(26,18) blocks.  hdr27/coded52 point to shared or global memory.
+__device__ void header_emit_warp(const t3c_config& c, int arith, const GfTables* gf, const RsTables* rs, uint8_t* hdr27, uint8_t* coded52)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) {
+        uint8_t p[27], r[12];
+        header_symbols(c, 0, 0, p);
+        header_crc(p, r);
+        p[20] = r[0] + 3 * r[1] + 9 * r[2]; p[21] = r[3] + 3 * r[4] + 9 * r[5];
+        p[22] = r[6] + 3 * r[7] + 9 * r[8]; p[26] = r[9] + 3 * r[10] + 9 * r[11];
+        for (int i = 0; i < 27; ++i) hdr27[i] = p[i];
+        for (int i = 0; i < 18; ++i) coded52[i] = p[i];                       // A = sym[0..17]
+        for (int i = 0; i < 18; ++i) coded52[26 + i] = i < 9 ? p[18 + i] : 0; // B = sym[18..26] | 0^9
+    }
+    __syncwarp();
+    if (lane < 16) {
+        const int blk = lane >> 3, j = lane & 7;
+        uint32_t acc = 0;
+        for (int i = 0; i < 18; ++i) acc = gf->add[acc * 27 + gf->mul[coded52[26 * blk + i] * 27 + rs->par[arith][3][i][j]]];
+        coded52[26 * blk + 18 + j] = (uint8_t)acc;
+    }
+    __syncwarp();
+}
+__global__ void k_header_emit(t3c_config cfg, int arith, const GfTables* gf, const RsTables* rs, uint8_t* hdr27, uint8_t* coded52)
+{
+    header_emit_warp(cfg, arith, gf, rs, hdr27, coded52);
+}
+
+// read_and_decode_header_from_words (OLD:918-937) + HeaderCodec::check/unpack (OLD:290-379)
+__global__ void k_header_parse(const GfTables* __restrict__ gf, int fixed, const uint8_t* __restrict__ words, size_t n_words,
+                               t3c_config* out, int* ok)
+{
+    __shared__ GfTables sg;
+    __shared__ uint8_t blk[2][26];
+    __shared__ int good[2];
+    load_gf(sg, gf);
+    __syncthreads();
+    if (n_words < 6) { if (threadIdx.x == 0) *ok = 0; return; }
+    if (threadIdx.x < 2) {
+        uint8_t c[26];
+        for (int i = 0; i < 26; ++i) c[i] = words[26 * threadIdx.x + i] % 27; // A = sy[0..25], B = sy[26..51]
+        good[threadIdx.x] = rs_decode_thread(sg, c, 18, fixed != 0) ? 1 : 0;
+        for (int i = 0; i < 26; ++i) blk[threadIdx.x][i] = c[i];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (!good[0] || !good[1]) { *ok = 0; return; }
+    uint8_t p[27], r[12];
+    for (int i = 0; i < 18; ++i) p[i] = blk[0][i];
+    for (int i = 0; i < 9; ++i) p[18 + i] = blk[1][i];
+    header_crc(p, r);
+    const uint8_t want[4] = {p[20], p[21], p[22], p[26]};
+    for (int i = 0; i < 4; ++i)
+        if (want[i] != r[3 * i] + 3 * r[3 * i + 1] + 9 * r[3 * i + 2]) { *ok = 0; return; }
+    t3c_config h = *out; // fields the header does not carry (superframe_words) are kept
+    h.profile = p[3] % 5;
+    for (int g = 0; g < 3; ++g) { // LSB-first triples (bug B7)
+        uint32_t v = p[4 + g];
+        h.uep[3 * g] = v % 3; h.uep[3 * g + 1] = (v / 3) % 3; h.uep[3 * g + 2] = (v / 9) % 3;
+    }
+    h.tile_w = p[7]; h.tile_h = p[8];
+    h.seed_a = p[9]; h.seed_b = p[10]; h.seed_s0 = p[11];
+    const uint32_t sub = p[12] % 9, cen = (p[12] / 9) % 3;
+    h.subword = sub == 1 ? 24 : sub == 2 ? 21 : sub == 3 ? 18 : sub == 4 ? 15 : 27;
+    h.centered = cen != 0;
+    h.coset = p[16] % 3;
+    h.beacon_enabled = p[23] != 0; h.beacon_slot = p[24] % 9; h.beacon_period = p[25];
+    *out = h;
+    *ok = 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// General profile encoder (A.1-A.6): one CTA = TPB codewords of one band
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restrict__ raw, uint8_t* __restrict__ out, Geom g,
+                                                        const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+{
+    __shared__ uint64_t row[24 * kVals];
+    __shared__ uint8_t stage[TPB * 26];
+    const int b = blockIdx.y, k = g.k[b], r = 26 - k;
+    const uint64_t c0 = (uint64_t)blockIdx.x * TPB;
+    if (c0 >= g.ncw[b]) return;
+    const RowTable& tab = rs->row[g.arith][(24 - k) / 2];
+    for (int i = threadIdx.x; i < k * kVals; i += TPB) row[i] = tab.e[i / kVals][i % kVals];
+    __syncthreads();
+    const uint64_t c = c0 + threadIdx.x;
+    const uint32_t ncta = (uint32_t)((g.ncw[b] - c0) < TPB ? (g.ncw[b] - c0) : TPB);
+    if (threadIdx.x < ncta) {
+        Planes acc{0, 0};
+        uint8_t* my = stage + 26 * threadIdx.x;
+        for (int i = 0; i < k; ++i) {
+            const uint64_t is = 9 * ((uint64_t)k * c + i) + b;                   // band split, A.3
+            const uint64_t j = perm2d(is, g.n_s, g.tile_area, g.tile_w);        // 2D interleave, A.2
+            const uint32_t d = raw_symbol(raw, g.n_words, j);                    // regroup, A.1
+            my[i] = (uint8_t)d;
+            gf3_add(acc, row[i * kVals + d]);
+        }
+        const uint32_t lo = planes_to_sym4_lo(acc), hi = planes_to_sym4_hi(acc);
+        for (int j = 0; j < r; ++j) my[k + j] = (uint8_t)((j < 4 ? lo >> (8 * j) : hi >> (8 * (j - 4))) & 0xFF);
+    }
+    __syncthreads();
+    const uint64_t p0 = 26 * (g.cw_base[b] + c0);
+    for (uint32_t idx = threadIdx.x; idx < 26 * ncta; idx += TPB) {
+        const uint64_t p = p0 + idx;
+        out[52 + beacon_expand(g, p)] = gf->scr[scr_state(g, p)][stage[idx]];   // scramble A.4, beacon A.5
+    }
+}
+// header, beacon symbols and zero padding of one super-frame
+__global__ void k_frame_misc(uint8_t* __restrict__ out, Geom g, t3c_config cfg, const GfTables* gf, const RsTables* rs)
+{
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        __shared__ uint8_t h27[27], c52[52];
+        header_emit_warp(cfg, g.arith, gf, rs, h27, c52);
+        for (int i = threadIdx.x; i < 52; i += 32) out[i] = c52[i];
+    }
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t W = g.l_exp / 9;
+    if (g.period && g.slot >= 0)
+        for (uint64_t wd = tid * g.period; wd < W; wd += nth * g.period) out[52 + 9 * wd + g.slot] = g.bsym;
+    // zeros after the last body symbol up to the end of the last word (never on a beacon position)
+    const uint64_t q_end = g.l_body ? beacon_expand(g, g.l_body - 1) + 1 : 0;
+    for (uint64_t q = q_end + tid; 52 + q < 9 * g.n_out; q += nth) {
+        const bool is_beacon = g.period && g.slot >= 0 && q < g.l_exp && (q / 9) % g.period == 0 && (int)(q % 9) == g.slot;
+        if (!is_beacon) out[52 + q] = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// General consistent decoder (A.8): thread per codeword -> symbol stream sy' in scratch
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_decode_fixed_general(const uint8_t* __restrict__ in, uint8_t* __restrict__ sy, Geom g,
+                                                              const GfTables* __restrict__ gf, uint32_t* status)
+{
+    __shared__ GfTables sg;
+    load_gf(sg, gf);
+    __syncthreads();
+    const int b = blockIdx.y, k = g.k[b];
+    const uint64_t c = (uint64_t)blockIdx.x * TPB + threadIdx.x;
+    if (c >= g.ncw[b]) return;
+    uint8_t cw[26], orig[26];
+    const uint64_t p0 = 26 * (g.cw_base[b] + c);
+    for (int i = 0; i < 26; ++i) {
+        const uint64_t p = p0 + i;
+        cw[i] = orig[i] = sg.dsc[scr_state(g, p)][in[52 + beacon_expand(g, p)] % 27];
+    }
+    if (!rs_decode_thread(sg, cw, k, true)) { atomicExch(&status[0], 0u); return; }
+    uint32_t nfix = 0;
+    for (int i = 0; i < 26; ++i) nfix += cw[i] != orig[i];
+    if (nfix) atomicAdd(&status[1], nfix);
+    for (int i = 0; i < k; ++i) sy[9 * ((uint64_t)k * c + i) + b] = cw[i];
+}
+// symbols -> trits -> groups of 26 -> Word27 (OLD:1022-1039), optional de-interleave (involution)
+__device__ __forceinline__ uint32_t stream_trit(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t w, uint64_t ti)
+{
+    const uint64_t j = ti / 3;
+    const uint32_t s = sy[perm2d(j, n_sy, area, w)], c = (uint32_t)(ti - 3 * j);
+    return c == 0 ? s % 3 : (c == 1 ? (s / 3) % 3 : (s / 9) % 3);
+}
+__global__ void k_regroup_words(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* __restrict__ out, size_t n_words)
+{
+    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words) return;
+    for (int s = 0; s < 9; ++s) {
+        uint32_t v = 0, mul = 1;
+        for (int c = 0; c < 3; ++c, mul *= 3) {
+            const int t = 3 * s + c;
+            if (t < 26) v += mul * stream_trit(sy, n_sy, area, tw, 26 * (uint64_t)w + t);
+        }
+        out[9 * w + s] = (uint8_t)v;
+    }
+}
+__global__ void k_regroup_rgb(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* __restrict__ rgb, size_t n_px)
+{
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_px) return;
+    uint32_t t[13];
+    for (int i = 0; i < 13; ++i) t[i] = stream_trit(sy, n_sy, area, tw, 13 * (uint64_t)p + i);
+    const int Yq = t[0] + 3 * t[1] + 9 * t[2] + 27 * t[3] + 81 * t[4];
+    const int Cb = (int)(t[5] + 3 * t[6] + 9 * t[7] + 27 * t[8]) - 40, Cr = (int)(t[9] + 3 * t[10] + 9 * t[11] + 27 * t[12]) - 40;
+    int R, G, B;
+    ycbcr8_to_rgb(dequant_y(Yq), dequant_c(Cb), dequant_c(Cr), R, G, B);
+    rgb[3 * p] = (uint8_t)R; rgb[3 * p + 1] = (uint8_t)G; rgb[3 * p + 2] = (uint8_t)B;
+}
+
+// ------------------------------------------------------------------------------------------
+// Reference decoder as shipped (A.7): slot-major demap of words 6.., descramble by absolute
+// body-symbol position, band-major `use`
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB) k_decode_ref_general(const uint8_t* __restrict__ in, uint8_t* __restrict__ use, RefDecGeom g,
+                                                            const GfTables* __restrict__ gf, uint32_t* status)
+{
+    __shared__ GfTables sg;
+    load_gf(sg, gf);
+    __syncthreads();
+    const int b = blockIdx.y, k = g.k[b];
+    const uint64_t c = (uint64_t)blockIdx.x * TPB + threadIdx.x;
+    if (c >= g.ncw[b]) return;
+    uint8_t cw[26];
+    const bool skipping = g.period && b == g.slot;
+    for (int i = 0; i < 26; ++i) {
+        const uint64_t n = 26 * c + i;                                            // n-th kept word of this band
+        const uint64_t wi = skipping ? n + n / (g.period - 1) + 1 : n;            // words with wi%P==0 are skipped (OLD:957)
+        const uint64_t pos = 9 * wi + b;                                          // descrambler runs over all 9 slots (OLD:938-947)
+        const uint32_t st = pos < 2 ? g.st[pos] : g.st[2 + (uint32_t)((pos - 2) % 6)];
+        cw[i] = sg.dsc[st][in[54 + pos] % 27];
+    }
+    if (!rs_decode_thread(sg, cw, k, false)) { atomicExch(&status[0], 0u); return; }
+    for (int i = 0; i < k; ++i) use[g.use_base[b] + (uint64_t)k * c + i] = cw[i];
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+int launch_init_status(uint32_t* d_status, size_t n_frames, cudaStream_t st)
+{
+    if (!n_frames) return 0;
+    k_init_status<<<blocks_for(2 * n_frames, 256), 256, 0, st>>>(d_status, n_frames);
+    return 1;
+}
+int launch_rgb_to_quant(const uint8_t* rgb, size_t n, t3c_pixel* out, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_rgb_to_quant<<<blocks_for(n, 256), 256, 0, st>>>(rgb, n, reinterpret_cast<uint16_t*>(out));
+    return 1;
+}
+int launch_quant_to_rgb(const t3c_pixel* px, size_t n, uint8_t* rgb, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_quant_to_rgb<<<blocks_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(px), n, rgb);
+    return 1;
+}
+int launch_pack_pixels(const t3c_pixel* px, size_t n, uint8_t* words, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_pack_pixels<<<blocks_for(n, PACK_PX_PER_BLOCK), PACK_TPB, 0, st>>>(reinterpret_cast<const uint16_t*>(px), n, words);
+    return 1;
+}
+int launch_unpack_pixels(const uint8_t* words, size_t n, t3c_pixel* px, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_unpack_pixels<<<blocks_for(n, PACK_PX_PER_BLOCK / 2), PACK_TPB, 0, st>>>(words, n, reinterpret_cast<uint16_t*>(px));
+    return 1;
+}
+int launch_mod27(const uint8_t* in, size_t n, uint8_t* out, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_mod27<<<blocks_for(n, 256), 256, 0, st>>>(in, n, out);
+    return 1;
+}
+int launch_rs_encode_blocks(const DevTables& T, int k, int arith, const uint8_t* data, size_t n, uint8_t* out, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_rs_encode_blocks<<<blocks_for(n, TPB), TPB, 0, st>>>(&T.rs->row[arith ? 1 : 0][kidx_of(k)], k, data, n, out);
+    return 1;
+}
+int launch_rs_decode_blocks(const DevTables& T, int k, int arith, uint8_t* inout, size_t n, uint8_t* out_k, uint8_t* ok, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_rs_decode_blocks<<<blocks_for(n, TPB), TPB, 0, st>>>(T.gf, k, arith, inout, n, out_k, ok);
+    return 1;
+}
+int launch_perm2d(const uint8_t* in, uint8_t* out, size_t n, uint32_t w, uint32_t h, cudaStream_t st)
+{
+    if (!n) return 0;
+    k_perm2d<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n, (uint64_t)w * h, w);
+    return 1;
+}
+int launch_header_emit(const DevTables& T, const t3c_config& cfg, int arith, uint8_t* hdr27, uint8_t* coded52, cudaStream_t st)
+{
+    k_header_emit<<<1, 32, 0, st>>>(cfg, arith ? 1 : 0, T.gf, T.rs, hdr27, coded52);
+    return 1;
+}
+int launch_header_parse(const DevTables& T, int arith, const uint8_t* words, size_t n_words, t3c_config* d_cfg, int* d_ok, cudaStream_t st)
+{
+    k_header_parse<<<1, 64, 0, st>>>(T.gf, arith, words, n_words, d_cfg, d_ok);
+    return 1;
+}
+int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw, uint8_t* out, cudaStream_t st)
+{
+    int n = 0;
+    uint64_t mx = 0;
+    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
+    if (mx) { k_encode_general<<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs); ++n; }
+    const uint64_t nb = g.period ? g.l_exp / 9 / g.period + 1 : 1;
+    unsigned blocks = (unsigned)((nb + 255) / 256);
+    if (blocks > 1024) blocks = 1024;
+    k_frame_misc<<<blocks, 256, 0, st>>>(out, g, cfg, T.gf, T.rs);
+    return n + 1;
+}
+int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint32_t* status, cudaStream_t st)
+{
+    uint64_t mx = 0;
+    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
+    if (!mx) return 0;
+    k_decode_fixed_general<<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status);
+    return 1;
+}
+int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* out, size_t n_words, cudaStream_t st)
+{
+    if (!n_words) return 0;
+    k_regroup_words<<<blocks_for(n_words, 256), 256, 0, st>>>(sy, n_sy, area, tw, out, n_words);
+    return 1;
+}
+int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* rgb, size_t n_px, cudaStream_t st)
+{
+    if (!n_px) return 0;
+    k_regroup_rgb<<<blocks_for(n_px, 256), 256, 0, st>>>(sy, n_sy, area, tw, rgb, n_px);
+    return 1;
+}
+int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uint8_t* in, uint8_t* use, uint32_t* status, cudaStream_t st)
+{
+    uint64_t mx = 0;
+    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
+    if (!mx) return 0;
+    k_decode_ref_general<<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(in, use, g, T.gf, status);
+    return 1;
+}
+
+} // namespace t3c

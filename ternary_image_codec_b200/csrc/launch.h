@@ -1,0 +1,50 @@
+// launch.h -- host-callable launchers implemented in the .cu files.  All take device pointers and
+// enqueue on `st`; none synchronises.  Each returns the number of kernels it launched.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "t3c_internal.h"
+
+namespace t3c {
+
+struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; };
+
+// geometry of the reference decoder as shipped (A.7): slot-major demap of words 6.. of the input
+struct RefDecGeom {
+    uint64_t n_body_words;
+    uint64_t ncw[9], use_base[9], n_use;
+    uint64_t tile_area;
+    uint32_t tile_w;
+    uint32_t period;   // 0 = no skipping
+    int32_t  slot;
+    int32_t  k[9];
+    uint8_t  st[8];
+};
+
+int launch_init_status(uint32_t* d_status, size_t n_frames, cudaStream_t st); // {ok=1, n_corrected=0} per frame
+// K1
+int launch_rgb_to_quant(const uint8_t* rgb, size_t n_px, t3c_pixel* out, cudaStream_t st);
+int launch_quant_to_rgb(const t3c_pixel* px, size_t n_px, uint8_t* rgb, cudaStream_t st);
+int launch_pack_pixels(const t3c_pixel* px, size_t n_px, uint8_t* words9, cudaStream_t st);
+int launch_unpack_pixels(const uint8_t* words9, size_t n_words, t3c_pixel* px, cudaStream_t st);
+int launch_mod27(const uint8_t* in, size_t n, uint8_t* out, cudaStream_t st);
+// block codecs
+int launch_rs_encode_blocks(const DevTables& T, int k, int arith, const uint8_t* data, size_t n, uint8_t* out26, cudaStream_t st);
+int launch_rs_decode_blocks(const DevTables& T, int k, int arith, uint8_t* inout26, size_t n, uint8_t* out_k, uint8_t* ok, cudaStream_t st);
+int launch_perm2d(const uint8_t* in, uint8_t* out, size_t n, uint32_t w, uint32_t h, cudaStream_t st);
+int launch_header_emit(const DevTables& T, const t3c_config& cfg, int arith, uint8_t* d_hdr27, uint8_t* d_coded52, cudaStream_t st);
+int launch_header_parse(const DevTables& T, int arith, const uint8_t* d_words9, size_t n_words, t3c_config* d_cfg, int* d_ok, cudaStream_t st);
+// general profile codec (any config)
+int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st);
+int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* scratch_sy, uint32_t* d_status, cudaStream_t st);
+int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* out9, size_t n_words, cudaStream_t st);
+int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* rgb, size_t n_px, cudaStream_t st);
+int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uint8_t* in9, uint8_t* use, uint32_t* d_status, cudaStream_t st);
+// fused fast path (uniform k, 1D, no beacon): frames batched
+bool fast_path_ok(const t3c_config& cfg);
+int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* rgb, size_t n_px, size_t n_frames,
+                           uint8_t* out9, size_t stride_words, cudaStream_t st);
+int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in9, size_t stride_words,
+                           size_t n_frames, size_t n_px, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st);
+
+} // namespace t3c

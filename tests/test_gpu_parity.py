@@ -1,0 +1,332 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libt3c.so), against the CPU oracle on the
+same seeded inputs and against the golden vectors generated from the reference.  Bit-exact everywhere:
+every quantity on this path is an integer/byte (the float32 bridge must match to the last bit too).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import t3oracle as T
+
+pytestmark = pytest.mark.gpu
+
+KS = (24, 22, 20, 18)
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+
+
+@pytest.fixture(scope="module")
+def t3():
+    import ternary_image_codec_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def codec(t3):
+    c = t3.Codec(0)
+    yield c
+    c.close()
+
+
+def rng(s):
+    return np.random.default_rng(s)
+
+
+def both(kw):
+    """same config for the oracle struct and the product struct"""
+    import ternary_image_codec_b200 as m
+    return T.make_cfg(**kw), m.make_config(**kw)
+
+
+CONFIGS = [
+    dict(),
+    dict(profile=T.P2, uep=T.UEP_LUMA),
+    dict(profile=T.P3, uep=2),
+    dict(profile=T.P1, uep=0), dict(profile=T.P4, uep=3),
+    dict(profile=T.P5, tile=(7, 5), beacon=(4, 2, True), uep=T.UEP_LUMA, seed=(2, 1, 1)),
+    dict(profile=T.P5, tile=(26, 3), beacon=(26, 8, True), uep=3, seed=(1, 2, 0)),
+    dict(profile=T.P5, tile=(26, 26), beacon=(26, 2, True), uep=T.UEP_LUMA, seed=(2, 1, 1), coset=1),
+    dict(profile=T.P2, tile=(64, 64), beacon=(83, 2, True)),
+    dict(profile=T.P5, tile=(300, 7), uep=(0, 1, 2, 3, 0, 1, 2, 3, 0), beacon=(1, 0, True)),
+    dict(profile=T.P3, uep=2, beacon=(5, 11, True)),
+    dict(profile=T.P3, uep=2, seed=(2 ** 32 - 1, 2 ** 31 + 5, 7)),
+    dict(profile=T.P3, uep=2, seed=(3, 5, 2)),      # a%3==0: constant scrambler after one step
+    dict(profile=T.RAW_MODE),
+]
+
+
+# ------------------------------------------------------------------ K1
+def test_bridge_exhaustive_2_24(codec, oracle):
+    idx = np.arange(1 << 24, dtype=np.uint32)
+    rgb = np.stack([(idx >> 16) & 255, (idx >> 8) & 255, idx & 255], axis=1).astype(np.uint8)
+    got = codec.rgb_to_quant_stream(rgb)
+    want = oracle.rgb_to_quant(rgb)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+def test_bridge_back_all_quant_values_and_wild(codec, oracle):
+    yq, cb, cr = np.meshgrid(np.arange(243), np.arange(-40, 41), np.arange(-40, 41), indexing="ij")
+    px = np.zeros(yq.size, T.PIXEL_DTYPE)
+    px["Yq"], px["Cbq"], px["Crq"] = yq.ravel(), cb.ravel(), cr.ravel()
+    assert np.array_equal(codec.quant_stream_to_rgb(px), oracle.quant_to_rgb(px))
+    r = rng(1)
+    wild = np.zeros(200000, T.PIXEL_DTYPE)  # out-of-range inputs clamp exactly like the reference
+    wild["Yq"], wild["Cbq"], wild["Crq"] = r.integers(0, 65536, wild.size), r.integers(-32768, 32768, wild.size), r.integers(-32768, 32768, wild.size)
+    assert np.array_equal(codec.quant_stream_to_rgb(wild), oracle.quant_to_rgb(wild))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 2047, 2048, 2049, 4096, 4097, 100001])
+def test_pack_unpack_pixels(codec, oracle, n):
+    px = T.synth_quant(4, n)
+    w = codec.encode_raw_pixels_to_words(px)
+    assert np.array_equal(w, oracle.pack_pixels(px))
+    assert np.array_equal(codec.decode_raw_words_to_pixels(w).view(np.uint8), oracle.unpack_pixels(w).view(np.uint8))
+    r = rng(n)
+    wild = np.zeros(n, T.PIXEL_DTYPE)
+    wild["Yq"], wild["Cbq"], wild["Crq"] = r.integers(0, 65536, n), r.integers(-32768, 32768, n), r.integers(-32768, 32768, n)
+    assert np.array_equal(codec.encode_raw_pixels_to_words(wild), oracle.pack_pixels(wild))
+    words = r.integers(0, 256, size=((n + 1) // 2, 9), dtype=np.uint8)  # bytes >= 27 read as their low three trits
+    assert np.array_equal(codec.decode_raw_words_to_pixels(words).view(np.uint8), oracle.unpack_pixels(words).view(np.uint8))
+    assert np.array_equal(codec.words_to_bytes(words), (words % 27).reshape(-1))
+
+
+def test_golden_bridge_and_packing(codec):
+    q = codec.rgb_to_quant_stream(G["rgb"])
+    assert np.array_equal(q.view(np.uint8).reshape(-1, 6), G["quant"])
+    assert np.array_equal(codec.quant_stream_to_rgb(q), G["rgb_back"])
+    assert np.array_equal(codec.encode_raw_pixels_to_words(q), G["raw_words"])
+    assert np.array_equal(codec.decode_raw_words_to_pixels(G["raw_words"]).view(np.uint8).reshape(-1, 6), G["unpacked"])
+
+
+# ------------------------------------------------------------------ RS block codec
+@pytest.mark.parametrize("k", KS)
+def test_rs_encode_blocks(codec, oracle, t3, k):
+    data = rng(k).integers(0, 27, size=(50000, k), dtype=np.uint8)
+    data[0] = (5 * np.arange(k) + 7) % 27
+    data[1] = 0
+    for arith in (t3.REF_EXACT, t3.FIXED):
+        assert np.array_equal(codec.rs_encode_blocks(k, data, arith), oracle.rs_encode_blocks(k, data, arith))
+    assert np.array_equal(codec.rs_encode_blocks(k, G[f"rs{k}_data"], 0), G[f"rs{k}_enc_ref"])
+    assert np.array_equal(codec.rs_encode_blocks(k, G[f"rs{k}_data"], 1), G[f"rs{k}_enc_fix"])
+    assert codec.rs_encode_blocks(k, np.zeros((0, k), np.uint8)).shape == (0, 26)
+
+
+def decode_inputs(oracle, k, n, seed):
+    r = rng(seed)
+    t = (26 - k) // 2
+    add = T.gf_add_table()
+    data = r.integers(0, 27, size=(n, k), dtype=np.uint8)
+    blocks = [r.integers(0, 27, size=(n, 26), dtype=np.uint8)]
+    for fixed in (1, 0):
+        cw = oracle.rs_encode_blocks(k, data, fixed)
+        for e in range(0, t + 3):
+            c = cw.copy()
+            pos = np.argsort(r.random((n, 26)), axis=1)[:, :e]
+            mag = r.integers(1, 27, size=(n, e))
+            rows = np.arange(n)[:, None]
+            c[rows, pos] = add[c[rows, pos], mag]
+            blocks.append(c)
+    return np.concatenate(blocks)
+
+
+@pytest.mark.parametrize("k", KS)
+def test_rs_decode_blocks(codec, oracle, t3, k):
+    blocks = decode_inputs(oracle, k, 8000, 100 + k)
+    for arith in (t3.REF_EXACT, t3.FIXED):
+        io_g, out_g, ok_g = codec.rs_decode_blocks(k, blocks, arith)
+        io_o, out_o, ok_o = oracle.rs_decode_blocks(k, blocks, arith)
+        assert np.array_equal(ok_g, ok_o)
+        assert np.array_equal(io_g, io_o)
+        assert np.array_equal(out_g, out_o)
+    for tag, arith in (("ref", 0), ("fix", 1)):
+        io, out, ok = codec.rs_decode_blocks(k, G[f"rs{k}_dec_in"], arith)
+        assert np.array_equal(ok, G[f"rs{k}_dec_{tag}_ok"]) and np.array_equal(io, G[f"rs{k}_dec_{tag}_io"]) and np.array_equal(out, G[f"rs{k}_dec_{tag}_out"])
+
+
+def test_selftest_rs_unit_inputs(codec, oracle, t3):
+    """selftest_rs_unit (OLD:1172-1207): t errors on (5i+7)%27; passes with the repaired arithmetic,
+    and reproduces the reference's wrong answer bit for bit as shipped."""
+    r = rng(1)
+    add = T.gf_add_table()
+    for k in KS:
+        t = (26 - k) // 2
+        d = ((5 * np.arange(k) + 7) % 27).astype(np.uint8)
+        for arith in (t3.REF_EXACT, t3.FIXED):
+            code = codec.rs_encode_blocks(k, d, arith)[0].copy()
+            pos = r.choice(26, size=t, replace=False)
+            code[pos] = add[code[pos], r.integers(1, 27, size=t)]
+            io, out, ok = codec.rs_decode_blocks(k, code, arith)
+            io_o, out_o, ok_o = oracle.rs_decode_blocks(k, code, arith)
+            assert np.array_equal(out, out_o) and np.array_equal(ok, ok_o)
+            if arith == t3.FIXED:
+                assert ok[0] and np.array_equal(out[0], d)
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (7, 5), (26, 26), (64, 64), (300, 2), (5, 1)])
+def test_interleave2d(codec, oracle, w, h):
+    r = rng(w * 131 + h)
+    for n in (0, 1, w * h - 1, w * h, w * h + 1, 3 * w * h + w + 1, 100003):
+        sy = r.integers(0, 27, n, dtype=np.uint8)
+        a = codec.interleave2D_boustrophedon(sy, w, h)
+        assert np.array_equal(a, oracle.interleave2d(sy, w, h))
+        assert np.array_equal(codec.interleave2D_boustrophedon(a, w, h, inverse=True), sy)
+
+
+# ------------------------------------------------------------------ header
+def test_header_emit_and_parse(codec, oracle, t3):
+    r = rng(7)
+    for i in range(60):
+        kw = dict(profile=int(r.choice([0, 1, 2, 3, 4])), uep=[int(x) for x in r.integers(0, 4, 9)],
+                  tile=(int(r.integers(0, 70)), int(r.integers(0, 70))),
+                  seed=tuple(int(x) for x in r.integers(0, 2 ** 32 if i % 2 else 27, 3)),
+                  beacon=(int(r.integers(0, 40)), int(r.integers(0, 12)), bool(r.integers(0, 2))),
+                  subword=int(r.choice([27, 24, 21, 18, 15])), centered=bool(r.integers(0, 2)), coset=int(r.integers(0, 3)))
+        oc, gc = both(kw)
+        for arith in (0, 1):
+            h27, c52 = codec.header_emit(gc, arith)
+            hp = oracle.header_pack(oc)
+            assert np.array_equal(h27, hp)
+            a = oracle.rs_encode_blocks(18, hp[:18], arith)[0]
+            b = oracle.rs_encode_blocks(18, np.concatenate([hp[18:], np.zeros(9, np.uint8)]), arith)[0]
+            assert np.array_equal(c52, np.concatenate([a, b]))
+        # parse: true RS(26,18) codewords (+ up to 4 symbol errors in FIXED mode)
+        _, c52 = codec.header_emit(gc, 1)
+        words = np.concatenate([c52, np.zeros(2, np.uint8)]).reshape(6, 9)
+        ok, got = codec.header_parse(words, arith=0)
+        want = oracle.header_unpack(oracle.header_pack(oc))[0]
+        assert ok and bytes(got)[:40] == bytes(want)[:40]
+        bad = words.copy().reshape(-1)
+        for p in r.choice(26, size=4, replace=False):
+            bad[p] = (bad[p] + 1 + int(r.integers(0, 25))) % 27
+        ok2, got2 = codec.header_parse(bad.reshape(6, 9), arith=1)
+        assert ok2 and bytes(got2)[:40] == bytes(want)[:40]
+    ok, _ = codec.header_parse(np.zeros((5, 9), np.uint8))
+    assert not ok
+
+
+# ------------------------------------------------------------------ profile encoder
+@pytest.mark.parametrize("ci", range(len(CONFIGS)))
+def test_encode_profile(codec, oracle, t3, ci):
+    oc, gc = both(CONFIGS[ci])
+    r = rng(1000 + ci)
+    for n in (0, 1, 2, 3, 5, 26, 27, 64, 777, 1000, 8192, 30011):
+        raw = r.integers(0, 27, size=(n, 9), dtype=np.uint8)
+        if n == 64:
+            raw = r.integers(0, 256, size=(n, 9), dtype=np.uint8)
+        for arith in (t3.REF_EXACT, t3.FIXED):
+            got = codec.encode_profile_from_raw(raw, gc, arith)
+            want = oracle.encode_profile(oc, raw, arith)
+            assert got.shape == want.shape and np.array_equal(got, want), (ci, n, arith)
+
+
+@pytest.mark.parametrize("name", sorted(k[4:] for k in G.files if k.startswith("cfg_")))
+def test_golden_pipeline(codec, t3, name):
+    gc = t3.Config.from_buffer_copy(G["cfg_" + name].tobytes())
+    raw = G["pipe_raw"]
+    assert np.array_equal(codec.encode_profile_from_raw(raw, gc, 0), G["enc_ref_" + name])
+    assert np.array_equal(codec.encode_profile_from_raw(raw, gc, 1), G["enc_fix_" + name])
+    assert np.array_equal(codec.encode_frames_rgb8(G["rgb"], gc, 0)[0], G["encrgb_ref_" + name])
+    codec.cfg_last_seen = t3.make_config()
+    ok, words = codec.decode_profile_to_raw(G["dec_ref_in_" + name])
+    assert ok == bool(G["dec_ref_ok_" + name][0])
+    assert np.array_equal(words, G["dec_ref_out_" + name])
+    assert bytes(codec.cfg_last_seen) == G["dec_ref_seen_" + name].tobytes()
+    ok, out, nc = codec.decode_profile_fixed(G["enc_fix_" + name], gc, n_raw_words=raw.shape[0])
+    assert ok and nc == 0 and np.array_equal(out, raw[:out.shape[0]]) and out.shape[0] > 700
+
+
+# ------------------------------------------------------------------ reference decoder as shipped
+def valid_header_stream(oracle, oc, body_words, rnd):
+    hp = oracle.header_pack(oc)
+    a = oracle.rs_encode_blocks(18, hp[:18], 1)[0]
+    b = oracle.rs_encode_blocks(18, np.concatenate([hp[18:], np.zeros(9, np.uint8)]), 1)[0]
+    head = np.concatenate([a, b, rnd.integers(0, 27, 2, dtype=np.uint8)])
+    return np.concatenate([head.reshape(6, 9), body_words])
+
+
+@pytest.mark.parametrize("ci", range(len(CONFIGS) - 1))
+def test_decode_profile_ref_exact(codec, oracle, t3, ci):
+    oc, gc = both(CONFIGS[ci])
+    r = rng(2000 + ci)
+
+    def check(stream, seen_kw=None):
+        codec.cfg_last_seen = t3.make_config(**(seen_kw or {}))
+        ok_g, out_g = codec.decode_profile_to_raw(stream)
+        ok_o, out_o, seen_o = oracle.decode_profile_ref(T.make_cfg(**(seen_kw or {})), stream)
+        assert ok_g == ok_o
+        assert out_g.shape == out_o.shape and np.array_equal(out_g, out_o)
+        assert bytes(codec.cfg_last_seen) == bytes(seen_o)
+        return ok_g
+
+    raw = r.integers(0, 27, size=(500, 9), dtype=np.uint8)
+    assert check(oracle.encode_profile(oc, raw, 0)) is False        # (i) the shipped encoder's output: rejected at the header
+    n_true = 0
+    for trial, nbody in enumerate((0, 5, 26, 27, 130, 260, 263, 2600)):
+        body = r.integers(0, 27, size=(nbody, 9), dtype=np.uint8)
+        if trial >= 3:
+            body = oracle.encode_profile(oc, r.integers(0, 27, size=(3 * nbody, 9), dtype=np.uint8), 1)[6:6 + nbody]
+        n_true += check(valid_header_stream(oracle, oc, body, r))    # (ii) valid header: the body path executes
+    for n in (0, 3, 6, 40):
+        check(r.integers(0, 27, size=(n, 9), dtype=np.uint8))       # (iii) random words / short inputs
+    assert check(raw, dict(profile=T.RAW_MODE))                     # RAW passthrough keyed on the previous header
+    if ci == 4:
+        assert n_true > 0
+
+
+# ------------------------------------------------------------------ FIXED: consistent decode
+@pytest.mark.parametrize("ci", range(len(CONFIGS) - 1))
+def test_fixed_roundtrip_with_errors(codec, oracle, t3, ci):
+    oc, gc = both(CONFIGS[ci])
+    r = rng(3000 + ci)
+    add = T.gf_add_table()
+    for n in (0, 1, 3, 64, 777, 4000, 30011):
+        raw = r.integers(0, 27, size=(n, 9), dtype=np.uint8)
+        raw[:, 8] %= 9
+        enc = codec.encode_profile_from_raw(raw, gc, t3.FIXED)
+        ok, out, nc = codec.decode_profile_fixed(enc, gc, n_raw_words=n)
+        ok_o, out_o, nc_o = oracle.decode_profile_fixed(oc, enc, n_raw_words=n)
+        assert ok and ok_o and nc == nc_o == 0
+        assert np.array_equal(out, out_o) and np.array_equal(out, raw[:out.shape[0]])
+        if not (gc.profile == 4 and gc.tile_w and gc.tile_h):
+            ok2, out2, _ = codec.decode_profile_fixed(enc, gc, n_raw_words=0)
+            assert ok2 and np.array_equal(out2, out)
+        if n >= 64 and not (gc.beacon_enabled and gc.beacon_slot > 8):
+            for exact_t in (False, True):
+                bad, nerr = T.inject_errors(enc, oc, n, seed=3 + exact_t, gf_add=add, exact_t=exact_t)
+                ok3, out3, nc3 = codec.decode_profile_fixed(bad, gc, n_raw_words=n)
+                assert ok3 and np.array_equal(out3, out) and nc3 == nerr and nerr > 0
+            # more than t errors in one codeword: same verdict and output as the oracle
+            worse = bad.copy().reshape(-1)
+            worse[52:52 + 12] = (worse[52:52 + 12] + 1) % 27
+            ok4, out4, _ = codec.decode_profile_fixed(worse.reshape(-1, 9), gc, n_raw_words=n)
+            ok5, out5, _ = oracle.decode_profile_fixed(oc, worse.reshape(-1, 9), n_raw_words=n)
+            assert ok4 == ok5 and np.array_equal(out4, out5)
+
+
+# ------------------------------------------------------------------ fused frames
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4, 5, 7, 9, 12])
+@pytest.mark.parametrize("shape", [(64, 64), (512, 512), (130, 77)])
+def test_fused_frames_rgb8(codec, oracle, t3, ci, shape):
+    oc, gc = both(CONFIGS[ci])
+    n_px = shape[0] * shape[1]
+    frames = np.stack([T.synth_rgb(1, n_px), T.synth_checker(shape[0], shape[1]), T.synth_rgb(9, n_px)])
+    add = T.gf_add_table()
+    for arith in (t3.REF_EXACT, t3.FIXED):
+        got = codec.encode_frames_rgb8(frames, gc, arith)
+        for f in range(frames.shape[0]):
+            assert np.array_equal(got[f], oracle.encode_rgb(oc, frames[f], arith)), (ci, shape, arith, f)
+    enc = codec.encode_frames_rgb8(frames, gc, t3.FIXED)
+    ok, rgb, nc = codec.decode_frames_rgb8(enc, n_px, gc)
+    assert ok.all() and nc == 0
+    for f in range(frames.shape[0]):
+        ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, enc[f], n_px)
+        assert ok_o and np.array_equal(rgb[f], rgb_o)
+        assert np.array_equal(rgb[f], oracle.quant_to_rgb(oracle.rgb_to_quant(frames[f]))[:rgb.shape[1]])
+    if not (gc.beacon_enabled and gc.beacon_slot > 8):
+        bad = enc.copy()
+        tot = 0
+        for f in range(frames.shape[0]):
+            bad[f], ne = T.inject_errors(enc[f], oc, (n_px + 1) // 2, seed=11 + f, gf_add=add)
+            tot += ne
+        ok2, rgb2, nc2 = codec.decode_frames_rgb8(bad, n_px, gc)
+        assert ok2.all() and nc2 == tot and np.array_equal(rgb2, rgb)
