@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json configs[1]):
+
+    single synthetic 8K (7680x4320) RGB8 frame, RS(26,20) (uep_uniform(2), profile P3), 1D 9-band
+    interleave, encode + decode, per B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference's CPU code on the host cores)
+
+One "step" = one fused encode (RGB8 -> profile words) plus one fused decode (profile words -> RGB8) of
+one 8K frame per GPU.  Frames shard across GPUs with no data-path collective (weak scaling): value =
+pixels all ranks processed / max-over-ranks device time.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W8K, H8K = 7680, 4320
+N_PX = W8K * H8K
+METRIC = "8k_rgb8_rs26_20_encode_plus_decode_throughput"
+UNIT = "Mpix/s"
+WORKLOAD = "8K (7680x4320) RGB8 frame, RS(26,20) uep_uniform(2)/P3, 1D 9-band interleave, scrambler {1,1,1}, no beacon; fused encode + decode (FIXED arithmetic, clean stream)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the checker / the reported baseline, never the product path)
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_step(n_px_per_thread: int, threads: int, use_ref: bool):
+    """One bounded sample of the same workload on the host cores; every thread runs encode + decode on its
+    own slice of a synthetic frame.  With oracle/_ref present this is the reference's own code
+    (libt3ref_fixed.so = reference + the 3-line RS repair, so that the decoder's clean fast-exit works and the
+    CPU number is the favourable one): encode = rgb_to_quant_stream + encode_raw_pixels_to_words +
+    encode_profile_from_raw; decode = descramble (numpy) + RSCodec::decode_block over every body codeword +
+    decode_raw_words_to_pixels + quant_stream_to_rgb (the band re-multiplex, a plain permutation, is left out
+    in the reference's favour: its shipped decoder cannot parse its own encoder's framing).
+    Otherwise the C port (oracle/t3_oracle.c) runs encode_rgb + decode_rgb_fixed.
+    Returns (pixels, seconds, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import t3oracle as T
+    from concurrent.futures import ThreadPoolExecutor
+    oracle = T.Oracle()
+    ref = None
+    if use_ref:
+        try:
+            ref = T.Reference(True)
+        except Exception:
+            ref = None
+    cfg = T.make_cfg(profile=T.P3, uep=2)
+    slices = [T.synth_rgb(100 + t, n_px_per_thread) for t in range(threads)]
+    add = T.gf_add_table()
+    neg = np.array([np.argmax(add[x] == 0) for x in range(27)], np.uint8)
+    st = T.C.c_uint32(cfg.seed_s0 % 3)
+    pat = np.array([oracle.lib.t3o_scramble_symbol(T.C.c_uint8(0), T.C.c_uint32(cfg.seed_a), T.C.c_uint32(cfg.seed_b), T.C.byref(st))
+                    for _ in range(6)], np.uint8)  # 13*st_p, period divides 6 (no transient for seed {1,1,1})
+
+    def work(rgb):
+        if ref is not None:
+            enc = ref.encode_rgb(cfg, rgb, 1)
+            flat = enc.reshape(-1)
+            ncw = (flat.size - 52) // 26
+            body = flat[52:52 + 26 * ncw]
+            desc = add[body, neg[np.resize(pat, body.size)]]
+            io, out, ok = ref.rs_decode_blocks(20, desc, 1)
+            assert ok.all()
+            px = ref.unpack_pixels(enc[6:6 + rgb.shape[0] // 2])
+            ref.quant_to_rgb(px[:rgb.shape[0]])
+            return enc.shape[0]
+        enc = oracle.encode_rgb(cfg, rgb, 1)
+        ok, back, _ = oracle.decode_rgb_fixed(cfg, enc, rgb.shape[0])
+        assert ok
+        return enc.shape[0]
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, slices))
+    dt = time.perf_counter() - t0
+    return n_px_per_thread * threads, dt, ("reference" if ref is not None else "port")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, 64))
+    n_slice = N_PX // 256  # 129600 px per thread and step
+    use_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libt3ref.so"))
+    for _ in range(args.warmup):
+        cpu_reference_step(n_slice // 4, threads, use_ref)
+    px = 0
+    secs = 0.0
+    kind = "port"
+    for _ in range(args.steps):
+        p, dt, kind = cpu_reference_step(n_slice, threads, use_ref)
+        px += p
+        secs += dt
+    v = px / secs / 1e6
+    sample = f"{threads} threads x {n_slice} px (1/256 of an 8K frame each) per step, reference encode chain + decode_block over every codeword + unpack + dequant"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ternary_image_codec_b200 as t3
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = t3.make_config(profile=t3.P3_RS26_20, uep=2)
+    codec = t3.Codec(local, arith=t3.FIXED)
+    n_px, n_words = N_PX, N_PX // 2
+    wpf = t3.profile_words(cfg, n_words)
+    NBUF = 3  # rotate buffers: every pass streams > L2 (126 MB) of fresh data, nothing is re-read from cache
+    g = torch.Generator(device=dev)
+    g.manual_seed(2 + rank)
+    rgb = [torch.randint(0, 256, (n_px * 3,), dtype=torch.uint8, device=dev, generator=g) for _ in range(NBUF)]
+    enc = [torch.empty(wpf * 9, dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+    back = [torch.empty(n_px * 3, dtype=torch.uint8, device=dev) for _ in range(NBUF)]
+    status = torch.zeros(2 * NBUF, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def encode(i):
+        codec.encode_frames_rgb8_dev(rgb[i], n_px, 1, enc[i], wpf, cfg, t3.FIXED, stream)
+
+    def decode(i):
+        codec.decode_frames_rgb8_dev(enc[i], wpf, wpf, 1, n_px, back[i], status[2 * i:], cfg, stream)
+
+    for i in range(NBUF):
+        encode(i)
+    for w in range(max(args.warmup, 3)):
+        encode(w % NBUF)
+        decode((w + 1) % NBUF)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = codec.kernel_launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        ev[s][0].record()
+        encode(s % NBUF)
+        ev[s][1].record()
+        decode((s + 1) % NBUF)
+        ev[s][2].record()
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = codec.kernel_launches - launches0
+    sampler.stop_flag.set()
+    sampler.join()
+    ms_total = t_start.elapsed_time(t_end)
+    enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    dec_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+    # correctness of what was timed: decode(encode(x)) == dequant(quant(x)) on the device, clean flags
+    torch.cuda.synchronize()
+    st = status.cpu().numpy()
+    assert (st[0::2] == 1).all(), f"decoder reported failure: {st}"
+    q = torch.empty(n_px * 6, dtype=torch.uint8, device=dev)
+    chk = torch.empty(n_px * 3, dtype=torch.uint8, device=dev)
+    codec.rgb_to_quant_dev(rgb[0], n_px, q, stream)
+    codec.quant_to_rgb_dev(q, n_px, chk, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(chk, back[0]), "round trip mismatch on the timed buffers"
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
+    e2e = None
+    cpu = None
+    if True:
+        h_rgb = torch.empty((1, n_px, 3), dtype=torch.uint8).pin_memory()
+        h_rgb.copy_(rgb[0].view(1, n_px, 3))
+        h_enc = torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory()
+        h_back = torch.empty((1, n_px, 3), dtype=torch.uint8).pin_memory()
+        import ctypes as C
+        L = codec.lib
+        okb = np.zeros(1, np.uint8)
+        got, rec, nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
+
+        def e2e_step():
+            s1 = L.t3c_encode_frames_rgb8(codec.h, C.byref(cfg), t3.FIXED, h_rgb.data_ptr(), n_px, 1, h_enc.data_ptr(), wpf, C.byref(got))
+            s2 = L.t3c_decode_frames_rgb8(codec.h, C.byref(cfg), h_enc.data_ptr(), wpf, wpf, 1, n_px, h_back.data_ptr(),
+                                          okb.ctypes.data_as(C.c_void_p), C.byref(rec), C.byref(nc))
+            assert s1 == 0 and s2 == 0 and okb[0] == 1
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert torch.equal(h_back.view(-1), chk.cpu()), "e2e round trip mismatch"
+        e2e = {"value": world * n_px * e2e_steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": 3 * n_px + 9 * wpf, "d2h_bytes_per_step": 9 * wpf + 3 * n_px,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
+
+    if rank == 0:
+        # parity spot check against the oracle on a slice of the timed frame + CPU baseline (bounded sample)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import t3oracle as T
+        oracle = T.Oracle()
+        nchk = 1 << 16
+        sl = rgb[0][:3 * nchk].cpu().numpy().reshape(-1, 3)
+        want = oracle.quant_to_rgb(oracle.rgb_to_quant(sl))
+        assert np.array_equal(back[0][:3 * nchk].cpu().numpy().reshape(-1, 3), want), "oracle spot check failed"
+        cores = os.cpu_count() or 1
+        threads = max(1, min(cores, 64))
+        n_slice = N_PX // 256
+        px, secs, kind = cpu_reference_step(n_slice, threads, os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libt3ref.so")))
+        cpu = {"value": px / secs / 1e6, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{threads} threads x {n_slice} px (1/256 of an 8K frame each), encode + decode, {secs:.1f} s"}
+
+        peak, peak_src = peaks()
+        alg = 3 * n_px + 9 * wpf  # algorithmic bytes of one fused launch: 286 433 334 B for 8K k=20
+        dom = "encode" if enc_ms >= dec_ms else "decode"
+        dom_ms = max(enc_ms, dec_ms)
+        ach = alg / (dom_ms * 1e-3) / 1e9
+        clocks = sampler.summary()
+        out = {
+            "metric": METRIC, "value": world * n_px * args.steps / (ms_total * 1e-3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "pixels_per_frame": n_px, "profile_words_per_frame": wpf,
+                       "l2_policy": f"{NBUF} rotating frame buffers, {(alg * 2) >> 20} MiB streamed per step (> 126 MB L2), decode reads a stream encoded 2 steps earlier",
+                       "fast_path": bool(t3.fast_path_available(cfg)), "sharding": "one 8K frame per GPU per step, no collective"},
+            "frames_per_s": world * args.steps / (ms_total * 1e-3),
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": f"fused {dom}", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "encode_ms": enc_ms, "decode_ms": dec_ms,
+                         "encode_gbs": alg / (enc_ms * 1e-3) / 1e9, "decode_gbs": alg / (dec_ms * 1e-3) / 1e9,
+                         "frac_of_nominal_8tbs": ach / 8000.0},
+            "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(out))
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
