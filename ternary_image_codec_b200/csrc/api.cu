@@ -19,6 +19,7 @@ struct t3c_ctx {
     cudaStream_t stream = nullptr;
     DevTables tabs{};
     void* d_tables = nullptr;
+    HostTables* host = nullptr; // host copy of the constant tables (decoder screen constants are derived per call)
     // grow-only device scratch
     struct Buf { void* p = nullptr; size_t cap = 0; };
     Buf buf[6];
@@ -156,7 +157,7 @@ t3c_status t3c_create(int device, t3c_ctx** out)
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_mail, sizeof(t3c_ctx::Mail));
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_mail, sizeof(t3c_ctx::Mail));
     if (e == cudaSuccess) e = cudaMemset(ctx->d_mail, 0, sizeof(t3c_ctx::Mail));
-    delete ht;
+    ctx->host = ht;
     if (e != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
     ctx->tabs.gf = &static_cast<HostTables*>(ctx->d_tables)->gf;
     ctx->tabs.rs = &static_cast<HostTables*>(ctx->d_tables)->rs;
@@ -177,6 +178,7 @@ void t3c_destroy(t3c_ctx* ctx)
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx->host;
     delete ctx;
 }
 
@@ -284,7 +286,9 @@ t3c_status t3c_encode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, int a
     if (cfg->profile != T3C_PROFILE_RAW && fast_path_ok(*cfg)) {
         Geom g;
         make_geom(*cfg, n_words, arith, g);
-        return check_launch(ctx, launch_encode_rgb_fast(ctx->tabs, *cfg, g, d_rgb, n_px, n_frames, d_out, stride_words, s));
+        const int n = launch_encode_rgb_fast(ctx->tabs, *cfg, g, d_rgb, n_px, n_frames, d_out, stride_words, s);
+        if (n >= 0) return check_launch(ctx, n);
+        // unaligned buffers: fall through to the general kernels
     }
     // general path: per frame K1 (bridge, pack) into scratch, then the general profile encoder
     t3c_pixel* q = nullptr;
@@ -315,8 +319,12 @@ t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, const
     if (nw > n_words) nw = n_words;
     size_t px_out = 2 * (size_t)nw < n_px ? 2 * (size_t)nw : n_px;
     TRY(check_launch(ctx, launch_init_status(d_status, n_frames, s)));
-    if (fast_path_ok(*cfg))
-        return check_launch(ctx, launch_decode_rgb_fast(ctx->tabs, *cfg, g, d_in, stride_words, n_frames, n_px, px_out, d_rgb, d_status, s));
+    if (fast_path_ok(*cfg)) {
+        uint32_t chk_nz[7], chk_two[7];
+        fast_check_constants(*ctx->host, g, chk_nz, chk_two);
+        const int n = launch_decode_rgb_fast(ctx->tabs, *cfg, g, d_in, stride_words, n_frames, n_px, px_out, d_rgb, d_status, s, chk_nz, chk_two);
+        if (n >= 0) return check_launch(ctx, n);
+    }
     uint8_t* sy = nullptr;
     TRY(reserve_t(ctx, B_TMP, g.n_s + 16, &sy));
     for (size_t f = 0; f < n_frames; ++f) {

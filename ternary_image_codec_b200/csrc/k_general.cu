@@ -369,8 +369,9 @@ __global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restric
     }
 }
 // header, beacon symbols and zero padding of one super-frame
-__global__ void k_frame_misc(uint8_t* __restrict__ out, Geom g, t3c_config cfg, const GfTables* gf, const RsTables* rs)
+__global__ void k_frame_misc(uint8_t* __restrict__ out_base, size_t stride_bytes, Geom g, t3c_config cfg, const GfTables* gf, const RsTables* rs)
 {
+    uint8_t* __restrict__ out = out_base + stride_bytes * blockIdx.y;
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         __shared__ uint8_t h27[27], c52[52];
         header_emit_warp(cfg, g.arith, gf, rs, h27, c52);
@@ -546,11 +547,16 @@ int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom&
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
     if (mx) { k_encode_general<<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs); ++n; }
+    return n + launch_frame_misc(T, cfg, g, out, 1, 0, st);
+}
+int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out, size_t n_frames, size_t stride_bytes, cudaStream_t st)
+{
+    if (!n_frames) return 0;
     const uint64_t nb = g.period ? g.l_exp / 9 / g.period + 1 : 1;
     unsigned blocks = (unsigned)((nb + 255) / 256);
     if (blocks > 1024) blocks = 1024;
-    k_frame_misc<<<blocks, 256, 0, st>>>(out, g, cfg, T.gf, T.rs);
-    return n + 1;
+    k_frame_misc<<<dim3(blocks, (unsigned)n_frames), 256, 0, st>>>(out, stride_bytes, g, cfg, T.gf, T.rs);
+    return 1;
 }
 int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint32_t* status, cudaStream_t st)
 {

@@ -44,7 +44,12 @@ int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uin
 bool fast_path_ok(const t3c_config& cfg);
 int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* rgb, size_t n_px, size_t n_frames,
                            uint8_t* out9, size_t stride_words, cudaStream_t st);
+// chk_*: bit planes of sum_i T_i[13*st_i] for the 6 scrambler phases and for the codeword at body index 0
 int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in9, size_t stride_words,
-                           size_t n_frames, size_t n_px, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st);
+                           size_t n_frames, size_t n_px, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st,
+                           const uint32_t* chk_nz, const uint32_t* chk_two);
+// both return -1 when the buffers are not 16-byte aligned (caller falls back to the general kernels)
+// header + beacons + zero padding for n_frames super-frames laid out every stride_bytes
+int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out9, size_t n_frames, size_t stride_bytes, cudaStream_t st);
 
 } // namespace t3c

@@ -69,6 +69,7 @@ struct Geom {
 
 struct HostTables { GfTables gf; RsTables rs; };
 void build_tables(HostTables& t);
+void fast_check_constants(const HostTables& H, const Geom& g, uint32_t chk_nz[7], uint32_t chk_two[7]);
 
 // host-side geometry; returns false on invalid config values
 void make_geom(const t3c_config& c, size_t n_words, int arith, Geom& g);

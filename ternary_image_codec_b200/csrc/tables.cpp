@@ -174,6 +174,31 @@ void make_geom(const t3c_config& c, size_t n_words, int arith, Geom& g)
     g.arith = (uint8_t)(arith ? 1 : 0);
 }
 
+// decoder screen: a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i]
+// (the row tables are GF(3)-linear).  One constant per scrambler phase, plus the block at body index 0
+// whose first two symbols may still be in the LCG's transient.
+void fast_check_constants(const HostTables& H, const Geom& g, uint32_t chk_nz[7], uint32_t chk_two[7])
+{
+    if (!g.uniform_k) { for (int i = 0; i < 7; ++i) chk_nz[i] = chk_two[i] = 0; return; }
+    const RowTable& R = H.rs.row[1][kidx_of(g.uniform_k)];
+    for (int ph = 0; ph < 7; ++ph) {
+        int trit[32] = {0};
+        for (int i = 0; i < 26; ++i) {
+            int st;
+            if (ph == 6) st = i < 2 ? g.st[i] : g.st[2 + (i - 2) % 6];
+            else st = g.st[2 + (ph + i) % 6];
+            const uint64_t e = R.e[i][13 * st];
+            for (int bit = 0; bit < 32; ++bit) {
+                const int v = ((e >> bit) & 1) + ((e >> (32 + bit)) & 1); // 0,1,2
+                trit[bit] = (trit[bit] + v) % 3;
+            }
+        }
+        uint32_t nz = 0, two = 0;
+        for (int bit = 0; bit < 32; ++bit) { if (trit[bit]) nz |= 1u << bit; if (trit[bit] == 2) two |= 1u << bit; }
+        chk_nz[ph] = nz; chk_two[ph] = two;
+    }
+}
+
 size_t profile_words(const t3c_config& c, size_t n_words)
 {
     if (c.profile == T3C_PROFILE_RAW) return n_words;
