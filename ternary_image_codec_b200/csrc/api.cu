@@ -592,10 +592,11 @@ t3c_status t3c_encode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, int arith
     if (stride_words < no) return fail(ctx, T3C_ERR_CAPACITY, "encode_frames: stride");
     if (!n_frames) return T3C_OK;
     uint8_t *d_in, *d_out;
-    TRY(reserve_t(ctx, B_IN, 3 * n_px * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * stride_words * n_frames, &d_out));
+    const size_t dstride = (no + 15) & ~(size_t)15; // device-side frame pitch: keeps every frame 16-byte aligned
+    TRY(reserve_t(ctx, B_IN, 3 * n_px * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * dstride * n_frames, &d_out));
     H2D(d_in, rgb, 3 * n_px * n_frames);
-    TRY(t3c_encode_frames_rgb8_dev(ctx, cfg, arith, d_in, n_px, n_frames, d_out, stride_words, ctx->stream));
-    D2H(out, d_out, 9 * stride_words * (n_frames - 1) + 9 * no);
+    TRY(t3c_encode_frames_rgb8_dev(ctx, cfg, arith, d_in, n_px, n_frames, d_out, dstride, ctx->stream));
+    CU(cudaMemcpy2DAsync(out, 9 * stride_words, d_out, 9 * dstride, 9 * no, n_frames, cudaMemcpyDeviceToHost, ctx->stream));
     SYNC();
     return T3C_OK;
 }
@@ -616,9 +617,10 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
     if (nw > n_words) nw = n_words;
     const size_t px_out = 2 * (size_t)nw < n_px ? 2 * (size_t)nw : n_px;
     uint8_t *d_in, *d_out;
-    TRY(reserve_t(ctx, B_IN, 9 * stride_words * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 3 * n_px * n_frames, &d_out));
-    H2D(d_in, in, 9 * stride_words * (n_frames - 1) + 9 * words_per_frame);
-    TRY(t3c_decode_frames_rgb8_dev(ctx, cfg, d_in, words_per_frame, stride_words, n_frames, n_px, d_out, ctx->d_mail->status, ctx->stream));
+    const size_t dstride = (words_per_frame + 15) & ~(size_t)15;
+    TRY(reserve_t(ctx, B_IN, 9 * dstride * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 3 * n_px * n_frames, &d_out));
+    CU(cudaMemcpy2DAsync(d_in, 9 * dstride, in, 9 * stride_words, 9 * words_per_frame, n_frames, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(t3c_decode_frames_rgb8_dev(ctx, cfg, d_in, words_per_frame, dstride, n_frames, n_px, d_out, ctx->d_mail->status, ctx->stream));
     for (size_t f = 0; f < n_frames; ++f) if (px_out) D2H(rgb + 3 * n_px * f, d_out + 3 * n_px * f, 3 * px_out);
     MAIL_DOWN();
     for (size_t f = 0; f < n_frames; ++f) {

@@ -70,7 +70,8 @@ __device__ __forceinline__ void triple_to_symbols(uint32_t A0, uint32_t A1, uint
 // inverse: 13 symbols -> three 13-trit pixel values
 __device__ __forceinline__ void symbols_to_triple(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t s12, uint32_t& A0, uint32_t& A1, uint32_t& A2)
 {
-    auto val4 = [](uint32_t w) { return (w & 0xFF) + 27u * ((w >> 8) & 0xFF) + 729u * ((w >> 16) & 0xFF) + 19683u * (w >> 24); };
+    // b0 + 27 b1 + 729 (b2 + 27 b3): two 4-way byte dot products and one multiply-add
+    auto val4 = [](uint32_t w) { return __dp4a(w, 0x00001B01u, 0u) + 729u * __dp4a(w, 0x1B010000u, 0u); };
     const uint32_t v0 = val4(w0), v1 = val4(w1), v2 = val4(w2) + 531441u * s12; // 12, 12 and 15 trits
     const uint32_t t = v1 % 3u;                         // trit 12 belongs to pixel 0
     A0 = v0 + 531441u * t;
@@ -86,13 +87,22 @@ __device__ __forceinline__ float byte_to_float(uint32_t w, int j)
 }
 // rgb_to_ycbcr + quantize_ycbcr (IMG:47-56,69-78) -> 13-trit pixel value; no clamps are needed for 8-bit
 // inputs: y in [0,255.0001), cb,cr in [0.5,255.5] and round(255.5)=256 quantises like 255.
+// 0.5f*x is exact, so fma(0.5,x,t) == fl(t + fl(0.5*x)): two multiplies are folded without changing a bit.
+// Rounding: FADD.RM against 2^22+0.5 leaves B = 0x25400000 + floor(v+0.5) after >>1 (see round_pos); the
+// offset is folded into the quantiser constants (0x25400000 has its low 7 bits clear).
 __device__ __forceinline__ uint32_t rgb_to_value(float r, float g, float b)
 {
     const float y = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
-    const float cb = __fadd_rn(__fadd_rn(__fsub_rn(__fmul_rn(-0.168736f, r), __fmul_rn(0.331264f, g)), __fmul_rn(0.5f, b)), 128.0f);
-    const float cr = __fadd_rn(__fsub_rn(__fsub_rn(__fmul_rn(0.5f, r), __fmul_rn(0.418688f, g)), __fmul_rn(0.081312f, b)), 128.0f);
-    const int Y = round_pos(y), Cb = round_pos(cb), Cr = round_pos(cr);
-    return (uint32_t)quant_y(Y) + 243u * (uint32_t)quant_c_off(Cb) + 19683u * (uint32_t)quant_c_off(Cr);
+    const float cb = __fadd_rn(__fmaf_rn(0.5f, b, __fsub_rn(__fmul_rn(-0.168736f, r), __fmul_rn(0.331264f, g))), 128.0f);
+    const float cr = __fadd_rn(__fsub_rn(__fmaf_rn(0.5f, r, -__fmul_rn(0.418688f, g)), __fmul_rn(0.081312f, b)), 128.0f);
+    constexpr uint32_t KB = 0x25400000u;
+    const uint32_t By = (uint32_t)__float_as_int(__fadd_rd(y, 4194304.5f)) >> 1;
+    const uint32_t Bb = (uint32_t)__float_as_int(__fadd_rd(cb, 4194304.5f)) >> 1;
+    const uint32_t Br = (uint32_t)__float_as_int(__fadd_rd(cr, 4194304.5f)) >> 1;
+    const uint32_t yq = (By * 484u + (255u - KB * 484u)) / 510u;                                   // quant_y
+    const uint32_t ub = (5u * Bb + (Bb >> 7) + (7u - 5u * KB - (KB >> 7))) >> 4;                   // quant_c_off
+    const uint32_t ur = (5u * Br + (Br >> 7) + (7u - 5u * KB - (KB >> 7))) >> 4;
+    return yq + 243u * ub + 19683u * ur;
 }
 // pixel value -> RGB8 bytes (decode_raw_words_to_pixels + quant_stream_to_rgb, OLD:706-722, IMG:57-84)
 __device__ __forceinline__ uint32_t value_to_rgb(uint32_t A)
@@ -134,16 +144,54 @@ __device__ __forceinline__ void store_run(const uint8_t* s, uint8_t* __restrict_
     }
 }
 
-__device__ __forceinline__ void store2(uint8_t* p, uint32_t lo, uint32_t hi)
+// the nine band runs of a tile, shared -> global, flattened over (run, 16-byte chunk); 32-bit index math,
+// 128-bit stores for interior chunks, 32-bit (or byte) stores only in the two boundary chunks of a run
+template <int PITCH>
+__device__ __forceinline__ void store_runs9(const uint8_t* O, uint8_t* __restrict__ gbase, const uint64_t* run_lo, const uint32_t* run_n)
 {
-    if (((uintptr_t)p & 1) == 0) *reinterpret_cast<uint16_t*>(p) = (uint16_t)(lo | (hi << 8));
-    else { p[0] = (uint8_t)lo; p[1] = (uint8_t)hi; }
+    constexpr int CH = PITCH / 16;
+    for (int j = threadIdx.x; j < 9 * CH; j += FAST_TPB) {
+        const int b = j / CH, c = j - b * CH;
+        const int len = 26 * (int)run_n[b];
+        const uint64_t lo = run_lo[b];
+        const int pad = (int)(lo & 15), r0 = 16 * c - pad, r1 = r0 + 16;
+        if (r1 <= 0 || r0 >= len) continue;
+        uint8_t* gp = gbase + (lo - pad) + 16 * c;
+        const uint8_t* sp = O + PITCH * b + 16 * c;
+        if (r0 >= 0 && r1 <= len) {
+            *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+        } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int a = r0 + 4 * w;
+                if (a >= 0 && a + 4 <= len) *reinterpret_cast<uint32_t*>(gp + 4 * w) = *reinterpret_cast<const uint32_t*>(sp + 4 * w);
+                else
+                    for (int i = 0; i < 4; ++i) if (a + i >= 0 && a + i < len) gp[4 * w + i] = sp[4 * w + i];
+            }
+        }
+    }
 }
-__device__ __forceinline__ uint32_t load2(const uint8_t* p)
+template <int PITCH>
+__device__ __forceinline__ void load_runs9(uint8_t* O, const uint8_t* __restrict__ gbase, const uint64_t* run_lo, const uint32_t* run_n, uint64_t g_limit)
 {
-    if (((uintptr_t)p & 1) == 0) return *reinterpret_cast<const uint16_t*>(p);
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+    constexpr int CH = PITCH / 16;
+    for (int j = threadIdx.x; j < 9 * CH; j += FAST_TPB) {
+        const int b = j / CH, c = j - b * CH;
+        const int len = 26 * (int)run_n[b];
+        const uint64_t lo = run_lo[b];
+        const int pad = (int)(lo & 15), r0 = 16 * c - pad;
+        if (r0 + 16 <= 0 || r0 >= len) continue;
+        const uint64_t ga = (lo - pad) + 16 * c;
+        uint8_t* sp = O + PITCH * b + 16 * c;
+        if (ga + 16 <= g_limit) *reinterpret_cast<uint4*>(sp) = __ldg(reinterpret_cast<const uint4*>(gbase + ga));
+        else
+            for (int i = 0; i < 16; ++i) sp[i] = ga + i < g_limit ? gbase[ga + i] : 0;
+    }
 }
+
+// body runs start at even byte offsets (the launchers only take the fast path when every frame does)
+__device__ __forceinline__ void store2(uint8_t* p, uint32_t lo, uint32_t hi) { *reinterpret_cast<uint16_t*>(p) = (uint16_t)(lo | (hi << 8)); }
+__device__ __forceinline__ uint32_t load2(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
 
 // =============================================================================================
 // encode
@@ -159,12 +207,14 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
     uint8_t* O = smem + L::OFF_O;
     uint8_t* scr = smem + L::OFF_GF; // 3 x 32 scramble look-up
     __shared__ uint64_t run_lo[9];
-    __shared__ uint32_t run_n[9];
+    __shared__ uint32_t run_n[9], run_ph[9];
     const int tid = threadIdx.x;
+    __shared__ uint32_t stoff[14]; // 32*st for phase index 0..11 (two periods) and for body indices 0,1
     {
         const RowTable& T = rs->row[g.arith][(24 - K) / 2];
         for (int i = tid; i < K * kVals; i += FAST_TPB) tab[i] = T.e[i / kVals][i % kVals];
         if (tid < 96) scr[tid] = gf->scr[tid / 32][tid % 32];
+        if (tid < 14) stoff[tid] = 32u * (tid < 12 ? g.st[2 + tid % 6] : g.st[tid - 12]);
     }
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
     for (uint64_t tile_id = blockIdx.x; tile_id < total; tile_id += gridDim.x) {
@@ -183,6 +233,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
             const uint64_t n = c0 >= g.ncw[tid] ? 0 : ((g.ncw[tid] - c0) < C_TILE ? (g.ncw[tid] - c0) : C_TILE);
             run_lo[tid] = (uint64_t)(out - P.out) + 52 + 26 * (g.cw_base[tid] + c0);
             run_n[tid] = (uint32_t)n;
+            run_ph[tid] = (uint32_t)((26 * (g.cw_base[tid] + c0) + 4) % 6) | (g.cw_base[tid] + c0 == 0 ? 8u : 0u);
         }
         load_run(s_rgb, P.in, g_lo, g_hi, P.in_stride * P.n_frames);
         __syncthreads();
@@ -194,6 +245,8 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
             uint32_t w[10];
 #pragma unroll
             for (int j = 0; j < 10; ++j) w[j] = mw[j];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh); // the 36 bytes, now word aligned
             uint32_t A[12];
 #pragma unroll
             for (int p = 0; p < 12; ++p) {
@@ -202,8 +255,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const int bi = 3 * p + c;
-                    const uint32_t word = __funnelshift_r(w[bi >> 2], w[(bi >> 2) + 1], sh);
-                    ch[c] = byte_to_float(word, bi & 3);
+                    ch[c] = byte_to_float(w[bi >> 2], bi & 3);
                 }
                 const uint64_t pix = px0 + 12ull * u + p;
                 uint32_t v = rgb_to_value(ch[0], ch[1], ch[2]);
@@ -211,18 +263,16 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
                 A[p] = v;
             }
             uint32_t o[13];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            {
                 uint32_t w0, w1, w2, s12;
-                triple_to_symbols(A[3 * t], A[3 * t + 1], A[3 * t + 2], w0, w1, w2, s12);
-                // 13 bytes at byte offset 13t of the unit's 52-byte output
-                const uint64_t lo = (uint64_t)w0 | ((uint64_t)w1 << 32), hi = (uint64_t)w2 | ((uint64_t)s12 << 32);
-#pragma unroll
-                for (int bq = 0; bq < 13; ++bq) {
-                    const uint32_t byte = (uint32_t)(((bq < 8 ? lo >> (8 * bq) : hi >> (8 * (bq - 8)))) & 0xFF);
-                    const int pos = 13 * t + bq;
-                    if ((pos & 3) == 0) o[pos >> 2] = byte; else o[pos >> 2] |= byte << (8 * (pos & 3));
-                }
+                triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);       // bytes 0..12
+                o[0] = w0; o[1] = w1; o[2] = w2; o[3] = s12;
+                triple_to_symbols(A[3], A[4], A[5], w0, w1, w2, s12);       // bytes 13..25
+                o[3] |= w0 << 8; o[4] = __funnelshift_l(w0, w1, 8); o[5] = __funnelshift_l(w1, w2, 8); o[6] = __funnelshift_l(w2, s12, 8);
+                triple_to_symbols(A[6], A[7], A[8], w0, w1, w2, s12);       // bytes 26..38
+                o[6] |= w0 << 16; o[7] = __funnelshift_l(w0, w1, 16); o[8] = __funnelshift_l(w1, w2, 16); o[9] = __funnelshift_l(w2, s12, 16);
+                triple_to_symbols(A[9], A[10], A[11], w0, w1, w2, s12);     // bytes 39..51
+                o[9] |= w0 << 24; o[10] = __funnelshift_l(w0, w1, 24); o[11] = __funnelshift_l(w1, w2, 24); o[12] = __funnelshift_l(w2, s12, 24);
             }
             uint32_t* dst = reinterpret_cast<uint32_t*>(S) + 13 * u;
 #pragma unroll
@@ -233,13 +283,13 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
         for (int cw = tid; cw < L::NCW; cw += FAST_TPB) {
             const int b = cw / C_TILE, cl = cw - b * C_TILE;
             if ((uint32_t)cl >= run_n[b]) continue;
-            const uint64_t c = (uint64_t)C_TILE * tile + cl;
-            const uint64_t p0 = 26 * (g.cw_base[b] + c);
-            const uint32_t ph = (uint32_t)((p0 + 4) % 6);
+            const uint32_t rp = run_ph[b];
+            const uint32_t ph = ((rp & 7) + 2u * (uint32_t)cl) % 6u;   // (p0 + 4) % 6 with p0 = 26*(cw_base_b + c)
+            const bool first = (rp & 8) && cl == 0;                    // the block at body index 0 (LCG transient)
             uint32_t so[6]; // scramble row offset for symbol i: so[i%6]
 #pragma unroll
-            for (int j = 0; j < 6; ++j) so[j] = 32u * g.st[2 + (ph + j) % 6];
-            const uint32_t so0 = p0 == 0 ? 32u * g.st[0] : so[0], so1 = p0 == 0 ? 32u * g.st[1] : so[1];
+            for (int j = 0; j < 6; ++j) so[j] = stoff[ph + j];
+            const uint32_t so0 = first ? stoff[12] : so[0], so1 = first ? stoff[13] : so[1];
             const uint8_t* src = S + 9 * K * cl + b;
             uint8_t* dst = O + L::RUN_PITCH * b + (uint32_t)(run_lo[b] & 15) + 26 * cl;
             Planes acc{0, 0};
@@ -261,8 +311,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
         }
         __syncthreads();
         // ---- phase C: nine band-major runs -> global (A.6 assembly: offset 52 + 26*(cw_base_b + c))
-#pragma unroll 1
-        for (int b = 0; b < 9; ++b) store_run(O + L::RUN_PITCH * b, P.out, run_lo[b], run_lo[b] + 26ull * run_n[b]);
+        store_runs9<L::RUN_PITCH>(O, P.out, run_lo, run_n);
     }
 }
 
@@ -280,12 +329,14 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
     uint8_t* O = smem + L::OFF_O;
     GfTables& sg = *reinterpret_cast<GfTables*>(smem + L::OFF_GF);
     __shared__ uint64_t run_lo[9];
-    __shared__ uint32_t run_n[9];
+    __shared__ uint32_t run_n[9], run_ph[9];
     const int tid = threadIdx.x;
+    __shared__ uint32_t stoff[14];
     {
         const RowTable& T = rs->row[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
         for (int i = tid; i < 26 * kVals; i += FAST_TPB) tab[i] = T.e[i / kVals][i % kVals];
         load_gf(sg, gf);
+        if (tid < 14) stoff[tid] = 32u * (tid < 12 ? g.st[2 + tid % 6] : g.st[tid - 12]);
     }
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
     for (uint64_t tile_id = blockIdx.x; tile_id < total; tile_id += gridDim.x) {
@@ -298,24 +349,24 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
             const uint64_t n = c0 >= g.ncw[tid] ? 0 : ((g.ncw[tid] - c0) < C_TILE ? (g.ncw[tid] - c0) : C_TILE);
             run_lo[tid] = (uint64_t)(in - P.in) + 52 + 26 * (g.cw_base[tid] + c0);
             run_n[tid] = (uint32_t)n;
+            run_ph[tid] = (uint32_t)((26 * (g.cw_base[tid] + c0) + 4) % 6) | (g.cw_base[tid] + c0 == 0 ? 8u : 0u);
         }
         __syncthreads();
         // ---- phase 0: nine runs -> shared
-#pragma unroll 1
-        for (int b = 0; b < 9; ++b)
-            if (run_n[b]) load_run(O + L::RUN_PITCH * b, P.in, run_lo[b], run_lo[b] + 26ull * run_n[b], P.in_stride * (P.n_frames - 1) + 9 * g.n_out);
+        load_runs9<L::RUN_PITCH>(O, P.in, run_lo, run_n, P.in_stride * (P.n_frames - 1) + 9 * g.n_out);
         __syncthreads();
         // ---- phase B: syndrome screen per codeword; dirty ones take BM/Chien/Forney; descramble; 9-band scatter
         for (int cw = tid; cw < L::NCW; cw += FAST_TPB) {
             const int b = cw / C_TILE, cl = cw - b * C_TILE;
             if ((uint32_t)cl >= run_n[b]) continue;
-            const uint64_t c = c0 + cl;
-            const uint64_t p0 = 26 * (g.cw_base[b] + c);
-            const uint32_t ph = (uint32_t)((p0 + 4) % 6);
+            const uint32_t rp = run_ph[b];
+            const uint32_t ph = ((rp & 7) + 2u * (uint32_t)cl) % 6u;
+            const bool first = (rp & 8) && cl == 0;
+            const uint64_t p0 = 26 * (g.cw_base[b] + c0 + cl);
             uint32_t so[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) so[j] = 32u * g.st[2 + (ph + j) % 6];
-            const uint32_t so0 = p0 == 0 ? 32u * g.st[0] : so[0], so1 = p0 == 0 ? 32u * g.st[1] : so[1];
+            for (int j = 0; j < 6; ++j) so[j] = stoff[ph + j];
+            const uint32_t so0 = first ? stoff[12] : so[0], so1 = first ? stoff[13] : so[1];
             const uint8_t* src = O + L::RUN_PITCH * b + (uint32_t)(run_lo[b] & 15) + 26 * cl;
             uint8_t* dst = S + 9 * K * cl + b;
             Planes acc{0, 0};
@@ -331,7 +382,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
                     if (ii < K) dst[9 * ii] = sg.dsc[0][(ii == 0 ? so0 : ii == 1 ? so1 : so[ii % 6]) + s];
                 }
             }
-            const int ci = p0 == 0 ? 6 : (int)ph;
+            const int ci = first ? 6 : (int)ph;
             if (acc.nz != P.chk_nz[ci] || acc.two != P.chk_two[ci]) {
                 // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
                 uint8_t cwd[26], orig[26];
@@ -364,14 +415,16 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
             uint32_t pixrgb[12];
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                // 13 bytes at byte offset 13t
-                auto byte_at = [&](int pos) { return (w[pos >> 2] >> (8 * (pos & 3))) & 0xFF; };
-                uint32_t ww[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    ww[q] = byte_at(13 * t + 4 * q) | (byte_at(13 * t + 4 * q + 1) << 8) | (byte_at(13 * t + 4 * q + 2) << 16) | (byte_at(13 * t + 4 * q + 3) << 24);
+                // 13 bytes at byte offset 13t = word 3t + t/4.. : realign with funnel shifts by 8t bits
+                uint32_t w0, w1, w2, s12;
+                if (t == 0) { w0 = w[0]; w1 = w[1]; w2 = w[2]; s12 = w[3] & 0xFF; }
+                else {
+                    const int q = 3 * t, sh = 8 * t;
+                    w0 = __funnelshift_r(w[q], w[q + 1], sh); w1 = __funnelshift_r(w[q + 1], w[q + 2], sh);
+                    w2 = __funnelshift_r(w[q + 2], w[q + 3], sh); s12 = (w[q + 3] >> sh) & 0xFF;
+                }
                 uint32_t A0, A1, A2;
-                symbols_to_triple(ww[0], ww[1], ww[2], byte_at(13 * t + 12), A0, A1, A2);
+                symbols_to_triple(w0, w1, w2, s12, A0, A1, A2);
                 pixrgb[3 * t] = value_to_rgb(A0);
                 pixrgb[3 * t + 1] = value_to_rgb(A1);
                 pixrgb[3 * t + 2] = value_to_rgb(A2);
@@ -435,6 +488,7 @@ int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
                            uint8_t* out, size_t stride_words, cudaStream_t st)
 {
     if (((uintptr_t)rgb | (uintptr_t)out) & 15) return -1; // 128-bit transfers need 16-byte aligned buffer bases
+    if (n_frames > 1 && (stride_words & 1)) return -1;     // and every frame's body must start on an even byte
     FastParams P{};
     P.in = rgb; P.out = out;
     P.in_stride = 3ull * n_px; P.out_stride = 9ull * stride_words;
@@ -459,6 +513,7 @@ int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
 {
     (void)cfg;
     if (((uintptr_t)rgb | (uintptr_t)in) & 15) return -1;
+    if (n_frames > 1 && (stride_words & 1)) return -1;
     FastParams P{};
     P.in = in; P.out = rgb;
     P.in_stride = 9ull * stride_words; P.out_stride = 3ull * n_px;
