@@ -5,18 +5,21 @@
 //   decode: 9 runs --> syndrome screen (same row tables) --> [dirty codewords: BM/Chien/Forney] --> descramble
 //           --> 9-band transpose back --> 13 trits/px --> dequant --> RGB8
 //
-// One CTA works on a tile of C=52 codewords per band (9*k*52 stream symbols = 108*k pixels): every global
-// access is a 128-bit coalesced transfer of a contiguous run (one RGB run, nine body runs), the band
-// transpose and all table look-ups stay in shared memory, and the grid is persistent (a multiple of the SM
-// count) so the row table is staged once per CTA.  HBM traffic is exactly the algorithmic 3 B/px + 9 B/word.
+// Work unit = a mini-tile of 13 codewords per band (9*k*13 stream symbols = 27*k pixels = 9*k pixel triples),
+// owned by ONE WARP from load to store: the three phases (bridge+regroup, RS+scramble, run copy) are separated
+// by __syncwarp only, so there is no block-level barrier in the steady state and every warp always has work
+// (the first CTA-tiled version spent 47 % of its warp-stall samples in bar.sync, profiles/r01_*).  Every global
+// access is a 128-bit transfer inside a contiguous run (one RGB run, nine body runs of 338 B), the 9-band
+// transpose and all table look-ups stay in shared memory, the grid is persistent (SM count x resident CTAs)
+// so the row table is staged once per CTA, and HBM traffic is exactly the algorithmic 3 B/px + 9 B/word.
 #include "dev.cuh"
 #include "launch.h"
 
 namespace t3c {
 namespace {
 
-constexpr int C_TILE = 52;      // codewords per band per tile (multiple of 26: tile = whole 12-pixel units)
-constexpr int FAST_TPB = 256;
+constexpr int C_MINI = 13;      // codewords per band per mini-tile: 9*k*13 symbols = 9*k whole pixel triples
+constexpr int FAST_TPB = 256, FAST_WARPS = FAST_TPB / 32;
 constexpr uint32_t M27 = 159072863u; // ceil(2^32/27): exact quotient for x < 2^26
 
 struct FastParams {
@@ -26,7 +29,7 @@ struct FastParams {
     uint64_t out_stride;
     uint64_t n_px;          // pixels per frame
     uint64_t px_out;        // decode: pixels to write per frame
-    uint32_t n_tiles;       // tiles per frame
+    uint32_t n_tiles;       // mini-tiles per frame
     uint32_t n_frames;
     uint32_t* status;       // decode: {ok, n_corrected} per frame
     uint32_t chk_nz[7], chk_two[7]; // decode: sum of T_i[13*st_i] per scrambler phase (6) and for p0==0
@@ -34,23 +37,32 @@ struct FastParams {
 
 template <int K> struct Cfg {
     static constexpr int R = 26 - K;
-    static constexpr int UNITS = 9 * K;                 // 12-pixel units per tile
-    static constexpr int PX = 12 * UNITS;               // pixels per tile
+    static constexpr int TRIPLES = 9 * K;               // pixel triples (13 symbols each) per mini-tile
+    static constexpr int PX = 3 * TRIPLES;
     static constexpr int RGB_BYTES = 3 * PX;
-    static constexpr int SYM = 52 * UNITS;              // stream symbols per tile = 9*K*C_TILE
-    static constexpr int RUN = 26 * C_TILE;             // bytes per band run
-    static constexpr int RUN_PITCH = RUN + 24;          // + alignment slack, multiple of 8
-    static constexpr int NCW = 9 * C_TILE;
-    // shared memory carve-up (bytes)
+    static constexpr int SYM = 13 * TRIPLES;            // stream symbols per mini-tile = 9*K*C_MINI
+    static constexpr int RUN = 26 * C_MINI;             // 338 bytes per band run
+    static constexpr int RUN_PITCH = 368;               // >= 15 + RUN, multiple of 16
+    static constexpr int NCW = 9 * C_MINI;
+    // per-warp shared memory: S (symbol stream) | U (RGB run, later reused for the nine body runs) | meta
+    static constexpr int S_BYTES = (SYM + 15) / 16 * 16;
+    static constexpr int RGB_PITCH = (RGB_BYTES + 15 + 15) / 16 * 16 + 16;
+    static constexpr int U_BYTES = RGB_PITCH > 9 * RUN_PITCH ? RGB_PITCH : 9 * RUN_PITCH;
+    static constexpr int META_BYTES = 160;              // run_lo[9] (u64) | run_n[9] | run_ph[9] (u32)
+    static constexpr int WARP_BYTES = S_BYTES + U_BYTES + META_BYTES;
+    // CTA-shared
     static constexpr int OFF_TAB = 0;
     static constexpr int TAB_BYTES = 26 * kVals * 8;
-    static constexpr int OFF_RGB = OFF_TAB + TAB_BYTES;
-    static constexpr int RGB_PITCH = ((RGB_BYTES + 15) / 16) * 16 + 32;
-    static constexpr int OFF_S = OFF_RGB + RGB_PITCH;
-    static constexpr int S_PITCH = ((SYM + 15) / 16) * 16;
-    static constexpr int OFF_O = OFF_S + S_PITCH;
-    static constexpr int OFF_GF = OFF_O + 9 * RUN_PITCH;
-    static constexpr int TOTAL = OFF_GF + ((int)sizeof(GfTables) + 15) / 16 * 16 + 64;
+    static constexpr int OFF_LUT = OFF_TAB + TAB_BYTES; // 3x32 scramble/descramble LUT + stoff[14]
+    static constexpr int LUT_BYTES = 96 + 64;
+    static constexpr int OFF_GF = OFF_LUT + LUT_BYTES;  // decode only: GF(27) tables of the slow path
+    static constexpr int GF_BYTES = ((int)sizeof(GfTables) + 15) / 16 * 16;
+    static constexpr int OFF_PXLUT = OFF_GF + GF_BYTES; // decode only: dequant + colour-matrix products per quantised value
+    static constexpr int PXLUT_BYTES = 256 * 4 + 2 * 88 * 8;
+    static constexpr int OFF_WARP_ENC = OFF_GF;
+    static constexpr int OFF_WARP_DEC = OFF_PXLUT + PXLUT_BYTES;
+    static constexpr int TOTAL_ENC = OFF_WARP_ENC + FAST_WARPS * WARP_BYTES;
+    static constexpr int TOTAL_DEC = OFF_WARP_DEC + FAST_WARPS * WARP_BYTES;
 };
 
 // 13 base-27 digits of three pixel values (39 trits): packed 4+4+4 symbols and the 13th
@@ -113,72 +125,103 @@ __device__ __forceinline__ uint32_t value_to_rgb(uint32_t A)
     return (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
 }
 
-// coalesced copy of a contiguous global byte range into shared memory; smem byte i <-> global byte
-// (g_lo - pad + i) with pad = g_lo % 16, so 16-byte global chunks stay 16-byte aligned in shared memory.
-__device__ __forceinline__ void load_run(uint8_t* s, const uint8_t* __restrict__ gbase, uint64_t g_lo, uint64_t g_hi, uint64_t g_limit)
+// body runs start at even byte offsets (the launchers only take the fast path when every frame does)
+__device__ __forceinline__ void store2(uint8_t* p, uint32_t lo, uint32_t hi) { *reinterpret_cast<uint16_t*>(p) = (uint16_t)(lo | (hi << 8)); }
+__device__ __forceinline__ uint32_t load2(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
+
+// pixel value -> RGB8 through per-component tables holding exactly the float32 terms of ycbcr_to_rgb
+// (IMG:57-66): y, (0.344136f*cb, 1.772f*cb), (1.402f*cr, 0.714136f*cr); the sums keep the reference's order.
+struct PxLut { float y[256]; float2 b[88]; float2 r[88]; };
+__device__ __forceinline__ uint32_t value_to_rgb_lut(const PxLut& T, uint32_t A)
 {
-    const uint64_t a0 = g_lo & ~15ull;
-    const uint32_t nchunk = (uint32_t)((g_hi - a0 + 15) >> 4);
-    for (uint32_t c = threadIdx.x; c < nchunk; c += FAST_TPB) {
-        const uint64_t ga = a0 + 16ull * c;
-        if (ga + 16 <= g_limit) {
-            *reinterpret_cast<uint4*>(s + 16 * c) = __ldg(reinterpret_cast<const uint4*>(gbase + ga));
-        } else {
-            for (int i = 0; i < 16; ++i) s[16 * c + i] = ga + i < g_limit ? gbase[ga + i] : 0;
-        }
-    }
-}
-// coalesced copy shared -> global of bytes [g_lo, g_hi); same alignment convention as load_run
-__device__ __forceinline__ void store_run(const uint8_t* s, uint8_t* __restrict__ gbase, uint64_t g_lo, uint64_t g_hi)
-{
-    if (g_hi <= g_lo) return;
-    const uint64_t a0 = g_lo & ~15ull;
-    const uint32_t nchunk = (uint32_t)((g_hi - a0 + 15) >> 4);
-    for (uint32_t c = threadIdx.x; c < nchunk; c += FAST_TPB) {
-        const uint64_t ga = a0 + 16ull * c;
-        if (ga >= g_lo && ga + 16 <= g_hi) {
-            *reinterpret_cast<uint4*>(gbase + ga) = *reinterpret_cast<const uint4*>(s + 16 * c);
-        } else {
-            for (int i = 0; i < 16; ++i) if (ga + i >= g_lo && ga + i < g_hi) gbase[ga + i] = s[16 * c + i];
-        }
-    }
+    const uint32_t q = A / 243u, Yq = A - 243u * q, ur = min(q / 81u, 87u), ub = q - 81u * (q / 81u);
+    const float y = T.y[Yq];
+    const float2 tb = T.b[ub], tr = T.r[ur];
+    const float r = __fadd_rn(y, tr.x);
+    const float g = __fsub_rn(__fsub_rn(y, tb.x), tr.y);
+    const float b = __fadd_rn(y, tb.y);
+    // clamp(round-half-away(x),0,255) == round(clamp(x,0,255)): FADD.RM against 2^22+0.5 leaves 2*value in the low bits
+    const uint32_t R = (uint32_t)__float_as_int(__fadd_rd(fminf(fmaxf(r, 0.0f), 255.0f), 4194304.5f)) >> 1;
+    const uint32_t G = (uint32_t)__float_as_int(__fadd_rd(fminf(fmaxf(g, 0.0f), 255.0f), 4194304.5f)) >> 1;
+    const uint32_t B = (uint32_t)__float_as_int(__fadd_rd(fminf(fmaxf(b, 0.0f), 255.0f), 4194304.5f)) >> 1;
+    return __byte_perm(__byte_perm(R, G, 0x0040), B, 0x7410) & 0x00FFFFFFu; // R | G<<8 | B<<16
 }
 
-// the nine band runs of a tile, shared -> global, flattened over (run, 16-byte chunk); 32-bit index math,
-// 128-bit stores for interior chunks, 32-bit (or byte) stores only in the two boundary chunks of a run
-template <int PITCH>
-__device__ __forceinline__ void store_runs9(const uint8_t* O, uint8_t* __restrict__ gbase, const uint64_t* run_lo, const uint32_t* run_n)
+struct WarpMeta { uint64_t run_lo[9]; uint32_t run_n[9]; uint32_t run_ph[9]; };
+static_assert(sizeof(WarpMeta) <= 160, "meta");
+
+// per-warp: where the nine body runs of mini-tile `tile` of a frame live (A.6: 52 + 26*(cw_base_b + c))
+__device__ __forceinline__ void setup_runs(WarpMeta& m, const Geom& g, uint64_t frame_off, uint32_t tile, int lane)
 {
-    constexpr int CH = PITCH / 16;
-    for (int j = threadIdx.x; j < 9 * CH; j += FAST_TPB) {
-        const int b = j / CH, c = j - b * CH;
-        const int len = 26 * (int)run_n[b];
-        const uint64_t lo = run_lo[b];
-        const int pad = (int)(lo & 15), r0 = 16 * c - pad, r1 = r0 + 16;
-        if (r1 <= 0 || r0 >= len) continue;
-        uint8_t* gp = gbase + (lo - pad) + 16 * c;
-        const uint8_t* sp = O + PITCH * b + 16 * c;
-        if (r0 >= 0 && r1 <= len) {
-            *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
-        } else {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int a = r0 + 4 * w;
-                if (a >= 0 && a + 4 <= len) *reinterpret_cast<uint32_t*>(gp + 4 * w) = *reinterpret_cast<const uint32_t*>(sp + 4 * w);
-                else
-                    for (int i = 0; i < 4; ++i) if (a + i >= 0 && a + i < len) gp[4 * w + i] = sp[4 * w + i];
-            }
-        }
+    if (lane < 9) {
+        const uint64_t c0 = (uint64_t)C_MINI * tile;
+        const uint64_t n = c0 >= g.ncw[lane] ? 0 : ((g.ncw[lane] - c0) < C_MINI ? (g.ncw[lane] - c0) : C_MINI);
+        const uint64_t cwi = g.cw_base[lane] + c0;
+        m.run_lo[lane] = frame_off + 52 + 26 * cwi;
+        m.run_n[lane] = (uint32_t)n;
+        m.run_ph[lane] = (uint32_t)((26 * cwi + 4) % 6) | (cwi == 0 ? 8u : 0u); // scrambler phase of the run's first symbol
+    }
+}
+// a contiguous global byte range -> shared; smem byte i <-> global byte (g_lo - g_lo%16 + i)
+__device__ __forceinline__ void warp_load_run(uint8_t* s, const uint8_t* __restrict__ gbase, uint64_t g_lo, uint64_t g_hi, uint64_t g_limit, int lane)
+{
+    const uint64_t a0 = g_lo & ~15ull;
+    const int nchunk = (int)((g_hi - a0 + 15) >> 4);
+    for (int c = lane; c < nchunk; c += 32) {
+        const uint64_t ga = a0 + 16ull * c;
+        if (ga + 16 <= g_limit) *reinterpret_cast<uint4*>(s + 16 * c) = __ldg(reinterpret_cast<const uint4*>(gbase + ga));
+        else
+            for (int i = 0; i < 16; ++i) s[16 * c + i] = ga + i < g_limit ? gbase[ga + i] : 0;
+    }
+}
+// shared -> global of one run [g_lo, g_lo+len): 128-bit stores for the interior 16-byte chunks, and the (at most
+// 15+15) edge bytes written one byte per lane, so that no lane ever walks an edge chunk alone
+__device__ __forceinline__ void warp_store_run(const uint8_t* s, uint8_t* __restrict__ gbase, uint64_t g_lo, int len, int lane)
+{
+    if (len <= 0) return;
+    const int pad = (int)(g_lo & 15);
+    uint8_t* g0 = gbase + (g_lo - pad);               // 16-byte aligned; smem byte i <-> g0[i]
+    const int first_full = pad ? 1 : 0, end = pad + len, last_full = end >> 4; // chunks [first_full, last_full) are interior
+    for (int c = first_full + lane; c < last_full; c += 32) *reinterpret_cast<uint4*>(g0 + 16 * c) = *reinterpret_cast<const uint4*>(s + 16 * c);
+    {   // head bytes [pad, min(16,end)) and tail bytes [max(16*last_full, pad), end)
+        const int hi = lane < 16 ? lane : 16 * last_full + (lane - 16);
+        const bool in_head = lane < 16 && pad && hi >= pad && hi < end && hi < 16;
+        const bool in_tail = lane >= 16 && hi >= pad && hi < end && (last_full >= first_full) && !(last_full == 0 && pad);
+        if (in_head || in_tail) g0[hi] = s[hi];
     }
 }
 template <int PITCH>
-__device__ __forceinline__ void load_runs9(uint8_t* O, const uint8_t* __restrict__ gbase, const uint64_t* run_lo, const uint32_t* run_n, uint64_t g_limit)
+__device__ __forceinline__ void warp_store_runs9(const uint8_t* O, uint8_t* __restrict__ gbase, const WarpMeta& m, int lane)
 {
     constexpr int CH = PITCH / 16;
-    for (int j = threadIdx.x; j < 9 * CH; j += FAST_TPB) {
+    // interior chunks of all nine runs, flattened
+    for (int j = lane; j < 9 * CH; j += 32) {
         const int b = j / CH, c = j - b * CH;
-        const int len = 26 * (int)run_n[b];
-        const uint64_t lo = run_lo[b];
+        const int len = 26 * (int)m.run_n[b];
+        const uint64_t lo = m.run_lo[b];
+        const int pad = (int)(lo & 15), r0 = 16 * c - pad;
+        if (r0 < 0 || r0 + 16 > len) continue;
+        *reinterpret_cast<uint4*>(gbase + (lo - pad) + 16 * c) = *reinterpret_cast<const uint4*>(O + PITCH * b + 16 * c);
+    }
+    // edge bytes: 9 runs x (16 head + 16 tail) byte slots, one per lane
+    for (int e = lane; e < 9 * 32; e += 32) {
+        const int b = e >> 5, i = e & 15, tail = (e >> 4) & 1;
+        const int len = 26 * (int)m.run_n[b];
+        const uint64_t lo = m.run_lo[b];
+        const int pad = (int)(lo & 15), end = pad + len;
+        const int pos = tail ? (end & ~15) + i : i;                  // byte position inside the padded run
+        const bool ok = len > 0 && pos >= pad && pos < end && (tail ? ((end & 15) != 0 && !(pad && (end >> 4) == 0)) : pad != 0);
+        if (ok) gbase[(lo - pad) + pos] = O[PITCH * b + pos];
+    }
+}
+template <int PITCH>
+__device__ __forceinline__ void warp_load_runs9(uint8_t* O, const uint8_t* __restrict__ gbase, const WarpMeta& m, uint64_t g_limit, int lane)
+{
+    constexpr int CH = PITCH / 16;
+    for (int j = lane; j < 9 * CH; j += 32) {
+        const int b = j / CH, c = j - b * CH;
+        const int len = 26 * (int)m.run_n[b];
+        const uint64_t lo = m.run_lo[b];
         const int pad = (int)(lo & 15), r0 = 16 * c - pad;
         if (r0 + 16 <= 0 || r0 >= len) continue;
         const uint64_t ga = (lo - pad) + 16 * c;
@@ -189,10 +232,6 @@ __device__ __forceinline__ void load_runs9(uint8_t* O, const uint8_t* __restrict
     }
 }
 
-// body runs start at even byte offsets (the launchers only take the fast path when every frame does)
-__device__ __forceinline__ void store2(uint8_t* p, uint32_t lo, uint32_t hi) { *reinterpret_cast<uint16_t*>(p) = (uint16_t)(lo | (hi << 8)); }
-__device__ __forceinline__ uint32_t load2(const uint8_t* p) { return *reinterpret_cast<const uint16_t*>(p); }
-
 // =============================================================================================
 // encode
 // =============================================================================================
@@ -201,106 +240,94 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
 {
     using L = Cfg<K>;
     extern __shared__ __align__(16) uint8_t smem[];
-    uint64_t* tab = reinterpret_cast<uint64_t*>(smem + L::OFF_TAB);
-    uint8_t* s_rgb = smem + L::OFF_RGB;
-    uint8_t* S = smem + L::OFF_S;
-    uint8_t* O = smem + L::OFF_O;
-    uint8_t* scr = smem + L::OFF_GF; // 3 x 32 scramble look-up
-    __shared__ uint64_t run_lo[9];
-    __shared__ uint32_t run_n[9], run_ph[9];
-    const int tid = threadIdx.x;
-    __shared__ uint32_t stoff[14]; // 32*st for phase index 0..11 (two periods) and for body indices 0,1
+    const uint64_t* tab = reinterpret_cast<const uint64_t*>(smem + L::OFF_TAB);
+    const uint8_t* scr = smem + L::OFF_LUT;                               // 3 x 32 scramble look-up
+    const uint32_t* stoff = reinterpret_cast<const uint32_t*>(smem + L::OFF_LUT + 96); // 32*st: phase 0..11, body index 0,1
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* S = smem + L::OFF_WARP_ENC + warp * L::WARP_BYTES;
+    uint8_t* U = S + L::S_BYTES;
+    WarpMeta& meta = *reinterpret_cast<WarpMeta*>(U + L::U_BYTES);
     {
         const RowTable& T = rs->row[g.arith][(24 - K) / 2];
-        for (int i = tid; i < K * kVals; i += FAST_TPB) tab[i] = T.e[i / kVals][i % kVals];
-        if (tid < 96) scr[tid] = gf->scr[tid / 32][tid % 32];
-        if (tid < 14) stoff[tid] = 32u * (tid < 12 ? g.st[2 + tid % 6] : g.st[tid - 12]);
+        uint64_t* t = reinterpret_cast<uint64_t*>(smem + L::OFF_TAB);
+        for (int i = tid; i < K * kVals; i += FAST_TPB) t[i] = T.e[i / kVals][i % kVals];
+        if (tid < 96) smem[L::OFF_LUT + tid] = gf->scr[tid / 32][tid % 32];
+        if (tid < 14) reinterpret_cast<uint32_t*>(smem + L::OFF_LUT + 96)[tid] = 32u * (tid < 12 ? g.st[2 + tid % 6] : g.st[tid - 12]);
     }
+    __syncthreads(); // the only block-level barrier: tables staged
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
-    for (uint64_t tile_id = blockIdx.x; tile_id < total; tile_id += gridDim.x) {
-        const uint32_t f = (uint32_t)(tile_id / P.n_tiles), tile = (uint32_t)(tile_id - (uint64_t)f * P.n_tiles);
-        const uint8_t* rgb = P.in + P.in_stride * f;
-        uint8_t* out = P.out + P.out_stride * f;
-        // ---- phase 0: the tile's RGB run -> shared
+    const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
+    for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
+        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = (uint32_t)(mt - (uint64_t)f * P.n_tiles);
         const uint64_t px0 = (uint64_t)L::PX * tile;
-        const uint64_t g_lo = (uint64_t)(rgb - P.in) + 3 * px0;
-        uint64_t g_hi = (uint64_t)(rgb - P.in) + 3 * (px0 + L::PX < P.n_px ? px0 + L::PX : P.n_px);
-        if (g_hi < g_lo) g_hi = g_lo;
-        const uint32_t pad = (uint32_t)(g_lo & 15);
-        __syncthreads(); // previous tile's phase C is done with O; tab/scr visible
-        if (tid < 9) { // the nine output runs of this tile, as byte offsets from P.out (A.6: 52 + 26*(cw_base_b + c))
-            const uint64_t c0 = (uint64_t)C_TILE * tile;
-            const uint64_t n = c0 >= g.ncw[tid] ? 0 : ((g.ncw[tid] - c0) < C_TILE ? (g.ncw[tid] - c0) : C_TILE);
-            run_lo[tid] = (uint64_t)(out - P.out) + 52 + 26 * (g.cw_base[tid] + c0);
-            run_n[tid] = (uint32_t)n;
-            run_ph[tid] = (uint32_t)((26 * (g.cw_base[tid] + c0) + 4) % 6) | (g.cw_base[tid] + c0 == 0 ? 8u : 0u);
-        }
-        load_run(s_rgb, P.in, g_lo, g_hi, P.in_stride * P.n_frames);
-        __syncthreads();
-        // ---- phase A: 12 pixels -> 52 stream symbols per thread (A.1 regroup fused with the bridge)
-        for (int u = tid; u < L::UNITS; u += FAST_TPB) {
-            const uint8_t* me = s_rgb + pad + 36 * u;
-            const uint32_t sh = (uint32_t)((uintptr_t)me & 3) * 8;
-            const uint32_t* mw = reinterpret_cast<const uint32_t*>((uintptr_t)me & ~(uintptr_t)3);
-            uint32_t w[10];
+        const uint64_t in_off = P.in_stride * f;
+        const uint64_t g_lo = in_off + 3 * (px0 < P.n_px ? px0 : P.n_px);
+        const uint64_t g_hi = in_off + 3 * (px0 + L::PX < P.n_px ? px0 + L::PX : P.n_px);
+        const int pad = (int)(g_lo & 15);
+        // pixels of this mini-tile that exist / that are the odd tail's default partner (OLD:730)
+        const int lim = px0 >= P.n_px ? 0 : (P.n_px - px0 < (uint64_t)L::PX ? (int)(P.n_px - px0) : L::PX);
+        const int lim2 = px0 >= 2 * g.n_words ? 0 : (2 * g.n_words - px0 < (uint64_t)L::PX ? (int)(2 * g.n_words - px0) : L::PX);
+        setup_runs(meta, g, P.out_stride * f, tile, lane);
+        warp_load_run(U, P.in, g_lo, g_hi, P.in_stride * P.n_frames, lane);
+        __syncwarp();
+        // ---- phase A: two pixel triples (18 bytes) -> 26 stream symbols per lane iteration (bridge + A.1 regroup)
+        for (int u = lane; u < L::TRIPLES / 2; u += 32) {
+            const uint32_t a = (uint32_t)pad + 18u * (uint32_t)u;
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
+            const uint32_t sh = (a & 3u) * 8u;
+            uint32_t x[5];
 #pragma unroll
-            for (int j = 0; j < 10; ++j) w[j] = mw[j];
+            for (int j = 0; j < 5; ++j) x[j] = mw[j];
+            uint32_t y[5]; // the 18 bytes, word aligned
 #pragma unroll
-            for (int j = 0; j < 9; ++j) w[j] = __funnelshift_r(w[j], w[j + 1], sh); // the 36 bytes, now word aligned
-            uint32_t A[12];
+            for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+            y[4] = x[4] >> sh;
+            uint32_t A[6];
 #pragma unroll
-            for (int p = 0; p < 12; ++p) {
-                // bytes 3p,3p+1,3p+2 of the (unaligned) 36-byte group
-                float ch[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const int bi = 3 * p + c;
-                    ch[c] = byte_to_float(w[bi >> 2], bi & 3);
-                }
-                const uint64_t pix = px0 + 12ull * u + p;
-                uint32_t v = rgb_to_value(ch[0], ch[1], ch[2]);
-                if (pix >= P.n_px) v = pix < 2 * g.n_words ? 797040u : 0u; // odd tail pairs with PixelYCbCrQuant{} (OLD:730); beyond: zero trits
-                A[p] = v;
+            for (int p = 0; p < 6; ++p) {
+                const int q = 3 * p;
+                A[p] = rgb_to_value(byte_to_float(y[q >> 2], q & 3), byte_to_float(y[(q + 1) >> 2], (q + 1) & 3), byte_to_float(y[(q + 2) >> 2], (q + 2) & 3));
             }
-            uint32_t o[13];
-            {
-                uint32_t w0, w1, w2, s12;
-                triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);       // bytes 0..12
-                o[0] = w0; o[1] = w1; o[2] = w2; o[3] = s12;
-                triple_to_symbols(A[3], A[4], A[5], w0, w1, w2, s12);       // bytes 13..25
-                o[3] |= w0 << 8; o[4] = __funnelshift_l(w0, w1, 8); o[5] = __funnelshift_l(w1, w2, 8); o[6] = __funnelshift_l(w2, s12, 8);
-                triple_to_symbols(A[6], A[7], A[8], w0, w1, w2, s12);       // bytes 26..38
-                o[6] |= w0 << 16; o[7] = __funnelshift_l(w0, w1, 16); o[8] = __funnelshift_l(w1, w2, 16); o[9] = __funnelshift_l(w2, s12, 16);
-                triple_to_symbols(A[9], A[10], A[11], w0, w1, w2, s12);     // bytes 39..51
-                o[9] |= w0 << 24; o[10] = __funnelshift_l(w0, w1, 24); o[11] = __funnelshift_l(w1, w2, 24); o[12] = __funnelshift_l(w2, s12, 24);
-            }
-            uint32_t* dst = reinterpret_cast<uint32_t*>(S) + 13 * u;
+            if (lim < L::PX) { // ragged end of the frame (warp-uniform)
 #pragma unroll
-            for (int j = 0; j < 13; ++j) dst[j] = o[j];
+                for (int p = 0; p < 6; ++p) { const int lp = 6 * u + p; if (lp >= lim) A[p] = lp < lim2 ? 797040u : 0u; }
+            }
+            uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
+            triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
+            triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
+            uint16_t* d = reinterpret_cast<uint16_t*>(S + 26 * u); // 13 halfwords (STS.U16 keeps the low 16 bits)
+            d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
+            d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
+            d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
+            d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
         }
-        __syncthreads();
-        // ---- phase B: one codeword per thread iteration: 9-band gather (A.3), RS parity, scramble (A.4)
-        for (int cw = tid; cw < L::NCW; cw += FAST_TPB) {
-            const int b = cw / C_TILE, cl = cw - b * C_TILE;
-            if ((uint32_t)cl >= run_n[b]) continue;
-            const uint32_t rp = run_ph[b];
+        __syncwarp();
+        // ---- phase B: one codeword per lane iteration: 9-band gather (A.3), RS parity, scramble (A.4)
+        for (int cw = lane; cw < L::NCW; cw += 32) {
+            const int b = cw / C_MINI, cl = cw - b * C_MINI;
+            if ((uint32_t)cl >= meta.run_n[b]) continue;
+            const uint32_t rp = meta.run_ph[b];
             const uint32_t ph = ((rp & 7) + 2u * (uint32_t)cl) % 6u;   // (p0 + 4) % 6 with p0 = 26*(cw_base_b + c)
             const bool first = (rp & 8) && cl == 0;                    // the block at body index 0 (LCG transient)
-            uint32_t so[6]; // scramble row offset for symbol i: so[i%6]
+            uint32_t so[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) so[j] = stoff[ph + j];
             const uint32_t so0 = first ? stoff[12] : so[0], so1 = first ? stoff[13] : so[1];
             const uint8_t* src = S + 9 * K * cl + b;
-            uint8_t* dst = O + L::RUN_PITCH * b + (uint32_t)(run_lo[b] & 15) + 26 * cl;
-            Planes acc{0, 0};
+            uint8_t* dst = U + L::RUN_PITCH * b + (uint32_t)(meta.run_lo[b] & 15) + 26 * cl;
+            uint32_t d[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) d[i] = src[9 * i];
+            Planes acc{0, 0}, acc2{0, 0};
             uint32_t pair = 0;
 #pragma unroll
             for (int i = 0; i < K; ++i) {
-                const uint32_t d = src[9 * i];
-                gf3_add(acc, tab[i * kVals + d]);
-                const uint32_t sc = scr[(i == 0 ? so0 : i == 1 ? so1 : so[i % 6]) + d];
+                const uint64_t e = tab[i * kVals + d[i]];
+                if (i & 1) gf3_add(acc2, e); else gf3_add(acc, e);
+                const uint32_t sc = scr[(i == 0 ? so0 : i == 1 ? so1 : so[i % 6]) + d[i]];
                 if (i & 1) store2(dst + i - 1, pair, sc); else pair = sc;
             }
+            gf3_add(acc, acc2.nz, acc2.two);
             const uint32_t lo = planes_to_sym4_lo(acc), hi = planes_to_sym4_hi(acc);
 #pragma unroll
             for (int j = 0; j < L::R; ++j) {
@@ -309,9 +336,10 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
                 if (j & 1) store2(dst + K + j - 1, pair, sc); else pair = sc;
             }
         }
-        __syncthreads();
-        // ---- phase C: nine band-major runs -> global (A.6 assembly: offset 52 + 26*(cw_base_b + c))
-        store_runs9<L::RUN_PITCH>(O, P.out, run_lo, run_n);
+        __syncwarp();
+        // ---- phase C: nine band-major runs -> global
+        warp_store_runs9<L::RUN_PITCH>(U, P.out, meta, lane);
+        __syncwarp();
     }
 }
 
@@ -323,73 +351,72 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
 {
     using L = Cfg<K>;
     extern __shared__ __align__(16) uint8_t smem[];
-    uint64_t* tab = reinterpret_cast<uint64_t*>(smem + L::OFF_TAB);
-    uint8_t* s_rgb = smem + L::OFF_RGB;
-    uint8_t* S = smem + L::OFF_S;
-    uint8_t* O = smem + L::OFF_O;
+    const uint64_t* tab = reinterpret_cast<const uint64_t*>(smem + L::OFF_TAB);
+    const uint8_t* dsc = smem + L::OFF_LUT;
+    const uint32_t* stoff = reinterpret_cast<const uint32_t*>(smem + L::OFF_LUT + 96);
     GfTables& sg = *reinterpret_cast<GfTables*>(smem + L::OFF_GF);
-    __shared__ uint64_t run_lo[9];
-    __shared__ uint32_t run_n[9], run_ph[9];
-    const int tid = threadIdx.x;
-    __shared__ uint32_t stoff[14];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* S = smem + L::OFF_WARP_DEC + warp * L::WARP_BYTES;
+    uint8_t* U = S + L::S_BYTES;
+    WarpMeta& meta = *reinterpret_cast<WarpMeta*>(U + L::U_BYTES);
     {
         const RowTable& T = rs->row[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
-        for (int i = tid; i < 26 * kVals; i += FAST_TPB) tab[i] = T.e[i / kVals][i % kVals];
+        uint64_t* t = reinterpret_cast<uint64_t*>(smem + L::OFF_TAB);
+        for (int i = tid; i < 26 * kVals; i += FAST_TPB) t[i] = T.e[i / kVals][i % kVals];
+        if (tid < 96) smem[L::OFF_LUT + tid] = gf->dsc[tid / 32][tid % 32];
+        if (tid < 14) reinterpret_cast<uint32_t*>(smem + L::OFF_LUT + 96)[tid] = 32u * (tid < 12 ? g.st[2 + tid % 6] : g.st[tid - 12]);
         load_gf(sg, gf);
-        if (tid < 14) stoff[tid] = 32u * (tid < 12 ? g.st[2 + tid % 6] : g.st[tid - 12]);
-    }
-    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
-    for (uint64_t tile_id = blockIdx.x; tile_id < total; tile_id += gridDim.x) {
-        const uint32_t f = (uint32_t)(tile_id / P.n_tiles), tile = (uint32_t)(tile_id - (uint64_t)f * P.n_tiles);
-        const uint8_t* in = P.in + P.in_stride * f;
-        uint8_t* rgb = P.out + P.out_stride * f;
-        const uint64_t c0 = (uint64_t)C_TILE * tile;
-        __syncthreads();
-        if (tid < 9) {
-            const uint64_t n = c0 >= g.ncw[tid] ? 0 : ((g.ncw[tid] - c0) < C_TILE ? (g.ncw[tid] - c0) : C_TILE);
-            run_lo[tid] = (uint64_t)(in - P.in) + 52 + 26 * (g.cw_base[tid] + c0);
-            run_n[tid] = (uint32_t)n;
-            run_ph[tid] = (uint32_t)((26 * (g.cw_base[tid] + c0) + 4) % 6) | (g.cw_base[tid] + c0 == 0 ? 8u : 0u);
+        PxLut& W = *reinterpret_cast<PxLut*>(smem + L::OFF_PXLUT);
+        if (tid < 256) W.y[tid] = (float)dequant_y(tid);
+        if (tid < 88) {
+            const float c = __fsub_rn((float)dequant_c(tid - 40), 128.0f);
+            W.b[tid] = make_float2(__fmul_rn(0.344136f, c), __fmul_rn(1.772f, c));
+            W.r[tid] = make_float2(__fmul_rn(1.402f, c), __fmul_rn(0.714136f, c));
         }
-        __syncthreads();
-        // ---- phase 0: nine runs -> shared
-        load_runs9<L::RUN_PITCH>(O, P.in, run_lo, run_n, P.in_stride * (P.n_frames - 1) + 9 * g.n_out);
-        __syncthreads();
+    }
+    __syncthreads();
+    const PxLut& pxlut = *reinterpret_cast<const PxLut*>(smem + L::OFF_PXLUT);
+    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
+    const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
+    const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
+    for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
+        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = (uint32_t)(mt - (uint64_t)f * P.n_tiles);
+        setup_runs(meta, g, P.in_stride * f, tile, lane);
+        __syncwarp();
+        warp_load_runs9<L::RUN_PITCH>(U, P.in, meta, in_limit, lane);
+        __syncwarp();
         // ---- phase B: syndrome screen per codeword; dirty ones take BM/Chien/Forney; descramble; 9-band scatter
-        for (int cw = tid; cw < L::NCW; cw += FAST_TPB) {
-            const int b = cw / C_TILE, cl = cw - b * C_TILE;
-            if ((uint32_t)cl >= run_n[b]) continue;
-            const uint32_t rp = run_ph[b];
+        for (int cw = lane; cw < L::NCW; cw += 32) {
+            const int b = cw / C_MINI, cl = cw - b * C_MINI;
+            if ((uint32_t)cl >= meta.run_n[b]) continue;
+            const uint32_t rp = meta.run_ph[b];
             const uint32_t ph = ((rp & 7) + 2u * (uint32_t)cl) % 6u;
             const bool first = (rp & 8) && cl == 0;
-            const uint64_t p0 = 26 * (g.cw_base[b] + c0 + cl);
             uint32_t so[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) so[j] = stoff[ph + j];
             const uint32_t so0 = first ? stoff[12] : so[0], so1 = first ? stoff[13] : so[1];
-            const uint8_t* src = O + L::RUN_PITCH * b + (uint32_t)(run_lo[b] & 15) + 26 * cl;
+            const uint8_t* src = U + L::RUN_PITCH * b + (uint32_t)(meta.run_lo[b] & 15) + 26 * cl;
             uint8_t* dst = S + 9 * K * cl + b;
-            Planes acc{0, 0};
+            Planes acc{0, 0}, acc2{0, 0};
 #pragma unroll
             for (int i = 0; i < 26; i += 2) {
                 const uint32_t two = load2(src + i);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int ii = i + h;
-                    uint32_t s = (two >> (8 * h)) & 0xFF;
-                    if (s >= 27) s %= 27; // out-of-alphabet bytes read as their low three trits, like unpack3 (OLD:28-31)
-                    gf3_add(acc, tab[ii * kVals + s]);
-                    if (ii < K) dst[9 * ii] = sg.dsc[0][(ii == 0 ? so0 : ii == 1 ? so1 : so[ii % 6]) + s];
-                }
+                uint32_t s0 = two & 0xFF, s1 = two >> 8;
+                if (s0 >= 27) s0 %= 27; // out-of-alphabet bytes read as their low three trits, like unpack3 (OLD:28-31)
+                if (s1 >= 27) s1 %= 27;
+                gf3_add(acc, tab[i * kVals + s0]);
+                gf3_add(acc2, tab[(i + 1) * kVals + s1]);
+                if (i < K) dst[9 * i] = dsc[(i == 0 ? so0 : so[i % 6]) + s0];
+                if (i + 1 < K) dst[9 * (i + 1)] = dsc[(i == 0 ? so1 : so[(i + 1) % 6]) + s1];
             }
+            gf3_add(acc, acc2.nz, acc2.two);
             const int ci = first ? 6 : (int)ph;
             if (acc.nz != P.chk_nz[ci] || acc.two != P.chk_two[ci]) {
                 // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
+                const uint64_t p0 = 26 * (g.cw_base[b] + (uint64_t)C_MINI * tile + cl);
                 uint8_t cwd[26], orig[26];
-                for (int i = 0; i < 26; ++i) {
-                    const uint32_t st = scr_state(g, p0 + i);
-                    cwd[i] = orig[i] = sg.dsc[st][src[i] % 27];
-                }
+                for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = sg.dsc[scr_state(g, p0 + i)][src[i] % 27];
                 if (!rs_decode_thread(sg, cwd, K, true)) {
                     atomicExch(&P.status[2 * f], 0u);
                 } else {
@@ -400,77 +427,82 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
                 }
             }
         }
-        __syncthreads();
-        // ---- phase A: 52 stream symbols -> 12 pixels -> RGB8 into the staging run
+        __syncwarp();
+        // ---- phase A: 13 stream symbols -> one pixel triple -> 9 RGB bytes per lane iteration
         const uint64_t px0 = (uint64_t)L::PX * tile;
-        const uint64_t g_lo = (uint64_t)(rgb - P.out) + 3 * px0;
-        const uint64_t px_hi = px0 + L::PX < P.px_out ? px0 + L::PX : P.px_out;
-        const uint64_t g_hi = (uint64_t)(rgb - P.out) + 3 * (px_hi > px0 ? px_hi : px0);
+        const uint64_t out_off = P.out_stride * f;
+        const uint64_t g_lo = out_off + 3 * (px0 < P.px_out ? px0 : P.px_out);
+        const int len = px0 >= P.px_out ? 0 : 3 * (int)(P.px_out - px0 < (uint64_t)L::PX ? P.px_out - px0 : L::PX);
         const uint32_t pad = (uint32_t)(g_lo & 15);
-        for (int u = tid; u < L::UNITS; u += FAST_TPB) {
-            const uint32_t* srcw = reinterpret_cast<const uint32_t*>(S) + 13 * u;
-            uint32_t w[13];
+        for (int u = lane; u < L::TRIPLES / 2; u += 32) {
+            const uint32_t a = 26u * (uint32_t)u;
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+            const uint32_t sh = (a & 2u) * 8u;
+            uint32_t x[7];
 #pragma unroll
-            for (int j = 0; j < 13; ++j) w[j] = srcw[j];
-            uint32_t pixrgb[12];
+            for (int j = 0; j < 7; ++j) x[j] = mw[j];
+            uint32_t y[7]; // the 26 symbols, word aligned
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                // 13 bytes at byte offset 13t = word 3t + t/4.. : realign with funnel shifts by 8t bits
-                uint32_t w0, w1, w2, s12;
-                if (t == 0) { w0 = w[0]; w1 = w[1]; w2 = w[2]; s12 = w[3] & 0xFF; }
-                else {
-                    const int q = 3 * t, sh = 8 * t;
-                    w0 = __funnelshift_r(w[q], w[q + 1], sh); w1 = __funnelshift_r(w[q + 1], w[q + 2], sh);
-                    w2 = __funnelshift_r(w[q + 2], w[q + 3], sh); s12 = (w[q + 3] >> sh) & 0xFF;
-                }
-                uint32_t A0, A1, A2;
-                symbols_to_triple(w0, w1, w2, s12, A0, A1, A2);
-                pixrgb[3 * t] = value_to_rgb(A0);
-                pixrgb[3 * t + 1] = value_to_rgb(A1);
-                pixrgb[3 * t + 2] = value_to_rgb(A2);
-            }
-            uint8_t* me = s_rgb + pad + 36 * u;
-            if ((pad & 3) == 0) {
-                uint32_t* mw = reinterpret_cast<uint32_t*>(me);
+            for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+            y[6] = x[6] >> sh;
+            uint32_t A[6];
+            symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+            symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+            uint32_t p[6];
 #pragma unroll
-                for (int q = 0; q < 3; ++q) { // 4 pixels = 12 bytes = 3 words
-                    const uint32_t a = pixrgb[4 * q], b2 = pixrgb[4 * q + 1], c2 = pixrgb[4 * q + 2], d = pixrgb[4 * q + 3];
-                    mw[3 * q] = a | (b2 << 24);
-                    mw[3 * q + 1] = (b2 >> 8) | (c2 << 16);
-                    mw[3 * q + 2] = (c2 >> 16) | (d << 8);
+            for (int q = 0; q < 6; ++q) p[q] = value_to_rgb_lut(pxlut, A[q]);
+            uint8_t* d = U + pad + 18 * u;
+            if ((pad & 1) == 0) {
+                uint16_t* dh = reinterpret_cast<uint16_t*>(d);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { // two pixels = three halfwords
+                    dh[3 * q] = (uint16_t)p[2 * q];
+                    dh[3 * q + 1] = (uint16_t)((p[2 * q] >> 16) | (p[2 * q + 1] << 8));
+                    dh[3 * q + 2] = (uint16_t)(p[2 * q + 1] >> 8);
                 }
             } else {
 #pragma unroll
-                for (int p = 0; p < 12; ++p) { me[3 * p] = (uint8_t)pixrgb[p]; me[3 * p + 1] = (uint8_t)(pixrgb[p] >> 8); me[3 * p + 2] = (uint8_t)(pixrgb[p] >> 16); }
+                for (int q = 0; q < 6; ++q) { d[3 * q] = (uint8_t)p[q]; d[3 * q + 1] = (uint8_t)(p[q] >> 8); d[3 * q + 2] = (uint8_t)(p[q] >> 16); }
             }
         }
-        __syncthreads();
-        store_run(s_rgb, P.out, g_lo, g_hi);
+        __syncwarp();
+        warp_store_run(U, P.out, g_lo, len, lane);
+        __syncwarp();
     }
 }
 
 template <int K>
 int launch_enc(const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_encode_rgb_fast<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<K>::TOTAL); attr = true; }
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        cudaFuncSetAttribute(k_encode_rgb_fast<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<K>::TOTAL_ENC);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_encode_rgb_fast<K>, FAST_TPB, Cfg<K>::TOTAL_ENC);
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
-    uint64_t grid = (uint64_t)T.sm_count * 4;
-    if (grid > total) grid = total;
+    uint64_t grid = (uint64_t)T.sm_count * ctas_per_sm;
+    const uint64_t need = (total + FAST_WARPS - 1) / FAST_WARPS;
+    if (grid > need) grid = need;
     if (!grid) return 0;
-    k_encode_rgb_fast<K><<<(unsigned)grid, FAST_TPB, Cfg<K>::TOTAL, st>>>(P, g, T.gf, T.rs);
+    k_encode_rgb_fast<K><<<(unsigned)grid, FAST_TPB, Cfg<K>::TOTAL_ENC, st>>>(P, g, T.gf, T.rs);
     return 1;
 }
 template <int K>
 int launch_dec(const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_decode_rgb_fast<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<K>::TOTAL); attr = true; }
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        cudaFuncSetAttribute(k_decode_rgb_fast<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<K>::TOTAL_DEC);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_decode_rgb_fast<K>, FAST_TPB, Cfg<K>::TOTAL_DEC);
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
-    uint64_t grid = (uint64_t)T.sm_count * 4;
-    if (grid > total) grid = total;
+    uint64_t grid = (uint64_t)T.sm_count * ctas_per_sm;
+    const uint64_t need = (total + FAST_WARPS - 1) / FAST_WARPS;
+    if (grid > need) grid = need;
     if (!grid) return 0;
-    k_decode_rgb_fast<K><<<(unsigned)grid, FAST_TPB, Cfg<K>::TOTAL, st>>>(P, g, T.gf, T.rs);
+    k_decode_rgb_fast<K><<<(unsigned)grid, FAST_TPB, Cfg<K>::TOTAL_DEC, st>>>(P, g, T.gf, T.rs);
     return 1;
 }
 
@@ -495,7 +527,7 @@ int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
     P.n_px = n_px; P.n_frames = (uint32_t)n_frames;
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    P.n_tiles = (uint32_t)((mx + C_TILE - 1) / C_TILE);
+    P.n_tiles = (uint32_t)((mx + C_MINI - 1) / C_MINI);
     int n = 0;
     switch (g.uniform_k) {
     case 24: n = launch_enc<24>(T, P, g, st); break;
@@ -522,7 +554,7 @@ int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
     for (int i = 0; i < 7; ++i) { P.chk_nz[i] = chk_nz[i]; P.chk_two[i] = chk_two[i]; }
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    P.n_tiles = (uint32_t)((mx + C_TILE - 1) / C_TILE);
+    P.n_tiles = (uint32_t)((mx + C_MINI - 1) / C_MINI);
     switch (g.uniform_k) {
     case 24: return launch_dec<24>(T, P, g, st);
     case 22: return launch_dec<22>(T, P, g, st);
