@@ -190,42 +190,41 @@ __device__ __forceinline__ void warp_store_run(const uint8_t* s, uint8_t* __rest
         if (in_head || in_tail) g0[hi] = s[hi];
     }
 }
+// nine runs, one per iteration: lanes 0..CH-1 move one interior 16-byte chunk each, and in the same pass
+// lanes 0-15 / 16-31 write the head / tail edge bytes, so the whole run costs ~20 warp instructions
 template <int PITCH>
 __device__ __forceinline__ void warp_store_runs9(const uint8_t* O, uint8_t* __restrict__ gbase, const WarpMeta& m, int lane)
 {
-    constexpr int CH = PITCH / 16;
-    // interior chunks of all nine runs, flattened
-    for (int j = lane; j < 9 * CH; j += 32) {
-        const int b = j / CH, c = j - b * CH;
+    static_assert(PITCH / 16 <= 32, "one chunk per lane");
+#pragma unroll 1
+    for (int b = 0; b < 9; ++b) {
         const int len = 26 * (int)m.run_n[b];
-        const uint64_t lo = m.run_lo[b];
-        const int pad = (int)(lo & 15), r0 = 16 * c - pad;
-        if (r0 < 0 || r0 + 16 > len) continue;
-        *reinterpret_cast<uint4*>(gbase + (lo - pad) + 16 * c) = *reinterpret_cast<const uint4*>(O + PITCH * b + 16 * c);
-    }
-    // edge bytes: 9 runs x (16 head + 16 tail) byte slots, one per lane
-    for (int e = lane; e < 9 * 32; e += 32) {
-        const int b = e >> 5, i = e & 15, tail = (e >> 4) & 1;
-        const int len = 26 * (int)m.run_n[b];
+        if (len == 0) continue;
         const uint64_t lo = m.run_lo[b];
         const int pad = (int)(lo & 15), end = pad + len;
-        const int pos = tail ? (end & ~15) + i : i;                  // byte position inside the padded run
-        const bool ok = len > 0 && pos >= pad && pos < end && (tail ? ((end & 15) != 0 && !(pad && (end >> 4) == 0)) : pad != 0);
-        if (ok) gbase[(lo - pad) + pos] = O[PITCH * b + pos];
+        uint8_t* g0 = gbase + (lo - pad);
+        const uint8_t* s0 = O + PITCH * b;
+        const int c16 = 16 * lane;
+        if (c16 >= pad && c16 + 16 <= end) *reinterpret_cast<uint4*>(g0 + c16) = *reinterpret_cast<const uint4*>(s0 + c16);
+        const int pos = lane < 16 ? lane : (end & ~15) + (lane - 16);
+        const bool head = lane < 16 && pad != 0;
+        const bool tail = lane >= 16 && (end & 15) != 0 && !(pad != 0 && (end >> 4) == 0);
+        if ((head || tail) && pos >= pad && pos < end) g0[pos] = s0[pos];
     }
 }
 template <int PITCH>
 __device__ __forceinline__ void warp_load_runs9(uint8_t* O, const uint8_t* __restrict__ gbase, const WarpMeta& m, uint64_t g_limit, int lane)
 {
-    constexpr int CH = PITCH / 16;
-    for (int j = lane; j < 9 * CH; j += 32) {
-        const int b = j / CH, c = j - b * CH;
+    static_assert(PITCH / 16 <= 32, "one chunk per lane");
+#pragma unroll 1
+    for (int b = 0; b < 9; ++b) {
         const int len = 26 * (int)m.run_n[b];
+        if (len == 0) continue;
         const uint64_t lo = m.run_lo[b];
-        const int pad = (int)(lo & 15), r0 = 16 * c - pad;
-        if (r0 + 16 <= 0 || r0 >= len) continue;
-        const uint64_t ga = (lo - pad) + 16 * c;
-        uint8_t* sp = O + PITCH * b + 16 * c;
+        const int pad = (int)(lo & 15), c16 = 16 * lane;
+        if (c16 >= pad + len) continue;
+        const uint64_t ga = (lo - pad) + c16;
+        uint8_t* sp = O + PITCH * b + c16;
         if (ga + 16 <= g_limit) *reinterpret_cast<uint4*>(sp) = __ldg(reinterpret_cast<const uint4*>(gbase + ga));
         else
             for (int i = 0; i < 16; ++i) sp[i] = ga + i < g_limit ? gbase[ga + i] : 0;
