@@ -1,0 +1,293 @@
+// ternary_image_codec_v6_min.hpp -- drop-in for the reference header of the same name
+// (old/include/ternary_image_codec_v6_min.hpp, "OLD"): same type and function names, same argument
+// meaning and error behaviour, but every data-path function forwards to libt3c.so (CUDA, sm_100a)
+// through the C ABI in t3c.h.  A translation unit written against the reference header compiles
+// against this one unchanged; link with -lt3c.  Nothing here computes codec data on the CPU.
+//
+// Additions (all optional, defaults reproduce the reference bit for bit):
+//   EncoderContext::arith / DecoderContext::arith   T3C_REF_EXACT (default) or T3C_FIXED
+//   DecoderContext::fixed_cfg / expected_raw_words  out-of-band config for the FIXED consistent decoder
+//   t3c_shim::context(device)                       the shared per-device t3c_ctx
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <vector>
+
+#include "t3c.h"
+
+using UTrit = uint8_t; // 0..2
+using GF27 = uint8_t;  // 0..26
+static constexpr int TRITS_PER_WORD = 27, SYM_PER_WORD = 9, NUM_BANDS = 9;
+
+inline GF27 pack3(UTrit a, UTrit b, UTrit c) { return (GF27)(a + 3 * b + 9 * c); }
+inline std::array<UTrit, 3> unpack3(GF27 s) { return {(UTrit)(s % 3), (UTrit)((s / 3) % 3), (UTrit)((s / 9) % 3)}; }
+
+enum class ProfileID : uint8_t { RAW_MODE = 0xFF, P1_RS26_24 = 0, P2_RS26_22 = 1, P3_RS26_20 = 2, P4_RS26_18 = 3, P5_RS26_22_2D = 4 };
+struct RSParams { uint8_t n = 26, k = 22; };
+inline RSParams rs_params_for(ProfileID p)
+{
+    static const uint8_t ks[5] = {24, 22, 20, 18, 22};
+    const unsigned i = (unsigned)p;
+    return RSParams{26, i < 5 ? ks[i] : (uint8_t)22};
+}
+struct UEPLayout { std::array<uint8_t, NUM_BANDS> band_profile{}; };
+inline void uep_uniform(UEPLayout& u, uint8_t idx = 1) { u.band_profile.fill((uint8_t)(idx % 4)); }
+inline void uep_luma_priority(UEPLayout& u) { u.band_profile = {2, 1, 1, 2, 1, 1, 2, 1, 1}; }
+struct Tile2D { uint16_t w = 0, h = 0; };
+struct ScramblerSeed { uint32_t a = 1, b = 1, s0 = 1; };
+struct SparseBeaconCfg { uint32_t words_period = 0; uint8_t band_slot = 0; bool enabled = false; };
+enum class CosetID : uint8_t { C0 = 0, C1 = 1, C2 = 2 };
+enum class SubwordMode : uint8_t { S27 = 27, S24 = 24, S21 = 21, S18 = 18, S15 = 15 };
+inline int payload_len_for(SubwordMode m) { return (int)m; }
+struct StdRes { uint16_t w, h; };
+inline StdRes std_res_for(SubwordMode m)
+{
+    switch (m) {
+    case SubwordMode::S24: return {3840, 2160};
+    case SubwordMode::S21: return {1920, 1080};
+    case SubwordMode::S18: return {1280, 720};
+    case SubwordMode::S15: return {854, 480};
+    default: return {7680, 4320};
+    }
+}
+struct ActiveWindow { uint32_t x0, y0, w, h; };
+inline ActiveWindow centered_window(SubwordMode m)
+{
+    const StdRes base = std_res_for(SubwordMode::S27), t = std_res_for(m);
+    return {(uint32_t)((base.w - t.w) / 2), (uint32_t)((base.h - t.h) / 2), t.w, t.h};
+}
+
+struct Word27 { std::array<GF27, SYM_PER_WORD> sym{}; };
+struct PixelYCbCrQuant { uint16_t Yq = 0; int16_t Cbq = 0, Crq = 0; };
+static_assert(sizeof(Word27) == 9 && sizeof(PixelYCbCrQuant) == sizeof(t3c_pixel), "POD layouts of the ABI");
+
+struct EncoderConfig {
+    ProfileID profile = ProfileID::P2_RS26_22;
+    UEPLayout uep{};
+    Tile2D tile{};
+    ScramblerSeed seed{1, 1, 1};
+    SparseBeaconCfg beacon{};
+    uint32_t superframe_words = 8192;
+    SubwordMode subword = SubwordMode::S27;
+    bool centered = true;
+    CosetID coset = CosetID::C0;
+};
+struct DecoderConfigSeen {
+    ProfileID profile = ProfileID::P2_RS26_22;
+    UEPLayout uep{};
+    Tile2D tile{};
+    ScramblerSeed seed{1, 1, 1};
+    SparseBeaconCfg beacon{};
+    SubwordMode subword = SubwordMode::S27;
+    bool centered = true;
+    CosetID coset = CosetID::C0;
+};
+
+namespace t3c_shim {
+// one t3c_ctx per device, created on first use; throws when there is no GPU (no CPU fallback exists)
+inline t3c_ctx* context(int device = 0)
+{
+    static std::mutex mu;
+    static std::array<t3c_ctx*, 16> ctxs{};
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0 || device >= (int)ctxs.size()) throw std::runtime_error("t3c: bad device index");
+    if (!ctxs[device]) {
+        const t3c_status st = t3c_create(device, &ctxs[device]);
+        if (st != T3C_OK) throw std::runtime_error(st == T3C_ERR_NODEVICE ? "t3c: no CUDA device (there is no CPU fallback)" : "t3c: context creation failed");
+    }
+    return ctxs[device];
+}
+template <class Cfg> inline t3c_config to_abi(const Cfg& c, uint32_t superframe_words)
+{
+    t3c_config o{};
+    o.profile = (uint8_t)c.profile;
+    for (int i = 0; i < 9; ++i) o.uep[i] = c.uep.band_profile[i];
+    o.tile_w = c.tile.w; o.tile_h = c.tile.h;
+    o.seed_a = c.seed.a; o.seed_b = c.seed.b; o.seed_s0 = c.seed.s0;
+    o.beacon_period = c.beacon.words_period; o.beacon_slot = c.beacon.band_slot; o.beacon_enabled = c.beacon.enabled ? 1 : 0;
+    o.subword = (uint8_t)c.subword; o.centered = c.centered ? 1 : 0; o.coset = (uint8_t)c.coset;
+    o.superframe_words = superframe_words;
+    return o;
+}
+inline void from_abi(const t3c_config& c, DecoderConfigSeen& o)
+{
+    o.profile = (ProfileID)c.profile;
+    for (int i = 0; i < 9; ++i) o.uep.band_profile[i] = c.uep[i];
+    o.tile = Tile2D{c.tile_w, c.tile_h};
+    o.seed = ScramblerSeed{c.seed_a, c.seed_b, c.seed_s0};
+    o.beacon.words_period = c.beacon_period; o.beacon.band_slot = c.beacon_slot; o.beacon.enabled = c.beacon_enabled != 0;
+    o.subword = (SubwordMode)c.subword; o.centered = c.centered != 0; o.coset = (CosetID)c.coset;
+}
+} // namespace t3c_shim
+
+// RSCodec keeps the reference's block-level interface (OLD:490-663); one call = one device launch, so bulk
+// work should go through t3c_rs_encode_blocks / t3c_rs_decode_blocks or the profile codec instead.
+struct GF27Context { void init() {} };
+struct RSCodec {
+    GF27Context* gf = nullptr;
+    RSParams params{};
+    int arith = T3C_REF_EXACT;
+    int device = 0;
+    void init(GF27Context* c, RSParams p) { gf = c; params = p; }
+    bool encode_block(const GF27* data_k, GF27* out_n) const
+    {
+        return t3c_rs_encode_blocks(t3c_shim::context(device), params.k, arith, data_k, 1, out_n) == T3C_OK;
+    }
+    bool decode_block(GF27* inout_n, GF27* out_k) const
+    {
+        uint8_t ok = 0;
+        GF27 tmp[26];
+        if (t3c_rs_decode_blocks(t3c_shim::context(device), params.k, arith, inout_n, 1, tmp, &ok) != T3C_OK) return false;
+        if (ok) std::memcpy(out_k, tmp, params.k); // the reference leaves out_k untouched on failure
+        return ok != 0;
+    }
+};
+
+struct EncoderContext {
+    GF27Context gf;
+    RSCodec rs_p1, rs_p2, rs_p3, rs_p4, rs_hdr;
+    EncoderConfig cfg;
+    int arith = T3C_REF_EXACT; // T3C_FIXED: repaired RS arithmetic
+    int device = 0;
+    EncoderContext()
+    {
+        rs_p1.init(&gf, rs_params_for(ProfileID::P1_RS26_24)); rs_p2.init(&gf, rs_params_for(ProfileID::P2_RS26_22));
+        rs_p3.init(&gf, rs_params_for(ProfileID::P3_RS26_20)); rs_p4.init(&gf, rs_params_for(ProfileID::P4_RS26_18));
+        rs_hdr.init(&gf, RSParams{26, 18});
+        uep_uniform(cfg.uep, 1);
+    }
+};
+struct DecoderContext {
+    GF27Context gf;
+    RSCodec rs_p1, rs_p2, rs_p3, rs_p4, rs_hdr;
+    DecoderConfigSeen cfg_last_seen;
+    int arith = T3C_REF_EXACT;          // T3C_FIXED selects the consistent decoder
+    int device = 0;
+    const EncoderConfig* fixed_cfg = nullptr; // FIXED: the encoder's config, carried out of band
+    size_t expected_raw_words = 0;      // FIXED: N_w given to the encoder (0 = infer; required with the 2D interleave)
+    size_t last_corrected = 0;          // FIXED: symbols corrected by the last call
+    DecoderContext()
+    {
+        rs_p1.init(&gf, rs_params_for(ProfileID::P1_RS26_24)); rs_p2.init(&gf, rs_params_for(ProfileID::P2_RS26_22));
+        rs_p3.init(&gf, rs_params_for(ProfileID::P3_RS26_20)); rs_p4.init(&gf, rs_params_for(ProfileID::P4_RS26_18));
+        rs_hdr.init(&gf, RSParams{26, 18});
+        uep_uniform(cfg_last_seen.uep, 1);
+    }
+};
+
+inline bool encode_raw_pixels_to_words(const std::vector<PixelYCbCrQuant>& px, std::vector<Word27>& out)
+{
+    out.assign((px.size() + 1) / 2, Word27{});
+    size_t n = 0;
+    return t3c_pack_pixels(t3c_shim::context(), reinterpret_cast<const t3c_pixel*>(px.data()), px.size(),
+                           reinterpret_cast<uint8_t*>(out.data()), &n) == T3C_OK;
+}
+inline bool decode_raw_words_to_pixels(const std::vector<Word27>& in, std::vector<PixelYCbCrQuant>& out)
+{
+    out.assign(in.size() * 2, PixelYCbCrQuant{});
+    return t3c_unpack_pixels(t3c_shim::context(), reinterpret_cast<const uint8_t*>(in.data()), in.size(),
+                             reinterpret_cast<t3c_pixel*>(out.data())) == T3C_OK;
+}
+inline void interleave2D_boustrophedon(std::vector<GF27>& syms, Tile2D tile)
+{
+    t3c_interleave2d(t3c_shim::context(), syms.data(), syms.size(), tile.w, tile.h, 0);
+}
+inline void deinterleave2D_boustrophedon(std::vector<GF27>& syms, Tile2D tile)
+{
+    t3c_interleave2d(t3c_shim::context(), syms.data(), syms.size(), tile.w, tile.h, 1);
+}
+
+inline bool encode_profile_from_raw(const std::vector<Word27>& in, std::vector<Word27>& out, EncoderContext& ectx)
+{
+    out.clear();
+    const t3c_config cfg = t3c_shim::to_abi(ectx.cfg, ectx.cfg.superframe_words);
+    out.assign(t3c_profile_words(&cfg, in.size()), Word27{});
+    size_t n = 0;
+    const t3c_status st = t3c_encode_profile(t3c_shim::context(ectx.device), &cfg, ectx.arith, reinterpret_cast<const uint8_t*>(in.data()),
+                                             in.size(), reinterpret_cast<uint8_t*>(out.data()), out.size(), &n);
+    out.resize(st == T3C_OK ? n : 0);
+    return st == T3C_OK; // the reference encoder never returns false
+}
+inline bool decode_profile_to_raw(const std::vector<Word27>& in, std::vector<Word27>& out, DecoderContext& dctx)
+{
+    out.clear();
+    t3c_ctx* ctx = t3c_shim::context(dctx.device);
+    std::vector<Word27> buf(in.size() + 8);
+    size_t n = 0;
+    int ok = 0;
+    if (dctx.arith == T3C_FIXED && dctx.fixed_cfg) {
+        const t3c_config cfg = t3c_shim::to_abi(*dctx.fixed_cfg, dctx.fixed_cfg->superframe_words);
+        size_t fixed = 0;
+        if (t3c_decode_profile_fixed(ctx, &cfg, dctx.expected_raw_words, reinterpret_cast<const uint8_t*>(in.data()), in.size(),
+                                     reinterpret_cast<uint8_t*>(buf.data()), buf.size(), &n, &ok, &fixed) != T3C_OK) return false;
+        dctx.last_corrected = fixed;
+    } else {
+        t3c_config seen = t3c_shim::to_abi(dctx.cfg_last_seen, 8192);
+        if (t3c_decode_profile(ctx, &seen, reinterpret_cast<const uint8_t*>(in.data()), in.size(), reinterpret_cast<uint8_t*>(buf.data()),
+                               buf.size(), &n, &ok) != T3C_OK) return false;
+        t3c_shim::from_abi(seen, dctx.cfg_last_seen); // mutated even when a later block fails (OLD:1006-1013)
+    }
+    if (!ok) return false;
+    buf.resize(n);
+    out.swap(buf);
+    return true;
+}
+
+// selftests with the reference's inputs (OLD:1172-1230).  As shipped (REF_EXACT) both report false, exactly
+// like the reference; with arith = T3C_FIXED the RS unit test passes and the API round trip compares the
+// recovered prefix through the consistent decoder.
+inline bool selftest_rs_unit(int arith = T3C_REF_EXACT)
+{
+    uint32_t lcg = 1;
+    auto next = [&]() { lcg = lcg * 1664525u + 1013904223u; return lcg >> 8; };
+    for (ProfileID pid : {ProfileID::P1_RS26_24, ProfileID::P2_RS26_22, ProfileID::P3_RS26_20, ProfileID::P4_RS26_18}) {
+        GF27Context gf;
+        RSCodec rs;
+        rs.init(&gf, rs_params_for(pid));
+        rs.arith = arith;
+        const int n = rs.params.n, k = rs.params.k, t = (n - k) / 2;
+        std::vector<GF27> data(k), code(n), outk(k);
+        for (int i = 0; i < k; ++i) data[i] = (GF27)((i * 5 + 7) % 27);
+        rs.encode_block(data.data(), code.data());
+        std::vector<int> used;
+        while ((int)used.size() < t) {
+            const int p = (int)(next() % (uint32_t)n);
+            if (std::find(used.begin(), used.end(), p) != used.end()) continue;
+            used.push_back(p);
+            const auto a = unpack3(code[p]), b = unpack3((GF27)(1 + next() % 26));
+            code[p] = pack3((UTrit)((a[0] + b[0]) % 3), (UTrit)((a[1] + b[1]) % 3), (UTrit)((a[2] + b[2]) % 3));
+        }
+        if (!rs.decode_block(code.data(), outk.data())) return false;
+        if (outk != data) return false;
+    }
+    return true;
+}
+inline bool selftest_api_roundtrip(int arith = T3C_REF_EXACT)
+{
+    std::vector<PixelYCbCrQuant> px(64);
+    for (size_t i = 0; i < px.size(); ++i) {
+        px[i].Yq = (uint16_t)((i * 7) % 243);
+        px[i].Cbq = (int16_t)((int)((i * 3) % 81) - 40);
+        px[i].Crq = (int16_t)((int)((i * 5) % 81) - 40);
+    }
+    std::vector<Word27> raw_in, prof, raw_out;
+    encode_raw_pixels_to_words(px, raw_in);
+    EncoderContext e;
+    e.arith = arith;
+    e.cfg.profile = ProfileID::P2_RS26_22;
+    uep_luma_priority(e.cfg.uep);
+    if (!encode_profile_from_raw(raw_in, prof, e)) return false;
+    DecoderContext d;
+    d.arith = arith;
+    if (arith == T3C_FIXED) { d.fixed_cfg = &e.cfg; d.expected_raw_words = raw_in.size(); }
+    if (!decode_profile_to_raw(prof, raw_out, d)) return false;
+    const size_t L = std::min(raw_in.size(), raw_out.size());
+    for (size_t i = 0; i < L; ++i)
+        if (raw_in[i].sym != raw_out[i].sym) return false;
+    return true;
+}

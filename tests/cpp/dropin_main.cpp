@@ -1,0 +1,84 @@
+// dropin_main.cpp -- a caller written ONLY against the reference's public names
+// (old/include/ternary_image_codec_v6_min.hpp + include/ternary_packing.hpp), in the style of
+// old/src/main.cpp:15-26 and old/src/main_bare.cpp.  It is compiled twice, unchanged:
+//   * against the reference headers            -> oracle/_ref/dropin_ref   (CPU, reference code)
+//   * against this repo's include/ + libt3c.so -> tests/cpp/_dropin_ours   (B200)
+// and tests/test_dropin_cpp.py requires the two programs to print identical lines.
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "ternary_image_codec_v6_min.hpp"
+#include "ternary_packing.hpp"
+
+static uint64_t fnv(const void* p, size_t n, uint64_t h = 1469598103934665603ull)
+{
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+static uint32_t lcg_state = 12345;
+static uint32_t lcg() { lcg_state = lcg_state * 1664525u + 1013904223u; return lcg_state >> 8; }
+
+int main()
+{
+    // pixels -> raw words
+    std::vector<PixelYCbCrQuant> px(20001);
+    for (auto& p : px) { p.Yq = (uint16_t)(lcg() % 243); p.Cbq = (int16_t)((int)(lcg() % 81) - 40); p.Crq = (int16_t)((int)(lcg() % 81) - 40); }
+    std::vector<Word27> raw;
+    encode_raw_pixels_to_words(px, raw);
+    std::printf("raw %zu %016llx\n", raw.size(), (unsigned long long)fnv(raw.data(), raw.size() * 9));
+    std::vector<PixelYCbCrQuant> back;
+    decode_raw_words_to_pixels(raw, back);
+    std::printf("unpack %zu %016llx\n", back.size(), (unsigned long long)fnv(back.data(), back.size() * sizeof(PixelYCbCrQuant)));
+
+    // profile encode over a small config matrix (old/src/main.cpp:17 uses P2 + tile + beacon)
+    for (int variant = 0; variant < 5; ++variant) {
+        EncoderContext e;
+        switch (variant) {
+        case 0: break;
+        case 1: e.cfg.profile = ProfileID::P2_RS26_22; e.cfg.tile = {64, 64}; e.cfg.beacon = {83, 2, true}; break;
+        case 2: e.cfg.profile = ProfileID::P3_RS26_20; uep_uniform(e.cfg.uep, 2); break;
+        case 3: e.cfg.profile = ProfileID::P5_RS26_22_2D; e.cfg.tile = {26, 26}; uep_luma_priority(e.cfg.uep); e.cfg.beacon = {26, 2, true};
+                e.cfg.seed = {2, 1, 1}; e.cfg.coset = CosetID::C1; break;
+        case 4: e.cfg.profile = ProfileID::RAW_MODE; break;
+        }
+        std::vector<Word27> prof;
+        const bool ok = encode_profile_from_raw(raw, prof, e);
+        std::printf("encode[%d] %d %zu %016llx\n", variant, (int)ok, prof.size(), (unsigned long long)fnv(prof.data(), prof.size() * 9));
+        DecoderContext d;
+        std::vector<Word27> dec;
+        const bool dok = decode_profile_to_raw(prof, dec, d); // as shipped: rejects its own encoder's output (bug B1)
+        std::printf("decode[%d] %d %zu seen_profile=%d\n", variant, (int)dok, dec.size(), (int)d.cfg_last_seen.profile);
+        std::vector<uint8_t> bytes;
+        tpack::words_to_bytes(prof, bytes);
+        std::printf("bytes[%d] %zu %016llx\n", variant, bytes.size(), (unsigned long long)fnv(bytes.data(), bytes.size()));
+    }
+
+    // block-level RS with the reference's selftest data
+    GF27Context gf;
+    gf.init();
+    for (ProfileID pid : {ProfileID::P1_RS26_24, ProfileID::P2_RS26_22, ProfileID::P3_RS26_20, ProfileID::P4_RS26_18}) {
+        RSCodec rs;
+        rs.init(&gf, rs_params_for(pid));
+        const int k = rs.params.k;
+        std::vector<GF27> data(k), code(26), outk(k, 0);
+        for (int i = 0; i < k; ++i) data[i] = (GF27)((i * 5 + 7) % 27);
+        rs.encode_block(data.data(), code.data());
+        std::printf("rs_enc k=%d %016llx\n", k, (unsigned long long)fnv(code.data(), 26));
+        code[3] = (GF27)((code[3] + 1) % 27);
+        const bool ok = rs.decode_block(code.data(), outk.data());
+        std::printf("rs_dec k=%d %d %016llx %016llx\n", k, (int)ok, (unsigned long long)fnv(code.data(), 26), (unsigned long long)fnv(outk.data(), k));
+    }
+
+    // 2D boustrophedon
+    std::vector<GF27> sy(1000);
+    for (auto& s : sy) s = (GF27)(lcg() % 27);
+    interleave2D_boustrophedon(sy, Tile2D{7, 5});
+    std::printf("il2d %016llx\n", (unsigned long long)fnv(sy.data(), sy.size()));
+    deinterleave2D_boustrophedon(sy, Tile2D{7, 5});
+    std::printf("dil2d %016llx\n", (unsigned long long)fnv(sy.data(), sy.size()));
+
+    std::printf("selftests RS:%s API:%s\n", selftest_rs_unit() ? "OK" : "FAIL", selftest_api_roundtrip() ? "OK" : "FAIL");
+    return 0;
+}
