@@ -1,0 +1,103 @@
+"""Secondary workloads of BASELINE.json (configs[2..4]) -- device-resident timing with CUDA events.
+Prints one JSON line per workload.  Not the driver's contract (that is bench.py); these numbers are
+quoted in DESIGN.md."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ternary_image_codec_b200 as t3
+
+N_PX = 7680 * 4320
+PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+dev = torch.device("cuda", 0)
+codec = t3.Codec(0, arith=t3.FIXED)
+S = torch.cuda.current_stream().cuda_stream
+
+
+def timeit(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
+        fn(); ev[i + 1].record()
+    torch.cuda.synchronize()
+    return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))[n // 2]
+
+
+def raw8k():
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    NB = 3
+    px = []
+    for _ in range(NB):
+        p = torch.empty(N_PX, 3, dtype=torch.int16, device=dev)
+        p[:, 0] = torch.randint(0, 243, (N_PX,), device=dev, generator=g, dtype=torch.int16)
+        p[:, 1:] = torch.randint(-40, 41, (N_PX, 2), device=dev, generator=g, dtype=torch.int16)
+        px.append(p)
+    words = [torch.empty(N_PX // 2 * 9, dtype=torch.uint8, device=dev) for _ in range(NB)]
+    back = [torch.empty_like(px[0]) for _ in range(NB)]
+    i = [0]
+    def pack(): codec.pack_pixels_dev(px[i[0] % NB], N_PX, words[i[0] % NB], S); i[0] += 1
+    def unpack(): codec.unpack_pixels_dev(words[i[0] % NB], N_PX // 2, back[i[0] % NB], S); i[0] += 1
+    tp, tu = timeit(pack), timeit(unpack)
+    alg = 6 * N_PX + 9 * (N_PX // 2)
+    assert torch.equal(px[0], back[0])
+    print(json.dumps({"workload": "raw8k: 8K PixelYCbCrQuant <-> Word27 (RAW mode, no RS)", "pack_us": tp * 1e3, "unpack_us": tu * 1e3,
+                      "pack_gbs": alg / tp / 1e6, "unpack_gbs": alg / tu / 1e6, "pack_frac_of_measured_peak": alg / tp / 1e6 / PEAK,
+                      "unpack_frac_of_measured_peak": alg / tu / 1e6 / PEAK, "mpix_per_s_pack_plus_unpack": N_PX / (tp + tu) / 1e3,
+                      "algorithmic_bytes": alg}))
+
+
+def uep2d(all_t=False):
+    cfg = t3.make_config(profile=t3.P5_RS26_22_2D, tile=(26, 26), beacon=(26, 2, True), uep=t3.UEP_LUMA_PRIORITY, seed=(2, 1, 1), coset=1)
+    wpf = t3.profile_words(cfg, N_PX // 2)
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    rgb = torch.randint(0, 256, (N_PX * 3,), dtype=torch.uint8, device=dev, generator=g)
+    enc = torch.empty(wpf * 9, dtype=torch.uint8, device=dev)
+    back = torch.empty(N_PX * 3, dtype=torch.uint8, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    def E(): codec.encode_frames_rgb8_dev(rgb, N_PX, 1, enc, wpf, cfg, t3.FIXED, S)
+    def D(): codec.decode_frames_rgb8_dev(enc, wpf, wpf, 1, N_PX, back, status, cfg, S)
+    te = timeit(E, n=5, warm=2)
+    td_clean = timeit(D, n=5, warm=2)
+    # one symbol error in every 26-symbol stretch of the body (beacon expansion ignored: <= 1 per codeword, <= t)
+    body = enc[52:]
+    idx = torch.arange(7, body.numel() - 30, 27 if not all_t else 9, device=dev)
+    body[idx] = (body[idx] + 1) % 27
+    td_err = timeit(D, n=3, warm=1)
+    alg = 3 * N_PX + 9 * wpf
+    print(json.dumps({"workload": "uep2d: 8K, P5 2D 26x26 + luma UEP + coset C1 + beacon(26,2), general kernels", "encode_us": te * 1e3,
+                      "decode_clean_us": td_clean * 1e3, "decode_with_errors_us": td_err * 1e3, "status": status.tolist(),
+                      "encode_gbs": alg / te / 1e6, "decode_clean_gbs": alg / td_clean / 1e6, "mpix_per_s_enc_plus_dec_clean": N_PX / (te + td_clean) / 1e3,
+                      "profile_words": wpf}))
+
+
+def stream240(frames_per_call=8):
+    cfg = t3.make_config(profile=t3.P3_RS26_20, uep=2)
+    wpf = t3.profile_words(cfg, N_PX // 2)
+    stride = (wpf + 15) & ~15
+    F = frames_per_call
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    rgb = torch.randint(0, 256, (F, N_PX * 3), dtype=torch.uint8, device=dev, generator=g)
+    enc = torch.empty(F, stride * 9, dtype=torch.uint8, device=dev)
+    back = torch.empty(F, N_PX * 3, dtype=torch.uint8, device=dev)
+    status = torch.zeros(2 * F, dtype=torch.int32, device=dev)
+    calls = 240 // F
+    def step():
+        codec.encode_frames_rgb8_dev(rgb, N_PX, F, enc, stride, cfg, t3.FIXED, S)
+        codec.decode_frames_rgb8_dev(enc, wpf, stride, F, N_PX, back, status, cfg, S)
+    step(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(calls):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"workload": f"stream240: 240 synthetic 8K frames, RS(26,20) 1D, {F} frames per batched launch, 1 GPU (frame f -> GPU f mod G shards this linearly)",
+                      "total_ms": ms, "frames_per_s": 240 / ms * 1e3, "mpix_per_s": 240 * N_PX / ms / 1e3, "ok": bool((status[0::2] == 1).all())}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["raw8k", "uep2d", "stream240"]
+    for w in which:
+        {"raw8k": raw8k, "uep2d": uep2d, "stream240": stream240}[w]()
