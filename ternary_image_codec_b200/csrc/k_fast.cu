@@ -29,7 +29,8 @@ struct FastParams {
     uint64_t out_stride;
     uint64_t n_px;          // pixels per frame
     uint64_t px_out;        // decode: pixels to write per frame
-    uint32_t n_tiles;       // mini-tiles per frame
+    uint32_t n_tiles;       // mini-tiles per frame handled by this launch
+    uint32_t tile0;         // first mini-tile of each frame handled by this launch
     uint32_t n_frames;
     uint32_t* status;       // decode: {ok, n_corrected} per frame
     uint32_t chk_nz[7], chk_two[7]; // decode: sum of T_i[13*st_i] per scrambler phase (6) and for p0==0
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
     const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
     for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
-        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = (uint32_t)(mt - (uint64_t)f * P.n_tiles);
+        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = P.tile0 + (uint32_t)(mt - (uint64_t)f * P.n_tiles);
         const uint64_t px0 = (uint64_t)L::PX * tile;
         const uint64_t in_off = P.in_stride * f;
         const uint64_t g_lo = in_off + 3 * (px0 < P.n_px ? px0 : P.n_px);
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
     const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
     const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
     for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
-        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = (uint32_t)(mt - (uint64_t)f * P.n_tiles);
+        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = P.tile0 + (uint32_t)(mt - (uint64_t)f * P.n_tiles);
         setup_runs(meta, g, P.in_stride * f, tile, lane);
         __syncwarp();
         warp_load_runs9<L::RUN_PITCH>(U, P.in, meta, in_limit, lane);
@@ -470,13 +471,404 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
     }
 }
 
-template <int K>
-int launch_enc(const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st)
+// =============================================================================================
+// v3: full mini-tiles (all 117 codewords and all 27k pixels exist; the ragged last tiles of a frame keep the
+// kernels above).  Same warp-autonomous structure, rebuilt around what the v2 profile showed
+// (profiles/r01a_fast_v2_ncu_summary.txt): the kernels were bound by shared-memory wavefronts (bank conflicts on
+// 64-bit row-table look-ups and on 2-byte accesses at 18/26-byte lane strides) and by the half-rate ALU pipe.
+//   * row tables split into two conflict-free 32-bit plane tables of 27 (encode) / 32 (decode) entries per
+//     position; the low byte of a plane entry carries the scrambled (descrambled) symbol for that position, one
+//     table variant per scrambler phase of the codeword (26 = 2 mod 6: three variants), so the separate
+//     scramble look-up and its address arithmetic disappear;
+//   * symbols travel pre-scaled by 4 (a table byte offset), so a look-up is LDS [reg + immediate];
+//   * parity leaves the bit planes through PRMT used as an 8-entry byte table (nibble = 3 plane bits), the
+//     scrambler is added to the parity in the plane domain (3 LOP3 for all parity symbols);
+//   * codewords are dealt to lanes row-major (9 bands of one codeword row are adjacent lanes) and 6-pixel units
+//     even/odd, which makes the 9-byte-stride gathers and the 18/26-byte-stride accesses conflict-free;
+//   * the bridge uses PRMT-built 2^23+x floats inside FFMAs (exactly fl(c*x)), two FADD.RM for the rounding and
+//     one IMAD.HI per quantiser (constants found by exhaustive search, checked by the 2^24 colour test).
+// =============================================================================================
+constexpr uint32_t QY_M = 4076008176u, QY_Z = 114u, QY_C0 = 1194143128u;  // hi32((0x4B000000+Z+Y)*M) - C0 == (484Y+255)/510, Y in [0,255]
+constexpr uint32_t QC_M = 1344274432u, QC_Z = 126u, QC_C0 = 393830439u;   // ... == (5C+7+(C>=128))>>4, C in [0,256]
+constexpr uint32_t Q_CONST = 0u - (QY_C0 + 243u * QC_C0 + 19683u * QC_C0);
+__device__ __forceinline__ uint32_t mad_hi(uint32_t a, uint32_t b, uint32_t c)
 {
-    static int ctas_per_sm = 0;
+    uint32_t d;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// byte j of w as the float 2^23 + byte
+__device__ __forceinline__ float byte_magic(uint32_t w, int j) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)j)); }
+// rgb_to_ycbcr + quantize_ycbcr (IMG:47-56,69-78) on magic-form bytes -> 13-trit pixel value.
+// fma(c, 2^23+x, -c*2^23) = fl(c*x) exactly (c*2^23 is representable, the fma rounds once), 0.5*x is exact.
+__device__ __forceinline__ uint32_t rgb_to_value3(float R, float G, float B)
+{
+    constexpr float T23 = 8388608.0f;
+    const float y = __fadd_rn(__fadd_rn(__fmaf_rn(0.299f, R, -0.299f * T23), __fmaf_rn(0.587f, G, -0.587f * T23)), __fmaf_rn(0.114f, B, -0.114f * T23));
+    const float cb = __fadd_rn(__fadd_rn(__fsub_rn(__fmaf_rn(-0.168736f, R, 0.168736f * T23), __fmaf_rn(0.331264f, G, -0.331264f * T23)),
+                                         __fmaf_rn(0.5f, B, -0.5f * T23)), 128.0f);
+    const float cr = __fadd_rn(__fsub_rn(__fsub_rn(__fmaf_rn(0.5f, R, -0.5f * T23), __fmaf_rn(0.418688f, G, -0.418688f * T23)),
+                                         __fmaf_rn(0.081312f, B, -0.081312f * T23)), 128.0f);
+    // floor(v + 0.5) into the low mantissa bits, offset by Z: both adds round down, the second one is exact on integers
+    const uint32_t by = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(y, 0.5f), T23 + (float)QY_Z));
+    const uint32_t bb = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(cb, 0.5f), T23 + (float)QC_Z));
+    const uint32_t br = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(cr, 0.5f), T23 + (float)QC_Z));
+    const uint32_t fy = mad_hi(by, QY_M, Q_CONST);
+    return fy + 243u * __umulhi(bb, QC_M) + 19683u * __umulhi(br, QC_M);
+}
+// pixel value -> RGB8 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84), arithmetic only
+__device__ __forceinline__ uint32_t value_to_rgb3(uint32_t A)
+{
+    const uint32_t q = __umulhi(A, 17674763u);                 // A / 243, exact for A < 3^13
+    const uint32_t Yq = A - 243u * q;
+    const uint32_t ur = __umulhi(q, 53024288u);                // q / 81, exact for q < 6561
+    const uint32_t ub = q - 81u * ur;
+    // Y = (510 Yq + 241) / 484 (dev.cuh dequant_y; <= 255 for Yq <= 242), C = min((64 u + 10) / 20, 255)
+    const float y = __fadd_rn(__uint_as_float(mad_hi(Yq * 510u + 241u, 8873899u, 0x4B000000u)), -8388608.0f);
+    const float cb = __fadd_rn(__uint_as_float(min(mad_hi(32u * ub + 5u, 429496730u, 0x4B000000u), 0x4B0000FFu)), -8388736.0f);
+    const float cr = __fadd_rn(__uint_as_float(min(mad_hi(32u * ur + 5u, 429496730u, 0x4B000000u), 0x4B0000FFu)), -8388736.0f);
+    const float r = __fadd_rn(y, __fmul_rn(1.402f, cr));
+    const float g = __fsub_rn(__fsub_rn(y, __fmul_rn(0.344136f, cb)), __fmul_rn(0.714136f, cr));
+    const float b = __fadd_rn(y, __fmul_rn(1.772f, cb));
+    const uint32_t Rb = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(fminf(fmaxf(r, 0.0f), 255.0f), 0.5f), 8388608.0f));
+    const uint32_t Gb = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(fminf(fmaxf(g, 0.0f), 255.0f), 0.5f), 8388608.0f));
+    const uint32_t Bb = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(fminf(fmaxf(b, 0.0f), 255.0f), 0.5f), 8388608.0f));
+    return __byte_perm(__byte_perm(Rb, Gb, 0x0040), Bb, 0x7410) & 0x00FFFFFFu; // R | G<<8 | B<<16
+}
+// 8-entry byte table through PRMT: nibble n of sel (3 plane bits b0 b1 b2) -> b0 + 3 b1 + 9 b2
+__device__ __forceinline__ uint32_t planes4_to_sym(uint32_t sel) { return __byte_perm(0x04030100u, 0x0D0C0A09u, sel); }
+
+template <int K> struct Cfg3 {
+    static_assert(K == 20 || K == 22 || K == 24, "the 8+4j+c plane layout holds r <= 6 parity symbols");
+    static constexpr int R = 26 - K;
+    static constexpr int TRIPLES = 9 * K, PX = 27 * K, RGB_BYTES = 81 * K, SYM = 117 * K, UNITS = TRIPLES / 2;
+    static constexpr int NCW = 9 * C_MINI, RUN = 26 * C_MINI;
+    static constexpr int PASS_A = (UNITS + 31) / 32, PASS_B = (NCW + 31) / 32;
+    static constexpr int RUN_PITCH = 368;
+    static constexpr int S_BYTES = (SYM + 15) / 16 * 16;
+    static constexpr int RGB_PITCH = (RGB_BYTES + 15 + 15) / 16 * 16 + 16;
+    static constexpr int U_BYTES = RGB_PITCH > 9 * RUN_PITCH ? RGB_PITCH : 9 * RUN_PITCH;
+    static constexpr int META_BYTES = 96;               // run_lo[9] (u64) | vb[9] (u8)
+    static constexpr int WARP_BYTES = S_BYTES + U_BYTES + META_BYTES;
+    // encode, CTA-shared: A[3][K][27] | B[K][27] | pat[3][2]
+    static constexpr int ENC_A = 0, ENC_B = ENC_A + 4 * 3 * K * 27, ENC_PAT = ENC_B + 4 * K * 27, ENC_WARP = (ENC_PAT + 24 + 15) / 16 * 16;
+    static constexpr int TOTAL_ENC = ENC_WARP + FAST_WARPS * WARP_BYTES;
+    // decode, CTA-shared: A[3][26][32] | B[26][32] | chk[3][2] | GF(27) tables of the slow path
+    static constexpr int DEC_A = 0, DEC_B = DEC_A + 4 * 3 * 26 * 32, DEC_CHK = DEC_B + 4 * 26 * 32, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
+    static constexpr int DEC_WARP = DEC_GF + ((int)sizeof(GfTables) + 15) / 16 * 16;
+    static constexpr int TOTAL_DEC = DEC_WARP + FAST_WARPS * WARP_BYTES;
+};
+struct WarpMeta3 { uint64_t run_lo[9]; uint8_t vb[16]; };
+static_assert(sizeof(WarpMeta3) <= 96, "meta3");
+
+// the six (periodic) scrambler states seen by a codeword of variant v (= codeword index mod 3) at position i
+__device__ __forceinline__ uint32_t st_of(const Geom& g, int v, int i) { return g.st[2 + (2 * v + i + 4) % 6]; }
+
+__device__ __forceinline__ void setup_runs3(WarpMeta3& m, const Geom& g, uint64_t frame_off, uint32_t tile, int lane)
+{
+    if (lane < 9) {
+        const uint64_t cwi = g.cw_base[lane] + (uint64_t)C_MINI * tile;
+        m.run_lo[lane] = frame_off + 52 + 26 * cwi;
+        m.vb[lane] = (uint8_t)(cwi % 3);
+    }
+}
+// nine full runs shared -> global (see warp_store_runs9)
+template <int PITCH>
+__device__ __forceinline__ void warp_store_runs9_full(const uint8_t* O, uint8_t* __restrict__ gbase, const WarpMeta3& m, int lane)
+{
+    constexpr int len = 26 * C_MINI;
+#pragma unroll 1
+    for (int b = 0; b < 9; ++b) {
+        const uint64_t lo = m.run_lo[b];
+        const int pad = (int)(lo & 15), end = pad + len;
+        uint8_t* g0 = gbase + (lo - pad);
+        const uint8_t* s0 = O + PITCH * b;
+        const int c16 = 16 * lane;
+        if (c16 >= pad && c16 + 16 <= end) *reinterpret_cast<uint4*>(g0 + c16) = *reinterpret_cast<const uint4*>(s0 + c16);
+        const int pos = lane < 16 ? lane : (end & ~15) + (lane - 16);
+        if (pos >= pad && pos < end && (lane < 16 ? pad != 0 : (end & 15) != 0)) g0[pos] = s0[pos];
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+{
+    using L = Cfg3<K>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* S = smem + L::ENC_WARP + warp * L::WARP_BYTES;     // stream symbols, pre-scaled by 4
+    uint8_t* U = S + L::S_BYTES;                                // RGB run, later the nine body runs
+    WarpMeta3& meta = *reinterpret_cast<WarpMeta3*>(U + L::U_BYTES);
+    {
+        uint32_t* A = reinterpret_cast<uint32_t*>(smem + L::ENC_A);
+        uint32_t* B = reinterpret_cast<uint32_t*>(smem + L::ENC_B);
+        const uint32_t(*pl)[kVals][2] = rs->pl[g.arith][(24 - K) / 2];
+        for (int idx = tid; idx < 3 * K * 27; idx += FAST_TPB) {
+            const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
+            A[idx] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
+            if (v == 0) B[rem] = pl[i][d][1];
+        }
+        if (tid < 3) { // the scrambler as seen by the parity symbols of a variant-tid codeword, in the plane domain
+            uint32_t nz = 0, two = 0;
+            for (int j = 0; j < L::R; ++j) {
+                const uint32_t st = st_of(g, tid, K + j);
+                if (st) nz |= 7u << (8 + 4 * j);
+                if (st == 2) two |= 7u << (8 + 4 * j);
+            }
+            reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid] = nz;
+            reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid + 1] = two;
+        }
+    }
+    __syncthreads(); // the only block-level barrier: tables staged
+    const uint8_t* tabA = smem + L::ENC_A;
+    const uint8_t* tabB = smem + L::ENC_B;
+    const uint32_t* pat = reinterpret_cast<const uint32_t*>(smem + L::ENC_PAT);
+    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
+    const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
+    for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
+        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = P.tile0 + (uint32_t)(mt - (uint64_t)f * P.n_tiles);
+        const uint64_t g_lo = P.in_stride * f + 3ull * L::PX * tile;
+        const uint32_t pad = (uint32_t)(g_lo & 15);
+        setup_runs3(meta, g, P.out_stride * f, tile, lane);
+        warp_load_run(U, P.in, g_lo, g_lo + L::RGB_BYTES, P.in_stride * P.n_frames, lane);
+        __syncwarp();
+        // ---- phase A: six pixels (18 bytes) -> 26 stream symbols (x4) per lane; units dealt even / odd so that the
+        // 18- and 26-byte lane strides become 36 and 52 bytes: 9 and 13 words, conflict-free
+#pragma unroll 1
+        for (int pass = 0; pass < L::PASS_A; ++pass) {
+            const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+            if (u >= L::UNITS) continue;
+            const uint32_t a = pad + 18u * (uint32_t)u;
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
+            const uint32_t sh = (a & 3u) * 8u;
+            uint32_t x[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) x[j] = mw[j];
+            uint32_t y[5]; // the 18 bytes, word aligned
+#pragma unroll
+            for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+            y[4] = x[4] >> sh;
+            uint32_t A[6];
+#pragma unroll
+            for (int p = 0; p < 6; ++p) {
+                const int q = 3 * p;
+                A[p] = rgb_to_value3(byte_magic(y[q >> 2], q & 3), byte_magic(y[(q + 1) >> 2], (q + 1) & 3), byte_magic(y[(q + 2) >> 2], (q + 2) & 3));
+            }
+            uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
+            triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
+            triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
+            w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
+            uint16_t* d = reinterpret_cast<uint16_t*>(S + 26 * u);
+            d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
+            d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
+            d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
+            d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+        }
+        __syncwarp();
+        // ---- phase B: one codeword per lane, row-major (cw = 9*row + band)
+#pragma unroll 1
+        for (int pass = 0; pass < L::PASS_B; ++pass) {
+            const int cw = 32 * pass + lane;
+            if (cw >= L::NCW) continue;
+            const int cl = cw / 9, b = cw - 9 * cl;
+            const uint32_t v = ((uint32_t)meta.vb[b] + (uint32_t)cl) % 3u;
+            const uint8_t* pa = tabA + v * (K * 108);
+            const uint8_t* src = S + 9 * K * cl + b;
+            uint8_t* dst = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
+            Planes acc{0, 0}, acc2{0, 0};
+            uint32_t prev = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t d4 = src[9 * i];
+                const uint32_t ea = *reinterpret_cast<const uint32_t*>(pa + d4 + 108 * i);
+                const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + d4 + 108 * i);
+                if (i & 1) { gf3_add(acc2, ea, eb); *reinterpret_cast<uint16_t*>(dst + i - 1) = (uint16_t)__byte_perm(prev, ea, 0x0040); }
+                else { gf3_add(acc, ea, eb); prev = ea; }
+            }
+            gf3_add(acc, acc2.nz, acc2.two);
+            gf3_add(acc, pat[2 * v], pat[2 * v + 1]);
+            const uint32_t nzp = acc.nz >> 8, twp = acc.two >> 8;
+            const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
+            *reinterpret_cast<uint16_t*>(dst + K) = (uint16_t)lo;
+            if (L::R > 2) *reinterpret_cast<uint16_t*>(dst + K + 2) = (uint16_t)(lo >> 16);
+            if (L::R > 4) {
+                const uint32_t hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
+                *reinterpret_cast<uint16_t*>(dst + K + 4) = (uint16_t)hi;
+            }
+        }
+        __syncwarp();
+        if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0 and 1 may still see the scrambler's transient (A.4)
+            uint8_t* dst = U + ((uint32_t)meta.run_lo[0] & 15u);
+            dst[0] = gf->scr[g.st[0]][S[0] >> 2];
+            dst[1] = gf->scr[g.st[1]][S[9] >> 2];
+        }
+        __syncwarp();
+        // ---- phase C: nine band-major runs -> global
+        warp_store_runs9_full<L::RUN_PITCH>(U, P.out, meta, lane);
+        __syncwarp();
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+{
+    using L = Cfg3<K>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* S = smem + L::DEC_WARP + warp * L::WARP_BYTES;     // descrambled stream symbols (plain)
+    uint8_t* U = S + L::S_BYTES;                                // the nine body runs (x4), later the RGB run
+    WarpMeta3& meta = *reinterpret_cast<WarpMeta3*>(U + L::U_BYTES);
+    GfTables& sg = *reinterpret_cast<GfTables*>(smem + L::DEC_GF);
+    {
+        uint32_t* A = reinterpret_cast<uint32_t*>(smem + L::DEC_A);
+        uint32_t* B = reinterpret_cast<uint32_t*>(smem + L::DEC_B);
+        const uint32_t(*pl)[kVals][2] = rs->pl[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
+        for (int idx = tid; idx < 3 * 26 * 32; idx += FAST_TPB) {
+            const int v = idx / (26 * 32), rem = idx - v * (26 * 32), i = rem / 32, x = rem - 32 * i, xm = x >= 27 ? x - 27 : x;
+            A[idx] = pl[i][xm][0] | gf->dsc[st_of(g, v, i)][xm];
+            if (v == 0) B[rem] = pl[i][xm][1];
+        }
+        load_gf(sg, gf);
+    }
+    __syncthreads();
+    if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
+        Planes c{0, 0};
+        for (int i = 0; i < 26; ++i) {
+            const int idx = i * 32 + 13 * (int)st_of(g, tid, i);
+            gf3_add(c, reinterpret_cast<const uint32_t*>(smem + L::DEC_A)[idx] & ~0xFFu, reinterpret_cast<const uint32_t*>(smem + L::DEC_B)[idx]);
+        }
+        reinterpret_cast<uint32_t*>(smem + L::DEC_CHK)[2 * tid] = c.nz;
+        reinterpret_cast<uint32_t*>(smem + L::DEC_CHK)[2 * tid + 1] = c.two;
+    }
+    __syncthreads();
+    const uint8_t* tabA = smem + L::DEC_A;
+    const uint8_t* tabB = smem + L::DEC_B;
+    const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L::DEC_CHK);
+    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
+    const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
+    const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
+    for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
+        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = P.tile0 + (uint32_t)(mt - (uint64_t)f * P.n_tiles);
+        setup_runs3(meta, g, P.in_stride * f, tile, lane);
+        __syncwarp();
+        // ---- nine runs -> shared, every byte scaled by 4 (table byte offset).  Bytes >= 32 would leave the 32-entry
+        // rows: they are reduced mod 27 first (out-of-alphabet symbols read as their low three trits, OLD:28-31)
+        bool wild = false;
+#pragma unroll 1
+        for (int b = 0; b < 9; ++b) {
+            const uint64_t lo = meta.run_lo[b];
+            const int padb = (int)(lo & 15), c16 = 16 * lane;
+            if (c16 < padb + L::RUN) {
+                const uint64_t ga = (lo - padb) + c16;
+                uint4 q;
+                if (ga + 16 <= in_limit) q = __ldg(reinterpret_cast<const uint4*>(P.in + ga));
+                else { // the last chunk of the last frame may poke past the buffer
+                    uint32_t t[4] = {0, 0, 0, 0};
+                    for (int i = 0; i < 16; ++i) if (ga + i < in_limit) t[i >> 2] |= (uint32_t)P.in[ga + i] << (8 * (i & 3));
+                    q = make_uint4(t[0], t[1], t[2], t[3]);
+                }
+                wild |= ((q.x | q.y | q.z | q.w) & 0xE0E0E0E0u) != 0;
+                q.x <<= 2; q.y <<= 2; q.z <<= 2; q.w <<= 2;
+                *reinterpret_cast<uint4*>(U + L::RUN_PITCH * b + c16) = q;
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, wild)) { // rare: reload those chunks byte by byte
+#pragma unroll 1
+            for (int b = 0; b < 9; ++b) {
+                const uint64_t lo = meta.run_lo[b];
+                const int padb = (int)(lo & 15), c16 = 16 * lane;
+                if (c16 < padb + L::RUN)
+                    for (int i = 0; i < 16; ++i) {
+                        const uint64_t ga = (lo - padb) + c16 + i;
+                        U[L::RUN_PITCH * b + c16 + i] = (uint8_t)(ga < in_limit ? 4u * (P.in[ga] % 27u) : 0u);
+                    }
+            }
+        }
+        __syncwarp();
+        if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0,1: move them from the transient states to the periodic ones
+            uint8_t* r0 = U + ((uint32_t)meta.run_lo[0] & 15u);
+            r0[0] = (uint8_t)(4u * sg.scr[st_of(g, 0, 0)][sg.dsc[g.st[0]][(r0[0] >> 2) % 27u]]);
+            r0[1] = (uint8_t)(4u * sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][(r0[1] >> 2) % 27u]]);
+        }
+        __syncwarp();
+        // ---- phase B: syndrome screen per codeword (row-major lanes); descrambled data symbols -> stream order
+#pragma unroll 1
+        for (int pass = 0; pass < L::PASS_B; ++pass) {
+            const int cw = 32 * pass + lane;
+            if (cw >= L::NCW) continue;
+            const int cl = cw / 9, b = cw - 9 * cl;
+            const uint32_t v = ((uint32_t)meta.vb[b] + (uint32_t)cl) % 3u;
+            const uint8_t* pa = tabA + v * (26 * 128);
+            const uint8_t* src = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
+            uint8_t* dst = S + 9 * K * cl + b;
+            Planes acc{0, 0}, acc2{0, 0};
+#pragma unroll
+            for (int i = 0; i < 26; ++i) {
+                const uint32_t x4 = src[i];
+                const uint32_t ea = *reinterpret_cast<const uint32_t*>(pa + x4 + 128 * i);
+                const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + x4 + 128 * i);
+                if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+                if (i < K) dst[9 * i] = (uint8_t)ea;
+            }
+            gf3_add(acc, acc2.nz, acc2.two);
+            if (((acc.nz ^ chk[2 * v]) | (acc.two ^ chk[2 * v + 1])) & ~0xFFu) { // the low bytes carry the embedded symbols
+                // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
+                uint8_t cwd[26], orig[26];
+                for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(pa + src[i] + 128 * i);
+                if (!rs_decode_thread(sg, cwd, K, true)) {
+                    atomicExch(&P.status[2 * f], 0u);
+                } else {
+                    uint32_t nfix = 0;
+                    for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
+                    if (nfix) atomicAdd(&P.status[2 * f + 1], nfix);
+                    for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- phase A: 26 stream symbols -> six pixels -> 18 RGB bytes per lane (units dealt even / odd)
+        const uint64_t g_lo = P.out_stride * f + 3ull * L::PX * tile;
+        const uint32_t pad = (uint32_t)(g_lo & 15);
+#pragma unroll 1
+        for (int pass = 0; pass < L::PASS_A; ++pass) {
+            const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+            if (u >= L::UNITS) continue;
+            const uint32_t a = 26u * (uint32_t)u;
+            const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+            const uint32_t sh = (a & 2u) * 8u;
+            uint32_t x[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) x[j] = mw[j];
+            uint32_t y[7]; // the 26 symbols, word aligned
+#pragma unroll
+            for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+            y[6] = x[6] >> sh;
+            uint32_t A[6];
+            symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+            symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+            uint32_t p[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) p[q] = value_to_rgb3(A[q]);
+            uint16_t* dh = reinterpret_cast<uint16_t*>(U + pad + 18 * u); // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { // two pixels = three halfwords
+                dh[3 * q] = (uint16_t)p[2 * q];
+                dh[3 * q + 1] = (uint16_t)((p[2 * q] >> 16) | (p[2 * q + 1] << 8));
+                dh[3 * q + 2] = (uint16_t)(p[2 * q + 1] >> 8);
+            }
+        }
+        __syncwarp();
+        warp_store_run(U, P.out, g_lo, L::RGB_BYTES, lane);
+        __syncwarp();
+    }
+}
+
+template <class Kern>
+int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st, int& ctas_per_sm)
+{
     if (!ctas_per_sm) {
-        cudaFuncSetAttribute(k_encode_rgb_fast<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<K>::TOTAL_ENC);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_encode_rgb_fast<K>, FAST_TPB, Cfg<K>::TOTAL_ENC);
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, FAST_TPB, smem_bytes);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
@@ -484,25 +876,43 @@ int launch_enc(const DevTables& T, const FastParams& P, const Geom& g, cudaStrea
     const uint64_t need = (total + FAST_WARPS - 1) / FAST_WARPS;
     if (grid > need) grid = need;
     if (!grid) return 0;
-    k_encode_rgb_fast<K><<<(unsigned)grid, FAST_TPB, Cfg<K>::TOTAL_ENC, st>>>(P, g, T.gf, T.rs);
+    kern<<<(unsigned)grid, FAST_TPB, smem_bytes, st>>>(P, g, T.gf, T.rs);
     return 1;
 }
+// tiles [0, n_full) of every frame go to the v3 kernels, the ragged rest to the general-tile kernels
 template <int K>
-int launch_dec(const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st)
+int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full)
 {
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) {
-        cudaFuncSetAttribute(k_decode_rgb_fast<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<K>::TOTAL_DEC);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_decode_rgb_fast<K>, FAST_TPB, Cfg<K>::TOTAL_DEC);
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
-    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
-    uint64_t grid = (uint64_t)T.sm_count * ctas_per_sm;
-    const uint64_t need = (total + FAST_WARPS - 1) / FAST_WARPS;
-    if (grid > need) grid = need;
-    if (!grid) return 0;
-    k_decode_rgb_fast<K><<<(unsigned)grid, FAST_TPB, Cfg<K>::TOTAL_DEC, st>>>(P, g, T.gf, T.rs);
-    return 1;
+    static int occ3 = 0, occ2 = 0;
+    const uint32_t n_all = P.n_tiles;
+    int n = 0;
+    if constexpr (K >= 20) {
+        if (n_full) { P.tile0 = 0; P.n_tiles = n_full; n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3); }
+    } else n_full = 0;
+    if (n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_encode_rgb_fast<K>, Cfg<K>::TOTAL_ENC, T, P, g, st, occ2); }
+    return n;
+}
+template <int K>
+int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full)
+{
+    static int occ3 = 0, occ2 = 0;
+    const uint32_t n_all = P.n_tiles;
+    int n = 0;
+    if constexpr (K >= 20) {
+        if (n_full) { P.tile0 = 0; P.n_tiles = n_full; n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3); }
+    } else n_full = 0;
+    if (n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_decode_rgb_fast<K>, Cfg<K>::TOTAL_DEC, T, P, g, st, occ2); }
+    return n;
+}
+// mini-tiles of a frame whose 117 codewords all exist and whose 27k pixels lie inside [0, px_limit)
+uint32_t full_tiles(const Geom& g, uint64_t px_limit)
+{
+    uint64_t mn = ~0ull;
+    for (int b = 0; b < 9; ++b) mn = g.ncw[b] < mn ? g.ncw[b] : mn;
+    uint64_t n = mn / C_MINI;
+    const uint64_t by_px = px_limit / (27ull * (uint64_t)g.uniform_k);
+    if (by_px < n) n = by_px;
+    return (uint32_t)n;
 }
 
 } // namespace
@@ -528,11 +938,13 @@ int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
     P.n_tiles = (uint32_t)((mx + C_MINI - 1) / C_MINI);
     int n = 0;
+    const uint64_t px_have = n_px < 2 * g.n_words ? n_px : 2 * g.n_words;
+    const uint32_t n_full = full_tiles(g, px_have);
     switch (g.uniform_k) {
-    case 24: n = launch_enc<24>(T, P, g, st); break;
-    case 22: n = launch_enc<22>(T, P, g, st); break;
-    case 20: n = launch_enc<20>(T, P, g, st); break;
-    case 18: n = launch_enc<18>(T, P, g, st); break;
+    case 24: n = launch_enc<24>(T, P, g, st, n_full); break;
+    case 22: n = launch_enc<22>(T, P, g, st, n_full); break;
+    case 20: n = launch_enc<20>(T, P, g, st, n_full); break;
+    case 18: n = launch_enc<18>(T, P, g, st, n_full); break;
     default: return 0;
     }
     return n + launch_frame_misc(T, cfg, g, out, n_frames, 9ull * stride_words, st);
@@ -554,11 +966,13 @@ int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
     P.n_tiles = (uint32_t)((mx + C_MINI - 1) / C_MINI);
+    // v3 writes RGB with 2-byte stores: every frame has to start on an even byte
+    const uint32_t n_full = (n_frames > 1 && (n_px & 1)) ? 0 : full_tiles(g, n_px_out);
     switch (g.uniform_k) {
-    case 24: return launch_dec<24>(T, P, g, st);
-    case 22: return launch_dec<22>(T, P, g, st);
-    case 20: return launch_dec<20>(T, P, g, st);
-    case 18: return launch_dec<18>(T, P, g, st);
+    case 24: return launch_dec<24>(T, P, g, st, n_full);
+    case 22: return launch_dec<22>(T, P, g, st, n_full);
+    case 20: return launch_dec<20>(T, P, g, st, n_full);
+    case 18: return launch_dec<18>(T, P, g, st, n_full);
     }
     return 0;
 }

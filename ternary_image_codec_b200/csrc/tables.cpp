@@ -111,6 +111,17 @@ void build_tables(HostTables& T)
                     if (i < k) for (int j = 0; j < r; ++j) v[j] = mul(d, T.rs.par[arith][ki][i][j]);
                     else v[i - k] = gneg(d);
                     R.e[i][d] = planes_of(v, r);
+                    uint32_t nz = 0, two = 0;
+                    if (r <= 6)
+                        for (int j = 0; j < r; ++j) {
+                            Tr t = split(v[j]);
+                            for (int c = 0; c < 3; ++c) {
+                                if (t.t[c]) nz |= 1u << (8 + 4 * j + c);
+                                if (t.t[c] == 2) two |= 1u << (8 + 4 * j + c);
+                            }
+                        }
+                    T.rs.pl[arith][ki][i][d][0] = nz;
+                    T.rs.pl[arith][ki][i][d][1] = two;
                 }
         }
     }

@@ -454,3 +454,59 @@ def test_multi_frame_stream_device(codec, oracle, t3):
     got = codec.encode_frames_rgb8(frames, gc, t3.REF_EXACT)
     for f in range(F):
         assert np.array_equal(got[f], oracle.encode_rgb(oc, frames[f], 0))
+
+
+@pytest.mark.parametrize("uep", [2, 1, 0])
+def test_fused_fast_path_all_2_24_colours_match_general_kernels(codec, t3, uep):
+    """Every RGB colour once (a 4096x4096 frame) through the fused tiled kernels, against the stage-by-stage
+    general kernels on the device (those are pinned to the oracle exhaustively by test_bridge_exhaustive_2_24
+    and test_encode_profile): identical profile words, identical decoded RGB."""
+    import torch
+    dev = torch.device("cuda", 0)
+    s = torch.cuda.current_stream().cuda_stream
+    _, gc = both(dict(profile=T.P3, uep=uep))
+    assert t3.fast_path_available(gc)
+    n_px = 1 << 24
+    idx = torch.arange(n_px, dtype=torch.int32, device=dev)
+    rgb = torch.stack([(idx >> 16) & 255, (idx >> 8) & 255, idx & 255], dim=1).to(torch.uint8).contiguous().view(-1)
+    wpf = t3.profile_words(gc, n_px // 2)
+    enc = torch.zeros(wpf * 9, dtype=torch.uint8, device=dev)
+    codec.encode_frames_rgb8_dev(rgb, n_px, 1, enc, wpf, gc, t3.FIXED, s)
+    q = torch.empty(n_px * 6, dtype=torch.uint8, device=dev)
+    raw = torch.empty(n_px // 2 * 9, dtype=torch.uint8, device=dev)
+    enc2 = torch.zeros_like(enc)
+    codec.rgb_to_quant_dev(rgb, n_px, q, s)
+    codec.pack_pixels_dev(q, n_px, raw, s)
+    codec.encode_profile_dev(raw, n_px // 2, enc2, wpf, gc, t3.FIXED, s)
+    torch.cuda.synchronize()
+    assert torch.equal(enc, enc2)
+    back = torch.zeros(n_px * 3, dtype=torch.uint8, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    codec.decode_frames_rgb8_dev(enc, wpf, wpf, 1, n_px, back, status, gc, s)
+    want = torch.zeros_like(back)
+    codec.quant_to_rgb_dev(q, n_px, want, s)
+    torch.cuda.synchronize()
+    assert status.tolist() == [1, 0]
+    n_ok = 3 * (n_px - 2000)  # the encoder drops < k symbols per band at the very end (bug B8)
+    assert torch.equal(back[:n_ok], want[:n_ok])
+
+
+def test_fused_fast_path_out_of_alphabet_and_uncorrectable(codec, oracle, t3):
+    """bytes >= 27 in a received stream read as their low three trits (unpack3, OLD:28-31), and a codeword with
+    more than t errors makes the frame fail: same verdicts and pixels as the oracle's consistent decoder"""
+    oc, gc = both(dict(profile=T.P3, uep=2))
+    n_px = 4 * 540 + 77
+    rgb = T.synth_rgb(5, n_px)
+    enc = codec.encode_frames_rgb8(rgb[None], gc, t3.FIXED)[0]
+    wild = enc.copy().reshape(-1)
+    r = rng(3)
+    pos = 52 + r.choice(wild.size - 60, 300, replace=False)
+    wild[pos] = wild[pos] + 27 * r.integers(1, 9, pos.size).astype(np.uint8)   # same symbol mod 27
+    ok, back, nc = codec.decode_frames_rgb8(wild.reshape(1, -1, 9), n_px, gc)
+    ok_o, back_o, nc_o = oracle.decode_rgb_fixed(oc, wild.reshape(-1, 9), n_px)
+    assert ok.all() and ok_o and nc == nc_o == 0 and np.array_equal(back[0], back_o)
+    bad = enc.copy().reshape(-1)
+    bad[52 + 26 * 7: 52 + 26 * 7 + 5] = (bad[52 + 26 * 7: 52 + 26 * 7 + 5] + 1) % 27     # 5 errors > t = 3
+    ok2, _, _ = codec.decode_frames_rgb8(bad.reshape(1, -1, 9), n_px, gc)
+    ok2_o, _, _ = oracle.decode_rgb_fixed(oc, bad.reshape(-1, 9), n_px)
+    assert bool(ok2[0]) == bool(ok2_o)
