@@ -12,6 +12,8 @@
 // access is a 128-bit transfer inside a contiguous run (one RGB run, nine body runs of 338 B), the 9-band
 // transpose and all table look-ups stay in shared memory, the grid is persistent (SM count x resident CTAs)
 // so the row table is staged once per CTA, and HBM traffic is exactly the algorithmic 3 B/px + 9 B/word.
+#include <type_traits>
+
 #include "dev.cuh"
 #include "launch.h"
 
@@ -549,13 +551,16 @@ template <int K> struct Cfg3 {
     static constexpr int RGB_PITCH = (RGB_BYTES + 15 + 15) / 16 * 16 + 16;
     static constexpr int U_BYTES = RGB_PITCH > 9 * RUN_PITCH ? RGB_PITCH : 9 * RUN_PITCH;
     static constexpr int META_BYTES = 96;               // run_lo[9] (u64) | vb[9] (u8)
-    static constexpr int WARP_BYTES = S_BYTES + U_BYTES + META_BYTES;
+    static constexpr int CARRY_BYTES = 9 * 16;          // the partial last 16-byte chunk of every output stream, kept for the next tile
+    static constexpr int WARP_BYTES = S_BYTES + U_BYTES + META_BYTES + CARRY_BYTES;
     // encode, CTA-shared: A[3][K][27] | B[K][27] | pat[3][2]
-    static constexpr int ENC_A = 0, ENC_B = ENC_A + 4 * 3 * K * 27, ENC_PAT = ENC_B + 4 * K * 27, ENC_WARP = (ENC_PAT + 24 + 15) / 16 * 16;
+    static_assert(RUN_PITCH == 16 * 23, "chunk slots per run");
+    static constexpr int ENC_A = 0, ENC_B = ENC_A + 4 * 3 * K * 27, ENC_PAT = ENC_B + 4 * K * 27, ENC_MAP = (ENC_PAT + 24 + 15) / 16 * 16, ENC_WARP = ENC_MAP + 3 * 128;
     static constexpr int TOTAL_ENC = ENC_WARP + FAST_WARPS * WARP_BYTES;
     // decode, CTA-shared: A[3][26][32] | B[26][32] | chk[3][2] | GF(27) tables of the slow path
     static constexpr int DEC_A = 0, DEC_B = DEC_A + 4 * 3 * 26 * 32, DEC_CHK = DEC_B + 4 * 26 * 32, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
-    static constexpr int DEC_WARP = DEC_GF + ((int)sizeof(GfTables) + 15) / 16 * 16;
+    static constexpr int DEC_MAP = DEC_GF + ((int)sizeof(GfTables) + 15) / 16 * 16;
+    static constexpr int DEC_WARP = DEC_MAP + 3 * 128;
     static constexpr int TOTAL_DEC = DEC_WARP + FAST_WARPS * WARP_BYTES;
 };
 struct WarpMeta3 { uint64_t run_lo[9]; uint8_t vb[16]; };
@@ -572,22 +577,62 @@ __device__ __forceinline__ void setup_runs3(WarpMeta3& m, const Geom& g, uint64_
         m.vb[lane] = (uint8_t)(cwi % 3);
     }
 }
-// nine full runs shared -> global (see warp_store_runs9)
-template <int PITCH>
-__device__ __forceinline__ void warp_store_runs9_full(const uint8_t* O, uint8_t* __restrict__ gbase, const WarpMeta3& m, int lane)
+// Output streams are written as whole 16-byte chunks only.  A warp owns a contiguous range of mini-tiles, so the
+// partial chunk at the end of a tile's run is completed by the same warp's next tile: it is parked in `carry` and
+// restored at offset 0 of the next staging buffer.  Only the first / last tile of a range (or of a frame) writes
+// edge bytes one by one.  len = bytes of this tile's piece, piece at staging offset pad = lo & 15.
+__device__ __forceinline__ void stream_store(const uint8_t* s0, uint8_t* __restrict__ gbase, uint64_t lo, int len, bool first, bool last, uint4* carry, int lane)
 {
-    constexpr int len = 26 * C_MINI;
-#pragma unroll 1
-    for (int b = 0; b < 9; ++b) {
-        const uint64_t lo = m.run_lo[b];
-        const int pad = (int)(lo & 15), end = pad + len;
-        uint8_t* g0 = gbase + (lo - pad);
-        const uint8_t* s0 = O + PITCH * b;
-        const int c16 = 16 * lane;
-        if (c16 >= pad && c16 + 16 <= end) *reinterpret_cast<uint4*>(g0 + c16) = *reinterpret_cast<const uint4*>(s0 + c16);
-        const int pos = lane < 16 ? lane : (end & ~15) + (lane - 16);
-        if (pos >= pad && pos < end && (lane < 16 ? pad != 0 : (end & 15) != 0)) g0[pos] = s0[pos];
+    const int pad = (int)(lo & 15), end = pad + len, cend = end >> 4;
+    uint8_t* g0 = gbase + (lo - pad);
+    const int c0 = (first && pad) ? 1 : 0;
+    for (int c = c0 + lane; c < cend; c += 32) *reinterpret_cast<uint4*>(g0 + 16 * c) = *reinterpret_cast<const uint4*>(s0 + 16 * c);
+    if (first && pad) { if (lane >= pad && lane < 16 && lane < end) g0[lane] = s0[lane]; }
+    if (last) { const int pos = 16 * cend + lane; if (lane < 16 && pos < end && !(c0 && cend == 0)) g0[pos] = s0[pos]; }
+    else if (lane == 0) *carry = *reinterpret_cast<const uint4*>(s0 + 16 * cend);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// read-only table word at shared address a + OFF.  Deliberately not volatile: the tables never change after the
+// kernel's first barrier, so the compiler may schedule these loads freely.
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_tab(uint32_t a)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
     }
+}
+// Phase-B lane -> codeword map.  A codeword's table variant is (band offset + tile + row) mod 3; passes 0..2 take 32
+// codewords of one variant each (all lanes then read the same 27-entry block of table A: no bank conflicts), pass 3
+// the remaining 21.  One 128-byte map per tile mod 3; 255 = idle lane.
+__device__ void build_pass_map(uint8_t* map, const Geom& g, int tm)
+{
+    int n0 = 0, n1 = 0, n2 = 0, extra = 96;
+    uint32_t cwb = 0; // cw_base[b] mod 3, two bits per band
+    for (int b = 0; b < 9; ++b) cwb |= (uint32_t)(g.cw_base[b] % 3) << (2 * b);
+    for (int cw = 0; cw < 9 * C_MINI; ++cw) {
+        const int cl = cw / 9, b = cw - 9 * cl;
+        const int v = (int)(((cwb >> (2 * b)) & 3u) + (uint32_t)tm + (uint32_t)cl) % 3;
+        int& n = v == 0 ? n0 : (v == 1 ? n1 : n2);
+        if (n < 32) map[32 * v + n++] = (uint8_t)cw; else map[extra++] = (uint8_t)cw;
+    }
+    for (; extra < 128; ++extra) map[extra] = 255;
+}
+// the nine staged runs <-> global in whole 16-byte chunks, flattened over (band, chunk): 9 x 23 slots in 7 steps
+constexpr int RUN_SLOTS = 23;
+// contiguous share of [0, total) for warp gw of nw
+__device__ __forceinline__ void warp_range(uint64_t total, uint32_t gw, uint32_t nw, uint32_t& lo, uint32_t& hi)
+{
+    lo = (uint32_t)(total * gw / nw);
+    hi = (uint32_t)(total * (gw + 1) / nw);
 }
 
 template <int K>
@@ -618,19 +663,23 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid] = nz;
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid + 1] = two;
         }
+        if (tid >= 32 && tid < 35) build_pass_map(smem + L::ENC_MAP + 128 * (tid - 32), g, tid - 32);
     }
     __syncthreads(); // the only block-level barrier: tables staged
-    const uint8_t* tabA = smem + L::ENC_A;
+    const uint32_t tabA32 = smem_u32(smem + L::ENC_A);
     const uint8_t* tabB = smem + L::ENC_B;
     const uint32_t* pat = reinterpret_cast<const uint32_t*>(smem + L::ENC_PAT);
-    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
-    const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
-    for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
-        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = P.tile0 + (uint32_t)(mt - (uint64_t)f * P.n_tiles);
+    uint4* carry = reinterpret_cast<uint4*>(U + L::U_BYTES + L::META_BYTES);
+    uint32_t mt_lo, mt_hi;
+    warp_range((uint64_t)P.n_tiles * P.n_frames, blockIdx.x * FAST_WARPS + warp, gridDim.x * FAST_WARPS, mt_lo, mt_hi);
+    for (uint32_t mt = mt_lo; mt < mt_hi; ++mt) {
+        const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
+        const bool first = mt == mt_lo || tile == P.tile0, last = mt + 1 == mt_hi || tile + 1 == P.tile0 + P.n_tiles; // of a contiguous stretch
         const uint64_t g_lo = P.in_stride * f + 3ull * L::PX * tile;
         const uint32_t pad = (uint32_t)(g_lo & 15);
         setup_runs3(meta, g, P.out_stride * f, tile, lane);
         warp_load_run(U, P.in, g_lo, g_lo + L::RGB_BYTES, P.in_stride * P.n_frames, lane);
+        if (!last && lane < (L::RGB_BYTES + 127) / 128 && g_lo + L::RGB_BYTES + 128 * lane < P.in_stride * P.n_frames) prefetch_l2(P.in + g_lo + L::RGB_BYTES + 128 * lane); // the next tile's pixels
         __syncwarp();
         // ---- phase A: six pixels (18 bytes) -> 26 stream symbols (x4) per lane; units dealt even / odd so that the
         // 18- and 26-byte lane strides become 36 and 52 bytes: 9 and 13 words, conflict-free
@@ -665,30 +714,36 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
             d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
         }
         __syncwarp();
-        // ---- phase B: one codeword per lane, row-major (cw = 9*row + band)
+        if (!first && lane < 9) *reinterpret_cast<uint4*>(U + L::RUN_PITCH * lane) = carry[lane]; // bytes [0, pad) of each run: the previous tile's tail
+        __syncwarp();
+        // ---- phase B: one codeword per lane (lane -> codeword through the variant-sorted pass map)
+        const uint8_t* pmap = smem + L::ENC_MAP + 128 * (tile % 3u);
 #pragma unroll 1
         for (int pass = 0; pass < L::PASS_B; ++pass) {
-            const int cw = 32 * pass + lane;
-            if (cw >= L::NCW) continue;
-            const int cl = cw / 9, b = cw - 9 * cl;
-            const uint32_t v = ((uint32_t)meta.vb[b] + (uint32_t)cl) % 3u;
-            const uint8_t* pa = tabA + v * (K * 108);
-            const uint8_t* src = S + 9 * K * cl + b;
+            const uint32_t cw = pmap[32 * pass + lane];
+            if (cw == 255) continue;
+            const uint32_t cl = (cw * 57u) >> 9, b = cw - 9u * cl;          // cw / 9 for cw < 128
+            const uint32_t v = ((uint32_t)meta.vb[b] + cl) % 3u;
+            uint32_t pa = tabA32 + v * (K * 108);
+            asm volatile("" : "+r"(pa));                                   // keep the variant base in a register
+            const uint8_t* src = S + cw + (9 * K - 9) * cl;                 // 9K*cl + b
             uint8_t* dst = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
             Planes acc{0, 0}, acc2{0, 0};
-            uint32_t prev = 0;
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
+            uint32_t prev = 0, pk[K / 2];
+            static_for<0, K>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
                 const uint32_t d4 = src[9 * i];
-                const uint32_t ea = *reinterpret_cast<const uint32_t*>(pa + d4 + 108 * i);
+                const uint32_t ea = lds_tab<108 * i>(pa + d4);
                 const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + d4 + 108 * i);
-                if (i & 1) { gf3_add(acc2, ea, eb); *reinterpret_cast<uint16_t*>(dst + i - 1) = (uint16_t)__byte_perm(prev, ea, 0x0040); }
+                if (i & 1) { gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
                 else { gf3_add(acc, ea, eb); prev = ea; }
-            }
+            });
             gf3_add(acc, acc2.nz, acc2.two);
             gf3_add(acc, pat[2 * v], pat[2 * v + 1]);
             const uint32_t nzp = acc.nz >> 8, twp = acc.two >> 8;
             const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
+#pragma unroll
+            for (int j = 0; j < K / 2; ++j) *reinterpret_cast<uint16_t*>(dst + 2 * j) = (uint16_t)pk[j]; // stores after all loads: nothing to order
             *reinterpret_cast<uint16_t*>(dst + K) = (uint16_t)lo;
             if (L::R > 2) *reinterpret_cast<uint16_t*>(dst + K + 2) = (uint16_t)(lo >> 16);
             if (L::R > 4) {
@@ -703,8 +758,31 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
             dst[1] = gf->scr[g.st[1]][S[9] >> 2];
         }
         __syncwarp();
-        // ---- phase C: nine band-major runs -> global
-        warp_store_runs9_full<L::RUN_PITCH>(U, P.out, meta, lane);
+        // ---- phase C: nine band-major runs -> global, whole chunks (see stream_store for the carry scheme)
+#pragma unroll 1
+        for (int it = 0; it < (9 * RUN_SLOTS + 31) / 32; ++it) {
+            const uint32_t sl = 32u * it + lane, b = (sl * 2850u) >> 16, c = sl - RUN_SLOTS * b;   // sl / 23 for sl < 256
+            if (b < 9) {
+                const uint64_t lo = meta.run_lo[b];
+                const uint32_t padb = (uint32_t)lo & 15u, cend = (padb + L::RUN) >> 4;
+                if (c < cend && !(first && padb && c == 0))
+                    *reinterpret_cast<uint4*>(P.out + (lo - padb) + 16 * c) = *reinterpret_cast<const uint4*>(U + 16 * sl);
+            }
+        }
+        if (!last) {
+            if (lane < 9) carry[lane] = *reinterpret_cast<const uint4*>(U + L::RUN_PITCH * lane + 16 * ((((uint32_t)meta.run_lo[lane] & 15u) + L::RUN) >> 4));
+        }
+        if (first || last) { // edge bytes of a contiguous stretch, one by one
+#pragma unroll 1
+            for (int b = 0; b < 9; ++b) {
+                const uint64_t lo = meta.run_lo[b];
+                const int padb = (int)(lo & 15), end = padb + L::RUN, cend = end >> 4;
+                const uint8_t* s0 = U + L::RUN_PITCH * b;
+                uint8_t* g0 = P.out + (lo - padb);
+                if (first && padb && lane >= padb && lane < 16) g0[lane] = s0[lane];
+                if (last && lane < 16 && 16 * cend + lane < end) g0[16 * cend + lane] = s0[16 * cend + lane];
+            }
+        }
         __syncwarp();
     }
 }
@@ -729,6 +807,7 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
             if (v == 0) B[rem] = pl[i][xm][1];
         }
         load_gf(sg, gf);
+        if (tid >= 32 && tid < 35) build_pass_map(smem + L::DEC_MAP + 128 * (tid - 32), g, tid - 32);
     }
     __syncthreads();
     if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
@@ -741,35 +820,44 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
         reinterpret_cast<uint32_t*>(smem + L::DEC_CHK)[2 * tid + 1] = c.two;
     }
     __syncthreads();
-    const uint8_t* tabA = smem + L::DEC_A;
+    const uint32_t tabA32 = smem_u32(smem + L::DEC_A);
     const uint8_t* tabB = smem + L::DEC_B;
     const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L::DEC_CHK);
-    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
-    const uint64_t nwarps = (uint64_t)gridDim.x * FAST_WARPS;
     const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
-    for (uint64_t mt = (uint64_t)blockIdx.x * FAST_WARPS + warp; mt < total; mt += nwarps) {
-        const uint32_t f = (uint32_t)(mt / P.n_tiles), tile = P.tile0 + (uint32_t)(mt - (uint64_t)f * P.n_tiles);
+    uint4* carry = reinterpret_cast<uint4*>(U + L::U_BYTES + L::META_BYTES);
+    uint32_t mt_lo, mt_hi;
+    warp_range((uint64_t)P.n_tiles * P.n_frames, blockIdx.x * FAST_WARPS + warp, gridDim.x * FAST_WARPS, mt_lo, mt_hi);
+    for (uint32_t mt = mt_lo; mt < mt_hi; ++mt) {
+        const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
+        const bool first = mt == mt_lo || tile == P.tile0, last = mt + 1 == mt_hi || tile + 1 == P.tile0 + P.n_tiles; // of a contiguous stretch
         setup_runs3(meta, g, P.in_stride * f, tile, lane);
         __syncwarp();
+        if (!last) { // the next tile's nine runs: 3 lines each, towards L2
+            const int b = lane / 3;
+            if (b < 9 && meta.run_lo[b] + L::RUN + 128 * (lane - 3 * b) < in_limit) prefetch_l2(P.in + meta.run_lo[b] + L::RUN + 128 * (lane - 3 * b));
+        }
         // ---- nine runs -> shared, every byte scaled by 4 (table byte offset).  Bytes >= 32 would leave the 32-entry
         // rows: they are reduced mod 27 first (out-of-alphabet symbols read as their low three trits, OLD:28-31)
         bool wild = false;
 #pragma unroll 1
-        for (int b = 0; b < 9; ++b) {
-            const uint64_t lo = meta.run_lo[b];
-            const int padb = (int)(lo & 15), c16 = 16 * lane;
-            if (c16 < padb + L::RUN) {
-                const uint64_t ga = (lo - padb) + c16;
-                uint4 q;
-                if (ga + 16 <= in_limit) q = __ldg(reinterpret_cast<const uint4*>(P.in + ga));
-                else { // the last chunk of the last frame may poke past the buffer
-                    uint32_t t[4] = {0, 0, 0, 0};
-                    for (int i = 0; i < 16; ++i) if (ga + i < in_limit) t[i >> 2] |= (uint32_t)P.in[ga + i] << (8 * (i & 3));
-                    q = make_uint4(t[0], t[1], t[2], t[3]);
+        for (int it = 0; it < (9 * RUN_SLOTS + 31) / 32; ++it) {
+            const uint32_t sl = 32u * it + lane, b = (sl * 2850u) >> 16, c = sl - RUN_SLOTS * b;   // sl / 23 for sl < 256
+            if (b < 9) {
+                const uint64_t lo = meta.run_lo[b];
+                const uint32_t padb = (uint32_t)lo & 15u;
+                const uint64_t ga = (lo - padb) + 16 * c;
+                if (16 * c < padb + L::RUN) {
+                    uint4 q;
+                    if (ga + 16 <= in_limit) q = __ldg(reinterpret_cast<const uint4*>(P.in + ga));
+                    else { // the last chunk of the last frame may poke past the buffer
+                        uint32_t t[4] = {0, 0, 0, 0};
+                        for (int i = 0; i < 16; ++i) if (ga + i < in_limit) t[i >> 2] |= (uint32_t)P.in[ga + i] << (8 * (i & 3));
+                        q = make_uint4(t[0], t[1], t[2], t[3]);
+                    }
+                    wild |= ((q.x | q.y | q.z | q.w) & 0xE0E0E0E0u) != 0;
+                    q.x <<= 2; q.y <<= 2; q.z <<= 2; q.w <<= 2;
+                    *reinterpret_cast<uint4*>(U + 16 * sl) = q;
                 }
-                wild |= ((q.x | q.y | q.z | q.w) & 0xE0E0E0E0u) != 0;
-                q.x <<= 2; q.y <<= 2; q.z <<= 2; q.w <<= 2;
-                *reinterpret_cast<uint4*>(U + L::RUN_PITCH * b + c16) = q;
             }
         }
         if (__any_sync(0xFFFFFFFFu, wild)) { // rare: reload those chunks byte by byte
@@ -791,30 +879,35 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
             r0[1] = (uint8_t)(4u * sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][(r0[1] >> 2) % 27u]]);
         }
         __syncwarp();
-        // ---- phase B: syndrome screen per codeword (row-major lanes); descrambled data symbols -> stream order
+        // ---- phase B: syndrome screen per codeword (variant-sorted lanes); descrambled data symbols -> stream order
+        const uint8_t* pmap = smem + L::DEC_MAP + 128 * (tile % 3u);
 #pragma unroll 1
         for (int pass = 0; pass < L::PASS_B; ++pass) {
-            const int cw = 32 * pass + lane;
-            if (cw >= L::NCW) continue;
-            const int cl = cw / 9, b = cw - 9 * cl;
-            const uint32_t v = ((uint32_t)meta.vb[b] + (uint32_t)cl) % 3u;
-            const uint8_t* pa = tabA + v * (26 * 128);
+            const uint32_t cw = pmap[32 * pass + lane];
+            if (cw == 255) continue;
+            const uint32_t cl = (cw * 57u) >> 9, b = cw - 9u * cl;          // cw / 9 for cw < 128
+            const uint32_t v = ((uint32_t)meta.vb[b] + cl) % 3u;
+            uint32_t pa = tabA32 + v * (26 * 128);
+            asm volatile("" : "+r"(pa));
             const uint8_t* src = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
-            uint8_t* dst = S + 9 * K * cl + b;
+            uint8_t* dst = S + cw + (9 * K - 9) * cl;                       // 9K*cl + b
             Planes acc{0, 0}, acc2{0, 0};
-#pragma unroll
-            for (int i = 0; i < 26; ++i) {
+            uint32_t ev[K];
+            static_for<0, 26>([&](auto ic) {
+                constexpr int i = decltype(ic)::value;
                 const uint32_t x4 = src[i];
-                const uint32_t ea = *reinterpret_cast<const uint32_t*>(pa + x4 + 128 * i);
+                const uint32_t ea = lds_tab<128 * i>(pa + x4);
                 const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + x4 + 128 * i);
                 if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
-                if (i < K) dst[9 * i] = (uint8_t)ea;
-            }
+                if (i < K) ev[i < K ? i : 0] = ea;
+            });
+#pragma unroll
+            for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
             gf3_add(acc, acc2.nz, acc2.two);
             if (((acc.nz ^ chk[2 * v]) | (acc.two ^ chk[2 * v + 1])) & ~0xFFu) { // the low bytes carry the embedded symbols
                 // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
                 uint8_t cwd[26], orig[26];
-                for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(pa + src[i] + 128 * i);
+                for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(smem + L::DEC_A + v * (26 * 128) + src[i] + 128 * i);
                 if (!rs_decode_thread(sg, cwd, K, true)) {
                     atomicExch(&P.status[2 * f], 0u);
                 } else {
@@ -829,6 +922,8 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
         // ---- phase A: 26 stream symbols -> six pixels -> 18 RGB bytes per lane (units dealt even / odd)
         const uint64_t g_lo = P.out_stride * f + 3ull * L::PX * tile;
         const uint32_t pad = (uint32_t)(g_lo & 15);
+        if (!first && lane == 0) *reinterpret_cast<uint4*>(U) = carry[0]; // bytes [0, pad): the previous tile's tail
+        __syncwarp();
 #pragma unroll 1
         for (int pass = 0; pass < L::PASS_A; ++pass) {
             const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
@@ -858,7 +953,7 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
             }
         }
         __syncwarp();
-        warp_store_run(U, P.out, g_lo, L::RGB_BYTES, lane);
+        stream_store(U, P.out, g_lo, L::RGB_BYTES, first, last, carry, lane);
         __syncwarp();
     }
 }
