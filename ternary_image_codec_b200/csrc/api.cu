@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +18,9 @@ static_assert(sizeof(t3c_config) == 44 && sizeof(t3c_pixel) == 6, "ABI struct la
 struct t3c_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr; // copy streams of the chunked host pipelines
+    cudaEvent_t ev[32] = {};
+    int ev_next = 0;
     DevTables tabs{};
     void* d_tables = nullptr;
     HostTables* host = nullptr; // host copy of the constant tables (decoder screen constants are derived per call)
@@ -85,6 +89,18 @@ t3c_status check_launch(t3c_ctx* ctx, int n)
 }
 #define TRY(expr) do { t3c_status s_ = (expr); if (s_ != T3C_OK) return s_; } while (0)
 
+// everything enqueued on `to` after this call runs after everything enqueued on `from` so far
+t3c_status chain(t3c_ctx* ctx, cudaStream_t from, cudaStream_t to)
+{
+    cudaEvent_t e = ctx->ev[ctx->ev_next];
+    ctx->ev_next = (ctx->ev_next + 1) % 32;
+    CU(cudaEventRecord(e, from));
+    CU(cudaStreamWaitEvent(to, e, 0));
+    return T3C_OK;
+}
+static uint32_t kPipeChunks = 8;          // chunks per frame in the host-buffer pipelines (T3C_PIPE_CHUNKS overrides)
+constexpr uint32_t kPipeMinTiles = 512;   // below this a frame is copied and coded in one piece
+
 void ref_dec_geom(const t3c_config& h, size_t n_words, RefDecGeom& g)
 {
     static const int ks[4] = {24, 22, 20, 18};
@@ -148,10 +164,14 @@ t3c_status t3c_create(int device, t3c_ctx** out)
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return T3C_ERR_NODEVICE;
     t3c_ctx* ctx = new t3c_ctx();
     ctx->device = device;
+    if (const char* e = getenv("T3C_PIPE_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64) kPipeChunks = (uint32_t)v; }
     DeviceGuard guard(device);
     HostTables* ht = new HostTables();
     build_tables(*ht);
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    for (auto& ev : ctx->ev) if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_tables, sizeof(HostTables));
     if (e == cudaSuccess) e = cudaMemcpy(ctx->d_tables, ht, sizeof(HostTables), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&ctx->h_mail, sizeof(t3c_ctx::Mail));
@@ -178,6 +198,9 @@ void t3c_destroy(t3c_ctx* ctx)
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     delete ctx->host;
     delete ctx;
 }
@@ -587,16 +610,62 @@ t3c_status t3c_encode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, int arith
 {
     if (!ctx || !cfg || !rgb || !out || !words_per_frame) return fail(ctx, T3C_ERR_ARG, "encode_frames: null");
     DeviceGuard guard(ctx->device);
-    const size_t no = profile_words(*cfg, (n_px + 1) / 2);
+    const size_t n_words = (n_px + 1) / 2;
+    const size_t no = profile_words(*cfg, n_words);
     *words_per_frame = no;
     if (stride_words < no) return fail(ctx, T3C_ERR_CAPACITY, "encode_frames: stride");
     if (!n_frames) return T3C_OK;
     uint8_t *d_in, *d_out;
     const size_t dstride = (no + 15) & ~(size_t)15; // device-side frame pitch: keeps every frame 16-byte aligned
-    TRY(reserve_t(ctx, B_IN, 3 * n_px * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * dstride * n_frames, &d_out));
-    H2D(d_in, rgb, 3 * n_px * n_frames);
-    TRY(t3c_encode_frames_rgb8_dev(ctx, cfg, arith, d_in, n_px, n_frames, d_out, dstride, ctx->stream));
-    CU(cudaMemcpy2DAsync(out, 9 * stride_words, d_out, 9 * dstride, 9 * no, n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+    Geom g;
+    uint32_t n_full = 0;
+    if (cfg->profile != T3C_PROFILE_RAW && fast_path_ok(*cfg)) { make_geom(*cfg, n_words, arith, g); n_full = fast_full_tiles_encode(g, n_px); }
+    if (n_full < kPipeMinTiles) { // one piece: stage in, run, stage out
+        TRY(reserve_t(ctx, B_IN, 3 * n_px * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * dstride * n_frames, &d_out));
+        H2D(d_in, rgb, 3 * n_px * n_frames);
+        TRY(t3c_encode_frames_rgb8_dev(ctx, cfg, arith, d_in, n_px, n_frames, d_out, dstride, ctx->stream));
+        CU(cudaMemcpy2DAsync(out, 9 * stride_words, d_out, 9 * dstride, 9 * no, n_frames, cudaMemcpyDeviceToHost, ctx->stream));
+        SYNC();
+        return T3C_OK;
+    }
+    // Chunked pipeline over the tiled fast path: the H2D copy of chunk c+1, the kernel of chunk c and the D2H copies of
+    // chunk c-1 (nine band segments each) overlap on three streams; both PCIe directions stay busy.
+    const size_t in_pitch = (3 * n_px + 15) & ~(size_t)15;
+    TRY(reserve_t(ctx, B_IN, in_pitch * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * dstride * n_frames, &d_out));
+    const size_t tile_bytes = 3 * 27 * (size_t)g.uniform_k;
+    bool uniform_bands = true;
+    for (int b = 1; b < 9; ++b) uniform_bands = uniform_bands && g.ncw[b] == g.ncw[0];
+    for (size_t f = 0; f < n_frames; ++f) {
+        const uint8_t* h_in = rgb + 3 * n_px * f;
+        uint8_t* h_out = out + 9 * stride_words * f;
+        uint8_t* df_in = d_in + in_pitch * f;
+        uint8_t* df_out = d_out + 9 * dstride * f;
+        for (uint32_t c = 0; c <= kPipeChunks; ++c) { // the last round is the ragged tail + header
+            const bool tail = c == kPipeChunks;
+            const uint32_t t0 = tail ? n_full : (uint32_t)((uint64_t)n_full * c / kPipeChunks), t1 = tail ? n_full : (uint32_t)((uint64_t)n_full * (c + 1) / kPipeChunks);
+            const size_t b0 = tile_bytes * t0, b1 = tail ? 3 * n_px : tile_bytes * t1;
+            if (b1 > b0) CU(cudaMemcpyAsync(df_in + b0, h_in + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_h2d));
+            TRY(chain(ctx, ctx->s_h2d, ctx->stream));
+            const int n = launch_encode_rgb_fast_part(ctx->tabs, *cfg, g, df_in, n_px, in_pitch, 1, df_out, dstride, ctx->stream, t0, t1, tail);
+            if (n < 0) return fail(ctx, T3C_ERR_CUDA, "encode_frames: unaligned staging");
+            TRY(check_launch(ctx, n));
+            TRY(chain(ctx, ctx->stream, ctx->s_d2h));
+            if (!tail && uniform_bands) { // nine equal segments, equally spaced: one strided copy
+                CU(cudaMemcpy2DAsync(h_out + 52 + 26 * 13ull * t0, 26 * g.ncw[0], df_out + 52 + 26 * 13ull * t0, 26 * g.ncw[0], 26 * 13ull * (t1 - t0), 9,
+                                     cudaMemcpyDeviceToHost, ctx->s_d2h));
+            } else
+                for (int b = 0; b < 9; ++b) {
+                    const uint64_t c0 = g.cw_base[b] + 13ull * t0, c1 = tail ? g.cw_base[b] + g.ncw[b] : g.cw_base[b] + 13ull * t1;
+                    if (c1 > c0) CU(cudaMemcpyAsync(h_out + 52 + 26 * c0, df_out + 52 + 26 * c0, 26 * (c1 - c0), cudaMemcpyDeviceToHost, ctx->s_d2h));
+                }
+            if (tail) {
+                CU(cudaMemcpyAsync(h_out, df_out, 52, cudaMemcpyDeviceToHost, ctx->s_d2h));
+                const size_t body_end = 52 + (size_t)g.l_body;
+                if (9 * no > body_end) CU(cudaMemcpyAsync(h_out + body_end, df_out + body_end, 9 * no - body_end, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            }
+        }
+    }
+    CU(cudaStreamSynchronize(ctx->s_d2h));
     SYNC();
     return T3C_OK;
 }
@@ -606,6 +675,7 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
 {
     if (!ctx || !cfg || !in || !rgb || !ok) return fail(ctx, T3C_ERR_ARG, "decode_frames: null");
     if (n_frames > 32) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: at most 32 frames per host-buffer call");
+    if (cfg->profile == T3C_PROFILE_RAW) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: RAW profile carries raw words, use unpack_pixels");
     DeviceGuard guard(ctx->device);
     if (n_corrected) *n_corrected = 0;
     if (px_recovered) *px_recovered = 0;
@@ -613,15 +683,60 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
     const size_t n_words = (n_px + 1) / 2;
     Geom g;
     make_geom(*cfg, n_words, 1, g);
+    if (g.n_out != words_per_frame) return fail(ctx, T3C_ERR_ARG, "decode_frames: words_per_frame does not match config and n_px");
     uint64_t nw = 3 * known_prefix(*cfg, g) / 26;
     if (nw > n_words) nw = n_words;
     const size_t px_out = 2 * (size_t)nw < n_px ? 2 * (size_t)nw : n_px;
     uint8_t *d_in, *d_out;
     const size_t dstride = (words_per_frame + 15) & ~(size_t)15;
-    TRY(reserve_t(ctx, B_IN, 9 * dstride * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 3 * n_px * n_frames, &d_out));
-    CU(cudaMemcpy2DAsync(d_in, 9 * dstride, in, 9 * stride_words, 9 * words_per_frame, n_frames, cudaMemcpyHostToDevice, ctx->stream));
-    TRY(t3c_decode_frames_rgb8_dev(ctx, cfg, d_in, words_per_frame, dstride, n_frames, n_px, d_out, ctx->d_mail->status, ctx->stream));
-    for (size_t f = 0; f < n_frames; ++f) if (px_out) D2H(rgb + 3 * n_px * f, d_out + 3 * n_px * f, 3 * px_out);
+    const size_t out_pitch = (3 * n_px + 15) & ~(size_t)15;
+    const uint32_t n_full = fast_path_ok(*cfg) ? fast_full_tiles_decode(g, px_out, out_pitch, 1) : 0;
+    if (n_full < kPipeMinTiles) { // one piece
+        TRY(reserve_t(ctx, B_IN, 9 * dstride * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, 3 * n_px * n_frames, &d_out));
+        CU(cudaMemcpy2DAsync(d_in, 9 * dstride, in, 9 * stride_words, 9 * words_per_frame, n_frames, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(t3c_decode_frames_rgb8_dev(ctx, cfg, d_in, words_per_frame, dstride, n_frames, n_px, d_out, ctx->d_mail->status, ctx->stream));
+        for (size_t f = 0; f < n_frames; ++f) if (px_out) D2H(rgb + 3 * n_px * f, d_out + 3 * n_px * f, 3 * px_out);
+    } else { // chunked pipeline, see t3c_encode_frames_rgb8
+        TRY(reserve_t(ctx, B_IN, 9 * dstride * n_frames, &d_in)); TRY(reserve_t(ctx, B_OUT, out_pitch * n_frames, &d_out));
+        TRY(check_launch(ctx, launch_init_status(ctx->d_mail->status, n_frames, ctx->stream)));
+        uint32_t chk_nz[7], chk_two[7];
+        fast_check_constants(*ctx->host, g, chk_nz, chk_two);
+        const size_t tile_bytes = 3 * 27 * (size_t)g.uniform_k, frame_bytes = 9 * words_per_frame;
+        bool uniform_bands = true;
+        for (int b = 1; b < 9; ++b) uniform_bands = uniform_bands && g.ncw[b] == g.ncw[0];
+        // (the header's 52 bytes are not needed: the consistent decoder takes its config out of band)
+        for (size_t f = 0; f < n_frames; ++f) {
+            const uint8_t* h_in = in + 9 * stride_words * f;
+            uint8_t* h_out = rgb + 3 * n_px * f;
+            uint8_t* df_in = d_in + 9 * dstride * f;
+            uint8_t* df_out = d_out + out_pitch * f;
+            for (uint32_t c = 0; c <= kPipeChunks; ++c) {
+                const bool tail = c == kPipeChunks;
+                const uint32_t t0 = tail ? n_full : (uint32_t)((uint64_t)n_full * c / kPipeChunks), t1 = tail ? n_full : (uint32_t)((uint64_t)n_full * (c + 1) / kPipeChunks);
+                // band segments, widened by 16 bytes: the kernels load whole 16-byte chunks around every run
+                if (!tail && uniform_bands && 52 + 26 * (g.cw_base[8] + 13ull * t1) + 16 <= frame_bytes) { // equal, equally spaced: one strided copy
+                    CU(cudaMemcpy2DAsync(df_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], h_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], 26 * 13ull * (t1 - t0) + 16, 9,
+                                         cudaMemcpyHostToDevice, ctx->s_h2d));
+                } else
+                    for (int b = 0; b < 9; ++b) {
+                        const uint64_t c0 = g.cw_base[b] + 13ull * t0, c1 = tail ? g.cw_base[b] + g.ncw[b] : g.cw_base[b] + 13ull * t1;
+                        if (c1 <= c0) continue;
+                        size_t lo = (52 + 26 * c0) & ~(size_t)15, hi = (52 + 26 * c1 + 15) & ~(size_t)15;
+                        if (hi > frame_bytes) hi = frame_bytes;
+                        CU(cudaMemcpyAsync(df_in + lo, h_in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_h2d));
+                    }
+                TRY(chain(ctx, ctx->s_h2d, ctx->stream));
+                const int n = launch_decode_rgb_fast_part(ctx->tabs, g, df_in, dstride, 1, n_px, out_pitch, px_out, df_out, ctx->d_mail->status + 2 * f,
+                                                          ctx->stream, chk_nz, chk_two, t0, t1, tail);
+                if (n < 0) return fail(ctx, T3C_ERR_CUDA, "decode_frames: unaligned staging");
+                TRY(check_launch(ctx, n));
+                TRY(chain(ctx, ctx->stream, ctx->s_d2h));
+                const size_t b0 = tile_bytes * t0, b1 = tail ? 3 * px_out : tile_bytes * t1;
+                if (b1 > b0) CU(cudaMemcpyAsync(h_out + b0, df_out + b0, b1 - b0, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            }
+        }
+        CU(cudaStreamSynchronize(ctx->s_d2h));
+    }
     MAIL_DOWN();
     for (size_t f = 0; f < n_frames; ++f) {
         ok[f] = ctx->h_mail->status[2 * f] ? 1 : 0;

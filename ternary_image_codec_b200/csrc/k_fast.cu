@@ -974,29 +974,32 @@ int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastP
     kern<<<(unsigned)grid, FAST_TPB, smem_bytes, st>>>(P, g, T.gf, T.rs);
     return 1;
 }
-// tiles [0, n_full) of every frame go to the v3 kernels, the ragged rest to the general-tile kernels
+// tiles [t0, t1) of [0, n_full) of every frame go to the v3 kernels; with `tail` the ragged rest [n_full, n_all) goes to
+// the general-tile kernels
 template <int K>
-int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full)
+int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail)
 {
     static int occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 20) {
-        if (n_full) { P.tile0 = 0; P.n_tiles = n_full; n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3); }
+        if (t1 > n_full) t1 = n_full;
+        if (t1 > t0) { P.tile0 = t0; P.n_tiles = t1 - t0; n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3); }
     } else n_full = 0;
-    if (n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_encode_rgb_fast<K>, Cfg<K>::TOTAL_ENC, T, P, g, st, occ2); }
+    if (tail && n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_encode_rgb_fast<K>, Cfg<K>::TOTAL_ENC, T, P, g, st, occ2); }
     return n;
 }
 template <int K>
-int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full)
+int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail)
 {
     static int occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 20) {
-        if (n_full) { P.tile0 = 0; P.n_tiles = n_full; n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3); }
+        if (t1 > n_full) t1 = n_full;
+        if (t1 > t0) { P.tile0 = t0; P.n_tiles = t1 - t0; n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3); }
     } else n_full = 0;
-    if (n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_decode_rgb_fast<K>, Cfg<K>::TOTAL_DEC, T, P, g, st, occ2); }
+    if (tail && n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_decode_rgb_fast<K>, Cfg<K>::TOTAL_DEC, T, P, g, st, occ2); }
     return n;
 }
 // mini-tiles of a frame whose 117 codewords all exist and whose 27k pixels lie inside [0, px_limit)
@@ -1020,56 +1023,79 @@ bool fast_path_ok(const t3c_config& cfg)
     return true;
 }
 
-int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* rgb, size_t n_px, size_t n_frames,
-                           uint8_t* out, size_t stride_words, cudaStream_t st)
+static uint32_t all_tiles(const Geom& g)
+{
+    uint64_t mx = 0;
+    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
+    return (uint32_t)((mx + C_MINI - 1) / C_MINI);
+}
+uint32_t fast_full_tiles_encode(const Geom& g, size_t n_px)
+{
+    if (g.uniform_k < 20) return 0;
+    return full_tiles(g, n_px < 2 * g.n_words ? n_px : 2 * g.n_words);
+}
+uint32_t fast_full_tiles_decode(const Geom& g, size_t n_px_out, size_t out_pitch, size_t n_frames)
+{
+    if (g.uniform_k < 20) return 0;
+    return (n_frames > 1 && (out_pitch & 1)) ? 0 : full_tiles(g, n_px_out); // v3 writes RGB with 2-byte stores: frames start on even bytes
+}
+
+int launch_encode_rgb_fast_part(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* rgb, size_t n_px, size_t in_pitch,
+                                size_t n_frames, uint8_t* out, size_t stride_words, cudaStream_t st, uint32_t t0, uint32_t t1, bool tail)
 {
     if (((uintptr_t)rgb | (uintptr_t)out) & 15) return -1; // 128-bit transfers need 16-byte aligned buffer bases
     if (n_frames > 1 && (stride_words & 1)) return -1;     // and every frame's body must start on an even byte
     FastParams P{};
     P.in = rgb; P.out = out;
-    P.in_stride = 3ull * n_px; P.out_stride = 9ull * stride_words;
+    P.in_stride = in_pitch; P.out_stride = 9ull * stride_words;
     P.n_px = n_px; P.n_frames = (uint32_t)n_frames;
-    uint64_t mx = 0;
-    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    P.n_tiles = (uint32_t)((mx + C_MINI - 1) / C_MINI);
+    P.n_tiles = all_tiles(g);
     int n = 0;
-    const uint64_t px_have = n_px < 2 * g.n_words ? n_px : 2 * g.n_words;
-    const uint32_t n_full = full_tiles(g, px_have);
+    const uint32_t n_full = fast_full_tiles_encode(g, n_px);
     switch (g.uniform_k) {
-    case 24: n = launch_enc<24>(T, P, g, st, n_full); break;
-    case 22: n = launch_enc<22>(T, P, g, st, n_full); break;
-    case 20: n = launch_enc<20>(T, P, g, st, n_full); break;
-    case 18: n = launch_enc<18>(T, P, g, st, n_full); break;
+    case 24: n = launch_enc<24>(T, P, g, st, n_full, t0, t1, tail); break;
+    case 22: n = launch_enc<22>(T, P, g, st, n_full, t0, t1, tail); break;
+    case 20: n = launch_enc<20>(T, P, g, st, n_full, t0, t1, tail); break;
+    case 18: n = launch_enc<18>(T, P, g, st, n_full, t0, t1, tail); break;
     default: return 0;
     }
-    return n + launch_frame_misc(T, cfg, g, out, n_frames, 9ull * stride_words, st);
+    if (tail) n += launch_frame_misc(T, cfg, g, out, n_frames, 9ull * stride_words, st);
+    return n;
+}
+int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* rgb, size_t n_px, size_t n_frames,
+                           uint8_t* out, size_t stride_words, cudaStream_t st)
+{
+    return launch_encode_rgb_fast_part(T, cfg, g, rgb, n_px, 3 * n_px, n_frames, out, stride_words, st, 0, ~0u, true);
 }
 
+int launch_decode_rgb_fast_part(const DevTables& T, const Geom& g, const uint8_t* in, size_t stride_words, size_t n_frames, size_t n_px,
+                                size_t out_pitch, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st, const uint32_t* chk_nz,
+                                const uint32_t* chk_two, uint32_t t0, uint32_t t1, bool tail)
+{
+    if (((uintptr_t)rgb | (uintptr_t)in) & 15) return -1;
+    if (n_frames > 1 && (stride_words & 1)) return -1;
+    FastParams P{};
+    P.in = in; P.out = rgb;
+    P.in_stride = 9ull * stride_words; P.out_stride = out_pitch;
+    P.n_px = n_px; P.px_out = n_px_out; P.n_frames = (uint32_t)n_frames;
+    P.status = d_status;
+    for (int i = 0; i < 7; ++i) { P.chk_nz[i] = chk_nz[i]; P.chk_two[i] = chk_two[i]; }
+    P.n_tiles = all_tiles(g);
+    const uint32_t n_full = fast_full_tiles_decode(g, n_px_out, out_pitch, n_frames);
+    switch (g.uniform_k) {
+    case 24: return launch_dec<24>(T, P, g, st, n_full, t0, t1, tail);
+    case 22: return launch_dec<22>(T, P, g, st, n_full, t0, t1, tail);
+    case 20: return launch_dec<20>(T, P, g, st, n_full, t0, t1, tail);
+    case 18: return launch_dec<18>(T, P, g, st, n_full, t0, t1, tail);
+    }
+    return 0;
+}
 int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in, size_t stride_words,
                            size_t n_frames, size_t n_px, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st,
                            const uint32_t* chk_nz, const uint32_t* chk_two)
 {
     (void)cfg;
-    if (((uintptr_t)rgb | (uintptr_t)in) & 15) return -1;
-    if (n_frames > 1 && (stride_words & 1)) return -1;
-    FastParams P{};
-    P.in = in; P.out = rgb;
-    P.in_stride = 9ull * stride_words; P.out_stride = 3ull * n_px;
-    P.n_px = n_px; P.px_out = n_px_out; P.n_frames = (uint32_t)n_frames;
-    P.status = d_status;
-    for (int i = 0; i < 7; ++i) { P.chk_nz[i] = chk_nz[i]; P.chk_two[i] = chk_two[i]; }
-    uint64_t mx = 0;
-    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    P.n_tiles = (uint32_t)((mx + C_MINI - 1) / C_MINI);
-    // v3 writes RGB with 2-byte stores: every frame has to start on an even byte
-    const uint32_t n_full = (n_frames > 1 && (n_px & 1)) ? 0 : full_tiles(g, n_px_out);
-    switch (g.uniform_k) {
-    case 24: return launch_dec<24>(T, P, g, st, n_full);
-    case 22: return launch_dec<22>(T, P, g, st, n_full);
-    case 20: return launch_dec<20>(T, P, g, st, n_full);
-    case 18: return launch_dec<18>(T, P, g, st, n_full);
-    }
-    return 0;
+    return launch_decode_rgb_fast_part(T, g, in, stride_words, n_frames, n_px, 3 * n_px, n_px_out, rgb, d_status, st, chk_nz, chk_two, 0, ~0u, true);
 }
 
 } // namespace t3c

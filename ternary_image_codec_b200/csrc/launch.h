@@ -48,6 +48,15 @@ int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
 int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in9, size_t stride_words,
                            size_t n_frames, size_t n_px, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st,
                            const uint32_t* chk_nz, const uint32_t* chk_two);
+// the same for tiles [t0, t1) of the full mini-tiles only (chunked host pipelines); `tail` adds the ragged last tiles
+// (and, for encode, header / padding).  in_pitch / out_pitch = bytes between RGB frames on the device.
+int launch_encode_rgb_fast_part(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* rgb, size_t n_px, size_t in_pitch,
+                                size_t n_frames, uint8_t* out9, size_t stride_words, cudaStream_t st, uint32_t t0, uint32_t t1, bool tail);
+int launch_decode_rgb_fast_part(const DevTables& T, const Geom& g, const uint8_t* in9, size_t stride_words, size_t n_frames, size_t n_px,
+                                size_t out_pitch, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st, const uint32_t* chk_nz,
+                                const uint32_t* chk_two, uint32_t t0, uint32_t t1, bool tail);
+uint32_t fast_full_tiles_encode(const Geom& g, size_t n_px);
+uint32_t fast_full_tiles_decode(const Geom& g, size_t n_px_out, size_t out_pitch, size_t n_frames);
 // both return -1 when the buffers are not 16-byte aligned (caller falls back to the general kernels)
 // header + beacons + zero padding for n_frames super-frames laid out every stride_bytes
 int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out9, size_t n_frames, size_t stride_bytes, cudaStream_t st);

@@ -510,3 +510,28 @@ def test_fused_fast_path_out_of_alphabet_and_uncorrectable(codec, oracle, t3):
     ok2, _, _ = codec.decode_frames_rgb8(bad.reshape(1, -1, 9), n_px, gc)
     ok2_o, _, _ = oracle.decode_rgb_fixed(oc, bad.reshape(-1, 9), n_px)
     assert bool(ok2[0]) == bool(ok2_o)
+
+
+@pytest.mark.parametrize("kw", [dict(profile=T.P3, uep=2), dict(profile=T.P2, uep=1)])
+def test_host_pipeline_chunked_frames_match_oracle(codec, oracle, t3, kw):
+    """frames large enough (>= 512 full mini-tiles) for the chunked H2D / kernel / D2H pipeline of the host-buffer
+    calls: same words as the oracle, round trip with injected errors, odd pixel count and two frames"""
+    oc, gc = both(kw)
+    n_px = 640 * 480 + 1
+    frames = np.stack([T.synth_rgb(21, n_px), T.synth_rgb(22, n_px)])
+    for arith in (t3.REF_EXACT, t3.FIXED):
+        got = codec.encode_frames_rgb8(frames, gc, arith)
+        for f in range(2):
+            assert np.array_equal(got[f], oracle.encode_rgb(oc, frames[f], arith)), (arith, f)
+    enc = codec.encode_frames_rgb8(frames, gc, t3.FIXED)
+    add = T.gf_add_table()
+    bad = enc.copy()
+    tot = 0
+    for f in range(2):
+        bad[f], ne = T.inject_errors(enc[f], oc, (n_px + 1) // 2, seed=31 + f, gf_add=add)
+        tot += ne
+    ok, rgb, nc = codec.decode_frames_rgb8(bad, n_px, gc)
+    assert ok.all() and nc == tot
+    for f in range(2):
+        ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, enc[f], n_px)
+        assert ok_o and np.array_equal(rgb[f], rgb_o)
