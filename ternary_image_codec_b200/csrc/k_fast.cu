@@ -12,6 +12,7 @@
 // access is a 128-bit transfer inside a contiguous run (one RGB run, nine body runs of 338 B), the 9-band
 // transpose and all table look-ups stay in shared memory, the grid is persistent (SM count x resident CTAs)
 // so the row table is staged once per CTA, and HBM traffic is exactly the algorithmic 3 B/px + 9 B/word.
+#include <cstdlib>
 #include <type_traits>
 
 #include "dev.cuh"
@@ -557,11 +558,13 @@ template <int K> struct Cfg3 {
     static_assert(RUN_PITCH == 16 * 23, "chunk slots per run");
     static constexpr int ENC_A = 0, ENC_B = ENC_A + 4 * 3 * K * 27, ENC_PAT = ENC_B + 4 * K * 27, ENC_MAP = (ENC_PAT + 24 + 15) / 16 * 16, ENC_WARP = ENC_MAP + 3 * 128;
     static constexpr int TOTAL_ENC = ENC_WARP + FAST_WARPS * WARP_BYTES;
-    // decode, CTA-shared: A[3][26][32] | B[26][32] | chk[3][2] | GF(27) tables of the slow path
-    static constexpr int DEC_A = 0, DEC_B = DEC_A + 4 * 3 * 26 * 32, DEC_CHK = DEC_B + 4 * 26 * 32, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
+    // decode, CTA-shared (offsets from a 256-byte aligned base): per variant {A[26][32], B[26][32]} | chk[3][2] | GF(27) tables
+    // of the slow path.  A variant block is 26*256 bytes, so the low byte of a row's address is zero and PRMT can drop a
+    // received symbol (x4, < 128) straight into it.
+    static constexpr int DEC_A = 0, DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
     static constexpr int DEC_MAP = DEC_GF + ((int)sizeof(GfTables) + 15) / 16 * 16;
     static constexpr int DEC_WARP = DEC_MAP + 3 * 128;
-    static constexpr int TOTAL_DEC = DEC_WARP + FAST_WARPS * WARP_BYTES;
+    static constexpr int TOTAL_DEC = 256 + DEC_WARP + FAST_WARPS * WARP_BYTES;
 };
 struct WarpMeta3 { uint64_t run_lo[9]; uint8_t vb[16]; };
 static_assert(sizeof(WarpMeta3) <= 96, "meta3");
@@ -635,6 +638,175 @@ __device__ __forceinline__ void warp_range(uint64_t total, uint32_t gw, uint32_t
     hi = (uint32_t)(total * (gw + 1) / nw);
 }
 
+// ---- encode phase A: six pixels (18 bytes at IN + pad + 18u) -> 26 stream symbols (x4) at S + 26u
+template <int K>
+__device__ __forceinline__ void enc_phase_a(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
+{
+    using L = Cfg3<K>;
+    // ---- phase A: six pixels (18 bytes) -> 26 stream symbols (x4) per lane; units dealt even / odd so that the
+    // 18- and 26-byte lane strides become 36 and 52 bytes: 9 and 13 words, conflict-free
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_A; ++pass) {
+        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+        if (u >= L::UNITS) continue;
+        const uint32_t a = pad + 18u * (uint32_t)u;
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
+        const uint32_t sh = (a & 3u) * 8u;
+        uint32_t x[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) x[j] = mw[j];
+        uint32_t y[5]; // the 18 bytes, word aligned
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+        y[4] = x[4] >> sh;
+        uint32_t A[6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            const int q = 3 * p;
+            A[p] = rgb_to_value3(byte_magic(y[q >> 2], q & 3), byte_magic(y[(q + 1) >> 2], (q + 1) & 3), byte_magic(y[(q + 2) >> 2], (q + 2) & 3));
+        }
+        uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
+        triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
+        triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
+        w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
+        uint16_t* d = reinterpret_cast<uint16_t*>(S + 26 * u);
+        d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
+        d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
+        d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
+        d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+    }
+}
+// ---- encode phase B: stream symbols -> nine staged runs (data scrambled through the table bytes, parity through the planes)
+template <int K>
+__device__ __forceinline__ void enc_phase_b(const uint8_t* S, uint8_t* U, const WarpMeta3& meta, const uint8_t* pmap, uint32_t tabA32,
+                                            const uint8_t* tabB, const uint32_t* pat, int lane)
+{
+    using L = Cfg3<K>;
+    // ---- phase B: one codeword per lane (lane -> codeword through the variant-sorted pass map)
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_B; ++pass) {
+        const uint32_t cw = pmap[32 * pass + lane];
+        if (cw == 255) continue;
+        const uint32_t cl = (cw * 57u) >> 9, b = cw - 9u * cl;          // cw / 9 for cw < 128
+        const uint32_t v = ((uint32_t)meta.vb[b] + cl) % 3u;
+        uint32_t pa = tabA32 + v * (K * 108);
+        asm volatile("" : "+r"(pa));                                   // keep the variant base in a register
+        const uint8_t* src = S + cw + (9 * K - 9) * cl;                 // 9K*cl + b
+        uint8_t* dst = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
+        Planes acc{0, 0}, acc2{0, 0};
+        uint32_t prev = 0, pk[K / 2];
+        static_for<0, K>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const uint32_t d4 = src[9 * i];
+            const uint32_t ea = lds_tab<108 * i>(pa + d4);
+            const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + d4 + 108 * i);
+            if (i & 1) { gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
+            else { gf3_add(acc, ea, eb); prev = ea; }
+        });
+        gf3_add(acc, acc2.nz, acc2.two);
+        gf3_add(acc, pat[2 * v], pat[2 * v + 1]);
+        const uint32_t nzp = acc.nz >> 8, twp = acc.two >> 8;
+        const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
+#pragma unroll
+        for (int j = 0; j < K / 2; ++j) *reinterpret_cast<uint16_t*>(dst + 2 * j) = (uint16_t)pk[j]; // stores after all loads: nothing to order
+        *reinterpret_cast<uint16_t*>(dst + K) = (uint16_t)lo;
+        if (L::R > 2) *reinterpret_cast<uint16_t*>(dst + K + 2) = (uint16_t)(lo >> 16);
+        if (L::R > 4) {
+            const uint32_t hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
+            *reinterpret_cast<uint16_t*>(dst + K + 4) = (uint16_t)hi;
+        }
+    }
+}
+// ---- decode phase B: nine staged runs (x4) -> syndrome screen / slow path -> descrambled stream symbols
+template <int K>
+__device__ __forceinline__ void dec_phase_b(const uint8_t* U, uint8_t* S, const WarpMeta3& meta, const uint8_t* pmap, uint32_t tabA32,
+                                            const uint8_t* tabA, const uint32_t* chk, const GfTables& sg, uint32_t* status, int lane)
+{
+    using L = Cfg3<K>;
+    // ---- phase B: syndrome screen per codeword (variant-sorted lanes); descrambled data symbols -> stream order
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_B; ++pass) {
+        const uint32_t cw = pmap[32 * pass + lane];
+        if (cw == 255) continue;
+        const uint32_t cl = (cw * 57u) >> 9, b = cw - 9u * cl;          // cw / 9 for cw < 128
+        const uint32_t v = ((uint32_t)meta.vb[b] + cl) % 3u;
+        uint32_t pa = tabA32 + v * L::DEC_VAR;                         // low byte 0
+        asm volatile("" : "+r"(pa));
+        const uint8_t* src = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
+        uint8_t* dst = S + cw + (9 * K - 9) * cl;                       // 9K*cl + b
+        // the codeword's 26 symbols as 7 words (it starts on an even byte), then one PRMT per symbol builds the
+        // table address: byte 0 = symbol x4, bytes 1..3 = the variant block's address
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+        const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 2u) * 8u;
+        uint32_t xw[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) xw[j] = mw[j];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) xw[j] = __funnelshift_r(xw[j], xw[j + 1], sh);
+        xw[6] >>= sh;
+        Planes acc{0, 0}, acc2{0, 0};
+        uint32_t ev[K];
+        static_for<0, 26>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
+            const uint32_t ea = lds_tab<128 * i>(ra);
+            const uint32_t eb = lds_tab<128 * i + L::DEC_PLANE>(ra);
+            if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+            if (i < K) ev[i < K ? i : 0] = ea;
+        });
+#pragma unroll
+        for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
+        gf3_add(acc, acc2.nz, acc2.two);
+        if (((acc.nz ^ chk[2 * v]) | (acc.two ^ chk[2 * v + 1])) & ~0xFFu) { // the low bytes carry the embedded symbols
+            // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
+            uint8_t cwd[26], orig[26];
+            for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tabA + v * L::DEC_VAR + src[i] + 128 * i);
+            if (!rs_decode_thread(sg, cwd, K, true)) {
+                atomicExch(&status[0], 0u);
+            } else {
+                uint32_t nfix = 0;
+                for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
+                if (nfix) atomicAdd(&status[1], nfix);
+                for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
+            }
+        }
+    }
+}
+// ---- decode phase A: 26 stream symbols at S + 26u -> six pixels -> 18 RGB bytes at U + pad + 18u
+template <int K>
+__device__ __forceinline__ void dec_phase_a(const uint8_t* S, uint8_t* U, uint32_t pad, int lane)
+{
+    using L = Cfg3<K>;
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_A; ++pass) {
+        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+        if (u >= L::UNITS) continue;
+        const uint32_t a = 26u * (uint32_t)u;
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+        const uint32_t sh = (a & 2u) * 8u;
+        uint32_t x[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) x[j] = mw[j];
+        uint32_t y[7]; // the 26 symbols, word aligned
+#pragma unroll
+        for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+        y[6] = x[6] >> sh;
+        uint32_t A[6];
+        symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+        symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+        uint32_t p[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) p[q] = value_to_rgb3(A[q]);
+        uint16_t* dh = reinterpret_cast<uint16_t*>(U + pad + 18 * u); // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { // two pixels = three halfwords
+            dh[3 * q] = (uint16_t)p[2 * q];
+            dh[3 * q + 1] = (uint16_t)((p[2 * q] >> 16) | (p[2 * q + 1] << 8));
+            dh[3 * q + 2] = (uint16_t)(p[2 * q + 1] >> 8);
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
 {
@@ -681,76 +853,11 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
         warp_load_run(U, P.in, g_lo, g_lo + L::RGB_BYTES, P.in_stride * P.n_frames, lane);
         if (!last && lane < (L::RGB_BYTES + 127) / 128 && g_lo + L::RGB_BYTES + 128 * lane < P.in_stride * P.n_frames) prefetch_l2(P.in + g_lo + L::RGB_BYTES + 128 * lane); // the next tile's pixels
         __syncwarp();
-        // ---- phase A: six pixels (18 bytes) -> 26 stream symbols (x4) per lane; units dealt even / odd so that the
-        // 18- and 26-byte lane strides become 36 and 52 bytes: 9 and 13 words, conflict-free
-#pragma unroll 1
-        for (int pass = 0; pass < L::PASS_A; ++pass) {
-            const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
-            if (u >= L::UNITS) continue;
-            const uint32_t a = pad + 18u * (uint32_t)u;
-            const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
-            const uint32_t sh = (a & 3u) * 8u;
-            uint32_t x[5];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) x[j] = mw[j];
-            uint32_t y[5]; // the 18 bytes, word aligned
-#pragma unroll
-            for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-            y[4] = x[4] >> sh;
-            uint32_t A[6];
-#pragma unroll
-            for (int p = 0; p < 6; ++p) {
-                const int q = 3 * p;
-                A[p] = rgb_to_value3(byte_magic(y[q >> 2], q & 3), byte_magic(y[(q + 1) >> 2], (q + 1) & 3), byte_magic(y[(q + 2) >> 2], (q + 2) & 3));
-            }
-            uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
-            triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
-            triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
-            w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
-            uint16_t* d = reinterpret_cast<uint16_t*>(S + 26 * u);
-            d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
-            d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
-            d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
-            d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
-        }
+        enc_phase_a<K>(U, pad, S, lane);
         __syncwarp();
         if (!first && lane < 9) *reinterpret_cast<uint4*>(U + L::RUN_PITCH * lane) = carry[lane]; // bytes [0, pad) of each run: the previous tile's tail
         __syncwarp();
-        // ---- phase B: one codeword per lane (lane -> codeword through the variant-sorted pass map)
-        const uint8_t* pmap = smem + L::ENC_MAP + 128 * (tile % 3u);
-#pragma unroll 1
-        for (int pass = 0; pass < L::PASS_B; ++pass) {
-            const uint32_t cw = pmap[32 * pass + lane];
-            if (cw == 255) continue;
-            const uint32_t cl = (cw * 57u) >> 9, b = cw - 9u * cl;          // cw / 9 for cw < 128
-            const uint32_t v = ((uint32_t)meta.vb[b] + cl) % 3u;
-            uint32_t pa = tabA32 + v * (K * 108);
-            asm volatile("" : "+r"(pa));                                   // keep the variant base in a register
-            const uint8_t* src = S + cw + (9 * K - 9) * cl;                 // 9K*cl + b
-            uint8_t* dst = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
-            Planes acc{0, 0}, acc2{0, 0};
-            uint32_t prev = 0, pk[K / 2];
-            static_for<0, K>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                const uint32_t d4 = src[9 * i];
-                const uint32_t ea = lds_tab<108 * i>(pa + d4);
-                const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + d4 + 108 * i);
-                if (i & 1) { gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
-                else { gf3_add(acc, ea, eb); prev = ea; }
-            });
-            gf3_add(acc, acc2.nz, acc2.two);
-            gf3_add(acc, pat[2 * v], pat[2 * v + 1]);
-            const uint32_t nzp = acc.nz >> 8, twp = acc.two >> 8;
-            const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
-#pragma unroll
-            for (int j = 0; j < K / 2; ++j) *reinterpret_cast<uint16_t*>(dst + 2 * j) = (uint16_t)pk[j]; // stores after all loads: nothing to order
-            *reinterpret_cast<uint16_t*>(dst + K) = (uint16_t)lo;
-            if (L::R > 2) *reinterpret_cast<uint16_t*>(dst + K + 2) = (uint16_t)(lo >> 16);
-            if (L::R > 4) {
-                const uint32_t hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
-                *reinterpret_cast<uint16_t*>(dst + K + 4) = (uint16_t)hi;
-            }
-        }
+        enc_phase_b<K>(S, U, meta, smem + L::ENC_MAP + 128 * (tile % 3u), tabA32, tabB, pat, lane);
         __syncwarp();
         if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0 and 1 may still see the scrambler's transient (A.4)
             uint8_t* dst = U + ((uint32_t)meta.run_lo[0] & 15u);
@@ -791,20 +898,20 @@ template <int K>
 __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
 {
     using L = Cfg3<K>;
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u); // 256-byte aligned (see Cfg3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t* S = smem + L::DEC_WARP + warp * L::WARP_BYTES;     // descrambled stream symbols (plain)
     uint8_t* U = S + L::S_BYTES;                                // the nine body runs (x4), later the RGB run
     WarpMeta3& meta = *reinterpret_cast<WarpMeta3*>(U + L::U_BYTES);
     GfTables& sg = *reinterpret_cast<GfTables*>(smem + L::DEC_GF);
     {
-        uint32_t* A = reinterpret_cast<uint32_t*>(smem + L::DEC_A);
-        uint32_t* B = reinterpret_cast<uint32_t*>(smem + L::DEC_B);
         const uint32_t(*pl)[kVals][2] = rs->pl[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
         for (int idx = tid; idx < 3 * 26 * 32; idx += FAST_TPB) {
             const int v = idx / (26 * 32), rem = idx - v * (26 * 32), i = rem / 32, x = rem - 32 * i, xm = x >= 27 ? x - 27 : x;
-            A[idx] = pl[i][xm][0] | gf->dsc[st_of(g, v, i)][xm];
-            if (v == 0) B[rem] = pl[i][xm][1];
+            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + L::DEC_A + v * L::DEC_VAR);
+            blk[rem] = pl[i][xm][0] | gf->dsc[st_of(g, v, i)][xm];
+            blk[26 * 32 + rem] = pl[i][xm][1];
         }
         load_gf(sg, gf);
         if (tid >= 32 && tid < 35) build_pass_map(smem + L::DEC_MAP + 128 * (tid - 32), g, tid - 32);
@@ -812,16 +919,16 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
     __syncthreads();
     if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
         Planes c{0, 0};
+        const uint32_t* blk = reinterpret_cast<const uint32_t*>(smem + L::DEC_A + tid * L::DEC_VAR);
         for (int i = 0; i < 26; ++i) {
             const int idx = i * 32 + 13 * (int)st_of(g, tid, i);
-            gf3_add(c, reinterpret_cast<const uint32_t*>(smem + L::DEC_A)[idx] & ~0xFFu, reinterpret_cast<const uint32_t*>(smem + L::DEC_B)[idx]);
+            gf3_add(c, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
         }
         reinterpret_cast<uint32_t*>(smem + L::DEC_CHK)[2 * tid] = c.nz;
         reinterpret_cast<uint32_t*>(smem + L::DEC_CHK)[2 * tid + 1] = c.two;
     }
     __syncthreads();
     const uint32_t tabA32 = smem_u32(smem + L::DEC_A);
-    const uint8_t* tabB = smem + L::DEC_B;
     const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L::DEC_CHK);
     const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
     uint4* carry = reinterpret_cast<uint4*>(U + L::U_BYTES + L::META_BYTES);
@@ -879,112 +986,350 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
             r0[1] = (uint8_t)(4u * sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][(r0[1] >> 2) % 27u]]);
         }
         __syncwarp();
-        // ---- phase B: syndrome screen per codeword (variant-sorted lanes); descrambled data symbols -> stream order
-        const uint8_t* pmap = smem + L::DEC_MAP + 128 * (tile % 3u);
-#pragma unroll 1
-        for (int pass = 0; pass < L::PASS_B; ++pass) {
-            const uint32_t cw = pmap[32 * pass + lane];
-            if (cw == 255) continue;
-            const uint32_t cl = (cw * 57u) >> 9, b = cw - 9u * cl;          // cw / 9 for cw < 128
-            const uint32_t v = ((uint32_t)meta.vb[b] + cl) % 3u;
-            uint32_t pa = tabA32 + v * (26 * 128);
-            asm volatile("" : "+r"(pa));
-            const uint8_t* src = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
-            uint8_t* dst = S + cw + (9 * K - 9) * cl;                       // 9K*cl + b
-            Planes acc{0, 0}, acc2{0, 0};
-            uint32_t ev[K];
-            static_for<0, 26>([&](auto ic) {
-                constexpr int i = decltype(ic)::value;
-                const uint32_t x4 = src[i];
-                const uint32_t ea = lds_tab<128 * i>(pa + x4);
-                const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + x4 + 128 * i);
-                if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
-                if (i < K) ev[i < K ? i : 0] = ea;
-            });
-#pragma unroll
-            for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
-            gf3_add(acc, acc2.nz, acc2.two);
-            if (((acc.nz ^ chk[2 * v]) | (acc.two ^ chk[2 * v + 1])) & ~0xFFu) { // the low bytes carry the embedded symbols
-                // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
-                uint8_t cwd[26], orig[26];
-                for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(smem + L::DEC_A + v * (26 * 128) + src[i] + 128 * i);
-                if (!rs_decode_thread(sg, cwd, K, true)) {
-                    atomicExch(&P.status[2 * f], 0u);
-                } else {
-                    uint32_t nfix = 0;
-                    for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
-                    if (nfix) atomicAdd(&P.status[2 * f + 1], nfix);
-                    for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
-                }
-            }
-        }
+        dec_phase_b<K>(U, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, P.status + 2 * f, lane);
         __syncwarp();
         // ---- phase A: 26 stream symbols -> six pixels -> 18 RGB bytes per lane (units dealt even / odd)
         const uint64_t g_lo = P.out_stride * f + 3ull * L::PX * tile;
         const uint32_t pad = (uint32_t)(g_lo & 15);
         if (!first && lane == 0) *reinterpret_cast<uint4*>(U) = carry[0]; // bytes [0, pad): the previous tile's tail
         __syncwarp();
-#pragma unroll 1
-        for (int pass = 0; pass < L::PASS_A; ++pass) {
-            const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
-            if (u >= L::UNITS) continue;
-            const uint32_t a = 26u * (uint32_t)u;
-            const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
-            const uint32_t sh = (a & 2u) * 8u;
-            uint32_t x[7];
-#pragma unroll
-            for (int j = 0; j < 7; ++j) x[j] = mw[j];
-            uint32_t y[7]; // the 26 symbols, word aligned
-#pragma unroll
-            for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-            y[6] = x[6] >> sh;
-            uint32_t A[6];
-            symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
-            symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
-            uint32_t p[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) p[q] = value_to_rgb3(A[q]);
-            uint16_t* dh = reinterpret_cast<uint16_t*>(U + pad + 18 * u); // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { // two pixels = three halfwords
-                dh[3 * q] = (uint16_t)p[2 * q];
-                dh[3 * q + 1] = (uint16_t)((p[2 * q] >> 16) | (p[2 * q + 1] << 8));
-                dh[3 * q + 2] = (uint16_t)(p[2 * q + 1] >> 8);
-            }
-        }
+        dec_phase_a<K>(S, U, pad, lane);
         __syncwarp();
         stream_store(U, P.out, g_lo, L::RGB_BYTES, first, last, carry, lane);
         __syncwarp();
     }
 }
 
+// =============================================================================================
+// v4: the v3 phases with all tile I/O on the bulk-async copy engine (cp.async.bulk, SASS UBLKCP) and one CTA per SM.
+//   * the next tile's input is fetched into its own shared buffer by cp.async.bulk + mbarrier while the current tile is
+//     processed (the v3 profile showed 12 % of warp time waiting on the tile's first global load);
+//   * finished runs leave shared memory as bulk stores of whole 16-byte chunks (one instruction per run, issued by one
+//     lane per band) instead of LDS.128/STG.128 loops; the partial last chunk is carried to the next tile as in v3;
+//   * 28 (encode) / 27 (decode) warps share one copy of the tables.
+// =============================================================================================
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <int K> struct Cfg4 {
+    using L = Cfg3<K>;
+    static constexpr int IN_BYTES = (L::RGB_BYTES + 15 + 15) / 16 * 16;     // an RGB tile with its alignment slack
+    static constexpr int RUNS_BYTES = 9 * L::RUN_PITCH;
+    static constexpr int TAIL_BYTES = L::META_BYTES + L::CARRY_BYTES + 16;   // meta | carry | mbarrier
+    static constexpr int WARP_BYTES = IN_BYTES + L::S_BYTES + RUNS_BYTES + TAIL_BYTES; // encode: IN | S | U(runs);  decode: OUT | S | R(runs)
+    static constexpr int SMEM_MAX = 227 * 1024;
+    static constexpr int ENC_WARPS = (SMEM_MAX - L::ENC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - L::ENC_WARP) / WARP_BYTES : 32; // K=20: 28
+    static constexpr int DEC_WARPS = (SMEM_MAX - 256 - L::DEC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - 256 - L::DEC_WARP) / WARP_BYTES : 32; // K=20: 27
+    static constexpr int TOTAL_ENC = L::ENC_WARP + ENC_WARPS * WARP_BYTES;
+    static constexpr int TOTAL_DEC = 256 + L::DEC_WARP + DEC_WARPS * WARP_BYTES;
+};
+
+template <int K>
+__global__ void __launch_bounds__(32 * Cfg4<K>::ENC_WARPS, 1) k_encode_rgb_v4(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+{
+    using L = Cfg3<K>;
+    using L4 = Cfg4<K>;
+    constexpr int V4_ENC_WARPS = L4::ENC_WARPS, TPB = 32 * V4_ENC_WARPS;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* IN = smem + L::ENC_WARP + warp * L4::WARP_BYTES;   // the RGB tile (bulk-loaded one tile ahead)
+    uint8_t* S = IN + L4::IN_BYTES;                             // stream symbols, pre-scaled by 4
+    uint8_t* U = S + L::S_BYTES;                                // the nine body runs
+    WarpMeta3& meta = *reinterpret_cast<WarpMeta3*>(U + L4::RUNS_BYTES);
+    uint4* carry = reinterpret_cast<uint4*>(U + L4::RUNS_BYTES + L::META_BYTES);
+    const uint32_t bar = smem_u32(U + L4::RUNS_BYTES + L::META_BYTES + L::CARRY_BYTES);
+    {
+        uint32_t* A = reinterpret_cast<uint32_t*>(smem + L::ENC_A);
+        uint32_t* B = reinterpret_cast<uint32_t*>(smem + L::ENC_B);
+        const uint32_t(*pl)[kVals][2] = rs->pl[g.arith][(24 - K) / 2];
+        for (int idx = tid; idx < 3 * K * 27; idx += TPB) {
+            const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
+            A[idx] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
+            if (v == 0) B[rem] = pl[i][d][1];
+        }
+        if (tid < 3) {
+            uint32_t nz = 0, two = 0;
+            for (int j = 0; j < L::R; ++j) {
+                const uint32_t st = st_of(g, tid, K + j);
+                if (st) nz |= 7u << (8 + 4 * j);
+                if (st == 2) two |= 7u << (8 + 4 * j);
+            }
+            reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid] = nz;
+            reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid + 1] = two;
+        }
+        if (tid >= 32 && tid < 35) build_pass_map(smem + L::ENC_MAP + 128 * (tid - 32), g, tid - 32);
+        if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    }
+    __syncthreads(); // the only block-level barrier: tables and barriers ready
+    const uint32_t tabA32 = smem_u32(smem + L::ENC_A);
+    const uint8_t* tabB = smem + L::ENC_B;
+    const uint32_t* pat = reinterpret_cast<const uint32_t*>(smem + L::ENC_PAT);
+    const uint64_t in_limit = P.in_stride * P.n_frames;
+    uint32_t mt_lo, mt_hi;
+    warp_range((uint64_t)P.n_tiles * P.n_frames, blockIdx.x * V4_ENC_WARPS + warp, gridDim.x * V4_ENC_WARPS, mt_lo, mt_hi);
+    // bulk load of tile mt's pixels: the 16-byte aligned superset of [g_lo, g_lo + RGB_BYTES), clipped to the buffer
+    auto fetch = [&](uint32_t mt) {
+        const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
+        const uint64_t g_lo = P.in_stride * f + 3ull * L::PX * tile, a0 = g_lo & ~15ull;
+        uint32_t bytes = (uint32_t)((g_lo - a0) + L::RGB_BYTES + 15) & ~15u;
+        if (a0 + bytes > in_limit) bytes = (uint32_t)(in_limit - a0) & ~15u;
+        fence_async_smem();
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(IN), P.in + a0, bytes, bar);
+    };
+    if (mt_lo < mt_hi && lane == 0) fetch(mt_lo);
+    uint32_t phase = 0;
+    for (uint32_t mt = mt_lo; mt < mt_hi; ++mt) {
+        const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
+        const bool first = mt == mt_lo || tile == P.tile0, last = mt + 1 == mt_hi || tile + 1 == P.tile0 + P.n_tiles; // of a contiguous stretch
+        const uint64_t g_lo = P.in_stride * f + 3ull * L::PX * tile;
+        const uint32_t pad = (uint32_t)(g_lo & 15);
+        setup_runs3(meta, g, P.out_stride * f, tile, lane);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        {   // the last bytes of the buffer that a clipped bulk copy left out (only the final tile of the final frame)
+            const uint64_t a0 = g_lo - pad;
+            const uint32_t want = pad + L::RGB_BYTES;
+            if (a0 + ((want + 15) & ~15u) > in_limit)
+                for (uint32_t i = ((uint32_t)(in_limit - a0) & ~15u) + lane; i < want; i += 32) IN[i] = a0 + i < in_limit ? P.in[a0 + i] : 0;
+        }
+        __syncwarp();
+        enc_phase_a<K>(IN, pad, S, lane);
+        __syncwarp();
+        if (mt + 1 < mt_hi && lane == 0) fetch(mt + 1);                      // IN is free again: next tile's pixels on their way
+        if (lane < 9) {
+            bulk_wait_read();                                                // the previous tile's bulk stores have read U
+            if (!first) *reinterpret_cast<uint4*>(U + L::RUN_PITCH * lane) = carry[lane]; // bytes [0, pad) of each run: the previous tile's tail
+        }
+        __syncwarp();
+        enc_phase_b<K>(S, U, meta, smem + L::ENC_MAP + 128 * (tile % 3u), tabA32, tabB, pat, lane);
+        __syncwarp();
+        if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0 and 1 may still see the scrambler's transient (A.4)
+            uint8_t* dst = U + ((uint32_t)meta.run_lo[0] & 15u);
+            dst[0] = gf->scr[g.st[0]][S[0] >> 2];
+            dst[1] = gf->scr[g.st[1]][S[9] >> 2];
+        }
+        fence_async_smem();                                                  // generic-proxy writes to U before the bulk engine reads it
+        __syncwarp();
+        // ---- phase C: nine band-major runs -> global as bulk stores of whole chunks (carry scheme of stream_store)
+        if (lane < 9) {
+            const uint64_t lo = meta.run_lo[lane];
+            const uint32_t padb = (uint32_t)lo & 15u, cend = (padb + L::RUN) >> 4, c0 = (first && padb) ? 1u : 0u;
+            if (!last) carry[lane] = *reinterpret_cast<const uint4*>(U + L::RUN_PITCH * lane + 16 * cend);
+            if (cend > c0) bulk_s2g(P.out + (lo - padb) + 16 * c0, smem_u32(U + L::RUN_PITCH * lane + 16 * c0), 16 * (cend - c0));
+            bulk_commit();
+        }
+        if (first || last) { // edge bytes of a contiguous stretch, one by one
+#pragma unroll 1
+            for (int b = 0; b < 9; ++b) {
+                const uint64_t lo = meta.run_lo[b];
+                const int padb = (int)(lo & 15), end = padb + L::RUN, cend = end >> 4;
+                const uint8_t* s0 = U + L::RUN_PITCH * b;
+                uint8_t* g0 = P.out + (lo - padb);
+                if (first && padb && lane >= padb && lane < 16) g0[lane] = s0[lane];
+                if (last && lane < 16 && 16 * cend + lane < end) g0[16 * cend + lane] = s0[16 * cend + lane];
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 9) bulk_wait_all(); // shared memory must outlive the copies that read it
+}
+
+template <int K>
+__global__ void __launch_bounds__(32 * Cfg4<K>::DEC_WARPS, 1) k_decode_rgb_v4(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+{
+    using L = Cfg3<K>;
+    using L4 = Cfg4<K>;
+    constexpr int V4_DEC_WARPS = L4::DEC_WARPS, TPB = 32 * V4_DEC_WARPS;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u); // 256-byte aligned (see Cfg3)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* OUT = smem + L::DEC_WARP + warp * L4::WARP_BYTES;  // the RGB tile on its way out
+    uint8_t* S = OUT + L4::IN_BYTES;                            // descrambled stream symbols (plain)
+    uint8_t* R = S + L::S_BYTES;                                // the nine body runs (bulk-loaded one tile ahead, then x4 in place)
+    WarpMeta3& meta = *reinterpret_cast<WarpMeta3*>(R + L4::RUNS_BYTES);
+    uint4* carry = reinterpret_cast<uint4*>(R + L4::RUNS_BYTES + L::META_BYTES);
+    const uint32_t bar = smem_u32(R + L4::RUNS_BYTES + L::META_BYTES + L::CARRY_BYTES);
+    GfTables& sg = *reinterpret_cast<GfTables*>(smem + L::DEC_GF);
+    {
+        const uint32_t(*pl)[kVals][2] = rs->pl[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
+        for (int idx = tid; idx < 3 * 26 * 32; idx += TPB) {
+            const int v = idx / (26 * 32), rem = idx - v * (26 * 32), i = rem / 32, x = rem - 32 * i, xm = x >= 27 ? x - 27 : x;
+            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + L::DEC_A + v * L::DEC_VAR);
+            blk[rem] = pl[i][xm][0] | gf->dsc[st_of(g, v, i)][xm];
+            blk[26 * 32 + rem] = pl[i][xm][1];
+        }
+        load_gf(sg, gf);
+        if (tid >= 32 && tid < 35) build_pass_map(smem + L::DEC_MAP + 128 * (tid - 32), g, tid - 32);
+        if (lane == 0) { mbar_init(bar, 9); fence_mbar_init(); }
+    }
+    __syncthreads();
+    if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
+        Planes c{0, 0};
+        const uint32_t* blk = reinterpret_cast<const uint32_t*>(smem + L::DEC_A + tid * L::DEC_VAR);
+        for (int i = 0; i < 26; ++i) {
+            const int idx = i * 32 + 13 * (int)st_of(g, tid, i);
+            gf3_add(c, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
+        }
+        reinterpret_cast<uint32_t*>(smem + L::DEC_CHK)[2 * tid] = c.nz;
+        reinterpret_cast<uint32_t*>(smem + L::DEC_CHK)[2 * tid + 1] = c.two;
+    }
+    __syncthreads();
+    const uint32_t tabA32 = smem_u32(smem + L::DEC_A);
+    const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L::DEC_CHK);
+    const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
+    uint32_t mt_lo, mt_hi;
+    warp_range((uint64_t)P.n_tiles * P.n_frames, blockIdx.x * V4_DEC_WARPS + warp, gridDim.x * V4_DEC_WARPS, mt_lo, mt_hi);
+    // lane b < 9 bulk-loads band b's run of tile mt: the 16-byte aligned superset of the run, clipped to the buffer
+    auto fetch = [&](uint32_t mt) {
+        const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
+        const uint64_t lo = P.in_stride * f + 52 + 26 * (g.cw_base[lane] + (uint64_t)C_MINI * tile), a0 = lo & ~15ull;
+        uint32_t bytes = (uint32_t)((lo - a0) + L::RUN + 15) & ~15u;
+        if (a0 + bytes > in_limit) bytes = (uint32_t)(in_limit - a0) & ~15u;
+        fence_async_smem();
+        mbar_expect_tx(bar, bytes);
+        if (bytes) bulk_g2s(smem_u32(R + L::RUN_PITCH * lane), P.in + a0, bytes, bar);
+    };
+    if (mt_lo < mt_hi && lane < 9) fetch(mt_lo);
+    uint32_t phase = 0;
+    for (uint32_t mt = mt_lo; mt < mt_hi; ++mt) {
+        const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
+        const bool first = mt == mt_lo || tile == P.tile0, last = mt + 1 == mt_hi || tile + 1 == P.tile0 + P.n_tiles; // of a contiguous stretch
+        setup_runs3(meta, g, P.in_stride * f, tile, lane);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        __syncwarp();
+        // ---- the nine runs are in R: scale every byte by 4 (table byte offset) in place.  Bytes >= 32 would leave the
+        // 32-entry rows: they are reduced mod 27 first (out-of-alphabet symbols read as their low three trits, OLD:28-31)
+        bool wild = false;
+#pragma unroll 1
+        for (int it = 0; it < (9 * RUN_SLOTS + 31) / 32; ++it) {
+            const uint32_t sl = 32u * it + lane, b = (sl * 2850u) >> 16, c = sl - RUN_SLOTS * b;   // sl / 23 for sl < 256
+            if (b < 9) {
+                const uint64_t lo = meta.run_lo[b];
+                const uint32_t padb = (uint32_t)lo & 15u;
+                if (16 * c < padb + L::RUN) {
+                    uint4 q = *reinterpret_cast<const uint4*>(R + 16 * sl);
+                    const uint64_t ga = (lo - padb) + 16 * c;
+                    if (ga + 16 > in_limit) { // the clipped end of the buffer: fetch what exists byte by byte
+                        uint32_t t[4] = {0, 0, 0, 0};
+                        for (int i = 0; i < 16; ++i) if (ga + i < in_limit) t[i >> 2] |= (uint32_t)P.in[ga + i] << (8 * (i & 3));
+                        q = make_uint4(t[0], t[1], t[2], t[3]);
+                    }
+                    if (((q.x | q.y | q.z | q.w) & 0xE0E0E0E0u) != 0) {
+                        wild = true;
+                        uint32_t t[4] = {q.x, q.y, q.z, q.w};
+                        for (int i = 0; i < 4; ++i) {
+                            uint32_t r = 0;
+                            for (int j = 0; j < 4; ++j) r |= (((t[i] >> (8 * j)) & 0xFFu) % 27u) << (8 * j);
+                            t[i] = r;
+                        }
+                        q = make_uint4(t[0], t[1], t[2], t[3]);
+                    }
+                    q.x <<= 2; q.y <<= 2; q.z <<= 2; q.w <<= 2;
+                    *reinterpret_cast<uint4*>(R + 16 * sl) = q;
+                }
+            }
+        }
+        (void)wild;
+        __syncwarp();
+        if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0,1: move them from the transient states to the periodic ones
+            uint8_t* r0 = R + ((uint32_t)meta.run_lo[0] & 15u);
+            r0[0] = (uint8_t)(4u * sg.scr[st_of(g, 0, 0)][sg.dsc[g.st[0]][(r0[0] >> 2) % 27u]]);
+            r0[1] = (uint8_t)(4u * sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][(r0[1] >> 2) % 27u]]);
+        }
+        __syncwarp();
+        dec_phase_b<K>(R, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, P.status + 2 * f, lane);
+        __syncwarp();
+        if (mt + 1 < mt_hi && lane < 9) fetch(mt + 1);                       // R is free again: next tile's runs on their way
+        const uint64_t g_lo = P.out_stride * f + 3ull * L::PX * tile;
+        const uint32_t pad = (uint32_t)(g_lo & 15);
+        if (lane == 0) {
+            bulk_wait_read();                                                // the previous tile's bulk store has read OUT
+            if (!first) *reinterpret_cast<uint4*>(OUT) = carry[0];           // bytes [0, pad): the previous tile's tail
+        }
+        __syncwarp();
+        dec_phase_a<K>(S, OUT, pad, lane);
+        fence_async_smem();
+        __syncwarp();
+        {   // the RGB tile -> global: whole chunks by one bulk store, edge bytes of a stretch one by one
+            const uint32_t end = pad + L::RGB_BYTES, cend = end >> 4, c0 = (first && pad) ? 1u : 0u;
+            uint8_t* g0 = P.out + (g_lo - pad);
+            if (lane == 0) {
+                if (!last) carry[0] = *reinterpret_cast<const uint4*>(OUT + 16 * cend);
+                bulk_s2g(g0 + 16 * c0, smem_u32(OUT + 16 * c0), 16 * (cend - c0));
+                bulk_commit();
+            }
+            if (first && pad && lane >= (int)pad && lane < 16) g0[lane] = OUT[lane];
+            if (last && lane < 16 && 16 * cend + lane < end) g0[16 * cend + lane] = OUT[16 * cend + lane];
+        }
+        __syncwarp();
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
 template <class Kern>
-int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st, int& ctas_per_sm)
+int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st, int& ctas_per_sm,
+                      int warps = FAST_WARPS)
 {
     if (!ctas_per_sm) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, FAST_TPB, smem_bytes);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * warps, smem_bytes);
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
     uint64_t grid = (uint64_t)T.sm_count * ctas_per_sm;
-    const uint64_t need = (total + FAST_WARPS - 1) / FAST_WARPS;
+    const uint64_t need = (total + warps - 1) / warps;
     if (grid > need) grid = need;
     if (!grid) return 0;
-    kern<<<(unsigned)grid, FAST_TPB, smem_bytes, st>>>(P, g, T.gf, T.rs);
+    kern<<<(unsigned)grid, 32 * warps, smem_bytes, st>>>(P, g, T.gf, T.rs);
     return 1;
+}
+// T3C_FAST=3 keeps the v3 kernels (plain loads/stores, 4 CTAs per SM) for A/B comparison; default is v4 (bulk-async I/O)
+static bool use_v4()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("T3C_FAST"); v = (e && e[0] == '3') ? 0 : 1; }
+    return v == 1;
 }
 // tiles [t0, t1) of [0, n_full) of every frame go to the v3 kernels; with `tail` the ragged rest [n_full, n_all) goes to
 // the general-tile kernels
 template <int K>
 int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail)
 {
-    static int occ3 = 0, occ2 = 0;
+    static int occ4 = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 20) {
         if (t1 > n_full) t1 = n_full;
-        if (t1 > t0) { P.tile0 = t0; P.n_tiles = t1 - t0; n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3); }
+        if (t1 > t0) {
+            P.tile0 = t0; P.n_tiles = t1 - t0;
+            if (use_v4()) n += launch_persistent(k_encode_rgb_v4<K>, Cfg4<K>::TOTAL_ENC, T, P, g, st, occ4, Cfg4<K>::ENC_WARPS);
+            else n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3);
+        }
     } else n_full = 0;
     if (tail && n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_encode_rgb_fast<K>, Cfg<K>::TOTAL_ENC, T, P, g, st, occ2); }
     return n;
@@ -992,12 +1337,16 @@ int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st,
 template <int K>
 int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail)
 {
-    static int occ3 = 0, occ2 = 0;
+    static int occ4 = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 20) {
         if (t1 > n_full) t1 = n_full;
-        if (t1 > t0) { P.tile0 = t0; P.n_tiles = t1 - t0; n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3); }
+        if (t1 > t0) {
+            P.tile0 = t0; P.n_tiles = t1 - t0;
+            if (use_v4()) n += launch_persistent(k_decode_rgb_v4<K>, Cfg4<K>::TOTAL_DEC, T, P, g, st, occ4, Cfg4<K>::DEC_WARPS);
+            else n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3);
+        }
     } else n_full = 0;
     if (tail && n_all > n_full) { P.tile0 = n_full; P.n_tiles = n_all - n_full; n += launch_persistent(k_decode_rgb_fast<K>, Cfg<K>::TOTAL_DEC, T, P, g, st, occ2); }
     return n;
