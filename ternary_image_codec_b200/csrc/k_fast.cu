@@ -616,18 +616,32 @@ __device__ __forceinline__ void static_for(F&& f)
 // Phase-B lane -> codeword map.  A codeword's table variant is (band offset + tile + row) mod 3; passes 0..2 take 32
 // codewords of one variant each (all lanes then read the same 27-entry block of table A: no bank conflicts), pass 3
 // the remaining 21.  One 128-byte map per tile mod 3; 255 = idle lane.
-__device__ void build_pass_map(uint8_t* map, const Geom& g, int tm)
+// Built by 3 x 128 threads (one per tile-mod-3 and slot candidate): a codeword's rank inside its variant's row-major list is
+// a closed form of how many bands share each band offset mod 3.
+__device__ __forceinline__ void build_pass_map(uint8_t* maps, const Geom& g, int t)
 {
-    int n0 = 0, n1 = 0, n2 = 0, extra = 96;
-    uint32_t cwb = 0; // cw_base[b] mod 3, two bits per band
-    for (int b = 0; b < 9; ++b) cwb |= (uint32_t)(g.cw_base[b] % 3) << (2 * b);
-    for (int cw = 0; cw < 9 * C_MINI; ++cw) {
-        const int cl = cw / 9, b = cw - 9 * cl;
-        const int v = (int)(((cwb >> (2 * b)) & 3u) + (uint32_t)tm + (uint32_t)cl) % 3;
-        int& n = v == 0 ? n0 : (v == 1 ? n1 : n2);
-        if (n < 32) map[32 * v + n++] = (uint8_t)cw; else map[extra++] = (uint8_t)cw;
+    if (t >= 3 * 128) return;
+    const int tm = t >> 7, cw = t & 127;
+    uint8_t* map = maps + 128 * tm;
+    if (cw >= 9 * C_MINI) { map[cw] = 255; return; }
+    uint32_t cwb[9];
+    int nb[3] = {0, 0, 0}; // bands per offset class
+    for (int b = 0; b < 9; ++b) { cwb[b] = (uint32_t)(g.cw_base[b] % 3); ++nb[cwb[b]]; }
+    const int cl = cw / 9, b = cw - 9 * cl;
+    const int v = (int)((cwb[b] + (uint32_t)tm + (uint32_t)cl) % 3);
+    // variant of (band class x, row r) is (x + tm + r) % 3
+    auto row_count = [&](int vv, int r) { return nb[((vv - tm - r) % 3 + 3) % 3]; };
+    int rank = 0;
+    for (int r = 0; r < cl; ++r) rank += row_count(v, r);
+    for (int bb = 0; bb < b; ++bb) rank += ((int)((cwb[bb] + (uint32_t)tm + (uint32_t)cl) % 3) == v);
+    if (rank < 32) { map[32 * v + rank] = (uint8_t)cw; return; }
+    int off = 96; // leftovers of variants below v come first in the mixed pass
+    for (int vv = 0; vv < v; ++vv) {
+        int n = 0;
+        for (int r = 0; r < C_MINI; ++r) n += row_count(vv, r);
+        off += n - 32;
     }
-    for (; extra < 128; ++extra) map[extra] = 255;
+    map[off + rank - 32] = (uint8_t)cw;
 }
 // the nine staged runs <-> global in whole 16-byte chunks, flattened over (band, chunk): 9 x 23 slots in 7 steps
 constexpr int RUN_SLOTS = 23;
@@ -835,7 +849,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid] = nz;
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid + 1] = two;
         }
-        if (tid >= 32 && tid < 35) build_pass_map(smem + L::ENC_MAP + 128 * (tid - 32), g, tid - 32);
+        for (int t = tid; t < 3 * 128; t += (int)blockDim.x) build_pass_map(smem + L::ENC_MAP, g, t);
     }
     __syncthreads(); // the only block-level barrier: tables staged
     const uint32_t tabA32 = smem_u32(smem + L::ENC_A);
@@ -914,7 +928,7 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
             blk[26 * 32 + rem] = pl[i][xm][1];
         }
         load_gf(sg, gf);
-        if (tid >= 32 && tid < 35) build_pass_map(smem + L::DEC_MAP + 128 * (tid - 32), g, tid - 32);
+        for (int t = tid; t < 3 * 128; t += (int)blockDim.x) build_pass_map(smem + L::DEC_MAP, g, t);
     }
     __syncthreads();
     if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
@@ -1034,6 +1048,18 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
+// v4 tile ranges: CTAs get equal contiguous shares; inside a CTA the four SM sub-partitions (warp % 4) get equal shares
+// (a sub-partition's time is the sum of its warps' work, so per-warp rounding must not pile up on one of them), and
+// the warps of a sub-partition split its share.
+__device__ __forceinline__ void warp_range_smsp(uint64_t total, uint32_t cta, uint32_t n_cta, uint32_t warp, uint32_t n_warps, uint32_t& lo, uint32_t& hi)
+{
+    const uint64_t c_lo = total * cta / n_cta, c_hi = total * (cta + 1) / n_cta;
+    const uint32_t q = warp & 3u, j = warp >> 2, nq = (n_warps - q + 3u) >> 2; // warps on sub-partition q
+    const uint64_t q_lo = c_lo + (c_hi - c_lo) * q / 4, q_hi = c_lo + (c_hi - c_lo) * (q + 1) / 4;
+    lo = (uint32_t)(q_lo + (q_hi - q_lo) * j / nq);
+    hi = (uint32_t)(q_lo + (q_hi - q_lo) * (j + 1) / nq);
+}
+
 template <int K> struct Cfg4 {
     using L = Cfg3<K>;
     static constexpr int IN_BYTES = (L::RGB_BYTES + 15 + 15) / 16 * 16;     // an RGB tile with its alignment slack
@@ -1080,7 +1106,7 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::ENC_WARPS, 1) k_encode_rgb_v4(Fa
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid] = nz;
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid + 1] = two;
         }
-        if (tid >= 32 && tid < 35) build_pass_map(smem + L::ENC_MAP + 128 * (tid - 32), g, tid - 32);
+        for (int t = tid; t < 3 * 128; t += (int)blockDim.x) build_pass_map(smem + L::ENC_MAP, g, t);
         if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     }
     __syncthreads(); // the only block-level barrier: tables and barriers ready
@@ -1089,7 +1115,7 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::ENC_WARPS, 1) k_encode_rgb_v4(Fa
     const uint32_t* pat = reinterpret_cast<const uint32_t*>(smem + L::ENC_PAT);
     const uint64_t in_limit = P.in_stride * P.n_frames;
     uint32_t mt_lo, mt_hi;
-    warp_range((uint64_t)P.n_tiles * P.n_frames, blockIdx.x * V4_ENC_WARPS + warp, gridDim.x * V4_ENC_WARPS, mt_lo, mt_hi);
+    warp_range_smsp((uint64_t)P.n_tiles * P.n_frames, blockIdx.x, gridDim.x, warp, V4_ENC_WARPS, mt_lo, mt_hi);
     // bulk load of tile mt's pixels: the 16-byte aligned superset of [g_lo, g_lo + RGB_BYTES), clipped to the buffer
     auto fetch = [&](uint32_t mt) {
         const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
@@ -1183,7 +1209,7 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::DEC_WARPS, 1) k_decode_rgb_v4(Fa
             blk[26 * 32 + rem] = pl[i][xm][1];
         }
         load_gf(sg, gf);
-        if (tid >= 32 && tid < 35) build_pass_map(smem + L::DEC_MAP + 128 * (tid - 32), g, tid - 32);
+        for (int t = tid; t < 3 * 128; t += (int)blockDim.x) build_pass_map(smem + L::DEC_MAP, g, t);
         if (lane == 0) { mbar_init(bar, 9); fence_mbar_init(); }
     }
     __syncthreads();
@@ -1202,7 +1228,7 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::DEC_WARPS, 1) k_decode_rgb_v4(Fa
     const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L::DEC_CHK);
     const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
     uint32_t mt_lo, mt_hi;
-    warp_range((uint64_t)P.n_tiles * P.n_frames, blockIdx.x * V4_DEC_WARPS + warp, gridDim.x * V4_DEC_WARPS, mt_lo, mt_hi);
+    warp_range_smsp((uint64_t)P.n_tiles * P.n_frames, blockIdx.x, gridDim.x, warp, V4_DEC_WARPS, mt_lo, mt_hi);
     // lane b < 9 bulk-loads band b's run of tile mt: the 16-byte aligned superset of the run, clipped to the buffer
     auto fetch = [&](uint32_t mt) {
         const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
