@@ -22,6 +22,7 @@ struct t3c_ctx {
     cudaEvent_t ev[32] = {};
     int ev_next = 0;
     DevTables tabs{};
+    HeaderCache hdr_cache{};
     void* d_tables = nullptr;
     HostTables* host = nullptr; // host copy of the constant tables (decoder screen constants are derived per call)
     // grow-only device scratch
@@ -184,6 +185,9 @@ t3c_status t3c_create(int device, t3c_ctx** out)
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->tabs.sm_count = prop.multiProcessorCount;
+    ctx->tabs.hdr = &ctx->hdr_cache;
+    if (cudaMalloc((void**)&ctx->hdr_cache.d52, 128) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
+    ctx->hdr_cache.d27 = ctx->hdr_cache.d52 + 64;
     *out = ctx;
     return T3C_OK;
 }
@@ -195,6 +199,7 @@ void t3c_destroy(t3c_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->buf) if (b.p) cudaFree(b.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->hdr_cache.d52) cudaFree(ctx->hdr_cache.d52);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -1434,7 +1434,7 @@ int launch_encode_rgb_fast_part(const DevTables& T, const t3c_config& cfg, const
     case 18: n = launch_enc<18>(T, P, g, st, n_full, t0, t1, tail); break;
     default: return 0;
     }
-    if (tail) n += launch_frame_misc(T, cfg, g, out, n_frames, 9ull * stride_words, st);
+    if (tail) n += launch_frame_finish(T, cfg, g, out, n_frames, 9ull * stride_words, st); // fast path: no beacon, only header + padding
     return n;
 }
 int launch_encode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* rgb, size_t n_px, size_t n_frames,

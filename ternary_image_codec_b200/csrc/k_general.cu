@@ -3,6 +3,8 @@
 // These kernels are correct for every configuration the reference accepts (mixed-k UEP, 2D
 // interleave with any tile, beacons, odd sizes).  The tiled fused kernels in k_fast.cu cover the
 // headline family (uniform k, 1D, no beacon) at memory-system speed.
+#include <cstring>
+
 #include "dev.cuh"
 #include "launch.h"
 
@@ -548,6 +550,31 @@ int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom&
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
     if (mx) { k_encode_general<<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs); ++n; }
     return n + launch_frame_misc(T, cfg, g, out, 1, 0, st);
+}
+const uint8_t* cached_header(const DevTables& T, const t3c_config& cfg, int arith, cudaStream_t st, int& launches)
+{
+    HeaderCache& H = *T.hdr;
+    if (!H.valid || H.arith != (arith ? 1 : 0) || std::memcmp(&H.cfg, &cfg, sizeof cfg) != 0) {
+        launches += launch_header_emit(T, cfg, arith, H.d27, H.d52, st);
+        cudaStreamSynchronize(st); // once per config change: later calls may come on other streams
+        H.cfg = cfg; H.arith = arith ? 1 : 0; H.valid = true;
+    }
+    return H.d52;
+}
+__global__ void k_frame_finish(uint8_t* __restrict__ out_base, size_t stride_bytes, const uint8_t* __restrict__ hdr52, uint64_t body_end, uint64_t frame_bytes)
+{
+    uint8_t* __restrict__ out = out_base + stride_bytes * blockIdx.x;
+    const uint32_t t = threadIdx.x;
+    if (t < 52) out[t] = hdr52[t];
+    if (body_end + t < frame_bytes && t < 16) out[body_end + t] = 0; // zeros up to the end of the last word
+}
+int launch_frame_finish(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out, size_t n_frames, size_t stride_bytes, cudaStream_t st)
+{
+    if (!n_frames) return 0;
+    int n = 0;
+    const uint8_t* hdr = cached_header(T, cfg, g.arith, st, n);
+    k_frame_finish<<<(unsigned)n_frames, 64, 0, st>>>(out, stride_bytes, hdr, 52 + g.l_body, 9 * g.n_out);
+    return n + 1;
 }
 int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out, size_t n_frames, size_t stride_bytes, cudaStream_t st)
 {

@@ -7,7 +7,10 @@
 
 namespace t3c {
 
-struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; };
+// The coded super-frame header depends on the config only: it is emitted on the device (k_header_emit) when the config
+// changes and kept in `d52`; every later frame copies the 52 symbols.
+struct HeaderCache { uint8_t* d52 = nullptr; uint8_t* d27 = nullptr; t3c_config cfg{}; int arith = -1; bool valid = false; };
+struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; };
 
 // geometry of the reference decoder as shipped (A.7): slot-major demap of words 6.. of the input
 struct RefDecGeom {
@@ -59,6 +62,10 @@ uint32_t fast_full_tiles_encode(const Geom& g, size_t n_px);
 uint32_t fast_full_tiles_decode(const Geom& g, size_t n_px_out, size_t out_pitch, size_t n_frames);
 // both return -1 when the buffers are not 16-byte aligned (caller falls back to the general kernels)
 // header + beacons + zero padding for n_frames super-frames laid out every stride_bytes
+// coded header for cfg (device pointer, 52 symbols), re-emitted on `st` only when cfg/arith differ from the cached one
+const uint8_t* cached_header(const DevTables& T, const t3c_config& cfg, int arith, cudaStream_t st, int& launches);
+// header copy + zero padding for fast-path frames (no beacon) from the cached header
+int launch_frame_finish(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out9, size_t n_frames, size_t stride_bytes, cudaStream_t st);
 int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out9, size_t n_frames, size_t stride_bytes, cudaStream_t st);
 
 } // namespace t3c
