@@ -64,7 +64,7 @@ class ClockSampler(threading.Thread):
                 sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
                 rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
-                self.rows.append([str(self.gpu), str(sm), str(mx), str(pw)] + ["Active" if rs & b else "Not Active" for _, b in bits])
+                self.rows.append([str(self.gpu), str(sm), str(mx), str(pw)] + ["Active" if rs & b else "Not Active" for _, b in bits] + [time.perf_counter()])
                 self.stop_flag.wait(0.0005)
             return
         except Exception:
@@ -74,12 +74,15 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                    self.rows.append([x.strip() for x in out.split(",")] + [time.perf_counter()])
             except Exception:
                 pass
             self.stop_flag.wait(0.1)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        if t0 is not None:  # samples taken inside the timed region (the sampler starts earlier: NVML init takes a while)
+            inside = [r for r in self.rows if t0 <= r[-1] <= t1]
+            self.rows = inside if inside else self.rows[-1:]
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -213,6 +216,8 @@ def run_ours(args):
     def decode(i):
         codec.decode_frames_rgb8_dev(enc[i], wpf, wpf, 1, n_px, back[i], status[2 * i:], cfg, stream)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for i in range(NBUF):
         encode(i)
     for w in range(max(args.warmup, 3)):
@@ -220,8 +225,6 @@ def run_ours(args):
         decode((w + 1) % NBUF)
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = codec.kernel_launches
     if world > 1:
@@ -229,6 +232,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
     t_start.record()
     for s in range(args.steps):
         ev[s][0].record()
@@ -238,6 +242,7 @@ def run_ours(args):
         ev[s][2].record()
     t_end.record()
     torch.cuda.synchronize()
+    wall1 = time.perf_counter()
     if world > 1:
         dist.barrier()
     launches = codec.kernel_launches - launches0
@@ -355,7 +360,7 @@ def run_ours(args):
         dom = "encode" if enc_ms >= dec_ms else "decode"
         dom_ms = max(enc_ms, dec_ms)
         ach = alg / (dom_ms * 1e-3) / 1e9
-        clocks = sampler.summary()
+        clocks = sampler.summary(wall0, wall1)
         out = {
             "metric": METRIC, "value": world * n_px * args.steps / (ms_total * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
