@@ -50,6 +50,7 @@ class ClockSampler(threading.Thread):
         self.gpu = gpu_index
         self.rows = []
         self.stop_flag = threading.Event()
+        self.ready = threading.Event()  # set after the first sample (NVML init takes ~25 ms: longer than the timed region)
 
     def run(self):
         try:  # NVML in-process: ~0.1 ms per sample, so even a few-millisecond timed region gets many
@@ -65,16 +66,18 @@ class ClockSampler(threading.Thread):
                 rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
                 self.rows.append([str(self.gpu), str(sm), str(mx), str(pw)] + ["Active" if rs & b else "Not Active" for _, b in bits] + [time.perf_counter()])
+                self.ready.set()
                 self.stop_flag.wait(0.0005)
             return
-        except Exception:
-            pass
+        except Exception as e:
+            sys.stderr.write(f"bench.py: NVML sampling unavailable ({e!r}), falling back to nvidia-smi\n")
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
                     self.rows.append([x.strip() for x in out.split(",")] + [time.perf_counter()])
+                    self.ready.set()
             except Exception:
                 pass
             self.stop_flag.wait(0.1)
@@ -218,6 +221,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.ready.wait(10.0)
     for i in range(NBUF):
         encode(i)
     for w in range(max(args.warmup, 3)):
@@ -285,7 +289,7 @@ def run_ours(args):
         # words cross PCIe inside the timed region in both calls.  The serial figure (one thread, encode then decode) is
         # reported next to it.
         codec2 = t3.Codec(local, arith=t3.FIXED)
-        h_enc2 = [h_enc, torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory()]
+        h_enc2 = [h_enc, torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory(), torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory()]
         okb2 = np.zeros(1, np.uint8)
         rec2, nc2 = C.c_size_t(), C.c_size_t()
 
@@ -302,18 +306,37 @@ def run_ours(args):
             enc_call(0)
             dec_call(0)
 
-        from concurrent.futures import ThreadPoolExecutor
-        pool = ThreadPoolExecutor(max_workers=2)
+        import queue
 
-        def e2e_pipelined(n):  # n frames: encode(i) || decode(i-1)
-            enc_call(0)
-            for i in range(1, n):
-                a = pool.submit(enc_call, i & 1)
-                b = pool.submit(dec_call, (i - 1) & 1)
-                a.result(); b.result()
-            dec_call((n - 1) & 1)
+        def e2e_pipelined(n):  # n frames: the encoder thread runs ahead of the decoder thread through a 3-slot ring of word buffers
+            ready, free = queue.Queue(), queue.Queue()
+            for slot in range(len(h_enc2)):
+                free.put(slot)
+            err = []
 
-        e2e_steps = max(4, min(args.steps, 10))
+            def producer():
+                try:
+                    for _ in range(n):
+                        slot = free.get()
+                        enc_call(slot)
+                        ready.put(slot)
+                except Exception as e:  # pragma: no cover
+                    err.append(e)
+                    ready.put(None)
+
+            th = threading.Thread(target=producer)
+            th.start()
+            for _ in range(n):
+                slot = ready.get()
+                if slot is None:
+                    break
+                dec_call(slot)
+                free.put(slot)
+            th.join()
+            if err:
+                raise err[0]
+
+        e2e_steps = max(8, min(args.steps, 20))
         e2e_step()
         e2e_pipelined(2)
         if world > 1:
@@ -331,7 +354,6 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        pool.shutdown()
         codec2.close()
         assert torch.equal(h_back.view(-1), chk.cpu()), "e2e round trip mismatch"
         e2e = {"value": world * n_px * e2e_steps / dt / 1e6, "unit": UNIT,
@@ -360,7 +382,10 @@ def run_ours(args):
         dom = "encode" if enc_ms >= dec_ms else "decode"
         dom_ms = max(enc_ms, dec_ms)
         ach = alg / (dom_ms * 1e-3) / 1e9
+        n_all = len(sampler.rows)
         clocks = sampler.summary(wall0, wall1)
+        clocks["samples_total"] = n_all
+        clocks["window_ms"] = 1e3 * (wall1 - wall0)
         out = {
             "metric": METRIC, "value": world * n_px * args.steps / (ms_total * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
