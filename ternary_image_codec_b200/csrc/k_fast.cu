@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_fast(FastParams P, G
             uint32_t y[5]; // the 18 bytes, word aligned
 #pragma unroll
             for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-            y[4] = x[4] >> sh;
+            y[4] = __funnelshift_r(x[4], sh == 24 ? mw[5] : 0u, sh); // 18 bytes from byte offset 3 reach into a sixth word (odd frame offsets)
             uint32_t A[6];
 #pragma unroll
             for (int p = 0; p < 6; ++p) {
@@ -672,7 +672,7 @@ __device__ __forceinline__ void enc_phase_a(const uint8_t* U, uint32_t pad, uint
         uint32_t y[5]; // the 18 bytes, word aligned
 #pragma unroll
         for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-        y[4] = x[4] >> sh;
+        y[4] = __funnelshift_r(x[4], sh == 24 ? mw[5] : 0u, sh); // 18 bytes from byte offset 3 reach into a sixth word (odd frame offsets)
         uint32_t A[6];
 #pragma unroll
         for (int p = 0; p < 6; ++p) {

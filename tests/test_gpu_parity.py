@@ -535,3 +535,27 @@ def test_host_pipeline_chunked_frames_match_oracle(codec, oracle, t3, kw):
     for f in range(2):
         ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, enc[f], n_px)
         assert ok_o and np.array_equal(rgb[f], rgb_o)
+
+
+@pytest.mark.parametrize("kw,n_px,nf", [(dict(profile=T.P3, uep=2), 540 * 70 + 33, 2), (dict(profile=T.P2, uep=1), 594 * 40, 1),
+                                        (dict(profile=T.P1, uep=0), 648 * 35 + 1, 3), (dict(profile=T.P4, uep=3), 486 * 9 + 5, 2)])
+def test_fused_multi_frame_odd_sizes(codec, oracle, t3, kw, n_px, nf):
+    """several frames of odd pixel count in one call: frames start on odd byte offsets (RGB) -- every alignment of the
+    tiled kernels' 18-byte pixel units and of the nine body runs; encode parity, error correction, decode parity"""
+    oc, gc = both(kw)
+    frames = np.stack([T.synth_rgb(40 + f, n_px) for f in range(nf)])
+    for arith in (t3.REF_EXACT, t3.FIXED):
+        enc = codec.encode_frames_rgb8(frames, gc, arith)
+        for f in range(nf):
+            assert np.array_equal(enc[f], oracle.encode_rgb(oc, frames[f], arith)), (arith, f)
+    add = T.gf_add_table()
+    bad = enc.copy()
+    tot = 0
+    for f in range(nf):
+        bad[f], ne = T.inject_errors(enc[f], oc, (n_px + 1) // 2, seed=5 + f, gf_add=add)
+        tot += ne
+    ok, rgb, nc = codec.decode_frames_rgb8(bad, n_px, gc)
+    assert ok.all() and nc == tot
+    for f in range(nf):
+        ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, enc[f], n_px)
+        assert ok_o and np.array_equal(rgb[f], rgb_o)
