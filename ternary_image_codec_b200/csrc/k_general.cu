@@ -172,6 +172,176 @@ __global__ void __launch_bounds__(PACK_TPB) k_unpack_pixels(const uint8_t* __res
     }
 }
 
+// =============================================================================================
+// RAW mode v2 (BASELINE config 3): persistent warps, 512-pixel tiles (3072 B of PixelYCbCrQuant <-> 2304 B of Word27:
+// both multiples of 16, so no edge handling), tile I/O on the bulk-async copy engine with the next tile prefetched,
+// and the per-word arithmetic cut from ~57 / ~81 to ~25 instructions per pixel (the v1 kernels were issue-bound:
+// profiles/r01c_raw_v1_ncu_summary.txt).  The ragged tail (< 512 pixels) keeps the v1 kernels.
+// =============================================================================================
+namespace raw2 {
+constexpr int TILE_PX = 512, TILE_IN = 6 * TILE_PX, TILE_OUT = 9 * TILE_PX / 2, WARPS = 32, TPB = 32 * WARPS;
+constexpr int WARP_BYTES = TILE_IN + TILE_OUT + 16; // quantised pixels | words | mbarrier
+constexpr int SMEM = WARPS * WARP_BYTES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) { asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// two pixels (six halfwords: Ya Cba Cra Yb Cbb Crb) -> nine symbols, pack_two_pixels OLD:693-705 with i2tr's wrap
+// (every field keeps its low 5 / 4 trits, OLD:675-682)
+__device__ __forceinline__ void word_from_pixels(uint32_t h0, uint32_t h1, uint32_t h2, uint32_t& o0, uint32_t& o1, uint32_t& o2)
+{
+    // fields as 16-bit values, chroma offset by 40; in range (Y < 243, chroma + 40 < 81) nothing wraps
+    uint32_t Ya = h0 & 0xFFFFu, Cba = ((h0 >> 16) + 40u) & 0xFFFFu, Cra = (h1 + 40u) & 0xFFFFu;
+    uint32_t Yb = h1 >> 16, Cbb = (h2 + 40u) & 0xFFFFu, Crb = ((h2 >> 16) + 40u) & 0xFFFFu;
+    if (((Ya + 13u) | (Yb + 13u) | (Cba + 175u) | (Cra + 175u) | (Cbb + 175u) | (Crb + 175u)) >> 8) { // rare: i2tr keeps the low trits of the 32-bit value
+        Ya %= 243u; Yb %= 243u;
+        Cba = (uint32_t)((int)(int16_t)(h0 >> 16) + 40) % 81u; Cra = (uint32_t)((int)(int16_t)(h1 & 0xFFFFu) + 40) % 81u;
+        Cbb = (uint32_t)((int)(int16_t)(h2 & 0xFFFFu) + 40) % 81u; Crb = (uint32_t)((int)(int16_t)(h2 >> 16) + 40) % 81u;
+    }
+    // all fields < 243: one IMAD.HI per quotient (ceil(2^32/d) is exact far beyond this range)
+    const uint32_t ya1 = __umulhi(Ya, 159072863u), cba1 = __umulhi(Cba, 1431655766u), cra1 = __umulhi(Cra, 159072863u);
+    const uint32_t yb1 = __umulhi(Yb, 477218589u), cbb1 = __umulhi(Cbb, 159072863u), crb1 = __umulhi(Crb, 477218589u);
+    const uint32_t s0 = Ya - 27u * ya1, s1 = ya1 + 9u * (Cba - 3u * cba1), s2 = cba1, s3 = Cra - 27u * cra1;
+    const uint32_t s4 = cra1 + 3u * (Yb - 9u * yb1), s5 = yb1, s6 = Cbb - 27u * cbb1, s7 = cbb1 + 3u * (Crb - 9u * crb1), s8 = crb1;
+    o0 = s0 + (s1 << 8) + (s2 << 16) + (s3 << 24);
+    o1 = s4 + (s5 << 8) + (s6 << 16) + (s7 << 24);
+    o2 = s8;
+}
+// nine symbols -> two pixels as three words of halfwords; every symbol contributes its low three trits (unpack3, OLD:28-31)
+__device__ __forceinline__ void pixels_from_word(uint32_t w0, uint32_t w1, uint32_t s8, uint32_t& h0, uint32_t& h1, uint32_t& h2)
+{
+    if (((w0 | w1 | s8) & 0xE0E0E0E0u) || (((w0 & 0x1F1F1F1Fu) + 0x05050505u) | ((w1 & 0x1F1F1F1Fu) + 0x05050505u) | (s8 + 5u)) & 0x20202020u) {
+        // some byte is >= 27: reduce every symbol mod 27 (rare)
+        uint32_t a = 0, b = 0;
+        for (int i = 0; i < 4; ++i) { a |= (((w0 >> (8 * i)) & 0xFFu) % 27u) << (8 * i); b |= (((w1 >> (8 * i)) & 0xFFu) % 27u) << (8 * i); }
+        w0 = a; w1 = b; s8 = (s8 & 0xFFu) % 27u;
+    }
+    const uint32_t v0 = w0 & 0xFFu, v1 = (w0 >> 8) & 0xFFu, v2 = (w0 >> 16) & 0xFFu, v3 = w0 >> 24;
+    const uint32_t v4 = w1 & 0xFFu, v5 = (w1 >> 8) & 0xFFu, v6 = (w1 >> 16) & 0xFFu, v7 = w1 >> 24;
+    const uint32_t q1 = __umulhi(v1, 477218589u), q4 = __umulhi(v4, 1431655766u), q7 = __umulhi(v7, 1431655766u); // v < 27
+    const uint32_t Ya = v0 + 27u * (v1 - 9u * q1), Cba = q1 + 3u * v2 - 40u, Cra = v3 + 27u * (v4 - 3u * q4) - 40u;
+    const uint32_t Yb = q4 + 9u * v5, Cbb = v6 + 27u * (v7 - 3u * q7) - 40u, Crb = q7 + 9u * (s8 - 9u * __umulhi(s8, 477218589u)) - 40u;
+    h0 = Ya | (Cba << 16);
+    h1 = (Cra & 0xFFFFu) | (Yb << 16);
+    h2 = (Cbb & 0xFFFFu) | (Crb << 16);
+}
+
+__global__ void __launch_bounds__(TPB, 1) k_pack_pixels_v2(const uint8_t* __restrict__ px, uint32_t n_tiles, uint8_t* __restrict__ words)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* IN = smem + warp * WARP_BYTES;
+    uint8_t* OUT = IN + TILE_IN;
+    const uint32_t bar = smem_u32(OUT + TILE_OUT);
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    // tiles are dealt round-robin over all warps of the grid: at any time the machine works on one moving window of
+    // consecutive tiles (DRAM-friendly); tile boundaries are 16-byte aligned, so nothing is carried between tiles
+    const uint32_t lo = blockIdx.x + gridDim.x * warp, hi = n_tiles, step = gridDim.x * WARPS;
+    auto fetch = [&](uint32_t t) { fence_async_smem(); mbar_expect_tx(bar, TILE_IN); bulk_g2s(smem_u32(IN), px + (size_t)TILE_IN * t, TILE_IN, bar); };
+    if (lo < hi && lane == 0) fetch(lo);
+    uint32_t phase = 0;
+    for (uint32_t t = lo; t < hi; t += step) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        uint4 q[6]; // two passes: this lane's 2 x 4 words = 2 x 48 bytes of pixels
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) q[3 * p + j] = *reinterpret_cast<const uint4*>(IN + 1536 * p + 48 * lane + 16 * j);
+        __syncwarp();
+        if (t + step < hi && lane == 0) fetch(t + step);           // IN is in registers: next tile on its way
+        if (lane == 0) bulk_wait_read();                           // the previous tile's store has read OUT
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t h[12] = {q[3 * p].x, q[3 * p].y, q[3 * p].z, q[3 * p].w, q[3 * p + 1].x, q[3 * p + 1].y, q[3 * p + 1].z, q[3 * p + 1].w,
+                                    q[3 * p + 2].x, q[3 * p + 2].y, q[3 * p + 2].z, q[3 * p + 2].w};
+            uint32_t o[9];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                uint32_t a, b, c;
+                word_from_pixels(h[3 * w], h[3 * w + 1], h[3 * w + 2], a, b, c);
+                // nine bytes at byte offset 9w of the lane's 36 output bytes
+                if (w == 0) { o[0] = a; o[1] = b; o[2] = c; }
+                if (w == 1) { o[2] |= a << 8; o[3] = (a >> 24) | (b << 8); o[4] = (b >> 24) | (c << 8); }
+                if (w == 2) { o[4] |= a << 16; o[5] = (a >> 16) | (b << 16); o[6] = (b >> 16) | (c << 16); }
+                if (w == 3) { o[6] |= a << 24; o[7] = (a >> 8) | (b << 24); o[8] = (b >> 8) | (c << 24); }
+            }
+            uint32_t* d = reinterpret_cast<uint32_t*>(OUT + 1152 * p + 36 * lane);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) d[j] = o[j];
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { bulk_s2g(words + (size_t)TILE_OUT * t, smem_u32(OUT), TILE_OUT); bulk_commit(); }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+__global__ void __launch_bounds__(TPB, 1) k_unpack_pixels_v2(const uint8_t* __restrict__ words, uint32_t n_tiles, uint8_t* __restrict__ px)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* OUT = smem + warp * WARP_BYTES;       // pixels
+    uint8_t* IN = OUT + TILE_IN;                   // words
+    const uint32_t bar = smem_u32(IN + TILE_OUT);
+    if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    __syncthreads();
+    const uint32_t lo = blockIdx.x + gridDim.x * warp, hi = n_tiles, step = gridDim.x * WARPS; // round-robin, see k_pack_pixels_v2
+    auto fetch = [&](uint32_t t) { fence_async_smem(); mbar_expect_tx(bar, TILE_OUT); bulk_g2s(smem_u32(IN), words + (size_t)TILE_OUT * t, TILE_OUT, bar); };
+    if (lo < hi && lane == 0) fetch(lo);
+    uint32_t phase = 0;
+    for (uint32_t t = lo; t < hi; t += step) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        uint32_t in[18]; // two passes: this lane's 2 x 4 words = 2 x 36 bytes of symbols
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) in[9 * p + j] = *reinterpret_cast<const uint32_t*>(IN + 1152 * p + 36 * lane + 4 * j);
+        __syncwarp();
+        if (t + step < hi && lane == 0) fetch(t + step);
+        if (lane == 0) bulk_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const uint32_t* s = in + 9 * p;
+            uint32_t h[12];
+            // word w = bytes 9w .. 9w+8 of the lane's 36 bytes
+            pixels_from_word(s[0], s[1], s[2] & 0xFFu, h[0], h[1], h[2]);
+            pixels_from_word(__funnelshift_r(s[2], s[3], 8), __funnelshift_r(s[3], s[4], 8), (s[4] >> 8) & 0xFFu, h[3], h[4], h[5]);
+            pixels_from_word(__funnelshift_r(s[4], s[5], 16), __funnelshift_r(s[5], s[6], 16), (s[6] >> 16) & 0xFFu, h[6], h[7], h[8]);
+            pixels_from_word(__funnelshift_r(s[6], s[7], 24), __funnelshift_r(s[7], s[8], 24), s[8] >> 24, h[9], h[10], h[11]);
+            uint4* d = reinterpret_cast<uint4*>(OUT + 1536 * p + 48 * lane);
+            d[0] = make_uint4(h[0], h[1], h[2], h[3]); d[1] = make_uint4(h[4], h[5], h[6], h[7]); d[2] = make_uint4(h[8], h[9], h[10], h[11]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { bulk_s2g(px + (size_t)TILE_IN * t, smem_u32(OUT), TILE_IN); bulk_commit(); }
+    }
+    if (lane == 0) bulk_wait_all();
+}
+} // namespace raw2
+
 __global__ void k_init_status(uint32_t* st, size_t n)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,17 +667,52 @@ int launch_quant_to_rgb(const t3c_pixel* px, size_t n, uint8_t* rgb, cudaStream_
     k_quant_to_rgb<<<blocks_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(px), n, rgb);
     return 1;
 }
+static int raw2_grid(uint32_t n_tiles)
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(raw2::k_pack_pixels_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, raw2::SMEM);
+        cudaFuncSetAttribute(raw2::k_unpack_pixels_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, raw2::SMEM);
+    }
+    const uint32_t need = (n_tiles + raw2::WARPS - 1) / raw2::WARPS;
+    return (int)(need < (uint32_t)sms ? need : (uint32_t)sms);
+}
 int launch_pack_pixels(const t3c_pixel* px, size_t n, uint8_t* words, cudaStream_t st)
 {
     if (!n) return 0;
-    k_pack_pixels<<<blocks_for(n, PACK_PX_PER_BLOCK), PACK_TPB, 0, st>>>(reinterpret_cast<const uint16_t*>(px), n, words);
-    return 1;
+    int k = 0;
+    size_t done = 0;
+    if (n >= 64 * raw2::TILE_PX && !(((uintptr_t)px | (uintptr_t)words) & 15)) { // whole 512-pixel tiles: bulk-async persistent kernel
+        const uint32_t n_tiles = (uint32_t)(n / raw2::TILE_PX);
+        raw2::k_pack_pixels_v2<<<raw2_grid(n_tiles), raw2::TPB, raw2::SMEM, st>>>(reinterpret_cast<const uint8_t*>(px), n_tiles, words);
+        done = (size_t)n_tiles * raw2::TILE_PX;
+        ++k;
+    }
+    if (done < n) {
+        k_pack_pixels<<<blocks_for(n - done, PACK_PX_PER_BLOCK), PACK_TPB, 0, st>>>(reinterpret_cast<const uint16_t*>(px) + 3 * done, n - done, words + 9 * (done / 2));
+        ++k;
+    }
+    return k;
 }
 int launch_unpack_pixels(const uint8_t* words, size_t n, t3c_pixel* px, cudaStream_t st)
 {
     if (!n) return 0;
-    k_unpack_pixels<<<blocks_for(n, PACK_PX_PER_BLOCK / 2), PACK_TPB, 0, st>>>(words, n, reinterpret_cast<uint16_t*>(px));
-    return 1;
+    int k = 0;
+    size_t done = 0; // words
+    if (n >= 32 * raw2::TILE_PX && !(((uintptr_t)px | (uintptr_t)words) & 15)) {
+        const uint32_t n_tiles = (uint32_t)(n / (raw2::TILE_PX / 2));
+        raw2::k_unpack_pixels_v2<<<raw2_grid(n_tiles), raw2::TPB, raw2::SMEM, st>>>(words, n_tiles, reinterpret_cast<uint8_t*>(px));
+        done = (size_t)n_tiles * (raw2::TILE_PX / 2);
+        ++k;
+    }
+    if (done < n) {
+        k_unpack_pixels<<<blocks_for(n - done, PACK_PX_PER_BLOCK / 2), PACK_TPB, 0, st>>>(words + 9 * done, n - done, reinterpret_cast<uint16_t*>(px) + 6 * done);
+        ++k;
+    }
+    return k;
 }
 int launch_mod27(const uint8_t* in, size_t n, uint8_t* out, cudaStream_t st)
 {

@@ -304,7 +304,7 @@ def test_fixed_roundtrip_with_errors(codec, oracle, t3, ci):
 
 
 # ------------------------------------------------------------------ fused frames
-@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4, 5, 7, 9, 12])
+@pytest.mark.parametrize("ci", [0, 1, 2, 3, 4, 5, 7, 9, 11, 12])
 @pytest.mark.parametrize("shape", [(64, 64), (512, 512), (130, 77)])
 def test_fused_frames_rgb8(codec, oracle, t3, ci, shape):
     oc, gc = both(CONFIGS[ci])

@@ -25,7 +25,7 @@ def timeit(fn, n=10, warm=3):
     return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))[n // 2]
 
 
-def raw8k():
+def raw8k():  # see also tools/quick_raw.py (back-to-back launches between two events)
     g = torch.Generator(device=dev); g.manual_seed(4)
     NB = 3
     px = []

@@ -80,7 +80,7 @@ def main():
             if r[iline].isdigit() and r[ie].isdigit():
                 key = (fpath, int(r[iline]))
                 e = lines.setdefault(key, [0, 0, 0, r[isrc].strip()[:100]])
-                e[0] += int(r[ie]); e[1] += int(r[iw] or 0); e[2] += int(r[ii] or 0)
+                e[0] += int(r[ie]); e[1] += int(r[iw]) if r[iw].isdigit() else 0; e[2] += int(r[ii]) if r[ii].isdigit() else 0
             elif r[iline] == "" and r[ie].isdigit():
                 op = r[isass].split()
                 if op:
