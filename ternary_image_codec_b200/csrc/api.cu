@@ -277,7 +277,14 @@ t3c_status t3c_encode_profile_dev(t3c_ctx* ctx, const t3c_config* cfg, int arith
     Geom g;
     make_geom(*cfg, n_words, arith, g);
     if (cap_words < g.n_out) return fail(ctx, T3C_ERR_CAPACITY, "encode_profile: capacity");
-    return check_launch(ctx, launch_encode_general(ctx->tabs, *cfg, g, d_raw, d_out, s));
+    uint32_t n_full = 0;
+    int n = 0;
+    if (fast_path_ok(*cfg)) { // uniform k, 1D, no beacon: the tiled kernels code the full mini-tiles straight from the raw words
+        n = launch_encode_words_fast(ctx->tabs, g, d_raw, d_out, s, &n_full);
+        if (n < 0) { n = 0; n_full = 0; }
+    }
+    n += launch_encode_general(ctx->tabs, *cfg, g, d_raw, d_out, s, 13ull * n_full); // the ragged rest (or everything), header, padding
+    return check_launch(ctx, n);
 }
 
 t3c_status t3c_decode_profile_fixed_dev(t3c_ctx* ctx, const t3c_config* cfg, size_t n_raw_words, const uint8_t* d_in, size_t n_words,
@@ -295,10 +302,16 @@ t3c_status t3c_decode_profile_fixed_dev(t3c_ctx* ctx, const t3c_config* cfg, siz
     if (cap_words < nw) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile_fixed: capacity");
     uint8_t* sy = nullptr;
     TRY(reserve_t(ctx, B_TMP, g.n_s + 16, &sy));
-    CU(cudaMemsetAsync(sy, 0, g.n_s + 16, s));
     int n = launch_init_status(d_status, 1, s);
-    n += launch_decode_fixed_general(ctx->tabs, g, d_in, sy, d_status, s);
-    n += launch_regroup_words(sy, g.n_s, g.tile_area, g.tile_w, d_out, (size_t)nw, s);
+    uint32_t n_full = 0;
+    if (fast_path_ok(*cfg)) { // tiled kernels: profile words -> raw words for the full mini-tiles
+        const int k = launch_decode_words_fast(ctx->tabs, g, d_in, d_out, (size_t)nw, d_status, s, &n_full);
+        if (k < 0) n_full = 0; else n += k;
+    }
+    const size_t sy_done = (size_t)n_full * 117 * (size_t)g.uniform_k; // stream symbols of the tiles already turned into words
+    CU(cudaMemsetAsync(sy + sy_done, 0, g.n_s + 16 - sy_done, s));
+    n += launch_decode_fixed_general(ctx->tabs, g, d_in, sy, d_status, s, 13ull * n_full);
+    n += launch_regroup_words(sy, g.n_s, g.tile_area, g.tile_w, d_out, (size_t)nw, s, (size_t)n_full * (27 * (size_t)g.uniform_k / 2));
     return check_launch(ctx, n);
 }
 

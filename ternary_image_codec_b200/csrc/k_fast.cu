@@ -821,6 +821,101 @@ __device__ __forceinline__ void dec_phase_a(const uint8_t* S, uint8_t* U, uint32
     }
 }
 
+// ---- raw-word front end (encode_profile_from_raw's own input, OLD:1051-1082): three Word27 (27 bytes at IN + pad + 27u) ->
+// six 13-trit pixel values -> 26 stream symbols (x4) at S + 26u.  The regroup keeps the first 26 trits of every word, which
+// are exactly the two 13-trit halves; bytes >= 27 read as their low three trits (unpack3, OLD:28-31).
+template <int K>
+__device__ __forceinline__ void enc_phase_a_words(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
+{
+    using L = Cfg3<K>;
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_A; ++pass) {
+        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+        if (u >= L::UNITS) continue;
+        const uint32_t a = pad + 27u * (uint32_t)u;
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
+        const uint32_t sh = (a & 3u) * 8u;
+        uint32_t x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = mw[j];
+        uint32_t y[7]; // the 27 bytes, word aligned
+#pragma unroll
+        for (int j = 0; j < 7; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+        y[6] &= 0x00FFFFFFu;
+        uint32_t wild = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) wild |= ((y[j] & 0x7F7F7F7Fu) + 0x65656565u) | y[j]; // bit 7 of a byte set <=> byte >= 27
+        if (wild & 0x80808080u) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                uint32_t r = 0;
+                for (int q = 0; q < 4; ++q) r |= (((y[j] >> (8 * q)) & 0xFFu) % 27u) << (8 * q);
+                y[j] = r;
+            }
+        }
+        auto val4 = [](uint32_t w) { return __dp4a(w, 0x00001B01u, 0u) + 729u * __dp4a(w, 0x1B010000u, 0u); };
+        uint32_t A[6];
+#pragma unroll
+        for (int w = 0; w < 3; ++w) { // word w = bytes 9w .. 9w+8
+            const int o = 9 * w;
+            auto word_at = [&](int b) { return (b & 3) ? __funnelshift_r(y[b >> 2], y[(b >> 2) + 1 > 6 ? 6 : (b >> 2) + 1], 8 * (b & 3)) : y[b >> 2]; };
+            const uint32_t lo4 = word_at(o), s4 = word_at(o + 4) & 0xFFu;
+            uint32_t hi4 = word_at(o + 5);
+            if (w == 2) hi4 = (y[5] >> 24) | (y[6] << 8);                   // bytes 23..26 (word_at would read past y[6])
+            const uint32_t s8 = hi4 >> 24, q8 = __umulhi(s8, 477218589u);      // the 27th trit is dropped: s8 % 9
+            hi4 = (hi4 & 0x00FFFFFFu) | ((s8 - 9u * q8) << 24);
+            const uint32_t q4 = __umulhi(s4, 1431655766u);                     // s4 / 3
+            A[2 * w] = val4(lo4) + 531441u * (s4 - 3u * q4);
+            A[2 * w + 1] = q4 + 9u * val4(hi4);
+        }
+        uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
+        triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
+        triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
+        w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2;
+        uint16_t* d = reinterpret_cast<uint16_t*>(S + 26 * u);
+        d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
+        d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
+        d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
+        d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+    }
+}
+// ---- raw-word back end (the regroup of decode_profile_to_raw, OLD:1022-1039): 26 stream symbols at S + 26u -> six pixel
+// values -> three Word27 (27 bytes, T[26] = 0) at U + pad + 27u
+template <int K>
+__device__ __forceinline__ void dec_phase_a_words(const uint8_t* S, uint8_t* U, uint32_t pad, int lane)
+{
+    using L = Cfg3<K>;
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_A; ++pass) {
+        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+        if (u >= L::UNITS) continue;
+        const uint32_t a = 26u * (uint32_t)u;
+        const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+        const uint32_t sh = (a & 2u) * 8u;
+        uint32_t x[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) x[j] = mw[j];
+        uint32_t y[7];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+        y[6] = x[6] >> sh;
+        uint32_t A[6];
+        symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+        symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+        uint8_t* d = U + pad + 27 * u;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) { // pack_two_pixels on values: s0..s3 | trit 12 + 3 (Ab % 9) | digits of Ab / 9
+            uint32_t t, q;
+            const uint32_t lo4 = digits4(A[2 * w], t);
+            const uint32_t h = __umulhi(A[2 * w + 1], 477218589u), s4 = t + 3u * (A[2 * w + 1] - 9u * h);
+            const uint32_t hi4 = digits4(h, q);
+            uint8_t* o = d + 9 * w; // arbitrary alignment: bytes
+            o[0] = (uint8_t)lo4; o[1] = (uint8_t)(lo4 >> 8); o[2] = (uint8_t)(lo4 >> 16); o[3] = (uint8_t)(lo4 >> 24); o[4] = (uint8_t)s4;
+            o[5] = (uint8_t)hi4; o[6] = (uint8_t)(hi4 >> 8); o[7] = (uint8_t)(hi4 >> 16); o[8] = (uint8_t)(hi4 >> 24);
+        }
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
 {
@@ -1060,9 +1155,11 @@ __device__ __forceinline__ void warp_range_smsp(uint64_t total, uint32_t cta, ui
     hi = (uint32_t)(q_lo + (q_hi - q_lo) * (j + 1) / nq);
 }
 
-template <int K> struct Cfg4 {
+// WORDS: the pixel side of the tile is raw Word27 words (9 bytes per two pixels) instead of RGB8
+template <int K, bool WORDS = false> struct Cfg4 {
     using L = Cfg3<K>;
-    static constexpr int IN_BYTES = (L::RGB_BYTES + 15 + 15) / 16 * 16;     // an RGB tile with its alignment slack
+    static constexpr int PIX_BYTES = WORDS ? 9 * (L::PX / 2) : L::RGB_BYTES; // pixel-side bytes of one mini-tile
+    static constexpr int IN_BYTES = (PIX_BYTES + 15 + 15) / 16 * 16 + (WORDS ? 16 : 0); // with alignment slack (+ the word front end reads 32 bytes per unit)
     static constexpr int RUNS_BYTES = 9 * L::RUN_PITCH;
     static constexpr int TAIL_BYTES = L::META_BYTES + L::CARRY_BYTES + 16;   // meta | carry | mbarrier
     static constexpr int WARP_BYTES = IN_BYTES + L::S_BYTES + RUNS_BYTES + TAIL_BYTES; // encode: IN | S | U(runs);  decode: OUT | S | R(runs)
@@ -1073,11 +1170,12 @@ template <int K> struct Cfg4 {
     static constexpr int TOTAL_DEC = 256 + L::DEC_WARP + DEC_WARPS * WARP_BYTES;
 };
 
-template <int K>
-__global__ void __launch_bounds__(32 * Cfg4<K>::ENC_WARPS, 1) k_encode_rgb_v4(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+template <int K, bool WORDS>
+__global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::ENC_WARPS, 1) k_encode_rgb_v4(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
 {
     using L = Cfg3<K>;
-    using L4 = Cfg4<K>;
+    using L4 = Cfg4<K, WORDS>;
+    constexpr int PIX = L4::PIX_BYTES;
     constexpr int V4_ENC_WARPS = L4::ENC_WARPS, TPB = 32 * V4_ENC_WARPS;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1119,8 +1217,8 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::ENC_WARPS, 1) k_encode_rgb_v4(Fa
     // bulk load of tile mt's pixels: the 16-byte aligned superset of [g_lo, g_lo + RGB_BYTES), clipped to the buffer
     auto fetch = [&](uint32_t mt) {
         const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
-        const uint64_t g_lo = P.in_stride * f + 3ull * L::PX * tile, a0 = g_lo & ~15ull;
-        uint32_t bytes = (uint32_t)((g_lo - a0) + L::RGB_BYTES + 15) & ~15u;
+        const uint64_t g_lo = P.in_stride * f + (uint64_t)PIX * tile, a0 = g_lo & ~15ull;
+        uint32_t bytes = (uint32_t)((g_lo - a0) + PIX + 15) & ~15u;
         if (a0 + bytes > in_limit) bytes = (uint32_t)(in_limit - a0) & ~15u;
         fence_async_smem();
         mbar_expect_tx(bar, bytes);
@@ -1131,19 +1229,19 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::ENC_WARPS, 1) k_encode_rgb_v4(Fa
     for (uint32_t mt = mt_lo; mt < mt_hi; ++mt) {
         const uint32_t f = mt / P.n_tiles, tile = P.tile0 + (mt - f * P.n_tiles);
         const bool first = mt == mt_lo || tile == P.tile0, last = mt + 1 == mt_hi || tile + 1 == P.tile0 + P.n_tiles; // of a contiguous stretch
-        const uint64_t g_lo = P.in_stride * f + 3ull * L::PX * tile;
+        const uint64_t g_lo = P.in_stride * f + (uint64_t)PIX * tile;
         const uint32_t pad = (uint32_t)(g_lo & 15);
         setup_runs3(meta, g, P.out_stride * f, tile, lane);
         mbar_wait(bar, phase);
         phase ^= 1;
         {   // the last bytes of the buffer that a clipped bulk copy left out (only the final tile of the final frame)
             const uint64_t a0 = g_lo - pad;
-            const uint32_t want = pad + L::RGB_BYTES;
+            const uint32_t want = pad + PIX;
             if (a0 + ((want + 15) & ~15u) > in_limit)
                 for (uint32_t i = ((uint32_t)(in_limit - a0) & ~15u) + lane; i < want; i += 32) IN[i] = a0 + i < in_limit ? P.in[a0 + i] : 0;
         }
         __syncwarp();
-        enc_phase_a<K>(IN, pad, S, lane);
+        if constexpr (WORDS) enc_phase_a_words<K>(IN, pad, S, lane); else enc_phase_a<K>(IN, pad, S, lane);
         __syncwarp();
         if (mt + 1 < mt_hi && lane == 0) fetch(mt + 1);                      // IN is free again: next tile's pixels on their way
         if (lane < 9) {
@@ -1184,11 +1282,12 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::ENC_WARPS, 1) k_encode_rgb_v4(Fa
     if (lane < 9) bulk_wait_all(); // shared memory must outlive the copies that read it
 }
 
-template <int K>
-__global__ void __launch_bounds__(32 * Cfg4<K>::DEC_WARPS, 1) k_decode_rgb_v4(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+template <int K, bool WORDS>
+__global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::DEC_WARPS, 1) k_decode_rgb_v4(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
 {
     using L = Cfg3<K>;
-    using L4 = Cfg4<K>;
+    using L4 = Cfg4<K, WORDS>;
+    constexpr int PIX = L4::PIX_BYTES;
     constexpr int V4_DEC_WARPS = L4::DEC_WARPS, TPB = 32 * V4_DEC_WARPS;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u); // 256-byte aligned (see Cfg3)
@@ -1291,18 +1390,18 @@ __global__ void __launch_bounds__(32 * Cfg4<K>::DEC_WARPS, 1) k_decode_rgb_v4(Fa
         dec_phase_b<K>(R, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, P.status + 2 * f, lane);
         __syncwarp();
         if (mt + 1 < mt_hi && lane < 9) fetch(mt + 1);                       // R is free again: next tile's runs on their way
-        const uint64_t g_lo = P.out_stride * f + 3ull * L::PX * tile;
+        const uint64_t g_lo = P.out_stride * f + (uint64_t)PIX * tile;
         const uint32_t pad = (uint32_t)(g_lo & 15);
         if (lane == 0) {
             bulk_wait_read();                                                // the previous tile's bulk store has read OUT
             if (!first) *reinterpret_cast<uint4*>(OUT) = carry[0];           // bytes [0, pad): the previous tile's tail
         }
         __syncwarp();
-        dec_phase_a<K>(S, OUT, pad, lane);
+        if constexpr (WORDS) dec_phase_a_words<K>(S, OUT, pad, lane); else dec_phase_a<K>(S, OUT, pad, lane);
         fence_async_smem();
         __syncwarp();
         {   // the RGB tile -> global: whole chunks by one bulk store, edge bytes of a stretch one by one
-            const uint32_t end = pad + L::RGB_BYTES, cend = end >> 4, c0 = (first && pad) ? 1u : 0u;
+            const uint32_t end = pad + PIX, cend = end >> 4, c0 = (first && pad) ? 1u : 0u;
             uint8_t* g0 = P.out + (g_lo - pad);
             if (lane == 0) {
                 if (!last) carry[0] = *reinterpret_cast<const uint4*>(OUT + 16 * cend);
@@ -1344,16 +1443,17 @@ static bool use_v4()
 // tiles [t0, t1) of [0, n_full) of every frame go to the v3 kernels; with `tail` the ragged rest [n_full, n_all) goes to
 // the general-tile kernels
 template <int K>
-int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail)
+int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail, bool words = false)
 {
-    static int occ4 = 0, occ3 = 0, occ2 = 0;
+    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 20) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
-            if (use_v4()) n += launch_persistent(k_encode_rgb_v4<K>, Cfg4<K>::TOTAL_ENC, T, P, g, st, occ4, Cfg4<K>::ENC_WARPS);
+            if (words) n += launch_persistent(k_encode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_ENC, T, P, g, st, occ4w, Cfg4<K, true>::ENC_WARPS);
+            else if (use_v4()) n += launch_persistent(k_encode_rgb_v4<K, false>, Cfg4<K>::TOTAL_ENC, T, P, g, st, occ4, Cfg4<K>::ENC_WARPS);
             else n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3);
         }
     } else n_full = 0;
@@ -1361,16 +1461,17 @@ int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st,
     return n;
 }
 template <int K>
-int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail)
+int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail, bool words = false)
 {
-    static int occ4 = 0, occ3 = 0, occ2 = 0;
+    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 20) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
-            if (use_v4()) n += launch_persistent(k_decode_rgb_v4<K>, Cfg4<K>::TOTAL_DEC, T, P, g, st, occ4, Cfg4<K>::DEC_WARPS);
+            if (words) n += launch_persistent(k_decode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_DEC, T, P, g, st, occ4w, Cfg4<K, true>::DEC_WARPS);
+            else if (use_v4()) n += launch_persistent(k_decode_rgb_v4<K, false>, Cfg4<K>::TOTAL_DEC, T, P, g, st, occ4, Cfg4<K>::DEC_WARPS);
             else n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3);
         }
     } else n_full = 0;
@@ -1471,6 +1572,54 @@ int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
 {
     (void)cfg;
     return launch_decode_rgb_fast_part(T, g, in, stride_words, n_frames, n_px, 3 * n_px, n_px_out, rgb, d_status, st, chk_nz, chk_two, 0, ~0u, true);
+}
+
+// ---- raw-word variants (encode_profile_from_raw / the consistent decoder on Word27 streams): the v4 kernels on the full
+// mini-tiles [0, *n_full) of one super-frame; the caller runs the general kernels on the codewords / words after them.
+// Return -1 when the fast path does not apply (K = 18, unaligned buffers).
+int launch_encode_words_fast(const DevTables& T, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, uint32_t* n_full_out)
+{
+    *n_full_out = 0;
+    if (g.uniform_k < 20 || (((uintptr_t)raw9 | (uintptr_t)out9) & 15)) return -1;
+    const uint32_t n_full = full_tiles(g, 2 * g.n_words);
+    if (!n_full) return 0;
+    FastParams P{};
+    P.in = raw9; P.out = out9;
+    P.in_stride = 9ull * g.n_words; P.out_stride = 9ull * g.n_out;
+    P.n_px = 2 * g.n_words; P.n_frames = 1;
+    P.n_tiles = all_tiles(g);
+    int n = 0;
+    switch (g.uniform_k) {
+    case 24: n = launch_enc<24>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    case 22: n = launch_enc<22>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    case 20: n = launch_enc<20>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    default: return -1;
+    }
+    *n_full_out = n_full;
+    return n;
+}
+int launch_decode_words_fast(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* raw9, size_t n_words_out, uint32_t* d_status,
+                             cudaStream_t st, uint32_t* n_full_out)
+{
+    *n_full_out = 0;
+    if (g.uniform_k < 20 || (((uintptr_t)raw9 | (uintptr_t)in9) & 15)) return -1;
+    const uint32_t n_full = full_tiles(g, 2 * n_words_out);
+    if (!n_full) return 0;
+    FastParams P{};
+    P.in = in9; P.out = raw9;
+    P.in_stride = 9ull * g.n_out; P.out_stride = 9ull * g.n_words;
+    P.n_px = 2 * g.n_words; P.px_out = 2 * n_words_out; P.n_frames = 1;
+    P.status = d_status;
+    P.n_tiles = all_tiles(g);
+    int n = 0;
+    switch (g.uniform_k) {
+    case 24: n = launch_dec<24>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    case 22: n = launch_dec<22>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    case 20: n = launch_dec<20>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    default: return -1;
+    }
+    *n_full_out = n_full;
+    return n;
 }
 
 } // namespace t3c

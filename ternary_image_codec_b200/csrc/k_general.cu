@@ -508,12 +508,12 @@ __global__ void k_header_parse(const GfTables* __restrict__ gf, int fixed, const
 // General profile encoder (A.1-A.6): one CTA = TPB codewords of one band
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restrict__ raw, uint8_t* __restrict__ out, Geom g,
-                                                        const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+                                                        const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, uint64_t cw_start)
 {
     __shared__ uint64_t row[24 * kVals];
     __shared__ uint8_t stage[TPB * 26];
     const int b = blockIdx.y, k = g.k[b], r = 26 - k;
-    const uint64_t c0 = (uint64_t)blockIdx.x * TPB;
+    const uint64_t c0 = cw_start + (uint64_t)blockIdx.x * TPB; // codewords before cw_start of every band were coded by the tiled kernels
     if (c0 >= g.ncw[b]) return;
     const RowTable& tab = rs->row[g.arith][(24 - k) / 2];
     for (int i = threadIdx.x; i < k * kVals; i += TPB) row[i] = tab.e[i / kVals][i % kVals];
@@ -565,13 +565,13 @@ __global__ void k_frame_misc(uint8_t* __restrict__ out_base, size_t stride_bytes
 // General consistent decoder (A.8): thread per codeword -> symbol stream sy' in scratch
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TPB) k_decode_fixed_general(const uint8_t* __restrict__ in, uint8_t* __restrict__ sy, Geom g,
-                                                              const GfTables* __restrict__ gf, uint32_t* status)
+                                                              const GfTables* __restrict__ gf, uint32_t* status, uint64_t cw_start)
 {
     __shared__ GfTables sg;
     load_gf(sg, gf);
     __syncthreads();
     const int b = blockIdx.y, k = g.k[b];
-    const uint64_t c = (uint64_t)blockIdx.x * TPB + threadIdx.x;
+    const uint64_t c = cw_start + (uint64_t)blockIdx.x * TPB + threadIdx.x;
     if (c >= g.ncw[b]) return;
     uint8_t cw[26], orig[26];
     const uint64_t p0 = 26 * (g.cw_base[b] + c);
@@ -592,9 +592,9 @@ __device__ __forceinline__ uint32_t stream_trit(const uint8_t* __restrict__ sy, 
     const uint32_t s = sy[perm2d(j, n_sy, area, w)], c = (uint32_t)(ti - 3 * j);
     return c == 0 ? s % 3 : (c == 1 ? (s / 3) % 3 : (s / 9) % 3);
 }
-__global__ void k_regroup_words(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* __restrict__ out, size_t n_words)
+__global__ void k_regroup_words(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* __restrict__ out, size_t n_words, size_t w_start)
 {
-    const size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t w = w_start + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     for (int s = 0; s < 9; ++s) {
         uint32_t v = 0, mul = 1;
@@ -748,13 +748,14 @@ int launch_header_parse(const DevTables& T, int arith, const uint8_t* words, siz
     k_header_parse<<<1, 64, 0, st>>>(T.gf, arith, words, n_words, d_cfg, d_ok);
     return 1;
 }
-int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw, uint8_t* out, cudaStream_t st)
+int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw, uint8_t* out, cudaStream_t st, uint64_t cw_start)
 {
     int n = 0;
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    if (mx) { k_encode_general<<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs); ++n; }
-    return n + launch_frame_misc(T, cfg, g, out, 1, 0, st);
+    if (mx > cw_start) { k_encode_general<<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cw_start); ++n; }
+    // without a beacon the rest of the frame is the (cached) coded header and the zero padding
+    return n + (use_beacon(cfg) ? launch_frame_misc(T, cfg, g, out, 1, 0, st) : launch_frame_finish(T, cfg, g, out, 1, 0, st));
 }
 const uint8_t* cached_header(const DevTables& T, const t3c_config& cfg, int arith, cudaStream_t st, int& launches)
 {
@@ -790,18 +791,18 @@ int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, 
     k_frame_misc<<<dim3(blocks, (unsigned)n_frames), 256, 0, st>>>(out, stride_bytes, g, cfg, T.gf, T.rs);
     return 1;
 }
-int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint32_t* status, cudaStream_t st)
+int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint32_t* status, cudaStream_t st, uint64_t cw_start)
 {
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    if (!mx) return 0;
-    k_decode_fixed_general<<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status);
+    if (mx <= cw_start) return 0;
+    k_decode_fixed_general<<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cw_start);
     return 1;
 }
-int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* out, size_t n_words, cudaStream_t st)
+int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* out, size_t n_words, cudaStream_t st, size_t w_start)
 {
-    if (!n_words) return 0;
-    k_regroup_words<<<blocks_for(n_words, 256), 256, 0, st>>>(sy, n_sy, area, tw, out, n_words);
+    if (n_words <= w_start) return 0;
+    k_regroup_words<<<blocks_for(n_words - w_start, 256), 256, 0, st>>>(sy, n_sy, area, tw, out, n_words, w_start);
     return 1;
 }
 int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* rgb, size_t n_px, cudaStream_t st)

@@ -38,9 +38,9 @@ int launch_perm2d(const uint8_t* in, uint8_t* out, size_t n, uint32_t w, uint32_
 int launch_header_emit(const DevTables& T, const t3c_config& cfg, int arith, uint8_t* d_hdr27, uint8_t* d_coded52, cudaStream_t st);
 int launch_header_parse(const DevTables& T, int arith, const uint8_t* d_words9, size_t n_words, t3c_config* d_cfg, int* d_ok, cudaStream_t st);
 // general profile codec (any config)
-int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st);
-int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* scratch_sy, uint32_t* d_status, cudaStream_t st);
-int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* out9, size_t n_words, cudaStream_t st);
+int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, uint64_t cw_start = 0);
+int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* scratch_sy, uint32_t* d_status, cudaStream_t st, uint64_t cw_start = 0);
+int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* out9, size_t n_words, cudaStream_t st, size_t w_start = 0);
 int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* rgb, size_t n_px, cudaStream_t st);
 int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uint8_t* in9, uint8_t* use, uint32_t* d_status, cudaStream_t st);
 // fused fast path (uniform k, 1D, no beacon): frames batched
@@ -58,6 +58,10 @@ int launch_encode_rgb_fast_part(const DevTables& T, const t3c_config& cfg, const
 int launch_decode_rgb_fast_part(const DevTables& T, const Geom& g, const uint8_t* in9, size_t stride_words, size_t n_frames, size_t n_px,
                                 size_t out_pitch, size_t n_px_out, uint8_t* rgb, uint32_t* d_status, cudaStream_t st, const uint32_t* chk_nz,
                                 const uint32_t* chk_two, uint32_t t0, uint32_t t1, bool tail);
+// raw-word variants of the tiled kernels for one super-frame: full mini-tiles [0, *n_full) only; -1 = not applicable
+int launch_encode_words_fast(const DevTables& T, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, uint32_t* n_full);
+int launch_decode_words_fast(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* raw9, size_t n_words_out, uint32_t* d_status, cudaStream_t st,
+                             uint32_t* n_full);
 uint32_t fast_full_tiles_encode(const Geom& g, size_t n_px);
 uint32_t fast_full_tiles_decode(const Geom& g, size_t n_px_out, size_t out_pitch, size_t n_frames);
 // both return -1 when the buffers are not 16-byte aligned (caller falls back to the general kernels)

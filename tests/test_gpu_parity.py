@@ -211,7 +211,7 @@ def test_encode_profile(codec, oracle, t3, ci):
     r = rng(1000 + ci)
     for n in (0, 1, 2, 3, 5, 26, 27, 64, 777, 1000, 8192, 30011):
         raw = r.integers(0, 27, size=(n, 9), dtype=np.uint8)
-        if n == 64:
+        if n in (64, 8192):  # out-of-alphabet bytes read as their low three trits (small: general kernels, large: tiled kernels)
             raw = r.integers(0, 256, size=(n, 9), dtype=np.uint8)
         for arith in (t3.REF_EXACT, t3.FIXED):
             got = codec.encode_profile_from_raw(raw, gc, arith)

@@ -25,6 +25,26 @@ def timeit(fn, n=10, warm=3):
     return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))[n // 2]
 
 
+def words8k(uep, name):
+    """the reference's own API on an 8K frame: encode_profile_from_raw / consistent decode on raw Word27 words (device-resident)"""
+    cfg = t3.make_config(profile=t3.P3_RS26_20 if uep == 2 else 1, uep=uep)
+    n_w = N_PX // 2
+    g = torch.Generator(device=dev); g.manual_seed(6)
+    raw = torch.randint(0, 27, (n_w, 9), dtype=torch.uint8, device=dev, generator=g)
+    raw[:, 8] %= 9
+    wpf = t3.profile_words(cfg, n_w)
+    enc = torch.empty(wpf * 9, dtype=torch.uint8, device=dev)
+    back = torch.zeros(n_w * 9, dtype=torch.uint8, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    te = timeit(lambda: codec.encode_profile_dev(raw, n_w, enc, wpf, cfg, t3.FIXED, S))
+    td = timeit(lambda: codec.decode_profile_fixed_dev(enc, wpf, n_w, back, n_w, status, cfg, S))
+    torch.cuda.synchronize()
+    alg = 9 * n_w + 9 * wpf
+    n_ok = (n_w - 300) * 9
+    print(json.dumps({"workload": name, "encode_us": te * 1e3, "decode_us": td * 1e3, "encode_gbs": alg / te / 1e6, "decode_gbs": alg / td / 1e6,
+                      "roundtrip": bool(torch.equal(back[:n_ok], raw.view(-1)[:n_ok])), "status": status.tolist(), "algorithmic_bytes": alg}))
+
+
 def raw8k():  # see also tools/quick_raw.py (back-to-back launches between two events)
     g = torch.Generator(device=dev); g.manual_seed(4)
     NB = 3
@@ -98,6 +118,8 @@ def stream240(frames_per_call=8):
 
 
 if __name__ == "__main__":
+    words8k(2, "words8k_k20: encode_profile_from_raw + consistent decode on 16.6 M raw words, RS(26,20) 1D")
+    words8k(1, "words8k_default: the reference's default EncoderContext (P2, uniform k=22), raw words in/out")
     which = sys.argv[1:] or ["raw8k", "uep2d", "stream240"]
     for w in which:
         {"raw8k": raw8k, "uep2d": uep2d, "stream240": stream240}[w]()
