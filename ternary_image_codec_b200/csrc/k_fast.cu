@@ -554,9 +554,9 @@ template <int K> struct Cfg3 {
     static constexpr int META_BYTES = 96;               // run_lo[9] (u64) | vb[9] (u8)
     static constexpr int CARRY_BYTES = 9 * 16;          // the partial last 16-byte chunk of every output stream, kept for the next tile
     static constexpr int WARP_BYTES = S_BYTES + U_BYTES + META_BYTES + CARRY_BYTES;
-    // encode, CTA-shared: A[3][K][27] | B[K][27] | pat[3][2]
+    // encode, CTA-shared: per variant {A[K][27] | B[K][27]} | pat[3][2]  (B is the same in every variant: one address register serves both planes)
     static_assert(RUN_PITCH == 16 * 23, "chunk slots per run");
-    static constexpr int ENC_A = 0, ENC_B = ENC_A + 4 * 3 * K * 27, ENC_PAT = ENC_B + 4 * K * 27, ENC_MAP = (ENC_PAT + 24 + 15) / 16 * 16, ENC_WARP = ENC_MAP + 3 * 128;
+    static constexpr int ENC_A = 0, ENC_PLANE = 4 * K * 27, ENC_VAR = 2 * ENC_PLANE, ENC_PAT = ENC_A + 3 * ENC_VAR, ENC_MAP = (ENC_PAT + 24 + 15) / 16 * 16, ENC_WARP = ENC_MAP + 3 * 128;
     static constexpr int TOTAL_ENC = ENC_WARP + FAST_WARPS * WARP_BYTES;
     // decode, CTA-shared (offsets from a 256-byte aligned base): per variant {A[26][32], B[26][32]} | chk[3][2] | GF(27) tables
     // of the slow path.  A variant block is 26*256 bytes, so the low byte of a row's address is zero and PRMT can drop a
@@ -653,8 +653,8 @@ __device__ __forceinline__ void warp_range(uint64_t total, uint32_t gw, uint32_t
 }
 
 // ---- encode phase A: six pixels (18 bytes at IN + pad + 18u) -> 26 stream symbols (x4) at S + 26u
-template <int K>
-__device__ __forceinline__ void enc_phase_a(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
+template <int K, bool ODD>
+__device__ __forceinline__ void enc_phase_a_impl(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
 {
     using L = Cfg3<K>;
     // ---- phase A: six pixels (18 bytes) -> 26 stream symbols (x4) per lane; units dealt even / odd so that the
@@ -672,7 +672,8 @@ __device__ __forceinline__ void enc_phase_a(const uint8_t* U, uint32_t pad, uint
         uint32_t y[5]; // the 18 bytes, word aligned
 #pragma unroll
         for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-        y[4] = __funnelshift_r(x[4], sh == 24 ? mw[5] : 0u, sh); // 18 bytes from byte offset 3 reach into a sixth word (odd frame offsets)
+        if constexpr (ODD) y[4] = __funnelshift_r(x[4], sh == 24 ? mw[5] : 0u, sh); // 18 bytes from byte offset 3 reach into a sixth word
+        else y[4] = x[4] >> sh;
         uint32_t A[6];
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
@@ -690,10 +691,16 @@ __device__ __forceinline__ void enc_phase_a(const uint8_t* U, uint32_t pad, uint
         d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
     }
 }
+// frames that start on an odd byte (odd pixel counts, several frames per call) put pixel units at byte offset 3 of a word
+template <int K>
+__device__ __forceinline__ void enc_phase_a(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
+{
+    if (pad & 1u) enc_phase_a_impl<K, true>(U, pad, S, lane); else enc_phase_a_impl<K, false>(U, pad, S, lane);
+}
 // ---- encode phase B: stream symbols -> nine staged runs (data scrambled through the table bytes, parity through the planes)
 template <int K>
 __device__ __forceinline__ void enc_phase_b(const uint8_t* S, uint8_t* U, const WarpMeta3& meta, const uint8_t* pmap, uint32_t tabA32,
-                                            const uint8_t* tabB, const uint32_t* pat, int lane)
+                                            const uint32_t* pat, int lane)
 {
     using L = Cfg3<K>;
     // ---- phase B: one codeword per lane (lane -> codeword through the variant-sorted pass map)
@@ -703,7 +710,7 @@ __device__ __forceinline__ void enc_phase_b(const uint8_t* S, uint8_t* U, const 
         if (cw == 255) continue;
         const uint32_t cl = (cw * 57u) >> 9, b = cw - 9u * cl;          // cw / 9 for cw < 128
         const uint32_t v = ((uint32_t)meta.vb[b] + cl) % 3u;
-        uint32_t pa = tabA32 + v * (K * 108);
+        uint32_t pa = tabA32 + v * L::ENC_VAR;
         asm volatile("" : "+r"(pa));                                   // keep the variant base in a register
         const uint8_t* src = S + cw + (9 * K - 9) * cl;                 // 9K*cl + b
         uint8_t* dst = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
@@ -712,8 +719,8 @@ __device__ __forceinline__ void enc_phase_b(const uint8_t* S, uint8_t* U, const 
         static_for<0, K>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             const uint32_t d4 = src[9 * i];
-            const uint32_t ea = lds_tab<108 * i>(pa + d4);
-            const uint32_t eb = *reinterpret_cast<const uint32_t*>(tabB + d4 + 108 * i);
+            const uint32_t ra = pa + d4;
+            const uint32_t ea = lds_tab<108 * i>(ra), eb = lds_tab<108 * i + L::ENC_PLANE>(ra);
             if (i & 1) { gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
             else { gf3_add(acc, ea, eb); prev = ea; }
         });
@@ -926,13 +933,12 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
     uint8_t* U = S + L::S_BYTES;                                // RGB run, later the nine body runs
     WarpMeta3& meta = *reinterpret_cast<WarpMeta3*>(U + L::U_BYTES);
     {
-        uint32_t* A = reinterpret_cast<uint32_t*>(smem + L::ENC_A);
-        uint32_t* B = reinterpret_cast<uint32_t*>(smem + L::ENC_B);
         const uint32_t(*pl)[kVals][2] = rs->pl[g.arith][(24 - K) / 2];
         for (int idx = tid; idx < 3 * K * 27; idx += FAST_TPB) {
             const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
-            A[idx] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
-            if (v == 0) B[rem] = pl[i][d][1];
+            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + L::ENC_A + v * L::ENC_VAR);
+            blk[rem] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
+            blk[K * 27 + rem] = pl[i][d][1];
         }
         if (tid < 3) { // the scrambler as seen by the parity symbols of a variant-tid codeword, in the plane domain
             uint32_t nz = 0, two = 0;
@@ -948,7 +954,6 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
     }
     __syncthreads(); // the only block-level barrier: tables staged
     const uint32_t tabA32 = smem_u32(smem + L::ENC_A);
-    const uint8_t* tabB = smem + L::ENC_B;
     const uint32_t* pat = reinterpret_cast<const uint32_t*>(smem + L::ENC_PAT);
     uint4* carry = reinterpret_cast<uint4*>(U + L::U_BYTES + L::META_BYTES);
     uint32_t mt_lo, mt_hi;
@@ -966,7 +971,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
         __syncwarp();
         if (!first && lane < 9) *reinterpret_cast<uint4*>(U + L::RUN_PITCH * lane) = carry[lane]; // bytes [0, pad) of each run: the previous tile's tail
         __syncwarp();
-        enc_phase_b<K>(S, U, meta, smem + L::ENC_MAP + 128 * (tile % 3u), tabA32, tabB, pat, lane);
+        enc_phase_b<K>(S, U, meta, smem + L::ENC_MAP + 128 * (tile % 3u), tabA32, pat, lane);
         __syncwarp();
         if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0 and 1 may still see the scrambler's transient (A.4)
             uint8_t* dst = U + ((uint32_t)meta.run_lo[0] & 15u);
@@ -1186,13 +1191,12 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::ENC_WARPS, 1) k_encode_rg
     uint4* carry = reinterpret_cast<uint4*>(U + L4::RUNS_BYTES + L::META_BYTES);
     const uint32_t bar = smem_u32(U + L4::RUNS_BYTES + L::META_BYTES + L::CARRY_BYTES);
     {
-        uint32_t* A = reinterpret_cast<uint32_t*>(smem + L::ENC_A);
-        uint32_t* B = reinterpret_cast<uint32_t*>(smem + L::ENC_B);
         const uint32_t(*pl)[kVals][2] = rs->pl[g.arith][(24 - K) / 2];
         for (int idx = tid; idx < 3 * K * 27; idx += TPB) {
             const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
-            A[idx] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
-            if (v == 0) B[rem] = pl[i][d][1];
+            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + L::ENC_A + v * L::ENC_VAR);
+            blk[rem] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
+            blk[K * 27 + rem] = pl[i][d][1];
         }
         if (tid < 3) {
             uint32_t nz = 0, two = 0;
@@ -1209,7 +1213,6 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::ENC_WARPS, 1) k_encode_rg
     }
     __syncthreads(); // the only block-level barrier: tables and barriers ready
     const uint32_t tabA32 = smem_u32(smem + L::ENC_A);
-    const uint8_t* tabB = smem + L::ENC_B;
     const uint32_t* pat = reinterpret_cast<const uint32_t*>(smem + L::ENC_PAT);
     const uint64_t in_limit = P.in_stride * P.n_frames;
     uint32_t mt_lo, mt_hi;
@@ -1249,7 +1252,7 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::ENC_WARPS, 1) k_encode_rg
             if (!first) *reinterpret_cast<uint4*>(U + L::RUN_PITCH * lane) = carry[lane]; // bytes [0, pad) of each run: the previous tile's tail
         }
         __syncwarp();
-        enc_phase_b<K>(S, U, meta, smem + L::ENC_MAP + 128 * (tile % 3u), tabA32, tabB, pat, lane);
+        enc_phase_b<K>(S, U, meta, smem + L::ENC_MAP + 128 * (tile % 3u), tabA32, pat, lane);
         __syncwarp();
         if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0 and 1 may still see the scrambler's transient (A.4)
             uint8_t* dst = U + ((uint32_t)meta.run_lo[0] & 15u);
