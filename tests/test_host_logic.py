@@ -1,0 +1,126 @@
+"""CPU checks of the arithmetic identities the CUDA kernels rely on (constants are parsed from the sources, so a
+changed constant is re-verified): the three-LOP3 trit adder, the single-multiply quantisers of the bridge, the
+magic divisions, the PRMT plane->symbol table and the pass map / tile-range helpers restated in Python."""
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KFAST = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "k_fast.cu")).read()
+DEV = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "dev.cuh")).read()
+KGEN = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "k_general.cu")).read()
+
+
+def lop3(a, b, c, imm):
+    r = 0
+    for bit in range(8):
+        if (imm >> bit) & 1:
+            x, y, z = (bit >> 2) & 1, (bit >> 1) & 1, bit & 1
+            r |= (a if x else ~a) & (b if y else ~b) & (c if z else ~c)
+    return r & 1
+
+
+def test_gf3_add_is_three_lop3():
+    """dev.cuh gf3_add: planes (nz, two) with 0->00, 1->10, 2->11; t = lop3<0x92>(a.nz, a.two, b.two),
+    nz' = lop3<0xE6>(t, a.nz, b.nz), two' = lop3<0x24>(t, a.two, b.nz)"""
+    imms = [int(x, 16) for x in re.findall(r"lop3<(0x[0-9A-Fa-f]+)>", DEV)][:3]
+    assert imms == [0x92, 0xE6, 0x24]
+    enc = {0: (0, 0), 1: (1, 0), 2: (1, 1)}
+    for a in range(3):
+        for b in range(3):
+            anz, atwo = enc[a]
+            bnz, btwo = enc[b]
+            t = lop3(anz, atwo, btwo, imms[0])
+            assert (lop3(t, anz, bnz, imms[1]), lop3(t, atwo, bnz, imms[2])) == enc[(a + b) % 3], (a, b)
+
+
+def _const(name, text=KFAST):
+    m = re.search(name + r"\s*=\s*(\d+)u", text)
+    assert m, name
+    return int(m.group(1))
+
+
+def test_bridge_quantisers_single_multiply():
+    """rgb_to_value3: hi32((0x4B000000 + Z + v) * M) - C0 equals quantize_ycbcr's integer form for every 8-bit input"""
+    K = 0x4B000000
+    M, Z, C0 = _const("QY_M"), _const("QY_Z"), _const("QY_C0")
+    for y in range(256):
+        assert (((K + Z + y) * M) >> 32) - C0 == (484 * y + 255) // 510
+    M, Z, C0 = _const("QC_M"), _const("QC_Z"), _const("QC_C0")
+    for c in range(257):  # 256 = round(255.5), quantises like 255
+        assert (((K + Z + c) * M) >> 32) - C0 == (5 * c + 7 + (1 if c >= 128 else 0)) >> 4
+    assert (5 * 256 + 8) >> 4 == (5 * 255 + 8) >> 4
+
+
+def test_magic_divisions():
+    for d, m, hi in ((243, 17674763, 3 ** 13), (81, 53024288, 6561 + 81), (27, 159072863, 1 << 17), (9, 477218589, 1 << 17), (3, 1431655766, 1 << 17)):
+        assert str(m) in KFAST or str(m) in KGEN
+        x = np.arange(hi, dtype=np.uint64)
+        assert np.array_equal((x * np.uint64(m)) >> np.uint64(32), x // np.uint64(d)), d
+    # dequantisers of value_to_rgb3
+    for q in range(243):
+        assert (((q * 510 + 241) * 8873899) >> 32) == (q * 510 + 241) // 484 <= 255
+    for u in range(81):
+        assert min(((32 * u + 5) * 429496730) >> 32, 255) == min((2570 + 64 * (u - 40)) // 20, 255)
+    # digits4: x + 229 q1 + 58624 q2 + 15007744 q3 - 452984832 q4 packs four base-27 digits into bytes
+    for x in list(range(0, 3 ** 13, 977)) + [3 ** 13 - 1, 3 ** 13 + 2 * 3 ** 13]:
+        q1, q2, q3, q4 = x // 27, x // 729, x // 19683, x // 531441
+        w = (x + 229 * q1 + 58624 * q2 + 15007744 * q3 - 452984832 * q4) & 0xFFFFFFFF
+        assert [(w >> (8 * i)) & 0xFF for i in range(4)] == [x % 27, q1 % 27, q2 % 27, q3 % 27]
+
+
+def test_prmt_plane_table():
+    """planes4_to_sym: the 8-entry byte table {LUT0, LUT1} maps 3 plane bits b0 b1 b2 to b0 + 3 b1 + 9 b2"""
+    m = re.search(r"__byte_perm\((0x[0-9A-Fa-f]+)u, (0x[0-9A-Fa-f]+)u, sel\)", KFAST)
+    lut = int(m.group(1), 16) | (int(m.group(2), 16) << 32)
+    for n in range(8):
+        assert (lut >> (8 * n)) & 0xFF == (n & 1) + 3 * ((n >> 1) & 1) + 9 * ((n >> 2) & 1)
+
+
+def pass_map(cw_base, tm):
+    """Python restatement of build_pass_map"""
+    cwb = [c % 3 for c in cw_base]
+    nb = [cwb.count(x) for x in range(3)]
+    out = [255] * 128
+    for cw in range(117):
+        cl, b = divmod(cw, 9)
+        v = (cwb[b] + tm + cl) % 3
+        row = lambda vv, r: nb[(vv - tm - r) % 3]
+        rank = sum(row(v, r) for r in range(cl)) + sum((cwb[bb] + tm + cl) % 3 == v for bb in range(b))
+        if rank < 32:
+            out[32 * v + rank] = cw
+        else:
+            off = 96 + sum(sum(row(vv, r) for r in range(13)) - 32 for vv in range(v))
+            out[off + rank - 32] = cw
+    return out
+
+
+def test_pass_map_is_a_variant_sorted_permutation():
+    rnd = np.random.default_rng(5)
+    for trial in range(200):
+        cw_base = [int(x) for x in rnd.integers(0, 10 ** 7, 9)] if trial else [798720 * b for b in range(9)]
+        for tm in range(3):
+            m = pass_map(cw_base, tm)
+            assert sorted(x for x in m if x != 255) == list(range(117)) and m[117:] == [255] * 11
+            for p in range(3):  # passes 0..2: one variant each
+                vs = {(cw_base[c % 9] + tm + c // 9) % 3 for c in m[32 * p:32 * p + 32]}
+                assert vs == {p}
+
+
+def test_smsp_balanced_ranges_cover_everything_once():
+    """warp_range_smsp: CTA -> sub-partition -> warp shares are disjoint, contiguous and complete"""
+    def rng_(total, cta, n_cta, warp, n_warps):
+        c_lo, c_hi = total * cta // n_cta, total * (cta + 1) // n_cta
+        q, j = warp & 3, warp >> 2
+        nq = (n_warps - q + 3) >> 2
+        q_lo, q_hi = c_lo + (c_hi - c_lo) * q // 4, c_lo + (c_hi - c_lo) * (q + 1) // 4
+        return q_lo + (q_hi - q_lo) * j // nq, q_lo + (q_hi - q_lo) * (j + 1) // nq
+    for total, n_cta, n_warps in ((61440, 148, 28), (61440, 148, 27), (5, 148, 28), (1000, 3, 25), (0, 148, 28)):
+        seen = []
+        for cta in range(n_cta):
+            for q in range(4):
+                for w in range(q, n_warps, 4):
+                    lo, hi = rng_(total, cta, n_cta, w, n_warps)
+                    seen.extend(range(lo, hi))
+        assert sorted(seen) == list(range(total))
