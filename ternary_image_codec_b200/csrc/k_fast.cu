@@ -13,7 +13,10 @@
 // transpose and all table look-ups stay in shared memory, the grid is persistent (SM count x resident CTAs)
 // so the row table is staged once per CTA, and HBM traffic is exactly the algorithmic 3 B/px + 9 B/word.
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <type_traits>
+#include <utility>
 
 #include "dev.cuh"
 #include "launch.h"
@@ -1419,15 +1422,28 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::DEC_WARPS, 1) k_decode_rg
     if (lane == 0) bulk_wait_all();
 }
 
+// occupancy (and the opt-in to > 48 KB of dynamic shared memory) per kernel AND per device: a process may drive several GPUs
+static int persistent_ctas_per_sm(const void* kern, int tpb, int smem_bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({kern, dev});
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, tpb, smem_bytes);
+    if (n < 1) n = 1;
+    cache[{kern, dev}] = n;
+    return n;
+}
 template <class Kern>
 int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st, int& ctas_per_sm,
                       int warps = FAST_WARPS)
 {
-    if (!ctas_per_sm) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 32 * warps, smem_bytes);
-        if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
+    ctas_per_sm = persistent_ctas_per_sm(reinterpret_cast<const void*>(kern), 32 * warps, smem_bytes);
     const uint64_t total = (uint64_t)P.n_tiles * P.n_frames;
     uint64_t grid = (uint64_t)T.sm_count * ctas_per_sm;
     const uint64_t need = (total + warps - 1) / warps;

@@ -669,16 +669,19 @@ int launch_quant_to_rgb(const t3c_pixel* px, size_t n, uint8_t* rgb, cudaStream_
 }
 static int raw2_grid(uint32_t n_tiles)
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int sms[64] = {}; // per device: SM count, and the opt-in to > 48 KB of dynamic shared memory
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         cudaFuncSetAttribute(raw2::k_pack_pixels_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, raw2::SMEM);
         cudaFuncSetAttribute(raw2::k_unpack_pixels_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, raw2::SMEM);
+        sms[dev] = n;
     }
     const uint32_t need = (n_tiles + raw2::WARPS - 1) / raw2::WARPS;
-    return (int)(need < (uint32_t)sms ? need : (uint32_t)sms);
+    return (int)(need < (uint32_t)sms[dev] ? need : (uint32_t)sms[dev]);
 }
 int launch_pack_pixels(const t3c_pixel* px, size_t n, uint8_t* words, cudaStream_t st)
 {

@@ -559,3 +559,22 @@ def test_fused_multi_frame_odd_sizes(codec, oracle, t3, kw, n_px, nf):
     for f in range(nf):
         ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, enc[f], n_px)
         assert ok_o and np.array_equal(rgb[f], rgb_o)
+
+
+def test_two_devices_in_one_process(oracle, t3):
+    """one context per GPU inside one process (t3c_shim::context(device) in the C++ headers): kernel attributes are per device"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    oc, gc = both(dict(profile=T.P3, uep=2))
+    n_px = 540 * 300 + 7
+    rgb = T.synth_rgb(77, n_px)
+    want = oracle.encode_rgb(oc, rgb, 1)
+    px = T.synth_quant(3, 40000)
+    for dev in (1, 0, 1):
+        c = t3.Codec(dev)
+        assert np.array_equal(c.encode_frames_rgb8(rgb[None], gc, t3.FIXED)[0], want)
+        ok, back, _ = c.decode_frames_rgb8(want[None], n_px, gc)
+        assert ok.all() and np.array_equal(back[0], oracle.decode_rgb_fixed(oc, want, n_px)[1])
+        assert np.array_equal(c.encode_raw_pixels_to_words(px), oracle.pack_pixels(px))
+        c.close()
