@@ -301,17 +301,18 @@ t3c_status t3c_decode_profile_fixed_dev(t3c_ctx* ctx, const t3c_config* cfg, siz
     if (nw > n_raw_words) nw = n_raw_words;
     if (cap_words < nw) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile_fixed: capacity");
     uint8_t* sy = nullptr;
-    TRY(reserve_t(ctx, B_TMP, g.n_s + 16, &sy));
+    const uint64_t pitch = (g.n_s + 8) / 9; // band-major scratch: band b's decoded symbols at b*pitch
+    TRY(reserve_t(ctx, B_TMP, 9 * pitch + 16, &sy));
     int n = launch_init_status(d_status, 1, s);
     uint32_t n_full = 0;
     if (fast_path_ok(*cfg)) { // tiled kernels: profile words -> raw words for the full mini-tiles
         const int k = launch_decode_words_fast(ctx->tabs, g, d_in, d_out, (size_t)nw, d_status, s, &n_full);
         if (k < 0) n_full = 0; else n += k;
     }
-    const size_t sy_done = (size_t)n_full * 117 * (size_t)g.uniform_k; // stream symbols of the tiles already turned into words
-    CU(cudaMemsetAsync(sy + sy_done, 0, g.n_s + 16 - sy_done, s));
-    n += launch_decode_fixed_general(ctx->tabs, g, d_in, sy, d_status, s, 13ull * n_full);
-    n += launch_regroup_words(sy, g.n_s, g.tile_area, g.tile_w, d_out, (size_t)nw, s, (size_t)n_full * (27 * (size_t)g.uniform_k / 2));
+    const uint64_t m_done = 13ull * n_full * (uint64_t)g.uniform_k; // symbols per band already turned into words by the tiled kernels
+    for (int b = 0; b < 9; ++b) if (pitch > m_done) CU(cudaMemsetAsync(sy + b * pitch + m_done, 0, pitch - m_done, s));
+    n += launch_decode_fixed_general(ctx->tabs, g, d_in, sy, pitch, d_status, s, 13ull * n_full);
+    n += launch_regroup_words(sy, g.n_s, g.tile_area, g.tile_w, d_out, (size_t)nw, s, (size_t)n_full * (27 * (size_t)g.uniform_k / 2), pitch);
     return check_launch(ctx, n);
 }
 
@@ -367,11 +368,12 @@ t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, const
         if (n >= 0) return check_launch(ctx, n);
     }
     uint8_t* sy = nullptr;
-    TRY(reserve_t(ctx, B_TMP, g.n_s + 16, &sy));
+    const uint64_t pitch = (g.n_s + 8) / 9;
+    TRY(reserve_t(ctx, B_TMP, 9 * pitch + 16, &sy));
     for (size_t f = 0; f < n_frames; ++f) {
-        CU(cudaMemsetAsync(sy, 0, g.n_s + 16, s));
-        int n = launch_decode_fixed_general(ctx->tabs, g, d_in + 9 * stride_words * f, sy, d_status + 2 * f, s);
-        n += launch_regroup_rgb(sy, g.n_s, g.tile_area, g.tile_w, d_rgb + 3 * n_px * f, px_out, s);
+        CU(cudaMemsetAsync(sy, 0, 9 * pitch + 16, s));
+        int n = launch_decode_fixed_general(ctx->tabs, g, d_in + 9 * stride_words * f, sy, pitch, d_status + 2 * f, s);
+        n += launch_regroup_rgb(sy, g.n_s, g.tile_area, g.tile_w, d_rgb + 3 * n_px * f, px_out, s, pitch);
         TRY(check_launch(ctx, n));
     }
     return T3C_OK;

@@ -391,11 +391,15 @@ __global__ void __launch_bounds__(TPB) k_rs_decode_blocks(const GfTables* __rest
     ok[blk] = good ? 1 : 0;
 }
 
-__global__ void k_perm2d(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, uint64_t area, uint32_t w)
+template <typename I>
+__global__ void k_perm2d(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, I n, I area, uint32_t w)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[perm2d(i, n, area, w)];
+    const I i = (I)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm2d<I>(i, n, area, w)];
 }
+
+// 32-bit index arithmetic is enough when every symbol / trit / byte index of the super-frame stays below 2^31
+static inline bool small_geom(const Geom& g) { return 27 * g.n_words + 64 < (1ull << 31) && 9 * g.n_out + 64 < (1ull << 31) && g.l_exp + 64 < (1ull << 31); }
 
 // ------------------------------------------------------------------------------------------
 // K5: super-frame header (OLD:155-380, 1142-1158) -- one warp
@@ -507,26 +511,27 @@ __global__ void k_header_parse(const GfTables* __restrict__ gf, int fixed, const
 // ------------------------------------------------------------------------------------------
 // General profile encoder (A.1-A.6): one CTA = TPB codewords of one band
 // ------------------------------------------------------------------------------------------
+template <typename I>
 __global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restrict__ raw, uint8_t* __restrict__ out, Geom g,
                                                         const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, uint64_t cw_start)
 {
     __shared__ uint64_t row[24 * kVals];
     __shared__ uint8_t stage[TPB * 26];
     const int b = blockIdx.y, k = g.k[b], r = 26 - k;
-    const uint64_t c0 = cw_start + (uint64_t)blockIdx.x * TPB; // codewords before cw_start of every band were coded by the tiled kernels
-    if (c0 >= g.ncw[b]) return;
+    const I c0 = (I)cw_start + (I)blockIdx.x * TPB; // codewords before cw_start of every band were coded by the tiled kernels
+    if (c0 >= (I)g.ncw[b]) return;
     const RowTable& tab = rs->row[g.arith][(24 - k) / 2];
     for (int i = threadIdx.x; i < k * kVals; i += TPB) row[i] = tab.e[i / kVals][i % kVals];
     __syncthreads();
-    const uint64_t c = c0 + threadIdx.x;
-    const uint32_t ncta = (uint32_t)((g.ncw[b] - c0) < TPB ? (g.ncw[b] - c0) : TPB);
+    const I c = c0 + threadIdx.x;
+    const uint32_t ncta = (uint32_t)(((I)g.ncw[b] - c0) < TPB ? ((I)g.ncw[b] - c0) : TPB);
     if (threadIdx.x < ncta) {
         Planes acc{0, 0};
         uint8_t* my = stage + 26 * threadIdx.x;
         for (int i = 0; i < k; ++i) {
-            const uint64_t is = 9 * ((uint64_t)k * c + i) + b;                   // band split, A.3
-            const uint64_t j = perm2d(is, g.n_s, g.tile_area, g.tile_w);        // 2D interleave, A.2
-            const uint32_t d = raw_symbol(raw, g.n_words, j);                    // regroup, A.1
+            const I is = 9 * ((I)k * c + i) + b;                                 // band split, A.3
+            const I j = perm2d<I>(is, (I)g.n_s, (I)g.tile_area, g.tile_w);       // 2D interleave, A.2
+            const uint32_t d = raw_symbol<I>(raw, (I)g.n_words, j);              // regroup, A.1
             my[i] = (uint8_t)d;
             gf3_add(acc, row[i * kVals + d]);
         }
@@ -534,10 +539,11 @@ __global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restric
         for (int j = 0; j < r; ++j) my[k + j] = (uint8_t)((j < 4 ? lo >> (8 * j) : hi >> (8 * (j - 4))) & 0xFF);
     }
     __syncthreads();
-    const uint64_t p0 = 26 * (g.cw_base[b] + c0);
+    // scramble (A.4) and beacon-aware scatter (A.5): one division per thread, then the expanded index advances with the body index
+    const I p0 = 26 * ((I)g.cw_base[b] + c0);
     for (uint32_t idx = threadIdx.x; idx < 26 * ncta; idx += TPB) {
-        const uint64_t p = p0 + idx;
-        out[52 + beacon_expand(g, p)] = gf->scr[scr_state(g, p)][stage[idx]];   // scramble A.4, beacon A.5
+        const I p = p0 + idx;
+        out[52 + beacon_expand<I>(g, p)] = gf->scr[scr_state<I>(g, p)][stage[idx]];
     }
 }
 // header, beacon symbols and zero padding of one super-frame
@@ -564,53 +570,59 @@ __global__ void k_frame_misc(uint8_t* __restrict__ out_base, size_t stride_bytes
 // ------------------------------------------------------------------------------------------
 // General consistent decoder (A.8): thread per codeword -> symbol stream sy' in scratch
 // ------------------------------------------------------------------------------------------
+template <typename I>
 __global__ void __launch_bounds__(TPB) k_decode_fixed_general(const uint8_t* __restrict__ in, uint8_t* __restrict__ sy, Geom g,
-                                                              const GfTables* __restrict__ gf, uint32_t* status, uint64_t cw_start)
+                                                              const GfTables* __restrict__ gf, uint32_t* status, uint64_t cw_start, uint64_t pitch)
 {
     __shared__ GfTables sg;
     load_gf(sg, gf);
     __syncthreads();
     const int b = blockIdx.y, k = g.k[b];
-    const uint64_t c = cw_start + (uint64_t)blockIdx.x * TPB + threadIdx.x;
-    if (c >= g.ncw[b]) return;
+    const I c = (I)cw_start + (I)blockIdx.x * TPB + threadIdx.x;
+    if (c >= (I)g.ncw[b]) return;
     uint8_t cw[26], orig[26];
-    const uint64_t p0 = 26 * (g.cw_base[b] + c);
+    const I p0 = 26 * ((I)g.cw_base[b] + c);
     for (int i = 0; i < 26; ++i) {
-        const uint64_t p = p0 + i;
-        cw[i] = orig[i] = sg.dsc[scr_state(g, p)][in[52 + beacon_expand(g, p)] % 27];
+        const I p = p0 + i;
+        cw[i] = orig[i] = sg.dsc[scr_state<I>(g, p)][in[52 + beacon_expand<I>(g, p)] % 27];
     }
     if (!rs_decode_thread(sg, cw, k, true)) { atomicExch(&status[0], 0u); return; }
     uint32_t nfix = 0;
     for (int i = 0; i < 26; ++i) nfix += cw[i] != orig[i];
     if (nfix) atomicAdd(&status[1], nfix);
-    for (int i = 0; i < k; ++i) sy[9 * ((uint64_t)k * c + i) + b] = cw[i];
+    // scratch is band-major (band b at b*pitch): a thread's k symbols are contiguous, the regroup kernels gather through stream_trit
+    for (int i = 0; i < k; ++i) sy[(I)b * (I)pitch + (I)k * c + i] = cw[i];
 }
 // symbols -> trits -> groups of 26 -> Word27 (OLD:1022-1039), optional de-interleave (involution)
-__device__ __forceinline__ uint32_t stream_trit(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t w, uint64_t ti)
+template <typename I>
+__device__ __forceinline__ uint32_t stream_trit(const uint8_t* __restrict__ sy, I n_sy, I area, uint32_t w, I ti, I pitch)
 {
-    const uint64_t j = ti / 3;
-    const uint32_t s = sy[perm2d(j, n_sy, area, w)], c = (uint32_t)(ti - 3 * j);
+    const I j = ti / 3, jp = perm2d<I>(j, n_sy, area, w);
+    const I q = jp / 9;
+    const uint32_t s = sy[pitch ? (jp - 9 * q) * pitch + q : jp], c = (uint32_t)(ti - 3 * j); // pitch != 0: band-major scratch
     return c == 0 ? s % 3 : (c == 1 ? (s / 3) % 3 : (s / 9) % 3);
 }
-__global__ void k_regroup_words(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* __restrict__ out, size_t n_words, size_t w_start)
+template <typename I>
+__global__ void k_regroup_words(const uint8_t* __restrict__ sy, I n_sy, I area, uint32_t tw, uint8_t* __restrict__ out, I n_words, I w_start, I pitch)
 {
-    const size_t w = w_start + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const I w = w_start + (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_words) return;
     for (int s = 0; s < 9; ++s) {
         uint32_t v = 0, mul = 1;
         for (int c = 0; c < 3; ++c, mul *= 3) {
             const int t = 3 * s + c;
-            if (t < 26) v += mul * stream_trit(sy, n_sy, area, tw, 26 * (uint64_t)w + t);
+            if (t < 26) v += mul * stream_trit<I>(sy, n_sy, area, tw, 26 * w + t, pitch);
         }
         out[9 * w + s] = (uint8_t)v;
     }
 }
-__global__ void k_regroup_rgb(const uint8_t* __restrict__ sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* __restrict__ rgb, size_t n_px)
+template <typename I>
+__global__ void k_regroup_rgb(const uint8_t* __restrict__ sy, I n_sy, I area, uint32_t tw, uint8_t* __restrict__ rgb, I n_px, I pitch)
 {
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const I p = (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_px) return;
     uint32_t t[13];
-    for (int i = 0; i < 13; ++i) t[i] = stream_trit(sy, n_sy, area, tw, 13 * (uint64_t)p + i);
+    for (int i = 0; i < 13; ++i) t[i] = stream_trit<I>(sy, n_sy, area, tw, 13 * p + i, pitch);
     const int Yq = t[0] + 3 * t[1] + 9 * t[2] + 27 * t[3] + 81 * t[4];
     const int Cb = (int)(t[5] + 3 * t[6] + 9 * t[7] + 27 * t[8]) - 40, Cr = (int)(t[9] + 3 * t[10] + 9 * t[11] + 27 * t[12]) - 40;
     int R, G, B;
@@ -738,7 +750,8 @@ int launch_rs_decode_blocks(const DevTables& T, int k, int arith, uint8_t* inout
 int launch_perm2d(const uint8_t* in, uint8_t* out, size_t n, uint32_t w, uint32_t h, cudaStream_t st)
 {
     if (!n) return 0;
-    k_perm2d<<<blocks_for(n, 256), 256, 0, st>>>(in, out, n, (uint64_t)w * h, w);
+    if (n < (1ull << 31)) k_perm2d<uint32_t><<<blocks_for(n, 256), 256, 0, st>>>(in, out, (uint32_t)n, (uint32_t)w * h, w);
+    else k_perm2d<uint64_t><<<blocks_for(n, 256), 256, 0, st>>>(in, out, (uint64_t)n, (uint64_t)w * h, w);
     return 1;
 }
 int launch_header_emit(const DevTables& T, const t3c_config& cfg, int arith, uint8_t* hdr27, uint8_t* coded52, cudaStream_t st)
@@ -756,7 +769,11 @@ int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom&
     int n = 0;
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    if (mx > cw_start) { k_encode_general<<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cw_start); ++n; }
+    if (mx > cw_start) {
+        if (small_geom(g)) k_encode_general<uint32_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cw_start);
+        else k_encode_general<uint64_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cw_start);
+        ++n;
+    }
     // without a beacon the rest of the frame is the (cached) coded header and the zero padding
     return n + (use_beacon(cfg) ? launch_frame_misc(T, cfg, g, out, 1, 0, st) : launch_frame_finish(T, cfg, g, out, 1, 0, st));
 }
@@ -794,24 +811,29 @@ int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, 
     k_frame_misc<<<dim3(blocks, (unsigned)n_frames), 256, 0, st>>>(out, stride_bytes, g, cfg, T.gf, T.rs);
     return 1;
 }
-int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint32_t* status, cudaStream_t st, uint64_t cw_start)
+int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint64_t pitch, uint32_t* status, cudaStream_t st, uint64_t cw_start)
 {
     uint64_t mx = 0;
     for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
     if (mx <= cw_start) return 0;
-    k_decode_fixed_general<<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cw_start);
+    if (small_geom(g)) k_decode_fixed_general<uint32_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cw_start, pitch);
+    else k_decode_fixed_general<uint64_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cw_start, pitch);
     return 1;
 }
-int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* out, size_t n_words, cudaStream_t st, size_t w_start)
+int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* out, size_t n_words, cudaStream_t st, size_t w_start, uint64_t pitch)
 {
     if (n_words <= w_start) return 0;
-    k_regroup_words<<<blocks_for(n_words - w_start, 256), 256, 0, st>>>(sy, n_sy, area, tw, out, n_words, w_start);
+    if (27 * (uint64_t)n_words + 64 < (1ull << 31) && 3 * n_sy + 64 < (1ull << 31))
+        k_regroup_words<uint32_t><<<blocks_for(n_words - w_start, 256), 256, 0, st>>>(sy, (uint32_t)n_sy, (uint32_t)area, tw, out, (uint32_t)n_words, (uint32_t)w_start, (uint32_t)pitch);
+    else k_regroup_words<uint64_t><<<blocks_for(n_words - w_start, 256), 256, 0, st>>>(sy, n_sy, area, tw, out, (uint64_t)n_words, (uint64_t)w_start, pitch);
     return 1;
 }
-int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* rgb, size_t n_px, cudaStream_t st)
+int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* rgb, size_t n_px, cudaStream_t st, uint64_t pitch)
 {
     if (!n_px) return 0;
-    k_regroup_rgb<<<blocks_for(n_px, 256), 256, 0, st>>>(sy, n_sy, area, tw, rgb, n_px);
+    if (13 * (uint64_t)n_px + 64 < (1ull << 31) && 3 * n_sy + 64 < (1ull << 31))
+        k_regroup_rgb<uint32_t><<<blocks_for(n_px, 256), 256, 0, st>>>(sy, (uint32_t)n_sy, (uint32_t)area, tw, rgb, (uint32_t)n_px, (uint32_t)pitch);
+    else k_regroup_rgb<uint64_t><<<blocks_for(n_px, 256), 256, 0, st>>>(sy, n_sy, area, tw, rgb, (uint64_t)n_px, pitch);
     return 1;
 }
 int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uint8_t* in, uint8_t* use, uint32_t* status, cudaStream_t st)

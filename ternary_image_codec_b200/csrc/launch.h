@@ -39,9 +39,13 @@ int launch_header_emit(const DevTables& T, const t3c_config& cfg, int arith, uin
 int launch_header_parse(const DevTables& T, int arith, const uint8_t* d_words9, size_t n_words, t3c_config* d_cfg, int* d_ok, cudaStream_t st);
 // general profile codec (any config)
 int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, uint64_t cw_start = 0);
-int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* scratch_sy, uint32_t* d_status, cudaStream_t st, uint64_t cw_start = 0);
-int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* out9, size_t n_words, cudaStream_t st, size_t w_start = 0);
-int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* rgb, size_t n_px, cudaStream_t st);
+// scratch_sy is band-major: decoded data symbol m of band b at b*pitch + m (pitch >= ceil(n_s / 9))
+int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* scratch_sy, uint64_t pitch, uint32_t* d_status, cudaStream_t st,
+                                uint64_t cw_start = 0);
+// pitch = 0: sy in stream order; pitch != 0: band-major scratch of launch_decode_fixed_general
+int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* out9, size_t n_words, cudaStream_t st, size_t w_start = 0,
+                         uint64_t pitch = 0);
+int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* rgb, size_t n_px, cudaStream_t st, uint64_t pitch = 0);
 int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uint8_t* in9, uint8_t* use, uint32_t* d_status, cudaStream_t st);
 // fused fast path (uniform k, 1D, no beacon): frames batched
 bool fast_path_ok(const t3c_config& cfg);

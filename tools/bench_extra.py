@@ -118,8 +118,9 @@ def stream240(frames_per_call=8):
 
 
 if __name__ == "__main__":
-    words8k(2, "words8k_k20: encode_profile_from_raw + consistent decode on 16.6 M raw words, RS(26,20) 1D")
-    words8k(1, "words8k_default: the reference's default EncoderContext (P2, uniform k=22), raw words in/out")
-    which = sys.argv[1:] or ["raw8k", "uep2d", "stream240"]
+    def words():
+        words8k(2, "words8k_k20: encode_profile_from_raw + consistent decode on 16.6 M raw words, RS(26,20) 1D")
+        words8k(1, "words8k_default: the reference's default EncoderContext (P2, uniform k=22), raw words in/out")
+    which = sys.argv[1:] or ["words8k", "raw8k", "uep2d", "stream240"]
     for w in which:
-        {"raw8k": raw8k, "uep2d": uep2d, "stream240": stream240}[w]()
+        {"words8k": words, "raw8k": raw8k, "uep2d": uep2d, "stream240": stream240}[w]()
