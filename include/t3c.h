@@ -155,6 +155,31 @@ T3C_API t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx*, const t3c_config*, const
 /* which kernel family the fused calls will use for this config: 1 = tiled fast path, 0 = general path */
 T3C_API int t3c_fast_path_available(const t3c_config* cfg);
 
+/* ---- SURVEY 8(f) "next" rows: the data formats either side of the path ------------------------ */
+/* 8(f).2 sub-word streams (OLD:816-859) and base-243 packing (include/ternary_packing.hpp:18-50), N in 1..27.
+ * extract_subword_stream_from_words, OLD:835-845: the first N trits of every word, one trit (0..2) per byte */
+T3C_API t3c_status t3c_subword_stream(t3c_ctx*, const uint8_t* words9, size_t n_words, int N, uint8_t* trits);
+/* build_words_from_subword_stream, OLD:846-859: ceil(n_trits/N) words, trits N..26 of each word = fill */
+T3C_API t3c_status t3c_words_from_subword_stream(t3c_ctx*, const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words9, size_t* n_words);
+/* tpack::ut_to_base243, include/ternary_packing.hpp:29-39: uint32 LE trit count, then 5 trits per byte: 4 + ceil(n/5) bytes */
+T3C_API t3c_status t3c_base243_pack(t3c_ctx*, const uint8_t* trits, size_t n_trits, uint8_t* out, size_t* n_bytes);
+/* tpack::base243_to_ut, include/ternary_packing.hpp:41-50: *ok = the reference's bool; writes min(count, cap) trits */
+T3C_API t3c_status t3c_base243_unpack(t3c_ctx*, const uint8_t* in, size_t n_bytes, uint8_t* trits, size_t cap, size_t* n_trits, int* ok);
+/* fused extract_subword_stream_from_words + ut_to_base243 (what old/include/t3p_io.hpp:19 writes), no 1-byte-per-trit stream */
+T3C_API t3c_status t3c_words_to_base243(t3c_ctx*, const uint8_t* words9, size_t n_words, int N, uint8_t* out, size_t* n_bytes);
+/* 8(f).3 NEW-generation RAW path, src/ternary_image_codec_v6_min.cpp:62-126: one pixel <-> one 32-bit word
+ * Y + 243 (Cb+40 + 81 (Cr+40)) with clamps; subword = 0 or a SubwordMode value (27/24/21/18/15), anything else
+ * makes the reference's *_subword variants return false: T3C_ERR_ARG here */
+T3C_API t3c_status t3c_v6new_pack_pixels(t3c_ctx*, const t3c_pixel* px, size_t n_px, uint32_t* words, int subword);
+T3C_API t3c_status t3c_v6new_unpack_pixels(t3c_ctx*, const uint32_t* words, size_t n_words, t3c_pixel* px, int subword);
+T3C_API t3c_status t3c_subword_stream_dev(t3c_ctx*, const uint8_t* d_words9, size_t n_words, int N, uint8_t* d_trits, void* stream);
+T3C_API t3c_status t3c_words_from_subword_stream_dev(t3c_ctx*, const uint8_t* d_trits, size_t n_trits, int N, uint8_t fill, uint8_t* d_words9, void* stream);
+T3C_API t3c_status t3c_base243_pack_dev(t3c_ctx*, const uint8_t* d_trits, size_t n_trits, uint8_t* d_out, void* stream);
+T3C_API t3c_status t3c_base243_unpack_dev(t3c_ctx*, const uint8_t* d_payload /* after the 4-byte count */, size_t n_trits, uint8_t* d_trits, void* stream);
+T3C_API t3c_status t3c_words_to_base243_dev(t3c_ctx*, const uint8_t* d_words9, size_t n_words, int N, uint8_t* d_out, void* stream);
+T3C_API t3c_status t3c_v6new_pack_pixels_dev(t3c_ctx*, const t3c_pixel* d_px, size_t n_px, uint32_t* d_words, void* stream);
+T3C_API t3c_status t3c_v6new_unpack_pixels_dev(t3c_ctx*, const uint32_t* d_words, size_t n_words, t3c_pixel* d_px, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

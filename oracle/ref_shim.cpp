@@ -227,4 +227,37 @@ size_t t3r_encode_rgb(const t3o_cfg* c, const uint8_t* rgb, size_t n_px, uint8_t
     return out.size();
 }
 
+// ---- sub-word streams (OLD:816-859) and base-243 (include/ternary_packing.hpp:18-50)
+void t3r_subword_stream(const uint8_t* words9, size_t n_words, int N, uint8_t* trits)
+{
+    std::vector<UTrit> out;
+    extract_subword_stream_from_words(to_words(words9, n_words), N, out);
+    if (!out.empty()) std::memcpy(trits, out.data(), out.size());
+}
+size_t t3r_words_from_subword_stream(const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words9)
+{
+    std::vector<UTrit> in(trits, trits + n_trits);
+    std::vector<Word27> out;
+    build_words_from_subword_stream(in, N, out, fill);
+    if (!out.empty()) std::memcpy(words9, out.data(), 9 * out.size());
+    return out.size();
+}
+size_t t3r_base243_pack(const uint8_t* trits, size_t n_trits, uint8_t* out_bytes)
+{
+    std::vector<UTrit> in(trits, trits + n_trits);
+    std::vector<uint8_t> out;
+    tpack::ut_to_base243(in, out);
+    std::memcpy(out_bytes, out.data(), out.size());
+    return out.size();
+}
+int t3r_base243_unpack(const uint8_t* in_bytes, size_t n_bytes, uint8_t* trits, size_t cap, size_t* n_trits)
+{
+    std::vector<uint8_t> in(in_bytes, in_bytes + n_bytes);
+    std::vector<UTrit> out;
+    const bool ok = tpack::base243_to_ut(in, out);
+    *n_trits = out.size();
+    std::memcpy(trits, out.data(), std::min(cap, out.size()));
+    return ok ? 1 : 0;
+}
+
 } // extern "C"

@@ -776,3 +776,76 @@ int t3o_decode_rgb_fixed(const t3o_cfg* c, size_t n_px, const uint8_t* in9, size
     free(raw);
     return ok;
 }
+
+/* ------------------------------------------------------------------ */
+/* sub-word streams, OLD:816-859                        */
+/* ------------------------------------------------------------------ */
+void t3o_subword_stream(const uint8_t* words9, size_t n_words, int N, uint8_t* trits) /* extract_subword_stream_from_words, OLD:835-845 */
+{
+    for (size_t w = 0; w < n_words; ++w) {
+        uint8_t T[27];
+        for (int s = 0; s < 9; ++s) unpack3(words9[9 * w + s], T + 3 * s); /* extract_subword_trits_from_word, OLD:817-827 */
+        for (int i = 0; i < N; ++i) trits[(size_t)N * w + i] = T[i];
+    }
+}
+size_t t3o_words_from_subword_stream(const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words9) /* OLD:846-859 */
+{
+    size_t idx = 0, nw = 0;
+    while (idx < n_trits) {
+        uint8_t buf[27] = {0}, T[27];
+        int take = (int)((n_trits - idx) < (size_t)N ? (n_trits - idx) : (size_t)N);
+        for (int i = 0; i < take; ++i) buf[i] = trits[idx + i];
+        for (int i = 0; i < N; ++i) T[i] = buf[i];            /* inject_subword_trits_into_word, OLD:828-834 */
+        for (int i = N; i < 27; ++i) T[i] = fill;
+        for (int s = 0; s < 9; ++s) words9[9 * nw + s] = pack3(T[3 * s], T[3 * s + 1], T[3 * s + 2]);
+        ++nw;
+        idx += (size_t)take;
+    }
+    return nw;
+}
+/* base-243, include/ternary_packing.hpp:18-50: uint32 LE trit count, then 5 trits per byte (LSD first, zero padded) */
+size_t t3o_base243_pack(const uint8_t* trits, size_t n_trits, uint8_t* out)
+{
+    uint32_t total = (uint32_t)n_trits;
+    memcpy(out, &total, 4);
+    size_t o = 4, i = 0;
+    while (i < n_trits) {
+        uint8_t buf[5] = {0, 0, 0, 0, 0};
+        for (int t = 0; t < 5 && i < n_trits; ++t) buf[t] = trits[i++];
+        out[o++] = (uint8_t)(buf[0] + 3 * buf[1] + 9 * buf[2] + 27 * buf[3] + 81 * buf[4]);
+    }
+    return o;
+}
+int t3o_base243_unpack(const uint8_t* in, size_t n_bytes, uint8_t* trits, size_t cap, size_t* n_trits)
+{
+    *n_trits = 0;
+    if (n_bytes < 4) return 0;
+    uint32_t total = 0;
+    memcpy(&total, in, 4);
+    size_t idx = 4, n = 0;
+    while (idx < n_bytes && n < total) {
+        int v = in[idx++];
+        for (int k = 0; k < 5; ++k) { uint8_t t = (uint8_t)(v % 3); v /= 3; if (n < total) { if (n < cap) trits[n] = t; ++n; } }
+    }
+    *n_trits = n;
+    return n == total;
+}
+/* ------------------------------------------------------------------ */
+/* NEW-generation RAW path, src/ternary_image_codec_v6_min.cpp:62-99 */
+/* ------------------------------------------------------------------ */
+void t3o_v6new_pack_pixels(const t3o_pixel* px, size_t n_px, uint32_t* words) /* pack13_from_quant, :62-78 */
+{
+    for (size_t i = 0; i < n_px; ++i) {
+        uint32_t Y = (uint32_t)clampi(px[i].Yq, 0, 242), Cb = (uint32_t)clampi(px[i].Cbq + 40, 0, 80), Cr = (uint32_t)clampi(px[i].Crq + 40, 0, 80);
+        words[i] = Y + 243u * (Cb + 81u * Cr);
+    }
+}
+void t3o_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3o_pixel* px) /* unpack13_to_quant, :81-95 */
+{
+    for (size_t i = 0; i < n_words; ++i) {
+        uint32_t code = words[i], block = code / 243u, Y = code % 243u, Cr = block / 81u, Cb = block % 81u;
+        px[i].Yq = (uint16_t)(Y < 242u ? Y : 242u);
+        px[i].Cbq = (int16_t)clampi((int32_t)Cb - 40, -40, 40);
+        px[i].Crq = (int16_t)clampi((int32_t)Cr - 40, -40, 40);
+    }
+}

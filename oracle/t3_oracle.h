@@ -109,6 +109,15 @@ size_t t3o_encode_rgb(const t3o_cfg* c, int fixed, const uint8_t* rgb, size_t n_
 int    t3o_decode_rgb_fixed(const t3o_cfg* c, size_t n_px, const uint8_t* in9, size_t n_words, uint8_t* rgb,
                             size_t* n_px_out, size_t* n_corrected);
 
+/* ---- sub-word streams + base-243 (OLD:816-859, include/ternary_packing.hpp:18-50) and the
+ * NEW-generation RAW path (src/ternary_image_codec_v6_min.cpp:62-126: one pixel -> one 32-bit word, clamped) ---- */
+void   t3o_subword_stream(const uint8_t* words9, size_t n_words, int N, uint8_t* trits /* N*n_words */);
+size_t t3o_words_from_subword_stream(const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words9 /* ceil(n/N) */);
+size_t t3o_base243_pack(const uint8_t* trits, size_t n_trits, uint8_t* out /* 4 + ceil(n/5) */);
+int    t3o_base243_unpack(const uint8_t* in, size_t n_bytes, uint8_t* trits, size_t cap, size_t* n_trits);
+void   t3o_v6new_pack_pixels(const t3o_pixel* px, size_t n_px, uint32_t* words);
+void   t3o_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3o_pixel* px);
+
 #ifdef __cplusplus
 }
 #endif

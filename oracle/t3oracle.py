@@ -88,7 +88,7 @@ class _Lib:
         self.fixed = fixed  # None: the library takes a `fixed` argument (oracle); else baked in (reference builds)
         L = self.lib
         sz, u8p = C.c_size_t, C.POINTER(C.c_uint8)
-        for name in ("encode_profile", "pack_pixels", "profile_words_bound", "bytes_to_words", "encode_rgb"):
+        for name in ("encode_profile", "pack_pixels", "profile_words_bound", "bytes_to_words", "encode_rgb", "words_from_subword_stream", "base243_pack"):
             if hasattr(L, pfx + name):
                 getattr(L, pfx + name).restype = sz
         for name in ("gf_add", "gf_sub", "gf_mul", "gf_inv", "gf_pow_alpha", "scramble_symbol", "descramble_symbol", "beacon_symbol"):
@@ -167,6 +167,34 @@ class _Lib:
         self.f("unpack_pixels")(wp, C.c_size_t(nw), px.ctypes.data_as(C.c_void_p))
         return px
 
+    # --- sub-word streams + base-243 (same symbols in the oracle and the reference shim) ---
+    def subword_stream(self, words, N):
+        w, wp = _u8(words)
+        nw = w.size // 9
+        out = np.zeros(nw * N, np.uint8)
+        self.f("subword_stream")(wp, C.c_size_t(nw), C.c_int(N), _ptr(out))
+        return out
+
+    def words_from_subword_stream(self, trits, N, fill=0):
+        t, tp = _u8(trits)
+        out = np.zeros(((t.size + N - 1) // N + 1, 9), np.uint8)
+        n = self.f("words_from_subword_stream")(tp, C.c_size_t(t.size), C.c_int(N), C.c_uint8(fill), _ptr(out))
+        return out[:n].copy()
+
+    def base243_pack(self, trits):
+        t, tp = _u8(trits)
+        out = np.zeros(4 + (t.size + 4) // 5 + 8, np.uint8)
+        n = self.f("base243_pack")(tp, C.c_size_t(t.size), _ptr(out))
+        return out[:n].copy()
+
+    def base243_unpack(self, data, cap=None):
+        d, dp = _u8(data)
+        cap = 5 * d.size + 8 if cap is None else cap
+        out = np.zeros(cap, np.uint8)
+        n = C.c_size_t()
+        ok = self.f("base243_unpack")(dp, C.c_size_t(d.size), _ptr(out), C.c_size_t(cap), C.byref(n))
+        return bool(ok), out[:min(n.value, cap)].copy()
+
     def rgb_to_quant(self, rgb):
         r, rp = _u8(rgb)
         n = r.size // 3
@@ -230,6 +258,18 @@ class Oracle(_Lib):
         build()
         super().__init__(os.path.join(HERE, "libt3oracle.so"), "t3o_", None)
         self.lib.t3o_gf_log.restype = C.c_int
+
+    def v6new_pack_pixels(self, px):
+        px = np.ascontiguousarray(px, dtype=PIXEL_DTYPE)
+        out = np.zeros(px.size, np.uint32)
+        self.lib.t3o_v6new_pack_pixels(px.ctypes.data_as(C.c_void_p), C.c_size_t(px.size), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def v6new_unpack_pixels(self, words):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        px = np.zeros(w.size, PIXEL_DTYPE)
+        self.lib.t3o_v6new_unpack_pixels(w.ctypes.data_as(C.c_void_p), C.c_size_t(w.size), px.ctypes.data_as(C.c_void_p))
+        return px
 
     def words_bound(self, cfg, n_words):
         return int(self.lib.t3o_profile_words_bound(C.byref(cfg), C.c_size_t(n_words)))
@@ -317,6 +357,29 @@ class Reference(_Lib):
         out = np.zeros((b.size // 9 + 1, 9), np.uint8)
         n = self.lib.t3r_bytes_to_words(bp, C.c_size_t(b.size), _ptr(out))
         return out[:n].copy()
+
+
+class ReferenceNew:
+    """The reference's NEW-generation core (one pixel -> one 32-bit word), oracle/_ref/libt3ref_new.so; SURVEY 8(f).3."""
+
+    def __init__(self):
+        build()
+        path = os.path.join(HERE, "_ref", "libt3ref_new.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+
+    def pack_pixels(self, px, subword=0):
+        px = np.ascontiguousarray(px, dtype=PIXEL_DTYPE)
+        out = np.zeros(px.size, np.uint32)
+        ok = self.lib.t3n_pack_pixels(px.ctypes.data_as(C.c_void_p), C.c_size_t(px.size), out.ctypes.data_as(C.c_void_p), C.c_int(subword))
+        return bool(ok), out
+
+    def unpack_pixels(self, words, subword=0):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        px = np.zeros(w.size, PIXEL_DTYPE)
+        ok = self.lib.t3n_unpack_pixels(w.ctypes.data_as(C.c_void_p), C.c_size_t(w.size), px.ctypes.data_as(C.c_void_p), C.c_int(subword))
+        return bool(ok), px
 
 
 # --------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libt3c.so")
-CU = ["k_general.cu", "k_fast.cu", "api.cu"]
+CU = ["k_general.cu", "k_fast.cu", "k_formats.cu", "api.cu"]
 CPP = ["tables.cpp"]
 HDRS = ["dev.cuh", "launch.h", "t3c_internal.h", os.path.join("..", "..", "include", "t3c.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

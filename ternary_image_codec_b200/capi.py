@@ -67,6 +67,9 @@ _EXPORTS = [
     "t3c_pack_pixels_dev", "t3c_unpack_pixels_dev", "t3c_rs_encode_blocks_dev", "t3c_rs_decode_blocks_dev",
     "t3c_encode_profile_dev", "t3c_decode_profile_fixed_dev", "t3c_encode_frames_rgb8_dev",
     "t3c_decode_frames_rgb8_dev", "t3c_fast_path_available",
+    "t3c_subword_stream", "t3c_words_from_subword_stream", "t3c_base243_pack", "t3c_base243_unpack", "t3c_words_to_base243",
+    "t3c_v6new_pack_pixels", "t3c_v6new_unpack_pixels", "t3c_subword_stream_dev", "t3c_words_from_subword_stream_dev",
+    "t3c_base243_pack_dev", "t3c_base243_unpack_dev", "t3c_words_to_base243_dev", "t3c_v6new_pack_pixels_dev", "t3c_v6new_unpack_pixels_dev",
 ]
 
 _lib = None
@@ -124,6 +127,20 @@ def load_library() -> C.CDLL:
     L.t3c_decode_profile_fixed_dev.argtypes = [vp, cfgp, sz, vp, sz, vp, sz, vp, vp]
     L.t3c_encode_frames_rgb8_dev.argtypes = [vp, cfgp, i32, vp, sz, sz, vp, sz, vp]
     L.t3c_decode_frames_rgb8_dev.argtypes = [vp, cfgp, vp, sz, sz, sz, sz, vp, vp, vp]
+    L.t3c_subword_stream.argtypes = [vp, u8p, sz, i32, u8p]
+    L.t3c_words_from_subword_stream.argtypes = [vp, u8p, sz, i32, C.c_uint8, u8p, szp]
+    L.t3c_base243_pack.argtypes = [vp, u8p, sz, u8p, szp]
+    L.t3c_base243_unpack.argtypes = [vp, u8p, sz, u8p, sz, szp, C.POINTER(i32)]
+    L.t3c_words_to_base243.argtypes = [vp, u8p, sz, i32, u8p, szp]
+    L.t3c_v6new_pack_pixels.argtypes = [vp, vp, sz, vp, i32]
+    L.t3c_v6new_unpack_pixels.argtypes = [vp, vp, sz, vp, i32]
+    L.t3c_subword_stream_dev.argtypes = [vp, vp, sz, i32, vp, vp]
+    L.t3c_words_from_subword_stream_dev.argtypes = [vp, vp, sz, i32, C.c_uint8, vp, vp]
+    L.t3c_base243_pack_dev.argtypes = [vp, vp, sz, vp, vp]
+    L.t3c_base243_unpack_dev.argtypes = [vp, vp, sz, vp, vp]
+    L.t3c_words_to_base243_dev.argtypes = [vp, vp, sz, i32, vp, vp]
+    L.t3c_v6new_pack_pixels_dev.argtypes = [vp, vp, sz, vp, vp]
+    L.t3c_v6new_unpack_pixels_dev.argtypes = [vp, vp, sz, vp, vp]
     for name in _EXPORTS:
         getattr(L, name)  # AttributeError here = header and library out of sync
     _lib = L
@@ -190,6 +207,81 @@ class Codec:
 
     def sync(self):
         self._ck(self.lib.t3c_sync(self.h))
+
+    # ---------------- data formats either side of the path ----------------
+    def extract_subword_stream_from_words(self, words, N) -> np.ndarray:
+        w = _u8(words)
+        nw = w.size // 9
+        out = np.zeros(nw * N, np.uint8)
+        self._ck(self.lib.t3c_subword_stream(self.h, _p(w), nw, N, _p(out)))
+        return out
+
+    def build_words_from_subword_stream(self, trits, N, fill=0) -> np.ndarray:
+        t = _u8(trits)
+        out = np.zeros(((t.size + N - 1) // N + 1, 9), np.uint8)
+        n = C.c_size_t()
+        self._ck(self.lib.t3c_words_from_subword_stream(self.h, _p(t), t.size, N, fill, _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def ut_to_base243(self, trits) -> np.ndarray:
+        t = _u8(trits)
+        out = np.zeros(4 + (t.size + 4) // 5 + 8, np.uint8)
+        n = C.c_size_t()
+        self._ck(self.lib.t3c_base243_pack(self.h, _p(t), t.size, _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def base243_to_ut(self, data, cap=None):
+        d = _u8(data)
+        cap = 5 * d.size + 8 if cap is None else cap
+        out = np.zeros(cap, np.uint8)
+        n, ok = C.c_size_t(), C.c_int()
+        self._ck(self.lib.t3c_base243_unpack(self.h, _p(d), d.size, _p(out), cap, C.byref(n), C.byref(ok)))
+        return bool(ok.value), out[:min(n.value, cap)].copy()
+
+    def words_to_base243(self, words, N) -> np.ndarray:
+        w = _u8(words)
+        nw = w.size // 9
+        out = np.zeros(4 + (nw * N + 4) // 5 + 8, np.uint8)
+        n = C.c_size_t()
+        self._ck(self.lib.t3c_words_to_base243(self.h, _p(w), nw, N, _p(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def v6new_encode_raw_pixels_to_words(self, px, subword=0):
+        """NEW-generation encode_raw_pixels_to_words[_subword]; returns (ok, words) like the reference's bool"""
+        px = np.ascontiguousarray(px, dtype=PIXEL_DTYPE)
+        out = np.zeros(px.size, np.uint32)
+        st = self.lib.t3c_v6new_pack_pixels(self.h, _p(px), px.size, _p(out), subword)
+        if st == ERR_ARG:
+            return False, out
+        self._ck(st)
+        return True, out
+
+    def v6new_decode_raw_words_to_pixels(self, words, subword=0):
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        px = np.zeros(w.size, PIXEL_DTYPE)
+        st = self.lib.t3c_v6new_unpack_pixels(self.h, _p(w), w.size, _p(px), subword)
+        if st == ERR_ARG:
+            return False, px
+        self._ck(st)
+        return True, px
+
+    def subword_stream_dev(self, d_words, n_words, N, d_trits, stream=0):
+        self._ck(self.lib.t3c_subword_stream_dev(self.h, self._dp(d_words), n_words, N, self._dp(d_trits), stream))
+
+    def words_to_base243_dev(self, d_words, n_words, N, d_out, stream=0):
+        self._ck(self.lib.t3c_words_to_base243_dev(self.h, self._dp(d_words), n_words, N, self._dp(d_out), stream))
+
+    def base243_pack_dev(self, d_trits, n_trits, d_out, stream=0):
+        self._ck(self.lib.t3c_base243_pack_dev(self.h, self._dp(d_trits), n_trits, self._dp(d_out), stream))
+
+    def base243_unpack_dev(self, d_payload, n_trits, d_trits, stream=0):
+        self._ck(self.lib.t3c_base243_unpack_dev(self.h, self._dp(d_payload), n_trits, self._dp(d_trits), stream))
+
+    def v6new_pack_pixels_dev(self, d_px, n_px, d_words, stream=0):
+        self._ck(self.lib.t3c_v6new_pack_pixels_dev(self.h, self._dp(d_px), n_px, self._dp(d_words), stream))
+
+    def v6new_unpack_pixels_dev(self, d_words, n_words, d_px, stream=0):
+        self._ck(self.lib.t3c_v6new_unpack_pixels_dev(self.h, self._dp(d_words), n_words, self._dp(d_px), stream))
 
     # ---------------- K1 ----------------
     def rgb_to_quant_stream(self, rgb) -> np.ndarray:

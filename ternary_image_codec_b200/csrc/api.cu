@@ -766,4 +766,156 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
     return T3C_OK;
 }
 
+// =============================================================================================
+// sub-word streams + base-243 (8(f).2), NEW-generation RAW path (8(f).3)
+// =============================================================================================
+static bool subword_ok(int sub) { return sub == 0 || sub == 27 || sub == 24 || sub == 21 || sub == 18 || sub == 15; } // is_valid_subword, NEW:118-123
+
+t3c_status t3c_subword_stream_dev(t3c_ctx* ctx, const uint8_t* d_words, size_t n_words, int N, uint8_t* d_trits, void* st)
+{
+    if (!ctx || N < 0 || N > 27 || (n_words && N && (!d_words || !d_trits))) return fail(ctx, T3C_ERR_ARG, "subword_stream: bad N or null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_subword_stream(d_words, n_words, N, d_trits, (cudaStream_t)st));
+}
+t3c_status t3c_words_from_subword_stream_dev(t3c_ctx* ctx, const uint8_t* d_trits, size_t n_trits, int N, uint8_t fill, uint8_t* d_words, void* st)
+{
+    if (!ctx || N < 1 || N > 27 || (n_trits && (!d_words || !d_trits))) return fail(ctx, T3C_ERR_ARG, "words_from_subword_stream: bad N or null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_words_from_subword_stream(d_trits, n_trits, N, fill, d_words, (cudaStream_t)st));
+}
+t3c_status t3c_base243_pack_dev(t3c_ctx* ctx, const uint8_t* d_trits, size_t n_trits, uint8_t* d_out, void* st)
+{
+    if (!ctx || !d_out || (n_trits && !d_trits)) return fail(ctx, T3C_ERR_ARG, "base243_pack: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_base243_pack(d_trits, n_trits, d_out, (cudaStream_t)st));
+}
+t3c_status t3c_base243_unpack_dev(t3c_ctx* ctx, const uint8_t* d_payload, size_t n_trits, uint8_t* d_trits, void* st)
+{
+    if (!ctx || (n_trits && (!d_payload || !d_trits))) return fail(ctx, T3C_ERR_ARG, "base243_unpack: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_base243_unpack(d_payload, n_trits, d_trits, (cudaStream_t)st));
+}
+t3c_status t3c_words_to_base243_dev(t3c_ctx* ctx, const uint8_t* d_words, size_t n_words, int N, uint8_t* d_out, void* st)
+{
+    if (!ctx || N < 1 || N > 27 || !d_out || (n_words && !d_words)) return fail(ctx, T3C_ERR_ARG, "words_to_base243: bad N or null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_words_to_base243(d_words, n_words, N, d_out, (cudaStream_t)st));
+}
+t3c_status t3c_v6new_pack_pixels_dev(t3c_ctx* ctx, const t3c_pixel* d_px, size_t n_px, uint32_t* d_words, void* st)
+{
+    if (!ctx || (n_px && (!d_px || !d_words))) return fail(ctx, T3C_ERR_ARG, "v6new_pack_pixels: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_v6new_pack_pixels(d_px, n_px, d_words, (cudaStream_t)st));
+}
+t3c_status t3c_v6new_unpack_pixels_dev(t3c_ctx* ctx, const uint32_t* d_words, size_t n_words, t3c_pixel* d_px, void* st)
+{
+    if (!ctx || (n_words && (!d_px || !d_words))) return fail(ctx, T3C_ERR_ARG, "v6new_unpack_pixels: null");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_v6new_unpack_pixels(d_words, n_words, d_px, (cudaStream_t)st));
+}
+
+t3c_status t3c_subword_stream(t3c_ctx* ctx, const uint8_t* words, size_t n_words, int N, uint8_t* trits)
+{
+    if (!ctx || N < 0 || N > 27 || (n_words && N && (!words || !trits))) return fail(ctx, T3C_ERR_ARG, "subword_stream: bad N or null");
+    if (!n_words || !N) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, n_words * (size_t)N, &d_out));
+    H2D(d_in, words, 9 * n_words);
+    TRY(t3c_subword_stream_dev(ctx, d_in, n_words, N, d_out, ctx->stream));
+    D2H(trits, d_out, n_words * (size_t)N);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_words_from_subword_stream(t3c_ctx* ctx, const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words, size_t* n_words)
+{
+    if (!ctx || !n_words || N < 1 || N > 27 || (n_trits && (!words || !trits))) return fail(ctx, T3C_ERR_ARG, "words_from_subword_stream: bad N or null");
+    const size_t nw = (n_trits + (size_t)N - 1) / (size_t)N;
+    *n_words = nw;
+    if (!nw) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, n_trits, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * nw, &d_out));
+    H2D(d_in, trits, n_trits);
+    TRY(t3c_words_from_subword_stream_dev(ctx, d_in, n_trits, N, fill, d_out, ctx->stream));
+    D2H(words, d_out, 9 * nw);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_base243_pack(t3c_ctx* ctx, const uint8_t* trits, size_t n_trits, uint8_t* out, size_t* n_bytes)
+{
+    if (!ctx || !out || !n_bytes || (n_trits && !trits)) return fail(ctx, T3C_ERR_ARG, "base243_pack: null");
+    const size_t nb = 4 + (n_trits + 4) / 5;
+    *n_bytes = nb;
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, n_trits, &d_in)); TRY(reserve_t(ctx, B_OUT, nb, &d_out));
+    if (n_trits) H2D(d_in, trits, n_trits);
+    TRY(t3c_base243_pack_dev(ctx, d_in, n_trits, d_out, ctx->stream));
+    D2H(out, d_out, nb);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_base243_unpack(t3c_ctx* ctx, const uint8_t* in, size_t n_bytes, uint8_t* trits, size_t cap, size_t* n_trits, int* ok)
+{
+    if (!ctx || !n_trits || !ok || (n_bytes && !in)) return fail(ctx, T3C_ERR_ARG, "base243_unpack: null");
+    *n_trits = 0; *ok = 0;
+    if (n_bytes < 4) return T3C_OK;                                   // base243_to_ut: false
+    uint32_t total = 0;
+    std::memcpy(&total, in, 4);                                       // the count is container metadata, read on the host like a header
+    const size_t avail = 5 * (n_bytes - 4), n = total < avail ? total : avail;
+    *n_trits = n; *ok = n == total;
+    const size_t nw = n < cap ? n : cap;
+    if (!nw) return T3C_OK;
+    if (!trits) return fail(ctx, T3C_ERR_ARG, "base243_unpack: null output");
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, n_bytes, &d_in)); TRY(reserve_t(ctx, B_OUT, nw, &d_out));
+    H2D(d_in, in + 4, n_bytes - 4);
+    TRY(t3c_base243_unpack_dev(ctx, d_in, nw, d_out, ctx->stream));
+    D2H(trits, d_out, nw);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_words_to_base243(t3c_ctx* ctx, const uint8_t* words, size_t n_words, int N, uint8_t* out, size_t* n_bytes)
+{
+    if (!ctx || !out || !n_bytes || N < 1 || N > 27 || (n_words && !words)) return fail(ctx, T3C_ERR_ARG, "words_to_base243: bad N or null");
+    const size_t nb = 4 + (n_words * (size_t)N + 4) / 5;
+    *n_bytes = nb;
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, nb, &d_out));
+    if (n_words) H2D(d_in, words, 9 * n_words);
+    TRY(t3c_words_to_base243_dev(ctx, d_in, n_words, N, d_out, ctx->stream));
+    D2H(out, d_out, nb);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_v6new_pack_pixels(t3c_ctx* ctx, const t3c_pixel* px, size_t n_px, uint32_t* words, int subword)
+{
+    if (!ctx || !subword_ok(subword) || (n_px && (!px || !words))) return fail(ctx, T3C_ERR_ARG, "v6new_pack_pixels: invalid subword mode or null");
+    if (!n_px) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    t3c_pixel* d_in; uint32_t* d_out;
+    TRY(reserve_t(ctx, B_IN, 6 * n_px, &d_in)); TRY(reserve_t(ctx, B_OUT, 4 * n_px, &d_out));
+    H2D(d_in, px, 6 * n_px);
+    TRY(t3c_v6new_pack_pixels_dev(ctx, d_in, n_px, d_out, ctx->stream));
+    D2H(words, d_out, 4 * n_px);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_v6new_unpack_pixels(t3c_ctx* ctx, const uint32_t* words, size_t n_words, t3c_pixel* px, int subword)
+{
+    if (!ctx || !subword_ok(subword) || (n_words && (!px || !words))) return fail(ctx, T3C_ERR_ARG, "v6new_unpack_pixels: invalid subword mode or null");
+    if (!n_words) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    uint32_t* d_in; t3c_pixel* d_out;
+    TRY(reserve_t(ctx, B_IN, 4 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, 6 * n_words, &d_out));
+    H2D(d_in, words, 4 * n_words);
+    TRY(t3c_v6new_unpack_pixels_dev(ctx, d_in, n_words, d_out, ctx->stream));
+    D2H(px, d_out, 6 * n_words);
+    SYNC();
+    return T3C_OK;
+}
+
 } // extern "C"

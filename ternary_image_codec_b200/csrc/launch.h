@@ -76,4 +76,13 @@ const uint8_t* cached_header(const DevTables& T, const t3c_config& cfg, int arit
 int launch_frame_finish(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out9, size_t n_frames, size_t stride_bytes, cudaStream_t st);
 int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out9, size_t n_frames, size_t stride_bytes, cudaStream_t st);
 
+// SURVEY 8(f).2 / 8(f).3 (k_formats.cu)
+int launch_subword_stream(const uint8_t* words9, size_t n_words, int N, uint8_t* trits, cudaStream_t st);
+int launch_words_from_subword_stream(const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words9, cudaStream_t st);
+int launch_base243_pack(const uint8_t* trits, size_t n_trits, uint8_t* out, cudaStream_t st);           // writes the 4-byte count too
+int launch_base243_unpack(const uint8_t* payload, size_t n_trits, uint8_t* trits, cudaStream_t st);
+int launch_words_to_base243(const uint8_t* words9, size_t n_words, int N, uint8_t* out, cudaStream_t st);
+int launch_v6new_pack_pixels(const t3c_pixel* px, size_t n_px, uint32_t* words, cudaStream_t st);
+int launch_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3c_pixel* px, cudaStream_t st);
+
 } // namespace t3c

@@ -36,3 +36,13 @@ def ref_fixed():
     if not t3oracle.Reference.available():
         pytest.skip("oracle/_ref not built and /root/reference absent")
     return t3oracle.Reference(fixed=True)
+
+
+@pytest.fixture(scope="session")
+def ref_new():
+    """The reference's NEW-generation core (oracle/_ref/libt3ref_new.so), SURVEY 8(f).3."""
+    import t3oracle
+    try:
+        return t3oracle.ReferenceNew()
+    except (FileNotFoundError, OSError):
+        pytest.skip("oracle/_ref/libt3ref_new.so not built and /root/reference absent")

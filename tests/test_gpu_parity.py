@@ -578,3 +578,44 @@ def test_two_devices_in_one_process(oracle, t3):
         assert ok.all() and np.array_equal(back[0], oracle.decode_rgb_fixed(oc, want, n_px)[1])
         assert np.array_equal(c.encode_raw_pixels_to_words(px), oracle.pack_pixels(px))
         c.close()
+
+
+# ------------------------------------------------------------------ SURVEY 8(f).2 / 8(f).3
+@pytest.mark.parametrize("N", (27, 24, 21, 18, 15, 1, 5))
+def test_subword_streams_and_base243(codec, oracle, N):
+    r = rng(600 + N)
+    for nw in (0, 1, 3, 50, 4097, 100003):
+        words = r.integers(0, 256, size=(nw, 9), dtype=np.uint8)
+        a = codec.extract_subword_stream_from_words(words, N)
+        assert np.array_equal(a, oracle.subword_stream(words, N))
+        assert np.array_equal(codec.words_to_base243(words, N), oracle.base243_pack(a))
+        for n in sorted({0, 1, N, N + 1, 5 * N + 3, a.size}):
+            if n > a.size:
+                continue
+            t = a[:n].copy()
+            if n > 10:
+                t[r.integers(0, n, 5)] = r.integers(3, 256, 5)          # bytes that are not trits wrap like pack3 / the byte cast
+            for fill in (0, 2, 200):
+                assert np.array_equal(codec.build_words_from_subword_stream(t, N, fill), oracle.words_from_subword_stream(t, N, fill))
+            p = codec.ut_to_base243(t)
+            assert np.array_equal(p, oracle.base243_pack(t))
+            for blob in (p, p[:max(0, p.size - 1)], p[:2], np.concatenate([p, np.array([7, 200], np.uint8)])):
+                ok_g, u_g = codec.base243_to_ut(blob)
+                ok_o, u_o = oracle.base243_unpack(blob)
+                assert ok_g == ok_o and np.array_equal(u_g, u_o)
+
+
+def test_v6new_raw_path(codec, oracle):
+    r = rng(700)
+    for n in (0, 1, 3, 4, 5, 4099, 200001):
+        px = np.zeros(n, T.PIXEL_DTYPE)
+        px["Yq"], px["Cbq"], px["Crq"] = r.integers(0, 65536, n), r.integers(-32768, 32768, n), r.integers(-32768, 32768, n)
+        px[: n // 2] = T.synth_quant(9, n // 2)
+        ok, w = codec.v6new_encode_raw_pixels_to_words(px)
+        assert ok and np.array_equal(w, oracle.v6new_pack_pixels(px))
+        wild = r.integers(0, 2 ** 32, n, dtype=np.uint32)
+        for words in (w, wild):
+            ok, p = codec.v6new_decode_raw_words_to_pixels(words)
+            assert ok and np.array_equal(p.view(np.uint8), oracle.v6new_unpack_pixels(words).view(np.uint8))
+    assert codec.v6new_encode_raw_pixels_to_words(px, 24)[0] and not codec.v6new_encode_raw_pixels_to_words(px, 7)[0]
+    assert codec.v6new_decode_raw_words_to_pixels(w, 15)[0] and not codec.v6new_decode_raw_words_to_pixels(w, 26)[0]

@@ -360,3 +360,62 @@ def test_tpack_words_bytes(ref):
     assert np.array_equal(b, (w % 27).reshape(-1))
     assert np.array_equal(ref.bytes_to_words(b), (w % 27))
     assert ref.bytes_to_words(b[:-1]).shape[0] == 0
+
+
+# ------------------------------------------------------------------ formats either side of the path
+SUBWORDS = (27, 24, 21, 18, 15)
+
+
+def _wild_trits(r, n):
+    t = r.integers(0, 3, n, dtype=np.uint8)
+    if n:
+        t[r.integers(0, n, max(1, n // 50))] = r.integers(3, 256, max(1, n // 50))  # UTrit is a byte: out-of-range values wrap through pack3
+    return t
+
+
+@pytest.mark.parametrize("N", SUBWORDS)
+def test_subword_streams_and_base243_match_reference(oracle, ref, N):
+    r = rng(800 + N)
+    for nw in (0, 1, 2, 7, 1000):
+        words = r.integers(0, 256, size=(nw, 9), dtype=np.uint8)      # bytes >= 27 read as their low three trits
+        a = oracle.subword_stream(words, N)
+        assert np.array_equal(a, ref.subword_stream(words, N)) and a.size == nw * N
+        for n in sorted({0, 1, N - 1, N, N + 1, 5 * N + 3, a.size}):
+            if n > a.size:
+                continue
+            for fill in (0, 1, 2, 77):
+                t = _wild_trits(r, n) if fill == 77 else a[:n]
+                assert np.array_equal(oracle.words_from_subword_stream(t, N, fill), ref.words_from_subword_stream(t, N, fill))
+            for t in (a[:n], _wild_trits(r, n)):
+                p = oracle.base243_pack(t)
+                assert np.array_equal(p, ref.base243_pack(t)) and p.size == 4 + (n + 4) // 5
+                for blob in (p, p[:max(0, p.size - 1)], p[:3], np.concatenate([p, r.integers(0, 256, 3, dtype=np.uint8)])):
+                    ok_o, u_o = oracle.base243_unpack(blob)
+                    ok_r, u_r = ref.base243_unpack(blob)
+                    assert ok_o == ok_r and np.array_equal(u_o, u_r)
+        # known answer: the first N trits of a valid word are the digits of its symbols
+        if nw:
+            w0 = words[0] % 27
+            digits = np.array([(w0[i // 3] // 3 ** (i % 3)) % 3 for i in range(27)], np.uint8)
+            assert np.array_equal(a[:N], digits[:N])
+
+
+def test_v6new_raw_path_matches_reference(oracle, ref_new):
+    r = rng(900)
+    px = np.zeros(20001, T.PIXEL_DTYPE)
+    px["Yq"], px["Cbq"], px["Crq"] = r.integers(0, 65536, px.size), r.integers(-32768, 32768, px.size), r.integers(-32768, 32768, px.size)
+    px[:6000] = T.synth_quant(7, 6000)
+    ok, w = ref_new.pack_pixels(px)
+    assert ok and np.array_equal(w, oracle.v6new_pack_pixels(px))
+    assert w[:6000].max() < 3 ** 13 and np.array_equal(oracle.v6new_unpack_pixels(w[:6000]).view(np.uint8), px[:6000].view(np.uint8))
+    wild = r.integers(0, 2 ** 32, 20000, dtype=np.uint32)
+    ok, p = ref_new.unpack_pixels(wild)
+    assert ok and np.array_equal(p.view(np.uint8), oracle.v6new_unpack_pixels(wild).view(np.uint8))
+    for sub, good in ((27, True), (24, True), (21, True), (18, True), (15, True), (7, False), (26, False)):
+        ok, w2 = ref_new.pack_pixels(px[:100], sub)
+        assert ok is good and (not good or np.array_equal(w2, w[:100]))     # the sub-word argument only gates validity (v6_min)
+        assert ref_new.unpack_pixels(w[:100], sub)[0] is good
+    # known answer: Y + 243 (Cb+40 + 81 (Cr+40))
+    one = np.zeros(1, T.PIXEL_DTYPE)
+    one["Yq"], one["Cbq"], one["Crq"] = 242, 40, 40
+    assert int(oracle.v6new_pack_pixels(one)[0]) == 3 ** 13 - 1
