@@ -66,7 +66,7 @@ _EXPORTS = [
     "t3c_encode_frames_rgb8", "t3c_decode_frames_rgb8", "t3c_rgb_to_quant_dev", "t3c_quant_to_rgb_dev",
     "t3c_pack_pixels_dev", "t3c_unpack_pixels_dev", "t3c_rs_encode_blocks_dev", "t3c_rs_decode_blocks_dev",
     "t3c_encode_profile_dev", "t3c_decode_profile_fixed_dev", "t3c_encode_frames_rgb8_dev",
-    "t3c_decode_frames_rgb8_dev", "t3c_fast_path_available",
+    "t3c_decode_frames_rgb8_dev", "t3c_fast_path_available", "t3c_super_path_available",
     "t3c_subword_stream", "t3c_words_from_subword_stream", "t3c_base243_pack", "t3c_base243_unpack", "t3c_words_to_base243",
     "t3c_v6new_pack_pixels", "t3c_v6new_unpack_pixels", "t3c_subword_stream_dev", "t3c_words_from_subword_stream_dev",
     "t3c_base243_pack_dev", "t3c_base243_unpack_dev", "t3c_words_to_base243_dev", "t3c_v6new_pack_pixels_dev", "t3c_v6new_unpack_pixels_dev",
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     L.t3c_profile_words.argtypes = [cfgp, sz]
     L.t3c_profile_words.restype = sz
     L.t3c_fast_path_available.argtypes = [cfgp]
+    L.t3c_super_path_available.argtypes = [cfgp]
     L.t3c_rgb_to_quant.argtypes = [vp, u8p, sz, vp]
     L.t3c_quant_to_rgb.argtypes = [vp, vp, sz, u8p]
     L.t3c_pack_pixels.argtypes = [vp, vp, sz, u8p, szp]
@@ -157,6 +158,11 @@ def profile_words(cfg: Config, n_raw_words: int) -> int:
 
 def fast_path_available(cfg: Config) -> bool:
     return bool(load_library().t3c_fast_path_available(C.byref(cfg)))
+
+
+def super_path_available(cfg: Config) -> bool:
+    """the super-tile kernels (per-band k, 2D, beacon) take this config"""
+    return bool(load_library().t3c_super_path_available(C.byref(cfg)))
 
 
 def _p(a: np.ndarray):

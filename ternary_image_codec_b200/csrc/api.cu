@@ -23,6 +23,7 @@ struct t3c_ctx {
     int ev_next = 0;
     DevTables tabs{};
     HeaderCache hdr_cache{};
+    SuperCache sup_cache{};
     void* d_tables = nullptr;
     HostTables* host = nullptr; // host copy of the constant tables (decoder screen constants are derived per call)
     // grow-only device scratch
@@ -188,6 +189,11 @@ t3c_status t3c_create(int device, t3c_ctx** out)
     ctx->tabs.hdr = &ctx->hdr_cache;
     if (cudaMalloc((void**)&ctx->hdr_cache.d52, 128) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
     ctx->hdr_cache.d27 = ctx->hdr_cache.d52 + 64;
+    ctx->tabs.sup = &ctx->sup_cache;
+    for (auto& sl : ctx->sup_cache.slot) {
+        if (cudaMalloc((void**)&sl.d_map, 3 * 64 * 32 * sizeof(uint16_t) + 256) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
+        sl.d_kv = reinterpret_cast<uint8_t*>(sl.d_map + 3 * 64 * 32);
+    }
     *out = ctx;
     return T3C_OK;
 }
@@ -200,6 +206,7 @@ void t3c_destroy(t3c_ctx* ctx)
     for (auto& b : ctx->buf) if (b.p) cudaFree(b.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->hdr_cache.d52) cudaFree(ctx->hdr_cache.d52);
+    for (auto& sl : ctx->sup_cache.slot) if (sl.d_map) cudaFree(sl.d_map);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -222,6 +229,7 @@ t3c_status t3c_sync(t3c_ctx* ctx)
 }
 size_t t3c_profile_words(const t3c_config* cfg, size_t n_raw_words) { return cfg ? profile_words(*cfg, n_raw_words) : 0; }
 int t3c_fast_path_available(const t3c_config* cfg) { return cfg && fast_path_ok(*cfg) ? 1 : 0; }
+int t3c_super_path_available(const t3c_config* cfg) { return cfg && super_path_ok(*cfg) ? 1 : 0; }
 
 // =============================================================================================
 // device-pointer API
@@ -283,6 +291,12 @@ t3c_status t3c_encode_profile_dev(t3c_ctx* ctx, const t3c_config* cfg, int arith
         n = launch_encode_words_fast(ctx->tabs, g, d_raw, d_out, s, &n_full);
         if (n < 0) { n = 0; n_full = 0; }
     }
+    else if (super_path_ok(*cfg)) { // per-band k / 2D / beacon: the super-tile kernels code the full super-tiles, the general kernel the rest
+        SuperTail tail;
+        n = launch_encode_super(ctx->tabs, *cfg, g, d_raw, 9 * n_words, true, 2 * n_words, 1, d_out, g.n_out, s, &tail);
+        n += launch_encode_general_from(ctx->tabs, *cfg, g, d_raw, d_out, s, tail.cs);
+        return check_launch(ctx, n);
+    }
     n += launch_encode_general(ctx->tabs, *cfg, g, d_raw, d_out, s, 13ull * n_full); // the ragged rest (or everything), header, padding
     return check_launch(ctx, n);
 }
@@ -309,6 +323,14 @@ t3c_status t3c_decode_profile_fixed_dev(t3c_ctx* ctx, const t3c_config* cfg, siz
         const int k = launch_decode_words_fast(ctx->tabs, g, d_in, d_out, (size_t)nw, d_status, s, &n_full);
         if (k < 0) n_full = 0; else n += k;
     }
+    else if (super_path_ok(*cfg)) {
+        SuperTail tail;
+        n += launch_decode_super(ctx->tabs, *cfg, g, d_in, g.n_out, 1, d_out, 9 * (size_t)nw, true, 2 * (size_t)nw, d_status, s, &tail);
+        for (int b = 0; b < 9; ++b) if (pitch > tail.m_start) CU(cudaMemsetAsync(sy + b * pitch + tail.m_start, 0, pitch - tail.m_start, s));
+        n += launch_decode_fixed_general_from(ctx->tabs, g, d_in, sy, pitch, d_status, s, tail.cs);
+        n += launch_regroup_words(sy, g.n_s, g.tile_area, g.tile_w, d_out, (size_t)nw, s, (size_t)(3 * tail.unit_start), pitch);
+        return check_launch(ctx, n);
+    }
     const uint64_t m_done = 13ull * n_full * (uint64_t)g.uniform_k; // symbols per band already turned into words by the tiled kernels
     for (int b = 0; b < 9; ++b) if (pitch > m_done) CU(cudaMemsetAsync(sy + b * pitch + m_done, 0, pitch - m_done, s));
     n += launch_decode_fixed_general(ctx->tabs, g, d_in, sy, pitch, d_status, s, 13ull * n_full);
@@ -331,6 +353,29 @@ t3c_status t3c_encode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, int a
         const int n = launch_encode_rgb_fast(ctx->tabs, *cfg, g, d_rgb, n_px, n_frames, d_out, stride_words, s);
         if (n >= 0) return check_launch(ctx, n);
         // unaligned buffers: fall through to the general kernels
+    }
+    if (cfg->profile != T3C_PROFILE_RAW && super_path_ok(*cfg)) { // per-band k / 2D / beacon: super-tile kernels + general kernels on the ragged rest
+        Geom g;
+        make_geom(*cfg, n_words, arith, g);
+        SuperTail tail;
+        const int ns = launch_encode_super(ctx->tabs, *cfg, g, d_rgb, 3 * n_px, false, n_px, n_frames, d_out, stride_words, s, &tail);
+        if (ns > 0) {
+            TRY(check_launch(ctx, ns));
+            const size_t px0 = 6 * (size_t)tail.unit_start, n_tail = n_px - px0, w_tail = (n_tail + 1) / 2; // px0 is even: whole words
+            t3c_pixel* q = nullptr;
+            uint8_t* raw = nullptr;
+            TRY(reserve_t(ctx, B_AUX, 6 * n_tail + 64, &q));
+            TRY(reserve_t(ctx, B_AUX2, 9 * w_tail + 64, &raw));
+            for (size_t f = 0; f < n_frames; ++f) {
+                int n = launch_rgb_to_quant(d_rgb + 3 * n_px * f + 3 * px0, n_tail, q, s);
+                n += launch_pack_pixels(q, n_tail, raw, s);
+                // the general encoder indexes raw words from the start of the frame: hand it the base the tail words would have there
+                const uint8_t* raw0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(raw) - 9 * (px0 / 2));
+                n += launch_encode_general_from(ctx->tabs, *cfg, g, raw0, d_out + 9 * stride_words * f, s, tail.cs);
+                TRY(check_launch(ctx, n));
+            }
+            return T3C_OK;
+        }
     }
     // general path: per frame K1 (bridge, pack) into scratch, then the general profile encoder
     t3c_pixel* q = nullptr;
@@ -366,6 +411,25 @@ t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, const
         fast_check_constants(*ctx->host, g, chk_nz, chk_two);
         const int n = launch_decode_rgb_fast(ctx->tabs, *cfg, g, d_in, stride_words, n_frames, n_px, px_out, d_rgb, d_status, s, chk_nz, chk_two);
         if (n >= 0) return check_launch(ctx, n);
+    }
+    if (super_path_ok(*cfg)) {
+        SuperTail tail;
+        const int ns = launch_decode_super(ctx->tabs, *cfg, g, d_in, stride_words, n_frames, d_rgb, 3 * n_px, false, px_out, d_status, s, &tail);
+        if (ns > 0) {
+            TRY(check_launch(ctx, ns));
+            // the ragged rest: band symbols from m_start on, in a band-major scratch addressed as if it started at symbol 0
+            const uint64_t pitch_all = (g.n_s + 8) / 9, pitch_t = pitch_all - tail.m_start;
+            uint8_t* syt = nullptr;
+            TRY(reserve_t(ctx, B_TMP, 9 * pitch_t + 16, &syt));
+            uint8_t* sy0 = reinterpret_cast<uint8_t*>(reinterpret_cast<uintptr_t>(syt) - tail.m_start);
+            for (size_t f = 0; f < n_frames; ++f) {
+                CU(cudaMemsetAsync(syt, 0, 9 * pitch_t + 16, s));
+                int n = launch_decode_fixed_general_from(ctx->tabs, g, d_in + 9 * stride_words * f, sy0, pitch_t, d_status + 2 * f, s, tail.cs);
+                n += launch_regroup_rgb(sy0, g.n_s, g.tile_area, g.tile_w, d_rgb + 3 * n_px * f, px_out, s, pitch_t, 6 * (size_t)tail.unit_start);
+                TRY(check_launch(ctx, n));
+            }
+            return T3C_OK;
+        }
     }
     uint8_t* sy = nullptr;
     const uint64_t pitch = (g.n_s + 8) / 9;

@@ -13,6 +13,7 @@
 // transpose and all table look-ups stay in shared memory, the grid is persistent (SM count x resident CTAs)
 // so the row table is staged once per CTA, and HBM traffic is exactly the algorithmic 3 B/px + 9 B/word.
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <type_traits>
@@ -655,43 +656,46 @@ __device__ __forceinline__ void warp_range(uint64_t total, uint32_t gw, uint32_t
     hi = (uint32_t)(total * (gw + 1) / nw);
 }
 
-// ---- encode phase A: six pixels (18 bytes at IN + pad + 18u) -> 26 stream symbols (x4) at S + 26u
+// ---- encode phase A: six pixels (18 bytes at U + a) -> 26 stream symbols (x4) at d
+template <bool ODD>
+__device__ __forceinline__ void enc_unit_rgb(const uint8_t* U, uint32_t a, uint8_t* dst)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
+    const uint32_t sh = (a & 3u) * 8u;
+    uint32_t x[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) x[j] = mw[j];
+    uint32_t y[5]; // the 18 bytes, word aligned
+#pragma unroll
+    for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+    if constexpr (ODD) y[4] = __funnelshift_r(x[4], sh == 24 ? mw[5] : 0u, sh); // 18 bytes from byte offset 3 reach into a sixth word
+    else y[4] = x[4] >> sh;
+    uint32_t A[6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        const int q = 3 * p;
+        A[p] = rgb_to_value3(byte_magic(y[q >> 2], q & 3), byte_magic(y[(q + 1) >> 2], (q + 1) & 3), byte_magic(y[(q + 2) >> 2], (q + 2) & 3));
+    }
+    uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
+    triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
+    triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
+    w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
+    d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
+    d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
+    d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+}
 template <int K, bool ODD>
 __device__ __forceinline__ void enc_phase_a_impl(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
 {
     using L = Cfg3<K>;
-    // ---- phase A: six pixels (18 bytes) -> 26 stream symbols (x4) per lane; units dealt even / odd so that the
-    // 18- and 26-byte lane strides become 36 and 52 bytes: 9 and 13 words, conflict-free
+    // units dealt even / odd so that the 18- and 26-byte lane strides become 36 and 52 bytes: 9 and 13 words, conflict-free
 #pragma unroll 1
     for (int pass = 0; pass < L::PASS_A; ++pass) {
         const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
         if (u >= L::UNITS) continue;
-        const uint32_t a = pad + 18u * (uint32_t)u;
-        const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
-        const uint32_t sh = (a & 3u) * 8u;
-        uint32_t x[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) x[j] = mw[j];
-        uint32_t y[5]; // the 18 bytes, word aligned
-#pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-        if constexpr (ODD) y[4] = __funnelshift_r(x[4], sh == 24 ? mw[5] : 0u, sh); // 18 bytes from byte offset 3 reach into a sixth word
-        else y[4] = x[4] >> sh;
-        uint32_t A[6];
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-            const int q = 3 * p;
-            A[p] = rgb_to_value3(byte_magic(y[q >> 2], q & 3), byte_magic(y[(q + 1) >> 2], (q + 1) & 3), byte_magic(y[(q + 2) >> 2], (q + 2) & 3));
-        }
-        uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
-        triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
-        triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
-        w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
-        uint16_t* d = reinterpret_cast<uint16_t*>(S + 26 * u);
-        d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
-        d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
-        d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
-        d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+        enc_unit_rgb<ODD>(U, pad + 18u * (uint32_t)u, S + 26 * u);
     }
 }
 // frames that start on an odd byte (odd pixel counts, several frames per call) put pixel units at byte offset 3 of a word
@@ -699,6 +703,35 @@ template <int K>
 __device__ __forceinline__ void enc_phase_a(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
 {
     if (pad & 1u) enc_phase_a_impl<K, true>(U, pad, S, lane); else enc_phase_a_impl<K, false>(U, pad, S, lane);
+}
+// ---- one codeword of encode phase B: K data symbols (x4) gathered at byte stride 9 from src -> 26 scrambled symbols at dst (even address).
+// pa = shared address of the codeword's table variant {A[K][27] | B[K][27]}; pat = the scrambler on the parity symbols, plane domain
+template <int K>
+__device__ __forceinline__ void enc_cw(const uint8_t* src, uint8_t* dst, uint32_t pa, uint32_t pat_nz, uint32_t pat_two)
+{
+    constexpr int R = 26 - K, PLANE = 4 * K * 27;
+    Planes acc{0, 0}, acc2{0, 0};
+    uint32_t prev = 0, pk[K / 2];
+    static_for<0, K>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const uint32_t d4 = src[9 * i];
+        const uint32_t ra = pa + d4;
+        const uint32_t ea = lds_tab<108 * i>(ra), eb = lds_tab<108 * i + PLANE>(ra);
+        if (i & 1) { gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
+        else { gf3_add(acc, ea, eb); prev = ea; }
+    });
+    gf3_add(acc, acc2.nz, acc2.two);
+    gf3_add(acc, pat_nz, pat_two);
+    const uint32_t nzp = acc.nz >> 8, twp = acc.two >> 8;
+    const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
+#pragma unroll
+    for (int j = 0; j < K / 2; ++j) *reinterpret_cast<uint16_t*>(dst + 2 * j) = (uint16_t)pk[j]; // stores after all loads: nothing to order
+    *reinterpret_cast<uint16_t*>(dst + K) = (uint16_t)lo;
+    if (R > 2) *reinterpret_cast<uint16_t*>(dst + K + 2) = (uint16_t)(lo >> 16);
+    if (R > 4) {
+        const uint32_t hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
+        *reinterpret_cast<uint16_t*>(dst + K + 4) = (uint16_t)hi;
+    }
 }
 // ---- encode phase B: stream symbols -> nine staged runs (data scrambled through the table bytes, parity through the planes)
 template <int K>
@@ -717,27 +750,51 @@ __device__ __forceinline__ void enc_phase_b(const uint8_t* S, uint8_t* U, const 
         asm volatile("" : "+r"(pa));                                   // keep the variant base in a register
         const uint8_t* src = S + cw + (9 * K - 9) * cl;                 // 9K*cl + b
         uint8_t* dst = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
-        Planes acc{0, 0}, acc2{0, 0};
-        uint32_t prev = 0, pk[K / 2];
-        static_for<0, K>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            const uint32_t d4 = src[9 * i];
-            const uint32_t ra = pa + d4;
-            const uint32_t ea = lds_tab<108 * i>(ra), eb = lds_tab<108 * i + L::ENC_PLANE>(ra);
-            if (i & 1) { gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
-            else { gf3_add(acc, ea, eb); prev = ea; }
-        });
-        gf3_add(acc, acc2.nz, acc2.two);
-        gf3_add(acc, pat[2 * v], pat[2 * v + 1]);
-        const uint32_t nzp = acc.nz >> 8, twp = acc.two >> 8;
-        const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
+        enc_cw<K>(src, dst, pa, pat[2 * v], pat[2 * v + 1]);
+    }
+}
+// ---- one codeword of decode phase B: 26 received symbols (x4) at src (even address) -> syndrome screen / slow path ->
+// K descrambled data symbols scattered at byte stride 9 from dst.  pa = shared address of the variant block {A[26][32] | B[26][32]}
+// (256-byte aligned), tab_v = the same block as a pointer, chk = the clean-codeword constant of the variant
+template <int K>
+__device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, uint32_t chk_nz, uint32_t chk_two,
+                                       const GfTables& sg, uint32_t* status, bool count = true)
+{
+    constexpr int PLANE = 4 * 26 * 32;
+    // the codeword's 26 symbols as 7 words (it starts on an even byte), then one PRMT per symbol builds the
+    // table address: byte 0 = symbol x4, bytes 1..3 = the variant block's address
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 2u) * 8u;
+    uint32_t xw[7];
 #pragma unroll
-        for (int j = 0; j < K / 2; ++j) *reinterpret_cast<uint16_t*>(dst + 2 * j) = (uint16_t)pk[j]; // stores after all loads: nothing to order
-        *reinterpret_cast<uint16_t*>(dst + K) = (uint16_t)lo;
-        if (L::R > 2) *reinterpret_cast<uint16_t*>(dst + K + 2) = (uint16_t)(lo >> 16);
-        if (L::R > 4) {
-            const uint32_t hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
-            *reinterpret_cast<uint16_t*>(dst + K + 4) = (uint16_t)hi;
+    for (int j = 0; j < 7; ++j) xw[j] = mw[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xw[j] = __funnelshift_r(xw[j], xw[j + 1], sh);
+    xw[6] >>= sh;
+    Planes acc{0, 0}, acc2{0, 0};
+    uint32_t ev[K];
+    static_for<0, 26>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
+        const uint32_t ea = lds_tab<128 * i>(ra);
+        const uint32_t eb = lds_tab<128 * i + PLANE>(ra);
+        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        if (i < K) ev[i < K ? i : 0] = ea;
+    });
+#pragma unroll
+    for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
+    gf3_add(acc, acc2.nz, acc2.two);
+    if (((acc.nz ^ chk_nz) | (acc.two ^ chk_two)) & ~0xFFu) { // the low bytes carry the embedded symbols
+        // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
+        uint8_t cwd[26], orig[26];
+        for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tab_v + src[i] + 128 * i);
+        if (!rs_decode_thread(sg, cwd, K, true)) {
+            atomicExch(&status[0], 0u);
+        } else {
+            uint32_t nfix = 0;
+            for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
+            if (nfix && count) atomicAdd(&status[1], nfix);
+            for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
         }
     }
 }
@@ -758,45 +815,35 @@ __device__ __forceinline__ void dec_phase_b(const uint8_t* U, uint8_t* S, const 
         asm volatile("" : "+r"(pa));
         const uint8_t* src = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
         uint8_t* dst = S + cw + (9 * K - 9) * cl;                       // 9K*cl + b
-        // the codeword's 26 symbols as 7 words (it starts on an even byte), then one PRMT per symbol builds the
-        // table address: byte 0 = symbol x4, bytes 1..3 = the variant block's address
-        const uint32_t* mw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-        const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 2u) * 8u;
-        uint32_t xw[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) xw[j] = mw[j];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) xw[j] = __funnelshift_r(xw[j], xw[j + 1], sh);
-        xw[6] >>= sh;
-        Planes acc{0, 0}, acc2{0, 0};
-        uint32_t ev[K];
-        static_for<0, 26>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
-            const uint32_t ea = lds_tab<128 * i>(ra);
-            const uint32_t eb = lds_tab<128 * i + L::DEC_PLANE>(ra);
-            if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
-            if (i < K) ev[i < K ? i : 0] = ea;
-        });
-#pragma unroll
-        for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
-        gf3_add(acc, acc2.nz, acc2.two);
-        if (((acc.nz ^ chk[2 * v]) | (acc.two ^ chk[2 * v + 1])) & ~0xFFu) { // the low bytes carry the embedded symbols
-            // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
-            uint8_t cwd[26], orig[26];
-            for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tabA + v * L::DEC_VAR + src[i] + 128 * i);
-            if (!rs_decode_thread(sg, cwd, K, true)) {
-                atomicExch(&status[0], 0u);
-            } else {
-                uint32_t nfix = 0;
-                for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
-                if (nfix) atomicAdd(&status[1], nfix);
-                for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
-            }
-        }
+        dec_cw<K>(src, dst, pa, tabA + v * L::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
     }
 }
-// ---- decode phase A: 26 stream symbols at S + 26u -> six pixels -> 18 RGB bytes at U + pad + 18u
+// ---- decode phase A: 26 stream symbols at src (even address) -> six pixels -> 18 RGB bytes at dst (even address)
+__device__ __forceinline__ void dec_unit_rgb(const uint8_t* S, uint32_t a, uint8_t* dst)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+    const uint32_t sh = (a & 2u) * 8u;
+    uint32_t x[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) x[j] = mw[j];
+    uint32_t y[7]; // the 26 symbols, word aligned
+#pragma unroll
+    for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+    y[6] = x[6] >> sh;
+    uint32_t A[6];
+    symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+    symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+    uint32_t p[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) p[q] = value_to_rgb3(A[q]);
+    uint16_t* dh = reinterpret_cast<uint16_t*>(dst);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { // two pixels = three halfwords
+        dh[3 * q] = (uint16_t)p[2 * q];
+        dh[3 * q + 1] = (uint16_t)((p[2 * q] >> 16) | (p[2 * q + 1] << 8));
+        dh[3 * q + 2] = (uint16_t)(p[2 * q + 1] >> 8);
+    }
+}
 template <int K>
 __device__ __forceinline__ void dec_phase_a(const uint8_t* S, uint8_t* U, uint32_t pad, int lane)
 {
@@ -805,35 +852,60 @@ __device__ __forceinline__ void dec_phase_a(const uint8_t* S, uint8_t* U, uint32
     for (int pass = 0; pass < L::PASS_A; ++pass) {
         const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
         if (u >= L::UNITS) continue;
-        const uint32_t a = 26u * (uint32_t)u;
-        const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
-        const uint32_t sh = (a & 2u) * 8u;
-        uint32_t x[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) x[j] = mw[j];
-        uint32_t y[7]; // the 26 symbols, word aligned
-#pragma unroll
-        for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-        y[6] = x[6] >> sh;
-        uint32_t A[6];
-        symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
-        symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
-        uint32_t p[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) p[q] = value_to_rgb3(A[q]);
-        uint16_t* dh = reinterpret_cast<uint16_t*>(U + pad + 18 * u); // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { // two pixels = three halfwords
-            dh[3 * q] = (uint16_t)p[2 * q];
-            dh[3 * q + 1] = (uint16_t)((p[2 * q] >> 16) | (p[2 * q + 1] << 8));
-            dh[3 * q + 2] = (uint16_t)(p[2 * q + 1] >> 8);
-        }
+        dec_unit_rgb(S, 26u * (uint32_t)u, U + pad + 18 * u); // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
     }
 }
 
 // ---- raw-word front end (encode_profile_from_raw's own input, OLD:1051-1082): three Word27 (27 bytes at IN + pad + 27u) ->
 // six 13-trit pixel values -> 26 stream symbols (x4) at S + 26u.  The regroup keeps the first 26 trits of every word, which
 // are exactly the two 13-trit halves; bytes >= 27 read as their low three trits (unpack3, OLD:28-31).
+__device__ __forceinline__ void enc_unit_words(const uint8_t* U, uint32_t a, uint8_t* dst)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
+    const uint32_t sh = (a & 3u) * 8u;
+    uint32_t x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = mw[j];
+    uint32_t y[7]; // the 27 bytes, word aligned
+#pragma unroll
+    for (int j = 0; j < 7; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+    y[6] &= 0x00FFFFFFu;
+    uint32_t wild = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) wild |= ((y[j] & 0x7F7F7F7Fu) + 0x65656565u) | y[j]; // bit 7 of a byte set <=> byte >= 27
+    if (wild & 0x80808080u) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            uint32_t r = 0;
+            for (int q = 0; q < 4; ++q) r |= (((y[j] >> (8 * q)) & 0xFFu) % 27u) << (8 * q);
+            y[j] = r;
+        }
+    }
+    auto val4 = [](uint32_t w) { return __dp4a(w, 0x00001B01u, 0u) + 729u * __dp4a(w, 0x1B010000u, 0u); };
+    uint32_t A[6];
+#pragma unroll
+    for (int w = 0; w < 3; ++w) { // word w = bytes 9w .. 9w+8
+        const int o = 9 * w;
+        auto word_at = [&](int b) { return (b & 3) ? __funnelshift_r(y[b >> 2], y[(b >> 2) + 1 > 6 ? 6 : (b >> 2) + 1], 8 * (b & 3)) : y[b >> 2]; };
+        const uint32_t lo4 = word_at(o), s4 = word_at(o + 4) & 0xFFu;
+        uint32_t hi4 = word_at(o + 5);
+        if (w == 2) hi4 = (y[5] >> 24) | (y[6] << 8);                   // bytes 23..26 (word_at would read past y[6])
+        const uint32_t s8 = hi4 >> 24, q8 = __umulhi(s8, 477218589u);      // the 27th trit is dropped: s8 % 9
+        hi4 = (hi4 & 0x00FFFFFFu) | ((s8 - 9u * q8) << 24);
+        const uint32_t q4 = __umulhi(s4, 1431655766u);                     // s4 / 3
+        A[2 * w] = val4(lo4) + 531441u * (s4 - 3u * q4);
+        A[2 * w + 1] = q4 + 9u * val4(hi4);
+    }
+    uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
+    triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
+    triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
+    w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2;
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
+    d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
+    d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
+    d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+}
 template <int K>
 __device__ __forceinline__ void enc_phase_a_words(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
 {
@@ -842,55 +914,36 @@ __device__ __forceinline__ void enc_phase_a_words(const uint8_t* U, uint32_t pad
     for (int pass = 0; pass < L::PASS_A; ++pass) {
         const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
         if (u >= L::UNITS) continue;
-        const uint32_t a = pad + 27u * (uint32_t)u;
-        const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
-        const uint32_t sh = (a & 3u) * 8u;
-        uint32_t x[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = mw[j];
-        uint32_t y[7]; // the 27 bytes, word aligned
-#pragma unroll
-        for (int j = 0; j < 7; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-        y[6] &= 0x00FFFFFFu;
-        uint32_t wild = 0;
-#pragma unroll
-        for (int j = 0; j < 7; ++j) wild |= ((y[j] & 0x7F7F7F7Fu) + 0x65656565u) | y[j]; // bit 7 of a byte set <=> byte >= 27
-        if (wild & 0x80808080u) {
-#pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                uint32_t r = 0;
-                for (int q = 0; q < 4; ++q) r |= (((y[j] >> (8 * q)) & 0xFFu) % 27u) << (8 * q);
-                y[j] = r;
-            }
-        }
-        auto val4 = [](uint32_t w) { return __dp4a(w, 0x00001B01u, 0u) + 729u * __dp4a(w, 0x1B010000u, 0u); };
-        uint32_t A[6];
-#pragma unroll
-        for (int w = 0; w < 3; ++w) { // word w = bytes 9w .. 9w+8
-            const int o = 9 * w;
-            auto word_at = [&](int b) { return (b & 3) ? __funnelshift_r(y[b >> 2], y[(b >> 2) + 1 > 6 ? 6 : (b >> 2) + 1], 8 * (b & 3)) : y[b >> 2]; };
-            const uint32_t lo4 = word_at(o), s4 = word_at(o + 4) & 0xFFu;
-            uint32_t hi4 = word_at(o + 5);
-            if (w == 2) hi4 = (y[5] >> 24) | (y[6] << 8);                   // bytes 23..26 (word_at would read past y[6])
-            const uint32_t s8 = hi4 >> 24, q8 = __umulhi(s8, 477218589u);      // the 27th trit is dropped: s8 % 9
-            hi4 = (hi4 & 0x00FFFFFFu) | ((s8 - 9u * q8) << 24);
-            const uint32_t q4 = __umulhi(s4, 1431655766u);                     // s4 / 3
-            A[2 * w] = val4(lo4) + 531441u * (s4 - 3u * q4);
-            A[2 * w + 1] = q4 + 9u * val4(hi4);
-        }
-        uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
-        triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
-        triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
-        w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2;
-        uint16_t* d = reinterpret_cast<uint16_t*>(S + 26 * u);
-        d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
-        d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
-        d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
-        d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+        enc_unit_words(U, pad + 27u * (uint32_t)u, S + 26 * u);
     }
 }
-// ---- raw-word back end (the regroup of decode_profile_to_raw, OLD:1022-1039): 26 stream symbols at S + 26u -> six pixel
-// values -> three Word27 (27 bytes, T[26] = 0) at U + pad + 27u
+// ---- raw-word back end (the regroup of decode_profile_to_raw, OLD:1022-1039): 26 stream symbols at S + a -> six pixel
+// values -> three Word27 (27 bytes, T[26] = 0) at d
+__device__ __forceinline__ void dec_unit_words(const uint8_t* S, uint32_t a, uint8_t* d)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+    const uint32_t sh = (a & 2u) * 8u;
+    uint32_t x[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) x[j] = mw[j];
+    uint32_t y[7];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+    y[6] = x[6] >> sh;
+    uint32_t A[6];
+    symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+    symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+#pragma unroll
+    for (int w = 0; w < 3; ++w) { // pack_two_pixels on values: s0..s3 | trit 12 + 3 (Ab % 9) | digits of Ab / 9
+        uint32_t t, q;
+        const uint32_t lo4 = digits4(A[2 * w], t);
+        const uint32_t h = __umulhi(A[2 * w + 1], 477218589u), s4 = t + 3u * (A[2 * w + 1] - 9u * h);
+        const uint32_t hi4 = digits4(h, q);
+        uint8_t* o = d + 9 * w; // arbitrary alignment: bytes
+        o[0] = (uint8_t)lo4; o[1] = (uint8_t)(lo4 >> 8); o[2] = (uint8_t)(lo4 >> 16); o[3] = (uint8_t)(lo4 >> 24); o[4] = (uint8_t)s4;
+        o[5] = (uint8_t)hi4; o[6] = (uint8_t)(hi4 >> 8); o[7] = (uint8_t)(hi4 >> 16); o[8] = (uint8_t)(hi4 >> 24);
+    }
+}
 template <int K>
 __device__ __forceinline__ void dec_phase_a_words(const uint8_t* S, uint8_t* U, uint32_t pad, int lane)
 {
@@ -899,30 +952,7 @@ __device__ __forceinline__ void dec_phase_a_words(const uint8_t* S, uint8_t* U, 
     for (int pass = 0; pass < L::PASS_A; ++pass) {
         const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
         if (u >= L::UNITS) continue;
-        const uint32_t a = 26u * (uint32_t)u;
-        const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
-        const uint32_t sh = (a & 2u) * 8u;
-        uint32_t x[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) x[j] = mw[j];
-        uint32_t y[7];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-        y[6] = x[6] >> sh;
-        uint32_t A[6];
-        symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
-        symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
-        uint8_t* d = U + pad + 27 * u;
-#pragma unroll
-        for (int w = 0; w < 3; ++w) { // pack_two_pixels on values: s0..s3 | trit 12 + 3 (Ab % 9) | digits of Ab / 9
-            uint32_t t, q;
-            const uint32_t lo4 = digits4(A[2 * w], t);
-            const uint32_t h = __umulhi(A[2 * w + 1], 477218589u), s4 = t + 3u * (A[2 * w + 1] - 9u * h);
-            const uint32_t hi4 = digits4(h, q);
-            uint8_t* o = d + 9 * w; // arbitrary alignment: bytes
-            o[0] = (uint8_t)lo4; o[1] = (uint8_t)(lo4 >> 8); o[2] = (uint8_t)(lo4 >> 16); o[3] = (uint8_t)(lo4 >> 24); o[4] = (uint8_t)s4;
-            o[5] = (uint8_t)hi4; o[6] = (uint8_t)(hi4 >> 8); o[7] = (uint8_t)(hi4 >> 16); o[8] = (uint8_t)(hi4 >> 24);
-        }
+        dec_unit_words(S, 26u * (uint32_t)u, U + pad + 27 * u);
     }
 }
 
@@ -1508,7 +1538,101 @@ uint32_t full_tiles(const Geom& g, uint64_t px_limit)
     return (uint32_t)n;
 }
 
+#include "k_super.cuh"
+
 } // namespace
+
+// ---- super-tile kernels: launchers ------------------------------------------------------------
+bool super_path_ok(const t3c_config& cfg) { return super_config_ok(cfg); }
+
+static void super_tail_all(SuperTail* tail)
+{
+    for (int b = 0; b < 9; ++b) tail->cs.c[b] = 0;
+    tail->m_start = 0;
+    tail->unit_start = 0;
+}
+// plan + pass maps (cached on the device per kernel flavour); false = the super-tile kernels do not apply
+static bool super_prepare(const DevTables& T, const t3c_config& cfg, const Geom& g, bool decode, bool words, uint64_t px_limit, cudaStream_t st, SuperPlan& P,
+                          SuperTail* tail)
+{
+    super_tail_all(tail);
+    if (!T.sup) return false;
+    static thread_local uint16_t h_map[3 * SUP_MAX_PASS * 32];
+    static thread_local uint8_t h_kv[3 * SUP_MAX_PASS];
+    if (!make_super_plan(cfg, g, decode, words, px_limit, P, h_map, h_kv)) return false;
+    SuperCache::Slot& C = T.sup->slot[(decode ? 2 : 0) + (words ? 1 : 0)];
+    if (!C.d_map) return false;
+    uint8_t key[48] = {};
+    for (int b = 0; b < 9; ++b) { key[b] = (uint8_t)g.k[b]; key[9 + b] = (uint8_t)(g.cw_base[b] % 3); }
+    std::memcpy(key + 20, &P.M, 4);
+    if (!C.valid || std::memcmp(C.key, key, sizeof key) != 0) {
+        cudaStreamSynchronize(st); // once per config change: kernels in flight may still read the old maps
+        cudaMemcpy(C.d_map, h_map, sizeof h_map, cudaMemcpyHostToDevice);
+        cudaMemcpy(C.d_kv, h_kv, sizeof h_kv, cudaMemcpyHostToDevice);
+        std::memcpy(C.key, key, sizeof key);
+        C.valid = true;
+    }
+    P.map = C.d_map;
+    P.pass_kv = C.d_kv;
+    for (int b = 0; b < 9; ++b) tail->cs.c[b] = (uint64_t)P.ncw[P.kslot[b]] * P.n_tiles;
+    tail->m_start = (uint64_t)P.M * P.n_tiles;
+    tail->unit_start = (uint64_t)P.UN * P.n_tiles;
+    return true;
+}
+template <class Kern>
+static int super_launch(Kern kern, const DevTables& T, const FastParams& Q, const SuperPlan& P, const Geom& g, cudaStream_t st)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, uint32_t> opted; // largest dynamic shared memory opted in per (kernel, device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        uint32_t& cur = opted[{reinterpret_cast<const void*>(kern), dev}];
+        if (cur < P.smem_bytes) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem_bytes) != cudaSuccess) return -1;
+            cur = P.smem_bytes;
+        }
+    }
+    const uint64_t total = (uint64_t)P.n_tiles * Q.n_frames;
+    uint64_t grid = 2ull * (uint64_t)T.sm_count;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, SUP_TPB, P.smem_bytes, st>>>(Q, P, g, T.gf, T.rs);
+    return 1;
+}
+int launch_encode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in, size_t in_pitch, bool words, size_t n_px,
+                        size_t n_frames, uint8_t* out9, size_t stride_words, cudaStream_t st, SuperTail* tail)
+{
+    super_tail_all(tail);
+    if ((((uintptr_t)in | (uintptr_t)out9) & 15) || !n_frames) return 0;      // 128-bit transfers need 16-byte aligned buffer bases
+    if (n_frames > 1 && (stride_words & 1)) return 0;                           // every frame's body must start on an even byte
+    SuperPlan P;
+    if (!super_prepare(T, cfg, g, false, words, n_px < 2 * g.n_words ? n_px : 2 * g.n_words, st, P, tail)) return 0;
+    FastParams Q{};
+    Q.in = in; Q.out = out9;
+    Q.in_stride = in_pitch; Q.out_stride = 9ull * stride_words;
+    Q.n_frames = (uint32_t)n_frames;
+    const int n = words ? super_launch(k_encode_super<true>, T, Q, P, g, st) : super_launch(k_encode_super<false>, T, Q, P, g, st);
+    if (n <= 0) { super_tail_all(tail); return 0; }
+    return n;
+}
+int launch_decode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in9, size_t stride_words, size_t n_frames, uint8_t* out,
+                        size_t out_pitch, bool words, size_t n_px_out, uint32_t* d_status, cudaStream_t st, SuperTail* tail)
+{
+    super_tail_all(tail);
+    if ((((uintptr_t)in9 | (uintptr_t)out) & 15) || !n_frames) return 0;
+    if (n_frames > 1 && ((stride_words & 1) || (out_pitch & 1))) return 0;      // codewords and pixel units are read / written in 2-byte pieces
+    SuperPlan P;
+    if (!super_prepare(T, cfg, g, true, words, n_px_out, st, P, tail)) return 0;
+    FastParams Q{};
+    Q.in = in9; Q.out = out;
+    Q.in_stride = 9ull * stride_words; Q.out_stride = out_pitch;
+    Q.n_frames = (uint32_t)n_frames;
+    Q.status = d_status;
+    const int n = words ? super_launch(k_decode_super<true>, T, Q, P, g, st) : super_launch(k_decode_super<false>, T, Q, P, g, st);
+    if (n <= 0) { super_tail_all(tail); return 0; }
+    return n;
+}
 
 bool fast_path_ok(const t3c_config& cfg)
 {

@@ -513,12 +513,12 @@ __global__ void k_header_parse(const GfTables* __restrict__ gf, int fixed, const
 // ------------------------------------------------------------------------------------------
 template <typename I>
 __global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restrict__ raw, uint8_t* __restrict__ out, Geom g,
-                                                        const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, uint64_t cw_start)
+                                                        const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, CwStart cs)
 {
     __shared__ uint64_t row[24 * kVals];
     __shared__ uint8_t stage[TPB * 26];
     const int b = blockIdx.y, k = g.k[b], r = 26 - k;
-    const I c0 = (I)cw_start + (I)blockIdx.x * TPB; // codewords before cw_start of every band were coded by the tiled kernels
+    const I c0 = (I)cs.c[b] + (I)blockIdx.x * TPB; // codewords before cs.c[b] of band b were coded by the tiled kernels
     if (c0 >= (I)g.ncw[b]) return;
     const RowTable& tab = rs->row[g.arith][(24 - k) / 2];
     for (int i = threadIdx.x; i < k * kVals; i += TPB) row[i] = tab.e[i / kVals][i % kVals];
@@ -572,13 +572,13 @@ __global__ void k_frame_misc(uint8_t* __restrict__ out_base, size_t stride_bytes
 // ------------------------------------------------------------------------------------------
 template <typename I>
 __global__ void __launch_bounds__(TPB) k_decode_fixed_general(const uint8_t* __restrict__ in, uint8_t* __restrict__ sy, Geom g,
-                                                              const GfTables* __restrict__ gf, uint32_t* status, uint64_t cw_start, uint64_t pitch)
+                                                              const GfTables* __restrict__ gf, uint32_t* status, CwStart cs, uint64_t pitch)
 {
     __shared__ GfTables sg;
     load_gf(sg, gf);
     __syncthreads();
     const int b = blockIdx.y, k = g.k[b];
-    const I c = (I)cw_start + (I)blockIdx.x * TPB + threadIdx.x;
+    const I c = (I)cs.c[b] + (I)blockIdx.x * TPB + threadIdx.x;
     if (c >= (I)g.ncw[b]) return;
     uint8_t cw[26], orig[26];
     const I p0 = 26 * ((I)g.cw_base[b] + c);
@@ -617,9 +617,9 @@ __global__ void k_regroup_words(const uint8_t* __restrict__ sy, I n_sy, I area, 
     }
 }
 template <typename I>
-__global__ void k_regroup_rgb(const uint8_t* __restrict__ sy, I n_sy, I area, uint32_t tw, uint8_t* __restrict__ rgb, I n_px, I pitch)
+__global__ void k_regroup_rgb(const uint8_t* __restrict__ sy, I n_sy, I area, uint32_t tw, uint8_t* __restrict__ rgb, I n_px, I pitch, I p_start)
 {
-    const I p = (I)blockIdx.x * blockDim.x + threadIdx.x;
+    const I p = p_start + (I)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_px) return;
     uint32_t t[13];
     for (int i = 0; i < 13; ++i) t[i] = stream_trit<I>(sy, n_sy, area, tw, 13 * p + i, pitch);
@@ -764,14 +764,26 @@ int launch_header_parse(const DevTables& T, int arith, const uint8_t* words, siz
     k_header_parse<<<1, 64, 0, st>>>(T.gf, arith, words, n_words, d_cfg, d_ok);
     return 1;
 }
+// most codewords any band still has to code after its start
+static uint64_t cw_left(const Geom& g, const CwStart& cs)
+{
+    uint64_t mx = 0;
+    for (int b = 0; b < 9; ++b) if (g.ncw[b] > cs.c[b] && g.ncw[b] - cs.c[b] > mx) mx = g.ncw[b] - cs.c[b];
+    return mx;
+}
 int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw, uint8_t* out, cudaStream_t st, uint64_t cw_start)
 {
+    CwStart cs;
+    for (int b = 0; b < 9; ++b) cs.c[b] = cw_start;
+    return launch_encode_general_from(T, cfg, g, raw, out, st, cs);
+}
+int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw, uint8_t* out, cudaStream_t st, const CwStart& cs)
+{
     int n = 0;
-    uint64_t mx = 0;
-    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    if (mx > cw_start) {
-        if (small_geom(g)) k_encode_general<uint32_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cw_start);
-        else k_encode_general<uint64_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cw_start);
+    const uint64_t mx = cw_left(g, cs);
+    if (mx) {
+        if (small_geom(g)) k_encode_general<uint32_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cs);
+        else k_encode_general<uint64_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cs);
         ++n;
     }
     // without a beacon the rest of the frame is the (cached) coded header and the zero padding
@@ -813,11 +825,16 @@ int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, 
 }
 int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint64_t pitch, uint32_t* status, cudaStream_t st, uint64_t cw_start)
 {
-    uint64_t mx = 0;
-    for (int b = 0; b < 9; ++b) mx = g.ncw[b] > mx ? g.ncw[b] : mx;
-    if (mx <= cw_start) return 0;
-    if (small_geom(g)) k_decode_fixed_general<uint32_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cw_start, pitch);
-    else k_decode_fixed_general<uint64_t><<<dim3(blocks_for(mx - cw_start, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cw_start, pitch);
+    CwStart cs;
+    for (int b = 0; b < 9; ++b) cs.c[b] = cw_start;
+    return launch_decode_fixed_general_from(T, g, in, sy, pitch, status, st, cs);
+}
+int launch_decode_fixed_general_from(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint64_t pitch, uint32_t* status, cudaStream_t st, const CwStart& cs)
+{
+    const uint64_t mx = cw_left(g, cs);
+    if (!mx) return 0;
+    if (small_geom(g)) k_decode_fixed_general<uint32_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cs, pitch);
+    else k_decode_fixed_general<uint64_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cs, pitch);
     return 1;
 }
 int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* out, size_t n_words, cudaStream_t st, size_t w_start, uint64_t pitch)
@@ -828,12 +845,12 @@ int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32
     else k_regroup_words<uint64_t><<<blocks_for(n_words - w_start, 256), 256, 0, st>>>(sy, n_sy, area, tw, out, (uint64_t)n_words, (uint64_t)w_start, pitch);
     return 1;
 }
-int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* rgb, size_t n_px, cudaStream_t st, uint64_t pitch)
+int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* rgb, size_t n_px, cudaStream_t st, uint64_t pitch, size_t p_start)
 {
-    if (!n_px) return 0;
+    if (n_px <= p_start) return 0;
     if (13 * (uint64_t)n_px + 64 < (1ull << 31) && 3 * n_sy + 64 < (1ull << 31))
-        k_regroup_rgb<uint32_t><<<blocks_for(n_px, 256), 256, 0, st>>>(sy, (uint32_t)n_sy, (uint32_t)area, tw, rgb, (uint32_t)n_px, (uint32_t)pitch);
-    else k_regroup_rgb<uint64_t><<<blocks_for(n_px, 256), 256, 0, st>>>(sy, n_sy, area, tw, rgb, (uint64_t)n_px, pitch);
+        k_regroup_rgb<uint32_t><<<blocks_for(n_px - p_start, 256), 256, 0, st>>>(sy, (uint32_t)n_sy, (uint32_t)area, tw, rgb, (uint32_t)n_px, (uint32_t)pitch, (uint32_t)p_start);
+    else k_regroup_rgb<uint64_t><<<blocks_for(n_px - p_start, 256), 256, 0, st>>>(sy, n_sy, area, tw, rgb, (uint64_t)n_px, pitch, (uint64_t)p_start);
     return 1;
 }
 int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uint8_t* in, uint8_t* use, uint32_t* status, cudaStream_t st)

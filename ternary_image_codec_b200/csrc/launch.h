@@ -10,7 +10,16 @@ namespace t3c {
 // The coded super-frame header depends on the config only: it is emitted on the device (k_header_emit) when the config
 // changes and kept in `d52`; every later frame copies the 52 symbols.
 struct HeaderCache { uint8_t* d52 = nullptr; uint8_t* d27 = nullptr; t3c_config cfg{}; int arith = -1; bool valid = false; };
-struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; };
+// Phase-B pass maps of the super-tile kernels (k_super.cuh): they depend on the per-band k and on cw_base mod 3 only; one slot
+// per kernel flavour (encode / decode x RGB / raw words), re-uploaded when the key changes.
+struct SuperCache {
+    struct Slot { uint16_t* d_map = nullptr; uint8_t* d_kv = nullptr; uint8_t key[48] = {}; bool valid = false; } slot[4];
+};
+struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; SuperCache* sup; };
+// first codeword of every band that the general kernels still have to code (the tiled kernels did the ones before)
+struct CwStart { uint64_t c[9]; };
+// what a super-tile launch leaves to the general kernels: codewords from cs.c[b] on, band symbols from m_start, 6-pixel units from unit_start
+struct SuperTail { CwStart cs; uint64_t m_start; uint64_t unit_start; };
 
 // geometry of the reference decoder as shipped (A.7): slot-major demap of words 6.. of the input
 struct RefDecGeom {
@@ -45,7 +54,18 @@ int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t
 // pitch = 0: sy in stream order; pitch != 0: band-major scratch of launch_decode_fixed_general
 int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* out9, size_t n_words, cudaStream_t st, size_t w_start = 0,
                          uint64_t pitch = 0);
-int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* rgb, size_t n_px, cudaStream_t st, uint64_t pitch = 0);
+int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* rgb, size_t n_px, cudaStream_t st, uint64_t pitch = 0,
+                       size_t p_start = 0);
+int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, const CwStart& cs);
+int launch_decode_fixed_general_from(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* scratch_sy, uint64_t pitch, uint32_t* d_status, cudaStream_t st,
+                                     const CwStart& cs);
+// super-tile kernels (k_super.cuh): per-band k, 2D tiles whose width divides 26, beacon periods 3..255.  They code the full
+// super-tiles of every frame and report what is left in *tail; 0 = not applicable (nothing launched, *tail = everything)
+bool super_path_ok(const t3c_config& cfg);
+int launch_encode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in, size_t in_pitch, bool words, size_t n_px,
+                        size_t n_frames, uint8_t* out9, size_t stride_words, cudaStream_t st, SuperTail* tail);
+int launch_decode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in9, size_t stride_words, size_t n_frames, uint8_t* out,
+                        size_t out_pitch, bool words, size_t n_px_out, uint32_t* d_status, cudaStream_t st, SuperTail* tail);
 int launch_decode_ref_general(const DevTables& T, const RefDecGeom& g, const uint8_t* in9, uint8_t* use, uint32_t* d_status, cudaStream_t st);
 // fused fast path (uniform k, 1D, no beacon): frames batched
 bool fast_path_ok(const t3c_config& cfg);

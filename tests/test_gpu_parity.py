@@ -619,3 +619,72 @@ def test_v6new_raw_path(codec, oracle):
             assert ok and np.array_equal(p.view(np.uint8), oracle.v6new_unpack_pixels(words).view(np.uint8))
     assert codec.v6new_encode_raw_pixels_to_words(px, 24)[0] and not codec.v6new_encode_raw_pixels_to_words(px, 7)[0]
     assert codec.v6new_decode_raw_words_to_pixels(w, 15)[0] and not codec.v6new_decode_raw_words_to_pixels(w, 26)[0]
+
+
+# ------------------------------------------------------------------ super-tile kernels (per-band k, 2D tiles, beacon): k_super.cuh
+SUPER_CONFIGS = [
+    dict(profile=T.P5, tile=(26, 26), beacon=(26, 2, True), uep=T.UEP_LUMA, seed=(2, 1, 1), coset=1),   # BASELINE config 2
+    dict(profile=T.P5, tile=(13, 7), uep=(0, 1, 0, 1, 0, 1, 0, 1, 0), seed=(1, 1, 1)),                   # k = 24/22, two rows per unit
+    dict(profile=T.P5, tile=(2, 5), uep=(2, 2, 0, 0, 2, 2, 0, 0, 2), beacon=(3, 0, True), seed=(1, 2, 2)),  # k = 20/24, shortest period, slot 0
+    dict(profile=T.P5, tile=(26, 5), uep=1, beacon=(255, 8, True), seed=(2, 2, 1)),                      # uniform k, odd tile height, longest period
+    dict(profile=T.P2, uep=(0, 1, 2, 0, 1, 2, 0, 1, 2), beacon=(7, 4, True)),                            # three k values, 1D
+    dict(profile=T.P5, tile=(1, 9), uep=T.UEP_LUMA, beacon=(26, 11, True)),                              # w = 1: identity rows; slot > 8: words completed, no beacon
+    dict(profile=T.P3, uep=2, beacon=(26, 2, True), seed=(0, 1, 2)),
+]
+
+
+@pytest.mark.parametrize("ci", range(len(SUPER_CONFIGS)))
+def test_super_tile_kernels_words(codec, oracle, t3, ci):
+    oc, gc = both(SUPER_CONFIGS[ci])
+    assert t3.super_path_available(gc)
+    r = rng(5000 + ci)
+    add = T.gf_add_table()
+    for n in (3000, 8192, 30011, 70001):
+        raw = r.integers(0, 27, size=(n, 9), dtype=np.uint8)
+        raw[:, 8] %= 9
+        wild = raw.copy()
+        wild[r.integers(0, n, 50), r.integers(0, 9, 50)] = r.integers(27, 256, 50)
+        for arith in (t3.REF_EXACT, t3.FIXED):
+            assert np.array_equal(codec.encode_profile_from_raw(wild, gc, arith), oracle.encode_profile(oc, wild, arith)), (ci, n, arith)
+        enc = codec.encode_profile_from_raw(raw, gc, t3.FIXED)
+        assert np.array_equal(enc, oracle.encode_profile(oc, raw, t3.FIXED))
+        ok, out, nc = codec.decode_profile_fixed(enc, gc, n_raw_words=n)
+        ok_o, out_o, nc_o = oracle.decode_profile_fixed(oc, enc, n_raw_words=n)
+        assert ok and ok_o and nc == nc_o == 0 and np.array_equal(out, out_o) and np.array_equal(out, raw[:out.shape[0]])
+        if not (gc.beacon_enabled and gc.beacon_slot > 8):
+            for exact_t in (False, True):
+                bad, nerr = T.inject_errors(enc, oc, n, seed=5 + exact_t, gf_add=add, exact_t=exact_t)
+                ok3, out3, nc3 = codec.decode_profile_fixed(bad, gc, n_raw_words=n)
+                assert ok3 and np.array_equal(out3, out) and nc3 == nerr and nerr > 0
+            worse = bad.copy().reshape(-1)
+            worse[52 + 26 * 700:52 + 26 * 700 + 12] = (worse[52 + 26 * 700:52 + 26 * 700 + 12] + 1) % 27   # more than t errors inside a super-tile
+            worse[60:70] = r.integers(27, 256, 10)                                                          # out-of-alphabet bytes
+            ok4, out4, _ = codec.decode_profile_fixed(worse.reshape(-1, 9), gc, n_raw_words=n)
+            ok5, out5, _ = oracle.decode_profile_fixed(oc, worse.reshape(-1, 9), n_raw_words=n)
+            assert ok4 == ok5 and np.array_equal(out4, out5)
+
+
+@pytest.mark.parametrize("ci", range(len(SUPER_CONFIGS)))
+@pytest.mark.parametrize("n_px,nf", [(512 * 512, 2), (130 * 77 * 3 + 1, 3), (5940 * 4, 1)])
+def test_super_tile_kernels_rgb_frames(codec, oracle, t3, ci, n_px, nf):
+    oc, gc = both(SUPER_CONFIGS[ci])
+    frames = np.stack([T.synth_rgb(21 + f, n_px) for f in range(nf)])
+    add = T.gf_add_table()
+    for arith in (t3.REF_EXACT, t3.FIXED):
+        got = codec.encode_frames_rgb8(frames, gc, arith)
+        for f in range(nf):
+            assert np.array_equal(got[f], oracle.encode_rgb(oc, frames[f], arith)), (ci, n_px, arith, f)
+    enc = codec.encode_frames_rgb8(frames, gc, t3.FIXED)
+    ok, rgb, nc = codec.decode_frames_rgb8(enc, n_px, gc)
+    assert ok.all() and nc == 0
+    for f in range(nf):
+        ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, enc[f], n_px)
+        assert ok_o and np.array_equal(rgb[f], rgb_o)
+    if not (gc.beacon_enabled and gc.beacon_slot > 8):
+        bad = enc.copy()
+        tot = 0
+        for f in range(nf):
+            bad[f], ne = T.inject_errors(enc[f], oc, (n_px + 1) // 2, seed=31 + f, gf_add=add, exact_t=bool(f & 1))
+            tot += ne
+        ok2, rgb2, nc2 = codec.decode_frames_rgb8(bad, n_px, gc)
+        assert ok2.all() and nc2 == tot and np.array_equal(rgb2, rgb)
