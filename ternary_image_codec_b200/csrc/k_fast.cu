@@ -656,9 +656,53 @@ __device__ __forceinline__ void warp_range(uint64_t total, uint32_t gw, uint32_t
     hi = (uint32_t)(total * (gw + 1) / nw);
 }
 
+// 26 stream symbols of one unit (x4, as produced by two triple_to_symbols) -> shared memory at dst (even address).  REV: units of an
+// odd row of a 26-wide 2D tile leave in reverse order (boustrophedon, OLD:750-780), decided per lane by `rev`
+template <bool REV>
+__device__ __forceinline__ void store_unit26(uint8_t* dst, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t s12, uint32_t v0, uint32_t v1, uint32_t v2,
+                                             uint32_t t12, bool rev)
+{
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst); // 13 halfwords (STS.U16 keeps the low 16 bits)
+    if constexpr (!REV) {
+        d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
+        d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
+        d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
+        d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+    } else {
+        uint32_t x[7] = {w0, w1, w2, s12 | (v0 << 8), __funnelshift_r(v0, v1, 24), __funnelshift_r(v1, v2, 24), (v2 >> 24) | (t12 << 8)};
+        uint32_t z[7];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) z[j] = rev ? __byte_perm(x[5 - j], x[6 - j], 0x2345) : x[j]; // bytes 25-4j .. 22-4j
+        z[6] = rev ? __byte_perm(x[0], 0u, 0x4401) : x[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { d[2 * j] = (uint16_t)z[j]; d[2 * j + 1] = (uint16_t)(z[j] >> 16); }
+        d[12] = (uint16_t)z[6];
+    }
+}
+// the inverse on the way back: 26 symbols at S + a (even) as seven word-aligned registers (y[6]: two symbols)
+template <bool REV>
+__device__ __forceinline__ void load_unit26(const uint8_t* S, uint32_t a, uint32_t (&y)[7], bool rev)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+    const uint32_t sh = (a & 2u) * 8u;
+    uint32_t x[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) x[j] = mw[j];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+    y[6] = x[6] >> sh;
+    if constexpr (REV) {
+        uint32_t z[7];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) z[j] = rev ? __byte_perm(y[5 - j], y[6 - j], 0x2345) : y[j];
+        z[6] = rev ? __byte_perm(y[0], 0u, 0x4401) : y[6];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) y[j] = z[j];
+    }
+}
 // ---- encode phase A: six pixels (18 bytes at U + a) -> 26 stream symbols (x4) at d
-template <bool ODD>
-__device__ __forceinline__ void enc_unit_rgb(const uint8_t* U, uint32_t a, uint8_t* dst)
+template <bool ODD, bool REV = false>
+__device__ __forceinline__ void enc_unit_rgb(const uint8_t* U, uint32_t a, uint8_t* dst, bool rev = false)
 {
     const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
     const uint32_t sh = (a & 3u) * 8u;
@@ -680,11 +724,7 @@ __device__ __forceinline__ void enc_unit_rgb(const uint8_t* U, uint32_t a, uint8
     triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
     triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
     w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
-    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-    d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
-    d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
-    d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
-    d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+    store_unit26<REV>(dst, w0, w1, w2, s12, v0, v1, v2, t12, rev);
 }
 template <int K, bool ODD>
 __device__ __forceinline__ void enc_phase_a_impl(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
@@ -819,17 +859,11 @@ __device__ __forceinline__ void dec_phase_b(const uint8_t* U, uint8_t* S, const 
     }
 }
 // ---- decode phase A: 26 stream symbols at src (even address) -> six pixels -> 18 RGB bytes at dst (even address)
-__device__ __forceinline__ void dec_unit_rgb(const uint8_t* S, uint32_t a, uint8_t* dst)
+template <bool REV = false>
+__device__ __forceinline__ void dec_unit_rgb(const uint8_t* S, uint32_t a, uint8_t* dst, bool rev = false)
 {
-    const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
-    const uint32_t sh = (a & 2u) * 8u;
-    uint32_t x[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) x[j] = mw[j];
     uint32_t y[7]; // the 26 symbols, word aligned
-#pragma unroll
-    for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-    y[6] = x[6] >> sh;
+    load_unit26<REV>(S, a, y, rev);
     uint32_t A[6];
     symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
     symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
@@ -859,7 +893,8 @@ __device__ __forceinline__ void dec_phase_a(const uint8_t* S, uint8_t* U, uint32
 // ---- raw-word front end (encode_profile_from_raw's own input, OLD:1051-1082): three Word27 (27 bytes at IN + pad + 27u) ->
 // six 13-trit pixel values -> 26 stream symbols (x4) at S + 26u.  The regroup keeps the first 26 trits of every word, which
 // are exactly the two 13-trit halves; bytes >= 27 read as their low three trits (unpack3, OLD:28-31).
-__device__ __forceinline__ void enc_unit_words(const uint8_t* U, uint32_t a, uint8_t* dst)
+template <bool REV = false>
+__device__ __forceinline__ void enc_unit_words(const uint8_t* U, uint32_t a, uint8_t* dst, bool rev = false)
 {
     const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
     const uint32_t sh = (a & 3u) * 8u;
@@ -900,11 +935,7 @@ __device__ __forceinline__ void enc_unit_words(const uint8_t* U, uint32_t a, uin
     triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
     triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
     w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2;
-    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-    d[0] = (uint16_t)w0; d[1] = (uint16_t)(w0 >> 16); d[2] = (uint16_t)w1; d[3] = (uint16_t)(w1 >> 16);
-    d[4] = (uint16_t)w2; d[5] = (uint16_t)(w2 >> 16); d[6] = (uint16_t)(s12 | (v0 << 8));
-    d[7] = (uint16_t)(v0 >> 8); d[8] = (uint16_t)__funnelshift_r(v0, v1, 24); d[9] = (uint16_t)(v1 >> 8);
-    d[10] = (uint16_t)__funnelshift_r(v1, v2, 24); d[11] = (uint16_t)(v2 >> 8); d[12] = (uint16_t)((v2 >> 24) | (t12 << 8));
+    store_unit26<REV>(dst, w0, w1, w2, s12, v0, v1, v2, t12, rev);
 }
 template <int K>
 __device__ __forceinline__ void enc_phase_a_words(const uint8_t* U, uint32_t pad, uint8_t* S, int lane)
@@ -919,17 +950,11 @@ __device__ __forceinline__ void enc_phase_a_words(const uint8_t* U, uint32_t pad
 }
 // ---- raw-word back end (the regroup of decode_profile_to_raw, OLD:1022-1039): 26 stream symbols at S + a -> six pixel
 // values -> three Word27 (27 bytes, T[26] = 0) at d
-__device__ __forceinline__ void dec_unit_words(const uint8_t* S, uint32_t a, uint8_t* d)
+template <bool REV = false>
+__device__ __forceinline__ void dec_unit_words(const uint8_t* S, uint32_t a, uint8_t* d, bool rev = false)
 {
-    const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
-    const uint32_t sh = (a & 2u) * 8u;
-    uint32_t x[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) x[j] = mw[j];
     uint32_t y[7];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
-    y[6] = x[6] >> sh;
+    load_unit26<REV>(S, a, y, rev);
     uint32_t A[6];
     symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
     symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);

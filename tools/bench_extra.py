@@ -86,7 +86,7 @@ def uep2d(all_t=False):
     body[idx] = (body[idx] + 1) % 27
     td_err = timeit(D, n=3, warm=1)
     alg = 3 * N_PX + 9 * wpf
-    print(json.dumps({"workload": "uep2d: 8K, P5 2D 26x26 + luma UEP + coset C1 + beacon(26,2), general kernels", "encode_us": te * 1e3,
+    print(json.dumps({"workload": "uep2d: 8K, P5 2D 26x26 + luma UEP + coset C1 + beacon(26,2), super-tile kernels" if t3.super_path_available(cfg) else "uep2d (general kernels)", "encode_us": te * 1e3,
                       "decode_clean_us": td_clean * 1e3, "decode_with_errors_us": td_err * 1e3, "status": status.tolist(),
                       "encode_gbs": alg / te / 1e6, "decode_clean_gbs": alg / td_clean / 1e6, "mpix_per_s_enc_plus_dec_clean": N_PX / (te + td_clean) / 1e3,
                       "profile_words": wpf}))
