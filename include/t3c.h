@@ -157,6 +157,8 @@ T3C_API int t3c_fast_path_available(const t3c_config* cfg);
 /* 1 = the super-tile kernels take this config (per-band k >= 20, 2D tile widths dividing 26, beacon periods 3..255); they run when
  * t3c_fast_path_available is 0, the general kernels otherwise keep only the ragged end of a frame */
 T3C_API int t3c_super_path_available(const t3c_config* cfg);
+/* development aid: per-phase cycle counters of the super-tile kernels (32 values, read and reset); 0 unless built with -DT3C_SUPER_DEBUG */
+T3C_API int t3c_debug_counters(uint32_t* out32);
 
 /* ---- SURVEY 8(f) "next" rows: the data formats either side of the path ------------------------ */
 /* 8(f).2 sub-word streams (OLD:816-859) and base-243 packing (include/ternary_packing.hpp:18-50), N in 1..27.

@@ -19,7 +19,7 @@ CPP = ["tables.cpp"]
 HDRS = ["dev.cuh", "k_super.cuh", "launch.h", "t3c_internal.h", os.path.join("..", "..", "include", "t3c.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"] + os.environ.get("T3C_NVCC_EXTRA", "").split()
 
 
 def _newest(paths):

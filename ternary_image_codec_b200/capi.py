@@ -66,7 +66,7 @@ _EXPORTS = [
     "t3c_encode_frames_rgb8", "t3c_decode_frames_rgb8", "t3c_rgb_to_quant_dev", "t3c_quant_to_rgb_dev",
     "t3c_pack_pixels_dev", "t3c_unpack_pixels_dev", "t3c_rs_encode_blocks_dev", "t3c_rs_decode_blocks_dev",
     "t3c_encode_profile_dev", "t3c_decode_profile_fixed_dev", "t3c_encode_frames_rgb8_dev",
-    "t3c_decode_frames_rgb8_dev", "t3c_fast_path_available", "t3c_super_path_available",
+    "t3c_decode_frames_rgb8_dev", "t3c_fast_path_available", "t3c_super_path_available", "t3c_debug_counters",
     "t3c_subword_stream", "t3c_words_from_subword_stream", "t3c_base243_pack", "t3c_base243_unpack", "t3c_words_to_base243",
     "t3c_v6new_pack_pixels", "t3c_v6new_unpack_pixels", "t3c_subword_stream_dev", "t3c_words_from_subword_stream_dev",
     "t3c_base243_pack_dev", "t3c_base243_unpack_dev", "t3c_words_to_base243_dev", "t3c_v6new_pack_pixels_dev", "t3c_v6new_unpack_pixels_dev",

@@ -230,6 +230,7 @@ t3c_status t3c_sync(t3c_ctx* ctx)
 size_t t3c_profile_words(const t3c_config* cfg, size_t n_raw_words) { return cfg ? profile_words(*cfg, n_raw_words) : 0; }
 int t3c_fast_path_available(const t3c_config* cfg) { return cfg && fast_path_ok(*cfg) ? 1 : 0; }
 int t3c_super_path_available(const t3c_config* cfg) { return cfg && super_path_ok(*cfg) ? 1 : 0; }
+int t3c_debug_counters(uint32_t* out32) { return out32 ? super_debug_counters(out32) : 0; }
 
 // =============================================================================================
 // device-pointer API

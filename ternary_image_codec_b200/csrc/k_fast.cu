@@ -18,6 +18,7 @@
 #include <mutex>
 #include <type_traits>
 #include <utility>
+#include <vector>
 
 #include "dev.cuh"
 #include "launch.h"
@@ -1569,6 +1570,20 @@ uint32_t full_tiles(const Geom& g, uint64_t px_limit)
 
 // ---- super-tile kernels: launchers ------------------------------------------------------------
 bool super_path_ok(const t3c_config& cfg) { return super_config_ok(cfg); }
+// debug builds (-DT3C_SUPER_DEBUG): per-phase cycle counters of CTA 0, read and reset
+int super_debug_counters(uint32_t* out32)
+{
+#ifdef T3C_SUPER_DEBUG
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, g_sup_dbg, 32 * sizeof(uint32_t));
+    uint32_t z[32] = {};
+    cudaMemcpyToSymbol(g_sup_dbg, z, sizeof z);
+    return 1;
+#else
+    (void)out32;
+    return 0;
+#endif
+}
 
 static void super_tail_all(SuperTail* tail)
 {
@@ -1582,21 +1597,24 @@ static bool super_prepare(const DevTables& T, const t3c_config& cfg, const Geom&
 {
     super_tail_all(tail);
     if (!T.sup) return false;
-    static thread_local uint16_t h_map[3 * SUP_MAX_PASS * 32];
-    static thread_local uint8_t h_kv[3 * SUP_MAX_PASS];
-    if (!make_super_plan(cfg, g, decode, words, px_limit, P, h_map, h_kv)) return false;
+    if (!make_super_plan(cfg, g, decode, words, px_limit, P)) return false;
     SuperCache::Slot& C = T.sup->slot[(decode ? 2 : 0) + (words ? 1 : 0)];
     if (!C.d_map) return false;
     uint8_t key[48] = {};
     for (int b = 0; b < 9; ++b) { key[b] = (uint8_t)g.k[b]; key[9 + b] = (uint8_t)(g.cw_base[b] % 3); }
     std::memcpy(key + 20, &P.M, 4);
     if (!C.valid || std::memcmp(C.key, key, sizeof key) != 0) {
+        static thread_local uint16_t h_map[3 * SUP_MAX_PASS * 32];
+        static thread_local uint8_t h_kv[3 * SUP_MAX_PASS];
+        C.valid = false;
+        if (!build_super_maps(P, g, h_map, h_kv, C.npass)) return false;
         cudaStreamSynchronize(st); // once per config change: kernels in flight may still read the old maps
         cudaMemcpy(C.d_map, h_map, sizeof h_map, cudaMemcpyHostToDevice);
         cudaMemcpy(C.d_kv, h_kv, sizeof h_kv, cudaMemcpyHostToDevice);
         std::memcpy(C.key, key, sizeof key);
         C.valid = true;
     }
+    for (int i = 0; i < 3; ++i) P.npass[i] = C.npass[i];
     P.map = C.d_map;
     P.pass_kv = C.d_kv;
     for (int b = 0; b < 9; ++b) tail->cs.c[b] = (uint64_t)P.ncw[P.kslot[b]] * P.n_tiles;
@@ -1621,6 +1639,7 @@ static int super_launch(Kern kern, const DevTables& T, const FastParams& Q, cons
     }
     const uint64_t total = (uint64_t)P.n_tiles * Q.n_frames;
     uint64_t grid = 2ull * (uint64_t)T.sm_count;
+    if (const char* e = getenv("T3C_SUPER_GRID")) { const int v = atoi(e); if (v > 0) grid = (uint64_t)v; } // experiments only
     if (grid > total) grid = total;
     kern<<<(unsigned)grid, SUP_TPB, P.smem_bytes, st>>>(Q, P, g, T.gf, T.rs);
     return 1;

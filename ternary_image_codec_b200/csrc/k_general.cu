@@ -511,30 +511,31 @@ __global__ void k_header_parse(const GfTables* __restrict__ gf, int fixed, const
 // ------------------------------------------------------------------------------------------
 // General profile encoder (A.1-A.6): one CTA = TPB codewords of one band
 // ------------------------------------------------------------------------------------------
+// cwb = codewords per CTA (<= TPB): TPB for whole frames (thread per codeword), small for the ragged end the tiled kernels leave,
+// where the symbol gather -- index maps with divisions -- is then spread over all threads
 template <typename I>
 __global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restrict__ raw, uint8_t* __restrict__ out, Geom g,
-                                                        const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, CwStart cs)
+                                                        const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, CwStart cs, uint32_t cwb)
 {
     __shared__ uint64_t row[24 * kVals];
     __shared__ uint8_t stage[TPB * 26];
     const int b = blockIdx.y, k = g.k[b], r = 26 - k;
-    const I c0 = (I)cs.c[b] + (I)blockIdx.x * TPB; // codewords before cs.c[b] of band b were coded by the tiled kernels
+    const I c0 = (I)cs.c[b] + (I)blockIdx.x * cwb; // codewords before cs.c[b] of band b were coded by the tiled kernels
     if (c0 >= (I)g.ncw[b]) return;
     const RowTable& tab = rs->row[g.arith][(24 - k) / 2];
     for (int i = threadIdx.x; i < k * kVals; i += TPB) row[i] = tab.e[i / kVals][i % kVals];
+    const uint32_t ncta = (uint32_t)(((I)g.ncw[b] - c0) < cwb ? ((I)g.ncw[b] - c0) : cwb);
+    for (uint32_t idx = threadIdx.x; idx < ncta * (uint32_t)k; idx += TPB) {
+        const uint32_t cl = idx / (uint32_t)k, i = idx - cl * (uint32_t)k;
+        const I is = 9 * ((I)k * (c0 + cl) + i) + b;                             // band split, A.3
+        const I j = perm2d<I>(is, (I)g.n_s, (I)g.tile_area, g.tile_w);           // 2D interleave, A.2
+        stage[26 * cl + i] = (uint8_t)raw_symbol<I>(raw, (I)g.n_words, j);       // regroup, A.1
+    }
     __syncthreads();
-    const I c = c0 + threadIdx.x;
-    const uint32_t ncta = (uint32_t)(((I)g.ncw[b] - c0) < TPB ? ((I)g.ncw[b] - c0) : TPB);
     if (threadIdx.x < ncta) {
         Planes acc{0, 0};
         uint8_t* my = stage + 26 * threadIdx.x;
-        for (int i = 0; i < k; ++i) {
-            const I is = 9 * ((I)k * c + i) + b;                                 // band split, A.3
-            const I j = perm2d<I>(is, (I)g.n_s, (I)g.tile_area, g.tile_w);       // 2D interleave, A.2
-            const uint32_t d = raw_symbol<I>(raw, (I)g.n_words, j);              // regroup, A.1
-            my[i] = (uint8_t)d;
-            gf3_add(acc, row[i * kVals + d]);
-        }
+        for (int i = 0; i < k; ++i) gf3_add(acc, row[i * kVals + my[i]]);
         const uint32_t lo = planes_to_sym4_lo(acc), hi = planes_to_sym4_hi(acc);
         for (int j = 0; j < r; ++j) my[k + j] = (uint8_t)((j < 4 ? lo >> (8 * j) : hi >> (8 * (j - 4))) & 0xFF);
     }
@@ -547,14 +548,10 @@ __global__ void __launch_bounds__(TPB) k_encode_general(const uint8_t* __restric
     }
 }
 // header, beacon symbols and zero padding of one super-frame
-__global__ void k_frame_misc(uint8_t* __restrict__ out_base, size_t stride_bytes, Geom g, t3c_config cfg, const GfTables* gf, const RsTables* rs)
+__global__ void k_frame_misc(uint8_t* __restrict__ out_base, size_t stride_bytes, Geom g, const uint8_t* __restrict__ hdr52)
 {
     uint8_t* __restrict__ out = out_base + stride_bytes * blockIdx.y;
-    if (blockIdx.x == 0 && threadIdx.x < 32) {
-        __shared__ uint8_t h27[27], c52[52];
-        header_emit_warp(cfg, g.arith, gf, rs, h27, c52);
-        for (int i = threadIdx.x; i < 52; i += 32) out[i] = c52[i];
-    }
+    if (blockIdx.x == 0 && threadIdx.x < 52) out[threadIdx.x] = hdr52[threadIdx.x]; // the coded header depends on the config only (cached_header)
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t W = g.l_exp / 9;
     if (g.period && g.slot >= 0)
@@ -782,8 +779,9 @@ int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const 
     int n = 0;
     const uint64_t mx = cw_left(g, cs);
     if (mx) {
-        if (small_geom(g)) k_encode_general<uint32_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cs);
-        else k_encode_general<uint64_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cs);
+        const uint32_t cwb = mx >= 4096 ? (uint32_t)TPB : 8u; // the ragged end of a frame: few codewords, many threads per codeword
+        if (small_geom(g)) k_encode_general<uint32_t><<<dim3(blocks_for(mx, cwb), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cs, cwb);
+        else k_encode_general<uint64_t><<<dim3(blocks_for(mx, cwb), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cs, cwb);
         ++n;
     }
     // without a beacon the rest of the frame is the (cached) coded header and the zero padding
@@ -820,8 +818,10 @@ int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, 
     const uint64_t nb = g.period ? g.l_exp / 9 / g.period + 1 : 1;
     unsigned blocks = (unsigned)((nb + 255) / 256);
     if (blocks > 1024) blocks = 1024;
-    k_frame_misc<<<dim3(blocks, (unsigned)n_frames), 256, 0, st>>>(out, stride_bytes, g, cfg, T.gf, T.rs);
-    return 1;
+    int n = 0;
+    const uint8_t* hdr = cached_header(T, cfg, g.arith, st, n);
+    k_frame_misc<<<dim3(blocks, (unsigned)n_frames), 256, 0, st>>>(out, stride_bytes, g, hdr);
+    return n + 1;
 }
 int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint64_t pitch, uint32_t* status, cudaStream_t st, uint64_t cw_start)
 {

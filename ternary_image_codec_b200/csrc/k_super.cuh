@@ -15,6 +15,15 @@
 
 constexpr int SUP_TPB = 512, SUP_WARPS = SUP_TPB / 32, SUP_MAX_PASS = 64;
 constexpr uint32_t SUP_IDLE = 0xFFFFu;
+// T3C_SUPER_DEBUG builds: CTA 0 accumulates the clock cycles between its barriers into g_sup_dbg[phase] (read with t3c_debug_counters)
+#ifdef T3C_SUPER_DEBUG
+__device__ uint32_t g_sup_dbg[32];
+#define SUP_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_sup_dbg[(i)], (uint32_t)(t_ - sup_t0)); sup_t0 = t_; } } while (0)
+#define SUP_TICK0() long long sup_t0 = clock64()
+#else
+#define SUP_TICK(i) do { } while (0)
+#define SUP_TICK0() do { } while (0)
+#endif
 
 struct SuperPlan {
     uint32_t M, UN, n_tiles, nk;
@@ -24,11 +33,11 @@ struct SuperPlan {
     uint32_t npass[3];      // phase-B passes per class of the super-tile index mod 3
     uint32_t run_base[9];   // staging slot (16-byte aligned, + 32 bytes of slack) of band b's pre-beacon run in U / R
     uint32_t raw_base[9];   // decode: slot of band b's run as it lies in the frame (beacon slots included)
-    uint32_t off_tab[4], off_aux, off_gf, off_meta, off_S, off_U, smem_bytes;
+    uint32_t off_tab[4], off_aux, off_gf, off_meta, off_S, off_U, off_IN, smem_bytes;
     uint32_t G, G_magic, Gm1_magic; // beacon: 9 * period (0: none), floor(2^32 / G) + 1, floor(2^32 / (G - 1)) + 1
     uint32_t slot, bsym;
-    uint32_t tile_w, tile_area, tile_h26; // tile_h26: tile height when the width is 26 (rows = units: reversed in registers), else 0
-    uint32_t ch_shift, sl_shift;          // log2 of the per-band slot counts of the flattened chunk loops (16-byte chunks / byte-wise chunks)
+    uint32_t tile_w, tile_area, tile_h26, h26_magic; // tile_h26: tile height when the width is 26 (rows = units: reversed in registers), else 0; floor(2^32 / h) + 1
+    uint32_t ch_shift;      // log2 of the per-band slot count of the flattened 16-byte chunk loops
     const uint16_t* map;    // [3][SUP_MAX_PASS * 32]: b | cl << 4, SUP_IDLE = idle lane
     const uint8_t* pass_kv; // [3][SUP_MAX_PASS]: k slot | variant << 2
 };
@@ -38,17 +47,39 @@ struct SuperMeta {          // per super-tile, written by threads 0..8
     uint32_t o_first[9];    // index, from the run's first byte, of the first beacon slot at or after it
     uint32_t stage[9];      // offset of the run's pre-beacon byte 0 inside U / R
     uint32_t nch[9];        // 16-byte chunks of the aligned superset of the run in the frame
-    uint32_t n_slow[9];     // encode: 2 + beacon slots inside the run; decode: slot-count boundaries inside the padded pre-beacon run
 };
 
-// 16 bytes at an arbitrary byte offset of a shared buffer (the buffer has >= 4 bytes of slack after the last byte read)
-__device__ __forceinline__ uint4 lds_gather16(const uint8_t* base, uint32_t off)
+// 16 bytes at an arbitrary shared-memory byte address (the buffer has >= 4 bytes of slack after the last byte read)
+__device__ __forceinline__ uint4 lds_gather16(uint32_t a)
 {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(base) + off;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    const uint32_t sh = ((uint32_t)a & 3u) * 8u;
-    const uint32_t x0 = w[0], x1 = w[1], x2 = w[2], x3 = w[3], x4 = w[4];
+    const uint32_t aw = a & ~3u, sh = (a & 3u) * 8u;
+    uint32_t x0, x1, x2, x3, x4;
+    asm volatile("ld.shared.u32 %0, [%5];\n\tld.shared.u32 %1, [%5+4];\n\tld.shared.u32 %2, [%5+8];\n\tld.shared.u32 %3, [%5+12];\n\tld.shared.u32 %4, [%5+16];"
+                 : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4) : "r"(aw) : "memory");
     return make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh));
+}
+// word j of the 16-byte mask whose bytes [0, e) are 0xFF (e in 0..16, branch-free)
+__device__ __forceinline__ uint32_t below16(uint32_t e, int j)
+{
+    const int k = min(max((int)e - 4 * j, 0), 4);
+    return __funnelshift_lc(0xFFFFFFFFu, 0u, 8u * (uint32_t)k);
+}
+// bytes [0, e) of a, bytes [e, 16) of b
+__device__ __forceinline__ uint4 merge16(uint4 a, uint4 b, uint32_t e)
+{
+    const uint32_t m0 = below16(e, 0), m1 = below16(e, 1), m2 = below16(e, 2), m3 = below16(e, 3);
+    return make_uint4((a.x & m0) | (b.x & ~m0), (a.y & m1) | (b.y & ~m1), (a.z & m2) | (b.z & ~m2), (a.w & m3) | (b.w & ~m3));
+}
+// bytes [0, e) of a, byte e = v (v4 = v in every byte), bytes (e, 16) of b
+__device__ __forceinline__ uint4 merge16_put(uint4 a, uint4 b, uint32_t e, uint32_t v4)
+{
+    uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w}, r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t m = below16(e, j), m1 = below16(e + 1u, j);
+        r[j] = (x[j] & m) | (v4 & (m1 ^ m)) | (y[j] & ~m1);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
 }
 // frame-local indices fit 32 bits (checked by the plan)
 template <bool DECODE>
@@ -69,14 +100,7 @@ __device__ __forceinline__ void super_run_meta(SuperMeta& m, const SuperPlan& P,
     m.len[b] = len;
     m.o_first[b] = o_first;
     m.nch[b] = (((uint32_t)lo & 15u) + len + 15u) >> 4;
-    if (DECODE) {
-        m.stage[b] = P.run_base[b];
-        const uint32_t lp = (L + 15u) & ~15u; // boundaries are counted up to the end of the last 16-byte chunk
-        m.n_slow[b] = (P.G && lp > o_first) ? (lp - 1u - o_first) / (P.G - 1u) + 1u : 0u;
-    } else {
-        m.stage[b] = P.run_base[b] + (P.G ? 0u : (uint32_t)lo & 15u); // without a beacon the staged run keeps the frame's 16-byte phase
-        m.n_slow[b] = 2u + ((P.G && len > o_first) ? (len - 1u - o_first) / P.G + 1u : 0u);
-    }
+    m.stage[b] = P.run_base[b] + ((DECODE || P.G) ? 0u : (uint32_t)lo & 15u); // encode without a beacon: the staged run keeps the frame's 16-byte phase
 }
 // boustrophedon rows of the super-tile (A.2) for tile widths 2 and 13: reverse, in place, every row whose index inside its
 // w x h tile is odd.  Super-tiles start on a row (9M is a multiple of 26, w divides 26) and hold whole rows only.  (Width 26:
@@ -92,6 +116,12 @@ __device__ __forceinline__ void super_reverse_rows(uint8_t* S, const SuperPlan& 
         uint8_t* p = S + row * w;
         for (uint32_t i = 0; i < w / 2; ++i) { const uint8_t a = p[i], c = p[w - 1 - i]; p[i] = c; p[w - 1 - i] = a; }
     }
+}
+// 26-wide tiles: is unit x of the frame an odd row of its tile?  x mod h through the reciprocal (exact: x * h < 2^32, plan)
+__device__ __forceinline__ bool super_row_odd(const SuperPlan& P, uint32_t x)
+{
+    if (!P.tile_h26) return false;
+    return ((x - __umulhi(x, P.h26_magic) * P.tile_h26) & 1u) != 0;
 }
 __device__ __forceinline__ bool super_rows_in_smem(const SuperPlan& P) { return P.tile_area && !P.tile_h26 && P.tile_w > 1; }
 // the lines of a byte range, towards L2 (the next super-tile's input while this one is being coded)
@@ -112,8 +142,7 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint8_t* S = smem + P.off_S;                   // stream symbols, pre-scaled by 4
-    uint8_t* U = smem + P.off_U;                   // the pixel-side bytes of the super-tile, later the nine pre-beacon runs
-    SuperMeta& meta = *reinterpret_cast<SuperMeta*>(smem + P.off_meta);
+    uint8_t* U = smem + P.off_U;                   // the nine pre-beacon runs
     uint32_t* pat = reinterpret_cast<uint32_t*>(smem + P.off_aux); // [k slot][variant][2]
     for (uint32_t ks = 0; ks < P.nk; ++ks) {
         const int K = (int)P.kk[ks];
@@ -135,52 +164,73 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
             pat[6 * ks + 2 * tid + 1] = two;
         }
     }
+    const uint32_t bar = smem_u32(smem + P.off_aux + 96);
+    if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     __syncthreads();
-    const uint32_t smem32 = smem_u32(smem);
+    const uint32_t smem32 = smem_u32(smem), U32 = smem_u32(U), bsym4 = P.bsym * 0x01010101u;
     const uint64_t in_limit = Q.in_stride * Q.n_frames;
     const uint32_t total = P.n_tiles * Q.n_frames;
-    for (uint32_t st = blockIdx.x; st < total; st += gridDim.x) {
-        const uint32_t f = st / P.n_tiles, T = st - f * P.n_tiles, tm = T % 3u;
-        // ---- the super-tile's pixels -> U (128-bit loads of the 16-byte aligned superset)
-        const uint64_t g_lo = Q.in_stride * f + (uint64_t)PIXB * P.UN * T, a0 = g_lo & ~15ull;
-        const uint32_t pad = (uint32_t)(g_lo & 15u), n_in = (pad + PIXB * P.UN + 15u) >> 4;
-        for (uint32_t c = tid; c < n_in; c += SUP_TPB) {
-            const uint64_t ga = a0 + 16ull * c;
-            uint4 q;
-            if (ga + 16 <= in_limit) q = __ldg(reinterpret_cast<const uint4*>(Q.in + ga));
-            else {
-                uint32_t t[4] = {0, 0, 0, 0};
-                for (int i = 0; i < 16; ++i) if (ga + i < in_limit) t[i >> 2] |= (uint32_t)Q.in[ga + i] << (8 * (i & 3));
-                q = make_uint4(t[0], t[1], t[2], t[3]);
-            }
-            *reinterpret_cast<uint4*>(U + 16 * c) = q;
+    uint8_t* IN = smem + P.off_IN;                 // the pixel-side bytes of a super-tile, fetched by the bulk copy engine one super-tile ahead
+    SuperMeta* metas = reinterpret_cast<SuperMeta*>(smem + P.off_meta); // two copies: phase C of one super-tile runs beside phase A of the next
+    // bulk load of super-tile st2: the 16-byte aligned superset of its pixel bytes, clipped to the buffer
+    auto fetch = [&](uint32_t st2) {
+        const uint32_t f2 = st2 / P.n_tiles, T2 = st2 - f2 * P.n_tiles;
+        const uint64_t lo = Q.in_stride * f2 + (uint64_t)PIXB * P.UN * T2, a0 = lo & ~15ull;
+        uint32_t bytes = ((uint32_t)(lo - a0) + PIXB * P.UN + 15u) & ~15u;
+        if (a0 + bytes > in_limit) bytes = (uint32_t)(in_limit - a0) & ~15u;
+        fence_async_smem();
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(IN), Q.in + a0, bytes, bar);
+    };
+    uint32_t phase = 0;
+    // ---- phase A of super-tile st2: its pixels (in IN once the mbarrier flips) -> stream symbols in S; thread per unit, dealt even / odd
+    // inside chunks of 64 units (conflict-free 36- and 52-byte lane strides); also its run geometry into metas[mb]
+    auto phase_a_wait = [&](uint32_t st2, uint32_t mb) { // all threads: geometry, arrival of the pixels, the clipped end of the buffer
+        const uint32_t f2 = st2 / P.n_tiles, T2 = st2 - f2 * P.n_tiles;
+        const uint64_t g_lo = Q.in_stride * f2 + (uint64_t)PIXB * P.UN * T2, a0 = g_lo & ~15ull;
+        const uint32_t want = (uint32_t)(g_lo & 15u) + PIXB * P.UN;
+        if (tid >= SUP_TPB - 9) super_run_meta<false>(metas[mb], P, g, Q.out_stride * f2, T2, SUP_TPB - 1 - tid); // (lanes of the last warp: it has the fewest units)
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        if (a0 + ((want + 15u) & ~15u) > in_limit) { // the last bytes of the buffer that a clipped bulk copy left out (final super-tile of the final frame)
+            for (uint32_t i = ((uint32_t)(in_limit - a0) & ~15u) + tid; i < want; i += SUP_TPB) IN[i] = a0 + i < in_limit ? Q.in[a0 + i] : 0;
+            __syncthreads();
         }
-        if (st + gridDim.x < total) { // this CTA's next super-tile: its pixels towards L2
-            const uint32_t st2 = st + gridDim.x, f2 = st2 / P.n_tiles, T2 = st2 - f2 * P.n_tiles;
-            super_prefetch(Q.in, Q.in_stride * f2 + (uint64_t)PIXB * P.UN * T2, PIXB * P.UN, in_limit, tid);
-        }
-        if (tid < 9) super_run_meta<false>(meta, P, g, Q.out_stride * f, T, tid);
-        __syncthreads();
-        // ---- phase A: thread per unit, dealt even / odd inside chunks of 64 units (conflict-free 36- and 52-byte lane strides)
-        for (uint32_t ch = warp; 64u * ch < P.UN; ch += SUP_WARPS) {
+    };
+    auto phase_a = [&](uint32_t st2) {
+        const uint32_t f2 = st2 / P.n_tiles, T2 = st2 - f2 * P.n_tiles;
+        const uint32_t pad = (uint32_t)((Q.in_stride * f2 + (uint64_t)PIXB * P.UN * T2) & 15u);
 #pragma unroll 1
-            for (uint32_t h = 0; h < 2; ++h) {
-                const uint32_t u = 64u * ch + 2u * lane + h;
-                if (u >= P.UN) continue;
-                const bool rev = P.tile_h26 && ((P.UN * T + u) % P.tile_h26 & 1u); // 26-wide tiles: unit = row
-                if constexpr (WORDS) enc_unit_words<true>(U, pad + 27u * u, S + 26u * u, rev);
-                else if (pad & 1u) enc_unit_rgb<true, true>(U, pad + 18u * u, S + 26u * u, rev);
-                else enc_unit_rgb<false, true>(U, pad + 18u * u, S + 26u * u, rev);
-            }
+        for (uint32_t hc = warp; 64u * (hc >> 1) < P.UN; hc += SUP_WARPS) { // half-chunk: the units of one parity of a 64-unit chunk
+            const uint32_t u = 64u * (hc >> 1) + 2u * lane + (hc & 1u);
+            if (u >= P.UN) continue;
+            const bool rev = super_row_odd(P, P.UN * T2 + u);               // 26-wide tiles: unit = row
+            if constexpr (WORDS) enc_unit_words<true>(IN, pad + 27u * u, S + 26u * u, rev);
+            else enc_unit_rgb<true, true>(IN, pad + 18u * u, S + 26u * u, rev); // (the variant that also takes units at byte offset 3 of a word)
         }
-        __syncthreads();                           // S complete, U (pixels) dead
+    };
+    if (blockIdx.x < total) {
+        if (tid == 0) fetch(blockIdx.x);
+        phase_a_wait(blockIdx.x, 0);
+        phase_a(blockIdx.x);
+    }
+    __syncthreads();                               // S complete, IN free again
+    if (blockIdx.x + gridDim.x < total && tid == 0) fetch(blockIdx.x + gridDim.x);
+    uint32_t mb = 0;
+    for (uint32_t st = blockIdx.x; st < total; st += gridDim.x, mb ^= 1u) {
+        const uint32_t f = st / P.n_tiles, T = st - f * P.n_tiles, tm = T % 3u;
+        const SuperMeta& meta = metas[mb];
+        SUP_TICK0();
         if (super_rows_in_smem(P)) { super_reverse_rows(S, P, T, tid); __syncthreads(); }
         // ---- phase B: one codeword per lane; a pass holds codewords of one k and one scrambler variant
         const uint16_t* map = P.map + tm * (SUP_MAX_PASS * 32);
         const uint8_t* pkv = P.pass_kv + tm * SUP_MAX_PASS;
+        uint32_t e_nx = 0, kv_nx = 0; // the map entry of a warp's next pass is fetched while it codes the current one
+        if ((uint32_t)warp < P.npass[tm]) { e_nx = __ldg(map + 32 * warp + lane); kv_nx = __ldg(pkv + warp); }
 #pragma unroll 1
         for (uint32_t pass = warp; pass < P.npass[tm]; pass += SUP_WARPS) {
-            const uint32_t e = __ldg(map + 32 * pass + lane), kv = __ldg(pkv + pass);
+            const uint32_t e = e_nx, kv = kv_nx;
+            if (pass + SUP_WARPS < P.npass[tm]) { e_nx = __ldg(map + 32 * (pass + SUP_WARPS) + lane); kv_nx = __ldg(pkv + pass + SUP_WARPS); }
             if (e == SUP_IDLE) continue;
             const uint32_t ks = kv & 3u, v = kv >> 2, b = e & 15u, cl = e >> 4, K = P.kk[ks];
             const uint8_t* src = S + 9u * K * cl + b;
@@ -191,7 +241,8 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
             else if (K == 22) enc_cw<22>(src, dst, pa, pnz, ptw);
             else enc_cw<24>(src, dst, pa, pnz, ptw);
         }
-        __syncthreads();
+        __syncthreads();                           // the nine runs complete, S free again
+        SUP_TICK(2);
         if (T == 0) { // body symbols 0 and 1 may still see the scrambler's transient (A.4)
             if (tid == 0) {
                 uint8_t* dst = U + meta.stage[0];
@@ -201,51 +252,55 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
             __syncthreads();
         }
         // ---- phase C: the nine runs -> global.  Chunk c of a run = 16 bytes at the aligned address a0 + 16c: bytes of the
-        // frame at index x = 16c - pad from the run's first byte.  Interior chunks without a beacon slot are one gather +
-        // one 128-bit store; the first / last chunk of a run and the chunks holding a beacon slot go byte by byte.
-        // Both loops are flattened over the nine bands (2^ch_shift / 2^sl_shift slots per band).
-        for (uint32_t idx = tid; idx < (9u << P.ch_shift); idx += SUP_TPB) {
-            const uint32_t b = idx >> P.ch_shift, c = idx & ((1u << P.ch_shift) - 1u);
-            if (c == 0 || c + 1 >= meta.nch[b]) continue;
-            const uint64_t lo = meta.g_lo[b];
-            const uint32_t padb = (uint32_t)lo & 15u, x0 = 16u * c - padb;
-            uint32_t nb = 0;
-            if (P.G) {
-                const uint32_t t = x0 + P.G - 1u - meta.o_first[b];
-                nb = __umulhi(t, P.G_magic);
-                if (P.G - 1u - (t - nb * P.G) < 16u) continue; // a beacon slot inside: second loop
-            }
-            const uint8_t* sp = U + meta.stage[b] + (x0 - nb);
-            uint4 q;
-            if (!P.G) q = *reinterpret_cast<const uint4*>(sp); // staged in the frame's 16-byte phase
-            else q = lds_gather16(sp, 0);
-            *reinterpret_cast<uint4*>(Q.out + (lo - padb) + 16u * c) = q;
-        }
-        // slow items per band: 0 = first chunk, 1 = last chunk, 2 + j = the chunk of beacon slot j (unless it is the first / last one)
-        for (uint32_t idx = tid; idx < (9u << P.sl_shift); idx += SUP_TPB) {
-            const uint32_t b = idx >> P.sl_shift, it = idx & ((1u << P.sl_shift) - 1u);
-            if (it >= meta.n_slow[b]) continue;
-            const uint64_t lo = meta.g_lo[b];
-            const uint32_t padb = (uint32_t)lo & 15u, len = meta.len[b], nch = meta.nch[b], of = meta.o_first[b];
-            uint32_t c;
-            if (it == 0) c = 0;
-            else if (it == 1) { if (nch < 2) continue; c = nch - 1; }
-            else { c = (of + P.G * (it - 2u) + padb) >> 4; if (c == 0 || c + 1 == nch) continue; }
-            uint8_t* gout = Q.out + (lo - padb) + 16u * c;
-            const uint8_t* sb = U + meta.stage[b];
-            for (uint32_t i = 0; i < 16; ++i) {
-                const int32_t x = (int32_t)(16u * c + i) - (int32_t)padb;
-                if (x < 0 || (uint32_t)x >= len) continue;
-                uint32_t nb = 0;
-                if (P.G) {
-                    const uint32_t t = (uint32_t)x + P.G - 1u - of;
-                    nb = __umulhi(t, P.G_magic);
-                    if (t - nb * P.G == P.G - 1u) { gout[i] = (uint8_t)P.bsym; continue; } // x is a beacon slot
+        // frame at index x = 16c - pad from the run's first byte.  Interior chunks are one gather + one 128-bit store (two
+        // gathers merged around the beacon symbol when the chunk holds a beacon slot); the loop is flattened over the nine
+        // bands (2^ch_shift slots per band).  It shares its barrier interval with phase A of the next super-tile.
+        auto phase_c = [&]() {
+            for (uint32_t idx = tid; idx < (9u << P.ch_shift); idx += SUP_TPB) {
+                const uint32_t b = idx >> P.ch_shift, c = idx & ((1u << P.ch_shift) - 1u);
+                if (c == 0 || c + 1 >= meta.nch[b]) continue;
+                const uint64_t lo = meta.g_lo[b];
+                const uint32_t padb = (uint32_t)lo & 15u, x0 = 16u * c - padb;
+                uint4 q;
+                if (!P.G) q = *reinterpret_cast<const uint4*>(U + meta.stage[b] + x0); // staged in the frame's 16-byte phase
+                else {
+                    const uint32_t t = x0 + P.G - 1u - meta.o_first[b], nb = __umulhi(t, P.G_magic);
+                    const uint32_t e = P.G - 1u - (t - nb * P.G);    // distance to the next beacon slot at or after x0
+                    const uint32_t sp = U32 + meta.stage[b] + (x0 - nb);
+                    q = lds_gather16(sp);
+                    if (e < 16u) q = merge16_put(q, lds_gather16(sp - 1u), e, bsym4); // bytes after the slot lag by one
                 }
-                gout[i] = sb[(uint32_t)x - nb];
+                *reinterpret_cast<uint4*>(Q.out + (lo - padb) + 16u * c) = q;
             }
-        }
-        __syncthreads();                           // U and S are reused by the next super-tile
+            // the first and the last chunk of every run may be partial: one byte per thread
+            if (tid < 18 * 16) {
+                const uint32_t b = (uint32_t)tid >> 5, last = ((uint32_t)tid >> 4) & 1u, i = (uint32_t)tid & 15u;
+                const uint64_t lo = meta.g_lo[b];
+                const uint32_t padb = (uint32_t)lo & 15u, len = meta.len[b], nch = meta.nch[b], of = meta.o_first[b];
+                const uint32_t c = last ? nch - 1u : 0u;
+                const int32_t x = (int32_t)(16u * c + i) - (int32_t)padb;
+                if (!(last && nch < 2u) && x >= 0 && (uint32_t)x < len) {
+                    uint8_t* gout = Q.out + (lo - padb) + 16u * c + i;
+                    uint32_t nb = 0;
+                    bool slot = false;
+                    if (P.G) {
+                        const uint32_t t = (uint32_t)x + P.G - 1u - of;
+                        nb = __umulhi(t, P.G_magic);
+                        slot = t - nb * P.G == P.G - 1u;         // x is a beacon slot
+                    }
+                    *gout = slot ? (uint8_t)P.bsym : U[meta.stage[b] + (uint32_t)x - nb];
+                }
+            }
+        };
+        // half of the warps store first and compute second, the other half the other way round: store latency and arithmetic interleave
+        const bool more = st + gridDim.x < total;
+        if (more) phase_a_wait(st + gridDim.x, mb ^ 1u);
+        if (warp & 1) { if (more) phase_a(st + gridDim.x); phase_c(); }
+        else { phase_c(); if (more) phase_a(st + gridDim.x); }
+        SUP_TICK(3);
+        __syncthreads();                           // S complete, IN and U free again
+        SUP_TICK(1);
+        if (st + 2 * gridDim.x < total && tid == 0) fetch(st + 2 * gridDim.x); // pixels of the super-tile after the next on their way
     }
 }
 
@@ -290,11 +345,12 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
     const uint32_t smem32 = smem_u32(smem);
     const uint64_t in_limit = Q.in_stride * (Q.n_frames - 1) + 9 * g.n_out;
     const uint32_t total = P.n_tiles * Q.n_frames;
-    const uint32_t ch_mask = (1u << P.ch_shift) - 1u, sl_mask = (1u << P.sl_shift) - 1u;
+    const uint32_t ch_mask = (1u << P.ch_shift) - 1u, S32 = smem_u32(S);
     if (blockIdx.x < total && tid < 9) super_run_meta<true>(meta, P, g, Q.in_stride * (blockIdx.x / P.n_tiles), blockIdx.x % P.n_tiles, tid);
     __syncthreads();
     for (uint32_t st = blockIdx.x; st < total; st += gridDim.x) {
         const uint32_t f = st / P.n_tiles, T = st - f * P.n_tiles, tm = T % 3u;
+        SUP_TICK0();
         // ---- the nine runs as they lie in the frame -> S region (slot raw_base[b], byte i <-> global a0 + i)
         for (uint32_t idx = tid; idx < (9u << P.ch_shift); idx += SUP_TPB) {
             const uint32_t b = idx >> P.ch_shift, c = idx & ch_mask;
@@ -310,19 +366,22 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             *reinterpret_cast<uint4*>(S + P.raw_base[b] + 16u * c) = q;
         }
         __syncthreads();
+        SUP_TICK(4);
         // ---- squeeze the beacon slots out and scale by 4 (table byte offset): R_b[q] = 4 * frame byte (q + beacon slots before
         // body symbol q).  Bytes >= 27 are reduced mod 27 first (out-of-alphabet symbols read as their low three trits, OLD:28-31)
         for (uint32_t idx = tid; idx < (9u << P.ch_shift); idx += SUP_TPB) {
             const uint32_t b = idx >> P.ch_shift, d = idx & ch_mask, L = 26u * P.ncw[P.kslot[b]];
             if (16u * d >= L) continue;
             const uint32_t q0 = 16u * d;
-            uint32_t nb = 0;
-            if (P.G) {
-                const uint32_t t = q0 + P.G - 1u - meta.o_first[b];
-                nb = __umulhi(t, P.Gm1_magic);
-                if (P.G - 2u - (t - nb * (P.G - 1u)) < 15u) continue; // the count changes inside this chunk: second loop
+            const uint32_t srcb = S32 + P.raw_base[b] + ((uint32_t)meta.g_lo[b] & 15u);
+            uint4 q;
+            if (!P.G) q = lds_gather16(srcb + q0);
+            else {
+                const uint32_t t = q0 + P.G - 1u - meta.o_first[b], nb = __umulhi(t, P.Gm1_magic);
+                const uint32_t e = P.G - 1u - (t - nb * (P.G - 1u)); // distance to the next body symbol with one more slot before it
+                q = lds_gather16(srcb + q0 + nb);
+                if (e < 16u) q = merge16(q, lds_gather16(srcb + q0 + nb + 1u), e);
             }
-            uint4 q = lds_gather16(S + P.raw_base[b] + ((uint32_t)meta.g_lo[b] & 15u), q0 + nb);
             if (((q.x | q.y | q.z | q.w) & 0xE0E0E0E0u) != 0) {
                 uint32_t t[4] = {q.x, q.y, q.z, q.w};
                 for (int i = 0; i < 4; ++i) {
@@ -335,21 +394,8 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             q.x <<= 2; q.y <<= 2; q.z <<= 2; q.w <<= 2;
             *reinterpret_cast<uint4*>(R + P.run_base[b] + q0) = q;
         }
-        // chunks in which the number of beacon slots passed changes, byte by byte: boundary j is the first q with j + 1 slots before it
-        for (uint32_t idx = tid; idx < (9u << P.sl_shift); idx += SUP_TPB) {
-            const uint32_t b = idx >> P.sl_shift, j = idx & sl_mask;
-            if (j >= meta.n_slow[b]) continue;
-            const uint32_t qj = meta.o_first[b] + (P.G - 1u) * j;
-            if (!(qj & 15u)) continue;
-            const uint32_t q0 = qj & ~15u;
-            const uint8_t* srcb = S + P.raw_base[b] + ((uint32_t)meta.g_lo[b] & 15u);
-            uint8_t* dstb = R + P.run_base[b];
-            for (uint32_t i = 0; i < 16; ++i) {
-                const uint32_t q = q0 + i, v = srcb[q + j + (q >= qj ? 1u : 0u)];
-                dstb[q] = (uint8_t)(4u * (v % 27u));
-            }
-        }
         __syncthreads();                           // R complete, the raw runs in S and this tile's meta dead
+        SUP_TICK(5);
         if (st + gridDim.x < total) { // this CTA's next super-tile: its run geometry now, its runs towards L2
             const uint32_t st2 = st + gridDim.x, f2 = st2 / P.n_tiles, T2 = st2 - f2 * P.n_tiles;
             if (tid < 9) super_run_meta<true>(meta, P, g, Q.in_stride * f2, T2, tid);
@@ -373,9 +419,12 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
         // ---- phase B: syndrome screen per codeword (BM / Chien / Forney in-thread for the dirty ones), descrambled data -> stream order
         const uint16_t* map = P.map + tm * (SUP_MAX_PASS * 32);
         const uint8_t* pkv = P.pass_kv + tm * SUP_MAX_PASS;
+        uint32_t e_nx = 0, kv_nx = 0; // the map entry of a warp's next pass is fetched while it decodes the current one
+        if ((uint32_t)warp < P.npass[tm]) { e_nx = __ldg(map + 32 * warp + lane); kv_nx = __ldg(pkv + warp); }
 #pragma unroll 1
         for (uint32_t pass = warp; pass < P.npass[tm]; pass += SUP_WARPS) {
-            const uint32_t e = __ldg(map + 32 * pass + lane), kv = __ldg(pkv + pass);
+            const uint32_t e = e_nx, kv = kv_nx;
+            if (pass + SUP_WARPS < P.npass[tm]) { e_nx = __ldg(map + 32 * (pass + SUP_WARPS) + lane); kv_nx = __ldg(pkv + pass + SUP_WARPS); }
             if (e == SUP_IDLE) continue;
             const uint32_t ks = kv & 3u, v = kv >> 2, b = e & 15u, cl = e >> 4, K = P.kk[ks];
             const uint8_t* src = R + P.run_base[b] + 26u * cl;
@@ -387,21 +436,23 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             else dec_cw<24>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
         }
         __syncthreads();                           // S complete, R dead
+        SUP_TICK(6);
         if (super_rows_in_smem(P)) { super_reverse_rows(S, P, T, tid); __syncthreads(); }
         // ---- phase A: 26 stream symbols -> six pixels per thread -> pixel-side bytes in R
         const uint64_t g_lo = Q.out_stride * f + (uint64_t)PIXB * P.UN * T;
         const uint32_t pad = (uint32_t)(g_lo & 15u);
-        for (uint32_t ch = warp; 64u * ch < P.UN; ch += SUP_WARPS) {
 #pragma unroll 1
-            for (uint32_t h = 0; h < 2; ++h) {
-                const uint32_t u = 64u * ch + 2u * lane + h;
+        for (uint32_t hc = warp; 64u * (hc >> 1) < P.UN; hc += SUP_WARPS) { // half-chunk: the units of one parity of a 64-unit chunk
+            {
+                const uint32_t u = 64u * (hc >> 1) + 2u * lane + (hc & 1u);
                 if (u >= P.UN) continue;
-                const bool rev = P.tile_h26 && ((P.UN * T + u) % P.tile_h26 & 1u); // 26-wide tiles: unit = row
+                const bool rev = super_row_odd(P, P.UN * T + u);                // 26-wide tiles: unit = row
                 if constexpr (WORDS) dec_unit_words<true>(S, 26u * u, R + pad + 27u * u, rev);
                 else dec_unit_rgb<true>(S, 26u * u, R + pad + 18u * u, rev);   // pad is even (frames start on even bytes, 18 UN T is even)
             }
         }
         __syncthreads();
+        SUP_TICK(7);
         {   // pixel-side bytes -> global: whole 16-byte chunks, the (at most 15 + 15) edge bytes one by one
             const uint32_t n_out = PIXB * P.UN, end = pad + n_out, c_lo = pad ? 1u : 0u, c_hi = end >> 4;
             uint8_t* gout = Q.out + (g_lo - pad);
@@ -410,6 +461,7 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             if (tid >= 32 && tid < 48) { const uint32_t pos = 16u * c_hi + (uint32_t)(tid - 32); if (pos < end && (c_hi >= c_lo) && !(c_hi == 0 && pad)) gout[pos] = R[pos]; }
         }
         __syncthreads();
+        SUP_TICK(8);
     }
 }
 
@@ -433,7 +485,7 @@ bool super_config_ok(const t3c_config& cfg)
     return true;
 }
 // false when no super-tile shape fits (shared memory, pass table) or the frame holds no full super-tile
-static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, bool words, uint64_t px_limit, SuperPlan& P, uint16_t* h_map, uint8_t* h_kv)
+static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, bool words, uint64_t px_limit, SuperPlan& P)
 {
     if (!super_config_ok(cfg)) return false;
     if (g.n_s >= (1ull << 31) || g.l_exp >= (1ull << 31)) return false;
@@ -451,7 +503,7 @@ static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, b
         P.G_magic = (uint32_t)((1ull << 32) / P.G) + 1u;
         P.Gm1_magic = (uint32_t)((1ull << 32) / (P.G - 1u)) + 1u;
     }
-    if (g.tile_area) { P.tile_w = g.tile_w; P.tile_area = (uint32_t)g.tile_area; P.tile_h26 = g.tile_w == 26 ? (uint32_t)(g.tile_area / 26) : 0u; }
+    if (g.tile_area) { P.tile_w = g.tile_w; P.tile_area = (uint32_t)g.tile_area; P.tile_h26 = (g.tile_w == 26 && g.tile_area > 26 && (g.n_s / 26 + 1) * (g.tile_area / 26) < (1ull << 32)) ? (uint32_t)(g.tile_area / 26) : 0u; if (P.tile_h26) P.h26_magic = (uint32_t)((1ull << 32) / P.tile_h26) + 1u; }
     const uint32_t pixb = words ? 27u : 18u;
     const uint32_t budget = (227u * 1024u - 2048u) / 2u - (decode ? 256u : 0u); // two CTAs per SM
     // the largest multiple of l that fits
@@ -469,21 +521,21 @@ static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, b
         }
         if (M / 20u >= 4095u || n_cw / 32u + 3u * P.nk > SUP_MAX_PASS) continue;
         for (uint32_t s = 0; s < P.nk; ++s) { P.off_tab[s] = off; off += decode ? 3u * 6656u : up256(3u * 8u * P.kk[s] * 27u); }
-        P.off_aux = off; off += up16(4u * 6u * 4u);
+        P.off_aux = off; off += up16(4u * 6u * 4u + 16u);   // + the mbarrier of the encoder's input buffer
         P.off_gf = off; off += decode ? up16((uint32_t)sizeof(GfTables)) : 0u;
-        P.off_meta = off; off += up16((uint32_t)sizeof(SuperMeta));
+        P.off_meta = off; off += 2u * up16((uint32_t)sizeof(SuperMeta));
         const uint32_t UN = 9u * M / 26u, pix = up16(pixb * UN + 48u);
         P.off_S = off; off += up16((decode && raws > 9u * M ? raws : 9u * M) + 32u);
-        P.off_U = off; off += runs > pix ? runs : pix;
+        if (decode) { P.off_U = off; off += runs > pix ? runs : pix; P.off_IN = P.off_U; }   // R, later the pixel-side bytes on their way out
+        else { P.off_U = off; off += runs; P.off_IN = off; off += pix; }                    // the runs | the pixels (bulk-loaded one super-tile ahead)
         if (off > budget) continue;
         P.smem_bytes = off + (decode ? 256u : 0u);
         P.M = M; P.UN = UN;
         uint32_t max_len = 0;
         for (uint32_t s = 0; s < P.nk; ++s) max_len = 26u * P.ncw[s] > max_len ? 26u * P.ncw[s] : max_len;
         const uint32_t max_exp = max_len + (P.G ? max_len / (P.G - 1u) + 2u : 0u);           // run length in the frame, beacon slots included
-        const uint32_t max_ch = (max_exp + 30u) / 16u + 1u, max_sl = 3u + (P.G ? (max_exp + 15u) / (P.G - 1u) + 1u : 0u);
+        const uint32_t max_ch = (max_exp + 30u) / 16u + 1u;
         P.ch_shift = 0; while ((1u << P.ch_shift) < max_ch) ++P.ch_shift;
-        P.sl_shift = 0; while ((1u << P.sl_shift) < max_sl) ++P.sl_shift;
         found = true;
     }
     if (!found) return false;
@@ -493,26 +545,48 @@ static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, b
     nt = by_px < nt ? by_px : nt;
     if (!nt || nt > 0x7FFFFFFFull) return false;
     P.n_tiles = (uint32_t)nt;
-    // pass maps: for super-tile index T = tm (mod 3), codeword cl of band b has scrambler variant (cw_base_b + n_b T + cl) mod 3;
-    // a pass takes 32 codewords of one (k, variant) in (row, band) order
+    return true;
+}
+// Pass maps (built when the cached ones do not match): for super-tile index T = tm (mod 3), codeword cl of band b has scrambler
+// variant (cw_base_b + n_b T + cl) mod 3; a pass takes up to 32 codewords of one (k, variant).  Phase B gathers a codeword's
+// symbols at byte addresses a + 9i, a = 9 k cl + b: two lanes collide on a bank for some i exactly when their a differ by more
+// than 3 and by 0, +-1, +-2, +-3 modulo 128, so codewords are dealt greedily into the first pass where they collide with nobody.
+static bool build_super_maps(const SuperPlan& P, const Geom& g, uint16_t* h_map, uint8_t* h_kv, uint32_t npass[3])
+{
+    struct Pass { int n; int32_t occ[128]; };
+    std::vector<Pass> passes;
     for (int tm = 0; tm < 3; ++tm) {
-        uint32_t pass = 0;
+        uint32_t pass0 = 0;
         for (uint32_t s = 0; s < P.nk; ++s)
             for (uint32_t v = 0; v < 3; ++v) {
-                uint32_t fill = 32;
+                std::vector<std::pair<uint32_t, int32_t>> list; // (map entry, gather address)
                 for (uint32_t cl = 0; cl < P.ncw[s]; ++cl)
-                    for (uint32_t b = 0; b < 9; ++b) {
-                        if (P.kslot[b] != s || (g.cw_base[b] + (uint64_t)P.ncw[s] * tm + cl) % 3 != v) continue;
-                        if (fill == 32) {
-                            if (pass == SUP_MAX_PASS) return false;
-                            for (int i = 0; i < 32; ++i) h_map[(tm * SUP_MAX_PASS + pass) * 32 + i] = (uint16_t)SUP_IDLE;
-                            h_kv[tm * SUP_MAX_PASS + pass] = (uint8_t)(s | v << 2);
-                            ++pass; fill = 0;
-                        }
-                        h_map[(tm * SUP_MAX_PASS + pass - 1) * 32 + fill++] = (uint16_t)(b | cl << 4);
+                    for (uint32_t b = 0; b < 9; ++b)
+                        if (P.kslot[b] == s && (g.cw_base[b] + (uint64_t)P.ncw[s] * tm + cl) % 3 == v) list.push_back({b | cl << 4, (int32_t)(9u * P.kk[s] * cl + b)});
+                const uint32_t np = ((uint32_t)list.size() + 31u) / 32u;
+                if (pass0 + np > SUP_MAX_PASS) return false;
+                passes.assign(np, Pass{});
+                for (auto& p : passes) { p.n = 0; for (int i = 0; i < 128; ++i) p.occ[i] = -1; }
+                for (uint32_t i = 0; i < np * 32u; ++i) h_map[(tm * SUP_MAX_PASS + pass0) * 32 + i] = (uint16_t)SUP_IDLE;
+                for (uint32_t p = 0; p < np; ++p) h_kv[tm * SUP_MAX_PASS + pass0 + p] = (uint8_t)(s | v << 2);
+                auto clash = [](const Pass& p, int32_t a) {
+                    for (int d = -3; d <= 3; ++d) {
+                        const int32_t o = p.occ[((a + d) % 128 + 128) % 128];
+                        if (o >= 0 && (o - a > 3 || a - o > 3)) return true;
                     }
+                    return false;
+                };
+                for (const auto& e : list) {
+                    int best = -1;
+                    for (uint32_t p = 0; p < np && best < 0; ++p) if (passes[p].n < 32 && !clash(passes[p], e.second)) best = (int)p;
+                    for (uint32_t p = 0; p < np && best < 0; ++p) if (passes[p].n < 32) best = (int)p; // no clean place left: take the clash
+                    Pass& q = passes[best];
+                    h_map[(tm * SUP_MAX_PASS + pass0 + best) * 32 + q.n++] = (uint16_t)e.first;
+                    q.occ[(e.second % 128 + 128) % 128] = e.second;
+                }
+                pass0 += np;
             }
-        P.npass[tm] = pass;
+        npass[tm] = pass0;
     }
     return true;
 }

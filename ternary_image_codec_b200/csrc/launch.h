@@ -13,7 +13,7 @@ struct HeaderCache { uint8_t* d52 = nullptr; uint8_t* d27 = nullptr; t3c_config 
 // Phase-B pass maps of the super-tile kernels (k_super.cuh): they depend on the per-band k and on cw_base mod 3 only; one slot
 // per kernel flavour (encode / decode x RGB / raw words), re-uploaded when the key changes.
 struct SuperCache {
-    struct Slot { uint16_t* d_map = nullptr; uint8_t* d_kv = nullptr; uint8_t key[48] = {}; bool valid = false; } slot[4];
+    struct Slot { uint16_t* d_map = nullptr; uint8_t* d_kv = nullptr; uint8_t key[48] = {}; uint32_t npass[3] = {}; bool valid = false; } slot[4];
 };
 struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; SuperCache* sup; };
 // first codeword of every band that the general kernels still have to code (the tiled kernels did the ones before)
@@ -62,6 +62,7 @@ int launch_decode_fixed_general_from(const DevTables& T, const Geom& g, const ui
 // super-tile kernels (k_super.cuh): per-band k, 2D tiles whose width divides 26, beacon periods 3..255.  They code the full
 // super-tiles of every frame and report what is left in *tail; 0 = not applicable (nothing launched, *tail = everything)
 bool super_path_ok(const t3c_config& cfg);
+int super_debug_counters(uint32_t* out32);
 int launch_encode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in, size_t in_pitch, bool words, size_t n_px,
                         size_t n_frames, uint8_t* out9, size_t stride_words, cudaStream_t st, SuperTail* tail);
 int launch_decode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in9, size_t stride_words, size_t n_frames, uint8_t* out,

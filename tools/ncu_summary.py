@@ -36,8 +36,12 @@ def main():
     raw = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     hdr, units = raw[0], raw[1]
     names = []
+    done_raw = set()
     for r in raw[2:]:
         name = r[hdr.index("Kernel Name")]
+        if name in done_raw:
+            continue
+        done_raw.add(name)
         short = name.split("(")[0].split("::")[-1]
         names.append(short)
         w.write(f"== {short}  [{name[:110]}]\n")
@@ -66,6 +70,9 @@ def main():
         h = hs[0]
         iline, isrc, iaddr, isass = 0, 1, 2, 3
         ie, iw, ii = h.index("Instructions Executed"), h.index("L1 Wavefronts Shared"), h.index("L1 Wavefronts Shared Ideal")
+        ismp = h.index("# Samples") if "# Samples" in h else -1
+        stall_cols = [(i, c[6:]) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
+        samples = collections.OrderedDict()   # (file, line) -> [n, Counter(reason)]
         fpath = ""
         lines = collections.OrderedDict()
         ops = collections.Counter()
@@ -81,6 +88,12 @@ def main():
                 key = (fpath, int(r[iline]))
                 e = lines.setdefault(key, [0, 0, 0, r[isrc].strip()[:100]])
                 e[0] += int(r[ie]); e[1] += int(r[iw]) if r[iw].isdigit() else 0; e[2] += int(r[ii]) if r[ii].isdigit() else 0
+                if ismp >= 0 and r[ismp].isdigit():
+                    se = samples.setdefault(key, [0, collections.Counter(), r[isrc].strip()[:100]])
+                    se[0] += int(r[ismp])
+                    for i, name in stall_cols:
+                        if r[i].isdigit() and r[i] != "0":
+                            se[1][name] += int(r[i])
             elif r[iline] == "" and r[ie].isdigit():
                 op = r[isass].split()
                 if op:
@@ -97,6 +110,11 @@ def main():
         for (f, ln), v in sorted(lines.items(), key=lambda kv: -kv[1][1])[:14]:
             if v[1]:
                 w.write(f"     {100 * v[1] / totw:5.1f}%  x{v[1] / max(1, v[2]):.2f}  {f}:{ln:<4d} {v[3]}\n")
+        tots = sum(v[0] for v in samples.values()) or 1
+        if samples:
+            w.write("   top lines by warp-stall samples (where warps wait; top reasons):\n")
+            for (f, ln), v in sorted(samples.items(), key=lambda kv: -kv[1][0])[:16]:
+                w.write(f"     {100 * v[0] / tots:5.1f}%  {f}:{ln:<4d} {v[2][:70]}  [" + ", ".join(f"{a}={100 * b / tots:.1f}%" for a, b in v[1].most_common(3)) + "]\n")
     open(out, "w").write(w.getvalue())
     print(w.getvalue())
 
