@@ -157,6 +157,11 @@ T3C_API int t3c_fast_path_available(const t3c_config* cfg);
 /* 1 = the super-tile kernels take this config (per-band k >= 20, 2D tile widths dividing 26, beacon periods 3..255); they run when
  * t3c_fast_path_available is 0, the general kernels otherwise keep only the ragged end of a frame */
 T3C_API int t3c_super_path_available(const t3c_config* cfg);
+/* host-only (no device needed): the plan of the super-tile kernels for one super-frame of n_raw_words: out16 = {M band symbols per
+ * super-tile, units (6 pixels) per super-tile, full super-tiles, number of distinct k, k[4], codewords per band and super-tile [4],
+ * phase-B passes per super-tile index mod 3 [3], shared memory bytes}; map (3 x 64 x 32 entries band | codeword << 4, 0xFFFF = idle lane)
+ * and pass_kv (3 x 64: k slot | scrambler variant << 2) may be NULL.  Returns 0 when the super-tile kernels do not take the config. */
+T3C_API int t3c_super_plan_describe(const t3c_config* cfg, size_t n_raw_words, int decode, int words, uint32_t* out16, uint16_t* map, uint8_t* pass_kv);
 /* development aid: per-phase cycle counters of the super-tile kernels (32 values, read and reset); 0 unless built with -DT3C_SUPER_DEBUG */
 T3C_API int t3c_debug_counters(uint32_t* out32);
 

@@ -66,7 +66,7 @@ _EXPORTS = [
     "t3c_encode_frames_rgb8", "t3c_decode_frames_rgb8", "t3c_rgb_to_quant_dev", "t3c_quant_to_rgb_dev",
     "t3c_pack_pixels_dev", "t3c_unpack_pixels_dev", "t3c_rs_encode_blocks_dev", "t3c_rs_decode_blocks_dev",
     "t3c_encode_profile_dev", "t3c_decode_profile_fixed_dev", "t3c_encode_frames_rgb8_dev",
-    "t3c_decode_frames_rgb8_dev", "t3c_fast_path_available", "t3c_super_path_available", "t3c_debug_counters",
+    "t3c_decode_frames_rgb8_dev", "t3c_fast_path_available", "t3c_super_path_available", "t3c_debug_counters", "t3c_super_plan_describe",
     "t3c_subword_stream", "t3c_words_from_subword_stream", "t3c_base243_pack", "t3c_base243_unpack", "t3c_words_to_base243",
     "t3c_v6new_pack_pixels", "t3c_v6new_unpack_pixels", "t3c_subword_stream_dev", "t3c_words_from_subword_stream_dev",
     "t3c_base243_pack_dev", "t3c_base243_unpack_dev", "t3c_words_to_base243_dev", "t3c_v6new_pack_pixels_dev", "t3c_v6new_unpack_pixels_dev",
@@ -158,6 +158,20 @@ def profile_words(cfg: Config, n_raw_words: int) -> int:
 
 def fast_path_available(cfg: Config) -> bool:
     return bool(load_library().t3c_fast_path_available(C.byref(cfg)))
+
+
+def super_plan(cfg: Config, n_raw_words: int, decode: bool = False, words: bool = False):
+    """host-only: the super-tile plan for one super-frame, or None; dict with M, UN, n_tiles, k, ncw, npass, smem, map, pass_kv"""
+    L = load_library()
+    out = (C.c_uint32 * 16)()
+    mp = np.zeros(3 * 64 * 32, np.uint16)
+    kv = np.zeros(3 * 64, np.uint8)
+    L.t3c_super_plan_describe.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    if not L.t3c_super_plan_describe(C.byref(cfg), n_raw_words, int(decode), int(words), out, mp.ctypes.data, kv.ctypes.data):
+        return None
+    v = list(out)
+    nk = v[3]
+    return dict(M=v[0], UN=v[1], n_tiles=v[2], k=v[4:4 + nk], ncw=v[8:8 + nk], npass=v[12:15], smem=v[15], map=mp.reshape(3, 64, 32), pass_kv=kv.reshape(3, 64))
 
 
 def super_path_available(cfg: Config) -> bool:

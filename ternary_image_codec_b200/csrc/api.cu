@@ -231,6 +231,10 @@ size_t t3c_profile_words(const t3c_config* cfg, size_t n_raw_words) { return cfg
 int t3c_fast_path_available(const t3c_config* cfg) { return cfg && fast_path_ok(*cfg) ? 1 : 0; }
 int t3c_super_path_available(const t3c_config* cfg) { return cfg && super_path_ok(*cfg) ? 1 : 0; }
 int t3c_debug_counters(uint32_t* out32) { return out32 ? super_debug_counters(out32) : 0; }
+int t3c_super_plan_describe(const t3c_config* cfg, size_t n_raw_words, int decode, int words, uint32_t* out16, uint16_t* map, uint8_t* pass_kv)
+{
+    return cfg && out16 ? super_plan_describe(*cfg, n_raw_words, decode, words, out16, map, pass_kv) : 0;
+}
 
 // =============================================================================================
 // device-pointer API

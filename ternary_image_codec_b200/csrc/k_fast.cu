@@ -1570,6 +1570,25 @@ uint32_t full_tiles(const Geom& g, uint64_t px_limit)
 
 // ---- super-tile kernels: launchers ------------------------------------------------------------
 bool super_path_ok(const t3c_config& cfg) { return super_config_ok(cfg); }
+// host-only view of the plan the super-tile kernels would use for one super-frame of n_words raw words (tests, tools):
+// out16 = {M, UN, n_tiles, nk, kk[4], ncw[4], npass[3], smem_bytes}; map / kv as uploaded to the device (may be null)
+int super_plan_describe(const t3c_config& cfg, size_t n_words, int decode, int words, uint32_t* out16, uint16_t* map, uint8_t* kv)
+{
+    Geom g;
+    make_geom(cfg, n_words, 1, g);
+    SuperPlan P;
+    if (!make_super_plan(cfg, g, decode != 0, words != 0, 2 * (uint64_t)n_words, P)) return 0;
+    static thread_local uint16_t h_map[3 * SUP_MAX_PASS * 32];
+    static thread_local uint8_t h_kv[3 * SUP_MAX_PASS];
+    uint32_t npass[3];
+    if (!build_super_maps(P, g, h_map, h_kv, npass)) return 0;
+    const uint32_t v[16] = {P.M, P.UN, P.n_tiles, P.nk, P.kk[0], P.kk[1], P.kk[2], P.kk[3], P.ncw[0], P.ncw[1], P.ncw[2], P.ncw[3],
+                            npass[0], npass[1], npass[2], P.smem_bytes};
+    std::memcpy(out16, v, sizeof v);
+    if (map) std::memcpy(map, h_map, sizeof h_map);
+    if (kv) std::memcpy(kv, h_kv, sizeof h_kv);
+    return 1;
+}
 // debug builds (-DT3C_SUPER_DEBUG): per-phase cycle counters of CTA 0, read and reset
 int super_debug_counters(uint32_t* out32)
 {
@@ -1638,7 +1657,7 @@ static int super_launch(Kern kern, const DevTables& T, const FastParams& Q, cons
         }
     }
     const uint64_t total = (uint64_t)P.n_tiles * Q.n_frames;
-    uint64_t grid = 2ull * (uint64_t)T.sm_count;
+    uint64_t grid = (uint64_t)P.ctas_per_sm * (uint64_t)T.sm_count;
     if (const char* e = getenv("T3C_SUPER_GRID")) { const int v = atoi(e); if (v > 0) grid = (uint64_t)v; } // experiments only
     if (grid > total) grid = total;
     kern<<<(unsigned)grid, SUP_TPB, P.smem_bytes, st>>>(Q, P, g, T.gf, T.rs);

@@ -38,6 +38,7 @@ struct SuperPlan {
     uint32_t slot, bsym;
     uint32_t tile_w, tile_area, tile_h26, h26_magic; // tile_h26: tile height when the width is 26 (rows = units: reversed in registers), else 0; floor(2^32 / h) + 1
     uint32_t ch_shift;      // log2 of the per-band slot count of the flattened 16-byte chunk loops
+    uint32_t ctas_per_sm;   // 2 when two CTAs' shared memory fits one SM, else 1
     const uint16_t* map;    // [3][SUP_MAX_PASS * 32]: b | cl << 4, SUP_IDLE = idle lane
     const uint8_t* pass_kv; // [3][SUP_MAX_PASS]: k slot | variant << 2
 };
@@ -505,10 +506,12 @@ static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, b
     }
     if (g.tile_area) { P.tile_w = g.tile_w; P.tile_area = (uint32_t)g.tile_area; P.tile_h26 = (g.tile_w == 26 && g.tile_area > 26 && (g.n_s / 26 + 1) * (g.tile_area / 26) < (1ull << 32)) ? (uint32_t)(g.tile_area / 26) : 0u; if (P.tile_h26) P.h26_magic = (uint32_t)((1ull << 32) / P.tile_h26) + 1u; }
     const uint32_t pixb = words ? 27u : 18u;
-    const uint32_t budget = (227u * 1024u - 2048u) / 2u - (decode ? 256u : 0u); // two CTAs per SM
-    // the largest multiple of l that fits
+    // the largest multiple of l that fits two CTAs per SM; one CTA per SM when even l itself does not (k = 24/22: M = 3432)
     bool found = false;
+    for (uint32_t per_sm = 2; per_sm >= 1 && !found; --per_sm)
     for (uint32_t mult = 16; mult >= 1 && !found; --mult) {
+        const uint32_t budget = (227u * 1024u - 1024u * per_sm) / per_sm - (decode ? 256u : 0u);
+        P.ctas_per_sm = per_sm;
         const uint32_t M = l * mult;
         if (9u * M % 26u) continue;
         uint32_t n_cw = 0, off = 0, runs = 0, raws = 0;

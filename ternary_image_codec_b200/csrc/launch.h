@@ -63,6 +63,7 @@ int launch_decode_fixed_general_from(const DevTables& T, const Geom& g, const ui
 // super-tiles of every frame and report what is left in *tail; 0 = not applicable (nothing launched, *tail = everything)
 bool super_path_ok(const t3c_config& cfg);
 int super_debug_counters(uint32_t* out32);
+int super_plan_describe(const t3c_config& cfg, size_t n_words, int decode, int words, uint32_t* out16, uint16_t* map, uint8_t* kv);
 int launch_encode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in, size_t in_pitch, bool words, size_t n_px,
                         size_t n_frames, uint8_t* out9, size_t stride_words, cudaStream_t st, SuperTail* tail);
 int launch_decode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in9, size_t stride_words, size_t n_frames, uint8_t* out,

