@@ -202,6 +202,21 @@ inline void deinterleave2D_boustrophedon(std::vector<GF27>& syms, Tile2D tile)
     t3c_interleave2d(t3c_shim::context(), syms.data(), syms.size(), tile.w, tile.h, 1);
 }
 
+// ---- Subword helpers (OLD:835-859): the first N trits of every word as one trit per element, and back
+inline void extract_subword_stream_from_words(const std::vector<Word27>& words, int N, std::vector<UTrit>& out)
+{
+    out.assign(N > 0 ? words.size() * (size_t)N : 0, 0);
+    if (!out.empty()) t3c_subword_stream(t3c_shim::context(), reinterpret_cast<const uint8_t*>(words.data()), words.size(), N, out.data());
+}
+inline void build_words_from_subword_stream(const std::vector<UTrit>& in, int N, std::vector<Word27>& out, UTrit fill = 0)
+{
+    out.clear();
+    if (in.empty() || N <= 0) return;
+    out.assign((in.size() + (size_t)N - 1) / (size_t)N, Word27{});
+    size_t n = 0;
+    t3c_words_from_subword_stream(t3c_shim::context(), in.data(), in.size(), N, fill, reinterpret_cast<uint8_t*>(out.data()), &n);
+}
+
 inline bool encode_profile_from_raw(const std::vector<Word27>& in, std::vector<Word27>& out, EncoderContext& ectx)
 {
     out.clear();

@@ -55,6 +55,23 @@ int main()
         std::printf("bytes[%d] %zu %016llx\n", variant, bytes.size(), (unsigned long long)fnv(bytes.data(), bytes.size()));
     }
 
+    // sub-word trit streams and base-243 packing (what the .t3p writer does: old/include/t3p_io.hpp:19)
+    for (int N : {27, 24, 15}) {
+        std::vector<UTrit> trits, back_t;
+        extract_subword_stream_from_words(raw, N, trits);
+        std::vector<uint8_t> packed;
+        tpack::ut_to_base243(trits, packed);
+        const bool uok = tpack::base243_to_ut(packed, back_t);
+        std::vector<Word27> rebuilt;
+        build_words_from_subword_stream(back_t, N, rebuilt, (UTrit)1);
+        std::printf("subword[%d] %zu %016llx packed %zu %016llx back %d %zu words %zu %016llx\n", N, trits.size(),
+                    (unsigned long long)fnv(trits.data(), trits.size()), packed.size(), (unsigned long long)fnv(packed.data(), packed.size()), (int)uok,
+                    back_t.size(), rebuilt.size(), (unsigned long long)fnv(rebuilt.data(), rebuilt.size() * 9));
+        packed.pop_back();
+        const bool sok = tpack::base243_to_ut(packed, back_t); // one payload byte short of the count it announces
+        std::printf("subword_short[%d] %d %zu %016llx\n", N, (int)sok, back_t.size(), (unsigned long long)fnv(back_t.data(), back_t.size()));
+    }
+
     // block-level RS with the reference's selftest data
     GF27Context gf;
     gf.init();
