@@ -115,22 +115,24 @@ __device__ __forceinline__ uint8_t gsub(const GfTables& g, uint32_t a, uint32_t 
 // logical sizes never exceed r+1 <= 9).  fixed selects the Forney sign (bug B2 / Appendix B).
 // c[] is corrected in place in ascending position order, including the partial corrections the
 // reference leaves behind when it bails out on a zero derivative.
-static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t* c, int k, bool fixed)
+// Two things are done differently from the reference without changing any result:
+//  * polynomial evaluations start at the highest non-zero coefficient (leading zeros contribute nothing to a Horner sum);
+//  * with the repaired arithmetic, syndromes of the form S_j = e X^(j+1) (X != 0) are the one-error case: Berlekamp-Massey
+//    would find sigma = 1 - X x (the shortest recurrence is unique while 2L <= r), Chien its single root at position log X and
+//    Forney the magnitude e, so the correction c[log X] -= e is applied directly.
+static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c, int k, bool fixed, const uint8_t* S)
 {
     const int r = 26 - k, t = r >> 1;
-    uint8_t S[8];
-    bool all0 = true;
-    for (int j = 0; j < r; ++j) {
-        uint32_t acc = 0, e = 0;
-        for (int i = 0; i < 26; ++i) {
-            acc = gadd(g, acc, gmul(g, c[i], g.exp[e]));
-            e += j + 1;
-            if (e >= 26) e -= 26;
+    if (fixed && S[0]) { // one error?
+        const uint32_t X = gmul(g, S[1], g.inv[S[0]]);
+        bool one = X != 0;
+        for (int j = 1; j + 1 < r; ++j) one = one && S[j + 1] == gmul(g, S[j], X);
+        if (one) {
+            const uint32_t pos = g.lg[X], e = gmul(g, S[0], g.inv[X]);
+            c[pos] = gsub(g, c[pos], e);
+            return true;
         }
-        S[j] = (uint8_t)acc;
-        all0 = all0 && acc == 0;
     }
-    if (all0) return true;
     uint8_t sg[10], B[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) sg[i] = B[i] = 0;
@@ -159,12 +161,14 @@ static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t*
         for (int a = 0; a <= i; ++a) acc = gadd(g, acc, gmul(g, S[a], sg[i - a])); // i-a <= 7 < 10
         Om[i] = (uint8_t)acc;
     }
+    int top = 9;
+    while (top > 0 && sg[top] == 0) --top; // sg[0] = 1 always
     uint32_t roots = 0;
     int nroots = 0;
     for (int i = 0; i < 26; ++i) {
         const uint32_t x = g.exp[(26 - i) % 26];
-        uint32_t acc = 0;
-        for (int d = 9; d >= 0; --d) acc = gadd(g, gmul(g, acc, x), sg[d]);
+        uint32_t acc = sg[top];
+        for (int d = top - 1; d >= 0; --d) acc = gadd(g, gmul(g, acc, x), sg[d]);
         if (acc == 0) { roots |= 1u << i; ++nroots; }
     }
     if (nroots > t) return false;
@@ -173,17 +177,52 @@ static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t*
         const int im = i % 3;
         sp[i - 1] = im == 0 ? 0 : (im == 1 ? sg[i] : g.neg[sg[i]]); // 2a = -a in characteristic 3
     }
+    int tsp = top > 0 ? top - 1 : 0, tom = r - 1;
+    while (tsp > 0 && sp[tsp] == 0) --tsp;
+    while (tom > 0 && Om[tom] == 0) --tom;
     for (int pos = 0; pos < 26; ++pos) {
         if (!((roots >> pos) & 1)) continue;
         const uint32_t x = g.exp[(26 - pos) % 26];
-        uint32_t num = 0, den = 0;
-        for (int d = r - 1; d >= 0; --d) num = gadd(g, gmul(g, num, x), Om[d]);
-        for (int d = 8; d >= 0; --d) den = gadd(g, gmul(g, den, x), sp[d]);
+        uint32_t num = Om[tom], den = sp[tsp];
+        for (int d = tom - 1; d >= 0; --d) num = gadd(g, gmul(g, num, x), Om[d]);
+        for (int d = tsp - 1; d >= 0; --d) den = gadd(g, gmul(g, den, x), sp[d]);
         if (den == 0) return false;
         const uint32_t mag = gmul(g, g.neg[num], g.inv[den]);
         c[pos] = fixed ? gsub(g, c[pos], mag) : gadd(g, c[pos], mag);
     }
     return true;
+}
+// power-sum syndromes straight from the block (any arithmetic)
+static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t* c, int k, bool fixed)
+{
+    const int r = 26 - k;
+    uint8_t S[8];
+    bool all0 = true;
+    for (int j = 0; j < r; ++j) {
+        uint32_t acc = 0, e = 0;
+        for (int i = 0; i < 26; ++i) {
+            acc = gadd(g, acc, gmul(g, c[i], g.exp[e]));
+            e += j + 1;
+            if (e >= 26) e -= 26;
+        }
+        S[j] = (uint8_t)acc;
+        all0 = all0 && acc == 0;
+    }
+    if (all0) return true;
+    return rs_decode_core(g, c, k, fixed, S);
+}
+// repaired arithmetic only: syndromes from the parity residual p[0..r) = parity(received data) - received parity, which the
+// tiled kernels' syndrome screen has already computed (S_j = sum_m syn[j][m] p_m: r*r products instead of 26*r)
+static __device__ __forceinline__ bool rs_decode_residual(const GfTables& g, uint8_t* c, int k, const uint8_t* p)
+{
+    const int r = 26 - k, ki = (24 - k) >> 1;
+    uint8_t S[8];
+    for (int j = 0; j < r; ++j) {
+        uint32_t acc = 0;
+        for (int m = 0; m < r; ++m) acc = gadd(g, acc, gmul(g, p[m], g.syn[ki][j][m]));
+        S[j] = (uint8_t)acc;
+    }
+    return rs_decode_core(g, c, k, true, S);
 }
 
 // ---------------------------------------------------------------------------------------------

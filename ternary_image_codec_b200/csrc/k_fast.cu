@@ -826,10 +826,18 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
     for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
     gf3_add(acc, acc2.nz, acc2.two);
     if (((acc.nz ^ chk_nz) | (acc.two ^ chk_two)) & ~0xFFu) { // the low bytes carry the embedded symbols
-        // slow path: full decode of this codeword (descrambled), then rewrite its data symbols
-        uint8_t cwd[26], orig[26];
+        // slow path: full decode of this codeword (descrambled), then rewrite its data symbols.  The screen's sum minus the
+        // clean-codeword constant is the parity residual, from which the syndromes follow without another pass over the block
+        uint8_t cwd[26], orig[26], res[8];
         for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tab_v + src[i] + 128 * i);
-        if (!rs_decode_thread(sg, cwd, K, true)) {
+        {
+            Planes d{acc.nz, acc.two};
+            gf3_add(d, chk_nz, chk_nz ^ chk_two);                  // minus the constant: -x keeps nz and flips two where nz is set
+            const uint32_t nzp = d.nz >> 8, twp = d.two >> 8;
+            const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp), hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
+            for (int j = 0; j < 4; ++j) { res[j] = (uint8_t)(lo >> (8 * j)); res[4 + j] = (uint8_t)(hi >> (8 * j)); }
+        }
+        if (!rs_decode_residual(sg, cwd, K, res)) {
             atomicExch(&status[0], 0u);
         } else {
             uint32_t nfix = 0;

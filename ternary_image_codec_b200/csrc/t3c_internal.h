@@ -21,6 +21,10 @@ struct GfTables {
     uint8_t neg[32];    // 0-a
     uint8_t scr[3][32]; // scr[st][s] = s (+) 13*st   (scramble_symbol, OLD:81-87)
     uint8_t dsc[3][32]; // dsc[st][s] = s (-) 13*st   (descramble_symbol, OLD:88-94)
+    uint8_t lg[32];     // lg[alpha^e] = e, lg[0] = 255
+    // syn[kidx][j][m] = -(alpha^((j+1)(k+m))): the power-sum syndromes of a received block from its parity residual
+    // p = parity(received data) - received parity (repaired code):  S_j = sum_m syn[j][m] * p_m
+    uint8_t syn[4][8][8];
 };
 
 // Bit-plane row tables: the RS encoder as shipped (B1) and repaired are both GF(27)-linear maps

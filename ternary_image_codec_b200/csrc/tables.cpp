@@ -69,6 +69,10 @@ void build_tables(HostTables& T)
         }
     }
     for (int i = 0; i < 26; ++i) g.exp[i] = (uint8_t)ex[i];
+    for (int a = 0; a < 32; ++a) g.lg[a] = (uint8_t)((a > 0 && a < 27) ? lg[a] : 255);
+    for (int ki = 0; ki < 4; ++ki)
+        for (int j = 0; j < 8; ++j)
+            for (int m = 0; m < 8; ++m) g.syn[ki][j][m] = (uint8_t)gneg(ex[((j + 1) * (24 - 2 * ki + m)) % 26]);
     // sanity: table multiply agrees with the polynomial product
     for (int a = 0; a < 27; ++a)
         for (int b = 0; b < 27; ++b)
