@@ -163,13 +163,29 @@ static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c
     }
     int top = 9;
     while (top > 0 && sg[top] == 0) --top; // sg[0] = 1 always
+    // Chien search: positions i with sigma(alpha^-i) = 0.  Degrees 1 and 2 are solved instead of searched (the same root set):
+    // in characteristic 3, x^2 + b x + c = (x - b)^2 - (b^2 - c), so the roots are b +- sqrt(b^2 - c)
     uint32_t roots = 0;
     int nroots = 0;
-    for (int i = 0; i < 26; ++i) {
-        const uint32_t x = g.exp[(26 - i) % 26];
-        uint32_t acc = sg[top];
-        for (int d = top - 1; d >= 0; --d) acc = gadd(g, gmul(g, acc, x), sg[d]);
-        if (acc == 0) { roots |= 1u << i; ++nroots; }
+    if (top == 1) {
+        const uint32_t x = g.neg[g.inv[sg[1]]];                 // 1 + s1 x = 0
+        roots = 1u << ((26 - g.lg[x]) % 26);
+        nroots = 1;
+    } else if (top == 2) {
+        const uint32_t i2 = g.inv[sg[2]], b = gmul(g, sg[1], i2), q = g.sqr[gsub(g, gmul(g, b, b), i2)]; // x^2 + b x + 1/s2
+        if (q != 255) {
+            const uint32_t x1 = gadd(g, b, q), x2 = gsub(g, b, q);  // never 0: their product is 1/s2
+            roots = 1u << ((26 - g.lg[x1]) % 26);
+            roots |= 1u << ((26 - g.lg[x2]) % 26);
+            nroots = x1 == x2 ? 1 : 2;
+        }
+    } else {
+        for (int i = 0; i < 26; ++i) {
+            const uint32_t x = g.exp[(26 - i) % 26];
+            uint32_t acc = sg[top];
+            for (int d = top - 1; d >= 0; --d) acc = gadd(g, gmul(g, acc, x), sg[d]);
+            if (acc == 0) { roots |= 1u << i; ++nroots; }
+        }
     }
     if (nroots > t) return false;
     uint8_t sp[9];
@@ -180,8 +196,8 @@ static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c
     int tsp = top > 0 ? top - 1 : 0, tom = r - 1;
     while (tsp > 0 && sp[tsp] == 0) --tsp;
     while (tom > 0 && Om[tom] == 0) --tom;
-    for (int pos = 0; pos < 26; ++pos) {
-        if (!((roots >> pos) & 1)) continue;
+    for (uint32_t left = roots; left; left &= left - 1) { // ascending positions
+        const int pos = __ffs((int)left) - 1;
         const uint32_t x = g.exp[(26 - pos) % 26];
         uint32_t num = Om[tom], den = sp[tsp];
         for (int d = tom - 1; d >= 0; --d) num = gadd(g, gmul(g, num, x), Om[d]);

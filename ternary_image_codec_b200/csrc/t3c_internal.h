@@ -22,6 +22,7 @@ struct GfTables {
     uint8_t scr[3][32]; // scr[st][s] = s (+) 13*st   (scramble_symbol, OLD:81-87)
     uint8_t dsc[3][32]; // dsc[st][s] = s (-) 13*st   (descramble_symbol, OLD:88-94)
     uint8_t lg[32];     // lg[alpha^e] = e, lg[0] = 255
+    uint8_t sqr[32];    // sqr[a] = a square root of a (the other one is its negative), sqr[0] = 0, 255 when a is not a square
     // syn[kidx][j][m] = -(alpha^((j+1)(k+m))): the power-sum syndromes of a received block from its parity residual
     // p = parity(received data) - received parity (repaired code):  S_j = sum_m syn[j][m] * p_m
     uint8_t syn[4][8][8];

@@ -70,6 +70,9 @@ void build_tables(HostTables& T)
     }
     for (int i = 0; i < 26; ++i) g.exp[i] = (uint8_t)ex[i];
     for (int a = 0; a < 32; ++a) g.lg[a] = (uint8_t)((a > 0 && a < 27) ? lg[a] : 255);
+    for (int a = 0; a < 32; ++a) g.sqr[a] = 255;
+    g.sqr[0] = 0;
+    for (int e = 0; e < 26; e += 2) g.sqr[ex[e]] = (uint8_t)ex[e / 2]; // alpha^e is a square iff e is even
     for (int ki = 0; ki < 4; ++ki)
         for (int j = 0; j < 8; ++j)
             for (int m = 0; m < 8; ++m) g.syn[ki][j][m] = (uint8_t)gneg(ex[((j + 1) * (24 - 2 * ki + m)) % 26]);

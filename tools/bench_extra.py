@@ -80,14 +80,47 @@ def uep2d(all_t=False):
     def D(): codec.decode_frames_rgb8_dev(enc, wpf, wpf, 1, N_PX, back, status, cfg, S)
     te = timeit(E, n=5, warm=2)
     td_clean = timeit(D, n=5, warm=2)
-    # one symbol error in every 26-symbol stretch of the body (beacon expansion ignored: <= 1 per codeword, <= t)
-    body = enc[52:]
-    idx = torch.arange(7, body.numel() - 30, 27 if not all_t else 9, device=dev)
-    body[idx] = (body[idx] + 1) % 27
-    td_err = timeit(D, n=3, warm=1)
+    # injected symbol errors (BASELINE config 2: "up to t"): in codeword c of band b (t_b = (26-k_b)/2), n errors at distinct positions
+    # 3, 11, 19 (+ c mod 7), each symbol + (1 + c mod 26) mod 27; the beacon expansion (A.5) maps body index -> frame index
+    ks = [24, 22, 20, 18]
+    kb = [ks[u % 4] for u in t3.UEP_LUMA_PRIORITY]
+    n_s = (26 * (N_PX // 2) + 2) // 3
+    ncw = [((n_s - b + 8) // 9) // kb[b] for b in range(9)]
+    P, slot = 26, 2
+    clean = enc.clone()
+
+    def inject(mode):
+        enc.copy_(clean)
+        body = enc[52:]
+        base = 0
+        total = 0
+        for b in range(9):
+            t_b = (26 - kb[b]) // 2
+            c = torch.arange(ncw[b], device=dev, dtype=torch.int64)
+            n_err = torch.full_like(c, t_b) if mode == "t" else (torch.ones_like(c) if mode == "one" else c % (t_b + 1))
+            for j in range(t_b):
+                sel = n_err > j
+                cc = c[sel]
+                p = 26 * (base + cc) + 3 + 8 * j + cc % 7
+                blk, rem = p // (9 * P - 1), p % (9 * P - 1)
+                o = torch.where(rem < 8, 9 * blk * P + torch.where(rem < slot, rem, rem + 1), 9 * (blk * P + 1 + (rem - 8) // 9) + (rem - 8) % 9)
+                body[o] = ((body[o].to(torch.int64) + 1 + cc % 26) % 27).to(torch.uint8)
+                total += int(sel.sum())
+            base += ncw[b]
+        return total
+
+    res = {}
+    for mode in ("one", "mixed", "t"):
+        n_inj = inject(mode)
+        res[mode] = {"us": timeit(D, n=3, warm=1) * 1e3, "injected": n_inj, "status": status.tolist()}
+        assert status[0].item() == 1 and status[1].item() == n_inj, (mode, status.tolist(), n_inj)
+    td_err = res["one"]["us"] / 1e3
+    enc.copy_(clean)
+    D(); torch.cuda.synchronize()
     alg = 3 * N_PX + 9 * wpf
     print(json.dumps({"workload": "uep2d: 8K, P5 2D 26x26 + luma UEP + coset C1 + beacon(26,2), super-tile kernels" if t3.super_path_available(cfg) else "uep2d (general kernels)", "encode_us": te * 1e3,
-                      "decode_clean_us": td_clean * 1e3, "decode_with_errors_us": td_err * 1e3, "status": status.tolist(),
+                      "decode_clean_us": td_clean * 1e3, "decode_with_errors_us": td_err * 1e3,
+                      "decode_errors": {"one per codeword": res["one"], "0..t per codeword": res["mixed"], "t per codeword": res["t"]}, "status": status.tolist(),
                       "encode_gbs": alg / te / 1e6, "decode_clean_gbs": alg / td_clean / 1e6, "mpix_per_s_enc_plus_dec_clean": N_PX / (te + td_clean) / 1e3,
                       "profile_words": wpf}))
 
