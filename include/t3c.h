@@ -190,6 +190,22 @@ T3C_API t3c_status t3c_words_to_base243_dev(t3c_ctx*, const uint8_t* d_words9, s
 T3C_API t3c_status t3c_v6new_pack_pixels_dev(t3c_ctx*, const t3c_pixel* d_px, size_t n_px, uint32_t* d_words, void* stream);
 T3C_API t3c_status t3c_v6new_unpack_pixels_dev(t3c_ctx*, const uint32_t* d_words, size_t n_words, t3c_pixel* d_px, void* stream);
 
+/* 8(f).1 the .t3v container's records (old/include/t3v_io.hpp).  A frame record is n (uint32 LE) | 9n symbol bytes, each % 27 |
+ * crc32(payload) ^ (crc32(&n, 4) * 16777619) (t3v_write_frame, :128-142); CRC-32 is the reflected 0xEDB88320 one (:14-40). */
+T3C_API t3c_status t3c_crc32(t3c_ctx*, const uint8_t* data, size_t n, uint32_t* crc);
+T3C_API t3c_status t3c_t3v_frame_record(t3c_ctx*, const uint8_t* words9, size_t n_words, uint8_t* record /* 8 + 9n bytes */, size_t* n_bytes);
+/* t3v_read_frame, :143-160: *ok = 0 when the record is short or its CRC does not match (nothing written); symbols are returned as stored */
+T3C_API t3c_status t3c_t3v_read_frame(t3c_ctx*, const uint8_t* record, size_t n_bytes, uint8_t* words9, size_t cap_words, size_t* n_words, int* ok);
+/* t3v_write_header, :97-119: the 54-byte packed T3VHeaderBin, its last field the CRC-32 of the 50 bytes before it; aw = {x0, y0, w, h} */
+T3C_API t3c_status t3c_t3v_header(t3c_ctx*, uint8_t out54[54], int profile, int subword_code, int centered, int coset, uint32_t width, uint32_t height,
+                                  const uint32_t aw[4], uint32_t fps_num, uint32_t fps_den, uint32_t frame_count, int file_type);
+/* batched, device-resident: frame f of n_words words at d_words9 + f * 9 * stride_words <-> record f at d_records + f * record_pitch; all frame
+ * starts 4-byte aligned, record_pitch >= 8 + 9 n_words.  d_ok[f] = the record announces n_words and carries the right CRC */
+T3C_API t3c_status t3c_t3v_frame_records_dev(t3c_ctx*, const uint8_t* d_words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* d_records,
+                                             size_t record_pitch, void* stream);
+T3C_API t3c_status t3c_t3v_read_frames_dev(t3c_ctx*, const uint8_t* d_records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* d_words9,
+                                           size_t stride_words, uint8_t* d_ok, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,8 @@
 #include "ref_bridge_extract.inc"          // rgb_to_ycbcr, ycbcr_to_rgb, quantize_ycbcr, dequantize_ycbcr
 #include REF_TPACK_HEADER                  // <reference>/include/ternary_packing.hpp (tpack::), staged in the temp dir so that its own #include resolves to OLD
 
+#include "t3v_io.hpp" // <reference>/old/include: .t3v container
+
 #include "t3_oracle.h" // t3o_cfg / t3o_pixel layouts only
 
 static_assert(sizeof(Word27) == 9, "Word27 must be 9 bytes");
@@ -261,3 +263,51 @@ int t3r_base243_unpack(const uint8_t* in_bytes, size_t n_bytes, uint8_t* trits, 
 }
 
 } // extern "C"
+
+// ---- .t3v container records through the reference's own FILE* functions (old/include/t3v_io.hpp), on a tmpfile
+extern "C" {
+uint32_t t3r_crc32(const uint8_t* data, size_t n) { return t3v_detail::crc32(data, n); }
+size_t t3r_t3v_frame_record(const uint8_t* words9, uint32_t n_words, uint8_t* out)
+{
+    std::vector<Word27> w(n_words);
+    if (n_words) std::memcpy(w.data(), words9, 9 * (size_t)n_words);
+    FILE* f = std::tmpfile();
+    if (!f) return 0;
+    const bool ok = t3v_write_frame(f, w);
+    const long len = std::ftell(f);
+    std::rewind(f);
+    size_t got = ok && len > 0 ? std::fread(out, 1, (size_t)len, f) : 0;
+    std::fclose(f);
+    return got;
+}
+int t3r_t3v_read_frame(const uint8_t* rec, size_t n_bytes, uint8_t* words9, uint32_t* n_words)
+{
+    FILE* f = std::tmpfile();
+    if (!f) return 0;
+    if (n_bytes) std::fwrite(rec, 1, n_bytes, f);
+    std::rewind(f);
+    std::vector<Word27> w;
+    const bool ok = t3v_read_frame(f, w);
+    std::fclose(f);
+    *n_words = ok ? (uint32_t)w.size() : 0;
+    if (ok && !w.empty()) std::memcpy(words9, w.data(), 9 * w.size());
+    return ok ? 1 : 0;
+}
+size_t t3r_t3v_header(uint8_t* out, int profile, int subword, int centered, int coset, uint32_t w, uint32_t h, const uint32_t aw[4],
+                      uint32_t fps_num, uint32_t fps_den, uint32_t frame_count, int file_type, int* reads_back)
+{
+    FILE* f = std::tmpfile();
+    if (!f) return 0;
+    ActiveWindow a{};
+    a.x0 = (decltype(a.x0))aw[0]; a.y0 = (decltype(a.y0))aw[1]; a.w = (decltype(a.w))aw[2]; a.h = (decltype(a.h))aw[3];
+    const bool ok = t3v_write_header(f, (ProfileID)profile, (SubwordMode)subword, centered != 0, (CosetID)coset, w, h, a, fps_num, fps_den, frame_count, (uint8_t)file_type);
+    const long len = std::ftell(f);
+    std::rewind(f);
+    size_t got = ok && len > 0 ? std::fread(out, 1, (size_t)len, f) : 0;
+    std::rewind(f);
+    T3VHeaderBin hb{};
+    *reads_back = t3v_read_header(f, hb) ? 1 : 0;
+    std::fclose(f);
+    return got;
+}
+}

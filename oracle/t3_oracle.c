@@ -849,3 +849,52 @@ void t3o_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3o_pixel* p
         px[i].Crq = (int16_t)clampi((int32_t)Cr - 40, -40, 40);
     }
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * the .t3v container's records (old/include/t3v_io.hpp).  CRC-32 (reflected 0xEDB88320, init and final
+ * xor 0xFFFFFFFF), :14-40; a frame record is n (uint32 LE) | 9n symbol bytes, each % 27 | crc, with
+ * crc = crc32(payload) ^ (crc32(&n, 4) * 16777619), :128-142; the header is the 54-byte packed T3VHeaderBin whose last
+ * field is the CRC of the 50 bytes before it, :42-60,97-119. */
+uint32_t t3o_crc32(const uint8_t* data, size_t n)
+{
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; ++i) {
+        c ^= data[i];
+        for (int j = 0; j < 8; ++j) c = (c & 1u) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
+    }
+    return c ^ 0xFFFFFFFFu;
+}
+static void put32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+static uint32_t get32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+size_t t3o_t3v_frame_record(const uint8_t* words9, uint32_t n_words, uint8_t* out)
+{
+    const size_t nb = 9 * (size_t)n_words;
+    put32(out, n_words);
+    for (size_t i = 0; i < nb; ++i) out[4 + i] = (uint8_t)(words9[i] % 27);
+    put32(out + 4 + nb, t3o_crc32(out + 4, nb) ^ (t3o_crc32(out, 4) * 16777619u));
+    return 8 + nb;
+}
+int t3o_t3v_read_frame(const uint8_t* rec, size_t n_bytes, uint8_t* words9, uint32_t* n_words)
+{
+    *n_words = 0;
+    if (n_bytes < 4) return 0;
+    const uint32_t n = get32(rec);
+    const size_t nb = 9 * (size_t)n;
+    if (n_bytes < 8 + nb) return 0;                                  /* fread fails */
+    if ((t3o_crc32(rec + 4, nb) ^ (t3o_crc32(rec, 4) * 16777619u)) != get32(rec + 4 + nb)) return 0;
+    memcpy(words9, rec + 4, nb);                                     /* symbols are stored as read, not reduced again */
+    *n_words = n;
+    return 1;
+}
+void t3o_t3v_header(uint8_t out[54], int profile, int subword_code, int centered, int coset, uint32_t w, uint32_t h, const uint32_t aw[4],
+                    uint32_t fps_num, uint32_t fps_den, uint32_t frame_count, int file_type)
+{
+    memset(out, 0, 54);
+    memcpy(out, "T3V1", 4);
+    out[4] = 1; out[5] = (uint8_t)file_type; out[6] = (uint8_t)profile; out[7] = (uint8_t)subword_code; out[8] = centered ? 1 : 0; out[9] = (uint8_t)coset;
+    put32(out + 10, w); put32(out + 14, h);
+    for (int i = 0; i < 4; ++i) put32(out + 18 + 4 * i, aw[i]);
+    put32(out + 34, fps_num); put32(out + 38, fps_den); put32(out + 42, frame_count); put32(out + 46, 0);
+    put32(out + 50, t3o_crc32(out, 50));
+}

@@ -111,6 +111,12 @@ int    t3o_decode_rgb_fixed(const t3o_cfg* c, size_t n_px, const uint8_t* in9, s
 
 /* ---- sub-word streams + base-243 (OLD:816-859, include/ternary_packing.hpp:18-50) and the
  * NEW-generation RAW path (src/ternary_image_codec_v6_min.cpp:62-126: one pixel -> one 32-bit word, clamped) ---- */
+/* ---- .t3v container records (old/include/t3v_io.hpp) */
+uint32_t t3o_crc32(const uint8_t* data, size_t n);                                            /* t3v_detail::crc32, :14-40 */
+size_t   t3o_t3v_frame_record(const uint8_t* words9, uint32_t n_words, uint8_t* out);       /* t3v_write_frame, :128-142: 8 + 9n bytes */
+int      t3o_t3v_read_frame(const uint8_t* rec, size_t n_bytes, uint8_t* words9, uint32_t* n_words); /* t3v_read_frame, :143-160 */
+void     t3o_t3v_header(uint8_t out54[54], int profile, int subword_code, int centered, int coset, uint32_t w, uint32_t h, const uint32_t aw[4],
+                        uint32_t fps_num, uint32_t fps_den, uint32_t frame_count, int file_type); /* t3v_write_header, :97-119 */
 void   t3o_subword_stream(const uint8_t* words9, size_t n_words, int N, uint8_t* trits /* N*n_words */);
 size_t t3o_words_from_subword_stream(const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words9 /* ceil(n/N) */);
 size_t t3o_base243_pack(const uint8_t* trits, size_t n_trits, uint8_t* out /* 4 + ceil(n/5) */);

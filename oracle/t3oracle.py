@@ -88,9 +88,12 @@ class _Lib:
         self.fixed = fixed  # None: the library takes a `fixed` argument (oracle); else baked in (reference builds)
         L = self.lib
         sz, u8p = C.c_size_t, C.POINTER(C.c_uint8)
-        for name in ("encode_profile", "pack_pixels", "profile_words_bound", "bytes_to_words", "encode_rgb", "words_from_subword_stream", "base243_pack"):
+        for name in ("encode_profile", "pack_pixels", "profile_words_bound", "bytes_to_words", "encode_rgb", "words_from_subword_stream", "base243_pack",
+                     "t3v_frame_record"):
             if hasattr(L, pfx + name):
                 getattr(L, pfx + name).restype = sz
+        if hasattr(L, pfx + "crc32"):
+            getattr(L, pfx + "crc32").restype = C.c_uint32
         for name in ("gf_add", "gf_sub", "gf_mul", "gf_inv", "gf_pow_alpha", "scramble_symbol", "descramble_symbol", "beacon_symbol"):
             if hasattr(L, pfx + name):
                 getattr(L, pfx + name).restype = C.c_uint8
@@ -194,6 +197,25 @@ class _Lib:
         n = C.c_size_t()
         ok = self.f("base243_unpack")(dp, C.c_size_t(d.size), _ptr(out), C.c_size_t(cap), C.byref(n))
         return bool(ok), out[:min(n.value, cap)].copy()
+
+    # --- .t3v container records (same symbols in the oracle and the reference shim) ---
+    def crc32(self, data):
+        d, dp = _u8(data)
+        return int(self.f("crc32")(dp, C.c_size_t(d.size)))
+
+    def t3v_frame_record(self, words):
+        w, wp = _u8(words)
+        nw = w.size // 9
+        out = np.zeros(8 + 9 * nw, np.uint8)
+        n = self.f("t3v_frame_record")(wp, C.c_uint32(nw), _ptr(out))
+        return out[:n].copy()
+
+    def t3v_read_frame(self, rec):
+        r, rp = _u8(rec)
+        out = np.zeros((max(r.size, 9) // 9 + 1, 9), np.uint8)
+        n = C.c_uint32()
+        ok = self.f("t3v_read_frame")(rp, C.c_size_t(r.size), _ptr(out), C.byref(n))
+        return bool(ok), out[:n.value].copy()
 
     def rgb_to_quant(self, rgb):
         r, rp = _u8(rgb)

@@ -70,6 +70,7 @@ _EXPORTS = [
     "t3c_subword_stream", "t3c_words_from_subword_stream", "t3c_base243_pack", "t3c_base243_unpack", "t3c_words_to_base243",
     "t3c_v6new_pack_pixels", "t3c_v6new_unpack_pixels", "t3c_subword_stream_dev", "t3c_words_from_subword_stream_dev",
     "t3c_base243_pack_dev", "t3c_base243_unpack_dev", "t3c_words_to_base243_dev", "t3c_v6new_pack_pixels_dev", "t3c_v6new_unpack_pixels_dev",
+    "t3c_crc32", "t3c_t3v_frame_record", "t3c_t3v_read_frame", "t3c_t3v_header", "t3c_t3v_frame_records_dev", "t3c_t3v_read_frames_dev",
 ]
 
 _lib = None
@@ -142,6 +143,13 @@ def load_library() -> C.CDLL:
     L.t3c_words_to_base243_dev.argtypes = [vp, vp, sz, i32, vp, vp]
     L.t3c_v6new_pack_pixels_dev.argtypes = [vp, vp, sz, vp, vp]
     L.t3c_v6new_unpack_pixels_dev.argtypes = [vp, vp, sz, vp, vp]
+    u32 = C.c_uint32
+    L.t3c_crc32.argtypes = [vp, u8p, sz, C.POINTER(u32)]
+    L.t3c_t3v_frame_record.argtypes = [vp, u8p, sz, u8p, szp]
+    L.t3c_t3v_read_frame.argtypes = [vp, u8p, sz, u8p, sz, szp, C.POINTER(i32)]
+    L.t3c_t3v_header.argtypes = [vp, u8p, i32, i32, i32, i32, u32, u32, C.POINTER(u32), u32, u32, u32, i32]
+    L.t3c_t3v_frame_records_dev.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp]
+    L.t3c_t3v_read_frames_dev.argtypes = [vp, vp, sz, sz, sz, vp, sz, vp, vp]
     for name in _EXPORTS:
         getattr(L, name)  # AttributeError here = header and library out of sync
     _lib = L
@@ -284,6 +292,40 @@ class Codec:
             return False, px
         self._ck(st)
         return True, px
+
+    # --- .t3v container records (old/include/t3v_io.hpp)
+    def crc32(self, data):
+        d = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        out = C.c_uint32()
+        self._ck(self.lib.t3c_crc32(self.h, _p(d), d.size, C.byref(out)))
+        return int(out.value)
+
+    def t3v_write_frame(self, words):
+        w = np.ascontiguousarray(words, dtype=np.uint8).reshape(-1, 9)
+        rec = np.zeros(8 + 9 * w.shape[0], np.uint8)
+        n = C.c_size_t()
+        self._ck(self.lib.t3c_t3v_frame_record(self.h, _p(w), w.shape[0], _p(rec), C.byref(n)))
+        return rec[:n.value]
+
+    def t3v_read_frame(self, rec):
+        r = np.ascontiguousarray(rec, dtype=np.uint8).reshape(-1)
+        cap = max(r.size, 9) // 9 + 1
+        out = np.zeros((cap, 9), np.uint8)
+        n, ok = C.c_size_t(), C.c_int()
+        self._ck(self.lib.t3c_t3v_read_frame(self.h, _p(r), r.size, _p(out), cap, C.byref(n), C.byref(ok)))
+        return bool(ok.value), out[:n.value].copy()
+
+    def t3v_header(self, profile, subword_code, centered, coset, width, height, aw, fps_num=0, fps_den=1, frame_count=1, file_type=0):
+        out = np.zeros(54, np.uint8)
+        a = (C.c_uint32 * 4)(*aw)
+        self._ck(self.lib.t3c_t3v_header(self.h, _p(out), profile, subword_code, int(centered), coset, width, height, a, fps_num, fps_den, frame_count, file_type))
+        return out
+
+    def t3v_frame_records_dev(self, d_words, n_words, stride_words, n_frames, d_records, record_pitch, stream=0):
+        self._ck(self.lib.t3c_t3v_frame_records_dev(self.h, self._dp(d_words), n_words, stride_words, n_frames, self._dp(d_records), record_pitch, stream))
+
+    def t3v_read_frames_dev(self, d_records, record_pitch, n_frames, n_words, d_words, stride_words, d_ok, stream=0):
+        self._ck(self.lib.t3c_t3v_read_frames_dev(self.h, self._dp(d_records), record_pitch, n_frames, n_words, self._dp(d_words), stride_words, self._dp(d_ok), stream))
 
     def subword_stream_dev(self, d_words, n_words, N, d_trits, stream=0):
         self._ck(self.lib.t3c_subword_stream_dev(self.h, self._dp(d_words), n_words, N, self._dp(d_trits), stream))

@@ -987,4 +987,97 @@ t3c_status t3c_v6new_unpack_pixels(t3c_ctx* ctx, const uint32_t* words, size_t n
     return T3C_OK;
 }
 
+
+// ---- .t3v container records -----------------------------------------------------
+t3c_status t3c_t3v_frame_records_dev(t3c_ctx* ctx, const uint8_t* d_words, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* d_rec,
+                                     size_t record_pitch, void* st)
+{
+    if (!ctx || !d_rec || (n_words && !d_words)) return fail(ctx, T3C_ERR_ARG, "t3v_frame_records: null");
+    if (record_pitch < 8 + 9 * n_words || (record_pitch & 3) || ((uintptr_t)d_rec & 3) || ((uintptr_t)d_words & 3) || (n_frames > 1 && ((9 * stride_words) & 3)))
+        return fail(ctx, T3C_ERR_ARG, "t3v_frame_records: pitch / alignment");
+    DeviceGuard guard(ctx->device);
+    uint32_t* part = nullptr;
+    TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part));
+    return check_launch(ctx, launch_t3v_records(d_words, n_words, stride_words, n_frames, d_rec, record_pitch, part, (cudaStream_t)st));
+}
+t3c_status t3c_t3v_read_frames_dev(t3c_ctx* ctx, const uint8_t* d_rec, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* d_words,
+                                   size_t stride_words, uint8_t* d_ok, void* st)
+{
+    if (!ctx || !d_rec || !d_ok) return fail(ctx, T3C_ERR_ARG, "t3v_read_frames: null");
+    if (record_pitch < 8 + 9 * n_words || (record_pitch & 3) || ((uintptr_t)d_rec & 3) || ((uintptr_t)d_words & 3) || (n_frames > 1 && ((9 * stride_words) & 3)))
+        return fail(ctx, T3C_ERR_ARG, "t3v_read_frames: pitch / alignment");
+    DeviceGuard guard(ctx->device);
+    uint32_t* part = nullptr;
+    TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part));
+    return check_launch(ctx, launch_t3v_read(d_rec, record_pitch, n_frames, n_words, d_words, stride_words, part, d_ok, (cudaStream_t)st));
+}
+t3c_status t3c_crc32(t3c_ctx* ctx, const uint8_t* data, size_t n, uint32_t* crc)
+{
+    if (!ctx || !crc || (n && !data)) return fail(ctx, T3C_ERR_ARG, "crc32: null");
+    DeviceGuard guard(ctx->device);
+    uint8_t* d_in;
+    uint32_t* part;
+    TRY(reserve_t(ctx, B_IN, n + 16, &d_in));
+    TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words((n + 8) / 9, 1) + 64, &part));
+    if (n) H2D(d_in, data, n);
+    TRY(check_launch(ctx, launch_crc32(d_in, n, part + 16, part, ctx->stream)));
+    D2H(&ctx->h_mail->status[0], part, 4);
+    SYNC();
+    *crc = ctx->h_mail->status[0];
+    return T3C_OK;
+}
+t3c_status t3c_t3v_frame_record(t3c_ctx* ctx, const uint8_t* words, size_t n_words, uint8_t* record, size_t* n_bytes)
+{
+    if (!ctx || !record || !n_bytes || (n_words && !words)) return fail(ctx, T3C_ERR_ARG, "t3v_frame_record: null");
+    if (n_words > 0xFFFFFFFFull) return fail(ctx, T3C_ERR_ARG, "t3v_frame_record: the count is a uint32");
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    const size_t pitch = (8 + 9 * n_words + 3) & ~(size_t)3;
+    TRY(reserve_t(ctx, B_IN, 9 * n_words + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, pitch + 16, &d_out));
+    if (n_words) H2D(d_in, words, 9 * n_words);
+    TRY(t3c_t3v_frame_records_dev(ctx, d_in, n_words, n_words, 1, d_out, pitch, ctx->stream));
+    D2H(record, d_out, 8 + 9 * n_words);
+    SYNC();
+    *n_bytes = 8 + 9 * n_words;
+    return T3C_OK;
+}
+t3c_status t3c_t3v_read_frame(t3c_ctx* ctx, const uint8_t* record, size_t n_bytes, uint8_t* words, size_t cap_words, size_t* n_words, int* ok)
+{
+    if (!ctx || !n_words || !ok || (n_bytes && !record)) return fail(ctx, T3C_ERR_ARG, "t3v_read_frame: null");
+    *n_words = 0; *ok = 0;
+    if (n_bytes < 4) return T3C_OK;                                   // fread of the count fails
+    uint32_t n = 0;
+    std::memcpy(&n, record, 4);                                       // the count is container metadata, read on the host like a header
+    if (n_bytes < 8 + 9 * (size_t)n) return T3C_OK;                   // fread of the payload / CRC fails
+    if (cap_words < n) return fail(ctx, T3C_ERR_CAPACITY, "t3v_read_frame: capacity");
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    const size_t pitch = (8 + 9 * (size_t)n + 3) & ~(size_t)3;
+    TRY(reserve_t(ctx, B_IN, pitch + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * (size_t)n + 32, &d_out));
+    H2D(d_in, record, 8 + 9 * (size_t)n);
+    uint8_t* d_ok = d_out + ((9 * (size_t)n + 15) & ~(size_t)15);
+    TRY(t3c_t3v_read_frames_dev(ctx, d_in, pitch, 1, n, d_out, n, d_ok, ctx->stream));
+    D2H(&ctx->h_mail->status[0], d_ok, 1);
+    SYNC();
+    if (!(ctx->h_mail->status[0] & 0xFF)) return T3C_OK;              // CRC mismatch: the reference returns false and leaves `words` alone
+    if (n) { D2H(words, d_out, 9 * (size_t)n); SYNC(); }
+    *n_words = n; *ok = 1;
+    return T3C_OK;
+}
+t3c_status t3c_t3v_header(t3c_ctx* ctx, uint8_t out[54], int profile, int subword_code, int centered, int coset, uint32_t width, uint32_t height,
+                          const uint32_t aw[4], uint32_t fps_num, uint32_t fps_den, uint32_t frame_count, int file_type)
+{
+    if (!ctx || !out || !aw) return fail(ctx, T3C_ERR_ARG, "t3v_header: null");
+    auto put32 = [](uint8_t* p, uint32_t v) { for (int i = 0; i < 4; ++i) p[i] = (uint8_t)(v >> (8 * i)); };
+    std::memset(out, 0, 54);
+    std::memcpy(out, "T3V1", 4);
+    out[4] = 1; out[5] = (uint8_t)file_type; out[6] = (uint8_t)profile; out[7] = (uint8_t)subword_code; out[8] = centered ? 1 : 0; out[9] = (uint8_t)coset;
+    put32(out + 10, width); put32(out + 14, height);
+    for (int i = 0; i < 4; ++i) put32(out + 18 + 4 * i, aw[i]);
+    put32(out + 34, fps_num); put32(out + 38, fps_den); put32(out + 42, frame_count);
+    uint32_t crc = 0;
+    TRY(t3c_crc32(ctx, out, 50, &crc));                               // the checksum itself comes from the device, like every other one
+    put32(out + 50, crc);
+    return T3C_OK;
+}
 } // extern "C"

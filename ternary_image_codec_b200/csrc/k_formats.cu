@@ -190,3 +190,180 @@ int launch_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3c_pixel*
 }
 
 } // namespace t3c
+
+// =============================================================================================
+// the .t3v container's frame records (old/include/t3v_io.hpp:128-160) and its CRC-32 (:14-40).
+//   record = n (uint32 LE) | 9n symbol bytes, each % 27 | crc32(payload) ^ (crc32(&n, 4) * 16777619)
+// k_t3v_tiles:  one CTA = one tile of 256 segments x 128 payload bytes: coalesced 32-bit loads -> [% 27] -> coalesced stores into the
+//               record, a padded copy in shared memory (segment stride 33 words: conflict-free), then thread = segment: slice-by-4 CRC-32
+//               of its 128 bytes -> one partial CRC per segment
+// k_t3v_finish: one CTA per frame joins the partials: crc(A | B) = x^(8|B|) * crc(A) + crc(B) over GF(2)[x] / P (the identity behind
+//               zlib's crc32_combine); a thread walks a contiguous group of segments with the constant multiplier x^1024 as four
+//               256-entry tables, the groups are joined with the generic multiply.  Writes n and the record's CRC (or checks them).
+// =============================================================================================
+namespace t3c {
+namespace {
+
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+constexpr int T3V_SEG = 128, T3V_TPB = 256, T3V_TILE = T3V_SEG * T3V_TPB; // bytes
+
+// reflected polynomials: bit 31 is x^0.  a * b mod P (zlib's multmodp)
+__host__ __device__ inline uint32_t crc_mul(uint32_t a, uint32_t b)
+{
+    uint32_t m = 1u << 31, p = 0;
+    for (;;) {
+        if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; }
+        m >>= 1;
+        b = (b & 1u) ? (b >> 1) ^ CRC_POLY : b >> 1;
+    }
+    return p;
+}
+// x^(8 n) mod P by square and multiply
+__host__ __device__ inline uint32_t crc_xpow8(uint64_t n_bytes)
+{
+    uint32_t p = 1u << 31, sq = 1u << 23; // x^0, x^8
+    for (uint64_t n = n_bytes; n; n >>= 1) { if (n & 1) p = crc_mul(sq, p); sq = crc_mul(sq, sq); }
+    return p;
+}
+__device__ __forceinline__ uint32_t crc_byte_table(uint32_t i)
+{
+    uint32_t c = i;
+    for (int j = 0; j < 8; ++j) c = (c & 1u) ? (CRC_POLY ^ (c >> 1)) : (c >> 1);
+    return c;
+}
+__device__ __forceinline__ uint32_t mod27_word(uint32_t w)
+{
+    if ((((w & 0x7F7F7F7Fu) + 0x65656565u) | w) & 0x80808080u) { // some byte >= 27
+        uint32_t r = 0;
+        for (int q = 0; q < 4; ++q) r |= (((w >> (8 * q)) & 0xFFu) % 27u) << (8 * q);
+        return r;
+    }
+    return w;
+}
+// src / dst: frame f at + f * pitch; payload_off = where the 9n payload bytes start inside a frame of src / dst (0 or 4), both 4-byte aligned
+__global__ void __launch_bounds__(T3V_TPB) k_t3v_tiles(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t src_off, uint8_t* __restrict__ dst,
+                                                     uint64_t dst_pitch, uint32_t dst_off, uint64_t n_bytes, uint32_t tiles_per_frame, int reduce,
+                                                     uint32_t* __restrict__ partial)
+{
+    __shared__ uint32_t tab[4][256];
+    __shared__ uint32_t tile[T3V_TPB * 33];
+    const uint32_t tid = threadIdx.x, f = blockIdx.x / tiles_per_frame, t = blockIdx.x - f * tiles_per_frame;
+    tab[0][tid] = crc_byte_table(tid);
+    __syncthreads();
+    for (int k = 1; k < 4; ++k) tab[k][tid] = tab[0][tab[k - 1][tid] & 0xFFu] ^ (tab[k - 1][tid] >> 8);
+    const uint64_t b0 = (uint64_t)t * T3V_TILE, left = n_bytes - b0, nb = left < T3V_TILE ? left : T3V_TILE; // bytes of this tile
+    const uint8_t* s = src + f * src_pitch + src_off + b0;
+    uint8_t* d = dst ? dst + f * dst_pitch + dst_off + b0 : nullptr;
+    const uint32_t nw = (uint32_t)(nb >> 2);
+    for (uint32_t i = tid; i < nw; i += T3V_TPB) {
+        uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(s) + i);
+        if (reduce) w = mod27_word(w);
+        if (d) reinterpret_cast<uint32_t*>(d)[i] = w;
+        tile[(i >> 5) * 33 + (i & 31)] = w;
+    }
+    if (tid < (nb & 3)) { // the last 1..3 bytes of the frame
+        uint32_t b = s[4 * nw + tid];
+        if (reduce) b %= 27u;
+        if (d) d[4 * nw + tid] = (uint8_t)b;
+        reinterpret_cast<uint8_t*>(tile)[4 * ((nw >> 5) * 33 + (nw & 31)) + tid] = (uint8_t)b;
+    }
+    __syncthreads();
+    const uint64_t sb = (uint64_t)tid * T3V_SEG;
+    if (sb < nb) {
+        const uint32_t len = (uint32_t)(nb - sb < T3V_SEG ? nb - sb : T3V_SEG);
+        const uint32_t* p = tile + tid * 33;
+        uint32_t c = 0xFFFFFFFFu;
+        uint32_t i = 0;
+        for (; i + 4 <= len; i += 4) {
+            c ^= p[i >> 2];
+            c = tab[3][c & 0xFFu] ^ tab[2][(c >> 8) & 0xFFu] ^ tab[1][(c >> 16) & 0xFFu] ^ tab[0][c >> 24];
+        }
+        for (; i < len; ++i) c = tab[0][(c ^ reinterpret_cast<const uint8_t*>(p)[i]) & 0xFFu] ^ (c >> 8);
+        partial[(uint64_t)f * tiles_per_frame * T3V_TPB + (uint64_t)t * T3V_TPB + tid] = c ^ 0xFFFFFFFFu;
+    }
+}
+// check = 0: write n and the record's CRC into dst (record f at dst + f * pitch).  check = 1: compare them with what the record holds, ok[f]
+__global__ void __launch_bounds__(1024) k_t3v_finish(const uint32_t* __restrict__ partial, uint32_t tiles_per_frame, uint64_t n_bytes, uint32_t n_words,
+                                                   uint8_t* __restrict__ rec, uint64_t pitch, int check, uint8_t* __restrict__ ok, uint32_t* __restrict__ crc_out)
+{
+    __shared__ uint32_t tab[4][256];
+    __shared__ uint32_t red[1024];
+    const uint32_t tid = threadIdx.x, f = blockIdx.x;
+    const uint32_t x1024 = crc_xpow8(T3V_SEG);
+    if (tid < 256) for (int k = 0; k < 4; ++k) tab[k][tid] = crc_mul(x1024, tid << (8 * k));
+    __syncthreads();
+    const uint64_t n_seg = (n_bytes + T3V_SEG - 1) / T3V_SEG;            // the last one may be short
+    const uint64_t per = (n_seg + 1023) / 1024, g0 = (uint64_t)tid * per, g1 = g0 + per < n_seg ? g0 + per : n_seg;
+    const uint32_t* p = partial + (uint64_t)f * tiles_per_frame * T3V_TPB;
+    uint32_t acc = 0;
+    uint64_t covered = 0;                                                 // bytes acc stands for
+    for (uint64_t sgm = g0; sgm < g1; ++sgm) {
+        const uint64_t len = sgm + 1 == n_seg ? n_bytes - sgm * T3V_SEG : T3V_SEG;
+        if (len == T3V_SEG) acc = tab[0][acc & 0xFFu] ^ tab[1][(acc >> 8) & 0xFFu] ^ tab[2][(acc >> 16) & 0xFFu] ^ tab[3][acc >> 24];
+        else acc = crc_mul(crc_xpow8(len), acc);
+        acc ^= p[sgm];
+        covered += len;
+    }
+    // bytes after this thread's group
+    const uint64_t end = g1 * T3V_SEG < n_bytes ? g1 * T3V_SEG : n_bytes;
+    red[tid] = (g0 < g1 && n_bytes > end) ? crc_mul(crc_xpow8(n_bytes - end), acc) : acc;
+    (void)covered;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) { if (tid < (uint32_t)s) red[tid] ^= red[tid + s]; __syncthreads(); }
+    if (tid == 0 && crc_out) crc_out[f] = red[0];                         // plain crc32 of the payload
+    if (tid == 0 && rec) {
+        uint32_t cn = 0xFFFFFFFFu;                                        // crc32 of the four bytes of n
+        for (int i = 0; i < 4; ++i) { cn ^= (n_words >> (8 * i)) & 0xFFu; for (int j = 0; j < 8; ++j) cn = (cn & 1u) ? (CRC_POLY ^ (cn >> 1)) : (cn >> 1); }
+        cn ^= 0xFFFFFFFFu;
+        const uint32_t crc = red[0] ^ (cn * 16777619u);                   // crc32 of no bytes is 0: red[0] = 0 for an empty frame
+        uint8_t* r = rec + f * pitch;
+        if (!check) {
+            for (int i = 0; i < 4; ++i) { r[i] = (uint8_t)(n_words >> (8 * i)); r[4 + n_bytes + i] = (uint8_t)(crc >> (8 * i)); }
+        } else {
+            uint32_t n_in = 0, c_in = 0;
+            for (int i = 0; i < 4; ++i) { n_in |= (uint32_t)r[i] << (8 * i); c_in |= (uint32_t)r[4 + n_bytes + i] << (8 * i); }
+            ok[f] = (n_in == n_words && c_in == crc) ? 1 : 0;
+        }
+    }
+}
+
+} // namespace
+
+size_t t3v_partial_words(size_t n_words, size_t n_frames)
+{
+    const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE;
+    return (size_t)((tiles ? tiles : 1) * T3V_TPB * n_frames);
+}
+// words9 (frame f at + f * 9 * stride_words, 4-byte aligned) -> records (record f at + f * record_pitch, 4-byte aligned)
+int launch_t3v_records(const uint8_t* words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* records, size_t record_pitch, uint32_t* partial,
+                       cudaStream_t st)
+{
+    if (!n_frames) return 0;
+    const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE;
+    int n = 0;
+    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(words9, 9ull * stride_words, 0, records, record_pitch, 4, nb, (uint32_t)tiles, 1, partial); ++n; }
+    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(partial, (uint32_t)(tiles ? tiles : 1), nb, (uint32_t)n_words, records, record_pitch, 0, nullptr, nullptr);
+    return n + 1;
+}
+// records -> words9 (may be null: check only) and ok[f] = the record announces n_words and its CRC matches (t3v_read_frame)
+int launch_t3v_read(const uint8_t* records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* words9, size_t stride_words, uint32_t* partial,
+                    uint8_t* ok, cudaStream_t st)
+{
+    if (!n_frames) return 0;
+    const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE;
+    int n = 0;
+    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(records, record_pitch, 4, words9, 9ull * stride_words, 0, nb, (uint32_t)tiles, 0, partial); ++n; }
+    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(partial, (uint32_t)(tiles ? tiles : 1), nb, (uint32_t)n_words, const_cast<uint8_t*>(records), record_pitch, 1, ok, nullptr);
+    return n + 1;
+}
+// plain CRC-32 of n bytes (4-byte aligned) with the same two kernels
+int launch_crc32(const uint8_t* data, size_t n, uint32_t* partial, uint32_t* out, cudaStream_t st)
+{
+    const uint64_t tiles = ((uint64_t)n + T3V_TILE - 1) / T3V_TILE;
+    int k = 0;
+    if (tiles) { k_t3v_tiles<<<(unsigned)tiles, T3V_TPB, 0, st>>>(data, 0, 0, nullptr, 0, 0, n, (uint32_t)tiles, 0, partial); ++k; }
+    k_t3v_finish<<<1, 1024, 0, st>>>(partial, (uint32_t)(tiles ? tiles : 1), n, 0, nullptr, 0, 0, nullptr, out);
+    return k + 1;
+}
+
+} // namespace t3c

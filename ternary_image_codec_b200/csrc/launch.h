@@ -107,4 +107,12 @@ int launch_words_to_base243(const uint8_t* words9, size_t n_words, int N, uint8_
 int launch_v6new_pack_pixels(const t3c_pixel* px, size_t n_px, uint32_t* words, cudaStream_t st);
 int launch_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3c_pixel* px, cudaStream_t st);
 
+// .t3v frame records and CRC-32 (k_formats.cu); partial = scratch of t3v_partial_words(...) uint32
+size_t t3v_partial_words(size_t n_words, size_t n_frames);
+int launch_t3v_records(const uint8_t* words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* records, size_t record_pitch, uint32_t* partial,
+                       cudaStream_t st);
+int launch_t3v_read(const uint8_t* records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* words9, size_t stride_words, uint32_t* partial,
+                    uint8_t* ok, cudaStream_t st);
+int launch_crc32(const uint8_t* data, size_t n, uint32_t* partial, uint32_t* out, cudaStream_t st);
+
 } // namespace t3c

@@ -10,6 +10,7 @@
 
 #include "ternary_image_codec_v6_min.hpp"
 #include "ternary_packing.hpp"
+#include "t3v_io.hpp"
 
 static uint64_t fnv(const void* p, size_t n, uint64_t h = 1469598103934665603ull)
 {
@@ -70,6 +71,40 @@ int main()
         packed.pop_back();
         const bool sok = tpack::base243_to_ut(packed, back_t); // one payload byte short of the count it announces
         std::printf("subword_short[%d] %d %zu %016llx\n", N, (int)sok, back_t.size(), (unsigned long long)fnv(back_t.data(), back_t.size()));
+    }
+
+    // the .t3v container as old/src/main.cpp:21-25 and main_video_t3v.cpp:19-26 use it: header + frame records, then read back
+    {
+        FILE* f = std::tmpfile();
+        const ActiveWindow aw = centered_window(SubwordMode::S27);
+        const bool hok = t3v_write_header(f, ProfileID::P2_RS26_22, SubwordMode::S27, true, CosetID::C0, std_res_for(SubwordMode::S27).w,
+                                          std_res_for(SubwordMode::S27).h, aw, 30000, 1001, 2, 1);
+        std::vector<Word27> wild = raw;
+        for (size_t i = 0; i < wild.size(); i += 7) wild[i].sym[i % 9] = (GF27)(200 + i % 50); // stored % 27
+        const bool f1 = t3v_write_frame(f, raw), f2 = t3v_write_frame(f, wild);
+        const long len = std::ftell(f);
+        std::rewind(f);
+        std::vector<uint8_t> all((size_t)len);
+        const size_t got = std::fread(all.data(), 1, all.size(), f);
+        std::printf("t3v write %d %d %d %ld %016llx\n", (int)hok, (int)f1, (int)f2, len, (unsigned long long)fnv(all.data(), got));
+        std::rewind(f);
+        T3VHeaderBin hb{};
+        const bool rh = t3v_read_header(f, hb);
+        std::vector<Word27> r1, r2, r3;
+        const bool b1 = t3v_read_frame(f, r1), b2 = t3v_read_frame(f, r2), b3 = t3v_read_frame(f, r3);
+        std::printf("t3v read %d frames=%u sub=%d aw=%u,%u,%u,%u %d %zu %016llx %d %zu %016llx %d %zu\n", (int)rh, hb.frame_count, (int)t3v_header_subword(hb),
+                    t3v_header_aw(hb).x0, t3v_header_aw(hb).y0, t3v_header_aw(hb).w, t3v_header_aw(hb).h, (int)b1, r1.size(),
+                    (unsigned long long)fnv(r1.data(), r1.size() * 9), (int)b2, r2.size(), (unsigned long long)fnv(r2.data(), r2.size() * 9), (int)b3, r3.size());
+        std::fclose(f);
+        // a damaged record is rejected
+        all[54 + 4 + 100] ^= 1;
+        FILE* g = std::tmpfile();
+        std::fwrite(all.data(), 1, all.size(), g);
+        std::rewind(g);
+        const bool rh2 = t3v_read_header(g, hb);
+        const bool d1 = t3v_read_frame(g, r1);
+        std::printf("t3v damaged %d %d\n", (int)rh2, (int)d1);
+        std::fclose(g);
     }
 
     // block-level RS with the reference's selftest data

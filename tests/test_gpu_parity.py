@@ -688,3 +688,63 @@ def test_super_tile_kernels_rgb_frames(codec, oracle, t3, ci, n_px, nf):
             tot += ne
         ok2, rgb2, nc2 = codec.decode_frames_rgb8(bad, n_px, gc)
         assert ok2.all() and nc2 == tot and np.array_equal(rgb2, rgb)
+
+
+# ------------------------------------------------------------------ .t3v container records
+def test_t3v_records_and_crc32(codec, oracle):
+    import zlib
+    r = rng(960)
+    for n in (0, 1, 3, 4, 5, 127, 128, 129, 32767, 32768, 32769, 1000003):
+        data = r.integers(0, 256, n, dtype=np.uint8)
+        assert codec.crc32(data) == zlib.crc32(data.tobytes()) == oracle.crc32(data), n
+    for nw in (0, 1, 2, 14, 15, 3640, 3641, 3642, 20011, 300007):     # around one segment (128 B), one tile (32 KiB) and many tiles
+        words = r.integers(0, 27, size=(nw, 9), dtype=np.uint8)
+        if nw in (2, 20011):
+            words = r.integers(0, 256, size=(nw, 9), dtype=np.uint8)    # bytes >= 27 are stored % 27
+        rec = codec.t3v_write_frame(words)
+        assert np.array_equal(rec, oracle.t3v_frame_record(words)), nw
+        ok, back = codec.t3v_read_frame(rec)
+        ok_o, back_o = oracle.t3v_read_frame(rec)
+        assert ok and ok_o and np.array_equal(back, back_o) and np.array_equal(back, words % 27)
+        for blob in (rec[:-1], rec[:3], np.concatenate([rec, rec[:5]])):
+            ok2, w2 = codec.t3v_read_frame(blob)
+            ok3, w3 = oracle.t3v_read_frame(blob)
+            assert ok2 == ok3 and np.array_equal(w2, w3)
+        if nw:
+            bad = rec.copy()
+            bad[4 + int(r.integers(0, 9 * nw))] ^= 0x10
+            assert codec.t3v_read_frame(bad)[0] is False and oracle.t3v_read_frame(bad)[0] is False
+            bad = rec.copy()
+            bad[-2] ^= 1
+            assert codec.t3v_read_frame(bad)[0] is False
+    aw = (140, 0, 6280, 4320)
+    o = np.zeros(54, np.uint8)
+    import ctypes as C
+    oracle.lib.t3o_t3v_header(o.ctypes.data_as(C.c_void_p), 4, 2, 1, 1, 7680, 4320, (C.c_uint32 * 4)(*aw), 30000, 1001, 240, 1)
+    assert np.array_equal(codec.t3v_header(4, 2, True, 1, 7680, 4320, aw, 30000, 1001, 240, 1), o)
+
+
+def test_t3v_records_batched_device(codec, oracle):
+    import torch
+    dev = torch.device("cuda", 0)
+    n_words, nf = 50001, 3
+    stride = (n_words + 3) & ~3
+    pitch = (8 + 9 * n_words + 15) & ~15
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    words = torch.randint(0, 27, (nf, stride * 9), dtype=torch.uint8, device=dev, generator=g)
+    rec = torch.zeros(nf, pitch, dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    codec.t3v_frame_records_dev(words, n_words, stride, nf, rec, pitch, s)
+    back = torch.zeros_like(words)
+    okf = torch.zeros(nf, dtype=torch.uint8, device=dev)
+    rec[1, 4 + 777] ^= 3                                                  # frame 1 is damaged in transit
+    codec.t3v_read_frames_dev(rec, pitch, nf, n_words, back, stride, okf, s)
+    torch.cuda.synchronize()
+    assert okf.cpu().tolist() == [1, 0, 1]
+    rec[1, 4 + 777] ^= 3
+    for f in range(nf):
+        w = words[f, :9 * n_words].cpu().numpy().reshape(-1, 9)
+        assert np.array_equal(rec[f, :8 + 9 * n_words].cpu().numpy(), oracle.t3v_frame_record(w))
+        if f != 1:
+            assert torch.equal(back[f, :9 * n_words], words[f, :9 * n_words])

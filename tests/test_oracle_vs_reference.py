@@ -5,6 +5,8 @@ against oracle/_ref/libt3ref.so (the reference compiled as shipped) and libt3ref
 sources + the 3-line repair of SURVEY Appendix B), stage by stage and through the whole pipeline,
 plus the known answers captured in SURVEY Appendix C.  CPU only.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -419,3 +421,42 @@ def test_v6new_raw_path_matches_reference(oracle, ref_new):
     one = np.zeros(1, T.PIXEL_DTYPE)
     one["Yq"], one["Cbq"], one["Crq"] = 242, 40, 40
     assert int(oracle.v6new_pack_pixels(one)[0]) == 3 ** 13 - 1
+
+
+# ------------------------------------------------------------------ .t3v container records
+def test_t3v_records_match_reference_and_zlib(oracle, ref):
+    import zlib
+    r = rng(950)
+    for n in (0, 1, 3, 4, 5, 1000, 65537):
+        data = r.integers(0, 256, n, dtype=np.uint8)
+        assert oracle.crc32(data) == ref.crc32(data) == zlib.crc32(data.tobytes())
+    assert oracle.crc32(np.frombuffer(b"123456789", np.uint8)) == 0xCBF43926           # the CRC-32 check value
+    for nw in (0, 1, 2, 7, 1000, 20011):
+        words = r.integers(0, 256, size=(nw, 9), dtype=np.uint8)                        # bytes >= 27 are stored % 27
+        rec = oracle.t3v_frame_record(words)
+        assert np.array_equal(rec, ref.t3v_frame_record(words)) and rec.size == 8 + 9 * nw
+        assert int.from_bytes(rec[:4].tobytes(), "little") == nw and np.array_equal(rec[4:4 + 9 * nw], (words % 27).reshape(-1))
+        want_crc = zlib.crc32(rec[4:4 + 9 * nw].tobytes()) ^ ((zlib.crc32(rec[:4].tobytes()) * 16777619) & 0xFFFFFFFF)
+        assert int.from_bytes(rec[-4:].tobytes(), "little") == want_crc
+        for blob in (rec, rec[:-1], rec[:3], np.concatenate([rec, rec[:5]])):
+            ok_o, w_o = oracle.t3v_read_frame(blob)
+            ok_r, w_r = ref.t3v_read_frame(blob)
+            assert ok_o == ok_r and np.array_equal(w_o, w_r)
+        if nw:
+            bad = rec.copy()
+            bad[4 + int(r.integers(0, 9 * nw))] ^= 1
+            assert oracle.t3v_read_frame(bad)[0] is False and ref.t3v_read_frame(bad)[0] is False
+            ok_o, w_o = oracle.t3v_read_frame(rec)
+            assert ok_o and np.array_equal(w_o, words % 27)
+
+
+def test_t3v_header_matches_reference(oracle, ref):
+    aw = (C.c_uint32 * 4)(140, 0, 6280, 4320)
+    for prof, sub_mode, sub_code, cen, coset, ft, fc in ((1, 27, 0, 1, 0, 0, 1), (4, 15, 4, 0, 2, 1, 240), (2, 21, 2, 1, 1, 1, 0)):
+        o = np.zeros(54, np.uint8)
+        oracle.lib.t3o_t3v_header(o.ctypes.data_as(C.c_void_p), prof, sub_code, cen, coset, 7680, 4320, aw, 30000, 1001, fc, ft)
+        rr = np.zeros(64, np.uint8)
+        back = C.c_int()
+        ref.lib.t3r_t3v_header.restype = C.c_size_t
+        n = ref.lib.t3r_t3v_header(rr.ctypes.data_as(C.c_void_p), prof, sub_mode, cen, coset, 7680, 4320, aw, 30000, 1001, fc, ft, C.byref(back))
+        assert n == 54 and back.value == 1 and np.array_equal(o, rr[:54])

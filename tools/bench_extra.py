@@ -125,6 +125,33 @@ def uep2d(all_t=False):
                       "profile_words": wpf}))
 
 
+def t3v8k():
+    """.t3v frame records of an 8K frame's profile words (RS(26,20): 20.8 M words): emit (n | payload % 27 | CRC) and check"""
+    cfg = t3.make_config(profile=t3.P3_RS26_20, uep=2)
+    wpf = t3.profile_words(cfg, N_PX // 2)
+    NB = 3
+    stride = (wpf + 15) & ~15
+    pitch = (8 + 9 * wpf + 15) & ~15
+    g = torch.Generator(device=dev); g.manual_seed(6)
+    words = torch.randint(0, 27, (NB, stride * 9), dtype=torch.uint8, device=dev, generator=g)
+    rec = torch.zeros(NB, pitch, dtype=torch.uint8, device=dev)
+    back = torch.zeros_like(words)
+    okf = torch.zeros(1, dtype=torch.uint8, device=dev)
+    i = [0]
+    def W(): codec.t3v_frame_records_dev(words[i[0] % NB], wpf, stride, 1, rec[i[0] % NB], pitch, S); i[0] += 1
+    def R(): codec.t3v_read_frames_dev(rec[i[0] % NB], pitch, 1, wpf, back[i[0] % NB], stride, okf, S); i[0] += 1
+    tw = timeit(W)
+    tr = timeit(R)
+    import zlib
+    r0 = rec[0, :8 + 9 * wpf].cpu().numpy()
+    want = zlib.crc32(r0[4:-4].tobytes()) ^ ((zlib.crc32(r0[:4].tobytes()) * 16777619) & 0xFFFFFFFF)
+    assert int.from_bytes(r0[-4:].tobytes(), "little") == want and okf.item() == 1 and torch.equal(back[0, :9 * wpf], words[0, :9 * wpf])
+    alg = 2 * 9 * wpf
+    print(json.dumps({"workload": "t3v8k: .t3v frame record of an 8K frame's 20.8 M profile words (payload % 27 + CRC-32), emit and check", "write_us": tw * 1e3,
+                      "read_check_us": tr * 1e3, "write_gbs": alg / tw / 1e6, "read_gbs": alg / tr / 1e6, "write_frac_of_measured_peak": alg / tw / 1e6 / PEAK,
+                      "algorithmic_bytes": alg}))
+
+
 def stream240(frames_per_call=8):
     cfg = t3.make_config(profile=t3.P3_RS26_20, uep=2)
     wpf = t3.profile_words(cfg, N_PX // 2)
@@ -154,6 +181,6 @@ if __name__ == "__main__":
     def words():
         words8k(2, "words8k_k20: encode_profile_from_raw + consistent decode on 16.6 M raw words, RS(26,20) 1D")
         words8k(1, "words8k_default: the reference's default EncoderContext (P2, uniform k=22), raw words in/out")
-    which = sys.argv[1:] or ["words8k", "raw8k", "uep2d", "stream240"]
+    which = sys.argv[1:] or ["words8k", "raw8k", "uep2d", "t3v8k", "stream240"]
     for w in which:
-        {"words8k": words, "raw8k": raw8k, "uep2d": uep2d, "stream240": stream240}[w]()
+        {"words8k": words, "raw8k": raw8k, "uep2d": uep2d, "t3v8k": t3v8k, "stream240": stream240}[w]()
