@@ -25,6 +25,7 @@ struct t3c_ctx {
     HeaderCache hdr_cache{};
     SuperCache sup_cache{};
     void* d_tables = nullptr;
+    uint32_t* d_crc = nullptr; // CRC-32 tables of the .t3v record kernels
     HostTables* host = nullptr; // host copy of the constant tables (decoder screen constants are derived per call)
     // grow-only device scratch
     struct Buf { void* p = nullptr; size_t cap = 0; };
@@ -190,6 +191,15 @@ t3c_status t3c_create(int device, t3c_ctx** out)
     if (cudaMalloc((void**)&ctx->hdr_cache.d52, 128) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
     ctx->hdr_cache.d27 = ctx->hdr_cache.d52 + 64;
     ctx->tabs.sup = &ctx->sup_cache;
+    {
+        std::vector<uint32_t> h(crc_table_words());
+        build_crc_tables(h.data());
+        if (cudaMalloc((void**)&ctx->d_crc, 4 * h.size()) != cudaSuccess || cudaMemcpy(ctx->d_crc, h.data(), 4 * h.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            t3c_destroy(ctx);
+            return T3C_ERR_CUDA;
+        }
+        ctx->tabs.crc = ctx->d_crc;
+    }
     for (auto& sl : ctx->sup_cache.slot) {
         if (cudaMalloc((void**)&sl.d_map, 3 * 64 * 32 * sizeof(uint16_t) + 256) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
         sl.d_kv = reinterpret_cast<uint8_t*>(sl.d_map + 3 * 64 * 32);
@@ -205,6 +215,7 @@ void t3c_destroy(t3c_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->buf) if (b.p) cudaFree(b.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->hdr_cache.d52) cudaFree(ctx->hdr_cache.d52);
     for (auto& sl : ctx->sup_cache.slot) if (sl.d_map) cudaFree(sl.d_map);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
@@ -998,7 +1009,7 @@ t3c_status t3c_t3v_frame_records_dev(t3c_ctx* ctx, const uint8_t* d_words, size_
     DeviceGuard guard(ctx->device);
     uint32_t* part = nullptr;
     TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part));
-    return check_launch(ctx, launch_t3v_records(d_words, n_words, stride_words, n_frames, d_rec, record_pitch, part, (cudaStream_t)st));
+    return check_launch(ctx, launch_t3v_records(ctx->tabs.crc, d_words, n_words, stride_words, n_frames, d_rec, record_pitch, part, (cudaStream_t)st));
 }
 t3c_status t3c_t3v_read_frames_dev(t3c_ctx* ctx, const uint8_t* d_rec, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* d_words,
                                    size_t stride_words, uint8_t* d_ok, void* st)
@@ -1009,7 +1020,7 @@ t3c_status t3c_t3v_read_frames_dev(t3c_ctx* ctx, const uint8_t* d_rec, size_t re
     DeviceGuard guard(ctx->device);
     uint32_t* part = nullptr;
     TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part));
-    return check_launch(ctx, launch_t3v_read(d_rec, record_pitch, n_frames, n_words, d_words, stride_words, part, d_ok, (cudaStream_t)st));
+    return check_launch(ctx, launch_t3v_read(ctx->tabs.crc, d_rec, record_pitch, n_frames, n_words, d_words, stride_words, part, d_ok, (cudaStream_t)st));
 }
 t3c_status t3c_crc32(t3c_ctx* ctx, const uint8_t* data, size_t n, uint32_t* crc)
 {
@@ -1020,7 +1031,7 @@ t3c_status t3c_crc32(t3c_ctx* ctx, const uint8_t* data, size_t n, uint32_t* crc)
     TRY(reserve_t(ctx, B_IN, n + 16, &d_in));
     TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words((n + 8) / 9, 1) + 64, &part));
     if (n) H2D(d_in, data, n);
-    TRY(check_launch(ctx, launch_crc32(d_in, n, part + 16, part, ctx->stream)));
+    TRY(check_launch(ctx, launch_crc32(ctx->tabs.crc, d_in, n, part + 16, part, ctx->stream)));
     D2H(&ctx->h_mail->status[0], part, 4);
     SYNC();
     *crc = ctx->h_mail->status[0];

@@ -240,17 +240,30 @@ __device__ __forceinline__ uint32_t mod27_word(uint32_t w)
     }
     return w;
 }
-// src / dst: frame f at + f * pitch; payload_off = where the 9n payload bytes start inside a frame of src / dst (0 or 4), both 4-byte aligned
+// Device table buffer (built once per context by build_crc_tables): [0, 1024) slice-by-4 tables T0..T3; then nine shift tables
+// of 4 x 256 entries, table j multiplying a 32-bit remainder by x^(8 * 128 * 2^j) (j = 0: one segment ... j = 8: one tile); then
+// x^(8 * 2^i), i = 0..31, for the generic shift.
+constexpr int CRC_SHIFT0 = 1024, CRC_NSHIFT = 9, CRC_POW0 = CRC_SHIFT0 + CRC_NSHIFT * 1024;
+__device__ __forceinline__ uint32_t crc_shift(const uint32_t* __restrict__ t, uint32_t v) // t = one shift table (shared or global)
+{
+    return t[v & 0xFFu] ^ t[256 + ((v >> 8) & 0xFFu)] ^ t[512 + ((v >> 16) & 0xFFu)] ^ t[768 + (v >> 24)];
+}
+__device__ inline uint32_t crc_shift_bytes(const uint32_t* __restrict__ tabs, uint32_t v, uint64_t n_bytes) // v * x^(8 n)
+{
+    for (int i = 0; n_bytes; ++i, n_bytes >>= 1) if (n_bytes & 1) v = crc_mul(__ldg(tabs + CRC_POW0 + i), v);
+    return v;
+}
+// src / dst: frame f at + f * pitch; *_off = where the 9n payload bytes start inside a frame of src / dst (0 or 4), all 4-byte aligned.
+// out: one CRC per full tile at tile_crc[f * tiles + t]; the last, partial tile of a frame leaves one CRC per segment at seg_crc[f * 256 + s]
 __global__ void __launch_bounds__(T3V_TPB) k_t3v_tiles(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t src_off, uint8_t* __restrict__ dst,
                                                      uint64_t dst_pitch, uint32_t dst_off, uint64_t n_bytes, uint32_t tiles_per_frame, int reduce,
-                                                     uint32_t* __restrict__ partial)
+                                                     const uint32_t* __restrict__ tabs, uint32_t* __restrict__ tile_crc, uint32_t* __restrict__ seg_crc)
 {
-    __shared__ uint32_t tab[4][256];
+    __shared__ uint32_t tab[4 * 256];
     __shared__ uint32_t tile[T3V_TPB * 33];
+    __shared__ uint32_t red[T3V_TPB];
     const uint32_t tid = threadIdx.x, f = blockIdx.x / tiles_per_frame, t = blockIdx.x - f * tiles_per_frame;
-    tab[0][tid] = crc_byte_table(tid);
-    __syncthreads();
-    for (int k = 1; k < 4; ++k) tab[k][tid] = tab[0][tab[k - 1][tid] & 0xFFu] ^ (tab[k - 1][tid] >> 8);
+    for (int k = 0; k < 4; ++k) tab[256 * k + tid] = __ldg(tabs + 256 * k + tid);
     const uint64_t b0 = (uint64_t)t * T3V_TILE, left = n_bytes - b0, nb = left < T3V_TILE ? left : T3V_TILE; // bytes of this tile
     const uint8_t* s = src + f * src_pitch + src_off + b0;
     uint8_t* d = dst ? dst + f * dst_pitch + dst_off + b0 : nullptr;
@@ -269,6 +282,7 @@ __global__ void __launch_bounds__(T3V_TPB) k_t3v_tiles(const uint8_t* __restrict
     }
     __syncthreads();
     const uint64_t sb = (uint64_t)tid * T3V_SEG;
+    uint32_t crc = 0;
     if (sb < nb) {
         const uint32_t len = (uint32_t)(nb - sb < T3V_SEG ? nb - sb : T3V_SEG);
         const uint32_t* p = tile + tid * 33;
@@ -276,38 +290,48 @@ __global__ void __launch_bounds__(T3V_TPB) k_t3v_tiles(const uint8_t* __restrict
         uint32_t i = 0;
         for (; i + 4 <= len; i += 4) {
             c ^= p[i >> 2];
-            c = tab[3][c & 0xFFu] ^ tab[2][(c >> 8) & 0xFFu] ^ tab[1][(c >> 16) & 0xFFu] ^ tab[0][c >> 24];
+            c = tab[768 + (c & 0xFFu)] ^ tab[512 + ((c >> 8) & 0xFFu)] ^ tab[256 + ((c >> 16) & 0xFFu)] ^ tab[c >> 24];
         }
-        for (; i < len; ++i) c = tab[0][(c ^ reinterpret_cast<const uint8_t*>(p)[i]) & 0xFFu] ^ (c >> 8);
-        partial[(uint64_t)f * tiles_per_frame * T3V_TPB + (uint64_t)t * T3V_TPB + tid] = c ^ 0xFFFFFFFFu;
+        for (; i < len; ++i) c = tab[(c ^ reinterpret_cast<const uint8_t*>(p)[i]) & 0xFFu] ^ (c >> 8);
+        crc = c ^ 0xFFFFFFFFu;
     }
+    if (nb < T3V_TILE) { if (sb < nb) seg_crc[(uint64_t)f * T3V_TPB + tid] = crc; return; } // the frame's last tile: joined by k_t3v_finish
+    // a full tile: crc(A | B) = crc(A) x^(8|B|) + crc(B), pairwise over 1, 2, 4 ... 128 segments (shift tables 0..7, read through L1)
+    red[tid] = crc;
+    __syncthreads();
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t st = 1u << j;
+        if ((tid & (2 * st - 1)) == 0) red[tid] = crc_shift(tabs + CRC_SHIFT0 + 1024 * j, red[tid]) ^ red[tid + st];
+        __syncthreads();
+    }
+    if (tid == 0) tile_crc[(uint64_t)f * tiles_per_frame + t] = red[0];
 }
-// check = 0: write n and the record's CRC into dst (record f at dst + f * pitch).  check = 1: compare them with what the record holds, ok[f]
-__global__ void __launch_bounds__(1024) k_t3v_finish(const uint32_t* __restrict__ partial, uint32_t tiles_per_frame, uint64_t n_bytes, uint32_t n_words,
-                                                   uint8_t* __restrict__ rec, uint64_t pitch, int check, uint8_t* __restrict__ ok, uint32_t* __restrict__ crc_out)
+// One CTA per frame joins the tile CRCs (full tiles) and the last tile's segment CRCs.  check = 0: write n and the record's CRC into rec
+// (record f at rec + f * pitch); check = 1: compare them with what the record holds -> ok[f]; crc_out: the payload's plain CRC-32
+__global__ void __launch_bounds__(1024) k_t3v_finish(const uint32_t* __restrict__ tabs, const uint32_t* __restrict__ tile_crc, const uint32_t* __restrict__ seg_crc,
+                                                   uint32_t tiles_per_frame, uint64_t n_bytes, uint32_t n_words, uint8_t* __restrict__ rec, uint64_t pitch,
+                                                   int check, uint8_t* __restrict__ ok, uint32_t* __restrict__ crc_out)
 {
-    __shared__ uint32_t tab[4][256];
     __shared__ uint32_t red[1024];
     const uint32_t tid = threadIdx.x, f = blockIdx.x;
-    const uint32_t x1024 = crc_xpow8(T3V_SEG);
-    if (tid < 256) for (int k = 0; k < 4; ++k) tab[k][tid] = crc_mul(x1024, tid << (8 * k));
-    __syncthreads();
-    const uint64_t n_seg = (n_bytes + T3V_SEG - 1) / T3V_SEG;            // the last one may be short
-    const uint64_t per = (n_seg + 1023) / 1024, g0 = (uint64_t)tid * per, g1 = g0 + per < n_seg ? g0 + per : n_seg;
-    const uint32_t* p = partial + (uint64_t)f * tiles_per_frame * T3V_TPB;
+    const uint64_t n_full = n_bytes / T3V_TILE, tail = n_bytes - n_full * T3V_TILE;     // full tiles, bytes of the partial last tile
+    // threads 0..767 walk contiguous groups of full tiles, threads 768..1023 take one segment of the last tile each
     uint32_t acc = 0;
-    uint64_t covered = 0;                                                 // bytes acc stands for
-    for (uint64_t sgm = g0; sgm < g1; ++sgm) {
-        const uint64_t len = sgm + 1 == n_seg ? n_bytes - sgm * T3V_SEG : T3V_SEG;
-        if (len == T3V_SEG) acc = tab[0][acc & 0xFFu] ^ tab[1][(acc >> 8) & 0xFFu] ^ tab[2][(acc >> 16) & 0xFFu] ^ tab[3][acc >> 24];
-        else acc = crc_mul(crc_xpow8(len), acc);
-        acc ^= p[sgm];
-        covered += len;
+    uint64_t after = 0;                                                                   // payload bytes after what acc stands for
+    if (tid < 768) {
+        const uint64_t per = (n_full + 767) / 768, g0 = (uint64_t)tid * per, g1 = g0 + per < n_full ? g0 + per : n_full;
+        const uint32_t* p = tile_crc + (uint64_t)f * tiles_per_frame;
+        for (uint64_t t = g0; t < g1; ++t) acc = crc_shift(tabs + CRC_SHIFT0 + 1024 * 8, acc) ^ p[t];
+        after = g0 < g1 ? n_bytes - g1 * T3V_TILE : 0;
+    } else {
+        const uint64_t sb = (uint64_t)(tid - 768) * T3V_SEG;
+        if (sb < tail) {
+            const uint64_t len = tail - sb < T3V_SEG ? tail - sb : T3V_SEG;
+            acc = seg_crc[(uint64_t)f * T3V_TPB + (tid - 768)];
+            after = tail - sb - len;
+        }
     }
-    // bytes after this thread's group
-    const uint64_t end = g1 * T3V_SEG < n_bytes ? g1 * T3V_SEG : n_bytes;
-    red[tid] = (g0 < g1 && n_bytes > end) ? crc_mul(crc_xpow8(n_bytes - end), acc) : acc;
-    (void)covered;
+    red[tid] = after ? crc_shift_bytes(tabs, acc, after) : acc;
     __syncthreads();
     for (int s = 512; s > 0; s >>= 1) { if (tid < (uint32_t)s) red[tid] ^= red[tid + s]; __syncthreads(); }
     if (tid == 0 && crc_out) crc_out[f] = red[0];                         // plain crc32 of the payload
@@ -329,40 +353,61 @@ __global__ void __launch_bounds__(1024) k_t3v_finish(const uint32_t* __restrict_
 
 } // namespace
 
+// host: the table buffer described above (T3V_CRC_TABLE_WORDS uint32)
+void build_crc_tables(uint32_t* h)
+{
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int j = 0; j < 8; ++j) c = (c & 1u) ? (CRC_POLY ^ (c >> 1)) : (c >> 1);
+        h[i] = c;
+    }
+    for (int k = 1; k < 4; ++k) for (uint32_t i = 0; i < 256; ++i) h[256 * k + i] = h[h[256 * (k - 1) + i] & 0xFFu] ^ (h[256 * (k - 1) + i] >> 8);
+    for (int j = 0; j < CRC_NSHIFT; ++j) {
+        const uint32_t m = crc_xpow8((uint64_t)T3V_SEG << j);
+        for (int k = 0; k < 4; ++k) for (uint32_t u = 0; u < 256; ++u) h[CRC_SHIFT0 + 1024 * j + 256 * k + u] = crc_mul(m, u << (8 * k));
+    }
+    uint32_t sq = 1u << 23; // x^8
+    for (int i = 0; i < 32; ++i) { h[CRC_POW0 + i] = sq; sq = crc_mul(sq, sq); }
+}
+size_t crc_table_words() { return CRC_POW0 + 32; }
+
+// scratch (uint32): one CRC per tile and 256 segment CRCs per frame
 size_t t3v_partial_words(size_t n_words, size_t n_frames)
 {
     const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE;
-    return (size_t)((tiles ? tiles : 1) * T3V_TPB * n_frames);
+    return (size_t)(((tiles ? tiles : 1) + T3V_TPB) * n_frames);
 }
 // words9 (frame f at + f * 9 * stride_words, 4-byte aligned) -> records (record f at + f * record_pitch, 4-byte aligned)
-int launch_t3v_records(const uint8_t* words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* records, size_t record_pitch, uint32_t* partial,
-                       cudaStream_t st)
+int launch_t3v_records(const uint32_t* tabs, const uint8_t* words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* records, size_t record_pitch,
+                       uint32_t* partial, cudaStream_t st)
 {
     if (!n_frames) return 0;
-    const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE;
+    const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
+    uint32_t* seg = partial + tpf * n_frames;
     int n = 0;
-    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(words9, 9ull * stride_words, 0, records, record_pitch, 4, nb, (uint32_t)tiles, 1, partial); ++n; }
-    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(partial, (uint32_t)(tiles ? tiles : 1), nb, (uint32_t)n_words, records, record_pitch, 0, nullptr, nullptr);
+    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(words9, 9ull * stride_words, 0, records, record_pitch, 4, nb, (uint32_t)tiles, 1, tabs, partial, seg); ++n; }
+    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, seg, (uint32_t)tpf, nb, (uint32_t)n_words, records, record_pitch, 0, nullptr, nullptr);
     return n + 1;
 }
 // records -> words9 (may be null: check only) and ok[f] = the record announces n_words and its CRC matches (t3v_read_frame)
-int launch_t3v_read(const uint8_t* records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* words9, size_t stride_words, uint32_t* partial,
-                    uint8_t* ok, cudaStream_t st)
+int launch_t3v_read(const uint32_t* tabs, const uint8_t* records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* words9, size_t stride_words,
+                    uint32_t* partial, uint8_t* ok, cudaStream_t st)
 {
     if (!n_frames) return 0;
-    const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE;
+    const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
+    uint32_t* seg = partial + tpf * n_frames;
     int n = 0;
-    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(records, record_pitch, 4, words9, 9ull * stride_words, 0, nb, (uint32_t)tiles, 0, partial); ++n; }
-    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(partial, (uint32_t)(tiles ? tiles : 1), nb, (uint32_t)n_words, const_cast<uint8_t*>(records), record_pitch, 1, ok, nullptr);
+    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(records, record_pitch, 4, words9, 9ull * stride_words, 0, nb, (uint32_t)tiles, 0, tabs, partial, seg); ++n; }
+    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, seg, (uint32_t)tpf, nb, (uint32_t)n_words, const_cast<uint8_t*>(records), record_pitch, 1, ok, nullptr);
     return n + 1;
 }
 // plain CRC-32 of n bytes (4-byte aligned) with the same two kernels
-int launch_crc32(const uint8_t* data, size_t n, uint32_t* partial, uint32_t* out, cudaStream_t st)
+int launch_crc32(const uint32_t* tabs, const uint8_t* data, size_t n, uint32_t* partial, uint32_t* out, cudaStream_t st)
 {
-    const uint64_t tiles = ((uint64_t)n + T3V_TILE - 1) / T3V_TILE;
+    const uint64_t tiles = ((uint64_t)n + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
     int k = 0;
-    if (tiles) { k_t3v_tiles<<<(unsigned)tiles, T3V_TPB, 0, st>>>(data, 0, 0, nullptr, 0, 0, n, (uint32_t)tiles, 0, partial); ++k; }
-    k_t3v_finish<<<1, 1024, 0, st>>>(partial, (uint32_t)(tiles ? tiles : 1), n, 0, nullptr, 0, 0, nullptr, out);
+    if (tiles) { k_t3v_tiles<<<(unsigned)tiles, T3V_TPB, 0, st>>>(data, 0, 0, nullptr, 0, 0, n, (uint32_t)tiles, 0, tabs, partial, partial + tpf); ++k; }
+    k_t3v_finish<<<1, 1024, 0, st>>>(tabs, partial, partial + tpf, (uint32_t)tpf, n, 0, nullptr, 0, 0, nullptr, out);
     return k + 1;
 }
 

@@ -15,7 +15,7 @@ struct HeaderCache { uint8_t* d52 = nullptr; uint8_t* d27 = nullptr; t3c_config 
 struct SuperCache {
     struct Slot { uint16_t* d_map = nullptr; uint8_t* d_kv = nullptr; uint8_t key[48] = {}; uint32_t npass[3] = {}; bool valid = false; } slot[4];
 };
-struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; SuperCache* sup; };
+struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; SuperCache* sup; const uint32_t* crc; };
 // first codeword of every band that the general kernels still have to code (the tiled kernels did the ones before)
 struct CwStart { uint64_t c[9]; };
 // what a super-tile launch leaves to the general kernels: codewords from cs.c[b] on, band symbols from m_start, 6-pixel units from unit_start
@@ -109,10 +109,12 @@ int launch_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3c_pixel*
 
 // .t3v frame records and CRC-32 (k_formats.cu); partial = scratch of t3v_partial_words(...) uint32
 size_t t3v_partial_words(size_t n_words, size_t n_frames);
-int launch_t3v_records(const uint8_t* words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* records, size_t record_pitch, uint32_t* partial,
+void build_crc_tables(uint32_t* h);   // host: crc_table_words() entries (slice-by-4 tables, shift tables, x^(8 2^i))
+size_t crc_table_words();
+int launch_t3v_records(const uint32_t* tabs, const uint8_t* words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* records, size_t record_pitch, uint32_t* partial,
                        cudaStream_t st);
-int launch_t3v_read(const uint8_t* records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* words9, size_t stride_words, uint32_t* partial,
+int launch_t3v_read(const uint32_t* tabs, const uint8_t* records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* words9, size_t stride_words, uint32_t* partial,
                     uint8_t* ok, cudaStream_t st);
-int launch_crc32(const uint8_t* data, size_t n, uint32_t* partial, uint32_t* out, cudaStream_t st);
+int launch_crc32(const uint32_t* tabs, const uint8_t* data, size_t n, uint32_t* partial, uint32_t* out, cudaStream_t st);
 
 } // namespace t3c
