@@ -206,6 +206,25 @@ T3C_API t3c_status t3c_t3v_frame_records_dev(t3c_ctx*, const uint8_t* d_words9, 
 T3C_API t3c_status t3c_t3v_read_frames_dev(t3c_ctx*, const uint8_t* d_records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* d_words9,
                                            size_t stride_words, uint8_t* d_ok, void* stream);
 
+/* 8(f).4 image-bridge geometry of the NEW generation (include/io_image.hpp:102-140, 215-235) and the pipelines built from it (:238-338).
+ * RGB8 images are w*h*3 bytes, row-major.  resize: nearest neighbour with the reference's double-precision index; an empty source leaves
+ * the destination black.  blit: black canvas with src centred (needs src_w <= canvas_w; rows below the canvas are dropped).
+ * extract: the centred sub_w x sub_h window of a quantised frame (needs sub_w <= full_w; rows below the frame are zero). */
+T3C_API t3c_status t3c_resize_rgb_nn(t3c_ctx*, const uint8_t* src, int src_w, int src_h, uint8_t* dst, int dst_w, int dst_h);
+T3C_API t3c_status t3c_blit_center_rgb(t3c_ctx*, const uint8_t* src, int src_w, int src_h, uint8_t* canvas, int canvas_w, int canvas_h);
+T3C_API t3c_status t3c_extract_center_q(t3c_ctx*, const t3c_pixel* full, int full_w, int full_h, int sub_w, int sub_h, t3c_pixel* sub);
+T3C_API t3c_status t3c_resize_rgb_nn_dev(t3c_ctx*, const uint8_t* d_src, int src_w, int src_h, uint8_t* d_dst, int dst_w, int dst_h, void* stream);
+T3C_API t3c_status t3c_blit_center_rgb_dev(t3c_ctx*, const uint8_t* d_src, int src_w, int src_h, uint8_t* d_canvas, int canvas_w, int canvas_h, void* stream);
+T3C_API t3c_status t3c_extract_center_q_dev(t3c_ctx*, const t3c_pixel* d_full, int full_w, int full_h, int sub_w, int sub_h, t3c_pixel* d_sub, void* stream);
+/* image_to_words_subword after the file load, :238-301: resize to std_res_for(subword) (NEW: 27 -> 7680x4320, 24 -> 3840x2160, 21 -> 1920x1080,
+ * 18 -> 1280x720, 15 -> 960x540), centred in the 7680x4320 canvas when centered && subword != 27, quantise, one 32-bit word per pixel.
+ * *ok = the reference's bool (0 for an invalid subword or an empty image). */
+T3C_API t3c_status t3c_v6new_image_to_words(t3c_ctx*, const uint8_t* rgb, int w, int h, int subword, int centered, uint32_t* words, size_t cap_words,
+                                            size_t* n_words, int* ok);
+/* words_to_image_subword before the file write, :304-338: words -> pixels; as many as w*h: that image; a full 7680x4320 canvas (subword != 27):
+ * its centre window of std_res_for(subword), poured row-major into w x h; anything else: poured into w x h as far as it goes (the rest black) */
+T3C_API t3c_status t3c_v6new_words_to_image(t3c_ctx*, const uint32_t* words, size_t n_words, int subword, int w, int h, uint8_t* rgb, int* ok);
+
 #ifdef __cplusplus
 }
 #endif

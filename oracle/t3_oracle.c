@@ -898,3 +898,39 @@ void t3o_t3v_header(uint8_t out[54], int profile, int subword_code, int centered
     put32(out + 34, fps_num); put32(out + 38, fps_den); put32(out + 42, frame_count); put32(out + 46, 0);
     put32(out + 50, t3o_crc32(out, 50));
 }
+
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * image-bridge geometry of the NEW generation (include/io_image.hpp). */
+void t3o_resize_rgb_nn(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh) /* :102-124 */
+{
+    memset(dst, 0, (size_t)dw * dh * 3);
+    if (sw <= 0 || sh <= 0) return;
+    for (int y = 0; y < dh; ++y) {
+        int sy = (int)((y + 0.5) * (double)sh / dh);
+        sy = sy < 0 ? 0 : (sy > sh - 1 ? sh - 1 : sy);
+        for (int x = 0; x < dw; ++x) {
+            int sx = (int)((x + 0.5) * (double)sw / dw);
+            sx = sx < 0 ? 0 : (sx > sw - 1 ? sw - 1 : sx);
+            memcpy(dst + ((size_t)y * dw + x) * 3, src + ((size_t)sy * sw + sx) * 3, 3);
+        }
+    }
+}
+void t3o_blit_center_rgb(const uint8_t* src, int sw, int sh, uint8_t* dst, int cw, int ch) /* :125-140 */
+{
+    memset(dst, 0, (size_t)cw * ch * 3);
+    const int x0 = (cw - sw) / 2 > 0 ? (cw - sw) / 2 : 0, y0 = (ch - sh) / 2 > 0 ? (ch - sh) / 2 : 0;
+    for (int y = 0; y < sh; ++y) {
+        if (y + y0 < 0 || y + y0 >= ch) continue;
+        memcpy(dst + (size_t)(y + y0) * cw * 3 + (size_t)x0 * 3, src + (size_t)y * sw * 3, (size_t)sw * 3);
+    }
+}
+void t3o_extract_center_q(const t3o_pixel* full, int fw, int fh, int sw, int sh, t3o_pixel* sub) /* :215-235 */
+{
+    const int x0 = (fw - sw) / 2 > 0 ? (fw - sw) / 2 : 0, y0 = (fh - sh) / 2 > 0 ? (fh - sh) / 2 : 0;
+    for (int y = 0; y < sh; ++y) {
+        const int fy = y + y0;
+        if (fy < 0 || fy >= fh) { memset(sub + (size_t)y * sw, 0, (size_t)sw * sizeof(t3o_pixel)); continue; } /* resize() value-initialises */
+        memcpy(sub + (size_t)y * sw, full + (size_t)fy * fw + x0, (size_t)sw * sizeof(t3o_pixel));
+    }
+}

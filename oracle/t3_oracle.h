@@ -111,6 +111,10 @@ int    t3o_decode_rgb_fixed(const t3o_cfg* c, size_t n_px, const uint8_t* in9, s
 
 /* ---- sub-word streams + base-243 (OLD:816-859, include/ternary_packing.hpp:18-50) and the
  * NEW-generation RAW path (src/ternary_image_codec_v6_min.cpp:62-126: one pixel -> one 32-bit word, clamped) ---- */
+/* ---- image-bridge geometry of the NEW generation (include/io_image.hpp:102-140, 215-235) */
+void t3o_resize_rgb_nn(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh);
+void t3o_blit_center_rgb(const uint8_t* src, int sw, int sh, uint8_t* dst, int cw, int ch);             /* needs sw <= cw */
+void t3o_extract_center_q(const t3o_pixel* full, int fw, int fh, int sw, int sh, t3o_pixel* sub);       /* needs sw <= fw */
 /* ---- .t3v container records (old/include/t3v_io.hpp) */
 uint32_t t3o_crc32(const uint8_t* data, size_t n);                                            /* t3v_detail::crc32, :14-40 */
 size_t   t3o_t3v_frame_record(const uint8_t* words9, uint32_t n_words, uint8_t* out);       /* t3v_write_frame, :128-142: 8 + 9n bytes */

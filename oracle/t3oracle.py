@@ -198,6 +198,50 @@ class _Lib:
         ok = self.f("base243_unpack")(dp, C.c_size_t(d.size), _ptr(out), C.c_size_t(cap), C.byref(n))
         return bool(ok), out[:min(n.value, cap)].copy()
 
+    # --- image-bridge geometry (oracle only; the reference's live in ReferenceNew) ---
+    def resize_rgb_nn(self, src, dw, dh):
+        a = np.ascontiguousarray(src, np.uint8)
+        sh, sw = a.shape[0], a.shape[1]
+        out = np.zeros((dh, dw, 3), np.uint8)
+        self.lib.t3o_resize_rgb_nn(_ptr(a), C.c_int(sw), C.c_int(sh), _ptr(out), C.c_int(dw), C.c_int(dh))
+        return out
+
+    def blit_center_rgb(self, src, cw, ch):
+        a = np.ascontiguousarray(src, np.uint8)
+        out = np.zeros((ch, cw, 3), np.uint8)
+        self.lib.t3o_blit_center_rgb(_ptr(a), C.c_int(a.shape[1]), C.c_int(a.shape[0]), _ptr(out), C.c_int(cw), C.c_int(ch))
+        return out
+
+    def extract_center_q(self, full, fw, fh, sw, sh):
+        f = np.ascontiguousarray(full, PIXEL_DTYPE)
+        out = np.zeros(sw * sh, PIXEL_DTYPE)
+        self.lib.t3o_extract_center_q(f.ctypes.data_as(C.c_void_p), C.c_int(fw), C.c_int(fh), C.c_int(sw), C.c_int(sh), out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def v6new_image_to_words(self, rgb, sub, centered):
+        """image_to_words_subword after the load (include/io_image.hpp:238-301), composed from the restated pieces"""
+        if sub not in V6NEW_STD_RES or rgb.size == 0:
+            return False, np.zeros(0, np.uint32)
+        tw, th = V6NEW_STD_RES[sub]
+        work = rgb if (rgb.shape[1], rgb.shape[0]) == (tw, th) else self.resize_rgb_nn(rgb, tw, th)
+        if centered and sub != 27:
+            work = self.blit_center_rgb(work, 7680, 4320)
+        return True, self.v6new_pack_pixels(self.rgb_to_quant(work.reshape(-1, 3)))
+
+    def v6new_words_to_image(self, words, sub, w, h):
+        """words_to_image_subword before the write (:304-338)"""
+        if sub not in V6NEW_STD_RES:
+            return False, np.zeros((h, w, 3), np.uint8)
+        q = self.v6new_unpack_pixels(words)
+        tw, th = V6NEW_STD_RES[sub]
+        if q.size != w * h and q.size == 7680 * 4320 and sub != 27:
+            q = self.extract_center_q(q, 7680, 4320, tw, th)
+        out = np.zeros((h * w, 3), np.uint8)
+        n = min(q.size, w * h)
+        if n:
+            out[:n] = self.quant_to_rgb(q[:n])
+        return True, out.reshape(h, w, 3)
+
     # --- SURVEY 8(f).1: .t3v container records (same symbols in the oracle and the reference shim) ---
     def crc32(self, data):
         d, dp = _u8(data)
@@ -381,6 +425,9 @@ class Reference(_Lib):
         return out[:n].copy()
 
 
+V6NEW_STD_RES = {27: (7680, 4320), 24: (3840, 2160), 21: (1920, 1080), 18: (1280, 720), 15: (960, 540)}   # std_res_for, NEW:55-64
+
+
 class ReferenceNew:
     """The reference's NEW-generation core (one pixel -> one 32-bit word), oracle/_ref/libt3ref_new.so; SURVEY 8(f).3."""
 
@@ -402,6 +449,42 @@ class ReferenceNew:
         px = np.zeros(w.size, PIXEL_DTYPE)
         ok = self.lib.t3n_unpack_pixels(w.ctypes.data_as(C.c_void_p), C.c_size_t(w.size), px.ctypes.data_as(C.c_void_p), C.c_int(subword))
         return bool(ok), px
+
+    # --- the image bridge (include/io_image.hpp) through in-memory stb stubs
+    def resize_rgb_nn(self, src, dw, dh):
+        a = np.ascontiguousarray(src, np.uint8)
+        out = np.zeros((dh, dw, 3), np.uint8)
+        self.lib.t3n_resize_rgb_nn(a.ctypes.data_as(C.c_void_p), C.c_int(a.shape[1]), C.c_int(a.shape[0]), out.ctypes.data_as(C.c_void_p), C.c_int(dw), C.c_int(dh))
+        return out
+
+    def blit_center_rgb(self, src, cw, ch):
+        a = np.ascontiguousarray(src, np.uint8)
+        out = np.zeros((ch, cw, 3), np.uint8)
+        self.lib.t3n_blit_center_rgb(a.ctypes.data_as(C.c_void_p), C.c_int(a.shape[1]), C.c_int(a.shape[0]), out.ctypes.data_as(C.c_void_p), C.c_int(cw), C.c_int(ch))
+        return out
+
+    def extract_center_q(self, full, fw, fh, sw, sh):
+        f = np.ascontiguousarray(full, PIXEL_DTYPE)
+        out = np.zeros(sw * sh, PIXEL_DTYPE)
+        self.lib.t3n_extract_center_q.restype = C.c_size_t
+        n = self.lib.t3n_extract_center_q(f.ctypes.data_as(C.c_void_p), C.c_int(fw), C.c_int(fh), C.c_int(sw), C.c_int(sh), out.ctypes.data_as(C.c_void_p))
+        return out[:n]
+
+    def image_to_words_subword(self, rgb, sub, centered):
+        a = np.ascontiguousarray(rgb, np.uint8)
+        cap = 7680 * 4320
+        out = np.zeros(cap, np.uint32)
+        self.lib.t3n_image_to_words_subword.restype = C.c_longlong
+        n = self.lib.t3n_image_to_words_subword(a.ctypes.data_as(C.c_void_p), C.c_int(a.shape[1]), C.c_int(a.shape[0]), C.c_int(sub), C.c_int(int(centered)),
+                                                out.ctypes.data_as(C.c_void_p), C.c_size_t(cap))
+        return (n >= 0), out[:max(n, 0)].copy()
+
+    def words_to_image_subword(self, words, sub, w, h):
+        wd = np.ascontiguousarray(words, np.uint32)
+        out = np.zeros((h, w, 3), np.uint8)
+        ok = self.lib.t3n_words_to_image_subword(wd.ctypes.data_as(C.c_void_p), C.c_size_t(wd.size), C.c_int(sub), C.c_int(w), C.c_int(h), out.ctypes.data_as(C.c_void_p))
+        return bool(ok), out
+
 
 
 # --------------------------------------------------------------------------------------

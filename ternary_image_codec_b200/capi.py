@@ -70,7 +70,8 @@ _EXPORTS = [
     "t3c_subword_stream", "t3c_words_from_subword_stream", "t3c_base243_pack", "t3c_base243_unpack", "t3c_words_to_base243",
     "t3c_v6new_pack_pixels", "t3c_v6new_unpack_pixels", "t3c_subword_stream_dev", "t3c_words_from_subword_stream_dev",
     "t3c_base243_pack_dev", "t3c_base243_unpack_dev", "t3c_words_to_base243_dev", "t3c_v6new_pack_pixels_dev", "t3c_v6new_unpack_pixels_dev",
-    "t3c_crc32", "t3c_t3v_frame_record", "t3c_t3v_read_frame", "t3c_t3v_header", "t3c_t3v_frame_records_dev", "t3c_t3v_read_frames_dev",
+    "t3c_resize_rgb_nn", "t3c_blit_center_rgb", "t3c_extract_center_q", "t3c_resize_rgb_nn_dev", "t3c_blit_center_rgb_dev", "t3c_extract_center_q_dev",
+    "t3c_v6new_image_to_words", "t3c_v6new_words_to_image", "t3c_crc32", "t3c_t3v_frame_record", "t3c_t3v_read_frame", "t3c_t3v_header", "t3c_t3v_frame_records_dev", "t3c_t3v_read_frames_dev",
 ]
 
 _lib = None
@@ -144,6 +145,14 @@ def load_library() -> C.CDLL:
     L.t3c_v6new_pack_pixels_dev.argtypes = [vp, vp, sz, vp, vp]
     L.t3c_v6new_unpack_pixels_dev.argtypes = [vp, vp, sz, vp, vp]
     u32 = C.c_uint32
+    L.t3c_resize_rgb_nn.argtypes = [vp, u8p, i32, i32, u8p, i32, i32]
+    L.t3c_blit_center_rgb.argtypes = [vp, u8p, i32, i32, u8p, i32, i32]
+    L.t3c_extract_center_q.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    L.t3c_resize_rgb_nn_dev.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp]
+    L.t3c_blit_center_rgb_dev.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp]
+    L.t3c_extract_center_q_dev.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.t3c_v6new_image_to_words.argtypes = [vp, u8p, i32, i32, i32, i32, vp, sz, szp, C.POINTER(i32)]
+    L.t3c_v6new_words_to_image.argtypes = [vp, vp, sz, i32, i32, i32, u8p, C.POINTER(i32)]
     L.t3c_crc32.argtypes = [vp, u8p, sz, C.POINTER(u32)]
     L.t3c_t3v_frame_record.argtypes = [vp, u8p, sz, u8p, szp]
     L.t3c_t3v_read_frame.argtypes = [vp, u8p, sz, u8p, sz, szp, C.POINTER(i32)]
@@ -292,6 +301,40 @@ class Codec:
             return False, px
         self._ck(st)
         return True, px
+
+    # --- image-bridge geometry and the NEW-generation image <-> words pipelines (include/io_image.hpp)
+    def resize_rgb_nn(self, src, dw, dh):
+        a = np.ascontiguousarray(src, dtype=np.uint8)
+        out = np.zeros((dh, dw, 3), np.uint8)
+        self._ck(self.lib.t3c_resize_rgb_nn(self.h, _p(a), a.shape[1], a.shape[0], _p(out), dw, dh))
+        return out
+
+    def blit_center_rgb(self, src, cw, ch):
+        a = np.ascontiguousarray(src, dtype=np.uint8)
+        out = np.zeros((ch, cw, 3), np.uint8)
+        self._ck(self.lib.t3c_blit_center_rgb(self.h, _p(a), a.shape[1], a.shape[0], _p(out), cw, ch))
+        return out
+
+    def extract_center_q(self, full, fw, fh, sw, sh):
+        f = np.ascontiguousarray(full, dtype=PIXEL_DTYPE)
+        out = np.zeros(sw * sh, PIXEL_DTYPE)
+        self._ck(self.lib.t3c_extract_center_q(self.h, _p(f), fw, fh, sw, sh, _p(out)))
+        return out
+
+    def v6new_image_to_words(self, rgb, sub, centered):
+        a = np.ascontiguousarray(rgb, dtype=np.uint8)
+        cap = 7680 * 4320
+        out = np.zeros(cap, np.uint32)
+        n, ok = C.c_size_t(), C.c_int()
+        self._ck(self.lib.t3c_v6new_image_to_words(self.h, _p(a), a.shape[1], a.shape[0], sub, int(centered), _p(out), cap, C.byref(n), C.byref(ok)))
+        return bool(ok.value), out[:n.value].copy()
+
+    def v6new_words_to_image(self, words, sub, w, h):
+        wd = np.ascontiguousarray(words, dtype=np.uint32)
+        out = np.zeros((h, w, 3), np.uint8)
+        ok = C.c_int()
+        self._ck(self.lib.t3c_v6new_words_to_image(self.h, _p(wd), wd.size, sub, w, h, _p(out), C.byref(ok)))
+        return bool(ok.value), out
 
     # --- .t3v container records (old/include/t3v_io.hpp)
     def crc32(self, data):

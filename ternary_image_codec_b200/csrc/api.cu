@@ -1091,4 +1091,144 @@ t3c_status t3c_t3v_header(t3c_ctx* ctx, uint8_t out[54], int profile, int subwor
     put32(out + 50, crc);
     return T3C_OK;
 }
+
+// ---- image-bridge geometry ------------------------------------------------------
+t3c_status t3c_resize_rgb_nn_dev(t3c_ctx* ctx, const uint8_t* d_src, int sw, int sh, uint8_t* d_dst, int dw, int dh, void* st)
+{
+    if (!ctx || dw < 0 || dh < 0 || (dw && dh && !d_dst) || (sw > 0 && sh > 0 && !d_src)) return fail(ctx, T3C_ERR_ARG, "resize_rgb_nn: null or negative size");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_resize_rgb_nn(d_src, sw, sh, d_dst, dw, dh, (cudaStream_t)st));
+}
+t3c_status t3c_blit_center_rgb_dev(t3c_ctx* ctx, const uint8_t* d_src, int sw, int sh, uint8_t* d_dst, int cw, int ch, void* st)
+{
+    if (!ctx || cw < 0 || ch < 0 || sw < 0 || sh < 0 || (cw && ch && !d_dst) || (sw && sh && !d_src)) return fail(ctx, T3C_ERR_ARG, "blit_center_rgb: null or negative size");
+    if (sw > cw) return fail(ctx, T3C_ERR_ARG, "blit_center_rgb: source wider than the canvas (the reference writes past the row)");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_blit_center_rgb(d_src, sw, sh, d_dst, cw, ch, (cudaStream_t)st));
+}
+t3c_status t3c_extract_center_q_dev(t3c_ctx* ctx, const t3c_pixel* d_full, int fw, int fh, int sw, int sh, t3c_pixel* d_sub, void* st)
+{
+    if (!ctx || fw < 0 || fh < 0 || sw < 0 || sh < 0 || (sw && sh && (!d_sub || !d_full))) return fail(ctx, T3C_ERR_ARG, "extract_center_q: null or negative size");
+    if (sw > fw) return fail(ctx, T3C_ERR_ARG, "extract_center_q: window wider than the frame (the reference reads past the row)");
+    DeviceGuard guard(ctx->device);
+    return check_launch(ctx, launch_extract_center_q(d_full, fw, fh, sw, sh, d_sub, (cudaStream_t)st));
+}
+t3c_status t3c_resize_rgb_nn(t3c_ctx* ctx, const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh)
+{
+    if (!ctx || sw < 0 || sh < 0 || dw < 0 || dh < 0) return fail(ctx, T3C_ERR_ARG, "resize_rgb_nn: negative size");
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    const size_t ni = (size_t)sw * sh * 3, no = (size_t)dw * dh * 3;
+    if (!no) return T3C_OK;
+    TRY(reserve_t(ctx, B_IN, ni + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, no + 16, &d_out));
+    if (ni) H2D(d_in, src, ni);
+    TRY(t3c_resize_rgb_nn_dev(ctx, d_in, sw, sh, d_out, dw, dh, ctx->stream));
+    D2H(dst, d_out, no);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_blit_center_rgb(t3c_ctx* ctx, const uint8_t* src, int sw, int sh, uint8_t* dst, int cw, int ch)
+{
+    if (!ctx || sw < 0 || sh < 0 || cw < 0 || ch < 0) return fail(ctx, T3C_ERR_ARG, "blit_center_rgb: negative size");
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_in, *d_out;
+    const size_t ni = (size_t)sw * sh * 3, no = (size_t)cw * ch * 3;
+    if (!no) return T3C_OK;
+    TRY(reserve_t(ctx, B_IN, ni + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, no + 16, &d_out));
+    if (ni) H2D(d_in, src, ni);
+    TRY(t3c_blit_center_rgb_dev(ctx, d_in, sw, sh, d_out, cw, ch, ctx->stream));
+    D2H(dst, d_out, no);
+    SYNC();
+    return T3C_OK;
+}
+t3c_status t3c_extract_center_q(t3c_ctx* ctx, const t3c_pixel* full, int fw, int fh, int sw, int sh, t3c_pixel* sub)
+{
+    if (!ctx || fw < 0 || fh < 0 || sw < 0 || sh < 0) return fail(ctx, T3C_ERR_ARG, "extract_center_q: negative size");
+    DeviceGuard guard(ctx->device);
+    t3c_pixel *d_in, *d_out;
+    const size_t ni = (size_t)fw * fh * 6, no = (size_t)sw * sh * 6;
+    if (!no) return T3C_OK;
+    TRY(reserve_t(ctx, B_IN, ni + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, no + 16, &d_out));
+    if (ni) H2D(d_in, full, ni);
+    TRY(t3c_extract_center_q_dev(ctx, d_in, fw, fh, sw, sh, d_out, ctx->stream));
+    D2H(sub, d_out, no);
+    SYNC();
+    return T3C_OK;
+}
+static bool v6new_std_res(int sub, int& w, int& h) // std_res_for, NEW:55-64
+{
+    switch (sub) {
+    case 27: w = 7680; h = 4320; return true;
+    case 24: w = 3840; h = 2160; return true;
+    case 21: w = 1920; h = 1080; return true;
+    case 18: w = 1280; h = 720; return true;
+    case 15: w = 960; h = 540; return true;
+    }
+    w = h = 0;
+    return false;
+}
+t3c_status t3c_v6new_image_to_words(t3c_ctx* ctx, const uint8_t* rgb, int w, int h, int subword, int centered, uint32_t* words, size_t cap_words,
+                                    size_t* n_words, int* ok)
+{
+    if (!ctx || !n_words || !ok) return fail(ctx, T3C_ERR_ARG, "v6new_image_to_words: null");
+    *n_words = 0; *ok = 0;
+    int tw, th;
+    if (!v6new_std_res(subword, tw, th) || w <= 0 || h <= 0 || !rgb) return T3C_OK;     // load fails / encode_*_subword rejects the mode
+    const bool embed = centered && subword != 27;
+    const int ow = embed ? 7680 : tw, oh = embed ? 4320 : th;
+    const size_t n_px = (size_t)ow * oh;
+    if (cap_words < n_px || !words) return fail(ctx, T3C_ERR_CAPACITY, "v6new_image_to_words: capacity");
+    DeviceGuard guard(ctx->device);
+    uint8_t *d_src, *d_work, *d_canvas;
+    t3c_pixel* d_q;
+    uint32_t* d_words;
+    TRY(reserve_t(ctx, B_IN, (size_t)w * h * 3 + 16, &d_src));
+    TRY(reserve_t(ctx, B_TMP, (size_t)tw * th * 3 + 16, &d_work));
+    TRY(reserve_t(ctx, B_TMP2, embed ? n_px * 3 + 16 : 16, &d_canvas));
+    TRY(reserve_t(ctx, B_AUX, n_px * 6 + 16, &d_q));
+    TRY(reserve_t(ctx, B_OUT, n_px * 4 + 16, &d_words));
+    H2D(d_src, rgb, (size_t)w * h * 3);
+    const uint8_t* img = d_src;
+    if (w != tw || h != th) { TRY(t3c_resize_rgb_nn_dev(ctx, d_src, w, h, d_work, tw, th, ctx->stream)); img = d_work; }
+    if (embed) { TRY(t3c_blit_center_rgb_dev(ctx, img, tw, th, d_canvas, ow, oh, ctx->stream)); img = d_canvas; }
+    TRY(check_launch(ctx, launch_rgb_to_quant(img, n_px, d_q, ctx->stream)));
+    TRY(check_launch(ctx, launch_v6new_pack_pixels(d_q, n_px, d_words, ctx->stream)));
+    D2H(words, d_words, 4 * n_px);
+    SYNC();
+    *n_words = n_px; *ok = 1;
+    return T3C_OK;
+}
+t3c_status t3c_v6new_words_to_image(t3c_ctx* ctx, const uint32_t* words, size_t n_words, int subword, int w, int h, uint8_t* rgb, int* ok)
+{
+    if (!ctx || !ok || w < 0 || h < 0) return fail(ctx, T3C_ERR_ARG, "v6new_words_to_image: null");
+    *ok = 0;
+    int tw, th;
+    if (!v6new_std_res(subword, tw, th)) return T3C_OK;                                   // decode_*_subword rejects the mode
+    const size_t need = (size_t)w * h, full = (size_t)7680 * 4320;
+    *ok = 1;
+    if (!need) return T3C_OK;
+    if (!rgb || (n_words && !words)) return fail(ctx, T3C_ERR_ARG, "v6new_words_to_image: null");
+    DeviceGuard guard(ctx->device);
+    uint32_t* d_words;
+    t3c_pixel *d_q, *d_sub;
+    uint8_t* d_rgb;
+    TRY(reserve_t(ctx, B_IN, 4 * n_words + 16, &d_words));
+    TRY(reserve_t(ctx, B_AUX, 6 * n_words + 16, &d_q));
+    TRY(reserve_t(ctx, B_AUX2, 6 * (size_t)tw * th + 16, &d_sub));
+    TRY(reserve_t(ctx, B_OUT, 3 * need + 16, &d_rgb));
+    if (n_words) H2D(d_words, words, 4 * n_words);
+    TRY(check_launch(ctx, launch_v6new_unpack_pixels(d_words, n_words, d_q, ctx->stream)));
+    const t3c_pixel* q = d_q;
+    size_t nq = n_words;
+    if (n_words != need && n_words == full && subword != 27) { // the core returned an S27 canvas: its centre window
+        TRY(t3c_extract_center_q_dev(ctx, d_q, 7680, 4320, tw, th, d_sub, ctx->stream));
+        q = d_sub; nq = (size_t)tw * th;
+    }
+    const size_t fill = nq < need ? nq : need;                  // quant_stream_to_rgb stops when the pixels run out (:195)
+    CU(cudaMemsetAsync(d_rgb, 0, 3 * need, ctx->stream));
+    TRY(check_launch(ctx, launch_quant_to_rgb(q, fill, d_rgb, ctx->stream)));
+    D2H(rgb, d_rgb, 3 * need);
+    SYNC();
+    return T3C_OK;
+}
 } // extern "C"

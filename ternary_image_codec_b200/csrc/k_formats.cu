@@ -412,3 +412,76 @@ int launch_crc32(const uint32_t* tabs, const uint8_t* data, size_t n, uint32_t* 
 }
 
 } // namespace t3c
+
+// =============================================================================================
+// image-bridge geometry of the NEW generation (include/io_image.hpp:102-140, 215-235): nearest-neighbour resize,
+// centre blit into the S27 canvas, centre-window extraction.  Pure copies: one thread per destination pixel.
+// =============================================================================================
+namespace t3c {
+namespace {
+// resize_rgb_nn, :102-124: sx = clamp((int)((x + 0.5) * (double)src_w / dst_w), 0, src_w - 1) -- the same two IEEE double operations
+__global__ void k_resize_rgb_nn(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int dw, int dh)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw) return;
+    int sy = (int)__ddiv_rn(__dmul_rn((double)y + 0.5, (double)sh), (double)dh);
+    int sx = (int)__ddiv_rn(__dmul_rn((double)x + 0.5, (double)sw), (double)dw);
+    sy = min(max(sy, 0), sh - 1);
+    sx = min(max(sx, 0), sw - 1);
+    const uint8_t* sp = src + ((size_t)sy * sw + sx) * 3;
+    uint8_t* dp = dst + ((size_t)y * dw + x) * 3;
+    dp[0] = sp[0]; dp[1] = sp[1]; dp[2] = sp[2];
+}
+// blit_center_rgb, :125-140 (src no wider than the canvas): black canvas, src rows at (x0, y0) = ((cw - sw) / 2, (ch - sh) / 2) clamped at 0,
+// rows that fall below the canvas dropped.  One thread per 4 canvas bytes.
+__global__ void k_blit_center_rgb(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int cw, int ch)
+{
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4, total = (size_t)cw * ch * 3;
+    if (i4 >= total) return;
+    const int x0 = max(0, (cw - sw) / 2), y0 = max(0, (ch - sh) / 2);
+    const size_t row_bytes = (size_t)cw * 3;
+    uint32_t v = 0;
+    for (int k = 0; k < 4 && i4 + k < total; ++k) {
+        const size_t i = i4 + k, y = i / row_bytes, xb = i - y * row_bytes;
+        const long long ys = (long long)y - y0, xs = (long long)xb - 3ll * x0;
+        uint32_t b = 0;
+        if (ys >= 0 && ys < sh && xs >= 0 && xs < 3ll * sw) b = src[(size_t)ys * sw * 3 + (size_t)xs];
+        v |= b << (8 * k);
+    }
+    if (i4 + 4 <= total && !(reinterpret_cast<uintptr_t>(dst) & 3)) *reinterpret_cast<uint32_t*>(dst + i4) = v;
+    else for (int k = 0; k < 4 && i4 + k < total; ++k) dst[i4 + k] = (uint8_t)(v >> (8 * k));
+}
+// extract_center_q, :215-235 (window no wider than the frame): sub_w x sub_h pixels from (x0, y0), rows below the frame zero
+__global__ void k_extract_center_q(const uint16_t* __restrict__ full, int fw, int fh, int sw, int sh, uint16_t* __restrict__ sub)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= sw) return;
+    const int x0 = max(0, (fw - sw) / 2), y0 = max(0, (fh - sh) / 2), fy = y + y0;
+    uint16_t* d = sub + ((size_t)y * sw + x) * 3;
+    if (fy >= fh) { d[0] = d[1] = d[2] = 0; return; }
+    const uint16_t* sp = full + ((size_t)fy * fw + x0 + x) * 3;
+    d[0] = sp[0]; d[1] = sp[1]; d[2] = sp[2];
+}
+} // namespace
+
+int launch_resize_rgb_nn(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh, cudaStream_t st)
+{
+    if (dw <= 0 || dh <= 0) return 0;
+    if (sw <= 0 || sh <= 0) { cudaMemsetAsync(dst, 0, (size_t)dw * dh * 3, st); return 0; } // the reference leaves the black image
+    k_resize_rgb_nn<<<dim3(blocks_for((size_t)dw, 256), (unsigned)dh), 256, 0, st>>>(src, sw, sh, dst, dw, dh);
+    return 1;
+}
+int launch_blit_center_rgb(const uint8_t* src, int sw, int sh, uint8_t* dst, int cw, int ch, cudaStream_t st)
+{
+    if (cw <= 0 || ch <= 0) return 0;
+    k_blit_center_rgb<<<blocks_for(((size_t)cw * ch * 3 + 3) / 4, 256), 256, 0, st>>>(src, sw, sh, dst, cw, ch);
+    return 1;
+}
+int launch_extract_center_q(const t3c_pixel* full, int fw, int fh, int sw, int sh, t3c_pixel* sub, cudaStream_t st)
+{
+    if (sw <= 0 || sh <= 0) return 0;
+    k_extract_center_q<<<dim3(blocks_for((size_t)sw, 256), (unsigned)sh), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(full), fw, fh, sw, sh, reinterpret_cast<uint16_t*>(sub));
+    return 1;
+}
+
+} // namespace t3c

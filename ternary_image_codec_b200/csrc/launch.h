@@ -107,6 +107,10 @@ int launch_words_to_base243(const uint8_t* words9, size_t n_words, int N, uint8_
 int launch_v6new_pack_pixels(const t3c_pixel* px, size_t n_px, uint32_t* words, cudaStream_t st);
 int launch_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3c_pixel* px, cudaStream_t st);
 
+// image-bridge geometry (k_formats.cu)
+int launch_resize_rgb_nn(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh, cudaStream_t st);
+int launch_blit_center_rgb(const uint8_t* src, int sw, int sh, uint8_t* dst, int cw, int ch, cudaStream_t st);
+int launch_extract_center_q(const t3c_pixel* full, int fw, int fh, int sw, int sh, t3c_pixel* sub, cudaStream_t st);
 // .t3v frame records and CRC-32 (k_formats.cu); partial = scratch of t3v_partial_words(...) uint32
 size_t t3v_partial_words(size_t n_words, size_t n_frames);
 void build_crc_tables(uint32_t* h);   // host: crc_table_words() entries (slice-by-4 tables, shift tables, x^(8 2^i))

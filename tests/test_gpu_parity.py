@@ -748,3 +748,35 @@ def test_t3v_records_batched_device(codec, oracle):
         assert np.array_equal(rec[f, :8 + 9 * n_words].cpu().numpy(), oracle.t3v_frame_record(w))
         if f != 1:
             assert torch.equal(back[f, :9 * n_words], words[f, :9 * n_words])
+
+
+# ------------------------------------------------------------------ image-bridge geometry and NEW-generation pipelines
+def test_image_bridge_geometry(codec, oracle, t3):
+    r = rng(980)
+    for (sh, sw), (dh, dw) in (((37, 53), (540, 960)), ((1, 1), (7, 5)), ((300, 200), (31, 17)), ((64, 64), (64, 64)), ((5, 9), (1, 1)), ((1080, 1920), (2160, 3840))):
+        img = r.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(codec.resize_rgb_nn(img, dw, dh), oracle.resize_rgb_nn(img, dw, dh)), ((sh, sw), (dh, dw))
+    for (sh, sw), (ch, cw) in (((37, 53), (77, 101)), ((540, 960), (541, 961)), ((10, 8), (4, 8)), ((3, 3), (3, 3)), ((9, 2), (1, 7)), ((540, 960), (4320, 7680))):
+        img = r.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(codec.blit_center_rgb(img, cw, ch), oracle.blit_center_rgb(img, cw, ch)), ((sh, sw), (ch, cw))
+    with pytest.raises(t3.T3CError):
+        codec.blit_center_rgb(np.zeros((2, 9, 3), np.uint8), 8, 8)        # wider than the canvas: the reference would write past the row
+    for (fh, fw), (sh, sw) in (((40, 60), (20, 30)), ((40, 60), (40, 60)), ((10, 60), (14, 30)), ((7, 9), (1, 1)), ((4320, 7680), (540, 960))):
+        q = T.synth_quant(3, fw * fh)
+        assert np.array_equal(codec.extract_center_q(q, fw, fh, sw, sh).view(np.uint8), oracle.extract_center_q(q, fw, fh, sw, sh).view(np.uint8))
+
+
+def test_v6new_image_pipelines(codec, oracle):
+    r = rng(981)
+    img = r.integers(0, 256, (41, 67, 3), dtype=np.uint8)
+    for sub, cen in ((15, True), (15, False), (21, False), (27, True), (7, True)):
+        ok_g, w_g = codec.v6new_image_to_words(img, sub, cen)
+        ok_o, w_o = oracle.v6new_image_to_words(img, sub, cen)
+        assert ok_g == ok_o and np.array_equal(w_g, w_o), (sub, cen)
+        if ok_g:
+            tw, th = T.V6NEW_STD_RES[sub]
+            for (w, h) in ((tw, th), (100, 50), (tw + 3, th)):
+                ok1, i1 = codec.v6new_words_to_image(w_g, sub, w, h)
+                ok2, i2 = oracle.v6new_words_to_image(w_o, sub, w, h)
+                assert ok1 and ok2 and np.array_equal(i1, i2), (sub, cen, w, h)
+    assert codec.v6new_words_to_image(np.zeros(4, np.uint32), 7, 2, 2)[0] is False

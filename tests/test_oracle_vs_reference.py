@@ -460,3 +460,37 @@ def test_t3v_header_matches_reference(oracle, ref):
         ref.lib.t3r_t3v_header.restype = C.c_size_t
         n = ref.lib.t3r_t3v_header(rr.ctypes.data_as(C.c_void_p), prof, sub_mode, cen, coset, 7680, 4320, aw, 30000, 1001, fc, ft, C.byref(back))
         assert n == 54 and back.value == 1 and np.array_equal(o, rr[:54])
+
+
+# ------------------------------------------------------------------ image-bridge geometry (NEW generation)
+def test_image_bridge_geometry_matches_reference(oracle, ref_new):
+    r = rng(970)
+    for (sh, sw), (dh, dw) in (((37, 53), (540, 960)), ((1, 1), (7, 5)), ((300, 200), (31, 17)), ((64, 64), (64, 64)), ((5, 9), (1, 1))):
+        img = r.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(oracle.resize_rgb_nn(img, dw, dh), ref_new.resize_rgb_nn(img, dw, dh))
+    for (sh, sw), (ch, cw) in (((37, 53), (77, 101)), ((540, 960), (541, 961)), ((10, 8), (4, 8)), ((3, 3), (3, 3)), ((9, 2), (1, 7))):
+        img = r.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        assert np.array_equal(oracle.blit_center_rgb(img, cw, ch), ref_new.blit_center_rgb(img, cw, ch))      # src taller than the canvas: rows dropped
+    for (fh, fw), (sh, sw) in (((40, 60), (20, 30)), ((40, 60), (40, 60)), ((10, 60), (14, 30)), ((7, 9), (1, 1))):
+        q = T.synth_quant(3, fw * fh)
+        a, b = oracle.extract_center_q(q, fw, fh, sw, sh), ref_new.extract_center_q(q, fw, fh, sw, sh)
+        assert a.size == b.size == sw * sh and np.array_equal(a.view(np.uint8), b.view(np.uint8))           # window taller than the frame: zero rows
+
+
+def test_image_to_words_pipelines_match_reference(oracle, ref_new):
+    r = rng(971)
+    img = r.integers(0, 256, (41, 67, 3), dtype=np.uint8)
+    for sub, cen in ((15, True), (15, False), (18, True), (27, True), (7, True)):
+        ok_r, w_r = ref_new.image_to_words_subword(img, sub, cen)
+        ok_o, w_o = oracle.v6new_image_to_words(img, sub, cen)
+        assert ok_r == ok_o and np.array_equal(w_r, w_o), (sub, cen)
+        if ok_r:
+            tw, th = T.V6NEW_STD_RES[sub]
+            for (w, h) in ((tw, th), (100, 50)):
+                ok1, i1 = ref_new.words_to_image_subword(w_r, sub, w, h)
+                ok2, i2 = oracle.v6new_words_to_image(w_o, sub, w, h)
+                assert ok1 and ok2 and np.array_equal(i1, i2), (sub, cen, w, h)
+    exact = r.integers(0, 256, (540, 960, 3), dtype=np.uint8)                                               # already the target size: no resize
+    ok_r, w_r = ref_new.image_to_words_subword(exact, 15, False)
+    ok_o, w_o = oracle.v6new_image_to_words(exact, 15, False)
+    assert ok_r and ok_o and w_r.size == 960 * 540 and np.array_equal(w_r, w_o)
