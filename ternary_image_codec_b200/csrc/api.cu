@@ -204,6 +204,9 @@ t3c_status t3c_create(int device, t3c_ctx** out)
         if (cudaMalloc((void**)&sl.d_map, 3 * 64 * 32 * sizeof(uint16_t) + 256) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
         sl.d_kv = reinterpret_cast<uint8_t*>(sl.d_map + 3 * 64 * 32);
     }
+    // the table uploads above come from pageable memory on the legacy stream: make sure they have landed before any kernel on the
+    // context's non-blocking streams can read them
+    if (cudaDeviceSynchronize() != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
     *out = ctx;
     return T3C_OK;
 }

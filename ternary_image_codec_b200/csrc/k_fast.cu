@@ -1635,9 +1635,13 @@ static bool super_prepare(const DevTables& T, const t3c_config& cfg, const Geom&
         static thread_local uint8_t h_kv[3 * SUP_MAX_PASS];
         C.valid = false;
         if (!build_super_maps(P, g, h_map, h_kv, C.npass)) return false;
-        cudaStreamSynchronize(st); // once per config change: kernels in flight may still read the old maps
-        cudaMemcpy(C.d_map, h_map, sizeof h_map, cudaMemcpyHostToDevice);
-        cudaMemcpy(C.d_kv, h_kv, sizeof h_kv, cudaMemcpyHostToDevice);
+        // once per config change: kernels in flight on any stream may still read the old maps, and the copies (pageable memory, legacy
+        // stream) must have landed before a kernel on a non-blocking stream reads the new ones
+        (void)st;
+        if (cudaDeviceSynchronize() != cudaSuccess) return false;
+        if (cudaMemcpy(C.d_map, h_map, sizeof h_map, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        if (cudaMemcpy(C.d_kv, h_kv, sizeof h_kv, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        if (cudaDeviceSynchronize() != cudaSuccess) return false;
         std::memcpy(C.key, key, sizeof key);
         C.valid = true;
     }
