@@ -524,6 +524,12 @@ __device__ __forceinline__ uint32_t rgb_to_value3(float R, float G, float B)
     const uint32_t fy = mad_hi(by, QY_M, Q_CONST);
     return fy + 243u * __umulhi(bb, QC_M) + 19683u * __umulhi(br, QC_M);
 }
+__device__ __forceinline__ uint32_t floor_sat_u8(float x)
+{
+    uint32_t r;
+    asm("cvt.rmi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
 // pixel value -> RGB8 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84), arithmetic only
 __device__ __forceinline__ uint32_t value_to_rgb3(uint32_t A)
 {
@@ -538,10 +544,11 @@ __device__ __forceinline__ uint32_t value_to_rgb3(uint32_t A)
     const float r = __fadd_rn(y, __fmul_rn(1.402f, cr));
     const float g = __fsub_rn(__fsub_rn(y, __fmul_rn(0.344136f, cb)), __fmul_rn(0.714136f, cr));
     const float b = __fadd_rn(y, __fmul_rn(1.772f, cb));
-    const uint32_t Rb = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(fminf(fmaxf(r, 0.0f), 255.0f), 0.5f), 8388608.0f));
-    const uint32_t Gb = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(fminf(fmaxf(g, 0.0f), 255.0f), 0.5f), 8388608.0f));
-    const uint32_t Bb = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(fminf(fmaxf(b, 0.0f), 255.0f), 0.5f), 8388608.0f));
-    return __byte_perm(__byte_perm(Rb, Gb, 0x0040), Bb, 0x7410) & 0x00FFFFFFu; // R | G<<8 | B<<16
+    // clamp(round-half-away(x), 0, 255) = sat_u8(floor(x + 0.5)) with the add rounded down (a round-to-nearest add could reach the next
+    // integer from just below a half): one FADD.RM and one saturating conversion per component instead of two FMNMX and two FADDs, and
+    // the bytes are packed by multiply-adds: the clamps and PRMTs left the half-rate ALU pipe, which bounds this kernel
+    const uint32_t Rb = floor_sat_u8(__fadd_rd(r, 0.5f)), Gb = floor_sat_u8(__fadd_rd(g, 0.5f)), Bb = floor_sat_u8(__fadd_rd(b, 0.5f));
+    return Rb + 256u * Gb + 65536u * Bb;                                       // R | G<<8 | B<<16
 }
 // 8-entry byte table through PRMT: nibble n of sel (3 plane bits b0 b1 b2) -> b0 + 3 b1 + 9 b2
 __device__ __forceinline__ uint32_t planes4_to_sym(uint32_t sel) { return __byte_perm(0x04030100u, 0x0D0C0A09u, sel); }
