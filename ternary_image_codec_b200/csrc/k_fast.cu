@@ -804,7 +804,9 @@ __device__ __forceinline__ void enc_phase_b(const uint8_t* S, uint8_t* U, const 
 // ---- one codeword of decode phase B: 26 received symbols (x4) at src (even address) -> syndrome screen / slow path ->
 // K descrambled data symbols scattered at byte stride 9 from dst.  pa = shared address of the variant block {A[26][32] | B[26][32]}
 // (256-byte aligned), tab_v = the same block as a pointer, chk = the clean-codeword constant of the variant
-template <int K>
+// PRESCALED = false: src holds the symbols as they lie in the frame; they are scaled here, four at a time, by multiply-shifts on the
+// full-rate pipe (bytes >= 32 -- out-of-alphabet symbols, OLD:28-31 -- are reduced mod 27 first; 27..31 alias 0..4 inside the tables)
+template <int K, bool PRESCALED = true>
 __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, uint32_t chk_nz, uint32_t chk_two,
                                        const GfTables& sg, uint32_t* status, bool count = true)
 {
@@ -819,6 +821,19 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
 #pragma unroll
     for (int j = 0; j < 6; ++j) xw[j] = __funnelshift_r(xw[j], xw[j + 1], sh);
     xw[6] >>= sh;
+    if constexpr (!PRESCALED) {
+        xw[6] &= 0xFFFFu;                                          // symbols 24, 25 only
+        if ((xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6]) & 0xE0E0E0E0u) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                uint32_t r = 0;
+                for (int q = 0; q < 4; ++q) r |= (((xw[j] >> (8 * q)) & 0xFFu) % 27u) << (8 * q);
+                xw[j] = r;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) xw[j] *= 4u;                   // < 128 per byte: no carry between symbols
+    }
     Planes acc{0, 0}, acc2{0, 0};
     uint32_t ev[K];
     static_for<0, 26>([&](auto ic) {
@@ -836,7 +851,7 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
         // slow path: full decode of this codeword (descrambled), then rewrite its data symbols.  The screen's sum minus the
         // clean-codeword constant is the parity residual, from which the syndromes follow without another pass over the block
         uint8_t cwd[26], orig[26], res[8];
-        for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tab_v + src[i] + 128 * i);
+        for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tab_v + (PRESCALED ? (uint32_t)src[i] : 4u * (src[i] % 27u)) + 128 * i);
         {
             Planes d{acc.nz, acc.two};
             gf3_add(d, chk_nz, chk_nz ^ chk_two);                  // minus the constant: -x keeps nz and flips two where nz is set
@@ -855,7 +870,7 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
     }
 }
 // ---- decode phase B: nine staged runs (x4) -> syndrome screen / slow path -> descrambled stream symbols
-template <int K>
+template <int K, bool PRESCALED = true>
 __device__ __forceinline__ void dec_phase_b(const uint8_t* U, uint8_t* S, const WarpMeta3& meta, const uint8_t* pmap, uint32_t tabA32,
                                             const uint8_t* tabA, const uint32_t* chk, const GfTables& sg, uint32_t* status, int lane)
 {
@@ -871,7 +886,7 @@ __device__ __forceinline__ void dec_phase_b(const uint8_t* U, uint8_t* S, const 
         asm volatile("" : "+r"(pa));
         const uint8_t* src = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
         uint8_t* dst = S + cw + (9 * K - 9) * cl;                       // 9K*cl + b
-        dec_cw<K>(src, dst, pa, tabA + v * L::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
+        dec_cw<K, PRESCALED>(src, dst, pa, tabA + v * L::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
     }
 }
 // ---- decode phase A: 26 stream symbols at src (even address) -> six pixels -> 18 RGB bytes at dst (even address)
@@ -1424,47 +1439,23 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::DEC_WARPS, 1) k_decode_rg
         mbar_wait(bar, phase);
         phase ^= 1;
         __syncwarp();
-        // ---- the nine runs are in R: scale every byte by 4 (table byte offset) in place.  Bytes >= 32 would leave the
-        // 32-entry rows: they are reduced mod 27 first (out-of-alphabet symbols read as their low three trits, OLD:28-31)
-        bool wild = false;
-#pragma unroll 1
-        for (int it = 0; it < (9 * RUN_SLOTS + 31) / 32; ++it) {
-            const uint32_t sl = 32u * it + lane, b = (sl * 2850u) >> 16, c = sl - RUN_SLOTS * b;   // sl / 23 for sl < 256
-            if (b < 9) {
-                const uint64_t lo = meta.run_lo[b];
-                const uint32_t padb = (uint32_t)lo & 15u;
-                if (16 * c < padb + L::RUN) {
-                    uint4 q = *reinterpret_cast<const uint4*>(R + 16 * sl);
-                    const uint64_t ga = (lo - padb) + 16 * c;
-                    if (ga + 16 > in_limit) { // the clipped end of the buffer: fetch what exists byte by byte
-                        uint32_t t[4] = {0, 0, 0, 0};
-                        for (int i = 0; i < 16; ++i) if (ga + i < in_limit) t[i >> 2] |= (uint32_t)P.in[ga + i] << (8 * (i & 3));
-                        q = make_uint4(t[0], t[1], t[2], t[3]);
-                    }
-                    if (((q.x | q.y | q.z | q.w) & 0xE0E0E0E0u) != 0) {
-                        wild = true;
-                        uint32_t t[4] = {q.x, q.y, q.z, q.w};
-                        for (int i = 0; i < 4; ++i) {
-                            uint32_t r = 0;
-                            for (int j = 0; j < 4; ++j) r |= (((t[i] >> (8 * j)) & 0xFFu) % 27u) << (8 * j);
-                            t[i] = r;
-                        }
-                        q = make_uint4(t[0], t[1], t[2], t[3]);
-                    }
-                    q.x <<= 2; q.y <<= 2; q.z <<= 2; q.w <<= 2;
-                    *reinterpret_cast<uint4*>(R + 16 * sl) = q;
-                }
-            }
+        // ---- the nine runs are in R as they lie in the frame (phase B scales the symbols itself).  Only the clipped end of the buffer
+        // (the last chunks of the last frame, which the bulk copy left out) is fetched here, byte by byte
+        if (lane < 9) {
+            const uint64_t lo = meta.run_lo[lane];
+            const uint32_t padb = (uint32_t)lo & 15u;
+            const uint64_t a0 = lo - padb, a1 = a0 + ((padb + L::RUN + 15u) & ~15u);
+            if (a1 > in_limit)
+                for (uint64_t ga = (in_limit > a0 ? (in_limit - a0) & ~15ull : 0) + a0; ga < a1; ++ga) R[L::RUN_PITCH * lane + (ga - a0)] = ga < in_limit ? P.in[ga] : 0;
         }
-        (void)wild;
         __syncwarp();
         if (tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0,1: move them from the transient states to the periodic ones
             uint8_t* r0 = R + ((uint32_t)meta.run_lo[0] & 15u);
-            r0[0] = (uint8_t)(4u * sg.scr[st_of(g, 0, 0)][sg.dsc[g.st[0]][(r0[0] >> 2) % 27u]]);
-            r0[1] = (uint8_t)(4u * sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][(r0[1] >> 2) % 27u]]);
+            r0[0] = sg.scr[st_of(g, 0, 0)][sg.dsc[g.st[0]][r0[0] % 27u]];
+            r0[1] = sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][r0[1] % 27u]];
         }
         __syncwarp();
-        dec_phase_b<K>(R, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, P.status + 2 * f, lane);
+        dec_phase_b<K, false>(R, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, P.status + 2 * f, lane);
         __syncwarp();
         if (mt + 1 < mt_hi && lane < 9) fetch(mt + 1);                       // R is free again: next tile's runs on their way
         const uint64_t g_lo = P.out_stride * f + (uint64_t)PIX * tile;
