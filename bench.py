@@ -173,7 +173,7 @@ def run_reference(args):
         secs += dt
     v = px / secs / 1e6
     sample = f"{threads} threads x {n_slice} px (1/64 of an 8K frame each) per step, reference encode chain + decode_block over every codeword + unpack + dequant"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
@@ -407,13 +407,29 @@ def run_ours(args):
                          "frac_of_nominal_8tbs": ach / 8000.0},
             "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     codec.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: str):
+    """the ONE line of the contract, on the process's original stdout"""
+    f = _JSON_OUT or sys.stdout
+    f.write(line + "\n")
+    f.flush()
+
+
 def main():
+    # Libraries write to stdout too (NCCL prints its version banner there when the box sets NCCL_DEBUG): keep the real stdout for the
+    # JSON line and send everything else to stderr
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
