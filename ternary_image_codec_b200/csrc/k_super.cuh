@@ -347,27 +347,32 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
     const uint64_t in_limit = Q.in_stride * (Q.n_frames - 1) + 9 * g.n_out;
     const uint32_t total = P.n_tiles * Q.n_frames;
     const uint32_t ch_mask = (1u << P.ch_shift) - 1u, S32 = smem_u32(S);
-    if (blockIdx.x < total && tid < 9) super_run_meta<true>(meta, P, g, Q.in_stride * (blockIdx.x / P.n_tiles), blockIdx.x % P.n_tiles, tid);
-    __syncthreads();
-    for (uint32_t st = blockIdx.x; st < total; st += gridDim.x) {
-        const uint32_t f = st / P.n_tiles, T = st - f * P.n_tiles, tm = T % 3u;
-        SUP_TICK0();
-        // ---- the nine runs as they lie in the frame -> S region (slot raw_base[b], byte i <-> global a0 + i)
+    // the nine runs of the super-tile described by `meta`, as they lie in the frame -> S region (slot raw_base[b], byte i <-> global a0 + i):
+    // 16-byte asynchronous copies (LDGSTS), issued as soon as S is free so that they land while the previous super-tile is stored
+    auto load_runs = [&]() {
         for (uint32_t idx = tid; idx < (9u << P.ch_shift); idx += SUP_TPB) {
             const uint32_t b = idx >> P.ch_shift, c = idx & ch_mask;
             if (c >= meta.nch[b]) continue;
             const uint64_t ga = (meta.g_lo[b] & ~15ull) + 16ull * c;
-            uint4 q;
-            if (ga + 16 <= in_limit) q = __ldg(reinterpret_cast<const uint4*>(Q.in + ga));
-            else {
-                uint32_t t[4] = {0, 0, 0, 0};
-                for (int i = 0; i < 16; ++i) if (ga + i < in_limit) t[i >> 2] |= (uint32_t)Q.in[ga + i] << (8 * (i & 3));
-                q = make_uint4(t[0], t[1], t[2], t[3]);
-            }
-            *reinterpret_cast<uint4*>(S + P.raw_base[b] + 16u * c) = q;
+            uint8_t* dstp = S + P.raw_base[b] + 16u * c;
+            if (ga + 16 <= in_limit) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dstp)), "l"(Q.in + ga) : "memory");
+            else for (int i = 0; i < 16; ++i) dstp[i] = ga + i < in_limit ? Q.in[ga + i] : 0;   // the end of the buffer
         }
-        __syncthreads();
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (blockIdx.x < total && tid < 9) super_run_meta<true>(meta, P, g, Q.in_stride * (blockIdx.x / P.n_tiles), blockIdx.x % P.n_tiles, tid);
+    __syncthreads();
+    if (blockIdx.x < total) load_runs();
+    for (uint32_t st = blockIdx.x; st < total; st += gridDim.x) {
+        const uint32_t f = st / P.n_tiles, T = st - f * P.n_tiles, tm = T % 3u, n_pass = P.npass[tm];
+        SUP_TICK0();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                           // this super-tile's runs are in S; the previous one's pixels have left R
         SUP_TICK(4);
+        const uint16_t* map = P.map + tm * (SUP_MAX_PASS * 32);
+        const uint8_t* pkv = P.pass_kv + tm * SUP_MAX_PASS;
+        uint32_t e_nx = 0, kv_nx = 0;              // the map entry of a warp's next phase-B pass is always fetched one pass (here: one phase) ahead
+        if ((uint32_t)warp < n_pass) { e_nx = __ldg(map + 32 * warp + lane); kv_nx = __ldg(pkv + warp); }
         // ---- squeeze the beacon slots out and scale by 4 (table byte offset): R_b[q] = 4 * frame byte (q + beacon slots before
         // body symbol q).  Bytes >= 27 are reduced mod 27 first (out-of-alphabet symbols read as their low three trits, OLD:28-31)
         for (uint32_t idx = tid; idx < (9u << P.ch_shift); idx += SUP_TPB) {
@@ -418,14 +423,10 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             __syncthreads();
         }
         // ---- phase B: syndrome screen per codeword (BM / Chien / Forney in-thread for the dirty ones), descrambled data -> stream order
-        const uint16_t* map = P.map + tm * (SUP_MAX_PASS * 32);
-        const uint8_t* pkv = P.pass_kv + tm * SUP_MAX_PASS;
-        uint32_t e_nx = 0, kv_nx = 0; // the map entry of a warp's next pass is fetched while it decodes the current one
-        if ((uint32_t)warp < P.npass[tm]) { e_nx = __ldg(map + 32 * warp + lane); kv_nx = __ldg(pkv + warp); }
 #pragma unroll 1
-        for (uint32_t pass = warp; pass < P.npass[tm]; pass += SUP_WARPS) {
+        for (uint32_t pass = warp; pass < n_pass; pass += SUP_WARPS) {
             const uint32_t e = e_nx, kv = kv_nx;
-            if (pass + SUP_WARPS < P.npass[tm]) { e_nx = __ldg(map + 32 * (pass + SUP_WARPS) + lane); kv_nx = __ldg(pkv + pass + SUP_WARPS); }
+            if (pass + SUP_WARPS < n_pass) { e_nx = __ldg(map + 32 * (pass + SUP_WARPS) + lane); kv_nx = __ldg(pkv + pass + SUP_WARPS); }
             if (e == SUP_IDLE) continue;
             const uint32_t ks = kv & 3u, v = kv >> 2, b = e & 15u, cl = e >> 4, K = P.kk[ks];
             const uint8_t* src = R + P.run_base[b] + 26u * cl;
@@ -454,6 +455,7 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
         }
         __syncthreads();
         SUP_TICK(7);
+        if (st + gridDim.x < total) load_runs();   // S is free since phase A: the next super-tile's runs (geometry computed after the squeeze)
         {   // pixel-side bytes -> global: whole 16-byte chunks, the (at most 15 + 15) edge bytes one by one
             const uint32_t n_out = PIXB * P.UN, end = pad + n_out, c_lo = pad ? 1u : 0u, c_hi = end >> 4;
             uint8_t* gout = Q.out + (g_lo - pad);
@@ -461,9 +463,9 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             if (tid < 16 && pad && (uint32_t)tid >= pad && (uint32_t)tid < end) gout[tid] = R[tid];
             if (tid >= 32 && tid < 48) { const uint32_t pos = 16u * c_hi + (uint32_t)(tid - 32); if (pos < end && (c_hi >= c_lo) && !(c_hi == 0 && pad)) gout[pos] = R[pos]; }
         }
-        __syncthreads();
-        SUP_TICK(8);
+        SUP_TICK(8);                               // (the barrier at the top of the loop separates this store from the next squeeze)
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // =============================================================================================
