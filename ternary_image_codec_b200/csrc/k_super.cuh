@@ -226,12 +226,13 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
         // ---- phase B: one codeword per lane; a pass holds codewords of one k and one scrambler variant
         const uint16_t* map = P.map + tm * (SUP_MAX_PASS * 32);
         const uint8_t* pkv = P.pass_kv + tm * SUP_MAX_PASS;
+        const uint32_t n_pass = P.npass[tm];
         uint32_t e_nx = 0, kv_nx = 0; // the map entry of a warp's next pass is fetched while it codes the current one
-        if ((uint32_t)warp < P.npass[tm]) { e_nx = __ldg(map + 32 * warp + lane); kv_nx = __ldg(pkv + warp); }
+        if ((uint32_t)warp < n_pass) { e_nx = __ldg(map + 32 * warp + lane); kv_nx = __ldg(pkv + warp); }
 #pragma unroll 1
-        for (uint32_t pass = warp; pass < P.npass[tm]; pass += SUP_WARPS) {
+        for (uint32_t pass = warp; pass < n_pass; pass += SUP_WARPS) {
             const uint32_t e = e_nx, kv = kv_nx;
-            if (pass + SUP_WARPS < P.npass[tm]) { e_nx = __ldg(map + 32 * (pass + SUP_WARPS) + lane); kv_nx = __ldg(pkv + pass + SUP_WARPS); }
+            if (pass + SUP_WARPS < n_pass) { e_nx = __ldg(map + 32 * (pass + SUP_WARPS) + lane); kv_nx = __ldg(pkv + pass + SUP_WARPS); }
             if (e == SUP_IDLE) continue;
             const uint32_t ks = kv & 3u, v = kv >> 2, b = e & 15u, cl = e >> 4, K = P.kk[ks];
             const uint8_t* src = S + 9u * K * cl + b;
