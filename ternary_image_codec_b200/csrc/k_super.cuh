@@ -59,26 +59,32 @@ __device__ __forceinline__ uint4 lds_gather16(uint32_t a)
                  : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3), "=r"(x4) : "r"(aw) : "memory");
     return make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh), __funnelshift_r(x3, x4, sh));
 }
-// word j of the 16-byte mask whose bytes [0, e) are 0xFF (e in 0..16, branch-free)
-__device__ __forceinline__ uint32_t below16(uint32_t e, int j)
+// the 16-byte mask whose bytes [0, e) are 0xFF (e in 0..16), as four words: two clamped 64-bit shifts
+__device__ __forceinline__ void below16(uint32_t e, uint32_t (&m)[4])
 {
-    const int k = min(max((int)e - 4 * j, 0), 4);
-    return __funnelshift_lc(0xFFFFFFFFu, 0u, 8u * (uint32_t)k);
+    const uint32_t s0 = min(8u * e, 64u), s1 = 8u * e > 64u ? 8u * e - 64u : 0u;
+    const uint64_t lo = s0 == 64u ? ~0ull : ((1ull << s0) - 1ull), hi = s1 == 64u ? ~0ull : ((1ull << s1) - 1ull);
+    m[0] = (uint32_t)lo; m[1] = (uint32_t)(lo >> 32); m[2] = (uint32_t)hi; m[3] = (uint32_t)(hi >> 32);
 }
 // bytes [0, e) of a, bytes [e, 16) of b
 __device__ __forceinline__ uint4 merge16(uint4 a, uint4 b, uint32_t e)
 {
-    const uint32_t m0 = below16(e, 0), m1 = below16(e, 1), m2 = below16(e, 2), m3 = below16(e, 3);
-    return make_uint4((a.x & m0) | (b.x & ~m0), (a.y & m1) | (b.y & ~m1), (a.z & m2) | (b.z & ~m2), (a.w & m3) | (b.w & ~m3));
+    uint32_t m[4];
+    below16(e, m);
+    return make_uint4((a.x & m[0]) | (b.x & ~m[0]), (a.y & m[1]) | (b.y & ~m[1]), (a.z & m[2]) | (b.z & ~m[2]), (a.w & m[3]) | (b.w & ~m[3]));
 }
-// bytes [0, e) of a, byte e = v (v4 = v in every byte), bytes (e, 16) of b
+// bytes [0, e) of a, byte e = v (v4 = v in every byte), bytes (e, 16) of b; e in 0..15
 __device__ __forceinline__ uint4 merge16_put(uint4 a, uint4 b, uint32_t e, uint32_t v4)
 {
-    uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w}, r[4];
+    uint32_t m[4];
+    below16(e, m);
+    const uint32_t bm = 0xFFu << (8u * (e & 3u)), w = e >> 2;              // the slot's byte inside word w
+    const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
+    uint32_t r[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const uint32_t m = below16(e, j), m1 = below16(e + 1u, j);
-        r[j] = (x[j] & m) | (v4 & (m1 ^ m)) | (y[j] & ~m1);
+        const uint32_t bj = w == (uint32_t)j ? bm : 0u;
+        r[j] = (x[j] & m[j]) | (v4 & bj) | (y[j] & ~(m[j] | bj));
     }
     return make_uint4(r[0], r[1], r[2], r[3]);
 }
