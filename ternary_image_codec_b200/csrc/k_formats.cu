@@ -88,6 +88,87 @@ __global__ void __launch_bounds__(TPB) k_words_to_base243(const uint8_t* __restr
     out[4 + j] = (uint8_t)v;
 }
 
+// ---- tiled versions of the two kernels that feed the .t3p / .t3b writers: a CTA takes 320 consecutive words (2880 bytes in, 320 N trits out;
+// 320 N is a multiple of 5, so base-243 bytes never straddle CTAs): coalesced 32-bit loads into shared memory, thread = word: nine symbols ->
+// 27 trits through a 27-entry table (three trit bytes per symbol), the first N laid down in shared memory, then coalesced stores.
+constexpr int SW_WORDS = 320, SW_TPB = 320;
+__device__ __forceinline__ void subword_tile_trits(const uint8_t* __restrict__ words, uint64_t n_words, uint32_t N, uint64_t w0, uint8_t* s_in, uint8_t* s_tr,
+                                                   const uint32_t* s_lut)
+{
+    const uint32_t tid = threadIdx.x;
+    const uint64_t left = n_words - w0;
+    const uint32_t nw = (uint32_t)(left < SW_WORDS ? left : SW_WORDS), nb = 9u * nw;
+    const uint8_t* src = words + 9ull * w0;
+    if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+        for (uint32_t i = tid; i < nb / 4; i += SW_TPB) reinterpret_cast<uint32_t*>(s_in)[i] = __ldg(reinterpret_cast<const uint32_t*>(src) + i);
+        for (uint32_t i = (nb & ~3u) + tid; i < nb; i += SW_TPB) s_in[i] = src[i];
+    } else
+        for (uint32_t i = tid; i < nb; i += SW_TPB) s_in[i] = src[i];
+    __syncthreads();
+    if (tid < nw) {
+        uint8_t* o = s_tr + N * tid;
+        uint32_t e[9];
+#pragma unroll
+        for (int sy = 0; sy < 9; ++sy) e[sy] = s_lut[s_in[9 * tid + sy] % 27u]; // trit bytes of the symbol reduced mod 27 (unpack3, OLD:28-31)
+        // 27 trit bytes as seven words
+        const uint32_t w[7] = {e[0] | e[1] << 24, e[1] >> 8 | e[2] << 16, e[2] >> 16 | e[3] << 8, e[4] | e[5] << 24, e[5] >> 8 | e[6] << 16, e[6] >> 16 | e[7] << 8, e[8]};
+        if ((N & 3u) == 0) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) if (4u * j < N) reinterpret_cast<uint32_t*>(o)[j] = w[j];
+        } else {
+#pragma unroll
+            for (int t = 0; t < 27; ++t) if ((uint32_t)t < N) o[t] = (uint8_t)(w[t >> 2] >> (8 * (t & 3)));
+        }
+    } else if (tid < SW_WORDS) {
+        for (uint32_t t = 0; t < N; ++t) s_tr[N * tid + t] = 0;       // past the end of the stream: zero trits (the base-243 padding)
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(SW_TPB) k_subword_stream_tiled(const uint8_t* __restrict__ words, uint64_t n_words, uint32_t N, uint8_t* __restrict__ out)
+{
+    __shared__ __align__(16) uint8_t s_in[9 * SW_WORDS];
+    __shared__ __align__(16) uint8_t s_tr[27 * SW_WORDS];
+    __shared__ uint32_t s_lut[27];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 27) s_lut[tid] = (tid % 3u) | ((tid / 3u) % 3u) << 8 | (tid / 9u) << 16;
+    const uint64_t w0 = (uint64_t)blockIdx.x * SW_WORDS;
+    subword_tile_trits(words, n_words, N, w0, s_in, s_tr, s_lut);
+    const uint64_t left = n_words - w0;
+    const uint32_t nw = (uint32_t)(left < SW_WORDS ? left : SW_WORDS), nb = N * nw;
+    uint8_t* dst = out + (uint64_t)N * w0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        for (uint32_t i = tid; i < nb / 4; i += SW_TPB) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(s_tr)[i];
+        for (uint32_t i = (nb & ~3u) + tid; i < nb; i += SW_TPB) dst[i] = s_tr[i];
+    } else
+        for (uint32_t i = tid; i < nb; i += SW_TPB) dst[i] = s_tr[i];
+}
+__global__ void __launch_bounds__(SW_TPB) k_words_to_base243_tiled(const uint8_t* __restrict__ words, uint64_t n_words, uint32_t N, uint8_t* __restrict__ out)
+{
+    __shared__ __align__(16) uint8_t s_in[9 * SW_WORDS];
+    __shared__ __align__(16) uint8_t s_tr[27 * SW_WORDS];
+    __shared__ __align__(16) uint8_t s_out[27 * SW_WORDS / 5 + 4];
+    __shared__ uint32_t s_lut[27];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 27) s_lut[tid] = (tid % 3u) | ((tid / 3u) % 3u) << 8 | (tid / 9u) << 16;
+    const uint64_t w0 = (uint64_t)blockIdx.x * SW_WORDS, n_trits = n_words * N;
+    if (blockIdx.x == 0 && tid < 4) out[tid] = (uint8_t)((uint32_t)n_trits >> (8 * tid));
+    subword_tile_trits(words, n_words, N, w0, s_in, s_tr, s_lut);
+    const uint64_t byte0 = (uint64_t)N * w0 / 5, nbytes_all = (n_trits + 4) / 5;      // N * w0 is a multiple of 5
+    const uint64_t left = nbytes_all - byte0;
+    const uint32_t nb = (uint32_t)(left < (uint64_t)N * SW_WORDS / 5 ? left : (uint64_t)N * SW_WORDS / 5);
+    for (uint32_t j = tid; j < nb; j += SW_TPB) {
+        const uint8_t* t = s_tr + 5 * j;
+        s_out[j] = (uint8_t)(t[0] + 3u * t[1] + 9u * t[2] + 27u * t[3] + 81u * t[4]);
+    }
+    __syncthreads();
+    uint8_t* dst = out + 4 + byte0;
+    if ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+        for (uint32_t i = tid; i < nb / 4; i += SW_TPB) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(s_out)[i];
+        for (uint32_t i = (nb & ~3u) + tid; i < nb; i += SW_TPB) dst[i] = s_out[i];
+    } else
+        for (uint32_t i = tid; i < nb; i += SW_TPB) dst[i] = s_out[i];
+}
+
 // NEW-generation RAW path.  pack13_from_quant (:62-78): clamp(Yq,0,242) + 243 (clamp(Cbq+40,0,80) + 81 clamp(Crq+40,0,80)).
 // Thread = 4 pixels: 24 bytes in (three 64-bit loads), one 128-bit store.
 __device__ __forceinline__ uint32_t v6new_code(uint32_t yq, int cb, int cr)
@@ -149,7 +230,7 @@ int launch_subword_stream(const uint8_t* words9, size_t n_words, int N, uint8_t*
 {
     const uint64_t n_out = (uint64_t)n_words * (uint64_t)N;
     if (!n_out) return 0;
-    k_subword_stream<<<blocks_for((n_out + 15) / 16, TPB), TPB, 0, st>>>(words9, n_out, (uint32_t)N, trits);
+    k_subword_stream_tiled<<<blocks_for(n_words, SW_WORDS), SW_TPB, 0, st>>>(words9, n_words, (uint32_t)N, trits);
     return 1;
 }
 int launch_words_from_subword_stream(const uint8_t* trits, size_t n_trits, int N, uint8_t fill, uint8_t* words9, cudaStream_t st)
@@ -173,7 +254,8 @@ int launch_base243_unpack(const uint8_t* payload, size_t n_trits, uint8_t* trits
 int launch_words_to_base243(const uint8_t* words9, size_t n_words, int N, uint8_t* out, cudaStream_t st)
 {
     const uint64_t n_trits = (uint64_t)n_words * (uint64_t)N;
-    k_words_to_base243<<<blocks_for((n_trits + 4) / 5 + 1, TPB), TPB, 0, st>>>(words9, n_trits, (uint32_t)N, out);
+    if (!n_words) { k_words_to_base243<<<1, TPB, 0, st>>>(words9, n_trits, (uint32_t)N, out); return 1; } // just the count
+    k_words_to_base243_tiled<<<blocks_for(n_words, SW_WORDS), SW_TPB, 0, st>>>(words9, n_words, (uint32_t)N, out);
     return 1;
 }
 int launch_v6new_pack_pixels(const t3c_pixel* px, size_t n_px, uint32_t* words, cudaStream_t st)

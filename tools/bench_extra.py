@@ -125,6 +125,30 @@ def uep2d(all_t=False):
                       "profile_words": wpf}))
 
 
+def formats8k():
+    """sub-word trit streams, base-243 packing and the NEW-generation 1-pixel words on 8K-sized inputs"""
+    n_words = N_PX // 2
+    g = torch.Generator(device=dev); g.manual_seed(8)
+    words = torch.randint(0, 27, (n_words * 9,), dtype=torch.uint8, device=dev, generator=g)
+    N = 24
+    trits = torch.empty(n_words * N, dtype=torch.uint8, device=dev)
+    packed = torch.empty(4 + (n_words * N + 4) // 5 + 16, dtype=torch.uint8, device=dev)
+    t_sub = timeit(lambda: codec.subword_stream_dev(words, n_words, N, trits, S))
+    t_fused = timeit(lambda: codec.words_to_base243_dev(words, n_words, N, packed, S))
+    px = torch.randint(0, 243, (N_PX, 3), dtype=torch.int16, device=dev, generator=g)
+    px[:, 1:] = px[:, 1:] % 81 - 40
+    w32 = torch.empty(N_PX, dtype=torch.int32, device=dev)
+    back = torch.empty_like(px)
+    t_pack = timeit(lambda: codec.lib.t3c_v6new_pack_pixels_dev(codec.h, px.data_ptr(), N_PX, w32.data_ptr(), S))
+    t_unpack = timeit(lambda: codec.lib.t3c_v6new_unpack_pixels_dev(codec.h, w32.data_ptr(), N_PX, back.data_ptr(), S))
+    assert torch.equal(px, back)
+    res = {"workload": "formats8k: 16.6 M Word27 -> first 24 trits per word (1 B/trit) | fused -> base-243 bytes; 33.2 M pixels <-> NEW-generation 32-bit words",
+           "subword_stream_us": t_sub * 1e3, "subword_stream_gbs": (9 + N) * n_words / t_sub / 1e6,
+           "words_to_base243_us": t_fused * 1e3, "words_to_base243_gbs": (9 + N / 5) * n_words / t_fused / 1e6,
+           "v6new_pack_us": t_pack * 1e3, "v6new_pack_gbs": 10 * N_PX / t_pack / 1e6, "v6new_unpack_us": t_unpack * 1e3, "v6new_unpack_gbs": 10 * N_PX / t_unpack / 1e6}
+    print(json.dumps(res))
+
+
 def t3v8k():
     """.t3v frame records of an 8K frame's profile words (RS(26,20): 20.8 M words): emit (n | payload % 27 | CRC) and check"""
     cfg = t3.make_config(profile=t3.P3_RS26_20, uep=2)
@@ -181,6 +205,6 @@ if __name__ == "__main__":
     def words():
         words8k(2, "words8k_k20: encode_profile_from_raw + consistent decode on 16.6 M raw words, RS(26,20) 1D")
         words8k(1, "words8k_default: the reference's default EncoderContext (P2, uniform k=22), raw words in/out")
-    which = sys.argv[1:] or ["words8k", "raw8k", "uep2d", "t3v8k", "stream240"]
+    which = sys.argv[1:] or ["words8k", "raw8k", "uep2d", "t3v8k", "formats8k", "stream240"]
     for w in which:
-        {"words8k": words, "raw8k": raw8k, "uep2d": uep2d, "t3v8k": t3v8k, "stream240": stream240}[w]()
+        {"words8k": words, "raw8k": raw8k, "uep2d": uep2d, "t3v8k": t3v8k, "formats8k": formats8k, "stream240": stream240}[w]()
