@@ -313,7 +313,10 @@ t3c_status t3c_encode_profile_dev(t3c_ctx* ctx, const t3c_config* cfg, int arith
     else if (super_path_ok(*cfg)) { // per-band k / 2D / beacon: the super-tile kernels code the full super-tiles, the general kernel the rest
         SuperTail tail;
         n = launch_encode_super(ctx->tabs, *cfg, g, d_raw, 9 * n_words, true, 2 * n_words, 1, d_out, g.n_out, s, &tail);
-        n += launch_encode_general_from(ctx->tabs, *cfg, g, d_raw, d_out, s, tail.cs);
+        if (n > 0) {
+            n += launch_encode_general_from(ctx->tabs, *cfg, g, d_raw, d_out, s, tail.cs, false);
+            n += launch_frame_misc_sparse(ctx->tabs, *cfg, g, d_out, 1, 0, s, tail.n_tiles, tail.ncw_tile);
+        } else n = launch_encode_general_from(ctx->tabs, *cfg, g, d_raw, d_out, s, tail.cs);
         return check_launch(ctx, n);
     }
     n += launch_encode_general(ctx->tabs, *cfg, g, d_raw, d_out, s, 13ull * n_full); // the ragged rest (or everything), header, padding
@@ -390,9 +393,11 @@ t3c_status t3c_encode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, int a
                 n += launch_pack_pixels(q, n_tail, raw, s);
                 // the general encoder indexes raw words from the start of the frame: hand it the base the tail words would have there
                 const uint8_t* raw0 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(raw) - 9 * (px0 / 2));
-                n += launch_encode_general_from(ctx->tabs, *cfg, g, raw0, d_out + 9 * stride_words * f, s, tail.cs);
+                n += launch_encode_general_from(ctx->tabs, *cfg, g, raw0, d_out + 9 * stride_words * f, s, tail.cs, false);
                 TRY(check_launch(ctx, n));
             }
+            // header, zero padding and the beacon slots outside the super-tile runs, all frames at once
+            TRY(check_launch(ctx, launch_frame_misc_sparse(ctx->tabs, *cfg, g, d_out, n_frames, 9 * stride_words, s, tail.n_tiles, tail.ncw_tile)));
             return T3C_OK;
         }
     }

@@ -1615,6 +1615,8 @@ static void super_tail_all(SuperTail* tail)
     for (int b = 0; b < 9; ++b) tail->cs.c[b] = 0;
     tail->m_start = 0;
     tail->unit_start = 0;
+    tail->n_tiles = 0;
+    for (int b = 0; b < 9; ++b) tail->ncw_tile[b] = 0;
 }
 // plan + pass maps (cached on the device per kernel flavour); false = the super-tile kernels do not apply
 static bool super_prepare(const DevTables& T, const t3c_config& cfg, const Geom& g, bool decode, bool words, uint64_t px_limit, cudaStream_t st, SuperPlan& P,
@@ -1646,7 +1648,8 @@ static bool super_prepare(const DevTables& T, const t3c_config& cfg, const Geom&
     for (int i = 0; i < 3; ++i) P.npass[i] = C.npass[i];
     P.map = C.d_map;
     P.pass_kv = C.d_kv;
-    for (int b = 0; b < 9; ++b) tail->cs.c[b] = (uint64_t)P.ncw[P.kslot[b]] * P.n_tiles;
+    for (int b = 0; b < 9; ++b) { tail->cs.c[b] = (uint64_t)P.ncw[P.kslot[b]] * P.n_tiles; tail->ncw_tile[b] = P.ncw[P.kslot[b]]; }
+    tail->n_tiles = P.n_tiles;
     tail->m_start = (uint64_t)P.M * P.n_tiles;
     tail->unit_start = (uint64_t)P.UN * P.n_tiles;
     return true;

@@ -564,6 +564,40 @@ __global__ void k_frame_misc(uint8_t* __restrict__ out_base, size_t stride_bytes
     }
 }
 
+// The same for frames whose full super-tiles were coded by the super-tile kernels (k_super.cuh): those write the beacon slots that lie
+// inside their runs, so only three kinds of slots are left: the one right before a run's first symbol (run boundaries), the ones inside the
+// ragged end of every band (coded by k_encode_general, which writes body symbols only) and the ones after the last body symbol.
+struct SparseMisc { uint32_t n_tiles; uint32_t ncw[9]; };
+__global__ void k_frame_misc_sparse(uint8_t* __restrict__ out_base, size_t stride_bytes, Geom g, const uint8_t* __restrict__ hdr52, SparseMisc sm)
+{
+    uint8_t* __restrict__ out = out_base + stride_bytes * blockIdx.y;
+    if (blockIdx.x == 0 && threadIdx.x < 52) out[threadIdx.x] = hdr52[threadIdx.x];
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t G = 9ull * g.period;
+    auto is_slot = [&](uint64_t o) { return (o / 9) % g.period == 0 && (int)(o % 9) == g.slot; };
+    // run boundaries: band b, super-tile T = 0 .. n_tiles (T = n_tiles: where the ragged end starts)
+    for (uint64_t i = tid; i < 9ull * (sm.n_tiles + 1); i += nth) {
+        const uint32_t b = (uint32_t)(i / (sm.n_tiles + 1)), T = (uint32_t)(i - (uint64_t)b * (sm.n_tiles + 1));
+        const uint64_t p = 26 * (g.cw_base[b] + (uint64_t)sm.ncw[b] * T);
+        if (p >= g.l_body) continue;
+        const uint64_t o = beacon_expand<uint64_t>(g, p);
+        if (o >= 1 && is_slot(o - 1)) out[52 + o - 1] = g.bsym;
+    }
+    // the ragged end of every band: slots inside [o(first symbol), o(last symbol)]
+    if (tid < 9) {
+        const uint32_t b = (uint32_t)tid;
+        const uint64_t c0 = (uint64_t)sm.ncw[b] * sm.n_tiles;
+        if (g.ncw[b] > c0) {
+            const uint64_t o_a = beacon_expand<uint64_t>(g, 26 * (g.cw_base[b] + c0)), o_b = beacon_expand<uint64_t>(g, 26 * (g.cw_base[b] + g.ncw[b]) - 1);
+            uint64_t s = o_a <= (uint64_t)g.slot ? (uint64_t)g.slot : ((o_a - g.slot + G - 1) / G) * G + g.slot; // first slot at or after o_a
+            for (; s <= o_b; s += G) out[52 + s] = g.bsym;
+        }
+    }
+    // after the last body symbol: slots of the remaining words, zeros elsewhere up to the end of the last word
+    const uint64_t q_end = g.l_body ? beacon_expand<uint64_t>(g, g.l_body - 1) + 1 : 0;
+    for (uint64_t q = q_end + tid; 52 + q < 9 * g.n_out; q += nth) out[52 + q] = (q < g.l_exp && is_slot(q)) ? g.bsym : 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // General consistent decoder (A.8): thread per codeword -> symbol stream sy' in scratch
 // ------------------------------------------------------------------------------------------
@@ -774,7 +808,7 @@ int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom&
     for (int b = 0; b < 9; ++b) cs.c[b] = cw_start;
     return launch_encode_general_from(T, cfg, g, raw, out, st, cs);
 }
-int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw, uint8_t* out, cudaStream_t st, const CwStart& cs)
+int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw, uint8_t* out, cudaStream_t st, const CwStart& cs, bool finish)
 {
     int n = 0;
     const uint64_t mx = cw_left(g, cs);
@@ -784,6 +818,7 @@ int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const 
         else k_encode_general<uint64_t><<<dim3(blocks_for(mx, cwb), 9), TPB, 0, st>>>(raw, out, g, T.gf, T.rs, cs, cwb);
         ++n;
     }
+    if (!finish) return n;
     // without a beacon the rest of the frame is the (cached) coded header and the zero padding
     return n + (use_beacon(cfg) ? launch_frame_misc(T, cfg, g, out, 1, 0, st) : launch_frame_finish(T, cfg, g, out, 1, 0, st));
 }
@@ -821,6 +856,23 @@ int launch_frame_misc(const DevTables& T, const t3c_config& cfg, const Geom& g, 
     int n = 0;
     const uint8_t* hdr = cached_header(T, cfg, g.arith, st, n);
     k_frame_misc<<<dim3(blocks, (unsigned)n_frames), 256, 0, st>>>(out, stride_bytes, g, hdr);
+    return n + 1;
+}
+// header, padding and the beacon slots the super-tile kernels and the general tail encoder leave (see k_frame_misc_sparse)
+int launch_frame_misc_sparse(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out, size_t n_frames, size_t stride_bytes, cudaStream_t st,
+                             uint32_t n_tiles, const uint32_t ncw_tile[9])
+{
+    if (!n_frames) return 0;
+    if (!(g.period && g.slot >= 0)) return use_beacon(cfg) ? launch_frame_misc(T, cfg, g, out, n_frames, stride_bytes, st) : launch_frame_finish(T, cfg, g, out, n_frames, stride_bytes, st);
+    int n = 0;
+    const uint8_t* hdr = cached_header(T, cfg, g.arith, st, n);
+    SparseMisc sm;
+    sm.n_tiles = n_tiles;
+    for (int b = 0; b < 9; ++b) sm.ncw[b] = ncw_tile[b];
+    const uint64_t items = 9ull * (n_tiles + 1);
+    unsigned blocks = (unsigned)((items + 255) / 256);
+    if (blocks > 256) blocks = 256;
+    k_frame_misc_sparse<<<dim3(blocks ? blocks : 1, (unsigned)n_frames), 256, 0, st>>>(out, stride_bytes, g, hdr, sm);
     return n + 1;
 }
 int launch_decode_fixed_general(const DevTables& T, const Geom& g, const uint8_t* in, uint8_t* sy, uint64_t pitch, uint32_t* status, cudaStream_t st, uint64_t cw_start)

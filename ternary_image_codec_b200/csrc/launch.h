@@ -19,7 +19,7 @@ struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderC
 // first codeword of every band that the general kernels still have to code (the tiled kernels did the ones before)
 struct CwStart { uint64_t c[9]; };
 // what a super-tile launch leaves to the general kernels: codewords from cs.c[b] on, band symbols from m_start, 6-pixel units from unit_start
-struct SuperTail { CwStart cs; uint64_t m_start; uint64_t unit_start; };
+struct SuperTail { CwStart cs; uint64_t m_start; uint64_t unit_start; uint32_t n_tiles; uint32_t ncw_tile[9]; };
 
 // geometry of the reference decoder as shipped (A.7): slot-major demap of words 6.. of the input
 struct RefDecGeom {
@@ -56,7 +56,10 @@ int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, u
                          uint64_t pitch = 0);
 int launch_regroup_rgb(const uint8_t* sy, uint64_t n_sy, uint64_t tile_area, uint32_t tile_w, uint8_t* rgb, size_t n_px, cudaStream_t st, uint64_t pitch = 0,
                        size_t p_start = 0);
-int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, const CwStart& cs);
+int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, const CwStart& cs,
+                               bool finish = true);
+int launch_frame_misc_sparse(const DevTables& T, const t3c_config& cfg, const Geom& g, uint8_t* out9, size_t n_frames, size_t stride_bytes, cudaStream_t st,
+                             uint32_t n_tiles, const uint32_t ncw_tile[9]);
 int launch_decode_fixed_general_from(const DevTables& T, const Geom& g, const uint8_t* in9, uint8_t* scratch_sy, uint64_t pitch, uint32_t* d_status, cudaStream_t st,
                                      const CwStart& cs);
 // super-tile kernels (k_super.cuh): per-band k, 2D tiles whose width divides 26, beacon periods 3..255.  They code the full
