@@ -601,22 +601,30 @@ __global__ void k_frame_misc_sparse(uint8_t* __restrict__ out_base, size_t strid
 // ------------------------------------------------------------------------------------------
 // General consistent decoder (A.8): thread per codeword -> symbol stream sy' in scratch
 // ------------------------------------------------------------------------------------------
+// cwb = codewords per CTA (<= TPB): TPB for whole frames, small for the ragged end the tiled kernels leave, where fetching the 26 symbols of
+// a codeword (beacon expansion and scrambler phase: divisions) is then spread over all threads
 template <typename I>
 __global__ void __launch_bounds__(TPB) k_decode_fixed_general(const uint8_t* __restrict__ in, uint8_t* __restrict__ sy, Geom g,
-                                                              const GfTables* __restrict__ gf, uint32_t* status, CwStart cs, uint64_t pitch)
+                                                              const GfTables* __restrict__ gf, uint32_t* status, CwStart cs, uint64_t pitch, uint32_t cwb)
 {
     __shared__ GfTables sg;
+    __shared__ uint8_t stage[TPB * 26];
     load_gf(sg, gf);
-    __syncthreads();
     const int b = blockIdx.y, k = g.k[b];
-    const I c = (I)cs.c[b] + (I)blockIdx.x * TPB + threadIdx.x;
-    if (c >= (I)g.ncw[b]) return;
-    uint8_t cw[26], orig[26];
-    const I p0 = 26 * ((I)g.cw_base[b] + c);
-    for (int i = 0; i < 26; ++i) {
-        const I p = p0 + i;
-        cw[i] = orig[i] = sg.dsc[scr_state<I>(g, p)][in[52 + beacon_expand<I>(g, p)] % 27];
+    const I c0 = (I)cs.c[b] + (I)blockIdx.x * cwb;
+    if (c0 >= (I)g.ncw[b]) return;
+    const uint32_t ncta = (uint32_t)(((I)g.ncw[b] - c0) < cwb ? ((I)g.ncw[b] - c0) : cwb);
+    __syncthreads();
+    const I p0 = 26 * ((I)g.cw_base[b] + c0);
+    for (uint32_t idx = threadIdx.x; idx < 26 * ncta; idx += TPB) {
+        const I p = p0 + idx;
+        stage[idx] = sg.dsc[scr_state<I>(g, p)][in[52 + beacon_expand<I>(g, p)] % 27];
     }
+    __syncthreads();
+    if (threadIdx.x >= ncta) return;
+    const I c = c0 + threadIdx.x;
+    uint8_t cw[26], orig[26];
+    for (int i = 0; i < 26; ++i) cw[i] = orig[i] = stage[26 * threadIdx.x + i];
     if (!rs_decode_thread(sg, cw, k, true)) { atomicExch(&status[0], 0u); return; }
     uint32_t nfix = 0;
     for (int i = 0; i < 26; ++i) nfix += cw[i] != orig[i];
@@ -885,8 +893,9 @@ int launch_decode_fixed_general_from(const DevTables& T, const Geom& g, const ui
 {
     const uint64_t mx = cw_left(g, cs);
     if (!mx) return 0;
-    if (small_geom(g)) k_decode_fixed_general<uint32_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cs, pitch);
-    else k_decode_fixed_general<uint64_t><<<dim3(blocks_for(mx, TPB), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cs, pitch);
+    const uint32_t cwb = mx >= 4096 ? (uint32_t)TPB : 8u; // the ragged end of a frame: few codewords, many threads per codeword
+    if (small_geom(g)) k_decode_fixed_general<uint32_t><<<dim3(blocks_for(mx, cwb), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cs, pitch, cwb);
+    else k_decode_fixed_general<uint64_t><<<dim3(blocks_for(mx, cwb), 9), TPB, 0, st>>>(in, sy, g, T.gf, status, cs, pitch, cwb);
     return 1;
 }
 int launch_regroup_words(const uint8_t* sy, uint64_t n_sy, uint64_t area, uint32_t tw, uint8_t* out, size_t n_words, cudaStream_t st, size_t w_start, uint64_t pitch)
