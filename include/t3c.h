@@ -154,7 +154,7 @@ T3C_API t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx*, const t3c_config*, const
                                               uint32_t* d_status, void* stream);
 /* which kernel family the fused calls will use for this config: 1 = tiled fast path, 0 = general path */
 T3C_API int t3c_fast_path_available(const t3c_config* cfg);
-/* 1 = the super-tile kernels take this config (per-band k >= 20, 2D tile widths dividing 26, beacon periods 3..255); they run when
+/* 1 = the super-tile kernels take this config (any per-band k, 2D tile widths dividing 26, beacon periods 3..255); they run when
  * t3c_fast_path_available is 0, the general kernels otherwise keep only the ragged end of a frame */
 T3C_API int t3c_super_path_available(const t3c_config* cfg);
 /* host-only (no device needed): the plan of the super-tile kernels for one super-frame of n_raw_words: out16 = {M band symbols per

@@ -552,9 +552,27 @@ __device__ __forceinline__ uint32_t value_to_rgb3(uint32_t A)
 }
 // 8-entry byte table through PRMT: nibble n of sel (3 plane bits b0 b1 b2) -> b0 + 3 b1 + 9 b2
 __device__ __forceinline__ uint32_t planes4_to_sym(uint32_t sel) { return __byte_perm(0x04030100u, 0x0D0C0A09u, sel); }
+// first plane bit of parity symbol j: nibbles while they fit (r <= 6), dense 3-bit groups for RS(26,18) (8 x 3 trits = bits 8..31)
+template <int K> __host__ __device__ constexpr int plane_shift(int j) { return 26 - K <= 6 ? 8 + 4 * j : 8 + 3 * j; }
+// eight 3-bit groups (24 bits) -> eight nibbles
+__device__ __forceinline__ uint32_t spread3to4(uint32_t x)
+{
+    x = (x & 0x00000FFFu) | ((x & 0x00FFF000u) << 4);
+    x = (x & 0x003F003Fu) | ((x & 0x0FC00FC0u) << 2);
+    return (x & 0x07070707u) | ((x & 0x38383838u) << 1);
+}
+// the parity symbols held by a pair of planes, as bytes: lo = symbols 0..3, hi = symbols 4..7
+template <int K>
+__device__ __forceinline__ void planes_to_parity(uint32_t nz, uint32_t two, uint32_t& lo, uint32_t& hi)
+{
+    uint32_t nzp = nz >> 8, twp = two >> 8;
+    if constexpr (26 - K > 6) { nzp = spread3to4(nzp); twp = spread3to4(twp); }
+    lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
+    hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
+}
 
 template <int K> struct Cfg3 {
-    static_assert(K == 20 || K == 22 || K == 24, "the 8+4j+c plane layout holds r <= 6 parity symbols");
+    static_assert(K == 18 || K == 20 || K == 22 || K == 24, "RS(26,k) profiles");
     static constexpr int R = 26 - K;
     static constexpr int TRIPLES = 9 * K, PX = 27 * K, RGB_BYTES = 81 * K, SYM = 117 * K, UNITS = TRIPLES / 2;
     static constexpr int NCW = 9 * C_MINI, RUN = 26 * C_MINI;
@@ -770,16 +788,14 @@ __device__ __forceinline__ void enc_cw(const uint8_t* src, uint8_t* dst, uint32_
     });
     gf3_add(acc, acc2.nz, acc2.two);
     gf3_add(acc, pat_nz, pat_two);
-    const uint32_t nzp = acc.nz >> 8, twp = acc.two >> 8;
-    const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp);
+    uint32_t lo, hi;
+    planes_to_parity<K>(acc.nz, acc.two, lo, hi);
 #pragma unroll
     for (int j = 0; j < K / 2; ++j) *reinterpret_cast<uint16_t*>(dst + 2 * j) = (uint16_t)pk[j]; // stores after all loads: nothing to order
     *reinterpret_cast<uint16_t*>(dst + K) = (uint16_t)lo;
     if (R > 2) *reinterpret_cast<uint16_t*>(dst + K + 2) = (uint16_t)(lo >> 16);
-    if (R > 4) {
-        const uint32_t hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
-        *reinterpret_cast<uint16_t*>(dst + K + 4) = (uint16_t)hi;
-    }
+    if (R > 4) *reinterpret_cast<uint16_t*>(dst + K + 4) = (uint16_t)hi;
+    if (R > 6) *reinterpret_cast<uint16_t*>(dst + K + 6) = (uint16_t)(hi >> 16);
 }
 // ---- encode phase B: stream symbols -> nine staged runs (data scrambled through the table bytes, parity through the planes)
 template <int K>
@@ -855,8 +871,8 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
         {
             Planes d{acc.nz, acc.two};
             gf3_add(d, chk_nz, chk_nz ^ chk_two);                  // minus the constant: -x keeps nz and flips two where nz is set
-            const uint32_t nzp = d.nz >> 8, twp = d.two >> 8;
-            const uint32_t lo = planes4_to_sym(nzp) + planes4_to_sym(twp), hi = planes4_to_sym(nzp >> 16) + planes4_to_sym(twp >> 16);
+            uint32_t lo, hi;
+            planes_to_parity<K>(d.nz, d.two, lo, hi);
             for (int j = 0; j < 4; ++j) { res[j] = (uint8_t)(lo >> (8 * j)); res[4 + j] = (uint8_t)(hi >> (8 * j)); }
         }
         if (!rs_decode_residual(sg, cwd, K, res)) {
@@ -1033,8 +1049,8 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_encode_rgb_v3(FastParams P, Geo
             uint32_t nz = 0, two = 0;
             for (int j = 0; j < L::R; ++j) {
                 const uint32_t st = st_of(g, tid, K + j);
-                if (st) nz |= 7u << (8 + 4 * j);
-                if (st == 2) two |= 7u << (8 + 4 * j);
+                if (st) nz |= 7u << plane_shift<K>(j);
+                if (st == 2) two |= 7u << plane_shift<K>(j);
             }
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid] = nz;
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid + 1] = two;
@@ -1291,8 +1307,8 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::ENC_WARPS, 1) k_encode_rg
             uint32_t nz = 0, two = 0;
             for (int j = 0; j < L::R; ++j) {
                 const uint32_t st = st_of(g, tid, K + j);
-                if (st) nz |= 7u << (8 + 4 * j);
-                if (st == 2) two |= 7u << (8 + 4 * j);
+                if (st) nz |= 7u << plane_shift<K>(j);
+                if (st == 2) two |= 7u << plane_shift<K>(j);
             }
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid] = nz;
             reinterpret_cast<uint32_t*>(smem + L::ENC_PAT)[2 * tid + 1] = two;
@@ -1529,7 +1545,7 @@ int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st,
     static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
-    if constexpr (K >= 20) {
+    if constexpr (K >= 18) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
@@ -1547,7 +1563,7 @@ int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st,
     static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
-    if constexpr (K >= 20) {
+    if constexpr (K >= 18) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
@@ -1726,12 +1742,12 @@ static uint32_t all_tiles(const Geom& g)
 }
 uint32_t fast_full_tiles_encode(const Geom& g, size_t n_px)
 {
-    if (g.uniform_k < 20) return 0;
+    if (g.uniform_k < 18) return 0;
     return full_tiles(g, n_px < 2 * g.n_words ? n_px : 2 * g.n_words);
 }
 uint32_t fast_full_tiles_decode(const Geom& g, size_t n_px_out, size_t out_pitch, size_t n_frames)
 {
-    if (g.uniform_k < 20) return 0;
+    if (g.uniform_k < 18) return 0;
     return (n_frames > 1 && (out_pitch & 1)) ? 0 : full_tiles(g, n_px_out); // v3 writes RGB with 2-byte stores: frames start on even bytes
 }
 
@@ -1799,7 +1815,7 @@ int launch_decode_rgb_fast(const DevTables& T, const t3c_config& cfg, const Geom
 int launch_encode_words_fast(const DevTables& T, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, uint32_t* n_full_out)
 {
     *n_full_out = 0;
-    if (g.uniform_k < 20 || (((uintptr_t)raw9 | (uintptr_t)out9) & 15)) return -1;
+    if (g.uniform_k < 18 || (((uintptr_t)raw9 | (uintptr_t)out9) & 15)) return -1;
     const uint32_t n_full = full_tiles(g, 2 * g.n_words);
     if (!n_full) return 0;
     FastParams P{};
@@ -1812,6 +1828,7 @@ int launch_encode_words_fast(const DevTables& T, const Geom& g, const uint8_t* r
     case 24: n = launch_enc<24>(T, P, g, st, n_full, 0, n_full, false, true); break;
     case 22: n = launch_enc<22>(T, P, g, st, n_full, 0, n_full, false, true); break;
     case 20: n = launch_enc<20>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    case 18: n = launch_enc<18>(T, P, g, st, n_full, 0, n_full, false, true); break;
     default: return -1;
     }
     *n_full_out = n_full;
@@ -1821,7 +1838,7 @@ int launch_decode_words_fast(const DevTables& T, const Geom& g, const uint8_t* i
                              cudaStream_t st, uint32_t* n_full_out)
 {
     *n_full_out = 0;
-    if (g.uniform_k < 20 || (((uintptr_t)raw9 | (uintptr_t)in9) & 15)) return -1;
+    if (g.uniform_k < 18 || (((uintptr_t)raw9 | (uintptr_t)in9) & 15)) return -1;
     const uint32_t n_full = full_tiles(g, 2 * n_words_out);
     if (!n_full) return 0;
     FastParams P{};
@@ -1835,6 +1852,7 @@ int launch_decode_words_fast(const DevTables& T, const Geom& g, const uint8_t* i
     case 24: n = launch_dec<24>(T, P, g, st, n_full, 0, n_full, false, true); break;
     case 22: n = launch_dec<22>(T, P, g, st, n_full, 0, n_full, false, true); break;
     case 20: n = launch_dec<20>(T, P, g, st, n_full, 0, n_full, false, true); break;
+    case 18: n = launch_dec<18>(T, P, g, st, n_full, 0, n_full, false, true); break;
     default: return -1;
     }
     *n_full_out = n_full;

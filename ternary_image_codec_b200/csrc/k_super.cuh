@@ -164,8 +164,9 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
             uint32_t nz = 0, two = 0;
             for (int j = 0; j < 26 - K; ++j) {
                 const uint32_t st = st_of(g, tid, K + j);
-                if (st) nz |= 7u << (8 + 4 * j);
-                if (st == 2) two |= 7u << (8 + 4 * j);
+                const int sh = K == 18 ? plane_shift<18>(j) : plane_shift<20>(j);
+                if (st) nz |= 7u << sh;
+                if (st == 2) two |= 7u << sh;
             }
             pat[6 * ks + 2 * tid] = nz;
             pat[6 * ks + 2 * tid + 1] = two;
@@ -247,7 +248,8 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
             const uint32_t pnz = pat[6 * ks + 2 * v], ptw = pat[6 * ks + 2 * v + 1];
             if (K == 20) enc_cw<20>(src, dst, pa, pnz, ptw);
             else if (K == 22) enc_cw<22>(src, dst, pa, pnz, ptw);
-            else enc_cw<24>(src, dst, pa, pnz, ptw);
+            else if (K == 24) enc_cw<24>(src, dst, pa, pnz, ptw);
+            else enc_cw<18>(src, dst, pa, pnz, ptw);
         }
         __syncthreads();                           // the nine runs complete, S free again
         SUP_TICK(2);
@@ -442,7 +444,8 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             const uint32_t cnz = chk[6 * ks + 2 * v], ctw = chk[6 * ks + 2 * v + 1];
             if (K == 20) dec_cw<20>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
             else if (K == 22) dec_cw<22>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
-            else dec_cw<24>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
+            else if (K == 24) dec_cw<24>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
+            else dec_cw<18>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
         }
         __syncthreads();                           // S complete, R dead
         SUP_TICK(6);
@@ -483,13 +486,12 @@ static uint32_t lcm_u32(uint32_t a, uint32_t b) { return a / gcd_u32(a, b) * b; 
 static uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
 static uint32_t up256(uint32_t x) { return (x + 255u) & ~255u; }
 
-// the configs the super-tile kernels take: every k >= 20 (plane tables), at most the 2D tile widths that divide 26,
+// the configs the super-tile kernels take: any per-band k, 2D tile widths that divide 26,
 // beacon periods that leave at most one slot per 16-byte chunk and fit the 32-bit reciprocal
 bool super_config_ok(const t3c_config& cfg)
 {
     if (cfg.profile == T3C_PROFILE_RAW) return false;
     static const int ks[4] = {24, 22, 20, 18};
-    for (int b = 0; b < 9; ++b) if (ks[cfg.uep[b] % 4] < 20) return false;
     if (use_2d(cfg) && (cfg.tile_w > 26 || 26 % cfg.tile_w != 0)) return false;
     if (use_beacon(cfg) && cfg.beacon_slot < 9 && (cfg.beacon_period < 3 || cfg.beacon_period > 255)) return false;
     return true;

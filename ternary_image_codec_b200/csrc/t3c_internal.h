@@ -40,8 +40,8 @@ struct RsTables {
     RowTable row[2][4];
     uint8_t  gen[4][12];      // generator polynomials, low-first (OLD:501-516)
     uint8_t  par[2][4][24][8]; // P[i][j] as symbols (general/per-symbol kernels)
-    // the same rows for the v3 tiled kernels (k >= 20 only): {nz, two} planes with trit c of parity symbol j at
-    // bit 8 + 4j + c, so that the low byte of an entry is free for an embedded (de)scrambled symbol and each
+    // the same rows for the tiled kernels: {nz, two} planes with trit c of parity symbol j at bit 8 + 4j + c (k >= 20; k = 18: its 24
+    // parity trits fill bits 8..31 densely, bit 8 + 3j + c, and are spread to nibbles when they leave the planes), so that the low byte of an entry is free for an embedded (de)scrambled symbol and each
     // nibble of (plane >> 8) is a PRMT selector (planes -> symbol bytes without shifts or tables)
     uint32_t pl[2][4][kRows][kVals][2];
 };

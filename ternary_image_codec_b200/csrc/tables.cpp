@@ -119,14 +119,14 @@ void build_tables(HostTables& T)
                     else v[i - k] = gneg(d);
                     R.e[i][d] = planes_of(v, r);
                     uint32_t nz = 0, two = 0;
-                    if (r <= 6)
-                        for (int j = 0; j < r; ++j) {
-                            Tr t = split(v[j]);
-                            for (int c = 0; c < 3; ++c) {
-                                if (t.t[c]) nz |= 1u << (8 + 4 * j + c);
-                                if (t.t[c] == 2) two |= 1u << (8 + 4 * j + c);
-                            }
+                    for (int j = 0; j < r; ++j) { // nibbles for r <= 6 (PRMT selectors), dense 3-bit groups for r = 8 (24 trits fill bits 8..31)
+                        Tr t = split(v[j]);
+                        const int sh = r <= 6 ? 8 + 4 * j : 8 + 3 * j;
+                        for (int c = 0; c < 3; ++c) {
+                            if (t.t[c]) nz |= 1u << (sh + c);
+                            if (t.t[c] == 2) two |= 1u << (sh + c);
                         }
+                    }
                     T.rs.pl[arith][ki][i][d][0] = nz;
                     T.rs.pl[arith][ki][i][d][1] = two;
                 }

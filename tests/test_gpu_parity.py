@@ -630,6 +630,8 @@ SUPER_CONFIGS = [
     dict(profile=T.P2, uep=(0, 1, 2, 0, 1, 2, 0, 1, 2), beacon=(7, 4, True)),                            # three k values, 1D
     dict(profile=T.P5, tile=(1, 9), uep=T.UEP_LUMA, beacon=(26, 11, True)),                              # w = 1: identity rows; slot > 8: words completed, no beacon
     dict(profile=T.P3, uep=2, beacon=(26, 2, True), seed=(0, 1, 2)),
+    dict(profile=T.P5, tile=(26, 4), uep=(3, 2, 3, 2, 3, 2, 3, 2, 3), beacon=(9, 5, True), seed=(1, 1, 0)),   # k = 18/20: eight parity symbols (dense plane layout)
+    dict(profile=T.P4, uep=3, beacon=(26, 2, True)),                                                            # uniform k = 18 with a beacon
 ]
 
 

@@ -182,7 +182,7 @@ def test_super_tile_plan_covers_every_codeword_once(kw, decode):
 
 def test_super_tile_plan_rejects_what_the_kernels_do_not_take():
     import ternary_image_codec_b200 as t3
-    for kw in (dict(profile=4, tile=(7, 5)), dict(profile=3, uep=3), dict(profile=1, beacon=(2, 1, True)), dict(profile=1, beacon=(300, 1, True)),
+    for kw in (dict(profile=4, tile=(7, 5)), dict(profile=1, beacon=(2, 1, True)), dict(profile=1, beacon=(300, 1, True)),
                dict(profile=t3.RAW_MODE)):
         gc = t3.make_config(**kw)
         assert not t3.super_path_available(gc) and t3.super_plan(gc, 100000) is None
