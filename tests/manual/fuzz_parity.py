@@ -1,7 +1,7 @@
 """Random configs x sizes: CUDA path (through the C ABI) against the CPU oracle -- raw-word API and RGB frames, both arithmetics,
-consistent decode with injected errors.  python tools/fuzz_parity.py [seconds] [seed]"""
+consistent decode with injected errors.  python tests/manual/fuzz_parity.py [seconds] [seed]"""
 import sys, os, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import t3oracle as T

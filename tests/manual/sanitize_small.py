@@ -1,7 +1,7 @@
 """Small fused encode/decode cases for compute-sanitizer (memcheck / racecheck): multi-frame, odd sizes, errors."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "oracle"))
 import numpy as np
 import t3oracle as T
 import ternary_image_codec_b200 as t3

@@ -1,7 +1,7 @@
 """Small super-tile kernel cases (per-band k, 2D, beacon) for compute-sanitizer: raw words and RGB frames, with errors."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "oracle"))
 import numpy as np
 import t3oracle as T
 import ternary_image_codec_b200 as t3
