@@ -326,6 +326,9 @@ __device__ __forceinline__ uint32_t mod27_word(uint32_t w)
 // of 4 x 256 entries, table j multiplying a 32-bit remainder by x^(8 * 128 * 2^j) (j = 0: one segment ... j = 8: one tile); then
 // x^(8 * 2^i), i = 0..31, for the generic shift.
 constexpr int CRC_SHIFT0 = 1024, CRC_NSHIFT = 9, CRC_POW0 = CRC_SHIFT0 + CRC_NSHIFT * 1024;
+// ... then, for the lane-strided tile kernel: sixteen 256-entry tables X_j[v] = (CRC state after byte v and 15 - j zero bytes, from state 0),
+// three shift tables for 16, 32 and 64 bytes, and the state after one tile of zero bytes from 0xFFFFFFFF
+constexpr int CRC_NPOW = 48, CRC_X0 = CRC_POW0 + CRC_NPOW, CRC_LANE0 = CRC_X0 + 16 * 256, CRC_K0 = CRC_LANE0 + 3 * 1024, CRC_WORDS = CRC_K0 + 1;
 __device__ __forceinline__ uint32_t crc_shift(const uint32_t* __restrict__ t, uint32_t v) // t = one shift table (shared or global)
 {
     return t[v & 0xFFu] ^ t[256 + ((v >> 8) & 0xFFu)] ^ t[512 + ((v >> 16) & 0xFFu)] ^ t[768 + (v >> 24)];
@@ -337,14 +340,27 @@ __device__ inline uint32_t crc_shift_bytes(const uint32_t* __restrict__ tabs, ui
 }
 // src / dst: frame f at + f * pitch; *_off = where the 9n payload bytes start inside a frame of src / dst (0 or 4), all 4-byte aligned.
 // out: one CRC per full tile at tile_crc[f * tiles + t]; the last, partial tile of a frame leaves one CRC per segment at seg_crc[f * 256 + s]
-__global__ void __launch_bounds__(T3V_TPB) k_t3v_tiles(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t src_off, uint8_t* __restrict__ dst,
-                                                     uint64_t dst_pitch, uint32_t dst_off, uint64_t n_bytes, uint32_t tiles_per_frame, int reduce,
-                                                     const uint32_t* __restrict__ tabs, uint32_t* __restrict__ tile_crc, uint32_t* __restrict__ seg_crc)
+// Shared-memory layout of the tile body below (uint32 words): slice tables, padded tile, join scratch
+constexpr int T3V_SW = 8; // warps (tiles in flight) per CTA of the lane-strided kernel
+constexpr int T3V_BODY_WORDS = 4 * 256 + T3V_TPB * 33 + T3V_TPB;
+__device__ inline uint32_t crc_mul_bf(uint32_t a, uint32_t b)   // crc_mul without data-dependent control flow
 {
-    __shared__ uint32_t tab[4 * 256];
-    __shared__ uint32_t tile[T3V_TPB * 33];
-    __shared__ uint32_t red[T3V_TPB];
-    const uint32_t tid = threadIdx.x, f = blockIdx.x / tiles_per_frame, t = blockIdx.x - f * tiles_per_frame;
+    uint32_t p = 0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) { p ^= b & (0u - (a >> 31)); a <<= 1; b = (b >> 1) ^ (CRC_POLY & (0u - (b & 1u))); }
+    return p;
+}
+// One CTA, one tile (tile t of frame f, possibly the partial last one): stage it in shared memory, one 128-byte segment per thread by
+// slice-by-4, then join: the complete segments sit right-aligned in red[] (empty strings in front: their CRC 0 joins as nothing), pairwise
+// crc(A | B) = crc(A) x^(8|B|) + crc(B) over 1, 2, 4 ... 128 segments with the shift tables 0..7, and thread 0 appends the last (1..128 byte) one.
+__device__ __forceinline__ void t3v_tile_body(uint32_t* __restrict__ sm, uint32_t f, uint32_t t, const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t src_off,
+                                              uint8_t* __restrict__ dst, uint64_t dst_pitch, uint32_t dst_off, uint64_t n_bytes, uint32_t tiles_per_frame, int reduce,
+                                              const uint32_t* __restrict__ tabs, uint32_t* __restrict__ tile_crc)
+{
+    uint32_t* tab = sm;
+    uint32_t* tile = sm + 4 * 256;
+    uint32_t* red = tile + T3V_TPB * 33;
+    const uint32_t tid = threadIdx.x;
     for (int k = 0; k < 4; ++k) tab[256 * k + tid] = __ldg(tabs + 256 * k + tid);
     const uint64_t b0 = (uint64_t)t * T3V_TILE, left = n_bytes - b0, nb = left < T3V_TILE ? left : T3V_TILE; // bytes of this tile
     const uint8_t* s = src + f * src_pitch + src_off + b0;
@@ -362,11 +378,12 @@ __global__ void __launch_bounds__(T3V_TPB) k_t3v_tiles(const uint8_t* __restrict
         if (d) d[4 * nw + tid] = (uint8_t)b;
         reinterpret_cast<uint8_t*>(tile)[4 * ((nw >> 5) * 33 + (nw & 31)) + tid] = (uint8_t)b;
     }
+    red[tid] = 0;
     __syncthreads();
-    const uint64_t sb = (uint64_t)tid * T3V_SEG;
+    const uint32_t nseg = (uint32_t)((nb + T3V_SEG - 1) / T3V_SEG), last_len = (uint32_t)(nb - (uint64_t)(nseg - 1) * T3V_SEG);   // nb >= 1
     uint32_t crc = 0;
-    if (sb < nb) {
-        const uint32_t len = (uint32_t)(nb - sb < T3V_SEG ? nb - sb : T3V_SEG);
+    if (tid < nseg) {
+        const uint32_t len = tid + 1 < nseg ? T3V_SEG : last_len;
         const uint32_t* p = tile + tid * 33;
         uint32_t c = 0xFFFFFFFFu;
         uint32_t i = 0;
@@ -376,46 +393,132 @@ __global__ void __launch_bounds__(T3V_TPB) k_t3v_tiles(const uint8_t* __restrict
         }
         for (; i < len; ++i) c = tab[(c ^ reinterpret_cast<const uint8_t*>(p)[i]) & 0xFFu] ^ (c >> 8);
         crc = c ^ 0xFFFFFFFFu;
+        if (tid + 1 < nseg) red[tid + T3V_TPB - (nseg - 1)] = crc;
     }
-    if (nb < T3V_TILE) { if (sb < nb) seg_crc[(uint64_t)f * T3V_TPB + tid] = crc; return; } // the frame's last tile: joined by k_t3v_finish
-    // a full tile: crc(A | B) = crc(A) x^(8|B|) + crc(B), pairwise over 1, 2, 4 ... 128 segments (shift tables 0..7, read through L1)
-    red[tid] = crc;
     __syncthreads();
     for (int j = 0; j < 8; ++j) {
         const uint32_t st = 1u << j;
         if ((tid & (2 * st - 1)) == 0) red[tid] = crc_shift(tabs + CRC_SHIFT0 + 1024 * j, red[tid]) ^ red[tid + st];
         __syncthreads();
     }
-    if (tid == 0) tile_crc[(uint64_t)f * tiles_per_frame + t] = red[0];
+    if (tid == nseg - 1) tile_crc[(uint64_t)f * tiles_per_frame + t] = crc_shift_bytes(tabs, red[0], last_len) ^ crc;
 }
-// One CTA per frame joins the tile CRCs (full tiles) and the last tile's segment CRCs.  check = 0: write n and the record's CRC into rec
-// (record f at rec + f * pitch); check = 1: compare them with what the record holds -> ok[f]; crc_out: the payload's plain CRC-32
-__global__ void __launch_bounds__(1024) k_t3v_finish(const uint32_t* __restrict__ tabs, const uint32_t* __restrict__ tile_crc, const uint32_t* __restrict__ seg_crc,
-                                                   uint32_t tiles_per_frame, uint64_t n_bytes, uint32_t n_words, uint8_t* __restrict__ rec, uint64_t pitch,
-                                                   int check, uint8_t* __restrict__ ok, uint32_t* __restrict__ crc_out)
+// Full tiles, lane-strided: a warp takes one 32 KiB tile in 64 steps of 512 bytes, lane l the 16 bytes at 512 k + 16 l: perfectly coalesced
+// loads and stores, no shared-memory tile.  A lane keeps the CRC state of "its" bytes as if the other lanes' bytes were zero:
+//   c <- c * x^(8*512) + X(16 bytes)     (CRC is linear over GF(2): X = sum_j X_j[byte j], sixteen small look-ups; the symbols are < 27, so the 32 lanes
+//   of one look-up hit at most 27 consecutive words: no bank conflicts; the shift by 512 bytes is four look-ups)
+// and the 32 lane states are joined at the end of the tile: crc = sum_l c_l * x^(8*16*(31-l)), pairwise by shuffles.
+__global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t src_off, uint8_t* __restrict__ dst,
+                                                                 uint64_t dst_pitch, uint32_t dst_off, uint32_t full_tiles, uint32_t tiles_per_frame, uint32_t n_frames,
+                                                                 int reduce, const uint32_t* __restrict__ tabs, uint32_t* __restrict__ tile_crc, uint64_t n_bytes,
+                                                                 uint32_t body_ctas)
+{
+    static_assert(T3V_BODY_WORDS >= 20 * 256 && 32 * T3V_SW == T3V_TPB, "one shared buffer, one CTA shape for both roles");
+    __shared__ __align__(16) uint32_t sm[T3V_BODY_WORDS];
+    if (blockIdx.x < body_ctas) {   // the partial last tile of frame blockIdx.x (first in the grid: it is the longest serial piece)
+        t3v_tile_body(sm, blockIdx.x, full_tiles, src, src_pitch, src_off, dst, dst_pitch, dst_off, n_bytes, tiles_per_frame, reduce, tabs, tile_crc);
+        return;
+    }
+    uint32_t* sx = sm;
+    uint32_t* s512 = sm + 16 * 256;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, cta = blockIdx.x - body_ctas, n_cta = gridDim.x - body_ctas;
+    for (uint32_t i = tid; i < 16 * 256; i += 32 * T3V_SW) sx[i] = __ldg(tabs + CRC_X0 + i);
+    for (uint32_t i = tid; i < 4 * 256; i += 32 * T3V_SW) s512[i] = __ldg(tabs + CRC_SHIFT0 + 1024 * 2 + i);   // 128 * 2^2 = 512 bytes
+    __syncthreads();
+    const uint32_t k0 = __ldg(tabs + CRC_K0);
+    const uint64_t total = (uint64_t)full_tiles * n_frames;
+    for (uint64_t gw = (uint64_t)cta * T3V_SW + warp; gw < total; gw += (uint64_t)n_cta * T3V_SW) {
+        const uint32_t f = (uint32_t)(gw / full_tiles), t = (uint32_t)(gw - (uint64_t)f * full_tiles);
+        const uint8_t* sp = src + f * src_pitch + src_off + (uint64_t)t * T3V_TILE + 16u * lane;
+        uint8_t* dp = dst ? dst + f * dst_pitch + dst_off + (uint64_t)t * T3V_TILE + 16u * lane : nullptr;
+        const bool s16 = (reinterpret_cast<uintptr_t>(sp) & 15) == 0, d16 = (reinterpret_cast<uintptr_t>(dp) & 15) == 0;   // else 4-byte accesses (the
+        // record's payload sits at + 4; re-aligning through shuffles was measured slower)
+        uint32_t c = 0;
+        constexpr int G = 4;   // steps per group: the group's loads are issued together
+#pragma unroll 1
+        for (int k0g = 0; k0g < T3V_TILE / 512; k0g += G) {
+            uint32_t w[G][4];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint8_t* a = sp + 512 * (k0g + g);
+                if (s16) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(a)); w[g][0] = q.x; w[g][1] = q.y; w[g][2] = q.z; w[g][3] = q.w; }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) w[g][i] = __ldg(reinterpret_cast<const uint32_t*>(a) + i);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (reduce) {   // symbols >= 27 are stored % 27 (rare: one test for the sixteen bytes)
+                    uint32_t bad = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bad |= (((w[g][i] & 0x7F7F7F7Fu) + 0x65656565u) | w[g][i]);
+                    if (bad & 0x80808080u) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) w[g][i] = mod27_word(w[g][i]);
+                    }
+                }
+                if (dp) {
+                    uint8_t* a = dp + 512 * (k0g + g);
+                    if (d16) *reinterpret_cast<uint4*>(a) = make_uint4(w[g][0], w[g][1], w[g][2], w[g][3]);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(a)[i] = w[g][i];
+                    }
+                }
+                uint32_t x = s512[c & 0xFFu] ^ s512[256 + ((c >> 8) & 0xFFu)] ^ s512[512 + ((c >> 16) & 0xFFu)] ^ s512[768 + (c >> 24)];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    x ^= sx[256 * (4 * i) + (w[g][i] & 0xFFu)] ^ sx[256 * (4 * i + 1) + ((w[g][i] >> 8) & 0xFFu)] ^ sx[256 * (4 * i + 2) + ((w[g][i] >> 16) & 0xFFu)] ^
+                         sx[256 * (4 * i + 3) + (w[g][i] >> 24)];
+                c = x;
+            }
+        }
+        // join the lanes: lane l stands 16 (31 - l) bytes before the end of a step
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, c, 1u << j);
+            const uint32_t* tb = j < 3 ? tabs + CRC_LANE0 + 1024 * j : tabs + CRC_SHIFT0 + 1024 * (j - 3);  // 16, 32, 64 | 128, 256 bytes
+            c = (__ldg(tb + (c & 0xFFu)) ^ __ldg(tb + 256 + ((c >> 8) & 0xFFu)) ^ __ldg(tb + 512 + ((c >> 16) & 0xFFu)) ^ __ldg(tb + 768 + (c >> 24))) ^ other;
+        }
+        if (lane == 0) tile_crc[(uint64_t)f * tiles_per_frame + t] = c ^ k0 ^ 0xFFFFFFFFu;   // + the initial state carried through the tile, final inversion
+    }
+}
+// One CTA per frame joins the tile CRCs.  check = 0: write n and the record's CRC into rec (record f at rec + f * pitch); check = 1: compare
+// them with what the record holds -> ok[f]; crc_out: the payload's plain CRC-32.
+// Thread i walks `per` consecutive full tiles (Horner with the 32 KiB shift table), the tiles right-aligned over the 1024 threads so that every
+// pairwise join on level j is the same multiplication by x^(8 * 32 KiB * per * 2^j); thread 0 appends the partial last tile.
+__global__ void __launch_bounds__(1024) k_t3v_finish(const uint32_t* __restrict__ tabs, const uint32_t* __restrict__ tile_crc, uint32_t tiles_per_frame, uint64_t n_bytes,
+                                                   uint32_t n_words, uint8_t* __restrict__ rec, uint64_t pitch, int check, uint8_t* __restrict__ ok,
+                                                   uint32_t* __restrict__ crc_out)
 {
     __shared__ uint32_t red[1024];
+    __shared__ uint32_t mlev[11];
     const uint32_t tid = threadIdx.x, f = blockIdx.x;
     const uint64_t n_full = n_bytes / T3V_TILE, tail = n_bytes - n_full * T3V_TILE;     // full tiles, bytes of the partial last tile
-    // threads 0..767 walk contiguous groups of full tiles, threads 768..1023 take one segment of the last tile each
+    const uint64_t per = n_full ? (n_full + 1023) / 1024 : 1, pad = 1024 * per - n_full; // empty places in front
+    const uint32_t* p = tile_crc + (uint64_t)f * tiles_per_frame;
     uint32_t acc = 0;
-    uint64_t after = 0;                                                                   // payload bytes after what acc stands for
-    if (tid < 768) {
-        const uint64_t per = (n_full + 767) / 768, g0 = (uint64_t)tid * per, g1 = g0 + per < n_full ? g0 + per : n_full;
-        const uint32_t* p = tile_crc + (uint64_t)f * tiles_per_frame;
-        for (uint64_t t = g0; t < g1; ++t) acc = crc_shift(tabs + CRC_SHIFT0 + 1024 * 8, acc) ^ p[t];
-        after = g0 < g1 ? n_bytes - g1 * T3V_TILE : 0;
-    } else {
-        const uint64_t sb = (uint64_t)(tid - 768) * T3V_SEG;
-        if (sb < tail) {
-            const uint64_t len = tail - sb < T3V_SEG ? tail - sb : T3V_SEG;
-            acc = seg_crc[(uint64_t)f * T3V_TPB + (tid - 768)];
-            after = tail - sb - len;
-        }
+    for (uint64_t v = (uint64_t)tid * per; v < (uint64_t)(tid + 1) * per; ++v)
+        if (v >= pad) acc = crc_shift(tabs + CRC_SHIFT0 + 1024 * 8, acc) ^ p[v - pad];
+    red[tid] = acc;
+    // warp j < 10: mlev[j] = x^(8 * 32 KiB * per * 2^j) = product over the set bits b of per of x^(8 * 2^(15 + j + b)); warp 10: x^(8 * tail).
+    // One table entry per lane, multiplied up by shuffles.  per < 2^11 (n_bytes < 2^36): 15 + 9 + 10 < CRC_NPOW
+    const uint32_t wj = tid >> 5, lb = tid & 31u;
+    if (wj <= 10) {
+        const uint64_t bits = wj < 10 ? per : tail;
+        uint32_t m = 1u << 31;                                              // x^0
+        if (lb < 16 && ((bits >> lb) & 1)) m = __ldg(tabs + CRC_POW0 + (wj < 10 ? 15 + wj : 0) + lb);
+        for (int sh = 8; sh; sh >>= 1) m = crc_mul_bf(m, __shfl_xor_sync(0xFFFFFFFFu, m, sh));
+        if (lb == 0) mlev[wj] = m;
     }
-    red[tid] = after ? crc_shift_bytes(tabs, acc, after) : acc;
     __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) { if (tid < (uint32_t)s) red[tid] ^= red[tid + s]; __syncthreads(); }
+    for (int j = 0; j < 10; ++j) {
+        const uint32_t st = 1u << j;
+        if ((tid & (2 * st - 1)) == 0) red[tid] = crc_mul_bf(mlev[j], red[tid]) ^ red[tid + st];
+        __syncthreads();
+    }
+    if (tid == 0 && tail) red[0] = crc_mul_bf(mlev[10], red[0]) ^ p[n_full];
     if (tid == 0 && crc_out) crc_out[f] = red[0];                         // plain crc32 of the payload
     if (tid == 0 && rec) {
         uint32_t cn = 0xFFFFFFFFu;                                        // crc32 of the four bytes of n
@@ -449,15 +552,36 @@ void build_crc_tables(uint32_t* h)
         for (int k = 0; k < 4; ++k) for (uint32_t u = 0; u < 256; ++u) h[CRC_SHIFT0 + 1024 * j + 256 * k + u] = crc_mul(m, u << (8 * k));
     }
     uint32_t sq = 1u << 23; // x^8
-    for (int i = 0; i < 32; ++i) { h[CRC_POW0 + i] = sq; sq = crc_mul(sq, sq); }
+    for (int i = 0; i < CRC_NPOW; ++i) { h[CRC_POW0 + i] = sq; sq = crc_mul(sq, sq); }
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t m = crc_xpow8((uint64_t)(15 - j));
+        for (uint32_t v = 0; v < 256; ++v) h[CRC_X0 + 256 * j + v] = crc_mul(m, h[v]);
+    }
+    for (int j = 0; j < 3; ++j) {
+        const uint32_t m = crc_xpow8(16ull << j);
+        for (int k = 0; k < 4; ++k) for (uint32_t u = 0; u < 256; ++u) h[CRC_LANE0 + 1024 * j + 256 * k + u] = crc_mul(m, u << (8 * k));
+    }
+    h[CRC_K0] = crc_mul(crc_xpow8(T3V_TILE), 0xFFFFFFFFu);
 }
-size_t crc_table_words() { return CRC_POW0 + 32; }
+size_t crc_table_words() { return CRC_WORDS; }
 
-// scratch (uint32): one CRC per tile and 256 segment CRCs per frame
+// one launch: the full tiles lane-strided, the partial last tile of every frame by a CTA of its own
+static int t3v_tiles(const uint8_t* src, uint64_t src_pitch, uint32_t src_off, uint8_t* dst, uint64_t dst_pitch, uint32_t dst_off, uint64_t nb, uint64_t tiles,
+                     size_t n_frames, int reduce, const uint32_t* tabs, uint32_t* tile_crc, cudaStream_t st)
+{
+    if (!tiles) return 0;
+    const uint64_t full = nb / T3V_TILE, total = full * n_frames, body = tiles > full ? n_frames : 0;
+    uint64_t grid = (total + T3V_SW - 1) / T3V_SW;
+    if (grid > 148 * 8) grid = 148 * 8;
+    k_t3v_tiles_strided<<<(unsigned)(grid + body), 32 * T3V_SW, 0, st>>>(src, src_pitch, src_off, dst, dst_pitch, dst_off, (uint32_t)full, (uint32_t)tiles, (uint32_t)n_frames,
+                                                                       reduce, tabs, tile_crc, nb, (uint32_t)body);
+    return 1;
+}
+// scratch (uint32): one CRC per tile
 size_t t3v_partial_words(size_t n_words, size_t n_frames)
 {
     const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE;
-    return (size_t)(((tiles ? tiles : 1) + T3V_TPB) * n_frames);
+    return (size_t)((tiles ? tiles : 1) * n_frames);
 }
 // words9 (frame f at + f * 9 * stride_words, 4-byte aligned) -> records (record f at + f * record_pitch, 4-byte aligned)
 int launch_t3v_records(const uint32_t* tabs, const uint8_t* words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* records, size_t record_pitch,
@@ -465,10 +589,9 @@ int launch_t3v_records(const uint32_t* tabs, const uint8_t* words9, size_t n_wor
 {
     if (!n_frames) return 0;
     const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
-    uint32_t* seg = partial + tpf * n_frames;
     int n = 0;
-    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(words9, 9ull * stride_words, 0, records, record_pitch, 4, nb, (uint32_t)tiles, 1, tabs, partial, seg); ++n; }
-    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, seg, (uint32_t)tpf, nb, (uint32_t)n_words, records, record_pitch, 0, nullptr, nullptr);
+    n += t3v_tiles(words9, 9ull * stride_words, 0, records, record_pitch, 4, nb, tiles, n_frames, 1, tabs, partial, st);
+    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, (uint32_t)tpf, nb, (uint32_t)n_words, records, record_pitch, 0, nullptr, nullptr);
     return n + 1;
 }
 // records -> words9 (may be null: check only) and ok[f] = the record announces n_words and its CRC matches (t3v_read_frame)
@@ -477,10 +600,9 @@ int launch_t3v_read(const uint32_t* tabs, const uint8_t* records, size_t record_
 {
     if (!n_frames) return 0;
     const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
-    uint32_t* seg = partial + tpf * n_frames;
     int n = 0;
-    if (tiles) { k_t3v_tiles<<<(unsigned)(tiles * n_frames), T3V_TPB, 0, st>>>(records, record_pitch, 4, words9, 9ull * stride_words, 0, nb, (uint32_t)tiles, 0, tabs, partial, seg); ++n; }
-    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, seg, (uint32_t)tpf, nb, (uint32_t)n_words, const_cast<uint8_t*>(records), record_pitch, 1, ok, nullptr);
+    n += t3v_tiles(records, record_pitch, 4, words9, 9ull * stride_words, 0, nb, tiles, n_frames, 0, tabs, partial, st);
+    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, (uint32_t)tpf, nb, (uint32_t)n_words, const_cast<uint8_t*>(records), record_pitch, 1, ok, nullptr);
     return n + 1;
 }
 // plain CRC-32 of n bytes (4-byte aligned) with the same two kernels
@@ -488,8 +610,8 @@ int launch_crc32(const uint32_t* tabs, const uint8_t* data, size_t n, uint32_t* 
 {
     const uint64_t tiles = ((uint64_t)n + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
     int k = 0;
-    if (tiles) { k_t3v_tiles<<<(unsigned)tiles, T3V_TPB, 0, st>>>(data, 0, 0, nullptr, 0, 0, n, (uint32_t)tiles, 0, tabs, partial, partial + tpf); ++k; }
-    k_t3v_finish<<<1, 1024, 0, st>>>(tabs, partial, partial + tpf, (uint32_t)tpf, n, 0, nullptr, 0, 0, nullptr, out);
+    k += t3v_tiles(data, 0, 0, nullptr, 0, 0, n, tiles, 1, 0, tabs, partial, st);
+    k_t3v_finish<<<1, 1024, 0, st>>>(tabs, partial, (uint32_t)tpf, n, 0, nullptr, 0, 0, nullptr, out);
     return k + 1;
 }
 

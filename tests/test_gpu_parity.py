@@ -696,7 +696,7 @@ def test_super_tile_kernels_rgb_frames(codec, oracle, t3, ci, n_px, nf):
 def test_t3v_records_and_crc32(codec, oracle):
     import zlib
     r = rng(960)
-    for n in (0, 1, 3, 4, 5, 127, 128, 129, 32767, 32768, 32769, 1000003):
+    for n in (0, 1, 3, 4, 5, 127, 128, 129, 32767, 32768, 32769, 1000003, 64 * 32768, 40000001):   # ... whole tiles only; more than 1024 tiles
         data = r.integers(0, 256, n, dtype=np.uint8)
         assert codec.crc32(data) == zlib.crc32(data.tobytes()) == oracle.crc32(data), n
     for nw in (0, 1, 2, 14, 15, 3640, 3641, 3642, 20011, 300007):     # around one segment (128 B), one tile (32 KiB) and many tiles
