@@ -486,39 +486,50 @@ __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t
 }
 // One CTA per frame joins the tile CRCs.  check = 0: write n and the record's CRC into rec (record f at rec + f * pitch); check = 1: compare
 // them with what the record holds -> ok[f]; crc_out: the payload's plain CRC-32.
-// Thread i walks `per` consecutive full tiles (Horner with the 32 KiB shift table), the tiles right-aligned over the 1024 threads so that every
-// pairwise join on level j is the same multiplication by x^(8 * 32 KiB * per * 2^j); thread 0 appends the partial last tile.
-__global__ void __launch_bounds__(1024) k_t3v_finish(const uint32_t* __restrict__ tabs, const uint32_t* __restrict__ tile_crc, uint32_t tiles_per_frame, uint64_t n_bytes,
-                                                   uint32_t n_words, uint8_t* __restrict__ rec, uint64_t pitch, int check, uint8_t* __restrict__ ok,
-                                                   uint32_t* __restrict__ crc_out)
+// Thread i < 128 walks `per` consecutive full tiles (Horner with the 32 KiB shift table: four look-ups a tile), the tiles right-aligned over the
+// 128 threads so that every pairwise join on level j is the same multiplication by x^(8 * 32 KiB * per * 2^j); thread 0 appends the partial last
+// tile.  The multipliers come from the other warps meanwhile.  (Bit-serial multiplications cost ~200 dependent instructions each: few threads
+// walking far and seven join levels beat 1024 threads and ten levels, 20 -> ~8 us.)
+constexpr int FIN_T = 128, FIN_LV = 7, FIN_TPB = FIN_T + 32 * (FIN_LV + 1);
+__global__ void __launch_bounds__(FIN_TPB) k_t3v_finish(const uint32_t* __restrict__ tabs, const uint32_t* __restrict__ tile_crc, uint32_t tiles_per_frame, uint64_t n_bytes,
+                                                      uint32_t n_words, uint8_t* __restrict__ rec, uint64_t pitch, int check, uint8_t* __restrict__ ok,
+                                                      uint32_t* __restrict__ crc_out)
 {
-    __shared__ uint32_t red[1024];
-    __shared__ uint32_t mlev[11];
+    __shared__ uint32_t red[FIN_T];
+    __shared__ uint32_t mlev[FIN_LV + 1];
     const uint32_t tid = threadIdx.x, f = blockIdx.x;
     const uint64_t n_full = n_bytes / T3V_TILE, tail = n_bytes - n_full * T3V_TILE;     // full tiles, bytes of the partial last tile
-    const uint64_t per = n_full ? (n_full + 1023) / 1024 : 1, pad = 1024 * per - n_full; // empty places in front
+    const uint64_t per = n_full ? (n_full + FIN_T - 1) / FIN_T : 1, pad = FIN_T * per - n_full; // empty places in front
     const uint32_t* p = tile_crc + (uint64_t)f * tiles_per_frame;
-    uint32_t acc = 0;
-    for (uint64_t v = (uint64_t)tid * per; v < (uint64_t)(tid + 1) * per; ++v)
-        if (v >= pad) acc = crc_shift(tabs + CRC_SHIFT0 + 1024 * 8, acc) ^ p[v - pad];
-    red[tid] = acc;
-    // warp j < 10: mlev[j] = x^(8 * 32 KiB * per * 2^j) = product over the set bits b of per of x^(8 * 2^(15 + j + b)); warp 10: x^(8 * tail).
-    // One table entry per lane, multiplied up by shuffles.  per < 2^11 (n_bytes < 2^36): 15 + 9 + 10 < CRC_NPOW
-    const uint32_t wj = tid >> 5, lb = tid & 31u;
-    if (wj <= 10) {
-        const uint64_t bits = wj < 10 ? per : tail;
+    __shared__ uint32_t sh32k[4 * 256];
+    for (uint32_t i = tid; i < 4 * 256; i += FIN_TPB) sh32k[i] = __ldg(tabs + CRC_SHIFT0 + 1024 * 8 + i);
+    __syncthreads();
+    if (tid < FIN_T) {
+        uint32_t acc = 0;
+        const uint64_t v0 = (uint64_t)tid * per;
+#pragma unroll 8
+        for (uint64_t i = 0; i < per; ++i) {     // the loads do not depend on acc: issued ahead; an empty place adds 0 to a still-zero acc
+            const uint32_t val = v0 + i >= pad ? __ldg(p + (v0 + i - pad)) : 0u;
+            acc = (sh32k[acc & 0xFFu] ^ sh32k[256 + ((acc >> 8) & 0xFFu)] ^ sh32k[512 + ((acc >> 16) & 0xFFu)] ^ sh32k[768 + (acc >> 24)]) ^ val;
+        }
+        red[tid] = acc;
+    } else {
+        // warp j < 7: mlev[j] = x^(8 * 32 KiB * per * 2^j) = product over the set bits b of per of x^(8 * 2^(15 + j + b)); warp 7: x^(8 * tail).
+        // One table entry per lane, multiplied up by shuffles.  per < 2^14 (n_bytes < 2^36): 15 + 6 + 13 < CRC_NPOW
+        const uint32_t wj = (tid - FIN_T) >> 5, lb = tid & 31u;
+        const uint64_t bits = wj < FIN_LV ? per : tail;
         uint32_t m = 1u << 31;                                              // x^0
-        if (lb < 16 && ((bits >> lb) & 1)) m = __ldg(tabs + CRC_POW0 + (wj < 10 ? 15 + wj : 0) + lb);
+        if (lb < 16 && ((bits >> lb) & 1)) m = __ldg(tabs + CRC_POW0 + (wj < FIN_LV ? 15 + wj : 0) + lb);
         for (int sh = 8; sh; sh >>= 1) m = crc_mul_bf(m, __shfl_xor_sync(0xFFFFFFFFu, m, sh));
         if (lb == 0) mlev[wj] = m;
     }
     __syncthreads();
-    for (int j = 0; j < 10; ++j) {
+    for (int j = 0; j < FIN_LV; ++j) {
         const uint32_t st = 1u << j;
-        if ((tid & (2 * st - 1)) == 0) red[tid] = crc_mul_bf(mlev[j], red[tid]) ^ red[tid + st];
+        if (tid < FIN_T && (tid & (2 * st - 1)) == 0) red[tid] = crc_mul_bf(mlev[j], red[tid]) ^ red[tid + st];
         __syncthreads();
     }
-    if (tid == 0 && tail) red[0] = crc_mul_bf(mlev[10], red[0]) ^ p[n_full];
+    if (tid == 0 && tail) red[0] = crc_mul_bf(mlev[FIN_LV], red[0]) ^ p[n_full];
     if (tid == 0 && crc_out) crc_out[f] = red[0];                         // plain crc32 of the payload
     if (tid == 0 && rec) {
         uint32_t cn = 0xFFFFFFFFu;                                        // crc32 of the four bytes of n
@@ -591,7 +602,7 @@ int launch_t3v_records(const uint32_t* tabs, const uint8_t* words9, size_t n_wor
     const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
     int n = 0;
     n += t3v_tiles(words9, 9ull * stride_words, 0, records, record_pitch, 4, nb, tiles, n_frames, 1, tabs, partial, st);
-    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, (uint32_t)tpf, nb, (uint32_t)n_words, records, record_pitch, 0, nullptr, nullptr);
+    k_t3v_finish<<<(unsigned)n_frames, FIN_TPB, 0, st>>>(tabs, partial, (uint32_t)tpf, nb, (uint32_t)n_words, records, record_pitch, 0, nullptr, nullptr);
     return n + 1;
 }
 // records -> words9 (may be null: check only) and ok[f] = the record announces n_words and its CRC matches (t3v_read_frame)
@@ -602,7 +613,7 @@ int launch_t3v_read(const uint32_t* tabs, const uint8_t* records, size_t record_
     const uint64_t nb = 9ull * n_words, tiles = (nb + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
     int n = 0;
     n += t3v_tiles(records, record_pitch, 4, words9, 9ull * stride_words, 0, nb, tiles, n_frames, 0, tabs, partial, st);
-    k_t3v_finish<<<(unsigned)n_frames, 1024, 0, st>>>(tabs, partial, (uint32_t)tpf, nb, (uint32_t)n_words, const_cast<uint8_t*>(records), record_pitch, 1, ok, nullptr);
+    k_t3v_finish<<<(unsigned)n_frames, FIN_TPB, 0, st>>>(tabs, partial, (uint32_t)tpf, nb, (uint32_t)n_words, const_cast<uint8_t*>(records), record_pitch, 1, ok, nullptr);
     return n + 1;
 }
 // plain CRC-32 of n bytes (4-byte aligned) with the same two kernels
@@ -611,7 +622,7 @@ int launch_crc32(const uint32_t* tabs, const uint8_t* data, size_t n, uint32_t* 
     const uint64_t tiles = ((uint64_t)n + T3V_TILE - 1) / T3V_TILE, tpf = tiles ? tiles : 1;
     int k = 0;
     k += t3v_tiles(data, 0, 0, nullptr, 0, 0, n, tiles, 1, 0, tabs, partial, st);
-    k_t3v_finish<<<1, 1024, 0, st>>>(tabs, partial, (uint32_t)tpf, n, 0, nullptr, 0, 0, nullptr, out);
+    k_t3v_finish<<<1, FIN_TPB, 0, st>>>(tabs, partial, (uint32_t)tpf, n, 0, nullptr, 0, 0, nullptr, out);
     return k + 1;
 }
 
