@@ -11,7 +11,7 @@
  * this restatement is pinned differentially against the reference itself,
  * compiled from /root/reference into oracle/_ref/ (see oracle/Makefile), by
  * tests/test_oracle_vs_reference.py, and against fixtures generated from that
- * reference build (tests/golden/, generator tests/golden/make_golden.py).
+ * reference build (tests/golden/, generators tests/golden/make_golden.py, make_golden_formats.py).
  *
  * Two arithmetic modes:
  *   fixed=0  REF-EXACT: the reference as shipped, bugs included.

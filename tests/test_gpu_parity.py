@@ -782,3 +782,52 @@ def test_v6new_image_pipelines(codec, oracle):
                 ok2, i2 = oracle.v6new_words_to_image(w_o, sub, w, h)
                 assert ok1 and ok2 and np.array_equal(i1, i2), (sub, cen, w, h)
     assert codec.v6new_words_to_image(np.zeros(4, np.uint32), 7, 2, 2)[0] is False
+
+
+# ------------------------------------------------------------------ golden vectors generated from the reference itself
+GF = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_formats_v1.npz"))   # tests/golden/make_golden_formats.py
+
+
+def test_golden_formats_t3v(codec):
+    for nw in sorted(int(k[3:-6]) for k in GF.files if k.startswith("t3v") and k.endswith("_words")):
+        words, rec = GF[f"t3v{nw}_words"], GF[f"t3v{nw}_record"]
+        assert np.array_equal(codec.t3v_write_frame(words), rec), nw
+        ok, back = codec.t3v_read_frame(rec)
+        assert ok and np.array_equal(back, words % 27)
+        if rec.size > 8:
+            assert codec.crc32(rec[4:-4]) == __import__("zlib").crc32(rec[4:-4].tobytes())
+    for i, (prof, code, cen, coset, fc, ft) in enumerate(((1, 0, 1, 0, 240, 0), (4, 2, 1, 1, 1, 1), (5, 4, 0, 2, 7, 0))):
+        assert np.array_equal(codec.t3v_header(prof, code, cen, coset, 7680, 4320, (3, 1, 4, 1), 30000, 1001, fc, ft), GF[f"t3vhdr{i}"]), i
+
+
+def test_golden_formats_subword_and_base243(codec):
+    words = GF["sub_words"]
+    for N in (27, 24, 21, 18, 15):
+        t = codec.extract_subword_stream_from_words(words, N)
+        assert np.array_equal(t, GF[f"sub{N}_stream"])
+        assert np.array_equal(codec.ut_to_base243(t), GF[f"sub{N}_pack"])
+        assert np.array_equal(codec.words_to_base243(words, N), GF[f"sub{N}_pack"])
+        assert np.array_equal(codec.build_words_from_subword_stream(t[:5 * N + 3], N, 2), GF[f"sub{N}_rebuilt_fill2"])
+    wild = GF["wild_trits"]
+    assert np.array_equal(codec.ut_to_base243(wild), GF["wild_pack"])
+    assert np.array_equal(codec.build_words_from_subword_stream(wild, 21, 1), GF["wild_rebuilt21"])
+    ok, u = codec.base243_to_ut(GF["wild_pack"])
+    assert ok == bool(GF["wild_unpack_ok"][0]) and np.array_equal(u, GF["wild_unpack"])
+
+
+def test_golden_formats_new_generation(codec, t3):
+    px = GF["new_px"].reshape(-1).view(t3.PIXEL_DTYPE)
+    for sub in (0, 15, 21):
+        ok, w = codec.v6new_encode_raw_pixels_to_words(px, sub)
+        assert ok == bool(GF[f"new_pack{sub}_ok"][0]) and np.array_equal(w, GF[f"new_pack{sub}"])
+    img = GF["img"]
+    assert np.array_equal(codec.resize_rgb_nn(img, 960, 540), GF["img_resize_960x540"])
+    assert np.array_equal(codec.resize_rgb_nn(img, 17, 31), GF["img_resize_17x31"])
+    assert np.array_equal(codec.blit_center_rgb(img, 101, 77), GF["img_blit_101x77"])
+    q = GF["q_60x40"].reshape(-1).view(t3.PIXEL_DTYPE)
+    assert np.array_equal(codec.extract_center_q(q, 60, 40, 30, 20).view(np.uint8).reshape(-1, q.dtype.itemsize), GF["q_center_30x20"])
+    for sub, cen in ((15, True), (15, False), (18, True)):
+        ok, w = codec.v6new_image_to_words(img, sub, cen)
+        assert ok and np.array_equal(w, GF[f"img_words_{sub}_{int(cen)}"])
+        ok, back = codec.v6new_words_to_image(w, sub, 100, 50)
+        assert ok and np.array_equal(back, GF[f"img_back_{sub}_{int(cen)}_100x50"])
