@@ -276,12 +276,13 @@ int launch_v6new_unpack_pixels(const uint32_t* words, size_t n_words, t3c_pixel*
 // =============================================================================================
 // the .t3v container's frame records (old/include/t3v_io.hpp:128-160) and its CRC-32 (:14-40).
 //   record = n (uint32 LE) | 9n symbol bytes, each % 27 | crc32(payload) ^ (crc32(&n, 4) * 16777619)
-// k_t3v_tiles:  one CTA = one tile of 256 segments x 128 payload bytes: coalesced 32-bit loads -> [% 27] -> coalesced stores into the
-//               record, a padded copy in shared memory (segment stride 33 words: conflict-free), then thread = segment: slice-by-4 CRC-32
-//               of its 128 bytes -> one partial CRC per segment
-// k_t3v_finish: one CTA per frame joins the partials: crc(A | B) = x^(8|B|) * crc(A) + crc(B) over GF(2)[x] / P (the identity behind
-//               zlib's crc32_combine); a thread walks a contiguous group of segments with the constant multiplier x^1024 as four
-//               256-entry tables, the groups are joined with the generic multiply.  Writes n and the record's CRC (or checks them).
+// CRC-32 is parallelised through crc(A | B) = x^(8|B|) * crc(A) + crc(B) over GF(2)[x] / P (the identity behind zlib's crc32_combine) and
+// through its linearity over GF(2).
+// k_t3v_tiles_strided: the payload in tiles of 32 KiB.  Full tiles: one warp per tile, lane-strided 16-byte accesses -> [% 27] -> record, the CRC
+//               kept per lane and joined by shuffles (see the kernel).  The partial last tile of a frame: one CTA of the same launch stages it in
+//               shared memory (t3v_tile_body: thread = 128-byte segment, slice-by-4).  One CRC per tile -> tile_crc[f * tiles + t]
+// k_t3v_finish: one CTA per frame joins the tile CRCs: Horner walks with the constant multiplier x^(8 * 32 KiB) as four 256-entry tables, then
+//               pairwise joins with per-level multipliers.  Writes n and the record's CRC (or checks them).
 // =============================================================================================
 namespace t3c {
 namespace {
@@ -339,7 +340,7 @@ __device__ inline uint32_t crc_shift_bytes(const uint32_t* __restrict__ tabs, ui
     return v;
 }
 // src / dst: frame f at + f * pitch; *_off = where the 9n payload bytes start inside a frame of src / dst (0 or 4), all 4-byte aligned.
-// out: one CRC per full tile at tile_crc[f * tiles + t]; the last, partial tile of a frame leaves one CRC per segment at seg_crc[f * 256 + s]
+// out: one CRC per tile (the partial last one included) at tile_crc[f * tiles + t]
 // Shared-memory layout of the tile body below (uint32 words): slice tables, padded tile, join scratch
 constexpr int T3V_SW = 8; // warps (tiles in flight) per CTA of the lane-strided kernel
 constexpr int T3V_BODY_WORDS = 4 * 256 + T3V_TPB * 33 + T3V_TPB;
