@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t
                                                                  int reduce, const uint32_t* __restrict__ tabs, uint32_t* __restrict__ tile_crc, uint64_t n_bytes,
                                                                  uint32_t body_ctas)
 {
-    static_assert(T3V_BODY_WORDS >= 20 * 256 && 32 * T3V_SW == T3V_TPB, "one shared buffer, one CTA shape for both roles");
+    static_assert(T3V_BODY_WORDS >= 32 * 256 && 32 * T3V_SW == T3V_TPB, "one shared buffer, one CTA shape for both roles");
     __shared__ __align__(16) uint32_t sm[T3V_BODY_WORDS];
     if (blockIdx.x < body_ctas) {   // the partial last tile of frame blockIdx.x (first in the grid: it is the longest serial piece)
         t3v_tile_body(sm, blockIdx.x, full_tiles, src, src_pitch, src_off, dst, dst_pitch, dst_off, n_bytes, tiles_per_frame, reduce, tabs, tile_crc);
@@ -424,7 +424,12 @@ __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t
     uint32_t* s512 = sm + 16 * 256;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, cta = blockIdx.x - body_ctas, n_cta = gridDim.x - body_ctas;
     for (uint32_t i = tid; i < 16 * 256; i += 32 * T3V_SW) sx[i] = __ldg(tabs + CRC_X0 + i);
-    for (uint32_t i = tid; i < 4 * 256; i += 32 * T3V_SW) s512[i] = __ldg(tabs + CRC_SHIFT0 + 1024 * 2 + i);   // 128 * 2^2 = 512 bytes
+    // the shift by 512 bytes (table 2: 128 * 2^2 bytes) by nibbles, every entry once per lane (word 32 * (16 n + v) + lane): the eight look-ups of a
+    // step, with state-dependent (random) indices, stay inside the lane's own bank
+    for (uint32_t i = tid; i < 8 * 16 * 32; i += 32 * T3V_SW) {
+        const uint32_t n = i >> 9, v = (i >> 5) & 15u;
+        s512[i] = __ldg(tabs + CRC_SHIFT0 + 1024 * 2 + 256 * (n >> 1) + (v << (4 * (n & 1))));
+    }
     __syncthreads();
     const uint32_t k0 = __ldg(tabs + CRC_K0);
     const uint64_t total = (uint64_t)full_tiles * n_frames;
@@ -467,7 +472,9 @@ __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t
                         for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(a)[i] = w[g][i];
                     }
                 }
-                uint32_t x = s512[c & 0xFFu] ^ s512[256 + ((c >> 8) & 0xFFu)] ^ s512[512 + ((c >> 16) & 0xFFu)] ^ s512[768 + (c >> 24)];
+                uint32_t x = 0;
+#pragma unroll
+                for (int n = 0; n < 8; ++n) x ^= s512[512 * n + 32 * ((c >> (4 * n)) & 15u) + lane];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     x ^= sx[256 * (4 * i) + (w[g][i] & 0xFFu)] ^ sx[256 * (4 * i + 1) + ((w[g][i] >> 8) & 0xFFu)] ^ sx[256 * (4 * i + 2) + ((w[g][i] >> 16) & 0xFFu)] ^
