@@ -407,7 +407,7 @@ __device__ __forceinline__ void t3v_tile_body(uint32_t* __restrict__ sm, uint32_
 // Full tiles, lane-strided: a warp takes one 32 KiB tile in 64 steps of 512 bytes, lane l the 16 bytes at 512 k + 16 l: perfectly coalesced
 // loads and stores, no shared-memory tile.  A lane keeps the CRC state of "its" bytes as if the other lanes' bytes were zero:
 //   c <- c * x^(8*512) + X(16 bytes)     (CRC is linear over GF(2): X = sum_j X_j[byte j], sixteen small look-ups; the symbols are < 27, so the 32 lanes
-//   of one look-up hit at most 27 consecutive words: no bank conflicts; the shift by 512 bytes is four look-ups)
+//   of one look-up hit at most 27 consecutive words: no bank conflicts; the shift by 512 bytes is eight nibble look-ups in a per-lane copy of the table)
 // and the 32 lane states are joined at the end of the tile: crc = sum_l c_l * x^(8*16*(31-l)), pairwise by shuffles.
 __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t src_off, uint8_t* __restrict__ dst,
                                                                  uint64_t dst_pitch, uint32_t dst_off, uint32_t full_tiles, uint32_t tiles_per_frame, uint32_t n_frames,
