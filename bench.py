@@ -289,54 +289,81 @@ def run_ours(args):
         # words cross PCIe inside the timed region in both calls.  The serial figure (one thread, encode then decode) is
         # reported next to it.
         codec2 = t3.Codec(local, arith=t3.FIXED)
-        h_enc2 = [h_enc, torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory(), torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory()]
         okb2 = np.zeros(1, np.uint8)
         rec2, nc2 = C.c_size_t(), C.c_size_t()
 
-        def enc_call(slot):
-            s1 = L.t3c_encode_frames_rgb8(codec.h, C.byref(cfg), t3.FIXED, h_rgb.data_ptr(), n_px, 1, h_enc2[slot].data_ptr(), wpf, C.byref(got))
-            assert s1 == 0
-
-        def dec_call(slot):
-            s2 = codec2.lib.t3c_decode_frames_rgb8(codec2.h, C.byref(cfg), h_enc2[slot].data_ptr(), wpf, wpf, 1, n_px, h_back.data_ptr(),
-                                                  okb2.ctypes.data_as(C.c_void_p), C.byref(rec2), C.byref(nc2))
-            assert s2 == 0 and okb2[0] == 1
-
         def e2e_step():
-            enc_call(0)
-            dec_call(0)
+            s1 = L.t3c_encode_frames_rgb8(codec.h, C.byref(cfg), t3.FIXED, h_rgb.data_ptr(), n_px, 1, h_enc.data_ptr(), wpf, C.byref(got))
+            s2 = codec2.lib.t3c_decode_frames_rgb8(codec2.h, C.byref(cfg), h_enc.data_ptr(), wpf, wpf, 1, n_px, h_back.data_ptr(),
+                                                  okb2.ctypes.data_as(C.c_void_p), C.byref(rec2), C.byref(nc2))
+            assert s1 == 0 and s2 == 0 and okb2[0] == 1
 
         import queue
 
-        def e2e_pipelined(n):  # n frames: the encoder thread runs ahead of the decoder thread through a 3-slot ring of word buffers
-            ready, free = queue.Queue(), queue.Queue()
-            for slot in range(len(h_enc2)):
-                free.put(slot)
-            err = []
+        class Lane:
+            """one encoder context + one decoder context on two host threads, a 3-slot ring of pinned word buffers between them"""
 
-            def producer():
+            def __init__(self, enc, dec, first_ring, back_buf):
+                self.enc, self.dec, self.back = enc, dec, back_buf
+                self.ring = [first_ring] + [torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory() for _ in range(2)]
+                self.ok = np.zeros(1, np.uint8)
+                self.got, self.rec, self.nc = C.c_size_t(), C.c_size_t(), C.c_size_t()
+                self.err = []
+
+            def producer(self, n, ready, free):
                 try:
                     for _ in range(n):
                         slot = free.get()
-                        enc_call(slot)
+                        s1 = self.enc.lib.t3c_encode_frames_rgb8(self.enc.h, C.byref(cfg), t3.FIXED, h_rgb.data_ptr(), n_px, 1, self.ring[slot].data_ptr(), wpf,
+                                                                 C.byref(self.got))
+                        assert s1 == 0
                         ready.put(slot)
                 except Exception as e:  # pragma: no cover
-                    err.append(e)
+                    self.err.append(e)
                     ready.put(None)
 
-            th = threading.Thread(target=producer)
-            th.start()
-            for _ in range(n):
-                slot = ready.get()
-                if slot is None:
-                    break
-                dec_call(slot)
-                free.put(slot)
-            th.join()
-            if err:
-                raise err[0]
+            def consumer(self, n, ready, free):
+                try:
+                    for _ in range(n):
+                        slot = ready.get()
+                        if slot is None:
+                            break
+                        s2 = self.dec.lib.t3c_decode_frames_rgb8(self.dec.h, C.byref(cfg), self.ring[slot].data_ptr(), wpf, wpf, 1, n_px, self.back.data_ptr(),
+                                                                 self.ok.ctypes.data_as(C.c_void_p), C.byref(self.rec), C.byref(self.nc))
+                        assert s2 == 0 and self.ok[0] == 1
+                        free.put(slot)
+                except Exception as e:  # pragma: no cover
+                    self.err.append(e)
+
+            def start(self, n):
+                ready, free = queue.Queue(), queue.Queue()
+                for slot in range(len(self.ring)):
+                    free.put(slot)
+                self.threads = [threading.Thread(target=self.producer, args=(n, ready, free)), threading.Thread(target=self.consumer, args=(n, ready, free))]
+                for th in self.threads:
+                    th.start()
+
+            def join(self):
+                for th in self.threads:
+                    th.join()
+                if self.err:
+                    raise self.err[0]
+
+        # Independent lanes keep both PCIe directions fed while one lane's call fills or drains its own chunk pipeline
+        n_lanes = max(1, min(4, int(os.environ.get("T3C_E2E_LANES", "2"))))
+        lanes = [Lane(codec, codec2, h_enc, h_back)]
+        for _ in range(1, n_lanes):
+            lanes.append(Lane(t3.Codec(local, arith=t3.FIXED), t3.Codec(local, arith=t3.FIXED), torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory(),
+                              torch.empty((1, n_px, 3), dtype=torch.uint8).pin_memory()))
+
+        def e2e_pipelined(n):  # n frames per lane: each lane's encoder thread runs ahead of its decoder thread
+            for ln in lanes:
+                ln.start(n)
+            for ln in lanes:
+                ln.join()
 
         e2e_steps = max(8, min(args.steps, 20))
+        e2e_steps -= e2e_steps % n_lanes
         e2e_step()
         e2e_pipelined(2)
         if world > 1:
@@ -348,18 +375,24 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        e2e_pipelined(e2e_steps)
+        e2e_pipelined(e2e_steps // n_lanes)
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        chk_host = chk.cpu()
+        for ln in lanes:
+            assert torch.equal(ln.back.view(-1), chk_host), "e2e round trip mismatch"
+        for ln in lanes[1:]:
+            ln.enc.close()
+            ln.dec.close()
         codec2.close()
-        assert torch.equal(h_back.view(-1), chk.cpu()), "e2e round trip mismatch"
         e2e = {"value": world * n_px * e2e_steps / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": 3 * n_px + 9 * wpf, "d2h_bytes_per_step": 9 * wpf + 3 * n_px,
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "serial_ms_per_step": 1e3 * dt_serial,
-               "how": "host-buffer C ABI, pinned memory; chunked H2D/kernel/D2H pipeline inside each call; encoder and decoder contexts on two host threads (frame i encodes while frame i-1 decodes)"}
+               "lanes": n_lanes,
+               "how": "host-buffer C ABI, pinned memory; chunked H2D/kernel/D2H pipeline inside each call; per lane an encoder and a decoder context on two host threads (frame i encodes while frame i-1 decodes); the lanes work on independent frames"}
 
     if rank == 0:
         # parity spot check against the oracle on a slice of the timed frame + CPU baseline (bounded sample)
