@@ -103,6 +103,19 @@ t3c_status chain(t3c_ctx* ctx, cudaStream_t from, cudaStream_t to)
 }
 static uint32_t kPipeChunks = 8;          // chunks per frame in the host-buffer pipelines (T3C_PIPE_CHUNKS overrides)
 constexpr uint32_t kPipeMinTiles = 512;   // below this a frame is copied and coded in one piece
+// Tiles before chunk c of a frame's host pipeline.  Chunk weights 1, 2, 4, then 5s: the encoder's first chunks are small (its device-to-host
+// leg, the long one, starts after a short fill), the decoder's last ones (a short drain after its host-to-device leg).  >= 1 tile per chunk
+// for n_full >= kPipeMinTiles and up to 64 chunks.
+static uint32_t pipe_edge(uint32_t n_full, uint32_t c, bool small_first)
+{
+    uint64_t tot = 0, before = 0;
+    for (uint32_t i = 0; i < kPipeChunks; ++i) {
+        const uint32_t j = small_first ? i : kPipeChunks - 1 - i, w = j < 3 ? (1u << j) : 5u;
+        tot += w;
+        if (i < c) before += w;
+    }
+    return (uint32_t)((uint64_t)n_full * before / tot);
+}
 
 void ref_dec_geom(const t3c_config& h, size_t n_words, RefDecGeom& g)
 {
@@ -750,7 +763,7 @@ t3c_status t3c_encode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, int arith
         uint8_t* df_out = d_out + 9 * dstride * f;
         for (uint32_t c = 0; c <= kPipeChunks; ++c) { // the last round is the ragged tail + header
             const bool tail = c == kPipeChunks;
-            const uint32_t t0 = tail ? n_full : (uint32_t)((uint64_t)n_full * c / kPipeChunks), t1 = tail ? n_full : (uint32_t)((uint64_t)n_full * (c + 1) / kPipeChunks);
+            const uint32_t t0 = tail ? n_full : pipe_edge(n_full, c, true), t1 = tail ? n_full : pipe_edge(n_full, c + 1, true);
             const size_t b0 = tile_bytes * t0, b1 = tail ? 3 * n_px : tile_bytes * t1;
             if (b1 > b0) CU(cudaMemcpyAsync(df_in + b0, h_in + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->s_h2d));
             TRY(chain(ctx, ctx->s_h2d, ctx->stream));
@@ -820,7 +833,7 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
             uint8_t* df_out = d_out + out_pitch * f;
             for (uint32_t c = 0; c <= kPipeChunks; ++c) {
                 const bool tail = c == kPipeChunks;
-                const uint32_t t0 = tail ? n_full : (uint32_t)((uint64_t)n_full * c / kPipeChunks), t1 = tail ? n_full : (uint32_t)((uint64_t)n_full * (c + 1) / kPipeChunks);
+                const uint32_t t0 = tail ? n_full : pipe_edge(n_full, c, false), t1 = tail ? n_full : pipe_edge(n_full, c + 1, false);
                 // band segments, widened by 16 bytes: the kernels load whole 16-byte chunks around every run
                 if (!tail && uniform_bands && 52 + 26 * (g.cw_base[8] + 13ull * t1) + 16 <= frame_bytes) { // equal, equally spaced: one strided copy
                     CU(cudaMemcpy2DAsync(df_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], h_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], 26 * 13ull * (t1 - t0) + 16, 9,
