@@ -124,7 +124,7 @@ void t3r_header_unpack(const uint8_t* sym27, t3o_cfg* o, uint32_t* frame_seq, ui
 size_t t3r_pack_pixels(const t3o_pixel* px, size_t n, uint8_t* words9)
 {
     std::vector<PixelYCbCrQuant> v(n);
-    if (n) std::memcpy(v.data(), px, 6 * n);
+    if (n) std::memcpy(static_cast<void*>(v.data()), px, 6 * n);
     std::vector<Word27> w; encode_raw_pixels_to_words(v, w);
     if (!w.empty()) std::memcpy(words9, w.data(), 9 * w.size());
     return w.size();
@@ -194,7 +194,7 @@ void t3r_rgb_to_quant(const uint8_t* rgb, size_t n, t3o_pixel* out) // loop body
 void t3r_quant_to_rgb(const t3o_pixel* px, size_t n, uint8_t* rgb) // loop body of quant_stream_to_rgb, io_image.hpp:171-192
 {
     for (size_t i = 0; i < n; ++i) {
-        PixelYCbCrQuant q; std::memcpy(&q, &px[i], 6);
+        PixelYCbCrQuant q; std::memcpy(static_cast<void*>(&q), &px[i], 6);
         uint8_t Y, Cb, Cr; dequantize_ycbcr(q, Y, Cb, Cr);
         ycbcr_to_rgb(Y, Cb, Cr, rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
     }

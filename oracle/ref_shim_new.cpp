@@ -25,7 +25,7 @@ int t3n_pack_pixels(const void* px6, size_t n_px, uint32_t* words, int subword)
 int t3n_unpack_pixels(const uint32_t* words, size_t n_words, void* px6, int subword)
 {
     std::vector<Word27> in(n_words);
-    if (n_words) std::memcpy(in.data(), words, 4 * n_words);
+    if (n_words) std::memcpy(static_cast<void*>(in.data()), words, 4 * n_words);
     std::vector<PixelYCbCrQuant> out;
     const bool ok = subword ? decode_raw_words_to_pixels_subword(in, (SubwordMode)subword, out) : decode_raw_words_to_pixels(in, out);
     if (ok && !out.empty()) std::memcpy(px6, out.data(), 6 * out.size());
@@ -93,7 +93,7 @@ long long t3n_image_to_words_subword(const uint8_t* rgb, int w, int h, int sub, 
 int t3n_words_to_image_subword(const uint32_t* words, size_t n, int sub, int w, int h, uint8_t* rgb)
 {
     std::vector<Word27> in(n);
-    if (n) std::memcpy(in.data(), words, 4 * n);
+    if (n) std::memcpy(static_cast<void*>(in.data()), words, 4 * n);
     g_saved.clear(); g_sw = g_sh = 0;
     const bool ok = words_to_image_subword(in, (SubwordMode)sub, w, h, "in-memory.png");
     if (ok && g_sw == w && g_sh == h && !g_saved.empty()) std::memcpy(rgb, g_saved.data(), g_saved.size());
