@@ -350,7 +350,8 @@ def run_ours(args):
                     raise self.err[0]
 
         # Independent lanes keep both PCIe directions fed while one lane's call fills or drains its own chunk pipeline
-        n_lanes = max(1, min(4, int(os.environ.get("T3C_E2E_LANES", "2"))))
+        # (beyond two GPUs the host side of the box is the limit and more threads do not help: one lane per rank there)
+        n_lanes = max(1, min(4, int(os.environ.get("T3C_E2E_LANES", "2" if world <= 2 else "1"))))
         lanes = [Lane(codec, codec2, h_enc, h_back)]
         for _ in range(1, n_lanes):
             lanes.append(Lane(t3.Codec(local, arith=t3.FIXED), t3.Codec(local, arith=t3.FIXED), torch.empty((1, wpf, 9), dtype=torch.uint8).pin_memory(),
