@@ -771,9 +771,10 @@ t3c_status t3c_encode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, int arith
             if (n < 0) return fail(ctx, T3C_ERR_CUDA, "encode_frames: unaligned staging");
             TRY(check_launch(ctx, n));
             TRY(chain(ctx, ctx->stream, ctx->s_d2h));
-            if (!tail && uniform_bands) { // nine equal segments, equally spaced: one strided copy
-                CU(cudaMemcpy2DAsync(h_out + 52 + 26 * 13ull * t0, 26 * g.ncw[0], df_out + 52 + 26 * 13ull * t0, 26 * g.ncw[0], 26 * 13ull * (t1 - t0), 9,
-                                     cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (uniform_bands) { // nine equal segments, equally spaced: one strided copy (a copy command costs ~10 us of the copy engine's time)
+                const uint64_t seg = tail ? 26 * (g.ncw[0] - 13ull * t0) : 26 * 13ull * (t1 - t0);
+                if (seg) CU(cudaMemcpy2DAsync(h_out + 52 + 26 * 13ull * t0, 26 * g.ncw[0], df_out + 52 + 26 * 13ull * t0, 26 * g.ncw[0], seg, 9, cudaMemcpyDeviceToHost,
+                                              ctx->s_d2h));
             } else
                 for (int b = 0; b < 9; ++b) {
                     const uint64_t c0 = g.cw_base[b] + 13ull * t0, c1 = tail ? g.cw_base[b] + g.ncw[b] : g.cw_base[b] + 13ull * t1;
@@ -835,9 +836,10 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
                 const bool tail = c == kPipeChunks;
                 const uint32_t t0 = tail ? n_full : pipe_edge(n_full, c, false), t1 = tail ? n_full : pipe_edge(n_full, c + 1, false);
                 // band segments, widened by 16 bytes: the kernels load whole 16-byte chunks around every run
-                if (!tail && uniform_bands && 52 + 26 * (g.cw_base[8] + 13ull * t1) + 16 <= frame_bytes) { // equal, equally spaced: one strided copy
-                    CU(cudaMemcpy2DAsync(df_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], h_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], 26 * 13ull * (t1 - t0) + 16, 9,
-                                         cudaMemcpyHostToDevice, ctx->s_h2d));
+                const uint64_t seg = tail ? 26 * (g.ncw[0] - 13ull * t0) : 26 * 13ull * (t1 - t0);
+                if (uniform_bands && 52 + 26 * (g.cw_base[8] + 13ull * t0) + seg + 16 <= frame_bytes) { // equal, equally spaced: one strided copy
+                    if (seg) CU(cudaMemcpy2DAsync(df_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], h_in + 52 + 26 * 13ull * t0, 26 * g.ncw[0], seg + 16, 9, cudaMemcpyHostToDevice,
+                                                  ctx->s_h2d));
                 } else
                     for (int b = 0; b < 9; ++b) {
                         const uint64_t c0 = g.cw_base[b] + 13ull * t0, c1 = tail ? g.cw_base[b] + g.ncw[b] : g.cw_base[b] + 13ull * t1;
