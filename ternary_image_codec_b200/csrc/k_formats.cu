@@ -591,7 +591,7 @@ static int t3v_tiles(const uint8_t* src, uint64_t src_pitch, uint32_t src_off, u
     if (!tiles) return 0;
     const uint64_t full = nb / T3V_TILE, total = full * n_frames, body = tiles > full ? n_frames : 0;
     uint64_t grid = (total + T3V_SW - 1) / T3V_SW;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > 148 * 8) grid = 148 * 8;   // B200: 148 SMs, up to 8 CTAs each; the warps stride over the tiles beyond that
     k_t3v_tiles_strided<<<(unsigned)(grid + body), 32 * T3V_SW, 0, st>>>(src, src_pitch, src_off, dst, dst_pitch, dst_off, (uint32_t)full, (uint32_t)tiles, (uint32_t)n_frames,
                                                                        reduce, tabs, tile_crc, nb, (uint32_t)body);
     return 1;
