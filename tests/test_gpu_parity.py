@@ -831,3 +831,11 @@ def test_golden_formats_new_generation(codec, t3):
         assert ok and np.array_equal(w, GF[f"img_words_{sub}_{int(cen)}"])
         ok, back = codec.v6new_words_to_image(w, sub, 100, 50)
         assert ok and np.array_equal(back, GF[f"img_back_{sub}_{int(cen)}_100x50"])
+
+
+def test_crc32_more_tiles_than_resident_warps(codec):
+    """more 32 KiB tiles than the tile kernel's capped grid holds warps: the warps stride over the tiles"""
+    import zlib
+    n = 9500 * 32768 + 12345
+    data = rng(961).integers(0, 256, n, dtype=np.uint8)
+    assert codec.crc32(data) == zlib.crc32(data.tobytes())
