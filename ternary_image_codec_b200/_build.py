@@ -16,7 +16,7 @@ OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libt3c.so")
 CU = ["k_general.cu", "k_fast.cu", "k_formats.cu", "api.cu"]
 CPP = ["tables.cpp"]
-HDRS = ["dev.cuh", "k_super.cuh", "launch.h", "t3c_internal.h", os.path.join("..", "..", "include", "t3c.h")]
+HDRS = ["dev.cuh", "k_super.cuh", "k_fast5.cuh", "launch.h", "t3c_internal.h", os.path.join("..", "..", "include", "t3c.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"] + os.environ.get("T3C_NVCC_EXTRA", "").split()

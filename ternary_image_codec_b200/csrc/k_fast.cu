@@ -829,11 +829,12 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
     constexpr int PLANE = 4 * 26 * 32;
     // the codeword's 26 symbols as 7 words (it starts on an even byte), then one PRMT per symbol builds the
     // table address: byte 0 = symbol x4, bytes 1..3 = the variant block's address
-    const uint32_t* mw = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-    const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(src) & 2u) * 8u;
+    const uint32_t sa = smem_u32(src), sh = (sa & 2u) * 8u;      // explicit shared-window loads (an integer round trip of the pointer made these generic LD.E)
     uint32_t xw[7];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) xw[j] = mw[j];
+    static_for<0, 7>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(xw[j]) : "r"(sa & ~3u), "n"(4 * j) : "memory");
+    });
 #pragma unroll
     for (int j = 0; j < 6; ++j) xw[j] = __funnelshift_r(xw[j], xw[j + 1], sh);
     xw[6] >>= sh;
@@ -1500,6 +1501,8 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::DEC_WARPS, 1) k_decode_rg
     if (lane == 0) bulk_wait_all();
 }
 
+#include "k_fast5.cuh"
+
 // occupancy (and the opt-in to > 48 KB of dynamic shared memory) per kernel AND per device: a process may drive several GPUs
 static int persistent_ctas_per_sm(const void* kern, int tpb, int smem_bytes)
 {
@@ -1530,26 +1533,52 @@ int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastP
     kern<<<(unsigned)grid, 32 * warps, smem_bytes, st>>>(P, g, T.gf, T.rs);
     return 1;
 }
-// T3C_FAST=3 keeps the v3 kernels (plain loads/stores, 4 CTAs per SM) for A/B comparison; default is v4 (bulk-async I/O)
-static bool use_v4()
+// T3C_FAST=3 / 4 keep the v3 kernels (plain loads/stores, 4 CTAs per SM) / the v4 kernels (bulk-async I/O) for A/B comparison;
+// default is v5 (k_fast5.cuh)
+static bool smem_window_ok();
+static int fast_version()
 {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("T3C_FAST"); v = (e && e[0] == '3') ? 0 : 1; }
-    return v == 1;
+    if (v < 0) { const char* e = getenv("T3C_FAST"); v = (e && e[0] == '3') ? 3 : (e && e[0] == '4') ? 4 : 5; }
+    return v == 5 && !smem_window_ok() ? 4 : v;
+}
+static bool use_v4() { return fast_version() >= 4; }
+// v5 addresses its phase-B tables absolutely (k_fast5.cuh, SMEM_WINDOW_BASE): check the assumption once per device
+static bool smem_window_ok()
+{
+    static std::mutex mu;
+    static std::map<int, bool> ok;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = ok.find(dev);
+    if (it != ok.end()) return it->second;
+    uint32_t* d = nullptr;
+    uint32_t h = 0;
+    bool r = false;
+    if (cudaMalloc(&d, 4) == cudaSuccess) {
+        k_smem_window_probe<<<1, 32, 64>>>(d);
+        r = cudaMemcpy(&h, d, 4, cudaMemcpyDeviceToHost) == cudaSuccess && h == SMEM_WINDOW_BASE;
+        cudaFree(d);
+    }
+    ok[dev] = r;
+    return r;
 }
 // tiles [t0, t1) of [0, n_full) of every frame go to the v3 kernels; with `tail` the ragged rest [n_full, n_all) goes to
 // the general-tile kernels
 template <int K>
 int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail, bool words = false)
 {
-    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
+    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0, occ5 = 0, occ5w = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 18) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
-            if (words) n += launch_persistent(k_encode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_ENC, T, P, g, st, occ4w, Cfg4<K, true>::ENC_WARPS);
+            if (fast_version() == 5 && words) n += launch_persistent(k_encode_v5<K, true>, Cfg5<K, true>::TOTAL_ENC, T, P, g, st, occ5w, Cfg5<K, true>::ENC_WARPS);
+            else if (fast_version() == 5) n += launch_persistent(k_encode_v5<K, false>, Cfg5<K, false>::TOTAL_ENC, T, P, g, st, occ5, Cfg5<K, false>::ENC_WARPS);
+            else if (words) n += launch_persistent(k_encode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_ENC, T, P, g, st, occ4w, Cfg4<K, true>::ENC_WARPS);
             else if (use_v4()) n += launch_persistent(k_encode_rgb_v4<K, false>, Cfg4<K>::TOTAL_ENC, T, P, g, st, occ4, Cfg4<K>::ENC_WARPS);
             else n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3);
         }
@@ -1560,14 +1589,16 @@ int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st,
 template <int K>
 int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail, bool words = false)
 {
-    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
+    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0, occ5 = 0, occ5w = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 18) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
-            if (words) n += launch_persistent(k_decode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_DEC, T, P, g, st, occ4w, Cfg4<K, true>::DEC_WARPS);
+            if (fast_version() == 5 && words) n += launch_persistent(k_decode_v5<K, true>, Cfg5<K, true>::TOTAL_DEC, T, P, g, st, occ5w, Cfg5<K, true>::DEC_WARPS);
+            else if (fast_version() == 5) n += launch_persistent(k_decode_v5<K, false>, Cfg5<K, false>::TOTAL_DEC, T, P, g, st, occ5, Cfg5<K, false>::DEC_WARPS);
+            else if (words) n += launch_persistent(k_decode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_DEC, T, P, g, st, occ4w, Cfg4<K, true>::DEC_WARPS);
             else if (use_v4()) n += launch_persistent(k_decode_rgb_v4<K, false>, Cfg4<K>::TOTAL_DEC, T, P, g, st, occ4, Cfg4<K>::DEC_WARPS);
             else n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3);
         }
@@ -1764,10 +1795,16 @@ int launch_encode_rgb_fast_part(const DevTables& T, const t3c_config& cfg, const
     int n = 0;
     const uint32_t n_full = fast_full_tiles_encode(g, n_px);
     switch (g.uniform_k) {
+#ifndef T3C_DEV_K20
     case 24: n = launch_enc<24>(T, P, g, st, n_full, t0, t1, tail); break;
+#endif
+#ifndef T3C_DEV_K20
     case 22: n = launch_enc<22>(T, P, g, st, n_full, t0, t1, tail); break;
+#endif
     case 20: n = launch_enc<20>(T, P, g, st, n_full, t0, t1, tail); break;
+#ifndef T3C_DEV_K20
     case 18: n = launch_enc<18>(T, P, g, st, n_full, t0, t1, tail); break;
+#endif
     default: return 0;
     }
     if (tail) n += launch_frame_finish(T, cfg, g, out, n_frames, 9ull * stride_words, st); // fast path: no beacon, only header + padding
@@ -1794,10 +1831,16 @@ int launch_decode_rgb_fast_part(const DevTables& T, const Geom& g, const uint8_t
     P.n_tiles = all_tiles(g);
     const uint32_t n_full = fast_full_tiles_decode(g, n_px_out, out_pitch, n_frames);
     switch (g.uniform_k) {
+#ifndef T3C_DEV_K20
     case 24: return launch_dec<24>(T, P, g, st, n_full, t0, t1, tail);
+#endif
+#ifndef T3C_DEV_K20
     case 22: return launch_dec<22>(T, P, g, st, n_full, t0, t1, tail);
+#endif
     case 20: return launch_dec<20>(T, P, g, st, n_full, t0, t1, tail);
+#ifndef T3C_DEV_K20
     case 18: return launch_dec<18>(T, P, g, st, n_full, t0, t1, tail);
+#endif
     }
     return 0;
 }
@@ -1825,10 +1868,16 @@ int launch_encode_words_fast(const DevTables& T, const Geom& g, const uint8_t* r
     P.n_tiles = all_tiles(g);
     int n = 0;
     switch (g.uniform_k) {
+#ifndef T3C_DEV_K20
     case 24: n = launch_enc<24>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#endif
+#ifndef T3C_DEV_K20
     case 22: n = launch_enc<22>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#endif
     case 20: n = launch_enc<20>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#ifndef T3C_DEV_K20
     case 18: n = launch_enc<18>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#endif
     default: return -1;
     }
     *n_full_out = n_full;
@@ -1849,10 +1898,16 @@ int launch_decode_words_fast(const DevTables& T, const Geom& g, const uint8_t* i
     P.n_tiles = all_tiles(g);
     int n = 0;
     switch (g.uniform_k) {
+#ifndef T3C_DEV_K20
     case 24: n = launch_dec<24>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#endif
+#ifndef T3C_DEV_K20
     case 22: n = launch_dec<22>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#endif
     case 20: n = launch_dec<20>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#ifndef T3C_DEV_K20
     case 18: n = launch_dec<18>(T, P, g, st, n_full, 0, n_full, false, true); break;
+#endif
     default: return -1;
     }
     *n_full_out = n_full;

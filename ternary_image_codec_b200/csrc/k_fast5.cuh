@@ -1,0 +1,543 @@
+// k_fast5.cuh -- v5 of the warp-tile kernels of k_fast.cu (uniform k, 1D 9-band interleave, no beacon: BASELINE configs 0, 1, 4).
+// Included by k_fast.cu inside its anonymous namespace; it reuses the digit / plane helpers defined there.
+//
+// Same work decomposition as v4 (a mini-tile of 13 codewords per band is owned by one warp from its bulk load to its bulk
+// stores), rebuilt around the per-phase instruction budget that the v4 SASS gave (round-2 notes in DESIGN.md section 4.1):
+// per mini-tile v4 issued ~2300 warp instructions -- 3 x 311 (phase A), 4 x 227 (phase B) and ~460 of per-tile bookkeeping.
+//   * bookkeeping: a warp walks its tile range with incremental state (global offsets, scrambler variant class, 16-byte phase of
+//     the nine runs live in registers and advance by constants); no divisions, no per-tile metadata in shared memory, the
+//     lane -> codeword assignment of phase B is a per-CTA table of ready-made (source, destination, band) records;
+//   * phase B: passes 0..2 hold codewords of ONE scrambler variant each, so their table block is a compile-time offset
+//     from the shared window: a look-up is LDS [symbol*4 + UR + imm] with no address arithmetic at all (3 LDS + 3 LOP3 per
+//     data symbol); only the mixed last pass adds a per-lane block offset;
+//   * phase A (RGB): the two chroma channels are computed in exact integer arithmetic straight from the packed pixel words --
+//     Cb = round(128 - 0.168736 R - 0.331264 G + 0.5 B) is floor((X + 15625) / 31250) + 128 with X = -5273 R - 10352 G + 15625 B
+//     (two 16x8-bit dot products, IDP.2A), and it agrees with the reference's float32 evaluation (IMG:47-56) for all 2^24 colours
+//     because no colour comes closer than 32e-6 to a rounding boundary other than exact ties, which float32 also hits exactly;
+//     the quantiser (IMG:69-78) follows as one mask-or and one multiply-high.  Luma keeps the float32 path: 824 of its 16782
+//     exact ties round down in float32.
+#pragma once
+
+// ---- exact integer chroma (checked against the float path over all 2^24 colours by tests/test_gpu_parity.py) ------------------------
+constexpr uint32_t C5_M = 2251799814u;                         // ceil(2^46 / 31250): hi32(X * M) >> 14 == X / 31250 for X < 2^32
+constexpr uint32_t C5_OFF = 128u * 31250u + 15625u + 31250u;   // +128, +0.5 (round half up), +1 (the quantiser below takes C + 1)
+constexpr uint32_t C5_Z = 6518u, C5_M2 = 82048u;               // hi32(((C+1) << 14 | Z) * M2) == (641 C + 896) >> 11 == (5C + 7 + (C >= 128)) >> 4
+constexpr int pk16(int lo, int hi) { return (int)(((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16)); }
+__device__ __forceinline__ int dp2a_lo(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(int a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// coefficient pairs of the dot products (kept in registers: IDP takes no constant-bank operand):
+// row c: {pk(c0,c1), pk(c2,0)};  rows: Cb, Cr (units of 1/31250), luma (units of 1/1000)
+__constant__ int c5_coef[6] = {pk16(-5273, -10352), pk16(15625, 0), pk16(15625, -13084), pk16(-2541, 0), pk16(299, 587), pk16(114, 0)};
+// X = c0*R + c1*G + c2*B + off for the pixel word px = {R, G, B, any}
+template <int ROW>
+__device__ __forceinline__ uint32_t dot_rgb(uint32_t px, int off)
+{
+    return (uint32_t)dp2a_hi(c5_coef[2 * ROW + 1], px, dp2a_lo(c5_coef[2 * ROW], px, off));
+}
+// quantised chroma + 40 (0..80) of the pixel word px: CB selects the Cb / Cr row of BT.601 (IMG:50-53)
+template <bool CB>
+__device__ __forceinline__ uint32_t chroma_q(uint32_t px)
+{
+    const uint32_t X = dot_rgb<CB ? 0 : 1>(px, (int)C5_OFF);
+    const uint32_t t = __umulhi(X, C5_M);
+    return __umulhi(lop3<0xEA>(t, 0xFFFFC000u, C5_Z), C5_M2);     // (t & mask) | Z
+}
+// luma in float32 exactly as rgb_to_value3 (IMG:47-49), quantised: Yq + QY_C0 (the caller subtracts the constant)
+__device__ __forceinline__ uint32_t luma_q(float R, float G, float B)
+{
+    constexpr float T23 = 8388608.0f;
+    const float y = __fadd_rn(__fadd_rn(__fmaf_rn(0.299f, R, -0.299f * T23), __fmaf_rn(0.587f, G, -0.587f * T23)), __fmaf_rn(0.114f, B, -0.114f * T23));
+    const uint32_t by = (uint32_t)__float_as_int(__fadd_rd(__fadd_rd(y, 0.5f), T23 + (float)QY_Z));
+    return __umulhi(by, QY_M);
+}
+// 13-trit value of the pixel word px = {R, G, B, any}, luma in float32 (exact for every colour).  Out of line: it runs for two
+// pixels in a thousand, and the hot loop should stay small (instruction cache)
+static __device__ __noinline__ uint32_t rgb_to_value5f(uint32_t px)
+{
+    return (luma_q(byte_magic(px, 0), byte_magic(px, 1), byte_magic(px, 2)) + (0u - QY_C0)) + 243u * chroma_q<true>(px) + 19683u * chroma_q<false>(px);
+}
+// The same with integer luma: Y = floor((299 R + 587 G + 114 B + 500) / 1000) equals the reference's float32 round(0.299f*R + 0.587f*G +
+// 0.114f*B) (IMG:47-49) for every colour that is not an exact tie (the float32 error stays below 5e-5, the nearest non-tie is 1e-3 away);
+// of the 16782 ties, 824 round down in float32.  t = floor(X * 2^9 / 1000): its low nine bits vanish for ties (and for X = 1 mod 1000);
+// those pixels are flagged and recomputed by rgb_to_value5f.  Yq = (484 Y + 255) / 510 (IMG:71) as one multiply-high.
+constexpr uint32_t Y5_M = 2199023256u;                          // ceil(2^41 / 1000)
+constexpr uint32_t Y5_Z = 269u, Y5_M2 = 7961011u;               // hi32(((Y << 9) | Z) * M2) == (484 Y + 255) / 510, Y in [0, 255]
+__device__ __forceinline__ uint32_t rgb_to_value5(uint32_t px, uint32_t& t)
+{
+    t = __umulhi(dot_rgb<2>(px, 500), Y5_M);
+    const uint32_t yq = __umulhi(lop3<0xEA>(t, 0xFFFFFE00u, Y5_Z), Y5_M2);
+    return yq + 243u * chroma_q<true>(px) + 19683u * chroma_q<false>(px);
+}
+// 26 bytes held in q[0..6] (q[6]: two bytes) -> shared memory at dst, which is 2-byte aligned: six 32-bit stores and one 16-bit store
+// instead of thirteen 16-bit ones (a 16-bit store costs a full wavefront, and lanes 26 bytes apart collide on banks either way).
+// PAR = 0 / 1: dst is known to be 0 / 2 mod 4;  PAR = 2: decided per lane (funnel shifts by 0 or 16 bits)
+template <int PAR>
+__device__ __forceinline__ void store26(uint8_t* dst, const uint32_t (&q)[7])
+{
+    if constexpr (PAR == 0) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) d[j] = q[j];
+        *reinterpret_cast<uint16_t*>(dst + 24) = (uint16_t)q[6];
+    } else if constexpr (PAR == 1) {
+        *reinterpret_cast<uint16_t*>(dst) = (uint16_t)q[0];
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst + 2);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) d[j] = __funnelshift_r(q[j], q[j + 1], 16);
+    } else {
+        const uint32_t a = smem_u32(dst), odd = a & 2u, sh = odd << 3;
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst + odd);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) d[j] = __funnelshift_r(q[j], q[j + 1], sh);
+        *reinterpret_cast<uint16_t*>(dst + (odd ? 0 : 24)) = (uint16_t)(odd ? q[0] : q[6]);
+    }
+}
+// ---- encode phase A: six pixels (18 bytes at U + a) -> 26 stream symbols (x4) at dst
+template <int PAR>
+__device__ __forceinline__ void enc_unit_rgb5(const uint8_t* U, uint32_t a, uint8_t* dst)
+{
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(U + (a & ~3u));
+    const uint32_t sh = (a & 3u) * 8u;
+    uint32_t x[6];  // 18 bytes from any byte offset touch at most six words (the buffer has the slack)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) x[j] = mw[j];
+    uint32_t y[5]; // the 18 bytes, word aligned
+#pragma unroll
+    for (int j = 0; j < 5; ++j) y[j] = __funnelshift_r(x[j], x[j + 1], sh);
+    // one word per pixel (fourth byte: don't care), so that every dot product uses the same two coefficient pairs
+    const uint32_t px[6] = {y[0], __byte_perm(y[0], y[1], 0x6543), __byte_perm(y[1], y[2], 0x5432), __byte_perm(y[2], y[2], 0x0321), y[3], __byte_perm(y[3], y[4], 0x6543)};
+    uint32_t A[6], t[6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) A[p] = rgb_to_value5(px[p], t[p]);
+    if (!(t[0] & 511u) | !(t[1] & 511u) | !(t[2] & 511u) | !(t[3] & 511u) | !(t[4] & 511u) | !(t[5] & 511u)) { // rare: a luma tie among the six
+#pragma unroll
+        for (int p = 0; p < 6; ++p) if (!(t[p] & 511u)) A[p] = rgb_to_value5f(px[p]);
+    }
+    uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
+    triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
+    triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
+    w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
+    const uint32_t q[7] = {w0, w1, w2, s12 | (v0 << 8), __funnelshift_r(v0, v1, 24), __funnelshift_r(v1, v2, 24), (v2 >> 24) | (t12 << 8)};
+    store26<PAR>(dst, q);
+}
+// one pass of phase A: unit u of the mini-tile; PAR as in store26 (S is 4-byte aligned, a unit is 26 bytes: PAR = u mod 2)
+template <int K, bool WORDS, int PAR>
+__device__ __forceinline__ void enc_unit5(const uint8_t* IN, uint32_t pad, uint8_t* S, int u)
+{
+    if constexpr (WORDS) enc_unit_words(IN, pad + 27u * (uint32_t)u, S + 26 * u);
+    else enc_unit_rgb5<PAR>(IN, pad + 18u * (uint32_t)u, S + 26 * u);
+}
+template <int K, bool WORDS>
+__device__ __forceinline__ void enc_phase_a5(const uint8_t* IN, uint32_t pad, uint8_t* S, int lane)
+{
+    using L = Cfg3<K>;
+    // units dealt even / odd over the first two passes: 36- and 52-byte lane strides (9 and 13 words, conflict-free)
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_A; ++pass) {
+        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+        if (u < L::UNITS) enc_unit5<K, WORDS, 2>(IN, pad, S, u);
+    }
+}
+
+// ---- shared-memory plan -----------------------------------------------------------------------------------------------------------
+template <int K, bool WORDS = false> struct Cfg5 {
+    using L = Cfg3<K>;
+    static constexpr int PIX_BYTES = WORDS ? 9 * (L::PX / 2) : L::RGB_BYTES;          // pixel-side bytes of one mini-tile
+    static constexpr int IN_BYTES = (PIX_BYTES + 15 + 15) / 16 * 16 + (WORDS ? 16 : 0); // with alignment slack (the word front end reads 32 bytes per unit)
+    static constexpr int RUN_PITCH = 368;                                              // >= 15 + 338, multiple of 16
+    static constexpr int RUNS_BYTES = 9 * RUN_PITCH;
+    static constexpr int CARRY_BYTES = 9 * 16, BAR_BYTES = 16;
+    static constexpr int WARP_BYTES = IN_BYTES + L::S_BYTES + RUNS_BYTES + CARRY_BYTES + BAR_BYTES; // encode: IN | S | U;  decode: OUT | S | R
+    static constexpr int SMEM_MAX = 227 * 1024;
+    // lane records of phase B: [tile mod 3][pass][lane] -> {source offset | destination offset << 16, band | variant << 8}
+    static constexpr int REC_BYTES = 3 * 128 * 8;
+    // encode, CTA-shared: per variant {A[K][27] | B[K][27]} | pat[3][2] | records
+    static constexpr int ENC_PLANE = 4 * K * 27, ENC_VAR = 2 * ENC_PLANE, ENC_PAT = 3 * ENC_VAR, ENC_REC = (ENC_PAT + 24 + 15) / 16 * 16;
+    static constexpr int ENC_WARP = ENC_REC + REC_BYTES;
+    static constexpr int ENC_WARPS = (SMEM_MAX - ENC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - ENC_WARP) / WARP_BYTES : 32;
+    static constexpr int TOTAL_ENC = ENC_WARP + ENC_WARPS * WARP_BYTES;
+    // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | GF(27) tables | records
+    static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
+    static constexpr int DEC_REC = DEC_GF + ((int)sizeof(GfTables) + 15) / 16 * 16;
+    static constexpr int DEC_WARP = DEC_REC + REC_BYTES;
+    static constexpr int DEC_WARPS = (SMEM_MAX - 256 - DEC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - 256 - DEC_WARP) / WARP_BYTES : 32;
+    static constexpr int TOTAL_DEC = 256 + DEC_WARP + DEC_WARPS * WARP_BYTES;
+};
+constexpr uint32_t REC_IDLE = 0xFFFFFFFFu;
+// records from the variant-sorted pass maps (build_pass_map): after the maps are in `maps` (3 x 128 bytes) and a barrier
+template <int K, int PITCH>
+__device__ __forceinline__ void build_records(uint2* rec, const uint8_t* maps, const Geom& g, int t)
+{
+    if (t >= 3 * 128) return;
+    const int tm = t >> 7;
+    const uint32_t cw = maps[t];
+    if (cw == 255) { rec[t] = make_uint2(0u, REC_IDLE); return; }
+    const uint32_t cl = cw / 9u, b = cw - 9u * cl;
+    const uint32_t v = ((uint32_t)(g.cw_base[b] % 3) + (uint32_t)tm + cl) % 3u;
+    rec[t] = make_uint2((9u * K * cl + b) | ((PITCH * b + 26u * cl) << 16), b | (v << 8));
+}
+
+// position of a warp inside its contiguous tile range: everything phase A / B / C need, advanced by constants
+struct TileCursor {
+    uint32_t f, tile, tm;      // frame, mini-tile inside the frame, tile mod 3
+    uint64_t pix;              // global byte offset of the tile's pixel-side bytes
+    uint64_t run;              // lanes 0..8: global byte offset of the band's run in the profile words
+};
+template <int PIX>
+__device__ __forceinline__ void cursor_seek(TileCursor& c, const FastParams& P, const Geom& g, uint64_t pix_stride, uint64_t run_stride, uint32_t mt, int lane)
+{
+    c.f = mt / P.n_tiles;
+    c.tile = P.tile0 + (mt - c.f * P.n_tiles);
+    c.tm = c.tile % 3u;
+    c.pix = pix_stride * c.f + (uint64_t)PIX * c.tile;
+    c.run = run_stride * c.f + 52 + 26 * (g.cw_base[lane < 9 ? lane : 0] + (uint64_t)C_MINI * c.tile);
+}
+template <int PIX>
+__device__ __forceinline__ void cursor_next(TileCursor& c, const FastParams& P, const Geom& g, uint64_t pix_stride, uint64_t run_stride, int lane)
+{
+    if (c.tile + 1 == P.tile0 + P.n_tiles) {   // next frame (rare)
+        c.f += 1;
+        c.tile = P.tile0;
+        c.tm = c.tile % 3u;
+        c.pix = pix_stride * c.f + (uint64_t)PIX * c.tile;
+        c.run = run_stride * c.f + 52 + 26 * (g.cw_base[lane < 9 ? lane : 0] + (uint64_t)C_MINI * c.tile);
+    } else {
+        c.tile += 1;
+        c.tm = c.tm == 2 ? 0 : c.tm + 1;
+        c.pix += PIX;
+        c.run += 26 * C_MINI;
+    }
+}
+
+// .shared address of the first byte of dynamic shared memory for a kernel without static shared memory that is not launched in a
+// cluster (sm_100a reserves the first KiB of the window).  The phase-B table look-ups below use ABSOLUTE addresses -- symbol*4 in
+// the register, table block + position as the immediate -- because inside the (to the compiler possibly divergent) tile loop the
+// window base would otherwise live in a vector register and cost one add per look-up.  smem_window_probe() checks the value on
+// the device before the first v5 launch; the v4 kernels are used if it ever differs.
+constexpr uint32_t SMEM_WINDOW_BASE = 0x400u;
+template <uint32_t ABS>
+__device__ __forceinline__ uint32_t lds_abs(uint32_t r)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(r), "n"(ABS));   // read-only tables: not volatile, the compiler may schedule these freely
+    return v;
+}
+__global__ void k_smem_window_probe(uint32_t* out)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    if (threadIdx.x == 0) *out = smem_u32(smem);
+}
+
+// ---- one codeword of encode phase B (see enc_cw).  VAR >= 0: the codeword's scrambler variant is the compile-time VAR (variant-uniform
+// pass, vb unused); VAR < 0: vb = variant * ENC_VAR, per lane.  TAB0 = offset of the variant-0 table block {A[K][27] | B[K][27]} from
+// the start of dynamic shared memory
+template <int K, int VAR, uint32_t TAB0, uint32_t ENC_VAR>
+__device__ __forceinline__ void enc_cw5(const uint8_t* src, uint8_t* dst, uint32_t vb, uint32_t pat_nz, uint32_t pat_two)
+{
+    constexpr int R = 26 - K;
+    constexpr uint32_t PLANE = 4 * K * 27, BASE = SMEM_WINDOW_BASE + TAB0 + (VAR >= 0 ? VAR * ENC_VAR : 0u);
+    Planes acc{0, 0}, acc2{0, 0};
+    uint32_t e[K];
+    static_for<0, K>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const uint32_t d4 = src[9 * i];
+        const uint32_t ra = VAR >= 0 ? d4 : d4 + vb;
+        // plane B is the same in every variant: the mixed pass reads it from block 0, where all its lanes meet in one 27-word row
+        const uint32_t ea = lds_abs<BASE + 108 * i>(ra), eb = lds_abs<(VAR >= 0 ? BASE : SMEM_WINDOW_BASE + TAB0) + 108 * i + PLANE>(d4);
+        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        e[i] = ea;
+    });
+    gf3_add(acc, acc2.nz, acc2.two);
+    gf3_add(acc, pat_nz, pat_two);
+    uint32_t lo, hi;
+    planes_to_parity<K>(acc.nz, acc.two, lo, hi);
+    // the codeword's 26 bytes as words: data symbols are the low bytes of the A entries
+    uint32_t q[7];
+#pragma unroll
+    for (int j = 0; j < K / 4; ++j) q[j] = __byte_perm(__byte_perm(e[4 * j], e[4 * j + 1], 0x0040), __byte_perm(e[4 * j + 2], e[4 * j + 3], 0x0040), 0x5410);
+    if constexpr (K % 4 == 0) {          // K = 20 / 24: parity starts on a word
+        q[K / 4] = lo;
+        if (K / 4 + 1 < 7) q[K / 4 + 1] = hi;
+    } else {                              // K = 18 / 22: two data symbols, then parity
+        const uint32_t t = __byte_perm(e[K - 2], e[K - 1], 0x0040);
+        q[K / 4] = __byte_perm(t, lo, 0x5410);
+        q[K / 4 + 1] = __byte_perm(lo, hi, 0x5432);
+        if (K / 4 + 2 < 7) q[K / 4 + 2] = hi >> 16;
+    }
+    store26<2>(dst, q);
+}
+
+template <int K, bool WORDS>
+__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+{
+    using L = Cfg3<K>;
+    using L5 = Cfg5<K, WORDS>;
+    constexpr int PIX = L5::PIX_BYTES, NW = L5::ENC_WARPS, TPB = 32 * NW, PITCH = L5::RUN_PITCH;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* IN = smem + L5::ENC_WARP + warp * L5::WARP_BYTES;  // the pixel side of the tile (bulk-loaded one tile ahead)
+    uint8_t* S = IN + L5::IN_BYTES;                             // stream symbols, pre-scaled by 4
+    uint8_t* U = S + L::S_BYTES;                                // the nine body runs
+    uint4* carry = reinterpret_cast<uint4*>(U + L5::RUNS_BYTES);
+    const uint32_t bar = smem_u32(U + L5::RUNS_BYTES + L5::CARRY_BYTES);
+    uint2* rec = reinterpret_cast<uint2*>(smem + L5::ENC_REC);
+    {
+        const uint32_t(*pl)[kVals][2] = rs->pl[g.arith][(24 - K) / 2];
+        for (int idx = tid; idx < 3 * K * 27; idx += TPB) {
+            const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
+            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::ENC_VAR);
+            blk[rem] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
+            blk[K * 27 + rem] = pl[i][d][1];
+        }
+        if (tid < 3) { // the scrambler as seen by the parity symbols of a variant-tid codeword, in the plane domain
+            uint32_t nz = 0, two = 0;
+            for (int j = 0; j < L::R; ++j) {
+                const uint32_t st = st_of(g, tid, K + j);
+                if (st) nz |= 7u << plane_shift<K>(j);
+                if (st == 2) two |= 7u << plane_shift<K>(j);
+            }
+            reinterpret_cast<uint32_t*>(smem + L5::ENC_PAT)[2 * tid] = nz;
+            reinterpret_cast<uint32_t*>(smem + L5::ENC_PAT)[2 * tid + 1] = two;
+        }
+        uint8_t* maps = smem + L5::ENC_WARP;                     // scratch: the first warp's IN buffer is not in use yet
+        for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
+        if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        for (int t = tid; t < 3 * 128; t += TPB) build_records<K, PITCH>(rec, maps, g, t);
+    }
+    __syncthreads(); // tables, records and barriers ready; no block-level barrier after this one
+    const uint32_t* patp = reinterpret_cast<const uint32_t*>(smem + L5::ENC_PAT);
+    const uint32_t pat0n = patp[0], pat0t = patp[1], pat1n = patp[2], pat1t = patp[3], pat2n = patp[4], pat2t = patp[5];
+    const uint64_t in_limit = P.in_stride * P.n_frames;
+    uint32_t mt_lo, mt_hi;
+    warp_range_smsp((uint64_t)P.n_tiles * P.n_frames, blockIdx.x, gridDim.x, warp, NW, mt_lo, mt_hi);
+    if (mt_lo >= mt_hi) return;
+    // bulk load of a tile's pixel side: the 16-byte aligned superset of [pix, pix + PIX), clipped to the buffer
+    auto fetch = [&](uint64_t pix) {
+        const uint64_t a0 = pix & ~15ull;
+        uint32_t bytes = (uint32_t)((pix - a0) + PIX + 15) & ~15u;
+        if (a0 + bytes > in_limit) bytes = (uint32_t)(in_limit - a0) & ~15u;
+        fence_async_smem();
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(IN), P.in + a0, bytes, bar);
+    };
+    TileCursor c;
+    cursor_seek<PIX>(c, P, g, P.in_stride, P.out_stride, mt_lo, lane);
+    if (lane == 0) fetch(c.pix);
+    uint32_t phase = 0;
+    bool first = true;
+    for (uint32_t left = mt_hi - mt_lo; left; --left) {
+        const bool last = left == 1 || c.tile + 1 == P.tile0 + P.n_tiles;           // of a contiguous stretch
+        const uint32_t pad = (uint32_t)c.pix & 15u, padb = (uint32_t)c.run & 15u;     // 16-byte phase of the pixel run / of lane b's band run
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        if (last) {   // the last bytes of the buffer that a clipped bulk copy left out (only the final tile of the final frame)
+            const uint64_t a0 = c.pix - pad;
+            const uint32_t want = pad + PIX;
+            if (a0 + ((want + 15) & ~15u) > in_limit)
+                for (uint32_t i = ((uint32_t)(in_limit - a0) & ~15u) + lane; i < want; i += 32) IN[i] = a0 + i < in_limit ? P.in[a0 + i] : 0;
+            __syncwarp();
+        }
+        enc_phase_a5<K, WORDS>(IN, pad, S, lane);
+        __syncwarp();
+        TileCursor nx = c;
+        cursor_next<PIX>(nx, P, g, P.in_stride, P.out_stride, lane);
+        if (left > 1 && lane == 0) fetch(nx.pix);                                  // IN is free again: next tile's pixels on their way
+        if (lane < 9) {
+            bulk_wait_read();                                                        // the previous tile's bulk stores have read U
+            if (!first) *reinterpret_cast<uint4*>(U + PITCH * lane) = carry[lane];   // bytes [0, padb) of each run: the previous tile's tail
+        }
+        __syncwarp();
+        // ---- phase B: one codeword per lane and pass; passes 0..2 are variant-uniform, pass 3 takes the leftovers of all three
+        {
+            const uint2* rt = rec + 128 * c.tm;
+            static_for<0, 3>([&](auto pc) {
+                constexpr int p = decltype(pc)::value;
+                const uint2 r = rt[32 * p + lane];
+                const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFFu));
+                enc_cw5<K, p, 0u, (uint32_t)L5::ENC_VAR>(S + (r.x & 0xFFFFu), U + (r.x >> 16) + pb, 0u, p == 0 ? pat0n : p == 1 ? pat1n : pat2n, p == 0 ? pat0t : p == 1 ? pat1t : pat2t);
+            });
+            const uint2 r = rt[96 + lane];
+            const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFu));
+            if (r.y != REC_IDLE) {
+                const uint32_t v = r.y >> 8;
+                enc_cw5<K, -1, 0u, (uint32_t)L5::ENC_VAR>(S + (r.x & 0xFFFFu), U + (r.x >> 16) + pb, v * L5::ENC_VAR, patp[2 * v], patp[2 * v + 1]);
+            }
+        }
+        __syncwarp();
+        if (c.tile == 0 && lane == 0 && g.cw_base[0] == 0) { // body symbols 0 and 1 may still see the scrambler's transient (A.4)
+            uint8_t* dst = U + padb;
+            dst[0] = gf->scr[g.st[0]][S[0] >> 2];
+            dst[1] = gf->scr[g.st[1]][S[9] >> 2];
+        }
+        fence_async_smem();                                                          // generic-proxy writes to U before the bulk engine reads it
+        __syncwarp();
+        // ---- phase C: nine band-major runs -> global as bulk stores of whole chunks; the partial last chunk is carried to the next tile
+        if (lane < 9) {
+            const uint32_t cend = (padb + L::RUN) >> 4, c0 = (first && padb) ? 1u : 0u;
+            if (!last) carry[lane] = *reinterpret_cast<const uint4*>(U + PITCH * lane + 16 * cend);
+            if (cend > c0) bulk_s2g(P.out + (c.run - padb) + 16 * c0, smem_u32(U + PITCH * lane + 16 * c0), 16 * (cend - c0));
+            bulk_commit();
+        }
+        if (first || last) { // edge bytes of a contiguous stretch, one by one
+#pragma unroll 1
+            for (int b = 0; b < 9; ++b) {
+                const uint64_t lo = __shfl_sync(0xFFFFFFFFu, c.run, b);
+                const int pb = (int)(lo & 15), end = pb + L::RUN, cend = end >> 4;
+                const uint8_t* s0 = U + PITCH * b;
+                uint8_t* g0 = P.out + (lo - pb);
+                if (first && pb && lane >= pb && lane < 16) g0[lane] = s0[lane];
+                if (last && lane < 16 && 16 * cend + lane < end) g0[16 * cend + lane] = s0[16 * cend + lane];
+            }
+        }
+        __syncwarp();
+        first = last;   // a stretch ends at a frame boundary: the next tile starts a new one
+        c = nx;
+    }
+    if (lane < 9) bulk_wait_all(); // shared memory must outlive the copies that read it
+}
+
+// =============================================================================================
+// decode
+// =============================================================================================
+template <int K, bool WORDS>
+__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+{
+    using L = Cfg3<K>;
+    using L5 = Cfg5<K, WORDS>;
+    constexpr int PIX = L5::PIX_BYTES, NW = L5::DEC_WARPS, TPB = 32 * NW, PITCH = L5::RUN_PITCH;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u); // 256-byte aligned: PRMT drops a symbol (x4) into the low address byte
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t* OUT = smem + L5::DEC_WARP + warp * L5::WARP_BYTES; // the pixel side of the tile on its way out
+    uint8_t* S = OUT + L5::IN_BYTES;                            // descrambled stream symbols (plain)
+    uint8_t* R = S + L::S_BYTES;                                // the nine body runs as they lie in the frame (bulk-loaded one tile ahead)
+    uint4* carry = reinterpret_cast<uint4*>(R + L5::RUNS_BYTES);
+    const uint32_t bar = smem_u32(R + L5::RUNS_BYTES + L5::CARRY_BYTES);
+    GfTables& sg = *reinterpret_cast<GfTables*>(smem + L5::DEC_GF);
+    uint2* rec = reinterpret_cast<uint2*>(smem + L5::DEC_REC);
+    {
+        const uint32_t(*pl)[kVals][2] = rs->pl[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
+        for (int idx = tid; idx < 3 * 26 * 32; idx += TPB) {
+            const int v = idx / (26 * 32), rem = idx - v * (26 * 32), i = rem / 32, x = rem - 32 * i, xm = x >= 27 ? x - 27 : x;
+            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::DEC_VAR);
+            blk[rem] = pl[i][xm][0] | gf->dsc[st_of(g, v, i)][xm];
+            blk[26 * 32 + rem] = pl[i][xm][1];
+        }
+        load_gf(sg, gf);
+        uint8_t* maps = smem + L5::DEC_WARP;                     // scratch: the first warp's OUT buffer is not in use yet
+        for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
+        if (lane == 0) { mbar_init(bar, 9); fence_mbar_init(); }
+        __syncthreads();
+        for (int t = tid; t < 3 * 128; t += TPB) build_records<K, PITCH>(rec, maps, g, t);
+        if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
+            Planes c{0, 0};
+            const uint32_t* blk = reinterpret_cast<const uint32_t*>(smem + tid * L5::DEC_VAR);
+            for (int i = 0; i < 26; ++i) {
+                const int idx = i * 32 + 13 * (int)st_of(g, tid, i);
+                gf3_add(c, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
+            }
+            reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid] = c.nz;
+            reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid + 1] = c.two;
+        }
+    }
+    __syncthreads();
+    const uint32_t tabA32 = smem_u32(smem);
+    const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L5::DEC_CHK);
+    const uint32_t chk0n = chk[0], chk0t = chk[1], chk1n = chk[2], chk1t = chk[3], chk2n = chk[4], chk2t = chk[5];
+    const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
+    uint32_t mt_lo, mt_hi;
+    warp_range_smsp((uint64_t)P.n_tiles * P.n_frames, blockIdx.x, gridDim.x, warp, NW, mt_lo, mt_hi);
+    if (mt_lo >= mt_hi) return;
+    // lane b < 9 bulk-loads band b's run: the 16-byte aligned superset of the run, clipped to the buffer
+    auto fetch = [&](uint64_t lo) {
+        const uint64_t a0 = lo & ~15ull;
+        uint32_t bytes = (uint32_t)((lo - a0) + L::RUN + 15) & ~15u;
+        if (a0 + bytes > in_limit) bytes = (uint32_t)(in_limit - a0) & ~15u;
+        fence_async_smem();
+        mbar_expect_tx(bar, bytes);
+        if (bytes) bulk_g2s(smem_u32(R + PITCH * lane), P.in + a0, bytes, bar);
+    };
+    TileCursor c;
+    cursor_seek<PIX>(c, P, g, P.out_stride, P.in_stride, mt_lo, lane);
+    if (lane < 9) fetch(c.run);
+    uint32_t phase = 0;
+    bool first = true;
+    for (uint32_t left = mt_hi - mt_lo; left; --left) {
+        const bool last = left == 1 || c.tile + 1 == P.tile0 + P.n_tiles;           // of a contiguous stretch
+        const uint32_t pad = (uint32_t)c.pix & 15u, padb = (uint32_t)c.run & 15u;
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        if (last) { // only the clipped end of the buffer (the last chunks of the last frame, which the bulk copy left out) is fetched here
+            if (lane < 9) {
+                const uint64_t a0 = c.run - padb, a1 = a0 + ((padb + L::RUN + 15u) & ~15u);
+                if (a1 > in_limit)
+                    for (uint64_t ga = (in_limit > a0 ? (in_limit - a0) & ~15ull : 0) + a0; ga < a1; ++ga) R[PITCH * lane + (ga - a0)] = ga < in_limit ? P.in[ga] : 0;
+            }
+            __syncwarp();
+        }
+        if (c.tile == 0) {
+            if (lane == 0 && g.cw_base[0] == 0) { // body symbols 0,1: move them from the transient states to the periodic ones
+                uint8_t* r0 = R + padb;
+                r0[0] = sg.scr[st_of(g, 0, 0)][sg.dsc[g.st[0]][r0[0] % 27u]];
+                r0[1] = sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][r0[1] % 27u]];
+            }
+            __syncwarp();
+        }
+        // ---- phase B: syndrome screen per codeword (passes 0..2 variant-uniform); descrambled data symbols -> stream order
+        {
+            uint32_t* status = P.status + 2 * c.f;
+            const uint2* rt = rec + 128 * c.tm;
+            static_for<0, 3>([&](auto pc) {
+                constexpr int p = decltype(pc)::value;
+                const uint2 r = rt[32 * p + lane];
+                const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFFu));
+                dec_cw<K, false>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, smem + p * L5::DEC_VAR, p == 0 ? chk0n : p == 1 ? chk1n : chk2n,
+                                 p == 0 ? chk0t : p == 1 ? chk1t : chk2t, sg, status);
+            });
+            const uint2 r = rt[96 + lane];
+            const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFu));
+            if (r.y != REC_IDLE) {
+                const uint32_t v = r.y >> 8;
+                dec_cw<K, false>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, smem + v * L5::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
+            }
+        }
+        __syncwarp();
+        TileCursor nx = c;
+        cursor_next<PIX>(nx, P, g, P.out_stride, P.in_stride, lane);
+        if (left > 1 && lane < 9) fetch(nx.run);                                    // R is free again: next tile's runs on their way
+        if (lane == 0) {
+            bulk_wait_read();                                                        // the previous tile's bulk store has read OUT
+            if (!first) *reinterpret_cast<uint4*>(OUT) = carry[0];                   // bytes [0, pad): the previous tile's tail
+        }
+        __syncwarp();
+        if constexpr (WORDS) dec_phase_a_words<K>(S, OUT, pad, lane); else dec_phase_a<K>(S, OUT, pad, lane);
+        fence_async_smem();
+        __syncwarp();
+        {   // the pixel side of the tile -> global: whole chunks by one bulk store, edge bytes of a stretch one by one
+            const uint32_t end = pad + PIX, cend = end >> 4, c0 = (first && pad) ? 1u : 0u;
+            uint8_t* g0 = P.out + (c.pix - pad);
+            if (lane == 0) {
+                if (!last) carry[0] = *reinterpret_cast<const uint4*>(OUT + 16 * cend);
+                bulk_s2g(g0 + 16 * c0, smem_u32(OUT + 16 * c0), 16 * (cend - c0));
+                bulk_commit();
+            }
+            if (first && pad && lane >= (int)pad && lane < 16) g0[lane] = OUT[lane];
+            if (last && lane < 16 && 16 * cend + lane < end) g0[16 * cend + lane] = OUT[16 * cend + lane];
+        }
+        __syncwarp();
+        first = last;
+        c = nx;
+    }
+    if (lane == 0) bulk_wait_all();
+}
