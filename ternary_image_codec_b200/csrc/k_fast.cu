@@ -42,6 +42,7 @@ struct FastParams {
     uint32_t n_frames;
     uint32_t* status;       // decode: {ok, n_corrected} per frame
     uint32_t chk_nz[7], chk_two[7]; // decode: sum of T_i[13*st_i] per scrambler phase (6) and for p0==0
+    uint32_t flags;         // v5: 1 | delay << 8 = staggered start of every other warp (k_fast5.cuh, T3C_V5_FLAGS)
 };
 
 template <int K> struct Cfg {
@@ -551,7 +552,13 @@ __device__ __forceinline__ uint32_t value_to_rgb3(uint32_t A)
     return Rb + 256u * Gb + 65536u * Bb;                                       // R | G<<8 | B<<16
 }
 // 8-entry byte table through PRMT: nibble n of sel (3 plane bits b0 b1 b2) -> b0 + 3 b1 + 9 b2
-__device__ __forceinline__ uint32_t planes4_to_sym(uint32_t sel) { return __byte_perm(0x04030100u, 0x0D0C0A09u, sel); }
+// (PRMT itself, not __byte_perm: the intrinsic masks bit 3 of every selector nibble first; plane nibbles hold three bits, bit 3 is never set)
+__device__ __forceinline__ uint32_t planes4_to_sym(uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0x04030100u), "r"(0x0D0C0A09u), "r"(sel));
+    return r;
+}
 // first plane bit of parity symbol j: nibbles while they fit (r <= 6), dense 3-bit groups for RS(26,18) (8 x 3 trits = bits 8..31)
 template <int K> __host__ __device__ constexpr int plane_shift(int j) { return 26 - K <= 6 ? 8 + 4 * j : 8 + 3 * j; }
 // eight 3-bit groups (24 bits) -> eight nibbles
@@ -1530,7 +1537,13 @@ int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastP
     const uint64_t need = (total + warps - 1) / warps;
     if (grid > need) grid = need;
     if (!grid) return 0;
-    kern<<<(unsigned)grid, 32 * warps, smem_bytes, st>>>(P, g, T.gf, T.rs);
+    FastParams Q = P;
+    {
+        static int fl = -1;
+        if (fl < 0) { const char* e = getenv("T3C_V5_FLAGS"); fl = e ? atoi(e) : (int)V5_FLAGS_DEFAULT; }
+        Q.flags = (uint32_t)fl;
+    }
+    kern<<<(unsigned)grid, 32 * warps, smem_bytes, st>>>(Q, g, T.gf, T.rs);
     return 1;
 }
 // T3C_FAST=3 / 4 keep the v3 kernels (plain loads/stores, 4 CTAs per SM) / the v4 kernels (bulk-async I/O) for A/B comparison;

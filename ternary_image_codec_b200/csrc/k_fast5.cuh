@@ -126,7 +126,10 @@ __device__ __forceinline__ void enc_unit_rgb5(const uint8_t* U, uint32_t a, uint
     uint32_t w0, w1, w2, s12, v0, v1, v2, t12;
     triple_to_symbols(A[0], A[1], A[2], w0, w1, w2, s12);
     triple_to_symbols(A[3], A[4], A[5], v0, v1, v2, t12);
-    w0 <<= 2; w1 <<= 2; w2 <<= 2; s12 <<= 2; v0 <<= 2; v1 <<= 2; v2 <<= 2; t12 <<= 2; // symbols <= 26: no carry between bytes
+    // x4 (table byte offsets; symbols <= 26: no carry between bytes) as funnel shifts: phase A is bound by the multiply pipe, which
+    // the compiler would otherwise also use for these shifts (IMAD.SHL)
+    w0 = __funnelshift_l(0u, w0, 2); w1 = __funnelshift_l(0u, w1, 2); w2 = __funnelshift_l(0u, w2, 2); s12 = __funnelshift_l(0u, s12, 2);
+    v0 = __funnelshift_l(0u, v0, 2); v1 = __funnelshift_l(0u, v1, 2); v2 = __funnelshift_l(0u, v2, 2); t12 = __funnelshift_l(0u, t12, 2);
     const uint32_t q[7] = {w0, w1, w2, s12 | (v0 << 8), __funnelshift_r(v0, v1, 24), __funnelshift_r(v1, v2, 24), (v2 >> 24) | (t12 << 8)};
     store26<PAR>(dst, q);
 }
@@ -187,6 +190,18 @@ __device__ __forceinline__ void build_records(uint2* rec, const uint8_t* maps, c
     rec[t] = make_uint2((9u * K * cl + b) | ((PITCH * b + 26u * cl) << 16), b | (v << 8));
 }
 
+// Phase A is bound by the multiply pipe (IMAD / IDP), phase B by the logic pipe (LOP3 / PRMT).  Warps that start together stay in step
+// and leave one of the two pipes idle most of the time (sm__pipe_fmaheavy 47 % + sm__pipe_alu 53 % of the elapsed cycles, back to back:
+// profiles/r02b_*); every other warp of a sub-partition therefore starts about half a tile period late, which keeps the two groups
+// in opposite phases (8K encode 160.8 -> 152.6 us).  flags = 1 | delay_cycles << 8 (T3C_V5_FLAGS overrides the default)
+constexpr uint32_t V5_FLAGS_DEFAULT = 1u | (9000u << 8);
+__device__ __forceinline__ void stagger_start(uint32_t flags, int warp, uint32_t n_tiles)
+{
+    if ((flags & 1u) && (warp & 4) && n_tiles >= 8) {   // short ranges (chunked host pipelines) would only lose the delay
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)(flags >> 8)) { }
+    }
+}
 // position of a warp inside its contiguous tile range: everything phase A / B / C need, advanced by constants
 struct TileCursor {
     uint32_t f, tile, tm;      // frame, mini-tile inside the frame, tile mod 3
@@ -334,6 +349,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
     TileCursor c;
     cursor_seek<PIX>(c, P, g, P.in_stride, P.out_stride, mt_lo, lane);
     if (lane == 0) fetch(c.pix);
+    stagger_start(P.flags, warp, mt_hi - mt_lo);
     uint32_t phase = 0;
     bool first = true;
     for (uint32_t left = mt_hi - mt_lo; left; --left) {
@@ -471,6 +487,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
     TileCursor c;
     cursor_seek<PIX>(c, P, g, P.out_stride, P.in_stride, mt_lo, lane);
     if (lane < 9) fetch(c.run);
+    stagger_start(P.flags, warp, mt_hi - mt_lo);
     uint32_t phase = 0;
     bool first = true;
     for (uint32_t left = mt_hi - mt_lo; left; --left) {
