@@ -141,7 +141,10 @@ void t3o_rs_encode(int k, int fixed, const uint8_t* data_k, uint8_t* out26) /* O
 }
 
 #define VMAX 40
-int t3o_rs_decode(int k, int fixed, uint8_t* c, uint8_t* out_k) /* OLD:546-662 */
+/* strict: the acceptance rule of the consistent (FIXED) frame decoder, which has no reference to match: reject unless L <= t,
+ * deg(sigma) == L and sigma has L distinct roots (with more than t errors OLD:611-624 accepts locators that locate nothing and
+ * "corrects" 0..t symbols of a block it cannot decode).  strict = 0 is decode_block as shipped / as repaired, bit for bit. */
+static int rs_decode_ex(int k, int fixed, int strict, uint8_t* c, uint8_t* out_k) /* OLD:546-662 */
 {
     gf_init();
     const int n = 26, r = n - k, t = r / 2;
@@ -182,6 +185,11 @@ int t3o_rs_decode(int k, int fixed, uint8_t* c, uint8_t* out_k) /* OLD:546-662 *
             } else m += 1;
         } else m += 1;
     }
+    if (strict) {
+        int deg = ns - 1;
+        while (deg > 0 && sigma[deg] == 0) --deg;
+        if (L > t || deg != L) return 0;
+    }
     /* Omega = (S * sigma) mod x^r, OLD:606-610 */
     uint8_t Om[VMAX + 9];
     memset(Om, 0, sizeof Om);
@@ -194,7 +202,7 @@ int t3o_rs_decode(int k, int fixed, uint8_t* c, uint8_t* out_k) /* OLD:546-662 *
         for (int d = ns - 1; d >= 0; --d) acc = t3o_gf_add(MUL(acc, x), sigma[d]);
         if (acc == 0) pos[np++] = i;
     }
-    if (np > t) return 0;
+    if (np > t || (strict && np != L)) return 0;
     /* formal derivative in char 3, OLD:625-641 */
     uint8_t sp[VMAX]; int nsp = ns > 1 ? ns - 1 : 1;
     memset(sp, 0, sizeof sp);
@@ -217,6 +225,8 @@ int t3o_rs_decode(int k, int fixed, uint8_t* c, uint8_t* out_k) /* OLD:546-662 *
     for (int i = 0; i < k; ++i) out_k[i] = c[i];
     return 1;
 }
+
+int t3o_rs_decode(int k, int fixed, uint8_t* c, uint8_t* out_k) { return rs_decode_ex(k, fixed, 0, c, out_k); }
 
 void t3o_rs_encode_blocks(int k, int fixed, const uint8_t* data, size_t nblk, uint8_t* out)
 {
@@ -676,7 +686,7 @@ int t3o_decode_profile_fixed(const t3o_cfg* c, size_t n_raw_words, const uint8_t
         for (size_t cw = 0; cw < g.ncw_b[b]; ++cw) {
             uint8_t nbuf[26], kbuf[26], orig[26];
             memcpy(nbuf, body + 26 * (g.cw_base[b] + cw), 26); memcpy(orig, nbuf, 26);
-            if (!t3o_rs_decode(k, 1, nbuf, kbuf)) { ok = 0; break; }
+            if (!rs_decode_ex(k, 1, 1, nbuf, kbuf)) { ok = 0; break; }
             for (int i = 0; i < 26; ++i) if (nbuf[i] != orig[i]) ++ncorr;
             for (int i = 0; i < k; ++i) sy[9 * ((size_t)k * cw + (size_t)i) + (size_t)b] = kbuf[i];
         }

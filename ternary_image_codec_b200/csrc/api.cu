@@ -28,7 +28,7 @@ struct t3c_ctx {
     uint32_t* d_crc = nullptr; // CRC-32 tables of the .t3v record kernels
     HostTables* host = nullptr; // host copy of the constant tables (decoder screen constants are derived per call)
     // grow-only device scratch
-    struct Buf { void* p = nullptr; size_t cap = 0; };
+    struct Buf { void* p = nullptr; size_t cap = 0; cudaStream_t last = nullptr; bool used = false; };  // last: the stream of the latest user
     Buf buf[6];
     // small results: device mailbox + pinned host mirror (copied explicitly, MAIL_DOWN)
     struct Mail { uint32_t status[64]; t3c_config cfg; int ok; uint8_t hdr27[27]; uint8_t coded52[52]; };
@@ -62,25 +62,39 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-t3c_status reserve(t3c_ctx* ctx, int slot, size_t bytes, void** out)
+t3c_status chain(t3c_ctx* ctx, cudaStream_t from, cudaStream_t to);
+// Scratch is per context, not per stream: a caller that moves to another stream is ordered after the work the previous stream
+// already holds (an event recorded on that stream now covers every earlier use of the buffer).  Growth synchronises the device.
+t3c_status reserve_on(t3c_ctx* ctx, int slot, size_t bytes, void** out, cudaStream_t s)
 {
     t3c_ctx::Buf& b = ctx->buf[slot];
     if (bytes + 64 > b.cap) {
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaDeviceSynchronize());
         if (b.p) CU(cudaFree(b.p));
-        b.p = nullptr; b.cap = 0;
+        b.p = nullptr; b.cap = 0; b.used = false;
         size_t want = bytes + 64 + bytes / 8;
         CU(cudaMalloc(&b.p, want));
         b.cap = want;
     }
+    if (b.used && b.last != s) { t3c_status r = chain(ctx, b.last, s); if (r != T3C_OK) return r; }
+    b.last = s; b.used = true;
     *out = b.p;
     return T3C_OK;
 }
+t3c_status reserve(t3c_ctx* ctx, int slot, size_t bytes, void** out) { return reserve_on(ctx, slot, bytes, out, ctx->stream); }
 template <class T>
 t3c_status reserve_t(t3c_ctx* ctx, int slot, size_t bytes, T** out)
 {
     void* p = nullptr;
     t3c_status s = reserve(ctx, slot, bytes, &p);
+    *out = static_cast<T*>(p);
+    return s;
+}
+template <class T>
+t3c_status reserve_t(t3c_ctx* ctx, int slot, size_t bytes, T** out, cudaStream_t st)
+{
+    void* p = nullptr;
+    t3c_status s = reserve_on(ctx, slot, bytes, &p, st);
     *out = static_cast<T*>(p);
     return s;
 }
@@ -201,8 +215,8 @@ t3c_status t3c_create(int device, t3c_ctx** out)
     cudaGetDeviceProperties(&prop, device);
     ctx->tabs.sm_count = prop.multiProcessorCount;
     ctx->tabs.hdr = &ctx->hdr_cache;
-    if (cudaMalloc((void**)&ctx->hdr_cache.d52, 128) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
-    ctx->hdr_cache.d27 = ctx->hdr_cache.d52 + 64;
+    if (cudaMalloc((void**)&ctx->hdr_cache.base, 128 * HeaderCache::N) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
+    for (int i = 0; i < HeaderCache::N; ++i) { ctx->hdr_cache.e[i].d52 = ctx->hdr_cache.base + 128 * i; ctx->hdr_cache.e[i].d27 = ctx->hdr_cache.base + 128 * i + 64; }
     ctx->tabs.sup = &ctx->sup_cache;
     {
         std::vector<uint32_t> h(crc_table_words());
@@ -232,7 +246,7 @@ void t3c_destroy(t3c_ctx* ctx)
     for (auto& b : ctx->buf) if (b.p) cudaFree(b.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
-    if (ctx->hdr_cache.d52) cudaFree(ctx->hdr_cache.d52);
+    if (ctx->hdr_cache.base) cudaFree(ctx->hdr_cache.base);
     for (auto& sl : ctx->sup_cache.slot) if (sl.d_map) cudaFree(sl.d_map);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);
@@ -351,7 +365,7 @@ t3c_status t3c_decode_profile_fixed_dev(t3c_ctx* ctx, const t3c_config* cfg, siz
     if (cap_words < nw) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile_fixed: capacity");
     uint8_t* sy = nullptr;
     const uint64_t pitch = (g.n_s + 8) / 9; // band-major scratch: band b's decoded symbols at b*pitch
-    TRY(reserve_t(ctx, B_TMP, 9 * pitch + 16, &sy));
+    TRY(reserve_t(ctx, B_TMP, 9 * pitch + 16, &sy, s));
     int n = launch_init_status(d_status, 1, s);
     uint32_t n_full = 0;
     if (fast_path_ok(*cfg)) { // tiled kernels: profile words -> raw words for the full mini-tiles
@@ -399,8 +413,8 @@ t3c_status t3c_encode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, int a
             const size_t px0 = 6 * (size_t)tail.unit_start, n_tail = n_px - px0, w_tail = (n_tail + 1) / 2; // px0 is even: whole words
             t3c_pixel* q = nullptr;
             uint8_t* raw = nullptr;
-            TRY(reserve_t(ctx, B_AUX, 6 * n_tail + 64, &q));
-            TRY(reserve_t(ctx, B_AUX2, 9 * w_tail + 64, &raw));
+            TRY(reserve_t(ctx, B_AUX, 6 * n_tail + 64, &q, s));
+            TRY(reserve_t(ctx, B_AUX2, 9 * w_tail + 64, &raw, s));
             for (size_t f = 0; f < n_frames; ++f) {
                 int n = launch_rgb_to_quant(d_rgb + 3 * n_px * f + 3 * px0, n_tail, q, s);
                 n += launch_pack_pixels(q, n_tail, raw, s);
@@ -417,8 +431,8 @@ t3c_status t3c_encode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, int a
     // general path: per frame K1 (bridge, pack) into scratch, then the general profile encoder
     t3c_pixel* q = nullptr;
     uint8_t* raw = nullptr;
-    TRY(reserve_t(ctx, B_AUX, 6 * n_px, &q));
-    TRY(reserve_t(ctx, B_AUX2, 9 * n_words, &raw));
+    TRY(reserve_t(ctx, B_AUX, 6 * n_px, &q, s));
+    TRY(reserve_t(ctx, B_AUX2, 9 * n_words, &raw, s));
     for (size_t f = 0; f < n_frames; ++f) {
         int n = launch_rgb_to_quant(d_rgb + 3 * n_px * f, n_px, q, s);
         n += launch_pack_pixels(q, n_px, raw, s);
@@ -457,7 +471,7 @@ t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, const
             // the ragged rest: band symbols from m_start on, in a band-major scratch addressed as if it started at symbol 0
             const uint64_t pitch_all = (g.n_s + 8) / 9, pitch_t = pitch_all - tail.m_start;
             uint8_t* syt = nullptr;
-            TRY(reserve_t(ctx, B_TMP, 9 * pitch_t + 16, &syt));
+            TRY(reserve_t(ctx, B_TMP, 9 * pitch_t + 16, &syt, s));
             uint8_t* sy0 = reinterpret_cast<uint8_t*>(reinterpret_cast<uintptr_t>(syt) - tail.m_start);
             for (size_t f = 0; f < n_frames; ++f) {
                 CU(cudaMemsetAsync(syt, 0, 9 * pitch_t + 16, s));
@@ -470,7 +484,7 @@ t3c_status t3c_decode_frames_rgb8_dev(t3c_ctx* ctx, const t3c_config* cfg, const
     }
     uint8_t* sy = nullptr;
     const uint64_t pitch = (g.n_s + 8) / 9;
-    TRY(reserve_t(ctx, B_TMP, 9 * pitch + 16, &sy));
+    TRY(reserve_t(ctx, B_TMP, 9 * pitch + 16, &sy, s));
     for (size_t f = 0; f < n_frames; ++f) {
         CU(cudaMemsetAsync(sy, 0, 9 * pitch + 16, s));
         int n = launch_decode_fixed_general(ctx->tabs, g, d_in + 9 * stride_words * f, sy, pitch, d_status + 2 * f, s);
@@ -1031,7 +1045,7 @@ t3c_status t3c_t3v_frame_records_dev(t3c_ctx* ctx, const uint8_t* d_words, size_
         return fail(ctx, T3C_ERR_ARG, "t3v_frame_records: pitch / alignment");
     DeviceGuard guard(ctx->device);
     uint32_t* part = nullptr;
-    TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part));
+    TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part, (cudaStream_t)st));
     return check_launch(ctx, launch_t3v_records(ctx->tabs.crc, d_words, n_words, stride_words, n_frames, d_rec, record_pitch, part, (cudaStream_t)st));
 }
 t3c_status t3c_t3v_read_frames_dev(t3c_ctx* ctx, const uint8_t* d_rec, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* d_words,
@@ -1042,7 +1056,7 @@ t3c_status t3c_t3v_read_frames_dev(t3c_ctx* ctx, const uint8_t* d_rec, size_t re
         return fail(ctx, T3C_ERR_ARG, "t3v_read_frames: pitch / alignment");
     DeviceGuard guard(ctx->device);
     uint32_t* part = nullptr;
-    TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part));
+    TRY(reserve_t(ctx, B_TMP2, 4 * t3v_partial_words(n_words, n_frames), &part, (cudaStream_t)st));
     return check_launch(ctx, launch_t3v_read(ctx->tabs.crc, d_rec, record_pitch, n_frames, n_words, d_words, stride_words, part, d_ok, (cudaStream_t)st));
 }
 t3c_status t3c_crc32(t3c_ctx* ctx, const uint8_t* data, size_t n, uint32_t* crc)

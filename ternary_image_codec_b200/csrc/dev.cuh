@@ -120,7 +120,10 @@ __device__ __forceinline__ uint8_t gsub(const GfTables& g, uint32_t a, uint32_t 
 //  * with the repaired arithmetic, syndromes of the form S_j = e X^(j+1) (X != 0) are the one-error case: Berlekamp-Massey
 //    would find sigma = 1 - X x (the shortest recurrence is unique while 2L <= r), Chien its single root at position log X and
 //    Forney the magnitude e, so the correction c[log X] -= e is applied directly.
-static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c, int k, bool fixed, const uint8_t* S)
+// strict (the frame-level consistent decoder only; the block-level API stays bit-exact with the reference's decode_block): reject
+// unless Berlekamp-Massey's L <= t, deg(sigma) == L and sigma has L distinct roots -- with more than t errors the reference accepts
+// locators that are not error locators and "corrects" 0..t symbols of a block it cannot decode (OLD:611-624 only counts roots).
+static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c, int k, bool fixed, const uint8_t* S, bool strict = false)
 {
     const int r = 26 - k, t = r >> 1;
     if (fixed && S[0]) { // one error?
@@ -163,6 +166,7 @@ static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c
     }
     int top = 9;
     while (top > 0 && sg[top] == 0) --top; // sg[0] = 1 always
+    if (strict && (L > t || top != L)) return false;
     // Chien search: positions i with sigma(alpha^-i) = 0.  Degrees 1 and 2 are solved instead of searched (the same root set):
     // in characteristic 3, x^2 + b x + c = (x - b)^2 - (b^2 - c), so the roots are b +- sqrt(b^2 - c)
     uint32_t roots = 0;
@@ -187,7 +191,7 @@ static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c
             if (acc == 0) { roots |= 1u << i; ++nroots; }
         }
     }
-    if (nroots > t) return false;
+    if (nroots > t || (strict && nroots != L)) return false;
     uint8_t sp[9];
     for (int i = 1; i < 10; ++i) {
         const int im = i % 3;
@@ -209,7 +213,7 @@ static __device__ __noinline__ bool rs_decode_core(const GfTables& g, uint8_t* c
     return true;
 }
 // power-sum syndromes straight from the block (any arithmetic)
-static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t* c, int k, bool fixed)
+static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t* c, int k, bool fixed, bool strict = false)
 {
     const int r = 26 - k;
     uint8_t S[8];
@@ -225,7 +229,7 @@ static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t*
         all0 = all0 && acc == 0;
     }
     if (all0) return true;
-    return rs_decode_core(g, c, k, fixed, S);
+    return rs_decode_core(g, c, k, fixed, S, strict);
 }
 // repaired arithmetic only: syndromes from the parity residual p[0..r) = parity(received data) - received parity, which the
 // tiled kernels' syndrome screen has already computed (S_j = sum_m syn[j][m] p_m: r*r products instead of 26*r)
@@ -238,7 +242,7 @@ static __device__ __forceinline__ bool rs_decode_residual(const GfTables& g, uin
         for (int m = 0; m < r; ++m) acc = gadd(g, acc, gmul(g, p[m], g.syn[ki][j][m]));
         S[j] = (uint8_t)acc;
     }
-    return rs_decode_core(g, c, k, true, S);
+    return rs_decode_core(g, c, k, true, S, true);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(FAST_TPB, 4) k_decode_rgb_fast(FastParams P, G
                 const uint64_t p0 = 26 * (g.cw_base[b] + (uint64_t)C_MINI * tile + cl);
                 uint8_t cwd[26], orig[26];
                 for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = sg.dsc[scr_state(g, p0 + i)][src[i] % 27];
-                if (!rs_decode_thread(sg, cwd, K, true)) {
+                if (!rs_decode_thread(sg, cwd, K, true, true)) {
                     atomicExch(&P.status[2 * f], 0u);
                 } else {
                     uint32_t nfix = 0;

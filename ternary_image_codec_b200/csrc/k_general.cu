@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(TPB) k_decode_fixed_general(const uint8_t* __r
     const I c = c0 + threadIdx.x;
     uint8_t cw[26], orig[26];
     for (int i = 0; i < 26; ++i) cw[i] = orig[i] = stage[26 * threadIdx.x + i];
-    if (!rs_decode_thread(sg, cw, k, true)) { atomicExch(&status[0], 0u); return; }
+    if (!rs_decode_thread(sg, cw, k, true, true)) { atomicExch(&status[0], 0u); return; }
     uint32_t nfix = 0;
     for (int i = 0; i < 26; ++i) nfix += cw[i] != orig[i];
     if (nfix) atomicAdd(&status[1], nfix);
@@ -833,12 +833,22 @@ int launch_encode_general_from(const DevTables& T, const t3c_config& cfg, const 
 const uint8_t* cached_header(const DevTables& T, const t3c_config& cfg, int arith, cudaStream_t st, int& launches)
 {
     HeaderCache& H = *T.hdr;
-    if (!H.valid || H.arith != (arith ? 1 : 0) || std::memcmp(&H.cfg, &cfg, sizeof cfg) != 0) {
-        launches += launch_header_emit(T, cfg, arith, H.d27, H.d52, st);
-        cudaStreamSynchronize(st); // once per config change: later calls may come on other streams
-        H.cfg = cfg; H.arith = arith ? 1 : 0; H.valid = true;
+    const int a = arith ? 1 : 0;
+    for (int i = 0; i < HeaderCache::N; ++i)
+        if (H.e[i].valid && H.e[i].arith == a && std::memcmp(&H.e[i].cfg, &cfg, sizeof cfg) == 0) return H.e[i].d52;
+    int slot = -1;
+    for (int i = 0; i < HeaderCache::N; ++i) if (!H.e[i].valid) { slot = i; break; }
+    if (slot < 0) {   // all entries taken: nothing in flight may still read the one that is reused
+        cudaDeviceSynchronize();
+        slot = H.next;
+        H.next = (H.next + 1) % HeaderCache::N;
     }
-    return H.d52;
+    HeaderCache::Entry& E = H.e[slot];
+    E.valid = false;
+    launches += launch_header_emit(T, cfg, arith, E.d27, E.d52, st);
+    cudaStreamSynchronize(st); // once per new config: later calls may come on other streams
+    E.cfg = cfg; E.arith = a; E.valid = true;
+    return E.d52;
 }
 __global__ void k_frame_finish(uint8_t* __restrict__ out_base, size_t stride_bytes, const uint8_t* __restrict__ hdr52, uint64_t body_end, uint64_t frame_bytes)
 {

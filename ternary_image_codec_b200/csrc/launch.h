@@ -9,7 +9,15 @@ namespace t3c {
 
 // The coded super-frame header depends on the config only: it is emitted on the device (k_header_emit) when the config
 // changes and kept in `d52`; every later frame copies the 52 symbols.
-struct HeaderCache { uint8_t* d52 = nullptr; uint8_t* d27 = nullptr; t3c_config cfg{}; int arith = -1; bool valid = false; };
+// One entry per (config, arithmetic) seen; an entry is written once (emit + stream synchronise) and never again while other entries are
+// free, so kernels in flight on any stream that copy an entry's 52 symbols can never see another config's header.  When all entries
+// are taken the device is synchronised before the oldest one is reused.
+struct HeaderCache {
+    static constexpr int N = 8;
+    struct Entry { uint8_t* d52 = nullptr; uint8_t* d27 = nullptr; t3c_config cfg{}; int arith = -1; bool valid = false; } e[N];
+    uint8_t* base = nullptr;   // N x 128 bytes
+    int next = 0;
+};
 // Phase-B pass maps of the super-tile kernels (k_super.cuh): they depend on the per-band k and on cw_base mod 3 only; one slot
 // per kernel flavour (encode / decode x RGB / raw words), re-uploaded when the key changes.
 struct SuperCache {

@@ -412,8 +412,77 @@ def test_8k_injected_errors_are_corrected(codec, t3):
     assert torch.equal(back, want)
 
 
-def test_8k_uep_2d_beacon_general_path_roundtrip(codec, t3):
-    """BASELINE configs[2]: 8K, 2D 26x26 interleave + luma-priority UEP + coset C1 + beacon(26,2), errors <= t."""
+# ------------------------------------------------------------------ BASELINE.json full sizes, whole frame against the oracle
+# One 8K frame costs the single-threaded C oracle ~20 s to encode and ~25 s to decode; the oracle calls of a test run side by
+# side on host threads (ctypes releases the GIL).  `slow`, but inside -m gpu: these are the parity tests proper for
+# BASELINE configs 1 and 2 -- every byte of every codeword of the frame, not a prefix.
+N8K = 7680 * 4320
+CFG1 = dict(profile=T.P3, uep=2)
+CFG2 = dict(profile=T.P5, tile=(26, 26), beacon=(26, 2, True), uep=T.UEP_LUMA, seed=(2, 1, 1), coset=1)
+
+
+def _pool(jobs):
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        futs = [ex.submit(j) for j in jobs]
+        return [f.result() for f in futs]
+
+
+@pytest.fixture(scope="module")
+def frame8k():
+    return T.synth_rgb(2, N8K)                                   # SURVEY 8(d) config 1 input: seed 2
+
+
+def _whole_frame_encode(codec, oracle, t3, kw, rgb):
+    oc, gc = both(kw)
+    got = [codec.encode_frames_rgb8(rgb[None], gc, a)[0] for a in (t3.REF_EXACT, t3.FIXED)]
+    oracle.rs_gen(20)  # the oracle's only global state is its lazily built GF(27) tables: built before the threads start
+    want = _pool([lambda: oracle.encode_rgb(oc, rgb, 0), lambda: oracle.encode_rgb(oc, rgb, 1)])
+    for g_, w_, name in zip(got, want, ("REF-EXACT", "FIXED")):
+        assert g_.shape == w_.shape, name
+        assert np.array_equal(g_, w_), name
+    return got[1]
+
+
+def _whole_frame_decode(codec, oracle, t3, kw, enc_fixed):
+    oc, gc = both(kw)
+    add = T.gf_add_table()
+    bad_some, n_some = T.inject_errors(enc_fixed, oc, N8K // 2, seed=3, gf_add=add)               # e_c = h(3, c) % (t + 1)
+    bad_all, n_all = T.inject_errors(enc_fixed, oc, N8K // 2, seed=5, gf_add=add, exact_t=True)   # exactly t in every codeword
+    oracle.rs_gen(20)
+    want = _pool([lambda: oracle.decode_rgb_fixed(oc, bad_some, N8K), lambda: oracle.decode_rgb_fixed(oc, bad_all, N8K)])
+    for bad, nerr, (ok_o, rgb_o, nc_o), name in ((bad_some, n_some, want[0], "0..t"), (bad_all, n_all, want[1], "t")):
+        ok, rgb, nc = codec.decode_frames_rgb8(bad[None], N8K, gc)
+        assert ok_o and ok.all(), name
+        assert nc == nc_o == nerr, (name, nc, nc_o, nerr)
+        assert rgb.shape[1] == rgb_o.shape[0] and np.array_equal(rgb[0], rgb_o), name
+
+
+@pytest.mark.slow
+def test_8k_config1_whole_frame_matches_oracle(codec, oracle, t3, frame8k):
+    """BASELINE configs[1] (8K RGB8, RS(26,20), 1D) through k_encode_v5 / k_decode_v5: the whole frame byte-exact against the oracle's
+    encode in both arithmetic modes (OLD:1043-1169), and the whole-frame decode of the FIXED encoding with injected symbol errors
+    (0..t per codeword, and exactly t in every codeword) against the oracle's consistent decoder: pixels, ok flag, corrected count."""
+    assert t3.fast_path_available(both(CFG1)[1])
+    enc = _whole_frame_encode(codec, oracle, t3, CFG1, frame8k)
+    assert enc.shape[0] == 20766726
+    _whole_frame_decode(codec, oracle, t3, CFG1, enc)
+
+
+@pytest.mark.slow
+def test_8k_config2_whole_frame_matches_oracle(codec, oracle, t3, frame8k):
+    """BASELINE configs[2] (8K, 2D 26x26 boustrophedon + luma-priority UEP + coset C1 + beacon(26,2)) through k_encode_super /
+    k_decode_super (+ the general kernels on the ragged end): whole-frame encode parity in both arithmetic modes and whole-frame
+    decode with injected errors up to t per codeword, against the oracle."""
+    gc = both(CFG2)[1]
+    assert not t3.fast_path_available(gc) and t3.super_path_available(gc)
+    enc = _whole_frame_encode(codec, oracle, t3, CFG2, frame8k)
+    _whole_frame_decode(codec, oracle, t3, CFG2, enc)
+
+
+def test_8k_config2_device_roundtrip_clean(codec, t3):
+    """BASELINE configs[2], device-resident clean round trip (no errors, no oracle: decode(encode(x)) == dequant(quant(x)) on the
+    pixels the encoder keeps); the oracle comparison with injected errors is test_8k_config2_whole_frame_matches_oracle."""
     import torch
     kw = dict(profile=T.P5, tile=(26, 26), beacon=(26, 2, True), uep=T.UEP_LUMA, seed=(2, 1, 1), coset=1)
     _, gc = both(kw)
@@ -510,6 +579,42 @@ def test_fused_fast_path_out_of_alphabet_and_uncorrectable(codec, oracle, t3):
     ok2, _, _ = codec.decode_frames_rgb8(bad.reshape(1, -1, 9), n_px, gc)
     ok2_o, _, _ = oracle.decode_rgb_fixed(oc, bad.reshape(-1, 9), n_px)
     assert bool(ok2[0]) == bool(ok2_o)
+
+
+@pytest.mark.parametrize("kw", [dict(profile=T.P3, uep=2), dict(profile=T.P2, uep=1), dict(profile=T.P1, uep=0), dict(profile=T.P4, uep=3),
+                                dict(profile=T.P2, uep=T.UEP_LUMA)])
+def test_consistent_decoder_rejects_more_than_t_errors(codec, oracle, t3, kw):
+    """t + 1 symbol errors in a codeword: decode_block (OLD:611-624) would accept most such blocks with 0..t bogus corrections; the
+    consistent decoder (ours, no reference to match) accepts a block only when Berlekamp-Massey's L <= t equals the number of distinct
+    roots of sigma.  Frames that each hold ONE such codeword (in band 0): same verdict as the oracle frame by frame, and the
+    share of rejected frames is what bounded-distance decoding predicts."""
+    oc, gc = both(kw)
+    n_px = 8 * 5940 + 3
+    rgb = T.synth_rgb(17, n_px)
+    enc = codec.encode_frames_rgb8(rgb[None], gc, t3.FIXED)[0]
+    add = T.gf_add_table()
+    k0 = T.K_OF_UEP[oc.uep[0] % 4]
+    t0 = (26 - k0) // 2
+    n_s = (26 * ((n_px + 1) // 2) + 2) // 3
+    ncw0 = ((n_s + 8) // 9) // k0                                  # codewords of band 0: body symbols [0, 26 * ncw0)
+    r = rng(23)
+    n_frames, rejected = 24, 0
+    bad = np.repeat(enc[None], n_frames, axis=0)
+    for f in range(n_frames):
+        flat = bad[f].reshape(-1)
+        start = 52 + 26 * int(r.integers(0, ncw0))
+        for q in start + r.choice(26, t0 + 1, replace=False):
+            flat[q] = add[flat[q] % 27, int(r.integers(1, 27))]
+    ok, back, _ = codec.decode_frames_rgb8(bad, n_px, gc)
+    for f in range(n_frames):
+        ok_o, back_o, _ = oracle.decode_rgb_fixed(oc, bad[f], n_px)
+        assert bool(ok[f]) == bool(ok_o), f
+        if ok_o:
+            assert np.array_equal(back[f], back_o), f
+        rejected += not ok_o
+    # a block with t + 1 errors decodes (to a wrong codeword) when its syndrome is one of the sum_{e<=t} C(26,e) 26^e correctable ones
+    # of 27^r: 93 % for k = 24, 41 % for k = 22, 12 % for k = 20, 2.4 % for k = 18
+    assert rejected >= {24: 0, 22: 6, 20: 15, 18: 19}[k0], rejected
 
 
 @pytest.mark.parametrize("kw", [dict(profile=T.P3, uep=2), dict(profile=T.P2, uep=1)])

@@ -73,7 +73,7 @@ def test_magic_divisions():
 
 def test_prmt_plane_table():
     """planes4_to_sym: the 8-entry byte table {LUT0, LUT1} maps 3 plane bits b0 b1 b2 to b0 + 3 b1 + 9 b2"""
-    m = re.search(r"__byte_perm\((0x[0-9A-Fa-f]+)u, (0x[0-9A-Fa-f]+)u, sel\)", KFAST)
+    m = re.search(r'"r"\((0x[0-9A-Fa-f]+)u\), "r"\((0x[0-9A-Fa-f]+)u\), "r"\(sel\)', KFAST)
     lut = int(m.group(1), 16) | (int(m.group(2), 16) << 32)
     for n in range(8):
         assert (lut >> (8 * n)) & 0xFF == (n & 1) + 3 * ((n >> 1) & 1) + 9 * ((n >> 2) & 1)
@@ -189,3 +189,36 @@ def test_super_tile_plan_rejects_what_the_kernels_do_not_take():
     assert t3.super_plan(t3.make_config(profile=1, uep=(0, 1, 0, 1, 0, 1, 0, 1, 0)), 100) is None            # no full super-tile in so short a frame
     three = t3.make_config(profile=1, uep=(0, 1, 2, 0, 1, 2, 0, 1, 2))                                        # k = 24, 22, 20: lcm(26, 24, 22, 20) = 17160 symbols per band
     assert t3.super_path_available(three) and t3.super_plan(three, 7680 * 4320 // 2) is None                  # ... does not fit shared memory: general kernels
+
+
+def test_v5_integer_bridge_matches_float32_reference_on_all_colours():
+    """k_fast5.cuh: the integer Cb / Cr path equals the reference's float32 BT.601 + quantiser (IMG:47-56,69-78) for all 2^24
+    colours; the integer luma path equals it wherever its tie flag (low nine bits of t) is clear -- flagged pixels take the float path."""
+    K5 = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "k_fast5.cuh")).read()
+    c = lambda n: _const(n, K5)
+    C5_M, C5_Z, C5_M2, Y5_M, Y5_Z, Y5_M2 = c("C5_M"), c("C5_Z"), c("C5_M2"), c("Y5_M"), c("Y5_Z"), c("Y5_M2")
+    coef = [int(x) for x in re.findall(r"pk16\((-?\d+), (-?\d+)\)", K5[K5.index("c5_coef[6]"):])[:6] for x in x]
+    (cb0, cb1), (cb2, _), (cr0, cr1), (cr2, _), (y0, y1), (y2, _) = [coef[i:i + 2] for i in range(0, 12, 2)]
+    f = np.float32
+    R, G, B = [a.ravel().astype(np.int64) for a in np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")]
+    r, g, b = R.astype(f), G.astype(f), B.astype(f)
+    rnd = lambda x: np.floor(x.astype(np.float64) + 0.5).astype(np.int64)
+    y = (f(0.299) * r + f(0.587) * g) + f(0.114) * b
+    cbf = ((f(-0.168736) * r - f(0.331264) * g) + f(0.5) * b) + f(128)
+    crf = ((f(0.5) * r - f(0.418688) * g) - f(0.081312) * b) + f(128)
+    Y8, Cb8, Cr8 = np.clip(rnd(y), 0, 255), np.clip(rnd(cbf), 0, 255), np.clip(rnd(crf), 0, 255)
+    qc = lambda C: (5 * C + 7 + (C >> 7)) >> 4
+    OFF = 128 * 31250 + 15625 + 31250
+    for (c0, c1, c2), C8 in (((cb0, cb1, cb2), Cb8), ((cr0, cr1, cr2), Cr8)):
+        X = c0 * R + c1 * G + c2 * B + OFF
+        assert X.min() >= 0 and X.max() < 2 ** 32
+        t = (X * C5_M) >> 32
+        u = (((t & 0xFFFFC000) | C5_Z) * C5_M2) >> 32
+        assert np.array_equal(u, qc(C8))
+    X = y0 * R + y1 * G + y2 * B + 500
+    t = (X * Y5_M) >> 32
+    yq = (((t & 0xFFFFFE00) | Y5_Z) * Y5_M2) >> 32
+    flagged = (t & 511) == 0
+    want = (484 * Y8 + 255) // 510
+    assert np.array_equal(yq[~flagged], want[~flagged])
+    assert 0 < np.count_nonzero(yq[flagged] != want[flagged]) < 2000 and flagged.mean() < 0.0025
