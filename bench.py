@@ -395,15 +395,43 @@ def run_ours(args):
                "lanes": n_lanes,
                "how": "host-buffer C ABI, pinned memory; chunked H2D/kernel/D2H pipeline inside each call; per lane an encoder and a decoder context on two host threads (frame i encodes while frame i-1 decodes); the lanes work on independent frames"}
 
+    # ---- BASELINE config 4: 240-frame synthetic 8K stream, frame f -> rank f mod world, device-resident, max over ranks
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import secondary as S2
+    sctx = S2.Ctx(local, codec)
+    nchk = 1 << 16
+    spot_in = rgb[0][:3 * nchk].cpu().numpy().reshape(-1, 3)
+    spot_out = back[0][:3 * nchk].cpu().numpy().reshape(-1, 3)
+    del rgb, enc, back, q, chk
+    torch.cuda.empty_cache()
+    my_frames = len(range(rank, 240, world))
+    if world > 1:
+        dist.barrier()
+    st4 = S2.stream240(sctx, frames_per_call=min(8, my_frames), n_frames=my_frames)
+    ms4 = st4["total_ms"]
+    if world > 1:
+        t = torch.tensor([ms4], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms4 = float(t.item())
+    secondary = {"config4_stream240": {"workload": "240 synthetic 8K frames, RS(26,20) 1D, frame f -> GPU f mod N, batched launches of up to 8 frames, device-resident; "
+                                                   "max over ranks", "frames": 240 if 240 % world == 0 else st4["frames"] * world, "ms": ms4,
+                                       "frames_per_s": (240 if 240 % world == 0 else st4["frames"] * world) / ms4 * 1e3,
+                                       "mpix_per_s": (240 if 240 % world == 0 else st4["frames"] * world) * n_px / ms4 / 1e3, "ok": st4["ok"]}}
+    if rank == 0:
+        try:
+            secondary.update(S2.secondary_single_gpu(sctx))
+        except Exception as e:  # the headline must not depend on the secondary workloads
+            secondary["error"] = repr(e)
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         # parity spot check against the oracle on a slice of the timed frame + CPU baseline (bounded sample)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import t3oracle as T
         oracle = T.Oracle()
-        nchk = 1 << 16
-        sl = rgb[0][:3 * nchk].cpu().numpy().reshape(-1, 3)
-        want = oracle.quant_to_rgb(oracle.rgb_to_quant(sl))
-        assert np.array_equal(back[0][:3 * nchk].cpu().numpy().reshape(-1, 3), want), "oracle spot check failed"
+        want = oracle.quant_to_rgb(oracle.rgb_to_quant(spot_in))
+        assert np.array_equal(spot_out, want), "oracle spot check failed"
         cores = os.cpu_count() or 1
         threads = max(1, min(cores, 64))
         n_slice = N_PX // 64
@@ -425,6 +453,16 @@ def run_ours(args):
             pass
         clocks["samples_total"] = n_all
         clocks["window_ms"] = 1e3 * (wall1 - wall0)
+        # issue fraction of the dominant kernel: warp instructions per launch (committed ncu capture, profiles/kernel_counts.json)
+        # / issue slots of the launch (148 SMs x 4 sub-partitions x cycles at the clock sampled in the timed region)
+        issue = None
+        try:
+            kc = json.load(open(os.path.join(ROOT, "profiles", "kernel_counts.json")))[f"fused {dom}"]
+            mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+            issue = {"frac": kc["warp_instructions"] / (148 * 4 * dom_ms * 1e-3 * mhz * 1e6), "warp_instructions_per_launch": kc["warp_instructions"],
+                     "source": kc.get("source"), "note": "the kernel is bound by instruction issue / the ALU and multiply pipes, not by HBM: see DESIGN.md 4.1"}
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": world * n_px * args.steps / (ms_total * 1e-3) / 1e6, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
@@ -438,8 +476,8 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "encode_ms": enc_ms, "decode_ms": dec_ms,
                          "encode_gbs": alg / (enc_ms * 1e-3) / 1e9, "decode_gbs": alg / (dec_ms * 1e-3) / 1e9,
-                         "frac_of_nominal_8tbs": ach / 8000.0},
-            "cpu_baseline": cpu, "clocks": clocks,
+                         "frac_of_nominal_8tbs": ach / 8000.0, "issue_frac": issue["frac"] if issue else None, "issue": issue},
+            "cpu_baseline": cpu, "clocks": clocks, "secondary": secondary,
         }
         emit(json.dumps(out))
     codec.close()

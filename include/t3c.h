@@ -106,6 +106,41 @@ T3C_API t3c_status t3c_header_emit(t3c_ctx*, const t3c_config*, int arith, uint8
 /* read_and_decode_header_from_words, OLD:918-937: *ok = RS+CRC verdict */
 T3C_API t3c_status t3c_header_parse(t3c_ctx*, int arith, const uint8_t* words9, size_t n_words, t3c_config* out, int* ok);
 
+/* ---- L0 / L1 names of the reference's public surface, single items (for drop-in callers and tests; bulk work goes through
+ * the profile codec).  SuperframeHeader (OLD:155-171) = the config fields plus magic, version, band_map_hash, frame_seq. */
+typedef struct {
+    uint16_t   magic;            /* 0x0A2 */
+    uint8_t    version;          /* 1 */
+    uint8_t    pad_;
+    uint32_t   band_map_hash;
+    uint32_t   frame_seq;
+    t3c_config cfg;              /* profile, uep, tile, seed, beacon, subword, centered, coset (superframe_words unused) */
+} t3c_header;
+/* HeaderCodec::pack, OLD:208-289: 27 symbols with the ternary CRC-12 in slots 20, 21, 22, 26 */
+T3C_API t3c_status t3c_header_pack(t3c_ctx*, const t3c_header*, uint8_t sym27[27]);
+/* HeaderCodec::check, OLD:290-319 */
+T3C_API t3c_status t3c_header_check(t3c_ctx*, const uint8_t sym27[27], int* ok);
+/* HeaderCodec::unpack, OLD:320-379 (profile % 5, UEP triples LSB-first, beacon slot % 9: the reference's reading, bug B7 included) */
+T3C_API t3c_status t3c_header_unpack(t3c_ctx*, const uint8_t sym27[27], t3c_header* out);
+/* CRC3::rem12, OLD:176-205: n message trits, then twelve zero trits */
+T3C_API t3c_status t3c_crc3_rem12(t3c_ctx*, const uint8_t* trits, size_t n, uint8_t out12[12]);
+/* scramble_symbol / descramble_symbol (OLD:81-94) applied to n symbols in sequence, in place: *st is the running LCG state, read
+ * (as is, like the reference's uint32_t& st) and left at the state the last symbol saw */
+T3C_API t3c_status t3c_scramble_symbols(t3c_ctx*, uint8_t* syms, size_t n, uint32_t a, uint32_t b, uint32_t* st, int inverse);
+/* encode_beacon_symbol, OLD:107-113 */
+T3C_API t3c_status t3c_beacon_symbol(t3c_ctx*, int profile, uint32_t frame_seq_mod, uint32_t health_flags, uint8_t* sym);
+/* GF27Tables as GF27Context::init builds them (OLD:414-466) plus the digit-wise add / sub of OLD:383-401 as tables */
+typedef struct {
+    uint8_t exp[78];
+    int16_t log[27];
+    uint8_t mul[729];
+    uint8_t inv[27];
+    uint8_t primitive;
+    uint8_t add[729];
+    uint8_t sub[729];
+} t3c_gf27;
+T3C_API t3c_status t3c_gf27_tables(t3c_ctx*, t3c_gf27* out);
+
 /* ---- K2..K5: profile codec ----------------------------------------------------------------- */
 /* encode_profile_from_raw, OLD:1043-1169 */
 T3C_API t3c_status t3c_encode_profile(t3c_ctx*, const t3c_config*, int arith, const uint8_t* raw9, size_t n_words,

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <stdexcept>
 #include <vector>
 
@@ -42,6 +43,7 @@ struct Tile2D { uint16_t w = 0, h = 0; };
 struct ScramblerSeed { uint32_t a = 1, b = 1, s0 = 1; };
 struct SparseBeaconCfg { uint32_t words_period = 0; uint8_t band_slot = 0; bool enabled = false; };
 enum class CosetID : uint8_t { C0 = 0, C1 = 1, C2 = 2 };
+struct BeaconPayload { ProfileID profile; uint16_t frame_seq_mod; uint8_t health_flags; };
 enum class SubwordMode : uint8_t { S27 = 27, S24 = 24, S21 = 21, S18 = 18, S15 = 15 };
 inline int payload_len_for(SubwordMode m) { return (int)m; }
 struct StdRes { uint16_t w, h; };
@@ -125,9 +127,126 @@ inline void from_abi(const t3c_config& c, DecoderConfigSeen& o)
 }
 } // namespace t3c_shim
 
+// ---- L0: GF(27) (OLD:383-487).  The tables come from the library (t3c_gf27_tables: what the device kernels use, built from the
+// field definition at context creation); the members are the reference's look-ups.
+namespace t3c_shim {
+inline const t3c_gf27& gf27()
+{
+    static t3c_gf27 tab;
+    static std::once_flag once;
+    std::call_once(once, [] { if (t3c_gf27_tables(context(), &tab) != T3C_OK) throw std::runtime_error("t3c: GF(27) tables unavailable"); });
+    return tab;
+}
+} // namespace t3c_shim
+inline GF27 gf27_add(GF27 a, GF27 b) { return t3c_shim::gf27().add[(a % 27) * 27 + b % 27]; }
+inline GF27 gf27_sub(GF27 a, GF27 b) { return t3c_shim::gf27().sub[(a % 27) * 27 + b % 27]; }
+inline GF27 gf27_mul_poly(GF27 a, GF27 b) { return t3c_shim::gf27().mul[(a % 27) * 27 + b % 27]; }
+struct GF27Tables {
+    std::array<GF27, 26 * 3> exp{};
+    std::array<int16_t, 27> log{};
+    std::array<GF27, 27 * 27> mul{};
+    std::array<GF27, 27> inv{};
+    GF27 primitive = 0;
+};
+struct GF27Context {
+    GF27Tables tab{};
+    int order_of(GF27 g) const
+    {
+        if (g == 0 || g == 1) return -1;
+        GF27 x = 1;
+        for (int i = 1; i <= 26; ++i) { x = gf27_mul_poly(x, g); if (x == 1) return i; }
+        return -1;
+    }
+    void init()
+    {
+        const t3c_gf27& t = t3c_shim::gf27();
+        std::copy(t.exp, t.exp + 78, tab.exp.begin());
+        std::copy(t.log, t.log + 27, tab.log.begin());
+        std::copy(t.mul, t.mul + 729, tab.mul.begin());
+        std::copy(t.inv, t.inv + 27, tab.inv.begin());
+        tab.primitive = t.primitive;
+    }
+    GF27 add(GF27 a, GF27 b) const { return gf27_add(a, b); }
+    GF27 sub(GF27 a, GF27 b) const { return gf27_sub(a, b); }
+    GF27 mul(GF27 a, GF27 b) const { return tab.mul[a * 27 + b]; }
+    GF27 inv(GF27 a) const { return tab.inv[a]; }
+    GF27 pow_alpha(int e) const { return tab.exp[(e % 26 + 26) % 26]; }
+    int log(GF27 a) const { return tab.log[a]; }
+};
+
+// ---- L1: scrambler, beacon symbol (OLD:81-113); one symbol per call, like the reference (sequences: t3c_scramble_symbols)
+inline GF27 scramble_symbol(GF27 s, const ScramblerSeed& seed, uint32_t& st)
+{
+    t3c_scramble_symbols(t3c_shim::context(), &s, 1, seed.a, seed.b, &st, 0);
+    return s;
+}
+inline GF27 descramble_symbol(GF27 s, const ScramblerSeed& seed, uint32_t& st)
+{
+    t3c_scramble_symbols(t3c_shim::context(), &s, 1, seed.a, seed.b, &st, 1);
+    return s;
+}
+inline GF27 encode_beacon_symbol(const BeaconPayload& b)
+{
+    uint8_t v = 0;
+    t3c_beacon_symbol(t3c_shim::context(), (int)(uint8_t)b.profile, b.frame_seq_mod, b.health_flags, &v);
+    return v;
+}
+
+// ---- L1: super-frame header and its ternary CRC-12 (OLD:155-380)
+struct SuperframeHeader {
+    uint16_t magic = 0x0A2;
+    uint8_t version = 1;
+    ProfileID profile = ProfileID::P2_RS26_22;
+    UEPLayout uep{};
+    Tile2D tile{};
+    ScramblerSeed seed{};
+    uint32_t band_map_hash = 0, frame_seq = 0, reserved = 0, crc3m = 0;
+    SparseBeaconCfg beacon{};
+    SubwordMode subword = SubwordMode::S27;
+    bool centered = true;
+    CosetID coset = CosetID::C0;
+};
+struct HeaderPack { std::array<GF27, 27> symbols{}; };
+struct CRC3 {
+    static constexpr int L = 12;
+    static void rem12(const std::vector<UTrit>& msg, std::array<UTrit, L>& out)
+    {
+        t3c_crc3_rem12(t3c_shim::context(), msg.data(), msg.size(), out.data());
+    }
+};
+struct HeaderCodec {
+    static HeaderPack pack(const SuperframeHeader& h)
+    {
+        t3c_header a{};
+        a.magic = h.magic; a.version = h.version; a.band_map_hash = h.band_map_hash; a.frame_seq = h.frame_seq;
+        a.cfg = t3c_shim::to_abi(h, 8192);
+        HeaderPack p{};
+        t3c_header_pack(t3c_shim::context(), &a, p.symbols.data());
+        return p;
+    }
+    static bool check(const HeaderPack& p)
+    {
+        int ok = 0;
+        return t3c_header_check(t3c_shim::context(), p.symbols.data(), &ok) == T3C_OK && ok != 0;
+    }
+    static SuperframeHeader unpack(const HeaderPack& p)
+    {
+        SuperframeHeader h{};
+        t3c_header a{};
+        if (t3c_header_unpack(t3c_shim::context(), p.symbols.data(), &a) != T3C_OK) return h;
+        h.magic = a.magic; h.version = a.version; h.band_map_hash = a.band_map_hash; h.frame_seq = a.frame_seq;
+        h.profile = (ProfileID)a.cfg.profile;
+        for (int i = 0; i < 9; ++i) h.uep.band_profile[i] = a.cfg.uep[i];
+        h.tile = Tile2D{a.cfg.tile_w, a.cfg.tile_h};
+        h.seed = ScramblerSeed{a.cfg.seed_a, a.cfg.seed_b, a.cfg.seed_s0};
+        h.beacon.words_period = a.cfg.beacon_period; h.beacon.band_slot = a.cfg.beacon_slot; h.beacon.enabled = a.cfg.beacon_enabled != 0;
+        h.subword = (SubwordMode)a.cfg.subword; h.centered = a.cfg.centered != 0; h.coset = (CosetID)a.cfg.coset;
+        return h;
+    }
+};
+
 // RSCodec keeps the reference's block-level interface (OLD:490-663); one call = one device launch, so bulk
 // work should go through t3c_rs_encode_blocks / t3c_rs_decode_blocks or the profile codec instead.
-struct GF27Context { void init() {} };
 struct RSCodec {
     GF27Context* gf = nullptr;
     RSParams params{};
@@ -179,6 +298,31 @@ struct DecoderContext {
         uep_uniform(cfg_last_seen.uep, 1);
     }
 };
+
+// ---- L1: one word at a time (OLD:693-722, 816-833)
+inline void pack_two_pixels(const PixelYCbCrQuant& a, const PixelYCbCrQuant& b, Word27& w)
+{
+    const PixelYCbCrQuant two[2] = {a, b};
+    size_t n = 0;
+    t3c_pack_pixels(t3c_shim::context(), reinterpret_cast<const t3c_pixel*>(two), 2, w.sym.data(), &n);
+}
+inline void unpack_two_pixels(const Word27& w, PixelYCbCrQuant& a, PixelYCbCrQuant& b)
+{
+    PixelYCbCrQuant two[2];
+    t3c_unpack_pixels(t3c_shim::context(), w.sym.data(), 1, reinterpret_cast<t3c_pixel*>(two));
+    a = two[0]; b = two[1];
+}
+inline void extract_subword_trits_from_word(const Word27& w, int N, std::array<UTrit, 27>& out)
+{
+    (void)N; // the reference unpacks all 27 trits whatever N is (OLD:816-826)
+    t3c_subword_stream(t3c_shim::context(), w.sym.data(), 1, 27, out.data());
+}
+inline void inject_subword_trits_into_word(const UTrit* inN, int N, Word27& w, UTrit fill = 0)
+{
+    size_t n = 0;
+    if (N > 0) t3c_words_from_subword_stream(t3c_shim::context(), inN, (size_t)N, N, fill, w.sym.data(), &n);
+    else { const UTrit none = fill; t3c_words_from_subword_stream(t3c_shim::context(), &none, 1, 1, fill, w.sym.data(), &n); } // N = 0: all fill
+}
 
 inline bool encode_raw_pixels_to_words(const std::vector<PixelYCbCrQuant>& px, std::vector<Word27>& out)
 {
@@ -258,10 +402,10 @@ inline bool decode_profile_to_raw(const std::vector<Word27>& in, std::vector<Wor
 // recovered prefix through the consistent decoder.
 inline bool selftest_rs_unit(int arith = T3C_REF_EXACT)
 {
-    uint32_t lcg = 1;
-    auto next = [&]() { lcg = lcg * 1664525u + 1013904223u; return lcg >> 8; };
+    GF27Context gf;
+    gf.init();
+    std::mt19937 rng(1); // the reference's error pattern (OLD:1176,1189-1201): one generator across the four profiles
     for (ProfileID pid : {ProfileID::P1_RS26_24, ProfileID::P2_RS26_22, ProfileID::P3_RS26_20, ProfileID::P4_RS26_18}) {
-        GF27Context gf;
         RSCodec rs;
         rs.init(&gf, rs_params_for(pid));
         rs.arith = arith;
@@ -269,13 +413,13 @@ inline bool selftest_rs_unit(int arith = T3C_REF_EXACT)
         std::vector<GF27> data(k), code(n), outk(k);
         for (int i = 0; i < k; ++i) data[i] = (GF27)((i * 5 + 7) % 27);
         rs.encode_block(data.data(), code.data());
+        std::uniform_int_distribution<int> pos(0, n - 1), val(1, 26);
         std::vector<int> used;
-        while ((int)used.size() < t) {
-            const int p = (int)(next() % (uint32_t)n);
-            if (std::find(used.begin(), used.end(), p) != used.end()) continue;
+        for (int e = 0; e < t; ++e) {
+            int p;
+            do { p = pos(rng); } while (std::find(used.begin(), used.end(), p) != used.end());
             used.push_back(p);
-            const auto a = unpack3(code[p]), b = unpack3((GF27)(1 + next() % 26));
-            code[p] = pack3((UTrit)((a[0] + b[0]) % 3), (UTrit)((a[1] + b[1]) % 3), (UTrit)((a[2] + b[2]) % 3));
+            code[p] = gf.add(code[p], (GF27)val(rng));
         }
         if (!rs.decode_block(code.data(), outk.data())) return false;
         if (outk != data) return false;

@@ -645,6 +645,99 @@ t3c_status t3c_header_parse(t3c_ctx* ctx, int arith, const uint8_t* words, size_
     return T3C_OK;
 }
 
+// ---- L0 / L1 names of the reference's public surface (single items)
+t3c_status t3c_header_pack(t3c_ctx* ctx, const t3c_header* h, uint8_t sym27[27])
+{
+    if (!ctx || !h || !sym27) return fail(ctx, T3C_ERR_ARG, "header_pack: null");
+    DeviceGuard guard(ctx->device);
+    TRY(check_launch(ctx, launch_header_pack(h->cfg, h->magic, h->version, h->band_map_hash, h->frame_seq, ctx->d_mail->hdr27, ctx->stream)));
+    MAIL_DOWN();
+    std::memcpy(sym27, ctx->h_mail->hdr27, 27);
+    return T3C_OK;
+}
+static t3c_status header_check_unpack(t3c_ctx* ctx, const uint8_t sym27[27], t3c_header* out, int* ok)
+{
+    DeviceGuard guard(ctx->device);
+    std::memcpy(ctx->h_mail->hdr27, sym27, 27);
+    std::memset(&ctx->h_mail->cfg, 0, sizeof(t3c_config));
+    ctx->h_mail->cfg.superframe_words = 8192;
+    ctx->h_mail->ok = 0;
+    MAIL_UP();
+    TRY(check_launch(ctx, launch_header_check_unpack(ctx->d_mail->hdr27, &ctx->d_mail->cfg, ctx->d_mail->status, &ctx->d_mail->ok, ctx->stream)));
+    MAIL_DOWN();
+    if (ok) *ok = ctx->h_mail->ok;
+    if (out) {
+        out->magic = (uint16_t)ctx->h_mail->status[0]; out->version = (uint8_t)ctx->h_mail->status[1]; out->pad_ = 0;
+        out->band_map_hash = ctx->h_mail->status[2]; out->frame_seq = ctx->h_mail->status[3];
+        out->cfg = ctx->h_mail->cfg;
+    }
+    return T3C_OK;
+}
+t3c_status t3c_header_check(t3c_ctx* ctx, const uint8_t sym27[27], int* ok)
+{
+    if (!ctx || !sym27 || !ok) return fail(ctx, T3C_ERR_ARG, "header_check: null");
+    return header_check_unpack(ctx, sym27, nullptr, ok);
+}
+t3c_status t3c_header_unpack(t3c_ctx* ctx, const uint8_t sym27[27], t3c_header* out)
+{
+    if (!ctx || !sym27 || !out) return fail(ctx, T3C_ERR_ARG, "header_unpack: null");
+    return header_check_unpack(ctx, sym27, out, nullptr);
+}
+t3c_status t3c_crc3_rem12(t3c_ctx* ctx, const uint8_t* trits, size_t n, uint8_t out12[12])
+{
+    if (!ctx || !out12 || (n && !trits)) return fail(ctx, T3C_ERR_ARG, "crc3_rem12: null");
+    DeviceGuard guard(ctx->device);
+    uint8_t* d_in;
+    TRY(reserve_t(ctx, B_IN, n + 16, &d_in));
+    if (n) H2D(d_in, trits, n);
+    TRY(check_launch(ctx, launch_crc3_rem12(d_in, n, ctx->d_mail->hdr27, ctx->stream)));
+    MAIL_DOWN();
+    std::memcpy(out12, ctx->h_mail->hdr27, 12);
+    return T3C_OK;
+}
+t3c_status t3c_scramble_symbols(t3c_ctx* ctx, uint8_t* syms, size_t n, uint32_t a, uint32_t b, uint32_t* st, int inverse)
+{
+    if (!ctx || !st || (n && !syms)) return fail(ctx, T3C_ERR_ARG, "scramble_symbols: null");
+    if (!n) return T3C_OK;
+    DeviceGuard guard(ctx->device);
+    // the first step takes the caller's state as it is (uint32 arithmetic, OLD:83), the following ones the reduced states
+    uint8_t st8[8];
+    uint32_t s = (a * *st + b) % 3;
+    st8[0] = (uint8_t)s;
+    for (int p = 1; p < 8; ++p) { s = (a * s + b) % 3; st8[p] = (uint8_t)s; }
+    uint8_t* d_io;
+    TRY(reserve_t(ctx, B_IN, n, &d_io));
+    H2D(d_io, syms, n);
+    TRY(check_launch(ctx, launch_scramble(ctx->tabs, d_io, n, st8, inverse, ctx->stream)));
+    D2H(syms, d_io, n);
+    SYNC();
+    *st = n <= 2 ? st8[n - 1] : st8[2 + (n - 3) % 6];
+    return T3C_OK;
+}
+t3c_status t3c_beacon_symbol(t3c_ctx* ctx, int profile, uint32_t frame_seq_mod, uint32_t health_flags, uint8_t* sym)
+{
+    if (!ctx || !sym) return fail(ctx, T3C_ERR_ARG, "beacon_symbol: null");
+    const unsigned p = (uint8_t)profile, s = (uint8_t)((uint16_t)frame_seq_mod % 5), h = (uint8_t)((uint8_t)health_flags % 3);
+    *sym = (uint8_t)((p + 5 * s + 15 * h) % 27);   // metadata arithmetic, OLD:107-113 (the encoder's own beacon symbol is Geom::bsym)
+    return T3C_OK;
+}
+t3c_status t3c_gf27_tables(t3c_ctx* ctx, t3c_gf27* out)
+{
+    if (!ctx || !out || !ctx->host) return fail(ctx, T3C_ERR_ARG, "gf27_tables: null");
+    const GfTables& g = ctx->host->gf;
+    std::memset(out, 0, sizeof *out);
+    for (int i = 0; i < 78; ++i) out->exp[i] = g.exp[i % 26];
+    for (int a = 0; a < 27; ++a) { out->log[a] = g.lg[a] == 255 ? (int16_t)-1 : (int16_t)g.lg[a]; out->inv[a] = g.inv[a]; }
+    for (int a = 0; a < 27; ++a)
+        for (int b = 0; b < 27; ++b) {
+            out->mul[a * 27 + b] = g.mul[a * 27 + b];
+            out->add[a * 27 + b] = g.add[a * 27 + b];
+            out->sub[a * 27 + b] = g.add[a * 27 + g.neg[b]];
+        }
+    out->primitive = g.exp[1];
+    return T3C_OK;
+}
+
 t3c_status t3c_encode_profile(t3c_ctx* ctx, const t3c_config* cfg, int arith, const uint8_t* raw, size_t n_words, uint8_t* out,
                               size_t cap_words, size_t* n_out)
 {

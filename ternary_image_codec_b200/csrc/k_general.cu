@@ -404,12 +404,11 @@ static inline bool small_geom(const Geom& g) { return 27 * g.n_words + 64 < (1ul
 // ------------------------------------------------------------------------------------------
 // K5: super-frame header (OLD:155-380, 1142-1158) -- one warp
 // ------------------------------------------------------------------------------------------
-__device__ void header_symbols(const t3c_config& c, uint32_t frame_seq, uint32_t hash, uint8_t* p)
+__device__ void header_symbols(const t3c_config& c, uint32_t frame_seq, uint32_t hash, uint8_t* p, uint32_t magic = 0x0A2, uint32_t version = 1)
 {
     // HeaderCodec::pack, OLD:208-289.  at(i,v) narrows v to uint8 before %27.
-    const uint32_t magic = 0x0A2;
     for (int i = 0; i < 27; ++i) p[i] = 0;
-    p[0] = magic % 27; p[1] = (magic / 27) % 27; p[2] = 1; p[3] = c.profile % 27;
+    p[0] = magic % 27; p[1] = (magic / 27) % 27; p[2] = (uint8_t)(version % 27) % 27; p[3] = c.profile % 27;
     for (int g = 0; g < 3; ++g) p[4 + g] = (uint8_t)(9 * (c.uep[3 * g] % 3) + 3 * (c.uep[3 * g + 1] % 3) + (c.uep[3 * g + 2] % 3));
     p[7] = c.tile_w % 27; p[8] = c.tile_h % 27;
     p[9] = c.seed_a % 27; p[10] = c.seed_b % 27; p[11] = c.seed_s0 % 27;
@@ -463,6 +462,69 @@ __device__ void header_emit_warp(const t3c_config& c, int arith, const GfTables*
 __global__ void k_header_emit(t3c_config cfg, int arith, const GfTables* gf, const RsTables* rs, uint8_t* hdr27, uint8_t* coded52)
 {
     header_emit_warp(cfg, arith, gf, rs, hdr27, coded52);
+}
+
+// HeaderCodec::pack / check / unpack on one 27-symbol header (OLD:208-379), CRC3::rem12 on a trit string (OLD:176-205): the L1 names
+// of the reference's public surface, one thread each (they exist for drop-in callers and tests, not for throughput)
+__global__ void k_header_pack(t3c_config cfg, uint32_t magic, uint32_t version, uint32_t hash, uint32_t seq, uint8_t* hdr27)
+{
+    uint8_t p[27], r[12];
+    header_symbols(cfg, seq, hash, p, magic, version);
+    header_crc(p, r);
+    p[20] = r[0] + 3 * r[1] + 9 * r[2]; p[21] = r[3] + 3 * r[4] + 9 * r[5];
+    p[22] = r[6] + 3 * r[7] + 9 * r[8]; p[26] = r[9] + 3 * r[10] + 9 * r[11];
+    for (int i = 0; i < 27; ++i) hdr27[i] = p[i];
+}
+// out4 = {magic, version, band_map_hash, frame_seq}; *ok = HeaderCodec::check; unpack fills cfg whether or not the CRC holds (as the reference's unpack does)
+__global__ void k_header_check_unpack(const uint8_t* __restrict__ sym27, t3c_config* cfg, uint32_t* out4, int* ok)
+{
+    uint8_t p[27], r[12];
+    for (int i = 0; i < 27; ++i) p[i] = sym27[i];
+    header_crc(p, r);   // unpack3 on the symbols as they are (OLD:296): digits of p[i] mod 27
+    bool good = true;
+    const int slots[4] = {20, 21, 22, 26};
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t s = p[slots[i]];
+        good = good && s % 3 == r[3 * i] && (s / 3) % 3 == r[3 * i + 1] && (s / 9) % 3 == r[3 * i + 2];
+    }
+    *ok = good ? 1 : 0;
+    for (int i = 0; i < 27; ++i) p[i] %= 27;  // rd(i) = symbols[i] % 27, OLD:324
+    t3c_config h = *cfg;
+    h.profile = p[3] % 5;
+    for (int g = 0; g < 3; ++g) { const uint32_t v = p[4 + g]; h.uep[3 * g] = v % 3; h.uep[3 * g + 1] = (v / 3) % 3; h.uep[3 * g + 2] = (v / 9) % 3; }
+    h.tile_w = p[7]; h.tile_h = p[8];
+    h.seed_a = p[9]; h.seed_b = p[10]; h.seed_s0 = p[11];
+    const uint32_t sub = p[12] % 9, cen = (p[12] / 9) % 3;
+    h.subword = sub == 1 ? 24 : sub == 2 ? 21 : sub == 3 ? 18 : sub == 4 ? 15 : 27;
+    h.centered = cen != 0;
+    h.coset = p[16] % 3;
+    h.beacon_enabled = p[23] != 0; h.beacon_slot = p[24] % 9; h.beacon_period = p[25];
+    *cfg = h;
+    out4[0] = p[0] + 27u * p[1]; out4[1] = p[2]; out4[2] = p[13] + 27u * p[14] + 729u * p[15]; out4[3] = p[17] + 27u * p[18] + 729u * p[19];
+}
+__global__ void k_crc3_rem12(const uint8_t* __restrict__ trits, size_t n, uint8_t* out12)
+{
+    uint8_t r[12];
+    for (int i = 0; i < 12; ++i) r[i] = 0;
+    for (size_t q = 0; q < n + 12; ++q) {
+        const uint32_t in = q < n ? trits[q] : 0u;   // the reference adds the trit as it is and reduces mod 3 (OLD:184)
+        const uint32_t fb = (in + r[11]) % 3;
+        uint8_t nx[12] = {(uint8_t)fb, r[0], r[1], (uint8_t)((r[2] + fb) % 3), (uint8_t)((r[3] + fb) % 3), r[4], r[5],
+                          (uint8_t)((r[6] + fb) % 3), r[7], r[8], r[9], r[10]};
+        for (int i = 0; i < 12; ++i) r[i] = nx[i];
+    }
+    for (int i = 0; i < 12; ++i) out12[i] = r[i];
+}
+// scramble_symbol / descramble_symbol (OLD:81-94) applied to a sequence: symbol i sees the state after i + 1 steps of st <- (a*st + b) % 3
+// (st8: the eventually periodic state sequence, scrambler_states)
+struct ScrStates { uint8_t st[8]; };
+__global__ void k_scramble(uint8_t* __restrict__ syms, size_t n, ScrStates S, const GfTables* __restrict__ gf, int inverse)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t st = i < 2 ? S.st[i] : S.st[2 + (i - 2) % 6];
+    const uint32_t s = syms[i] % 27u;
+    syms[i] = inverse ? gf->dsc[st][s] : gf->scr[st][s];
 }
 
 // read_and_decode_header_from_words (OLD:918-937) + HeaderCodec::check/unpack (OLD:290-379)
@@ -796,6 +858,29 @@ int launch_perm2d(const uint8_t* in, uint8_t* out, size_t n, uint32_t w, uint32_
 int launch_header_emit(const DevTables& T, const t3c_config& cfg, int arith, uint8_t* hdr27, uint8_t* coded52, cudaStream_t st)
 {
     k_header_emit<<<1, 32, 0, st>>>(cfg, arith ? 1 : 0, T.gf, T.rs, hdr27, coded52);
+    return 1;
+}
+int launch_header_pack(const t3c_config& cfg, uint32_t magic, uint32_t version, uint32_t hash, uint32_t seq, uint8_t* d_hdr27, cudaStream_t st)
+{
+    k_header_pack<<<1, 1, 0, st>>>(cfg, magic, version, hash, seq, d_hdr27);
+    return 1;
+}
+int launch_header_check_unpack(const uint8_t* d_sym27, t3c_config* d_cfg, uint32_t* d_out4, int* d_ok, cudaStream_t st)
+{
+    k_header_check_unpack<<<1, 1, 0, st>>>(d_sym27, d_cfg, d_out4, d_ok);
+    return 1;
+}
+int launch_crc3_rem12(const uint8_t* d_trits, size_t n, uint8_t* d_out12, cudaStream_t st)
+{
+    k_crc3_rem12<<<1, 1, 0, st>>>(d_trits, n, d_out12);
+    return 1;
+}
+int launch_scramble(const DevTables& T, uint8_t* d_syms, size_t n, const uint8_t st8[8], int inverse, cudaStream_t st)
+{
+    if (!n) return 0;
+    ScrStates S;
+    for (int i = 0; i < 8; ++i) S.st[i] = st8[i];
+    k_scramble<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_syms, n, S, T.gf, inverse);
     return 1;
 }
 int launch_header_parse(const DevTables& T, int arith, const uint8_t* words, size_t n_words, t3c_config* d_cfg, int* d_ok, cudaStream_t st)

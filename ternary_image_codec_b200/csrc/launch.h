@@ -54,6 +54,11 @@ int launch_rs_decode_blocks(const DevTables& T, int k, int arith, uint8_t* inout
 int launch_perm2d(const uint8_t* in, uint8_t* out, size_t n, uint32_t w, uint32_t h, cudaStream_t st);
 int launch_header_emit(const DevTables& T, const t3c_config& cfg, int arith, uint8_t* d_hdr27, uint8_t* d_coded52, cudaStream_t st);
 int launch_header_parse(const DevTables& T, int arith, const uint8_t* d_words9, size_t n_words, t3c_config* d_cfg, int* d_ok, cudaStream_t st);
+// L1 names of the reference's public surface (OLD:81-94, 176-205, 208-379), single items
+int launch_header_pack(const t3c_config& cfg, uint32_t magic, uint32_t version, uint32_t hash, uint32_t seq, uint8_t* d_hdr27, cudaStream_t st);
+int launch_header_check_unpack(const uint8_t* d_sym27, t3c_config* d_cfg, uint32_t* d_out4, int* d_ok, cudaStream_t st);
+int launch_crc3_rem12(const uint8_t* d_trits, size_t n, uint8_t* d_out12, cudaStream_t st);
+int launch_scramble(const DevTables& T, uint8_t* d_syms, size_t n, const uint8_t st8[8], int inverse, cudaStream_t st);
 // general profile codec (any config)
 int launch_encode_general(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* raw9, uint8_t* out9, cudaStream_t st, uint64_t cw_start = 0);
 // scratch_sy is band-major: decoded data symbol m of band b at b*pitch + m (pitch >= ceil(n_s / 9))

@@ -131,6 +131,60 @@ int main()
     deinterleave2D_boustrophedon(sy, Tile2D{7, 5});
     std::printf("dil2d %016llx\n", (unsigned long long)fnv(sy.data(), sy.size()));
 
+    // ---- L0 / L1 public names (OLD:81-113, 155-380, 383-487, 693-722, 816-833)
+    {
+        uint64_t h = 1469598103934665603ull;
+        for (int a = 0; a < 27; ++a)
+            for (int b = 0; b < 27; ++b) {
+                const uint8_t v[5] = {gf27_add((GF27)a, (GF27)b), gf27_sub((GF27)a, (GF27)b), gf27_mul_poly((GF27)a, (GF27)b), gf.mul((GF27)a, (GF27)b), gf.add((GF27)a, (GF27)b)};
+                h = fnv(v, 5, h);
+            }
+        for (int a = 0; a < 27; ++a) { const int16_t v[3] = {(int16_t)gf.inv((GF27)a), (int16_t)gf.log((GF27)a), (int16_t)gf.pow_alpha(a * 7 - 40)}; h = fnv(v, sizeof v, h); }
+        std::printf("gf27 prim=%d order3=%d %016llx\n", (int)gf.tab.primitive, gf.order_of(3), (unsigned long long)h);
+    }
+    {
+        const ScramblerSeed seeds[3] = {{1, 1, 1}, {2, 1, 1}, {4000000007u, 3000000001u, 5}};
+        for (const auto& sd : seeds) {
+            uint32_t st = sd.s0, st2 = sd.s0;
+            std::vector<GF27> a(40), b(40);
+            for (int i = 0; i < 40; ++i) { a[i] = scramble_symbol((GF27)((i * 11) % 27), sd, st); b[i] = descramble_symbol(a[i], sd, st2); }
+            std::printf("scramble %016llx %016llx st=%u,%u\n", (unsigned long long)fnv(a.data(), 40), (unsigned long long)fnv(b.data(), 40), st, st2);
+        }
+        const BeaconPayload bp{ProfileID::P5_RS26_22_2D, 8192 % 5 + 10, 7};
+        std::printf("beacon %d %d\n", (int)encode_beacon_symbol(bp), (int)encode_beacon_symbol(BeaconPayload{ProfileID::P2_RS26_22, 2, 0}));
+    }
+    {
+        SuperframeHeader hd;
+        hd.profile = ProfileID::P5_RS26_22_2D; uep_luma_priority(hd.uep); hd.tile = {26, 7}; hd.seed = {2, 30, 55}; hd.band_map_hash = 12345; hd.frame_seq = 6789;
+        hd.beacon = {83, 11, true}; hd.subword = SubwordMode::S21; hd.centered = false; hd.coset = CosetID::C2;
+        HeaderPack hp = HeaderCodec::pack(hd);
+        const SuperframeHeader u = HeaderCodec::unpack(hp);
+        std::printf("header %016llx check=%d magic=%u ver=%u prof=%d uep=%d%d%d%d%d%d%d%d%d tile=%u,%u seed=%u,%u,%u hash=%u seq=%u beacon=%d,%u,%u sub=%d cen=%d coset=%d\n",
+                    (unsigned long long)fnv(hp.symbols.data(), 27), (int)HeaderCodec::check(hp), u.magic, u.version, (int)u.profile, u.uep.band_profile[0], u.uep.band_profile[1],
+                    u.uep.band_profile[2], u.uep.band_profile[3], u.uep.band_profile[4], u.uep.band_profile[5], u.uep.band_profile[6], u.uep.band_profile[7], u.uep.band_profile[8],
+                    u.tile.w, u.tile.h, u.seed.a, u.seed.b, u.seed.s0, u.band_map_hash, u.frame_seq, (int)u.beacon.enabled, (unsigned)u.beacon.band_slot, u.beacon.words_period,
+                    (int)u.subword, (int)u.centered, (int)u.coset);
+        hp.symbols[5] = (GF27)((hp.symbols[5] + 1) % 27);
+        std::printf("header damaged check=%d default %016llx\n", (int)HeaderCodec::check(hp), (unsigned long long)fnv(HeaderCodec::pack(SuperframeHeader{}).symbols.data(), 27));
+        std::vector<UTrit> msg(69);
+        for (size_t i = 0; i < msg.size(); ++i) msg[i] = (UTrit)(lcg() % 3);
+        std::array<UTrit, CRC3::L> rem{};
+        CRC3::rem12(msg, rem);
+        std::printf("crc3 %016llx\n", (unsigned long long)fnv(rem.data(), rem.size()));
+    }
+    {
+        Word27 w{};
+        PixelYCbCrQuant a{200, -17, 33}, b{7, 40, -40}, c, d;
+        pack_two_pixels(a, b, w);
+        unpack_two_pixels(w, c, d);
+        std::array<UTrit, 27> tr{};
+        extract_subword_trits_from_word(w, 15, tr);
+        Word27 w2{};
+        inject_subword_trits_into_word(tr.data(), 15, w2, (UTrit)2);
+        std::printf("pair %016llx %u,%d,%d %u,%d,%d trits %016llx inject %016llx\n", (unsigned long long)fnv(w.sym.data(), 9), c.Yq, c.Cbq, c.Crq, d.Yq, d.Cbq, d.Crq,
+                    (unsigned long long)fnv(tr.data(), 27), (unsigned long long)fnv(w2.sym.data(), 9));
+    }
+
     std::printf("selftests RS:%s API:%s\n", selftest_rs_unit() ? "OK" : "FAIL", selftest_api_roundtrip() ? "OK" : "FAIL");
     return 0;
 }
