@@ -63,7 +63,7 @@ _EXPORTS = [
     "t3c_kernel_launches", "t3c_profile_words", "t3c_rgb_to_quant", "t3c_quant_to_rgb", "t3c_pack_pixels",
     "t3c_unpack_pixels", "t3c_words_to_bytes", "t3c_rs_encode_blocks", "t3c_rs_decode_blocks", "t3c_interleave2d",
     "t3c_header_emit", "t3c_header_parse", "t3c_header_pack", "t3c_header_check", "t3c_header_unpack", "t3c_crc3_rem12",
-    "t3c_scramble_symbols", "t3c_beacon_symbol", "t3c_gf27_tables", "t3c_encode_profile", "t3c_decode_profile", "t3c_decode_profile_fixed",
+    "t3c_scramble_symbols", "t3c_beacon_symbol", "t3c_gf27_tables", "t3c_t3v_index_build", "t3c_encode_profile", "t3c_decode_profile", "t3c_decode_profile_fixed",
     "t3c_encode_frames_rgb8", "t3c_decode_frames_rgb8", "t3c_rgb_to_quant_dev", "t3c_quant_to_rgb_dev",
     "t3c_pack_pixels_dev", "t3c_unpack_pixels_dev", "t3c_rs_encode_blocks_dev", "t3c_rs_decode_blocks_dev",
     "t3c_encode_profile_dev", "t3c_decode_profile_fixed_dev", "t3c_encode_frames_rgb8_dev",
@@ -124,6 +124,7 @@ def load_library() -> C.CDLL:
     L.t3c_scramble_symbols.argtypes = [vp, u8p, sz, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), i32]
     L.t3c_beacon_symbol.argtypes = [vp, i32, C.c_uint32, C.c_uint32, u8p]
     L.t3c_gf27_tables.argtypes = [vp, vp]
+    L.t3c_t3v_index_build.argtypes = [vp, vp, sz, C.c_uint64, u8p, szp]
     L.t3c_encode_profile.argtypes = [vp, cfgp, i32, u8p, sz, u8p, sz, szp]
     L.t3c_decode_profile.argtypes = [vp, cfgp, u8p, sz, u8p, sz, szp, C.POINTER(i32)]
     L.t3c_decode_profile_fixed.argtypes = [vp, cfgp, sz, u8p, sz, u8p, sz, szp, C.POINTER(i32), szp]

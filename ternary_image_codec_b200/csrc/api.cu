@@ -1167,6 +1167,26 @@ t3c_status t3c_crc32(t3c_ctx* ctx, const uint8_t* data, size_t n, uint32_t* crc)
     *crc = ctx->h_mail->status[0];
     return T3C_OK;
 }
+t3c_status t3c_t3v_index_build(t3c_ctx* ctx, const uint64_t* n_words, size_t n_frames, uint64_t first_offset, uint8_t* out, size_t* n_bytes)
+{
+    if (!ctx || !out || !n_bytes || (n_frames && !n_words)) return fail(ctx, T3C_ERR_ARG, "t3v_index_build: null");
+    if (n_frames > 0xFFFFFFFFull) return fail(ctx, T3C_ERR_ARG, "t3v_index_build: the frame count is a uint32");
+    uint8_t h[17] = {'T', '3', 'V', 'I', 1};
+    const uint32_t cnt = (uint32_t)n_frames, zero = 0;
+    std::memcpy(h + 5, &cnt, 4); std::memcpy(h + 9, &zero, 4);
+    uint32_t crc = 0;
+    TRY(t3c_crc32(ctx, h, 13, &crc));          // device CRC-32, as for the .t3v header
+    std::memcpy(h + 13, &crc, 4);
+    std::memcpy(out, h, 17);
+    uint64_t off = first_offset;                // record i = 4 + 9 n_i + 4 bytes (t3v_write_frame, old/include/t3v_io.hpp:128-142)
+    for (size_t i = 0; i < n_frames; ++i) {
+        if (n_words[i] > 0xFFFFFFFFull) return fail(ctx, T3C_ERR_ARG, "t3v_index_build: a record's count is a uint32");
+        std::memcpy(out + 17 + 8 * i, &off, 8);
+        off += 8 + 9 * n_words[i];
+    }
+    *n_bytes = 17 + 8 * n_frames;
+    return T3C_OK;
+}
 t3c_status t3c_t3v_frame_record(t3c_ctx* ctx, const uint8_t* words, size_t n_words, uint8_t* record, size_t* n_bytes)
 {
     if (!ctx || !record || !n_bytes || (n_words && !words)) return fail(ctx, T3C_ERR_ARG, "t3v_frame_record: null");

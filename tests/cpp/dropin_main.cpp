@@ -6,11 +6,15 @@
 // and tests/test_dropin_cpp.py requires the two programs to print identical lines.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "ternary_image_codec_v6_min.hpp"
 #include "ternary_packing.hpp"
 #include "t3v_io.hpp"
+#include "t3v_indexed_io.hpp"
 
 static uint64_t fnv(const void* p, size_t n, uint64_t h = 1469598103934665603ull)
 {
@@ -96,6 +100,23 @@ int main()
                     t3v_header_aw(hb).x0, t3v_header_aw(hb).y0, t3v_header_aw(hb).w, t3v_header_aw(hb).h, (int)b1, r1.size(),
                     (unsigned long long)fnv(r1.data(), r1.size() * 9), (int)b2, r2.size(), (unsigned long long)fnv(r2.data(), r2.size() * 9), (int)b3, r3.size());
         std::fclose(f);
+        // the index sidecar (old/include/t3v_indexed_io.hpp): scan the file just written, read the index back
+        {
+            char tn[] = "/tmp/t3c_dropin_XXXXXX";
+            const int fd = mkstemp(tn);
+            FILE* tf = fdopen(fd, "wb");
+            std::fwrite(all.data(), 1, got, tf);
+            std::fclose(tf);
+            const std::string t3v = tn, idx = t3v + ".t3vi";
+            const bool sok = t3v_scan_and_index(t3v, idx);
+            T3VIndexBin ib{};
+            std::vector<uint64_t> offs;
+            const bool rok = t3v_index_read(idx, ib, offs);
+            std::printf("t3vi %d %d count=%u crc=%08x offs=%zu %016llx\n", (int)sok, (int)rok, ib.frame_count, ib.header_crc32, offs.size(),
+                        (unsigned long long)fnv(offs.data(), offs.size() * 8));
+            std::remove(t3v.c_str());
+            std::remove(idx.c_str());
+        }
         // a damaged record is rejected
         all[54 + 4 + 100] ^= 1;
         FILE* g = std::tmpfile();
