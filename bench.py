@@ -382,6 +382,34 @@ def run_ours(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # the ceiling of that figure on this box, in this run: the same bytes as one step (pixels + words each way) as plain pinned
+        # copies, H2D and D2H at once on two streams, all ranks at the same time, max over ranks -- no kernels, no pipeline
+        step_bytes = 3 * n_px + 9 * wpf
+        p_src = torch.empty(step_bytes, dtype=torch.uint8).pin_memory()
+        p_dst = torch.empty(step_bytes, dtype=torch.uint8).pin_memory()
+        d_a = torch.empty(step_bytes, dtype=torch.uint8, device=dev)
+        d_b = torch.empty(step_bytes, dtype=torch.uint8, device=dev)
+        cs1, cs2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def plain_copy():
+            with torch.cuda.stream(cs1):
+                d_a.copy_(p_src, non_blocking=True)
+            with torch.cuda.stream(cs2):
+                p_dst.copy_(d_b, non_blocking=True)
+        plain_copy()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(6):
+            plain_copy()
+        torch.cuda.synchronize()
+        dt_copy = (time.perf_counter() - t0) / 6
+        if world > 1:
+            t = torch.tensor([dt_copy], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_copy = float(t.item())
+        del p_src, p_dst, d_a, d_b
         chk_host = chk.cpu()
         for ln in lanes:
             assert torch.equal(ln.back.view(-1), chk_host), "e2e round trip mismatch"
@@ -393,6 +421,9 @@ def run_ours(args):
                "h2d_bytes_per_step": 3 * n_px + 9 * wpf, "d2h_bytes_per_step": 9 * wpf + 3 * n_px,
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "serial_ms_per_step": 1e3 * dt_serial,
                "lanes": n_lanes,
+               "plain_copy_ceiling": {"ms_per_step": 1e3 * dt_copy, "value": world * n_px / dt_copy / 1e6, "unit": UNIT,
+                                      "how": "the step's bytes (pixels + words) as plain pinned copies, H2D and D2H concurrently on two streams, all ranks at once, max over ranks"},
+               "frac_of_plain_copy_ceiling": (world * n_px * e2e_steps / dt) / (world * n_px / dt_copy),
                "how": "host-buffer C ABI, pinned memory; chunked H2D/kernel/D2H pipeline inside each call; per lane an encoder and a decoder context on two host threads (frame i encodes while frame i-1 decodes); the lanes work on independent frames"}
 
     # ---- BASELINE config 4: 240-frame synthetic 8K stream, frame f -> rank f mod world, device-resident, max over ranks
@@ -404,7 +435,8 @@ def run_ours(args):
     spot_out = back[0][:3 * nchk].cpu().numpy().reshape(-1, 3)
     del rgb, enc, back, q, chk
     torch.cuda.empty_cache()
-    my_frames = len(range(rank, 240, world))
+    from ternary_image_codec_b200 import sharding
+    my_frames = len(sharding.frames_for_rank(240, rank, world))
     if world > 1:
         dist.barrier()
     st4 = S2.stream240(sctx, frames_per_call=min(8, my_frames), n_frames=my_frames)
@@ -422,6 +454,45 @@ def run_ours(args):
             secondary.update(S2.secondary_single_gpu(sctx))
         except Exception as e:  # the headline must not depend on the secondary workloads
             secondary["error"] = repr(e)
+        torch.cuda.empty_cache()
+        try:   # single-process multi-device call (t3c_stream_*): frame f -> device f mod N from host threads, pinned host buffers, results in order
+            n_dev = min(world, torch.cuda.device_count())
+            lanes_per_dev = 2 if n_dev <= 2 else 1
+            stream = t3.Stream([d for d in range(n_dev)] * lanes_per_dev)
+            nf = 8 * max(1, n_dev // 2)
+            h_in = torch.randint(0, 256, (nf, n_px, 3), dtype=torch.uint8).pin_memory()
+            h_words = torch.empty((nf, wpf, 9), dtype=torch.uint8).pin_memory()
+            h_out = torch.empty((nf, n_px, 3), dtype=torch.uint8).pin_memory()
+            okv = np.zeros(nf, np.uint8)
+            import ctypes as C
+            got, ncv = C.c_size_t(), C.c_size_t()
+
+            def stream_pass():
+                a = stream.lib.t3c_stream_encode_rgb8(stream.h, C.byref(cfg), t3.FIXED, h_in.data_ptr(), n_px, nf, 0, h_words.data_ptr(), wpf, C.byref(got))
+                b = stream.lib.t3c_stream_decode_rgb8(stream.h, C.byref(cfg), h_words.data_ptr(), wpf, wpf, nf, 0, n_px, h_out.data_ptr(), okv.ctypes.data, C.byref(ncv))
+                assert a == 0 and b == 0 and okv.all()
+            stream_pass()
+            t0 = time.perf_counter()
+            stream_pass()
+            stream_pass()
+            dts = (time.perf_counter() - t0) / 2
+            secondary["config4_stream_api_e2e"] = {
+                "workload": f"t3c_stream_encode_rgb8 + t3c_stream_decode_rgb8: {nf} 8K frames per call from pinned host memory, one process, {n_dev} device(s) x {lanes_per_dev} lane(s), "
+                            "frame f -> lane f mod n, host threads, results in frame order", "frames": nf, "ms": 1e3 * dts, "frames_per_s": nf / dts, "mpix_per_s": nf * n_px / dts / 1e6}
+            stream.close()
+            del h_in, h_words, h_out
+        except Exception as e:
+            secondary["config4_stream_api_e2e"] = {"error": repr(e)}
+        try:   # the reference's own call chain through the std::vector drop-in headers (pageable memory), built here with g++
+            exe = os.path.join(ROOT, "tools", "_e2e_vector_api")
+            pkg = os.path.join(ROOT, "ternary_image_codec_b200")
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "e2e_vector_api.cpp"),
+                                   "-L" + pkg, "-lt3c", "-Wl,-rpath," + pkg, "-o", exe])
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(local))
+            r = subprocess.run([exe, "6"], capture_output=True, text=True, timeout=300, env=env)
+            secondary["vector_api_e2e"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.stdout.strip() else {"error": r.stderr[-300:]}
+        except Exception as e:
+            secondary["vector_api_e2e"] = {"error": repr(e)}
     if world > 1:
         dist.barrier()
 

@@ -35,7 +35,7 @@ extern "C" {
 inline void rgb_to_quant_stream(const ImageU8& rgb, std::vector<PixelYCbCrQuant>& out)
 {
     const size_t n = (size_t)rgb.w * (size_t)rgb.h;
-    out.assign(n, PixelYCbCrQuant{});
+    t3c_shim::size_for_output(out, n);
     if (n) t3c_rgb_to_quant(t3c_shim::context(), rgb.data.data(), n, reinterpret_cast<t3c_pixel*>(out.data()));
 }
 
@@ -43,7 +43,7 @@ inline void quant_stream_to_rgb(const std::vector<PixelYCbCrQuant>& q, int w, in
 {
     out.w = w; out.h = h; out.c = 3;
     const size_t n = (size_t)w * (size_t)h;
-    out.data.assign(n * 3, 0);
+    t3c_shim::size_for_output(out.data, n * 3);
     if (n) t3c_quant_to_rgb(t3c_shim::context(), reinterpret_cast<const t3c_pixel*>(q.data()), n, out.data.data());
 }
 

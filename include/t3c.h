@@ -72,6 +72,12 @@ typedef struct { uint16_t Yq; int16_t Cbq, Crq; } t3c_pixel; /* PixelYCbCrQuant 
 T3C_API t3c_status  t3c_create(int device, t3c_ctx** out);      /* EncoderContext()/DecoderContext() ctor work, OLD:885-916 */
 T3C_API void        t3c_destroy(t3c_ctx* ctx);
 T3C_API const char* t3c_last_error(const t3c_ctx* ctx);
+/* Host-buffer calls copy through PCIe in chunks that overlap with the kernels; with PAGEABLE buffers every copy is staged by the driver
+ * and blocks (an 8K encode + decode drops from 7.9 to 43.8 ms).  mode = 1: a pageable buffer of 8 MiB or more that is passed a second
+ * time (same address and size) is page-locked in place (cudaHostRegister, ~170 us per MB once) and stays so until it falls out of a
+ * 16-entry LRU or the context is destroyed; do not free such a buffer while a call that uses it is running.  mode = 0 (default): never.
+ * The C++ drop-in headers switch it on for their shared context (std::vector storage is pageable). */
+T3C_API t3c_status  t3c_set_host_registration(t3c_ctx* ctx, int mode);
 T3C_API int         t3c_version(void);
 T3C_API void        t3c_config_default(t3c_config* cfg);        /* EncoderConfig defaults + uep_uniform(1), OLD:862-873,898 */
 T3C_API void*       t3c_stream(t3c_ctx* ctx);                   /* the context's cudaStream_t */
@@ -170,6 +176,10 @@ T3C_API t3c_status t3c_decode_frames_rgb8(t3c_ctx*, const t3c_config*, const uin
                                           uint8_t* ok, size_t* px_recovered, size_t* n_corrected);
 
 /* ---- device-pointer variants (bench / pipelines: PCIe outside the timed region) ------------- */
+/* The _dev calls enqueue on `stream` and return; they never wait for the device EXCEPT when they have to change context-wide state: the
+ * first use of a config (the coded header / the pass maps of the super-tile kernels are built once and cached: one stream or device
+ * synchronisation) and the growth of the context's scratch buffers.  They are therefore not safe under stream capture.  Scratch is per
+ * context: a call on another stream than the previous one is ordered after it by an event. */
 T3C_API t3c_status t3c_rgb_to_quant_dev(t3c_ctx*, const uint8_t* d_rgb, size_t n_px, t3c_pixel* d_out, void* stream);
 T3C_API t3c_status t3c_quant_to_rgb_dev(t3c_ctx*, const t3c_pixel* d_px, size_t n_px, uint8_t* d_rgb, void* stream);
 T3C_API t3c_status t3c_pack_pixels_dev(t3c_ctx*, const t3c_pixel* d_px, size_t n_px, uint8_t* d_words9, void* stream);
@@ -262,6 +272,22 @@ T3C_API t3c_status t3c_v6new_image_to_words(t3c_ctx*, const uint8_t* rgb, int w,
 /* words_to_image_subword before the file write, :304-338: words -> pixels; as many as w*h: that image; a full 7680x4320 canvas (subword != 27):
  * its centre window of std_res_for(subword), poured row-major into w x h; anything else: poured into w x h as far as it goes (the rest black) */
 T3C_API t3c_status t3c_v6new_words_to_image(t3c_ctx*, const uint32_t* words, size_t n_words, int subword, int w, int h, uint8_t* rgb, int* ok);
+
+/* ---- multi-device streams (old/src/main_video_t3v.cpp:19-26 for a whole stream; BASELINE config 4) ---------------------------------
+ * A stream owns one context per listed device (a device may be listed more than once: several lanes on one GPU).  Frame f of a call
+ * is coded on lane (first_frame + f) % n_lanes by that lane's own host thread through the chunked host-buffer pipeline; frames are
+ * independent (one super-frame per frame, no state between them), every lane writes its frames at their place in the caller's
+ * output, so the result is in frame order when the call returns.  No collective, no device-to-device traffic. */
+typedef struct t3c_streamset t3c_streamset;
+T3C_API t3c_status t3c_stream_create(const int* devices, int n_lanes, t3c_streamset** out);
+T3C_API void       t3c_stream_destroy(t3c_streamset*);
+T3C_API int        t3c_stream_lanes(const t3c_streamset*);
+/* n_frames RGB8 frames of n_px pixels, contiguous -> profile words, frame f at out + 9 * stride_words * f */
+T3C_API t3c_status t3c_stream_encode_rgb8(t3c_streamset*, const t3c_config*, int arith, const uint8_t* rgb, size_t n_px, size_t n_frames, size_t first_frame,
+                                          uint8_t* out9, size_t stride_words, size_t* words_per_frame);
+/* the inverse (consistent decoder); ok[f] per frame, *n_corrected summed over the frames */
+T3C_API t3c_status t3c_stream_decode_rgb8(t3c_streamset*, const t3c_config*, const uint8_t* in9, size_t words_per_frame, size_t stride_words, size_t n_frames,
+                                          size_t first_frame, size_t n_px, uint8_t* rgb, uint8_t* ok, size_t* n_corrected);
 
 #ifdef __cplusplus
 }

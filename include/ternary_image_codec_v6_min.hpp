@@ -101,6 +101,7 @@ inline t3c_ctx* context(int device = 0)
     if (!ctxs[device]) {
         const t3c_status st = t3c_create(device, &ctxs[device]);
         if (st != T3C_OK) throw std::runtime_error(st == T3C_ERR_NODEVICE ? "t3c: no CUDA device (there is no CPU fallback)" : "t3c: context creation failed");
+        t3c_set_host_registration(ctxs[device], 1); // std::vector storage is pageable: page-lock the buffers that come back (t3c.h)
     }
     return ctxs[device];
 }
@@ -324,16 +325,21 @@ inline void inject_subword_trits_into_word(const UTrit* inN, int N, Word27& w, U
     else { const UTrit none = fill; t3c_words_from_subword_stream(t3c_shim::context(), &none, 1, 1, fill, w.sym.data(), &n); } // N = 0: all fill
 }
 
+// Outputs are sized, not cleared and refilled: the library overwrites every element, and a caller that passes the same vector again
+// keeps its storage (no 100+ MB of zero fill per 8K frame, and the buffer can stay page-locked: t3c_set_host_registration)
+namespace t3c_shim {
+template <class V> inline void size_for_output(V& v, size_t n) { if (v.size() != n) v.resize(n); }
+} // namespace t3c_shim
 inline bool encode_raw_pixels_to_words(const std::vector<PixelYCbCrQuant>& px, std::vector<Word27>& out)
 {
-    out.assign((px.size() + 1) / 2, Word27{});
+    t3c_shim::size_for_output(out, (px.size() + 1) / 2);
     size_t n = 0;
     return t3c_pack_pixels(t3c_shim::context(), reinterpret_cast<const t3c_pixel*>(px.data()), px.size(),
                            reinterpret_cast<uint8_t*>(out.data()), &n) == T3C_OK;
 }
 inline bool decode_raw_words_to_pixels(const std::vector<Word27>& in, std::vector<PixelYCbCrQuant>& out)
 {
-    out.assign(in.size() * 2, PixelYCbCrQuant{});
+    t3c_shim::size_for_output(out, in.size() * 2);
     return t3c_unpack_pixels(t3c_shim::context(), reinterpret_cast<const uint8_t*>(in.data()), in.size(),
                              reinterpret_cast<t3c_pixel*>(out.data())) == T3C_OK;
 }
@@ -363,9 +369,8 @@ inline void build_words_from_subword_stream(const std::vector<UTrit>& in, int N,
 
 inline bool encode_profile_from_raw(const std::vector<Word27>& in, std::vector<Word27>& out, EncoderContext& ectx)
 {
-    out.clear();
     const t3c_config cfg = t3c_shim::to_abi(ectx.cfg, ectx.cfg.superframe_words);
-    out.assign(t3c_profile_words(&cfg, in.size()), Word27{});
+    t3c_shim::size_for_output(out, t3c_profile_words(&cfg, in.size()));
     size_t n = 0;
     const t3c_status st = t3c_encode_profile(t3c_shim::context(ectx.device), &cfg, ectx.arith, reinterpret_cast<const uint8_t*>(in.data()),
                                              in.size(), reinterpret_cast<uint8_t*>(out.data()), out.size(), &n);
@@ -374,26 +379,24 @@ inline bool encode_profile_from_raw(const std::vector<Word27>& in, std::vector<W
 }
 inline bool decode_profile_to_raw(const std::vector<Word27>& in, std::vector<Word27>& out, DecoderContext& dctx)
 {
-    out.clear();
     t3c_ctx* ctx = t3c_shim::context(dctx.device);
-    std::vector<Word27> buf(in.size() + 8);
+    t3c_shim::size_for_output(out, in.size() + 8);     // decoded in place into the caller's vector, trimmed below
     size_t n = 0;
     int ok = 0;
     if (dctx.arith == T3C_FIXED && dctx.fixed_cfg) {
         const t3c_config cfg = t3c_shim::to_abi(*dctx.fixed_cfg, dctx.fixed_cfg->superframe_words);
         size_t fixed = 0;
         if (t3c_decode_profile_fixed(ctx, &cfg, dctx.expected_raw_words, reinterpret_cast<const uint8_t*>(in.data()), in.size(),
-                                     reinterpret_cast<uint8_t*>(buf.data()), buf.size(), &n, &ok, &fixed) != T3C_OK) return false;
+                                     reinterpret_cast<uint8_t*>(out.data()), out.size(), &n, &ok, &fixed) != T3C_OK) { out.clear(); return false; }
         dctx.last_corrected = fixed;
     } else {
         t3c_config seen = t3c_shim::to_abi(dctx.cfg_last_seen, 8192);
-        if (t3c_decode_profile(ctx, &seen, reinterpret_cast<const uint8_t*>(in.data()), in.size(), reinterpret_cast<uint8_t*>(buf.data()),
-                               buf.size(), &n, &ok) != T3C_OK) return false;
+        if (t3c_decode_profile(ctx, &seen, reinterpret_cast<const uint8_t*>(in.data()), in.size(), reinterpret_cast<uint8_t*>(out.data()),
+                               out.size(), &n, &ok) != T3C_OK) { out.clear(); return false; }
         t3c_shim::from_abi(seen, dctx.cfg_last_seen); // mutated even when a later block fails (OLD:1006-1013)
     }
-    if (!ok) return false;
-    buf.resize(n);
-    out.swap(buf);
+    if (!ok) { out.clear(); return false; }            // the reference leaves `out` empty on failure (OLD:997)
+    out.resize(n);
     return true;
 }
 

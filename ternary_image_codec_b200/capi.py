@@ -59,7 +59,8 @@ def make_config(profile=P2_RS26_22, uep=1, tile=(0, 0), seed=(1, 1, 1), beacon=(
 
 
 _EXPORTS = [
-    "t3c_create", "t3c_destroy", "t3c_last_error", "t3c_version", "t3c_config_default", "t3c_stream", "t3c_sync",
+    "t3c_create", "t3c_destroy", "t3c_set_host_registration", "t3c_stream_create", "t3c_stream_destroy", "t3c_stream_lanes",
+    "t3c_stream_encode_rgb8", "t3c_stream_decode_rgb8", "t3c_last_error", "t3c_version", "t3c_config_default", "t3c_stream", "t3c_sync",
     "t3c_kernel_launches", "t3c_profile_words", "t3c_rgb_to_quant", "t3c_quant_to_rgb", "t3c_pack_pixels",
     "t3c_unpack_pixels", "t3c_words_to_bytes", "t3c_rs_encode_blocks", "t3c_rs_decode_blocks", "t3c_interleave2d",
     "t3c_header_emit", "t3c_header_parse", "t3c_header_pack", "t3c_header_check", "t3c_header_unpack", "t3c_crc3_rem12",
@@ -92,6 +93,13 @@ def load_library() -> C.CDLL:
     szp = C.POINTER(C.c_size_t)
     L.t3c_create.argtypes = [i32, C.POINTER(vp)]
     L.t3c_destroy.argtypes = [vp]
+    L.t3c_set_host_registration.argtypes = [vp, i32]
+    L.t3c_stream_create.argtypes = [C.POINTER(i32), i32, C.POINTER(vp)]
+    L.t3c_stream_destroy.argtypes = [vp]
+    L.t3c_stream_destroy.restype = None
+    L.t3c_stream_lanes.argtypes = [vp]
+    L.t3c_stream_encode_rgb8.argtypes = [vp, cfgp, i32, vp, sz, sz, sz, vp, sz, szp]
+    L.t3c_stream_decode_rgb8.argtypes = [vp, cfgp, vp, sz, sz, sz, sz, sz, vp, vp, szp]
     L.t3c_destroy.restype = None
     L.t3c_last_error.argtypes = [vp]
     L.t3c_last_error.restype = C.c_char_p
@@ -570,3 +578,58 @@ class Codec:
     def rs_decode_blocks_dev(self, k, d_inout, n, d_out, d_ok, arith=None, stream=0):
         self._ck(self.lib.t3c_rs_decode_blocks_dev(self.h, k, self.arith if arith is None else arith, self._dp(d_inout), n, self._dp(d_out),
                                                    self._dp(d_ok), stream))
+
+
+class Stream:
+    """A multi-device stream (t3c_stream_*, include/t3c.h): one context and one host thread per lane, frame f -> lane f mod n_lanes,
+    results in frame order.  ``devices`` may list a device more than once (several lanes on one GPU)."""
+
+    def __init__(self, devices):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        devs = (C.c_int32 * len(devices))(*devices)
+        st = self.lib.t3c_stream_create(devs, len(devices), C.byref(self.h))
+        if st == ERR_NODEVICE:
+            raise T3CError("t3c_stream_create: no CUDA device -- this library has no CPU fallback")
+        if st != OK:
+            raise T3CError(f"t3c_stream_create failed with status {st}")
+
+    @property
+    def lanes(self):
+        return int(self.lib.t3c_stream_lanes(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.t3c_stream_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode_rgb8(self, rgb: np.ndarray, cfg: Config, arith: int, first_frame: int = 0, out: np.ndarray | None = None):
+        """rgb: (n_frames, n_px, 3) uint8 -> (n_frames, words_per_frame, 9) uint8"""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        n_frames, n_px = rgb.shape[0], rgb.shape[1]
+        wpf = profile_words(cfg, (n_px + 1) // 2)
+        if out is None:
+            out = np.empty((n_frames, wpf, 9), np.uint8)
+        got = C.c_size_t()
+        st = self.lib.t3c_stream_encode_rgb8(self.h, C.byref(cfg), arith, rgb.ctypes.data, n_px, n_frames, first_frame, out.ctypes.data, out.shape[1], C.byref(got))
+        if st != OK:
+            raise T3CError(f"t3c_stream_encode_rgb8: status {st}")
+        return out[:, :got.value]
+
+    def decode_rgb8(self, enc: np.ndarray, n_px: int, cfg: Config, first_frame: int = 0):
+        """enc: (n_frames, words_per_frame, 9) -> (ok[n_frames], rgb (n_frames, n_px, 3), n_corrected)"""
+        enc = np.ascontiguousarray(enc, dtype=np.uint8)
+        n_frames, wpf = enc.shape[0], enc.shape[1]
+        rgb = np.empty((n_frames, n_px, 3), np.uint8)
+        ok = np.zeros(n_frames, np.uint8)
+        nc = C.c_size_t()
+        st = self.lib.t3c_stream_decode_rgb8(self.h, C.byref(cfg), enc.ctypes.data, wpf, wpf, n_frames, first_frame, n_px, rgb.ctypes.data, ok.ctypes.data, C.byref(nc))
+        if st != OK:
+            raise T3CError(f"t3c_stream_decode_rgb8: status {st}")
+        return ok, rgb, int(nc.value)

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,11 @@ struct t3c_ctx {
     Mail* d_mail = nullptr;
     uint64_t launches = 0;
     std::string err;
+    // pageable host buffers of the host-buffer calls (t3c_set_host_registration): ranges seen before are page-locked in place
+    struct HostReg { const void* p = nullptr; size_t n = 0; bool registered = false; uint64_t last_use = 0; };
+    HostReg regs[16];
+    int host_reg_mode = 0;
+    uint64_t reg_clock = 0;
 };
 
 namespace {
@@ -97,6 +103,39 @@ t3c_status reserve_t(t3c_ctx* ctx, int slot, size_t bytes, T** out, cudaStream_t
     t3c_status s = reserve_on(ctx, slot, bytes, &p, st);
     *out = static_cast<T*>(p);
     return s;
+}
+// Pageable host memory makes every cudaMemcpyAsync a staged, blocking copy: the chunked pipelines degrade to ~1/5 of their pinned
+// throughput (8K encode + decode: 43.8 ms against 7.9 ms per frame, tools/e2e_pageable.py).  Page-locking a range costs ~170 us per
+// MB, so it only pays for buffers that come back: a large pageable range is noted the first time it is seen and page-locked
+// (cudaHostRegister) when the same range is passed again; the registrations are kept (least recently used out) and dropped with
+// the context.  The caller must not free such a buffer while another thread is inside a call that uses it -- nothing new -- and a
+// range that was freed and re-allocated elsewhere simply stops matching.  Off unless t3c_set_host_registration(ctx, 1).
+constexpr size_t kHostRegMinBytes = 8u << 20;
+void host_buffer(t3c_ctx* ctx, const void* p, size_t bytes)
+{
+    if (!ctx->host_reg_mode || !p || bytes < kHostRegMinBytes) return;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+    if (at.type != cudaMemoryTypeUnregistered) return;                       // already pinned (or device / managed memory)
+    ++ctx->reg_clock;
+    t3c_ctx::HostReg* slot = nullptr;
+    for (auto& r : ctx->regs) if (r.p == p && r.n == bytes) { slot = &r; break; }
+    if (!slot) {                                                              // first sight: remember, evicting the least recently used entry
+        for (auto& r : ctx->regs) if (!slot || r.last_use < slot->last_use) slot = &r;
+        if (slot->registered) { cudaHostUnregister(const_cast<void*>(slot->p)); cudaGetLastError(); }
+        *slot = t3c_ctx::HostReg{p, bytes, false, ctx->reg_clock};
+        return;
+    }
+    slot->last_use = ctx->reg_clock;
+    if (slot->registered) return;                                             // (the attribute query would have said so; a stale entry)
+    cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {                          // overlaps a range registered earlier at another size: drop those and retry
+        cudaGetLastError();
+        for (auto& r : ctx->regs)
+            if (r.registered && (const char*)r.p < (const char*)p + bytes && (const char*)p < (const char*)r.p + r.n) { cudaHostUnregister(const_cast<void*>(r.p)); r = t3c_ctx::HostReg{}; }
+        e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault);
+    }
+    if (e == cudaSuccess) slot->registered = true; else cudaGetLastError();   // could not pin: the call proceeds with pageable copies
 }
 t3c_status check_launch(t3c_ctx* ctx, int n)
 {
@@ -243,6 +282,7 @@ void t3c_destroy(t3c_ctx* ctx)
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->regs) if (r.registered) cudaHostUnregister(const_cast<void*>(r.p));
     for (auto& b : ctx->buf) if (b.p) cudaFree(b.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
@@ -258,6 +298,12 @@ void t3c_destroy(t3c_ctx* ctx)
     delete ctx;
 }
 
+t3c_status t3c_set_host_registration(t3c_ctx* ctx, int mode)
+{
+    if (!ctx) return T3C_ERR_ARG;
+    ctx->host_reg_mode = mode ? 1 : 0;
+    return T3C_OK;
+}
 const char* t3c_last_error(const t3c_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
 void* t3c_stream(t3c_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t t3c_kernel_launches(const t3c_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -512,6 +558,7 @@ t3c_status t3c_rgb_to_quant(t3c_ctx* ctx, const uint8_t* rgb, size_t n_px, t3c_p
     if (!ctx || (n_px && (!rgb || !out))) return fail(ctx, T3C_ERR_ARG, "rgb_to_quant: null");
     if (!n_px) return T3C_OK;
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, rgb, 3 * n_px); host_buffer(ctx, out, 6 * n_px);
     uint8_t* d_in; t3c_pixel* d_out;
     TRY(reserve_t(ctx, B_IN, 3 * n_px, &d_in)); TRY(reserve_t(ctx, B_OUT, 6 * n_px, &d_out));
     H2D(d_in, rgb, 3 * n_px);
@@ -525,6 +572,7 @@ t3c_status t3c_quant_to_rgb(t3c_ctx* ctx, const t3c_pixel* px, size_t n_px, uint
     if (!ctx || (n_px && (!rgb || !px))) return fail(ctx, T3C_ERR_ARG, "quant_to_rgb: null");
     if (!n_px) return T3C_OK;
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, px, 6 * n_px); host_buffer(ctx, rgb, 3 * n_px);
     t3c_pixel* d_in; uint8_t* d_out;
     TRY(reserve_t(ctx, B_IN, 6 * n_px, &d_in)); TRY(reserve_t(ctx, B_OUT, 3 * n_px, &d_out));
     H2D(d_in, px, 6 * n_px);
@@ -540,6 +588,7 @@ t3c_status t3c_pack_pixels(t3c_ctx* ctx, const t3c_pixel* px, size_t n_px, uint8
     if (n_words) *n_words = nw;
     if (!n_px) return T3C_OK;
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, px, 6 * n_px); host_buffer(ctx, words, 9 * ((n_px + 1) / 2));
     t3c_pixel* d_in; uint8_t* d_out;
     TRY(reserve_t(ctx, B_IN, 6 * n_px, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * nw, &d_out));
     H2D(d_in, px, 6 * n_px);
@@ -553,6 +602,7 @@ t3c_status t3c_unpack_pixels(t3c_ctx* ctx, const uint8_t* words, size_t n_words,
     if (!ctx || (n_words && (!px || !words))) return fail(ctx, T3C_ERR_ARG, "unpack_pixels: null");
     if (!n_words) return T3C_OK;
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, words, 9 * n_words); host_buffer(ctx, px, 12 * n_words);
     uint8_t* d_in; t3c_pixel* d_out;
     TRY(reserve_t(ctx, B_IN, 9 * n_words, &d_in)); TRY(reserve_t(ctx, B_OUT, 12 * n_words, &d_out));
     H2D(d_in, words, 9 * n_words);
@@ -743,6 +793,7 @@ t3c_status t3c_encode_profile(t3c_ctx* ctx, const t3c_config* cfg, int arith, co
 {
     if (!ctx || !cfg || !out || !n_out || (n_words && !raw)) return fail(ctx, T3C_ERR_ARG, "encode_profile: null");
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, raw, 9 * n_words); host_buffer(ctx, out, 9 * cap_words);
     const size_t no = profile_words(*cfg, n_words);
     *n_out = 0;
     if (cap_words < no) return fail(ctx, T3C_ERR_CAPACITY, "encode_profile: capacity");
@@ -761,6 +812,7 @@ t3c_status t3c_decode_profile(t3c_ctx* ctx, t3c_config* seen, const uint8_t* in,
 {
     if (!ctx || !seen || !n_out || !ok || (n_words && !in)) return fail(ctx, T3C_ERR_ARG, "decode_profile: null");
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, in, 9 * n_words); host_buffer(ctx, out, 9 * cap_words);
     *n_out = 0; *ok = 0;
     if (seen->profile == T3C_PROFILE_RAW) { // stateful passthrough keyed on the PREVIOUS header, OLD:998-1002
         if (cap_words < n_words) return fail(ctx, T3C_ERR_CAPACITY, "decode_profile: capacity");
@@ -802,6 +854,7 @@ t3c_status t3c_decode_profile_fixed(t3c_ctx* ctx, const t3c_config* cfg, size_t 
 {
     if (!ctx || !cfg || !n_out || !ok || (n_words && !in)) return fail(ctx, T3C_ERR_ARG, "decode_profile_fixed: null");
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, in, 9 * n_words); host_buffer(ctx, out, 9 * cap_words);
     *n_out = 0; *ok = 0;
     if (n_corrected) *n_corrected = 0;
     if (cfg->profile == T3C_PROFILE_RAW) {
@@ -838,6 +891,7 @@ t3c_status t3c_encode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, int arith
 {
     if (!ctx || !cfg || !rgb || !out || !words_per_frame) return fail(ctx, T3C_ERR_ARG, "encode_frames: null");
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, rgb, 3 * n_px * n_frames); host_buffer(ctx, out, 9 * stride_words * n_frames);
     const size_t n_words = (n_px + 1) / 2;
     const size_t no = profile_words(*cfg, n_words);
     *words_per_frame = no;
@@ -906,6 +960,7 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
     if (n_frames > 32) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: at most 32 frames per host-buffer call");
     if (cfg->profile == T3C_PROFILE_RAW) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: RAW profile carries raw words, use unpack_pixels");
     DeviceGuard guard(ctx->device);
+    host_buffer(ctx, in, 9 * stride_words * n_frames); host_buffer(ctx, rgb, 3 * n_px * n_frames);
     if (n_corrected) *n_corrected = 0;
     if (px_recovered) *px_recovered = 0;
     if (!n_frames) return T3C_OK;
@@ -1382,3 +1437,74 @@ t3c_status t3c_v6new_words_to_image(t3c_ctx* ctx, const uint32_t* words, size_t 
     return T3C_OK;
 }
 } // extern "C"
+
+
+// ---- multi-device streams: one context and one host thread per lane, frame f -> lane f mod n (include/t3c.h) -----------------------
+struct t3c_streamset {
+    std::vector<t3c_ctx*> lane;
+};
+t3c_status t3c_stream_create(const int* devices, int n_lanes, t3c_streamset** out)
+{
+    if (!devices || n_lanes <= 0 || n_lanes > 64 || !out) return T3C_ERR_ARG;
+    *out = nullptr;
+    t3c_streamset* s = new t3c_streamset;
+    for (int i = 0; i < n_lanes; ++i) {
+        t3c_ctx* c = nullptr;
+        const t3c_status st = t3c_create(devices[i], &c);
+        if (st != T3C_OK) { t3c_stream_destroy(s); return st; }
+        s->lane.push_back(c);
+    }
+    *out = s;
+    return T3C_OK;
+}
+void t3c_stream_destroy(t3c_streamset* s)
+{
+    if (!s) return;
+    for (t3c_ctx* c : s->lane) t3c_destroy(c);
+    delete s;
+}
+int t3c_stream_lanes(const t3c_streamset* s) { return s ? (int)s->lane.size() : 0; }
+namespace {
+// lane l codes frames f with (first_frame + f) % n == l, one call per frame, on its own thread; the first failure is reported
+template <class F>
+t3c_status stream_run(t3c_streamset* s, size_t n_frames, size_t first_frame, F&& per_frame)
+{
+    const size_t n = s->lane.size();
+    std::vector<t3c_status> res(n, T3C_OK);
+    std::vector<std::thread> th;
+    for (size_t l = 0; l < n; ++l)
+        th.emplace_back([&, l] {
+            for (size_t f = 0; f < n_frames; ++f) {
+                if ((first_frame + f) % n != l) continue;
+                const t3c_status st = per_frame(s->lane[l], f);
+                if (st != T3C_OK) { res[l] = st; return; }
+            }
+        });
+    for (auto& t : th) t.join();
+    for (t3c_status r : res) if (r != T3C_OK) return r;
+    return T3C_OK;
+}
+} // namespace
+t3c_status t3c_stream_encode_rgb8(t3c_streamset* s, const t3c_config* cfg, int arith, const uint8_t* rgb, size_t n_px, size_t n_frames, size_t first_frame,
+                                  uint8_t* out9, size_t stride_words, size_t* words_per_frame)
+{
+    if (!s || s->lane.empty() || !cfg || !words_per_frame || (n_frames && (!rgb || !out9))) return T3C_ERR_ARG;
+    *words_per_frame = profile_words(*cfg, (n_px + 1) / 2);
+    if (stride_words < *words_per_frame) return T3C_ERR_CAPACITY;
+    return stream_run(s, n_frames, first_frame, [&](t3c_ctx* c, size_t f) {
+        size_t w = 0;
+        return t3c_encode_frames_rgb8(c, cfg, arith, rgb + 3 * n_px * f, n_px, 1, out9 + 9 * stride_words * f, stride_words, &w);
+    });
+}
+t3c_status t3c_stream_decode_rgb8(t3c_streamset* s, const t3c_config* cfg, const uint8_t* in9, size_t words_per_frame, size_t stride_words, size_t n_frames,
+                                  size_t first_frame, size_t n_px, uint8_t* rgb, uint8_t* ok, size_t* n_corrected)
+{
+    if (!s || s->lane.empty() || !cfg || (n_frames && (!in9 || !rgb || !ok))) return T3C_ERR_ARG;
+    std::vector<size_t> fixed(n_frames, 0);
+    const t3c_status st = stream_run(s, n_frames, first_frame, [&](t3c_ctx* c, size_t f) {
+        size_t rec = 0;
+        return t3c_decode_frames_rgb8(c, cfg, in9 + 9 * stride_words * f, words_per_frame, stride_words, 1, n_px, rgb + 3 * n_px * f, ok + f, &rec, &fixed[f]);
+    });
+    if (n_corrected) { *n_corrected = 0; for (size_t v : fixed) *n_corrected += v; }
+    return st;
+}

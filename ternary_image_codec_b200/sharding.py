@@ -1,13 +1,11 @@
-"""Frame / super-frame sharding across the GPUs of one box.
-
-Every ``encode_profile_from_raw`` / ``decode_profile_to_raw`` call is independent, so frames shard with
-NO data-path collective: frame f goes to rank f mod world, each rank runs its frames on its own GPU, and
-the only communication is the host-side gather of the per-frame results in frame order (gloo on CPU
-tensors, or NCCL on device tensors).  This module holds that plumbing; it never touches codec data itself.
-"""
+"""Frame sharding across the processes of one box, for callers that run ONE PROCESS PER GPU (bench.py under torchrun):
+frame f goes to rank f mod world, each rank codes its frames on its own GPU with no data-path collective, and the only
+communication is the host-side gather of the per-frame streams in frame order.  (A single process that drives several GPUs uses
+t3c_stream_* / ``Stream`` instead: same assignment, host threads instead of ranks, nothing to gather.)  bench.py takes its config-4
+frame assignment from here; tests/test_sharding_gloo.py runs the gather on two gloo ranks."""
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
@@ -20,11 +18,6 @@ def frames_for_rank(n_frames: int, rank: int, world: int) -> List[int]:
 
 def owner_of(frame: int, world: int) -> int:
     return frame % world
-
-
-def run_sharded(n_frames: int, process_frame: Callable[[int], torch.Tensor], rank: int, world: int) -> dict:
-    """Run ``process_frame(f)`` for this rank's frames; returns {frame: result tensor}."""
-    return {f: process_frame(f) for f in frames_for_rank(n_frames, rank, world)}
 
 
 def gather_in_frame_order(local: dict, n_frames: int, rank: int, world: int, dst: int = 0,
@@ -62,9 +55,3 @@ def gather_in_frame_order(local: dict, n_frames: int, rank: int, world: int, dst
             out[f] = bufs[r][off:off + n].clone()
             off += n
     return out  # type: ignore[return-value]
-
-
-def split_superframes(n_words: int, superframe_words: int) -> Sequence[range]:
-    """Optional segmentation of one raw-word stream into super-frames of ``superframe_words`` words each
-    (the reference never segments: one call = one header + one body, SURVEY bug B10)."""
-    return [range(s, min(s + superframe_words, n_words)) for s in range(0, n_words, superframe_words)]

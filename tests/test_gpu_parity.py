@@ -944,3 +944,33 @@ def test_crc32_more_tiles_than_resident_warps(codec):
     n = 9500 * 32768 + 12345
     data = rng(961).integers(0, 256, n, dtype=np.uint8)
     assert codec.crc32(data) == zlib.crc32(data.tobytes())
+
+
+# ------------------------------------------------------------------ multi-device streams (t3c_stream_*, BASELINE config 4)
+@pytest.mark.parametrize("lanes", [[0], [0, 0, 0]])
+def test_stream_api_frames_in_order_match_oracle(oracle, t3, lanes):
+    """t3c_stream_encode_rgb8 / t3c_stream_decode_rgb8: frame f -> lane (first_frame + f) mod n_lanes, every frame equal to the oracle's
+    encode of that frame, in frame order; decode with injected errors returns the oracle's pixels and the total corrected count"""
+    import torch
+    n_gpu = torch.cuda.device_count()
+    devs = [d % n_gpu for d in (lanes if len(lanes) == 1 else list(range(len(lanes))))]
+    kw = dict(profile=T.P3, uep=2)
+    oc, gc = both(kw)
+    n_px, n_frames = 540 * 40 + 17, 7
+    frames = np.stack([T.synth_rgb(5 + f, n_px) for f in range(n_frames)])
+    st = t3.Stream(devs)
+    assert st.lanes == len(devs)
+    enc = st.encode_rgb8(frames, gc, t3.FIXED, first_frame=3)
+    add = T.gf_add_table()
+    bad = enc.copy()
+    tot = 0
+    for f in range(n_frames):
+        assert np.array_equal(enc[f], oracle.encode_rgb(oc, frames[f], 1)), f
+        bad[f], ne = T.inject_errors(enc[f], oc, (n_px + 1) // 2, seed=40 + f, gf_add=add)
+        tot += ne
+    ok, rgb, nc = st.decode_rgb8(bad, n_px, gc, first_frame=1)
+    assert ok.all() and nc == tot
+    for f in range(n_frames):
+        ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, bad[f], n_px)
+        assert ok_o and np.array_equal(rgb[f, :rgb_o.shape[0]], rgb_o), f
+    st.close()
