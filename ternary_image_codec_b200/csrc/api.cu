@@ -25,6 +25,7 @@ struct t3c_ctx {
     DevTables tabs{};
     HeaderCache hdr_cache{};
     SuperCache sup_cache{};
+    FastImageCache img_cache{};
     void* d_tables = nullptr;
     uint32_t* d_crc = nullptr; // CRC-32 tables of the .t3v record kernels
     HostTables* host = nullptr; // host copy of the constant tables (decoder screen constants are derived per call)
@@ -257,6 +258,8 @@ t3c_status t3c_create(int device, t3c_ctx** out)
     if (cudaMalloc((void**)&ctx->hdr_cache.base, 128 * HeaderCache::N) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
     for (int i = 0; i < HeaderCache::N; ++i) { ctx->hdr_cache.e[i].d52 = ctx->hdr_cache.base + 128 * i; ctx->hdr_cache.e[i].d27 = ctx->hdr_cache.base + 128 * i + 64; }
     ctx->tabs.sup = &ctx->sup_cache;
+    ctx->tabs.img = &ctx->img_cache;
+    if (cudaMalloc((void**)&ctx->img_cache.base, (size_t)FastImageCache::N * FastImageCache::BYTES) != cudaSuccess) { t3c_destroy(ctx); return T3C_ERR_CUDA; }
     {
         std::vector<uint32_t> h(crc_table_words());
         build_crc_tables(h.data());
@@ -287,6 +290,7 @@ void t3c_destroy(t3c_ctx* ctx)
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_crc) cudaFree(ctx->d_crc);
     if (ctx->hdr_cache.base) cudaFree(ctx->hdr_cache.base);
+    if (ctx->img_cache.base) cudaFree(ctx->img_cache.base);
     for (auto& sl : ctx->sup_cache.slot) if (sl.d_map) cudaFree(sl.d_map);
     if (ctx->h_mail) cudaFreeHost(ctx->h_mail);
     if (ctx->d_mail) cudaFree(ctx->d_mail);

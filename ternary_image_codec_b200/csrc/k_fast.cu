@@ -1527,6 +1527,74 @@ static int persistent_ctas_per_sm(const void* kern, int tpb, int smem_bytes)
     cache[{kern, dev}] = n;
     return n;
 }
+// the config's CTA-shared image of the v5 kernels (FastImageCache, launch.h), built on `st` the first time a config is seen
+template <int K>
+static const uint8_t* v5_image(const DevTables& T, const Geom& g, bool dec, cudaStream_t st, int& launches)
+{
+    static_assert(Cfg5<K>::ENC_WARP <= FastImageCache::BYTES && Cfg5<K>::DEC_WARP <= FastImageCache::BYTES && Cfg5<K>::ENC_WARP % 16 == 0 && Cfg5<K>::DEC_WARP % 16 == 0, "image size");
+    FastImageCache& C = *T.img;
+    uint8_t key[40] = {};
+    key[0] = (uint8_t)K; key[1] = dec ? 1 : g.arith; key[2] = dec ? 1 : 0;      // the decoder's tables are always the repaired code's
+    for (int i = 0; i < 8; ++i) key[3 + i] = g.st[i];
+    for (int b = 0; b < 9; ++b) key[11 + b] = (uint8_t)(g.cw_base[b] % 3);
+    for (int i = 0; i < FastImageCache::N; ++i)
+        if (C.e[i].valid && std::memcmp(C.e[i].key, key, sizeof key) == 0) return C.base + (size_t)i * FastImageCache::BYTES;
+    int slot = -1;
+    for (int i = 0; i < FastImageCache::N; ++i) if (!C.e[i].valid) { slot = i; break; }
+    if (slot < 0) { cudaDeviceSynchronize(); slot = C.next; C.next = (C.next + 1) % FastImageCache::N; }
+    C.e[slot].valid = false;
+    uint8_t* img = C.base + (size_t)slot * FastImageCache::BYTES;
+    if (dec) {
+        cudaFuncSetAttribute(k_v5_image_dec<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg5<K>::DEC_WARP);
+        k_v5_image_dec<K><<<1, 256, Cfg5<K>::DEC_WARP, st>>>(g, T.gf, T.rs, img);
+    } else {
+        cudaFuncSetAttribute(k_v5_image_enc<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg5<K>::ENC_WARP);
+        k_v5_image_enc<K><<<1, 256, Cfg5<K>::ENC_WARP, st>>>(g, T.gf, T.rs, img);
+    }
+    ++launches;
+    cudaStreamSynchronize(st);   // once per new config: later calls may come on other streams
+    std::memcpy(C.e[slot].key, key, sizeof key);
+    C.e[slot].valid = true;
+    return img;
+}
+static uint32_t v5_flags()
+{
+    static int fl = -1;
+    if (fl < 0) { const char* e = getenv("T3C_V5_FLAGS"); fl = e ? atoi(e) : (int)V5_FLAGS_DEFAULT; }
+    return (uint32_t)fl;
+}
+template <int K, bool WORDS>
+static int launch_v5_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st)
+{
+    static int occ = 0;
+    using L5 = Cfg5<K, WORDS>;
+    int n = 0;
+    const uint8_t* img = v5_image<K>(T, g, false, st, n);
+    occ = persistent_ctas_per_sm(reinterpret_cast<const void*>(k_encode_v5<K, WORDS>), 32 * L5::ENC_WARPS, L5::TOTAL_ENC);
+    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames, need = (total + L5::ENC_WARPS - 1) / L5::ENC_WARPS;
+    uint64_t grid = (uint64_t)T.sm_count * occ;
+    if (grid > need) grid = need;
+    if (!grid) return n;
+    P.flags = v5_flags();
+    k_encode_v5<K, WORDS><<<(unsigned)grid, 32 * L5::ENC_WARPS, L5::TOTAL_ENC, st>>>(P, g, T.gf, img);
+    return n + 1;
+}
+template <int K, bool WORDS>
+static int launch_v5_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st)
+{
+    static int occ = 0;
+    using L5 = Cfg5<K, WORDS>;
+    int n = 0;
+    const uint8_t* img = v5_image<K>(T, g, true, st, n);
+    occ = persistent_ctas_per_sm(reinterpret_cast<const void*>(k_decode_v5<K, WORDS>), 32 * L5::DEC_WARPS, L5::TOTAL_DEC);
+    const uint64_t total = (uint64_t)P.n_tiles * P.n_frames, need = (total + L5::DEC_WARPS - 1) / L5::DEC_WARPS;
+    uint64_t grid = (uint64_t)T.sm_count * occ;
+    if (grid > need) grid = need;
+    if (!grid) return n;
+    P.flags = v5_flags();
+    k_decode_v5<K, WORDS><<<(unsigned)grid, 32 * L5::DEC_WARPS, L5::TOTAL_DEC, st>>>(P, g, img);
+    return n + 1;
+}
 template <class Kern>
 int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastParams& P, const Geom& g, cudaStream_t st, int& ctas_per_sm,
                       int warps = FAST_WARPS)
@@ -1537,13 +1605,7 @@ int launch_persistent(Kern kern, int smem_bytes, const DevTables& T, const FastP
     const uint64_t need = (total + warps - 1) / warps;
     if (grid > need) grid = need;
     if (!grid) return 0;
-    FastParams Q = P;
-    {
-        static int fl = -1;
-        if (fl < 0) { const char* e = getenv("T3C_V5_FLAGS"); fl = e ? atoi(e) : (int)V5_FLAGS_DEFAULT; }
-        Q.flags = (uint32_t)fl;
-    }
-    kern<<<(unsigned)grid, 32 * warps, smem_bytes, st>>>(Q, g, T.gf, T.rs);
+    kern<<<(unsigned)grid, 32 * warps, smem_bytes, st>>>(P, g, T.gf, T.rs);
     return 1;
 }
 // T3C_FAST=3 / 4 keep the v3 kernels (plain loads/stores, 4 CTAs per SM) / the v4 kernels (bulk-async I/O) for A/B comparison;
@@ -1582,15 +1644,15 @@ static bool smem_window_ok()
 template <int K>
 int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail, bool words = false)
 {
-    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0, occ5 = 0, occ5w = 0;
+    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 18) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
-            if (fast_version() == 5 && words) n += launch_persistent(k_encode_v5<K, true>, Cfg5<K, true>::TOTAL_ENC, T, P, g, st, occ5w, Cfg5<K, true>::ENC_WARPS);
-            else if (fast_version() == 5) n += launch_persistent(k_encode_v5<K, false>, Cfg5<K, false>::TOTAL_ENC, T, P, g, st, occ5, Cfg5<K, false>::ENC_WARPS);
+            if (fast_version() == 5 && words) n += launch_v5_enc<K, true>(T, P, g, st);
+            else if (fast_version() == 5) n += launch_v5_enc<K, false>(T, P, g, st);
             else if (words) n += launch_persistent(k_encode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_ENC, T, P, g, st, occ4w, Cfg4<K, true>::ENC_WARPS);
             else if (use_v4()) n += launch_persistent(k_encode_rgb_v4<K, false>, Cfg4<K>::TOTAL_ENC, T, P, g, st, occ4, Cfg4<K>::ENC_WARPS);
             else n += launch_persistent(k_encode_rgb_v3<K>, Cfg3<K>::TOTAL_ENC, T, P, g, st, occ3);
@@ -1602,15 +1664,15 @@ int launch_enc(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st,
 template <int K>
 int launch_dec(const DevTables& T, FastParams P, const Geom& g, cudaStream_t st, uint32_t n_full, uint32_t t0, uint32_t t1, bool tail, bool words = false)
 {
-    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0, occ5 = 0, occ5w = 0;
+    static int occ4 = 0, occ4w = 0, occ3 = 0, occ2 = 0;
     const uint32_t n_all = P.n_tiles;
     int n = 0;
     if constexpr (K >= 18) {
         if (t1 > n_full) t1 = n_full;
         if (t1 > t0) {
             P.tile0 = t0; P.n_tiles = t1 - t0;
-            if (fast_version() == 5 && words) n += launch_persistent(k_decode_v5<K, true>, Cfg5<K, true>::TOTAL_DEC, T, P, g, st, occ5w, Cfg5<K, true>::DEC_WARPS);
-            else if (fast_version() == 5) n += launch_persistent(k_decode_v5<K, false>, Cfg5<K, false>::TOTAL_DEC, T, P, g, st, occ5, Cfg5<K, false>::DEC_WARPS);
+            if (fast_version() == 5 && words) n += launch_v5_dec<K, true>(T, P, g, st);
+            else if (fast_version() == 5) n += launch_v5_dec<K, false>(T, P, g, st);
             else if (words) n += launch_persistent(k_decode_rgb_v4<K, true>, Cfg4<K, true>::TOTAL_DEC, T, P, g, st, occ4w, Cfg4<K, true>::DEC_WARPS);
             else if (use_v4()) n += launch_persistent(k_decode_rgb_v4<K, false>, Cfg4<K>::TOTAL_DEC, T, P, g, st, occ4, Cfg4<K>::DEC_WARPS);
             else n += launch_persistent(k_decode_rgb_v3<K>, Cfg3<K>::TOTAL_DEC, T, P, g, st, occ3);

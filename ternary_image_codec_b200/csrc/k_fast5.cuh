@@ -292,8 +292,74 @@ __device__ __forceinline__ void enc_cw5(const uint8_t* src, uint8_t* dst, uint32
     store26<2>(dst, q);
 }
 
+// ---- the CTA-shared image of the encoder (Cfg5: per variant {A[K][27] | B[K][27]} | pat[3][2] | lane records), built in the shared
+// memory of a one-CTA setup kernel and copied out to the config's FastImageCache entry
+template <int K>
+__global__ void __launch_bounds__(256, 1) k_v5_image_enc(Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, uint8_t* __restrict__ image)
+{
+    using L = Cfg3<K>;
+    using L5 = Cfg5<K, false>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint8_t maps[3 * 128];
+    const int tid = threadIdx.x, TPB = blockDim.x;
+    const uint32_t(*pl)[kVals][2] = rs->pl[g.arith][(24 - K) / 2];
+    for (int idx = tid; idx < 3 * K * 27; idx += TPB) {
+        const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
+        uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::ENC_VAR);
+        blk[rem] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
+        blk[K * 27 + rem] = pl[i][d][1];
+    }
+    if (tid < 3) { // the scrambler as seen by the parity symbols of a variant-tid codeword, in the plane domain
+        uint32_t nz = 0, two = 0;
+        for (int j = 0; j < L::R; ++j) {
+            const uint32_t st = st_of(g, tid, K + j);
+            if (st) nz |= 7u << plane_shift<K>(j);
+            if (st == 2) two |= 7u << plane_shift<K>(j);
+        }
+        reinterpret_cast<uint32_t*>(smem + L5::ENC_PAT)[2 * tid] = nz;
+        reinterpret_cast<uint32_t*>(smem + L5::ENC_PAT)[2 * tid + 1] = two;
+    }
+    for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
+    __syncthreads();
+    for (int t = tid; t < 3 * 128; t += TPB) build_records<K, L5::RUN_PITCH>(reinterpret_cast<uint2*>(smem + L5::ENC_REC), maps, g, t);
+    __syncthreads();
+    for (int i = tid; i < L5::ENC_WARP / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
+}
+template <int K>
+__global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, uint8_t* __restrict__ image)
+{
+    using L5 = Cfg5<K, false>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint8_t maps[3 * 128];
+    const int tid = threadIdx.x, TPB = blockDim.x;
+    GfTables& sg = *reinterpret_cast<GfTables*>(smem + L5::DEC_GF);
+    const uint32_t(*pl)[kVals][2] = rs->pl[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
+    for (int idx = tid; idx < 3 * 26 * 32; idx += TPB) {
+        const int v = idx / (26 * 32), rem = idx - v * (26 * 32), i = rem / 32, x = rem - 32 * i, xm = x >= 27 ? x - 27 : x;
+        uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::DEC_VAR);
+        blk[rem] = pl[i][xm][0] | gf->dsc[st_of(g, v, i)][xm];
+        blk[26 * 32 + rem] = pl[i][xm][1];
+    }
+    load_gf(sg, gf);
+    for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
+    __syncthreads();
+    for (int t = tid; t < 3 * 128; t += TPB) build_records<K, L5::RUN_PITCH>(reinterpret_cast<uint2*>(smem + L5::DEC_REC), maps, g, t);
+    if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
+        Planes c{0, 0};
+        const uint32_t* blk = reinterpret_cast<const uint32_t*>(smem + tid * L5::DEC_VAR);
+        for (int i = 0; i < 26; ++i) {
+            const int idx = i * 32 + 13 * (int)st_of(g, tid, i);
+            gf3_add(c, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
+        }
+        reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid] = c.nz;
+        reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid + 1] = c.two;
+    }
+    __syncthreads();
+    for (int i = tid; i < L5::DEC_WARP / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
+}
+
 template <int K, bool WORDS>
-__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5(FastParams P, Geom g, const GfTables* __restrict__ gf, const uint8_t* __restrict__ image)
 {
     using L = Cfg3<K>;
     using L5 = Cfg5<K, WORDS>;
@@ -305,30 +371,12 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
     uint8_t* U = S + L::S_BYTES;                                // the nine body runs
     uint4* carry = reinterpret_cast<uint4*>(U + L5::RUNS_BYTES);
     const uint32_t bar = smem_u32(U + L5::RUNS_BYTES + L5::CARRY_BYTES);
-    uint2* rec = reinterpret_cast<uint2*>(smem + L5::ENC_REC);
-    {
-        const uint32_t(*pl)[kVals][2] = rs->pl[g.arith][(24 - K) / 2];
-        for (int idx = tid; idx < 3 * K * 27; idx += TPB) {
-            const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
-            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::ENC_VAR);
-            blk[rem] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
-            blk[K * 27 + rem] = pl[i][d][1];
-        }
-        if (tid < 3) { // the scrambler as seen by the parity symbols of a variant-tid codeword, in the plane domain
-            uint32_t nz = 0, two = 0;
-            for (int j = 0; j < L::R; ++j) {
-                const uint32_t st = st_of(g, tid, K + j);
-                if (st) nz |= 7u << plane_shift<K>(j);
-                if (st == 2) two |= 7u << plane_shift<K>(j);
-            }
-            reinterpret_cast<uint32_t*>(smem + L5::ENC_PAT)[2 * tid] = nz;
-            reinterpret_cast<uint32_t*>(smem + L5::ENC_PAT)[2 * tid + 1] = two;
-        }
-        uint8_t* maps = smem + L5::ENC_WARP;                     // scratch: the first warp's IN buffer is not in use yet
-        for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
+    const uint2* rec = reinterpret_cast<const uint2*>(smem + L5::ENC_REC);
+    {   // the CTA-shared tables: a copy of the image v5_build_enc made once for this config (FastImageCache)
+        const uint4* src = reinterpret_cast<const uint4*>(image);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < L5::ENC_WARP / 16; i += TPB) dst[i] = __ldg(src + i);
         if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-        __syncthreads();
-        for (int t = tid; t < 3 * 128; t += TPB) build_records<K, PITCH>(rec, maps, g, t);
     }
     __syncthreads(); // tables, records and barriers ready; no block-level barrier after this one
     const uint32_t* patp = reinterpret_cast<const uint32_t*>(smem + L5::ENC_PAT);
@@ -426,8 +474,129 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
 // =============================================================================================
 // decode
 // =============================================================================================
+// The rare branches of a codeword's screen live out of line: inlined into the four unrolled passes they made the hot loop 100 KB of
+// code (6350 instructions), more than the instruction caches hold for 27 warps at different places of it.
+// bytes >= 27 in the received words (out-of-alphabet symbols read as their low three trits, unpack3, OLD:28-31)
+static __device__ __noinline__ void dec_cw_mod27(uint8_t* src)
+{
+    for (int i = 0; i < 26; ++i) src[i] = (uint8_t)(src[i] % 27u);   // in place in the staged run: the codeword belongs to this lane alone
+}
+// a codeword that fails the screen: full decode (descrambled), then its data symbols are rewritten.  The screen's sum minus the
+// clean-codeword constant is the parity residual, from which the syndromes follow without another pass over the block
+template <int K>
+static __device__ __noinline__ void dec_cw_dirty(const uint8_t* src, uint8_t* dst, const uint8_t* tab_v, uint32_t acc_nz, uint32_t acc_two, uint32_t chk_nz,
+                                                 uint32_t chk_two, const GfTables& sg, uint32_t* status)
+{
+    uint8_t cwd[26], orig[26], res[8];
+    for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tab_v + 4u * (src[i] % 27u) + 128 * i);
+    {
+        Planes d{acc_nz, acc_two};
+        gf3_add(d, chk_nz, chk_nz ^ chk_two);                  // minus the constant: -x keeps nz and flips two where nz is set
+        uint32_t lo, hi;
+        planes_to_parity<K>(d.nz, d.two, lo, hi);
+        for (int j = 0; j < 4; ++j) { res[j] = (uint8_t)(lo >> (8 * j)); res[4 + j] = (uint8_t)(hi >> (8 * j)); }
+    }
+    if (!rs_decode_residual(sg, cwd, K, res)) {
+        atomicExch(&status[0], 0u);
+    } else {
+        uint32_t nfix = 0;
+        for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
+        if (nfix) atomicAdd(&status[1], nfix);
+        for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
+    }
+}
+// ---- one codeword of decode phase B (see dec_cw, PRESCALED = false): 26 received symbols at src (even address) -> screen -> K descrambled
+// data symbols scattered at byte stride 9 from dst
+template <int K>
+__device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, uint32_t chk_nz, uint32_t chk_two,
+                                        const GfTables& sg, uint32_t* status)
+{
+    constexpr int PLANE = 4 * 26 * 32;
+    asm volatile("" : "+r"(pa));   // the block address in a vector register: with a uniform one PRMT would need its selector in a register (a move per symbol)
+    const uint32_t sa = smem_u32(src), sh = (sa & 2u) * 8u;
+    uint32_t xw[7];
+    auto load = [&]() {
+        static_for<0, 7>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(xw[j]) : "r"(sa & ~3u), "n"(4 * j) : "memory");
+        });
+#pragma unroll
+        for (int j = 0; j < 6; ++j) xw[j] = __funnelshift_r(xw[j], xw[j + 1], sh);
+        xw[6] = (xw[6] >> sh) & 0xFFFFu;                           // symbols 24, 25 only
+    };
+    load();
+    if ((xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6]) & 0xE0E0E0E0u) { dec_cw_mod27(const_cast<uint8_t*>(src)); load(); }
+#pragma unroll
+    for (int j = 0; j < 7; ++j) xw[j] *= 4u;                       // table byte offsets; < 128 per byte: no carry between symbols
+    Planes acc{0, 0}, acc2{0, 0};
+    uint32_t ev[K];
+    static_for<0, 26>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
+        const uint32_t ea = lds_tab<128 * i>(ra);
+        const uint32_t eb = lds_tab<128 * i + PLANE>(ra);
+        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        if (i < K) ev[i < K ? i : 0] = ea;
+    });
+#pragma unroll
+    for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
+    gf3_add(acc, acc2.nz, acc2.two);
+    if (((acc.nz ^ chk_nz) | (acc.two ^ chk_two)) & ~0xFFu)        // the low bytes carry the embedded symbols
+        dec_cw_dirty<K>(src, dst, tab_v, acc.nz, acc.two, chk_nz, chk_two, sg, status);
+}
+
+// pixel value -> RGB8 as value_to_rgb3 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84); the 2^23 magic is
+// OR-ed into the dequantised integers (one logic op each) instead of riding on the multiply-high's 64-bit addend (two register moves each)
+__device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
+{
+    const uint32_t q = __umulhi(A, 17674763u);                 // A / 243, exact for A < 3^13
+    const uint32_t Yq = A - 243u * q;
+    const uint32_t ur = __umulhi(q, 53024288u);                // q / 81, exact for q < 6561
+    const uint32_t ub = q - 81u * ur;
+    // Y = (510 Yq + 241) / 484 (dev.cuh dequant_y; <= 255 for Yq <= 242), C = min((64 u + 10) / 20, 255)
+    const float y = __fadd_rn(__uint_as_float(__umulhi(Yq * 510u + 241u, 8873899u) | 0x4B000000u), -8388608.0f);
+    const float cb = __fadd_rn(__uint_as_float(min(__umulhi(32u * ub + 5u, 429496730u), 255u) | 0x4B000000u), -8388736.0f);
+    const float cr = __fadd_rn(__uint_as_float(min(__umulhi(32u * ur + 5u, 429496730u), 255u) | 0x4B000000u), -8388736.0f);
+    const float r = __fadd_rn(y, __fmul_rn(1.402f, cr));
+    const float g = __fsub_rn(__fsub_rn(y, __fmul_rn(0.344136f, cb)), __fmul_rn(0.714136f, cr));
+    const float b = __fadd_rn(y, __fmul_rn(1.772f, cb));
+    const uint32_t Rb = floor_sat_u8(__fadd_rd(r, 0.5f)), Gb = floor_sat_u8(__fadd_rd(g, 0.5f)), Bb = floor_sat_u8(__fadd_rd(b, 0.5f));
+    return Rb + 256u * Gb + 65536u * Bb;                                       // R | G<<8 | B<<16
+}
+// ---- decode phase A: 26 stream symbols at S + a (even) -> six pixels -> 18 RGB bytes at dst (even address): four 32-bit stores and one
+// 16-bit store, aligned per lane by funnel shifts (see store26)
+__device__ __forceinline__ void dec_unit_rgb5(const uint8_t* S, uint32_t a, uint8_t* dst)
+{
+    uint32_t y[7]; // the 26 symbols, word aligned
+    load_unit26<false>(S, a, y, false);
+    uint32_t A[6];
+    symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+    symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+    uint32_t p[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) p[q] = value_to_rgb5(A[q]);
+    // 18 bytes as words: p0 | p1<<24, p1>>8 | p2<<16, p2>>16 | p3<<8, p4 | p5<<24, (p5>>8: two bytes)
+    const uint32_t w[5] = {p[0] | (p[1] << 24), (p[1] >> 8) | (p[2] << 16), (p[2] >> 16) | (p[3] << 8), p[4] | (p[5] << 24), p[5] >> 8};
+    const uint32_t da = smem_u32(dst), odd = da & 2u, sh = odd << 3;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + odd);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = __funnelshift_r(w[j], w[j + 1], sh);
+    *reinterpret_cast<uint16_t*>(dst + (odd ? 0 : 16)) = (uint16_t)(odd ? w[0] : w[4]);
+}
+template <int K>
+__device__ __forceinline__ void dec_phase_a5(const uint8_t* S, uint8_t* OUT, uint32_t pad, int lane)
+{
+    using L = Cfg3<K>;
+#pragma unroll 1
+    for (int pass = 0; pass < L::PASS_A; ++pass) {
+        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+        if (u >= L::UNITS) continue;
+        dec_unit_rgb5(S, 26u * (uint32_t)u, OUT + pad + 18 * u); // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
+    }
+}
+
 template <int K, bool WORDS>
-__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5(FastParams P, Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs)
+__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5(FastParams P, Geom g, const uint8_t* __restrict__ image)
 {
     using L = Cfg3<K>;
     using L5 = Cfg5<K, WORDS>;
@@ -440,32 +609,13 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
     uint8_t* R = S + L::S_BYTES;                                // the nine body runs as they lie in the frame (bulk-loaded one tile ahead)
     uint4* carry = reinterpret_cast<uint4*>(R + L5::RUNS_BYTES);
     const uint32_t bar = smem_u32(R + L5::RUNS_BYTES + L5::CARRY_BYTES);
-    GfTables& sg = *reinterpret_cast<GfTables*>(smem + L5::DEC_GF);
-    uint2* rec = reinterpret_cast<uint2*>(smem + L5::DEC_REC);
-    {
-        const uint32_t(*pl)[kVals][2] = rs->pl[1][(24 - K) / 2]; // the consistent decoder always uses the repaired code
-        for (int idx = tid; idx < 3 * 26 * 32; idx += TPB) {
-            const int v = idx / (26 * 32), rem = idx - v * (26 * 32), i = rem / 32, x = rem - 32 * i, xm = x >= 27 ? x - 27 : x;
-            uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::DEC_VAR);
-            blk[rem] = pl[i][xm][0] | gf->dsc[st_of(g, v, i)][xm];
-            blk[26 * 32 + rem] = pl[i][xm][1];
-        }
-        load_gf(sg, gf);
-        uint8_t* maps = smem + L5::DEC_WARP;                     // scratch: the first warp's OUT buffer is not in use yet
-        for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
+    const GfTables& sg = *reinterpret_cast<const GfTables*>(smem + L5::DEC_GF);
+    const uint2* rec = reinterpret_cast<const uint2*>(smem + L5::DEC_REC);
+    {   // the CTA-shared tables: a copy of the image k_v5_image_dec made once for this config (FastImageCache)
+        const uint4* src = reinterpret_cast<const uint4*>(image);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < L5::DEC_WARP / 16; i += TPB) dst[i] = __ldg(src + i);
         if (lane == 0) { mbar_init(bar, 9); fence_mbar_init(); }
-        __syncthreads();
-        for (int t = tid; t < 3 * 128; t += TPB) build_records<K, PITCH>(rec, maps, g, t);
-        if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
-            Planes c{0, 0};
-            const uint32_t* blk = reinterpret_cast<const uint32_t*>(smem + tid * L5::DEC_VAR);
-            for (int i = 0; i < 26; ++i) {
-                const int idx = i * 32 + 13 * (int)st_of(g, tid, i);
-                gf3_add(c, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
-            }
-            reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid] = c.nz;
-            reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid + 1] = c.two;
-        }
     }
     __syncthreads();
     const uint32_t tabA32 = smem_u32(smem);
@@ -519,14 +669,14 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
                 constexpr int p = decltype(pc)::value;
                 const uint2 r = rt[32 * p + lane];
                 const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFFu));
-                dec_cw<K, false>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, smem + p * L5::DEC_VAR, p == 0 ? chk0n : p == 1 ? chk1n : chk2n,
+                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, smem + p * L5::DEC_VAR, p == 0 ? chk0n : p == 1 ? chk1n : chk2n,
                                  p == 0 ? chk0t : p == 1 ? chk1t : chk2t, sg, status);
             });
             const uint2 r = rt[96 + lane];
             const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFu));
             if (r.y != REC_IDLE) {
                 const uint32_t v = r.y >> 8;
-                dec_cw<K, false>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, smem + v * L5::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
+                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, smem + v * L5::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
             }
         }
         __syncwarp();
@@ -538,7 +688,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
             if (!first) *reinterpret_cast<uint4*>(OUT) = carry[0];                   // bytes [0, pad): the previous tile's tail
         }
         __syncwarp();
-        if constexpr (WORDS) dec_phase_a_words<K>(S, OUT, pad, lane); else dec_phase_a<K>(S, OUT, pad, lane);
+        if constexpr (WORDS) dec_phase_a_words<K>(S, OUT, pad, lane); else dec_phase_a5<K>(S, OUT, pad, lane);
         fence_async_smem();
         __syncwarp();
         {   // the pixel side of the tile -> global: whole chunks by one bulk store, edge bytes of a stretch one by one

@@ -23,7 +23,17 @@ struct HeaderCache {
 struct SuperCache {
     struct Slot { uint16_t* d_map = nullptr; uint8_t* d_kv = nullptr; uint8_t key[48] = {}; uint32_t npass[3] = {}; bool valid = false; } slot[4];
 };
-struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; SuperCache* sup; const uint32_t* crc; };
+// The CTA-shared part of the v5 kernels' shared memory (plane tables with the embedded (de)scrambled symbols, parity / screen constants,
+// GF(27) tables, phase-B lane records: 16-26 KB) depends on the config only.  It is built once by a one-CTA setup kernel and kept on
+// the device; the kernels' prologue is then a plain copy (building it in every CTA cost ~8 us of a 150 us launch).  Entries are
+// written once (kernel + stream synchronise) and reused; when all are taken the device is synchronised before one is replaced.
+struct FastImageCache {
+    static constexpr int N = 8, BYTES = 32 * 1024;
+    struct Entry { uint8_t key[40] = {}; bool valid = false; } e[N];
+    uint8_t* base = nullptr;   // N x BYTES
+    int next = 0;
+};
+struct DevTables { const GfTables* gf; const RsTables* rs; int sm_count; HeaderCache* hdr; SuperCache* sup; const uint32_t* crc; FastImageCache* img; };
 // first codeword of every band that the general kernels still have to code (the tiled kernels did the ones before)
 struct CwStart { uint64_t c[9]; };
 // what a super-tile launch leaves to the general kernels: codewords from cs.c[b] on, band symbols from m_start, 6-pixel units from unit_start
