@@ -12,6 +12,9 @@
 // access is a 128-bit transfer inside a contiguous run (one RGB run, nine body runs of 338 B), the 9-band
 // transpose and all table look-ups stay in shared memory, the grid is persistent (SM count x resident CTAs)
 // so the row table is staged once per CTA, and HBM traffic is exactly the algorithmic 3 B/px + 9 B/word.
+#include <cuda.h>
+
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -42,7 +45,8 @@ struct FastParams {
     uint32_t n_frames;
     uint32_t* status;       // decode: {ok, n_corrected} per frame
     uint32_t chk_nz[7], chk_two[7]; // decode: sum of T_i[13*st_i] per scrambler phase (6) and for p0==0
-    uint32_t flags;         // v5: 1 | delay << 8 = staggered start of every other warp (k_fast5.cuh, T3C_V5_FLAGS)
+    uint32_t flags;         // v5: 1 | delay << 8 = staggered start of every other warp (k_fast5.cuh, T3C_V5_FLAGS); 2 = decode: runs arrive by one 3-D tensor copy
+    uint64_t band_stride;   // v5 decode with the tensor copy: bytes between the runs of neighbouring bands (26 * codewords per band, a multiple of 16)
 };
 
 template <int K> struct Cfg {
@@ -1591,8 +1595,47 @@ static int launch_v5_dec(const DevTables& T, FastParams P, const Geom& g, cudaSt
     uint64_t grid = (uint64_t)T.sm_count * occ;
     if (grid > need) grid = need;
     if (!grid) return n;
-    P.flags = v5_flags();
-    k_decode_v5<K, WORDS><<<(unsigned)grid, 32 * L5::DEC_WARPS, L5::TOTAL_DEC, st>>>(P, g, img);
+    P.flags = v5_flags() & ~2u;
+    // One 3-D tensor copy (TMA, SASS UTMALDG) per mini-tile instead of nine bulk copies when the nine runs of a tile form a regular
+    // box: every band holds the same number of codewords and the band pitch 26 * ncw is a multiple of 16 bytes (8K / 4K / 1080p frames
+    // at k = 20 are) and frames start on 16-byte boundaries.  Tensor {band pitch, 9 bands, frames} of 16-bit elements over the input
+    // buffer, box {RUN_PITCH, 9, 1} at the 16-byte aligned column below the runs' first byte 52 + 338 * tile.  Tiles whose box would
+    // reach past the band's row (the last one or two of a frame) keep the nine bulk copies.
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof tmap);
+    if (!(v5_flags() & 4u)) {
+        bool regular = P.in_stride % 16 == 0 || P.n_frames == 1;
+        for (int b = 1; b < 9; ++b) regular = regular && g.ncw[b] == g.ncw[0];
+        const uint64_t pitch = 26 * g.ncw[0];
+        regular = regular && pitch % 16 == 0 && pitch >= 4096 && ((uintptr_t)P.in & 15) == 0 && g.cw_base[0] == 0;
+        if (regular) {
+            typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                          CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            static encode_fn enc = nullptr;
+            static bool tried = false;
+            if (!tried) {
+                tried = true;
+                void* fn = nullptr;
+                cudaDriverEntryPointQueryResult qr;
+                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) enc = (encode_fn)fn;
+                else cudaGetLastError();
+            }
+            if (enc) {
+                const cuuint64_t frame_pitch = P.n_frames > 1 ? P.in_stride : (9 * pitch + 4096 + 15) / 16 * 16;
+                // 16-bit elements: a box side holds at most 256 elements, a run needs 368 bytes (runs start on even bytes: x = 2 + 169 * tile)
+                const cuuint64_t dims[3] = {pitch / 2, 9, P.n_frames}, strides[2] = {pitch, frame_pitch};
+                const cuuint32_t box[3] = {(cuuint32_t)L5::RUN_PITCH / 2, 9, 1}, estr[3] = {1, 1, 1};
+                if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint8_t*>(P.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                    P.flags |= 2u;
+                    P.band_stride = pitch;
+                }
+            }
+        }
+    }
+    if (getenv("T3C_DEBUG")) std::fprintf(stderr, "t3c: k_decode_v5<%d,%d> grid %u, flags %#x, band pitch %llu (tensor copy %s)\n", K, (int)WORDS, (unsigned)grid, P.flags,
+                                          (unsigned long long)P.band_stride, (P.flags & 2u) ? "on" : "off");
+    k_decode_v5<K, WORDS><<<(unsigned)grid, 32 * L5::DEC_WARPS, L5::TOTAL_DEC, st>>>(P, g, img, tmap);
     return n + 1;
 }
 template <class Kern>

@@ -172,9 +172,11 @@ template <int K, bool WORDS = false> struct Cfg5 {
     // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | GF(27) tables | records
     static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
     static constexpr int DEC_REC = DEC_GF + ((int)sizeof(GfTables) + 15) / 16 * 16;
-    static constexpr int DEC_WARP = DEC_REC + REC_BYTES;
-    static constexpr int DEC_WARPS = (SMEM_MAX - 256 - DEC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - 256 - DEC_WARP) / WARP_BYTES : 32;
-    static constexpr int TOTAL_DEC = 256 + DEC_WARP + DEC_WARPS * WARP_BYTES;
+    static constexpr int DEC_IMAGE = DEC_REC + REC_BYTES;                       // what the image holds
+    static constexpr int DEC_WARP = (DEC_IMAGE + 127) / 128 * 128;              // per-warp blocks start 128-byte aligned (tensor copies land there)
+    static constexpr int DEC_WARP_BYTES = (WARP_BYTES + 127) / 128 * 128;       // decode: R | OUT | S | carry | barrier
+    static constexpr int DEC_WARPS = (SMEM_MAX - 256 - DEC_WARP) / DEC_WARP_BYTES < 32 ? (SMEM_MAX - 256 - DEC_WARP) / DEC_WARP_BYTES : 32;
+    static constexpr int TOTAL_DEC = 256 + DEC_WARP + DEC_WARPS * DEC_WARP_BYTES;
 };
 constexpr uint32_t REC_IDLE = 0xFFFFFFFFu;
 // records from the variant-sorted pass maps (build_pass_map): after the maps are in `maps` (3 x 128 bytes) and a barrier
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables*
         reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid + 1] = c.two;
     }
     __syncthreads();
-    for (int i = tid; i < L5::DEC_WARP / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
+    for (int i = tid; i < L5::DEC_IMAGE / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
 }
 
 template <int K, bool WORDS>
@@ -596,7 +598,7 @@ __device__ __forceinline__ void dec_phase_a5(const uint8_t* S, uint8_t* OUT, uin
 }
 
 template <int K, bool WORDS>
-__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5(FastParams P, Geom g, const uint8_t* __restrict__ image)
+__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5(FastParams P, Geom g, const uint8_t* __restrict__ image, const __grid_constant__ CUtensorMap tmap)
 {
     using L = Cfg3<K>;
     using L5 = Cfg5<K, WORDS>;
@@ -604,17 +606,17 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((256u - (smem_u32(smem_raw) & 255u)) & 255u); // 256-byte aligned: PRMT drops a symbol (x4) into the low address byte
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t* OUT = smem + L5::DEC_WARP + warp * L5::WARP_BYTES; // the pixel side of the tile on its way out
+    uint8_t* R = smem + L5::DEC_WARP + warp * L5::DEC_WARP_BYTES; // the nine body runs as they lie in the frame (loaded one tile ahead); 128-byte aligned
+    uint8_t* OUT = R + L5::RUNS_BYTES;                          // the pixel side of the tile on its way out
     uint8_t* S = OUT + L5::IN_BYTES;                            // descrambled stream symbols (plain)
-    uint8_t* R = S + L::S_BYTES;                                // the nine body runs as they lie in the frame (bulk-loaded one tile ahead)
-    uint4* carry = reinterpret_cast<uint4*>(R + L5::RUNS_BYTES);
-    const uint32_t bar = smem_u32(R + L5::RUNS_BYTES + L5::CARRY_BYTES);
+    uint4* carry = reinterpret_cast<uint4*>(S + L::S_BYTES);
+    const uint32_t bar = smem_u32(S + L::S_BYTES + L5::CARRY_BYTES);
     const GfTables& sg = *reinterpret_cast<const GfTables*>(smem + L5::DEC_GF);
     const uint2* rec = reinterpret_cast<const uint2*>(smem + L5::DEC_REC);
     {   // the CTA-shared tables: a copy of the image k_v5_image_dec made once for this config (FastImageCache)
         const uint4* src = reinterpret_cast<const uint4*>(image);
         uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < L5::DEC_WARP / 16; i += TPB) dst[i] = __ldg(src + i);
+        for (int i = tid; i < L5::DEC_IMAGE / 16; i += TPB) dst[i] = __ldg(src + i);
         if (lane == 0) { mbar_init(bar, 9); fence_mbar_init(); }
     }
     __syncthreads();
@@ -634,9 +636,21 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
         mbar_expect_tx(bar, bytes);
         if (bytes) bulk_g2s(smem_u32(R + PITCH * lane), P.in + a0, bytes, bar);
     };
+    // the same nine (16-byte aligned supersets of the) runs by ONE 3-D tensor copy when the frame's runs form a regular box
+    // (launch_v5_dec): same layout in R as the bulk copies give; all nine lanes arrive on the barrier, lane 0 carries the byte count
+    // (a box must start on a 16-byte boundary -- a tensor copy from an unaligned column raises an illegal-instruction fault,
+    // tools/probe/tma3d_probe.cu -- so it is the aligned superset of the runs, exactly what the bulk copies fetch)
+    auto tensor_tile = [&](uint32_t tile) { return (P.flags & 2u) && ((52ull + 338ull * tile) & ~15ull) + PITCH <= P.band_stride; };
+    auto fetch_tensor = [&](uint32_t f, uint32_t tile) {
+        fence_async_smem();
+        mbar_expect_tx(bar, lane == 0 ? 9u * PITCH : 0u);
+        if (lane == 0)
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                         ::"r"(smem_u32(R)), "l"(&tmap), "r"((int)(((52u + 338u * tile) & ~15u) >> 1)), "r"(0), "r"((int)f), "r"(bar) : "memory");   // x in 16-bit elements
+    };
     TileCursor c;
     cursor_seek<PIX>(c, P, g, P.out_stride, P.in_stride, mt_lo, lane);
-    if (lane < 9) fetch(c.run);
+    if (lane < 9) { if (tensor_tile(c.tile)) fetch_tensor(c.f, c.tile); else fetch(c.run); }
     stagger_start(P.flags, warp, mt_hi - mt_lo);
     uint32_t phase = 0;
     bool first = true;
@@ -645,7 +659,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
         const uint32_t pad = (uint32_t)c.pix & 15u, padb = (uint32_t)c.run & 15u;
         mbar_wait(bar, phase);
         phase ^= 1;
-        if (last) { // only the clipped end of the buffer (the last chunks of the last frame, which the bulk copy left out) is fetched here
+        if (last && !tensor_tile(c.tile)) { // only the clipped end of the buffer (the last chunks of the last frame, which the bulk copy left out) is fetched here
             if (lane < 9) {
                 const uint64_t a0 = c.run - padb, a1 = a0 + ((padb + L::RUN + 15u) & ~15u);
                 if (a1 > in_limit)
@@ -682,7 +696,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
         __syncwarp();
         TileCursor nx = c;
         cursor_next<PIX>(nx, P, g, P.out_stride, P.in_stride, lane);
-        if (left > 1 && lane < 9) fetch(nx.run);                                    // R is free again: next tile's runs on their way
+        if (left > 1 && lane < 9) { if (tensor_tile(nx.tile)) fetch_tensor(nx.f, nx.tile); else fetch(nx.run); }  // R is free again: next tile's runs on their way
         if (lane == 0) {
             bulk_wait_read();                                                        // the previous tile's bulk store has read OUT
             if (!first) *reinterpret_cast<uint4*>(OUT) = carry[0];                   // bytes [0, pad): the previous tile's tail
