@@ -245,6 +245,116 @@ static __device__ __forceinline__ bool rs_decode_residual(const GfTables& g, uin
     return rs_decode_core(g, c, k, true, S, true);
 }
 
+// The Chien tables lie directly behind the GF(27) tables (HostTables; the tiled kernels copy both into their shared image)
+__device__ __forceinline__ const uint32_t* chien_of(const GfTables* gf) { return reinterpret_cast<const uint32_t*>(gf + 1); }
+
+// Slow path of the tiled decoders (repaired code, strict acceptance): a bounded-distance decoder in registers with uniform control
+// flow, so that a warp whose lanes hold codewords with different error counts does not serialise.  Under strict acceptance
+// (rs_decode_core above: L <= t, deg sigma == L, L distinct roots) a block is corrected iff a codeword lies within distance t, and
+// then to that codeword -- which any bounded-distance decoder finds -- so this one returns what rs_decode_residual returns:
+//  * syndromes from the parity residual (res_lo/res_hi: parity symbols 0..3 / 4..7 as bytes);
+//  * Berlekamp-Massey (Massey's form, OLD:572-600) on T+1 coefficients with x^m B kept pre-shifted: while L <= T neither sigma nor
+//    x^m B has a term above x^T (deg x^m B <= n+1-L), and L > T is final, so dropping higher terms changes no accepted result;
+//  * roots of sigma for all 26 positions at once on GF(3) bit planes (ChienTables); fewer than L roots covers deg sigma < L;
+//  * Forney with Omega = S sigma mod x^T (the key equation makes the higher coefficients vanish for an accepted locator) and the
+//    formal derivative in characteristic 3; the L corrections go straight to the data symbols already stored at dst (stride 9).
+// status[0] = 0 when a block is rejected, status[1] += corrected symbols (count), aggregated over the lanes that are here together.
+template <int K>
+static __device__ __noinline__ void rs_bd_fix(const GfTables& g, const uint32_t* __restrict__ chien, uint8_t* dst, uint32_t res_lo, uint32_t res_hi,
+                                              uint32_t* status, bool count)
+{
+    constexpr int R = 26 - K, T = R / 2, KI = (24 - K) / 2;
+    uint32_t S[R];
+    {
+        uint32_t p[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) p[m] = ((m < 4 ? res_lo : res_hi) >> (8 * (m & 3))) & 0xFFu;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            uint32_t acc = gmul(g, p[0], g.syn[KI][j][0]);
+#pragma unroll
+            for (int m = 1; m < R; ++m) acc = gadd(g, acc, gmul(g, p[m], g.syn[KI][j][m]));
+            S[j] = acc;
+        }
+    }
+    uint32_t sig[T + 1], Bs[T + 1];                       // sigma and x^m B
+#pragma unroll
+    for (int i = 0; i <= T; ++i) sig[i] = Bs[i] = 0;
+    sig[0] = 1;
+    Bs[1] = 1;
+    uint32_t L = 0;
+    bool bad = false;
+#pragma unroll
+    for (int n = 0; n < R; ++n) {
+        uint32_t delta = S[n];
+#pragma unroll
+        for (int i = 1; i <= T; ++i)
+            if (i <= n) delta = gadd(g, delta, gmul(g, sig[i], S[n - i]));
+        const bool grow = delta != 0 && 2 * L <= (uint32_t)n;
+        const uint32_t nd = g.neg[delta], invd = g.inv[delta];
+        uint32_t old[T + 1];
+#pragma unroll
+        for (int i = 0; i <= T; ++i) old[i] = sig[i];
+#pragma unroll
+        for (int i = 1; i <= T; ++i) sig[i] = gadd(g, sig[i], gmul(g, nd, Bs[i]));   // delta = 0 adds nothing; x^m B has no constant term
+#pragma unroll
+        for (int i = T; i >= 1; --i) Bs[i] = grow ? gmul(g, old[i - 1], invd) : Bs[i - 1];
+        if (grow) L = (uint32_t)n + 1 - L;
+        bad = bad || L > (uint32_t)T;
+    }
+    uint32_t z[3];
+    {
+        Planes a[3] = {{0x09249249u, 0}, {0x09249249u, 0}, {0x00009249u, 0}};                  // sigma_0 = 1 at the 10 + 10 + 6 positions
+#pragma unroll
+        for (int j = 1; j <= T; ++j) {
+            const uint2* e = reinterpret_cast<const uint2*>(chien + ((j - 1) * 27 + sig[j]) * 6);
+            const uint2 e0 = e[0], e1 = e[1], e2 = e[2];
+            gf3_add(a[0], e0.x, e1.y);
+            gf3_add(a[1], e0.y, e2.x);
+            gf3_add(a[2], e1.x, e2.y);
+        }
+#pragma unroll
+        for (int w = 0; w < 3; ++w) z[w] = ~(a[w].nz | (a[w].nz >> 1) | (a[w].nz >> 2)) & (w < 2 ? 0x09249249u : 0x00009249u);
+    }
+    const bool ok = !bad && (uint32_t)(__popc(z[0]) + __popc(z[1]) + __popc(z[2])) == L;
+    uint32_t Om[T], sp[T];
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+        uint32_t acc = S[i];
+#pragma unroll
+        for (int a = 0; a < i; ++a) acc = gadd(g, acc, gmul(g, S[a], sig[i - a]));
+        Om[i] = acc;
+        sp[i] = (i + 1) % 3 == 0 ? 0u : ((i + 1) % 3 == 1 ? sig[i + 1] : (uint32_t)g.neg[sig[i + 1]]);   // 2a = -a
+    }
+#pragma unroll
+    for (int e = 0; e < T; ++e) {
+        if (ok && (uint32_t)e < L) {
+            const uint32_t w = z[0] ? 0u : (z[1] ? 1u : 2u), zw = z[0] ? z[0] : (z[1] ? z[1] : z[2]);
+            const uint32_t b = (uint32_t)__ffs((int)zw) - 1u, pos = 10u * w + (b * 11u >> 5);    // b / 3 for b < 32
+            const uint32_t low = zw & (0u - zw);
+            if (w == 0) z[0] ^= low; else if (w == 1) z[1] ^= low; else z[2] ^= low;
+            const uint32_t x = g.exp[pos ? 26u - pos : 0u];
+            uint32_t num = Om[T - 1], den = sp[T - 1];
+#pragma unroll
+            for (int d = T - 2; d >= 0; --d) {
+                num = gadd(g, gmul(g, num, x), Om[d]);
+                den = gadd(g, gmul(g, den, x), sp[d]);
+            }
+            const uint32_t mag = gmul(g, g.neg[num], g.inv[den]);
+            if (pos < (uint32_t)K) dst[9 * pos] = gsub(g, dst[9 * pos], mag);
+        }
+    }
+    // one status update per frame and warp: with every codeword of an 8K frame dirty, 6.8 M same-address atomics are 4 ms on their own
+    const uint32_t am = __activemask();
+    const uint32_t grp = __match_any_sync(am, reinterpret_cast<uintptr_t>(status));
+    const uint32_t fixed = __reduce_add_sync(grp, ok && count ? L : 0u);
+    const uint32_t failed = __ballot_sync(am, !ok) & grp;
+    if (((uint32_t)threadIdx.x & 31u) == (uint32_t)__ffs((int)grp) - 1u) {
+        if (fixed) atomicAdd(&status[1], fixed);
+        if (failed) atomicExch(&status[0], 0u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-pixel arithmetic
 // ---------------------------------------------------------------------------------------------

@@ -835,7 +835,7 @@ __device__ __forceinline__ void enc_phase_b(const uint8_t* S, uint8_t* U, const 
 // full-rate pipe (bytes >= 32 -- out-of-alphabet symbols, OLD:28-31 -- are reduced mod 27 first; 27..31 alias 0..4 inside the tables)
 template <int K, bool PRESCALED = true>
 __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, uint32_t chk_nz, uint32_t chk_two,
-                                       const GfTables& sg, uint32_t* status, bool count = true)
+                                       const GfTables& sg, const uint32_t* chien, uint32_t* status, bool count = true)
 {
     constexpr int PLANE = 4 * 26 * 32;
     // the codeword's 26 symbols as 7 words (it starts on an even byte), then one PRMT per symbol builds the
@@ -876,31 +876,19 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
     for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
     gf3_add(acc, acc2.nz, acc2.two);
     if (((acc.nz ^ chk_nz) | (acc.two ^ chk_two)) & ~0xFFu) { // the low bytes carry the embedded symbols
-        // slow path: full decode of this codeword (descrambled), then rewrite its data symbols.  The screen's sum minus the
-        // clean-codeword constant is the parity residual, from which the syndromes follow without another pass over the block
-        uint8_t cwd[26], orig[26], res[8];
-        for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tab_v + (PRESCALED ? (uint32_t)src[i] : 4u * (src[i] % 27u)) + 128 * i);
-        {
-            Planes d{acc.nz, acc.two};
-            gf3_add(d, chk_nz, chk_nz ^ chk_two);                  // minus the constant: -x keeps nz and flips two where nz is set
-            uint32_t lo, hi;
-            planes_to_parity<K>(d.nz, d.two, lo, hi);
-            for (int j = 0; j < 4; ++j) { res[j] = (uint8_t)(lo >> (8 * j)); res[4 + j] = (uint8_t)(hi >> (8 * j)); }
-        }
-        if (!rs_decode_residual(sg, cwd, K, res)) {
-            atomicExch(&status[0], 0u);
-        } else {
-            uint32_t nfix = 0;
-            for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
-            if (nfix && count) atomicAdd(&status[1], nfix);
-            for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
-        }
+        // slow path: the screen's sum minus the clean-codeword constant is the parity residual, from which the bounded-distance
+        // decoder (dev.cuh) finds the error values and repairs the data symbols stored above
+        Planes d{acc.nz, acc.two};
+        gf3_add(d, chk_nz, chk_nz ^ chk_two);                      // minus the constant: -x keeps nz and flips two where nz is set
+        uint32_t lo, hi;
+        planes_to_parity<K>(d.nz, d.two, lo, hi);
+        rs_bd_fix<K>(sg, chien, dst, lo, hi, status, count);
     }
 }
 // ---- decode phase B: nine staged runs (x4) -> syndrome screen / slow path -> descrambled stream symbols
 template <int K, bool PRESCALED = true>
 __device__ __forceinline__ void dec_phase_b(const uint8_t* U, uint8_t* S, const WarpMeta3& meta, const uint8_t* pmap, uint32_t tabA32,
-                                            const uint8_t* tabA, const uint32_t* chk, const GfTables& sg, uint32_t* status, int lane)
+                                            const uint8_t* tabA, const uint32_t* chk, const GfTables& sg, const uint32_t* chien, uint32_t* status, int lane)
 {
     using L = Cfg3<K>;
     // ---- phase B: syndrome screen per codeword (variant-sorted lanes); descrambled data symbols -> stream order
@@ -914,7 +902,7 @@ __device__ __forceinline__ void dec_phase_b(const uint8_t* U, uint8_t* S, const 
         asm volatile("" : "+r"(pa));
         const uint8_t* src = U + L::RUN_PITCH * b + ((uint32_t)meta.run_lo[b] & 15u) + 26 * cl;
         uint8_t* dst = S + cw + (9 * K - 9) * cl;                       // 9K*cl + b
-        dec_cw<K, PRESCALED>(src, dst, pa, tabA + v * L::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
+        dec_cw<K, PRESCALED>(src, dst, pa, tabA + v * L::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, chien, status);
     }
 }
 // ---- decode phase A: 26 stream symbols at src (even address) -> six pixels -> 18 RGB bytes at dst (even address)
@@ -1217,7 +1205,7 @@ __global__ void __launch_bounds__(FAST_TPB, 3) k_decode_rgb_v3(FastParams P, Geo
             r0[1] = (uint8_t)(4u * sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][(r0[1] >> 2) % 27u]]);
         }
         __syncwarp();
-        dec_phase_b<K>(U, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, P.status + 2 * f, lane);
+        dec_phase_b<K>(U, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, chien_of(gf), P.status + 2 * f, lane);
         __syncwarp();
         // ---- phase A: 26 stream symbols -> six pixels -> 18 RGB bytes per lane (units dealt even / odd)
         const uint64_t g_lo = P.out_stride * f + 3ull * L::PX * tile;
@@ -1483,7 +1471,7 @@ __global__ void __launch_bounds__(32 * Cfg4<K, WORDS>::DEC_WARPS, 1) k_decode_rg
             r0[1] = sg.scr[st_of(g, 0, 1)][sg.dsc[g.st[1]][r0[1] % 27u]];
         }
         __syncwarp();
-        dec_phase_b<K, false>(R, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, P.status + 2 * f, lane);
+        dec_phase_b<K, false>(R, S, meta, smem + L::DEC_MAP + 128 * (tile % 3u), tabA32, smem + L::DEC_A, chk, sg, chien_of(gf), P.status + 2 * f, lane);
         __syncwarp();
         if (mt + 1 < mt_hi && lane < 9) fetch(mt + 1);                       // R is free again: next tile's runs on their way
         const uint64_t g_lo = P.out_stride * f + (uint64_t)PIX * tile;

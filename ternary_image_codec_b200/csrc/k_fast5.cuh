@@ -169,9 +169,10 @@ template <int K, bool WORDS = false> struct Cfg5 {
     static constexpr int ENC_WARP = ENC_REC + REC_BYTES;
     static constexpr int ENC_WARPS = (SMEM_MAX - ENC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - ENC_WARP) / WARP_BYTES : 32;
     static constexpr int TOTAL_ENC = ENC_WARP + ENC_WARPS * WARP_BYTES;
-    // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | GF(27) tables | records
+    // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | GF(27) + Chien tables | records
     static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
-    static constexpr int DEC_REC = DEC_GF + ((int)sizeof(GfTables) + 15) / 16 * 16;
+    static constexpr int CHIEN_BYTES = ((26 - K) / 2) * 27 * 24;                // the locator has at most t coefficients besides sigma_0
+    static constexpr int DEC_REC = DEC_GF + ((int)sizeof(GfTables) + CHIEN_BYTES + 15) / 16 * 16;
     static constexpr int DEC_IMAGE = DEC_REC + REC_BYTES;                       // what the image holds
     static constexpr int DEC_WARP = (DEC_IMAGE + 127) / 128 * 128;              // per-warp blocks start 128-byte aligned (tensor copies land there)
     static constexpr int DEC_WARP_BYTES = (WARP_BYTES + 127) / 128 * 128;       // decode: R | OUT | S | carry | barrier
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables*
         blk[26 * 32 + rem] = pl[i][xm][1];
     }
     load_gf(sg, gf);
+    for (int i = tid; i < L5::CHIEN_BYTES / 4; i += TPB) reinterpret_cast<uint32_t*>(&sg + 1)[i] = chien_of(gf)[i];
     for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
     __syncthreads();
     for (int t = tid; t < 3 * 128; t += TPB) build_records<K, L5::RUN_PITCH>(reinterpret_cast<uint2*>(smem + L5::DEC_REC), maps, g, t);
@@ -483,29 +485,16 @@ static __device__ __noinline__ void dec_cw_mod27(uint8_t* src)
 {
     for (int i = 0; i < 26; ++i) src[i] = (uint8_t)(src[i] % 27u);   // in place in the staged run: the codeword belongs to this lane alone
 }
-// a codeword that fails the screen: full decode (descrambled), then its data symbols are rewritten.  The screen's sum minus the
-// clean-codeword constant is the parity residual, from which the syndromes follow without another pass over the block
+// a codeword that fails the screen: the screen's sum minus the clean-codeword constant is the parity residual, from which the
+// bounded-distance decoder (dev.cuh rs_bd_fix) repairs the data symbols the hot path has already stored
 template <int K>
-static __device__ __noinline__ void dec_cw_dirty(const uint8_t* src, uint8_t* dst, const uint8_t* tab_v, uint32_t acc_nz, uint32_t acc_two, uint32_t chk_nz,
-                                                 uint32_t chk_two, const GfTables& sg, uint32_t* status)
+static __device__ __noinline__ void dec_cw_dirty(uint8_t* dst, uint32_t acc_nz, uint32_t acc_two, uint32_t chk_nz, uint32_t chk_two, const GfTables& sg, uint32_t* status)
 {
-    uint8_t cwd[26], orig[26], res[8];
-    for (int i = 0; i < 26; ++i) cwd[i] = orig[i] = (uint8_t)*reinterpret_cast<const uint32_t*>(tab_v + 4u * (src[i] % 27u) + 128 * i);
-    {
-        Planes d{acc_nz, acc_two};
-        gf3_add(d, chk_nz, chk_nz ^ chk_two);                  // minus the constant: -x keeps nz and flips two where nz is set
-        uint32_t lo, hi;
-        planes_to_parity<K>(d.nz, d.two, lo, hi);
-        for (int j = 0; j < 4; ++j) { res[j] = (uint8_t)(lo >> (8 * j)); res[4 + j] = (uint8_t)(hi >> (8 * j)); }
-    }
-    if (!rs_decode_residual(sg, cwd, K, res)) {
-        atomicExch(&status[0], 0u);
-    } else {
-        uint32_t nfix = 0;
-        for (int i = 0; i < 26; ++i) nfix += cwd[i] != orig[i];
-        if (nfix) atomicAdd(&status[1], nfix);
-        for (int i = 0; i < K; ++i) dst[9 * i] = cwd[i];
-    }
+    Planes d{acc_nz, acc_two};
+    gf3_add(d, chk_nz, chk_nz ^ chk_two);                      // minus the constant: -x keeps nz and flips two where nz is set
+    uint32_t lo, hi;
+    planes_to_parity<K>(d.nz, d.two, lo, hi);
+    rs_bd_fix<K>(sg, chien_of(&sg), dst, lo, hi, status, true);   // the image keeps the Chien tables behind the GF(27) tables, as HostTables does
 }
 // ---- one codeword of decode phase B (see dec_cw, PRESCALED = false): 26 received symbols at src (even address) -> screen -> K descrambled
 // data symbols scattered at byte stride 9 from dst
@@ -544,7 +533,7 @@ __device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32
     for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
     gf3_add(acc, acc2.nz, acc2.two);
     if (((acc.nz ^ chk_nz) | (acc.two ^ chk_two)) & ~0xFFu)        // the low bytes carry the embedded symbols
-        dec_cw_dirty<K>(src, dst, tab_v, acc.nz, acc.two, chk_nz, chk_two, sg, status);
+        dec_cw_dirty<K>(dst, acc.nz, acc.two, chk_nz, chk_two, sg, status);
 }
 
 // pixel value -> RGB8 as value_to_rgb3 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84); the 2^23 magic is

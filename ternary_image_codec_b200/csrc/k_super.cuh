@@ -442,10 +442,10 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             uint8_t* dst = S + 9u * K * cl + b;
             const uint32_t toff = P.off_tab[ks] + v * 6656u;
             const uint32_t cnz = chk[6 * ks + 2 * v], ctw = chk[6 * ks + 2 * v + 1];
-            if (K == 20) dec_cw<20>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
-            else if (K == 22) dec_cw<22>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
-            else if (K == 24) dec_cw<24>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
-            else dec_cw<18>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, Q.status + 2 * f);
+            if (K == 20) dec_cw<20>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
+            else if (K == 22) dec_cw<22>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
+            else if (K == 24) dec_cw<24>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
+            else dec_cw<18>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
         }
         __syncthreads();                           // S complete, R dead
         SUP_TICK(6);

@@ -36,6 +36,11 @@ struct GfTables {
 constexpr int kRows = 26, kVals = 27;
 struct RowTable { uint64_t e[kRows][kVals]; };      // 5616 B
 // index: [arith][kidx] with kidx = (24-k)/2
+// Root search of the bounded-distance decoder on bit planes: e[j-1][v] holds v * alpha^(-i*j) for the 26 positions i as GF(3) trits,
+// ten positions per word, trit c of position i at bit 3*(i%10)+c of word i/10; words 0..2 are the nz plane, 3..5 the two plane.
+// 1 + sum_j sigma_j * alpha^(-i*j) over all positions at once is then one plane addition per coefficient; position i is a root where
+// its three nz bits are clear.  Lies directly behind GfTables in the device copy (chien_of below).
+struct ChienTables { uint32_t e[4][27][6]; };
 struct RsTables {
     RowTable row[2][4];
     uint8_t  gen[4][12];      // generator polynomials, low-first (OLD:501-516)
@@ -76,7 +81,8 @@ struct Geom {
     uint8_t  hdr[52];     // coded header (filled by the header kernel for device paths)
 };
 
-struct HostTables { GfTables gf; RsTables rs; };
+struct HostTables { GfTables gf; ChienTables ch; RsTables rs; };
+static_assert(offsetof(HostTables, ch) == sizeof(GfTables) && sizeof(GfTables) % 16 == 0, "ChienTables must follow GfTables directly (chien_of)");
 void build_tables(HostTables& t);
 void fast_check_constants(const HostTables& H, const Geom& g, uint32_t chk_nz[7], uint32_t chk_two[7]);
 

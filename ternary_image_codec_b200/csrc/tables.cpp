@@ -76,6 +76,16 @@ void build_tables(HostTables& T)
     for (int ki = 0; ki < 4; ++ki)
         for (int j = 0; j < 8; ++j)
             for (int m = 0; m < 8; ++m) g.syn[ki][j][m] = (uint8_t)gneg(ex[((j + 1) * (24 - 2 * ki + m)) % 26]);
+    for (int j = 1; j <= 4; ++j)
+        for (int v = 0; v < 27; ++v)
+            for (int i = 0; i < 26; ++i) {
+                const int s = (int)g.mul[v * 27 + ex[((26 - i) * j) % 26]];
+                Tr t = split(s);
+                for (int c = 0; c < 3; ++c) {
+                    if (t.t[c]) T.ch.e[j - 1][v][i / 10] |= 1u << (3 * (i % 10) + c);
+                    if (t.t[c] == 2) T.ch.e[j - 1][v][3 + i / 10] |= 1u << (3 * (i % 10) + c);
+                }
+            }
     // sanity: table multiply agrees with the polynomial product
     for (int a = 0; a < 27; ++a)
         for (int b = 0; b < 27; ++b)
