@@ -231,28 +231,15 @@ static __device__ __noinline__ bool rs_decode_thread(const GfTables& g, uint8_t*
     if (all0) return true;
     return rs_decode_core(g, c, k, fixed, S, strict);
 }
-// repaired arithmetic only: syndromes from the parity residual p[0..r) = parity(received data) - received parity, which the
-// tiled kernels' syndrome screen has already computed (S_j = sum_m syn[j][m] p_m: r*r products instead of 26*r)
-static __device__ __forceinline__ bool rs_decode_residual(const GfTables& g, uint8_t* c, int k, const uint8_t* p)
-{
-    const int r = 26 - k, ki = (24 - k) >> 1;
-    uint8_t S[8];
-    for (int j = 0; j < r; ++j) {
-        uint32_t acc = 0;
-        for (int m = 0; m < r; ++m) acc = gadd(g, acc, gmul(g, p[m], g.syn[ki][j][m]));
-        S[j] = (uint8_t)acc;
-    }
-    return rs_decode_core(g, c, k, true, S, true);
-}
-
 // The Chien tables lie directly behind the GF(27) tables (HostTables; the tiled kernels copy both into their shared image)
 __device__ __forceinline__ const uint32_t* chien_of(const GfTables* gf) { return reinterpret_cast<const uint32_t*>(gf + 1); }
 
 // Slow path of the tiled decoders (repaired code, strict acceptance): a bounded-distance decoder in registers with uniform control
 // flow, so that a warp whose lanes hold codewords with different error counts does not serialise.  Under strict acceptance
 // (rs_decode_core above: L <= t, deg sigma == L, L distinct roots) a block is corrected iff a codeword lies within distance t, and
-// then to that codeword -- which any bounded-distance decoder finds -- so this one returns what rs_decode_residual returns:
-//  * syndromes from the parity residual (res_lo/res_hi: parity symbols 0..3 / 4..7 as bytes);
+// then to that codeword -- which any bounded-distance decoder finds -- so this one returns what rs_decode_core(strict) returns on the same block:
+//  * syndromes from the parity residual p = parity(received data) - received parity, which the syndrome screen has already
+//    computed (res_lo/res_hi: symbols 0..3 / 4..7 as bytes): S_j = sum_m syn[j][m] p_m, r*r products instead of 26*r;
 //  * Berlekamp-Massey (Massey's form, OLD:572-600) on T+1 coefficients with x^m B kept pre-shifted: while L <= T neither sigma nor
 //    x^m B has a term above x^T (deg x^m B <= n+1-L), and L > T is final, so dropping higher terms changes no accepted result;
 //  * roots of sigma for all 26 positions at once on GF(3) bit planes (ChienTables); fewer than L roots covers deg sigma < L;

@@ -197,6 +197,8 @@ __device__ __forceinline__ void build_records(uint2* rec, const uint8_t* maps, c
 // and leave one of the two pipes idle most of the time (sm__pipe_fmaheavy 47 % + sm__pipe_alu 53 % of the elapsed cycles, back to back:
 // profiles/r02b_*); every other warp of a sub-partition therefore starts about half a tile period late, which keeps the two groups
 // in opposite phases (8K encode 160.8 -> 152.6 us).  flags = 1 | delay_cycles << 8 (T3C_V5_FLAGS overrides the default)
+constexpr int V5_CR = 91881, V5_CB = 116130;         // 1.402, 1.772 x 2^16 (value_to_rgb5)
+constexpr int V5_G1 = 1443411, V5_G2 = 2995303;      // 0.344136, 0.714136 x 2^22
 constexpr uint32_t V5_FLAGS_DEFAULT = 1u | (9000u << 8);
 __device__ __forceinline__ void stagger_start(uint32_t flags, int warp, uint32_t n_tiles)
 {
@@ -536,8 +538,12 @@ __device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32
         dec_cw_dirty<K>(dst, acc.nz, acc.two, chk_nz, chk_two, sg, status);
 }
 
-// pixel value -> RGB8 as value_to_rgb3 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84); the 2^23 magic is
-// OR-ed into the dequantised integers (one logic op each) instead of riding on the multiply-high's 64-bit addend (two register moves each)
+// pixel value -> RGB8 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84) in integers.  The
+// reference's float32 chain  r = y + 1.402 cr,  g = (y - 0.344136 cb) - 0.714136 cr,  b = y + 1.772 cb  followed by round-half-away
+// and the clamp is reproduced for every one of the 243 x 81 x 81 dequantised (Y, Cb, Cr) by fixed-point sums: 16 fraction bits for r and
+// b (their exact fractions are multiples of 0.002 / 0.004, never .5 for r; b has one exact tie, cb = -125, which the +32 keeps on the
+// round-half-away side), 22 bits for g (closest approach to a tie 5.6e-5).  tests/test_host_logic.py checks all 1 594 323 values
+// against the float32 chain.  No conversions, no F2I (quarter-rate pipe), and the clamped r / b leave through byte 2 of their sums.
 __device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
 {
     const uint32_t q = __umulhi(A, 17674763u);                 // A / 243, exact for A < 3^13
@@ -545,14 +551,16 @@ __device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
     const uint32_t ur = __umulhi(q, 53024288u);                // q / 81, exact for q < 6561
     const uint32_t ub = q - 81u * ur;
     // Y = (510 Yq + 241) / 484 (dev.cuh dequant_y; <= 255 for Yq <= 242), C = min((64 u + 10) / 20, 255)
-    const float y = __fadd_rn(__uint_as_float(__umulhi(Yq * 510u + 241u, 8873899u) | 0x4B000000u), -8388608.0f);
-    const float cb = __fadd_rn(__uint_as_float(min(__umulhi(32u * ub + 5u, 429496730u), 255u) | 0x4B000000u), -8388736.0f);
-    const float cr = __fadd_rn(__uint_as_float(min(__umulhi(32u * ur + 5u, 429496730u), 255u) | 0x4B000000u), -8388736.0f);
-    const float r = __fadd_rn(y, __fmul_rn(1.402f, cr));
-    const float g = __fsub_rn(__fsub_rn(y, __fmul_rn(0.344136f, cb)), __fmul_rn(0.714136f, cr));
-    const float b = __fadd_rn(y, __fmul_rn(1.772f, cb));
-    const uint32_t Rb = floor_sat_u8(__fadd_rd(r, 0.5f)), Gb = floor_sat_u8(__fadd_rd(g, 0.5f)), Bb = floor_sat_u8(__fadd_rd(b, 0.5f));
-    return Rb + 256u * Gb + 65536u * Bb;                                       // R | G<<8 | B<<16
+    const int Y = (int)__umulhi(Yq * 510u + 241u, 8873899u);
+    // (96 u + 15) / 30 rather than (32 u + 5) / 10: a multiplier that is not a power of two stays on the multiply pipe (the logic pipe is the busy one)
+    const int Cb = (int)min(__umulhi(96u * ub + 15u, 143165577u), 255u);
+    const int Cr = (int)min(__umulhi(96u * ur + 15u, 143165577u), 255u);
+    const int Y16 = Y << 16, Y22 = Y << 22;
+    // add the constant, clamp to [0, max] in one instruction each (VIADDMNMX.RELU)
+    const uint32_t r = (uint32_t)__viaddmin_s32_relu(Cr * V5_CR + Y16, 32768 - 128 * V5_CR, 0xFFFFFF);
+    const uint32_t b = (uint32_t)__viaddmin_s32_relu(Cb * V5_CB + Y16, 32768 + 32 - 128 * V5_CB, 0xFFFFFF);
+    const uint32_t g = (uint32_t)__viaddmin_s32_relu(Cr * -V5_G2 + (Cb * -V5_G1 + Y22), 2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22;
+    return __byte_perm(__byte_perm(r, g, 0x3042), b, 0x3610);                  // R | G<<8 | B<<16 (byte 3 of the clamped r is 0)
 }
 // ---- decode phase A: 26 stream symbols at S + a (even) -> six pixels -> 18 RGB bytes at dst (even address): four 32-bit stores and one
 // 16-bit store, aligned per lane by funnel shifts (see store26)

@@ -37,7 +37,7 @@ def test_gf3_add_is_three_lop3():
 
 
 def _const(name, text=KFAST):
-    m = re.search(name + r"\s*=\s*(\d+)u", text)
+    m = re.search(name + r"\s*=\s*(\d+)u?\b", text)
     assert m, name
     return int(m.group(1))
 
@@ -189,6 +189,40 @@ def test_super_tile_plan_rejects_what_the_kernels_do_not_take():
     assert t3.super_plan(t3.make_config(profile=1, uep=(0, 1, 0, 1, 0, 1, 0, 1, 0)), 100) is None            # no full super-tile in so short a frame
     three = t3.make_config(profile=1, uep=(0, 1, 2, 0, 1, 2, 0, 1, 2))                                        # k = 24, 22, 20: lcm(26, 24, 22, 20) = 17160 symbols per band
     assert t3.super_path_available(three) and t3.super_plan(three, 7680 * 4320 // 2) is None                  # ... does not fit shared memory: general kernels
+
+
+def test_v5_fixed_point_colour_matrix_matches_float32_reference_on_all_values():
+    """k_fast5.cuh value_to_rgb5: the fixed-point YCbCr -> RGB sums equal the reference's float32 chain + round-half-away + clamp
+    (IMG:57-66 after dequantize_ycbcr, IMG:79-84) for every one of the 243 x 81 x 81 pixel values a 13-trit half-word can hold."""
+    K5 = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "k_fast5.cuh")).read()
+    c = lambda n: _const(n, K5)
+    CR, CB, G1, G2 = c("V5_CR"), c("V5_CB"), c("V5_G1"), c("V5_G2")
+    body = K5[K5.index("uint32_t value_to_rgb5"):]
+    assert "32768 + 32 - 128 * V5_CB" in body and "2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22" in body
+    assert "__umulhi(96u * ub + 15u, 143165577u)" in body and "__umulhi(96u * ur + 15u, 143165577u)" in body
+    u64 = np.arange(81, dtype=np.int64)
+    assert np.array_equal(((96 * u64 + 15) * 143165577) >> 32, (64 * u64 + 10) // 20)
+    f = np.float32
+    Yq, u = np.arange(243), np.arange(81)
+    Y = (Yq * 510 + 241) // 484                                             # dev.cuh dequant_y / dequant_c, pinned by the parity tests
+    C = np.minimum((64 * u + 10) // 20, 255)
+    assert Y.max() == 255
+    y, cb, cr = Y.astype(f)[:, None, None], (C.astype(f) - f(128))[None, :, None], (C.astype(f) - f(128))[None, None, :]
+    rf = (y + f(1.402) * cr) + 0 * cb
+    gf = (y - f(0.344136) * cb) - f(0.714136) * cr
+    bf = (y + f(1.772) * cb) + 0 * cr
+    rnd = lambda x: np.clip(np.where(x <= 0, 0, np.floor(x.astype(np.float64) + 0.5)), 0, 255).astype(np.int64)
+    yi, cbi, cri = Y[:, None, None].astype(np.int64), C[None, :, None].astype(np.int64), C[None, None, :].astype(np.int64)
+    vr = cri * CR + (yi * 65536 + (32768 - 128 * CR)) + 0 * cbi
+    vb = cbi * CB + (yi * 65536 + (32768 + 32 - 128 * CB)) + 0 * cri
+    vg = (cri * -G2 + (cbi * -G1 + (yi * 4194304 + (2097152 + 128 * (G1 + G2))))) >> 22
+    for v in (vr, vb, cri * -G2 + (cbi * -G1 + (yi * 4194304 + (2097152 + 128 * (G1 + G2))))):
+        assert -2 ** 31 <= v.min() and v.max() < 2 ** 31
+    assert np.array_equal(np.clip(vr, 0, 0xFFFFFF) >> 16, rnd(rf))
+    assert np.array_equal(np.clip(vb, 0, 0xFFFFFF) >> 16, rnd(bf))
+    assert np.array_equal(np.clip(vg, 0, 255), rnd(gf))
+    full = cri * -G2 + (cbi * -G1 + (yi * 4194304 + (2097152 + 128 * (G1 + G2))))
+    assert np.array_equal(np.clip(full, 0, 0x3FFFFFFF) >> 22, rnd(gf))         # clamp first, then shift, as the kernel does
 
 
 def test_v5_integer_bridge_matches_float32_reference_on_all_colours():
