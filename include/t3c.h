@@ -244,11 +244,13 @@ T3C_API t3c_status t3c_t3v_read_frame(t3c_ctx*, const uint8_t* record, size_t n_
 /* t3v_write_header, :97-119: the 54-byte packed T3VHeaderBin, its last field the CRC-32 of the 50 bytes before it; aw = {x0, y0, w, h} */
 T3C_API t3c_status t3c_t3v_header(t3c_ctx*, uint8_t out54[54], int profile, int subword_code, int centered, int coset, uint32_t width, uint32_t height,
                                   const uint32_t aw[4], uint32_t fps_num, uint32_t fps_den, uint32_t frame_count, int file_type);
-/* batched, device-resident: frame f of n_words words at d_words9 + f * 9 * stride_words <-> record f at d_records + f * record_pitch; all frame
- * starts 4-byte aligned, record_pitch >= 8 + 9 n_words.  d_ok[f] = the record announces n_words and carries the right CRC */
 /* the .t3vi sidecar (old/include/t3v_indexed_io.hpp:14-44) of n_frames records that lie back to back from byte first_offset of a .t3v
  * file, frame i holding n_words[i] words: 17-byte header ("T3VI", 1, n_frames, 0, CRC-32 of those 13 bytes) + n_frames uint64 offsets */
 T3C_API t3c_status t3c_t3v_index_build(t3c_ctx*, const uint64_t* n_words, size_t n_frames, uint64_t first_offset, uint8_t* out /* 17 + 8 n */, size_t* n_bytes);
+/* batched, device-resident: frame f of n_words words at d_words9 + f * 9 * stride_words <-> record f at d_records + f * record_pitch; all frame
+ * starts 4-byte aligned, record_pitch >= 8 + 9 n_words.  d_ok[f] = the record announces n_words and carries the right CRC.
+ * A record is n | payload | CRC, so its payload starts 4 bytes in: with d_records at 12 mod 16 (and record_pitch, 9 * stride_words multiples
+ * of 16) both sides of the copy move in 16-byte accesses; any 4-byte aligned placement is correct, only slower (4-byte accesses on one side) */
 T3C_API t3c_status t3c_t3v_frame_records_dev(t3c_ctx*, const uint8_t* d_words9, size_t n_words, size_t stride_words, size_t n_frames, uint8_t* d_records,
                                              size_t record_pitch, void* stream);
 T3C_API t3c_status t3c_t3v_read_frames_dev(t3c_ctx*, const uint8_t* d_records, size_t record_pitch, size_t n_frames, size_t n_words, uint8_t* d_words9,

@@ -1253,7 +1253,8 @@ t3c_status t3c_t3v_frame_record(t3c_ctx* ctx, const uint8_t* words, size_t n_wor
     DeviceGuard guard(ctx->device);
     uint8_t *d_in, *d_out;
     const size_t pitch = (8 + 9 * n_words + 3) & ~(size_t)3;
-    TRY(reserve_t(ctx, B_IN, 9 * n_words + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, pitch + 16, &d_out));
+    TRY(reserve_t(ctx, B_IN, 9 * n_words + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, pitch + 32, &d_out));
+    d_out += 12;                                                      // the record at 12 mod 16: its payload (at + 4) moves in 16-byte accesses
     if (n_words) H2D(d_in, words, 9 * n_words);
     TRY(t3c_t3v_frame_records_dev(ctx, d_in, n_words, n_words, 1, d_out, pitch, ctx->stream));
     D2H(record, d_out, 8 + 9 * n_words);
@@ -1273,7 +1274,8 @@ t3c_status t3c_t3v_read_frame(t3c_ctx* ctx, const uint8_t* record, size_t n_byte
     DeviceGuard guard(ctx->device);
     uint8_t *d_in, *d_out;
     const size_t pitch = (8 + 9 * (size_t)n + 3) & ~(size_t)3;
-    TRY(reserve_t(ctx, B_IN, pitch + 16, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * (size_t)n + 32, &d_out));
+    TRY(reserve_t(ctx, B_IN, pitch + 32, &d_in)); TRY(reserve_t(ctx, B_OUT, 9 * (size_t)n + 32, &d_out));
+    d_in += 12;                                                       // as in t3c_t3v_frame_record
     H2D(d_in, record, 8 + 9 * (size_t)n);
     uint8_t* d_ok = d_out + ((9 * (size_t)n + 15) & ~(size_t)15);
     TRY(t3c_t3v_read_frames_dev(ctx, d_in, pitch, 1, n, d_out, n, d_ok, ctx->stream));

@@ -1829,6 +1829,22 @@ static int super_launch(Kern kern, const DevTables& T, const FastParams& Q, cons
     kern<<<(unsigned)grid, SUP_TPB, P.smem_bytes, st>>>(Q, P, g, T.gf, T.rs);
     return 1;
 }
+// the 8-pixels-per-thread bridge kernels (k_fast5.cuh) for the leading multiple of eight pixels of 16-byte aligned buffers; returns the
+// number of pixels covered (the caller's one-pixel kernels take the rest)
+size_t launch_rgb_to_quant8(const uint8_t* rgb, size_t n_px, t3c_pixel* out, cudaStream_t st)
+{
+    const size_t groups = n_px / 8;
+    if (!groups || (reinterpret_cast<uintptr_t>(rgb) & 7u) || (reinterpret_cast<uintptr_t>(out) & 15u)) return 0;
+    k_rgb_to_quant8<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(rgb), groups, reinterpret_cast<uint4*>(out));
+    return 8 * groups;
+}
+size_t launch_quant_to_rgb8(const t3c_pixel* px, size_t n_px, uint8_t* rgb, cudaStream_t st)
+{
+    const size_t groups = n_px / 8;
+    if (!groups || (reinterpret_cast<uintptr_t>(rgb) & 7u) || (reinterpret_cast<uintptr_t>(px) & 15u)) return 0;
+    k_quant_to_rgb8<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(px), groups, reinterpret_cast<uint2*>(rgb));
+    return 8 * groups;
+}
 int launch_encode_super(const DevTables& T, const t3c_config& cfg, const Geom& g, const uint8_t* in, size_t in_pitch, bool words, size_t n_px,
                         size_t n_frames, uint8_t* out9, size_t stride_words, cudaStream_t st, SuperTail* tail)
 {

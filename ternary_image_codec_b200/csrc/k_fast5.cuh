@@ -544,13 +544,8 @@ __device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32
 // b (their exact fractions are multiples of 0.002 / 0.004, never .5 for r; b has one exact tie, cb = -125, which the +32 keeps on the
 // round-half-away side), 22 bits for g (closest approach to a tie 5.6e-5).  tests/test_host_logic.py checks all 1 594 323 values
 // against the float32 chain.  No conversions, no F2I (quarter-rate pipe), and the clamped r / b leave through byte 2 of their sums.
-__device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
+__device__ __forceinline__ uint32_t yuvq_to_rgb5(uint32_t Yq, uint32_t ub, uint32_t ur)   // Yq <= 242, ub = Cbq + 40, ur = Crq + 40 <= 80
 {
-    const uint32_t q = __umulhi(A, 17674763u);                 // A / 243, exact for A < 3^13
-    const uint32_t Yq = A - 243u * q;
-    const uint32_t ur = __umulhi(q, 53024288u);                // q / 81, exact for q < 6561
-    const uint32_t ub = q - 81u * ur;
-    // Y = (510 Yq + 241) / 484 (dev.cuh dequant_y; <= 255 for Yq <= 242), C = min((64 u + 10) / 20, 255)
     const int Y = (int)__umulhi(Yq * 510u + 241u, 8873899u);
     // (96 u + 15) / 30 rather than (32 u + 5) / 10: a multiplier that is not a power of two stays on the multiply pipe (the logic pipe is the busy one)
     const int Cb = (int)min(__umulhi(96u * ub + 15u, 143165577u), 255u);
@@ -561,6 +556,13 @@ __device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
     const uint32_t b = (uint32_t)__viaddmin_s32_relu(Cb * V5_CB + Y16, 32768 + 32 - 128 * V5_CB, 0xFFFFFF);
     const uint32_t g = (uint32_t)__viaddmin_s32_relu(Cr * -V5_G2 + (Cb * -V5_G1 + Y22), 2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22;
     return __byte_perm(__byte_perm(r, g, 0x3042), b, 0x3610);                  // R | G<<8 | B<<16 (byte 3 of the clamped r is 0)
+}
+__device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
+{
+    const uint32_t q = __umulhi(A, 17674763u);                 // A / 243, exact for A < 3^13
+    const uint32_t Yq = A - 243u * q;
+    const uint32_t ur = __umulhi(q, 53024288u);                // q / 81, exact for q < 6561
+    return yuvq_to_rgb5(Yq, q - 81u * ur, ur);
 }
 // ---- decode phase A: 26 stream symbols at S + a (even) -> six pixels -> 18 RGB bytes at dst (even address): four 32-bit stores and one
 // 16-bit store, aligned per lane by funnel shifts (see store26)
@@ -718,4 +720,62 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
         c = nx;
     }
     if (lane == 0) bulk_wait_all();
+}
+
+// ---- the bridge of the general chain at streaming speed (rgb_to_quant_stream / quant_stream_to_rgb, IMG:156-192): eight pixels per
+// thread -- 24 bytes of RGB8 as three 8-byte accesses, 48 bytes of PixelYCbCrQuant {u16 Yq, i16 Cbq, i16 Crq} as three 16-byte ones --
+// with the integer arithmetic of the fused kernels (luma ties and out-of-range quantised values take the float32 path of dev.cuh).
+// 9 bytes per pixel either way; the one-pixel-per-thread kernels of k_general.cu (byte loads, 2-byte stores) stay for unaligned
+// buffers and the last n mod 8 pixels.
+__device__ __forceinline__ void px8_from_words(const uint32_t (&y)[6], uint32_t (&px)[8])
+{
+    px[0] = y[0]; px[1] = __byte_perm(y[0], y[1], 0x6543); px[2] = __byte_perm(y[1], y[2], 0x5432); px[3] = __byte_perm(y[2], y[2], 0x0321);
+    px[4] = y[3]; px[5] = __byte_perm(y[3], y[4], 0x6543); px[6] = __byte_perm(y[4], y[5], 0x5432); px[7] = __byte_perm(y[5], y[5], 0x0321);
+}
+__global__ void __launch_bounds__(256) k_rgb_to_quant8(const uint2* __restrict__ rgb, size_t n_groups, uint4* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_groups) return;
+    const uint2 a = __ldcs(rgb + 3 * i), b = __ldcs(rgb + 3 * i + 1), c = __ldcs(rgb + 3 * i + 2);
+    const uint32_t y[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+    uint32_t px[8], h[24];
+    px8_from_words(y, px);
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const uint32_t t = __umulhi(dot_rgb<2>(px[p], 500), Y5_M);
+        uint32_t yq = __umulhi(lop3<0xEA>(t, 0xFFFFFE00u, Y5_Z), Y5_M2);
+        if (!(t & 511u)) yq = luma_q(byte_magic(px[p], 0), byte_magic(px[p], 1), byte_magic(px[p], 2)) + (0u - QY_C0);   // possible tie: float32 decides
+        h[3 * p] = yq;
+        h[3 * p + 1] = (chroma_q<true>(px[p]) - 40u) & 0xFFFFu;
+        h[3 * p + 2] = (chroma_q<false>(px[p]) - 40u) & 0xFFFFu;
+    }
+    uint32_t w[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) w[j] = h[2 * j] | (h[2 * j + 1] << 16);
+    __stcs(out + 3 * i, make_uint4(w[0], w[1], w[2], w[3]));
+    __stcs(out + 3 * i + 1, make_uint4(w[4], w[5], w[6], w[7]));
+    __stcs(out + 3 * i + 2, make_uint4(w[8], w[9], w[10], w[11]));
+}
+__global__ void __launch_bounds__(256) k_quant_to_rgb8(const uint4* __restrict__ px, size_t n_groups, uint2* __restrict__ rgb)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_groups) return;
+    const uint4 a = __ldcs(px + 3 * i), b = __ldcs(px + 3 * i + 1), c = __ldcs(px + 3 * i + 2);
+    const uint32_t w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    uint32_t p[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t h0 = (w[(3 * q) >> 1] >> (16 * ((3 * q) & 1))) & 0xFFFFu, h1 = (w[(3 * q + 1) >> 1] >> (16 * ((3 * q + 1) & 1))) & 0xFFFFu,
+                       h2 = (w[(3 * q + 2) >> 1] >> (16 * ((3 * q + 2) & 1))) & 0xFFFFu;
+        const uint32_t ub = (h1 + 40u) & 0xFFFFu, ur = (h2 + 40u) & 0xFFFFu;
+        if (h0 <= 242u && ub <= 80u && ur <= 80u) p[q] = yuvq_to_rgb5(h0, ub, ur);
+        else {                                                       // anything a PixelYCbCrQuant can hold: the clamping float32 path (IMG:57-66,79-84)
+            int R, G, B;
+            ycbcr8_to_rgb(dequant_y((int)h0), dequant_c((int)(int16_t)h1), dequant_c((int)(int16_t)h2), R, G, B);
+            p[q] = (uint32_t)R | ((uint32_t)G << 8) | ((uint32_t)B << 16);
+        }
+    }
+    __stcs(rgb + 3 * i, make_uint2(p[0] | (p[1] << 24), (p[1] >> 8) | (p[2] << 16)));
+    __stcs(rgb + 3 * i + 1, make_uint2((p[2] >> 16) | (p[3] << 8), p[4] | (p[5] << 24)));
+    __stcs(rgb + 3 * i + 2, make_uint2((p[5] >> 8) | (p[6] << 16), (p[6] >> 16) | (p[7] << 8)));
 }

@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(TPB) k_base243_unpack(const uint8_t* __restric
     for (int c = 0; c < 5; ++c) { if (5 * j + c < n_trits) trits[5 * j + c] = (uint8_t)(v % 3); v /= 3; }
 }
 // fused extract + base-243: byte j packs stream trits 5j..5j+4, stream trit t = trit t%N of word t/N
-__global__ void __launch_bounds__(TPB) k_words_to_base243(const uint8_t* __restrict__ words, uint64_t n_trits, uint32_t N, uint8_t* __restrict__ out)
+__global__ void __launch_bounds__(TPB) k_words_to_base243(const uint8_t* __restrict__ words, uint64_t n_trits, uint32_t N, uint8_t* __restrict__ out, uint64_t j0 = 0)
 {
-    const uint64_t j = (uint64_t)blockIdx.x * TPB + threadIdx.x, nb = (n_trits + 4) / 5;
+    const uint64_t j = j0 + (uint64_t)blockIdx.x * TPB + threadIdx.x, nb = (n_trits + 4) / 5;
     if (j == 0) { const uint32_t total = (uint32_t)n_trits; for (int i = 0; i < 4; ++i) out[i] = (uint8_t)(total >> (8 * i)); }
     if (j >= nb) return;
     uint64_t w = (5 * j) / N;
@@ -169,6 +169,104 @@ __global__ void __launch_bounds__(SW_TPB) k_words_to_base243_tiled(const uint8_t
         for (uint32_t i = tid; i < nb; i += SW_TPB) dst[i] = s_out[i];
 }
 
+// ---- v2 of the fused kernel.  The tiled version above goes through shared memory one byte at a time (~100 wavefronts per word: it is
+// bound by the shared-memory pipe at 0.15 of the HBM roofline).  Here a thread owns 20 consecutive words -- 180 bytes in, 20 N trits =
+// exactly 4 N payload bytes out -- held in 45 registers; every payload byte is a compile-time sum of at most three pieces
+// (symbol / 3^a) % 3^len * 3^c of the symbols it straddles (the pieces come from one 27-entry table look-up per symbol), so N is a
+// template parameter.  Global traffic is coalesced through shared
+// memory with 32-bit accesses at odd word pitches (45 in, N or N + 1 out): ~4 wavefronts per word.
+constexpr int B243_TPB = 128, B243_WPT = 20, B243_INW = 9 * B243_WPT / 4;
+__host__ __device__ constexpr uint32_t pow3(int e) { return e <= 0 ? 1u : 3u * pow3(e - 1); }
+// piece (symbol / 3^d) % 3^len of symbol byte bi of the thread's 180 bytes: the symbol itself, or a byte of its look-up word
+// lut[s] = s % 9 | (s / 9) << 8 | (s % 3) << 16 | (s / 3) << 24 (one conflict-free shared load per symbol, shared by the bytes it straddles)
+template <int BI, int D, int LEN>
+__device__ __forceinline__ uint32_t b243_piece(const uint32_t (&x)[B243_INW], const uint32_t* lut)
+{
+    const uint32_t sym = (x[BI >> 2] >> (8 * (BI & 3))) & 0xFFu;
+    if constexpr (D == 0 && LEN == 3) return sym;
+    else {
+        const uint32_t l = lut[sym];
+        if constexpr (D == 0 && LEN == 2) return l & 0xFFu;
+        else if constexpr (D == 0 && LEN == 1) return (l >> 16) & 0xFFu;
+        else if constexpr (D == 1 && LEN == 2) return l >> 24;
+        else if constexpr (D == 2) return (l >> 8) & 0xFFu;
+        else return (l >> 24) - 3u * ((l >> 8) & 0xFFu);                       // D == 1, LEN == 1: only where a word's N trits end inside a symbol
+    }
+}
+template <int N, int J, int C>
+__device__ __forceinline__ uint32_t b243_terms(const uint32_t (&x)[B243_INW], const uint32_t* lut)
+{
+    if constexpr (C >= 5) return 0u;
+    else {
+        constexpr int T = 5 * J + C, wd = T / N, tr = T % N, sy = tr / 3, d = tr % 3;
+        constexpr int l0 = 3 - d, l1 = 5 - C, l2 = N - tr;                     // to the end of the symbol / of the byte / of the word's N trits
+        constexpr int len = l0 < l1 ? (l0 < l2 ? l0 : l2) : (l1 < l2 ? l1 : l2);
+        return b243_piece<9 * wd + sy, d, len>(x, lut) * pow3(C) + b243_terms<N, J, C + len>(x, lut);
+    }
+}
+template <int N, int JW>
+__device__ __forceinline__ void b243_words(const uint32_t (&x)[B243_INW], const uint32_t* lut, uint32_t (&o)[N])
+{
+    if constexpr (JW < N) {
+        o[JW] = b243_terms<N, 4 * JW, 0>(x, lut) | (b243_terms<N, 4 * JW + 1, 0>(x, lut) << 8) | (b243_terms<N, 4 * JW + 2, 0>(x, lut) << 16) |
+                (b243_terms<N, 4 * JW + 3, 0>(x, lut) << 24);
+        b243_words<N, JW + 1>(x, lut, o);
+    }
+}
+// bytes >= 27 of a word reduced mod 27 (unpack3, OLD:28-31); bit 7 of (b & 0x7F) + 101 or of b itself is set exactly for b >= 27
+__device__ __forceinline__ uint32_t mod27x4(uint32_t w)
+{
+    if (((((w & 0x7F7F7F7Fu) + 0x65656565u) | w) & 0x80808080u) == 0) return w;
+    uint32_t r = 0;
+    for (int q = 0; q < 4; ++q) r |= (((w >> (8 * q)) & 0xFFu) % 27u) << (8 * q);
+    return r;
+}
+template <int N>
+__global__ void __launch_bounds__(B243_TPB) k_words_to_base243_v2(const uint8_t* __restrict__ words, uint32_t n_groups, uint32_t total_trits, uint8_t* __restrict__ out)
+{
+    constexpr int PITCH = (N & 1) ? N : N + 1;
+    __shared__ __align__(16) uint32_t s_in[B243_TPB * B243_INW];
+    uint32_t* s_out = s_in;                                      // the payload words take the input's place once every thread holds its 45 words
+    static_assert(PITCH <= B243_INW, "output tile fits the input tile");
+    __shared__ uint32_t s_lut[32];
+    const uint32_t tid = threadIdx.x, g0 = blockIdx.x * B243_TPB, ng = min((uint32_t)B243_TPB, n_groups - g0);
+    if (tid < 32) s_lut[tid] = (tid % 9u) | (tid / 9u) << 8 | (tid % 3u) << 16 | (tid / 3u) << 24;
+    if (blockIdx.x == 0 && tid == 0) *reinterpret_cast<uint32_t*>(out) = total_trits;
+    const uint8_t* src = words + (size_t)(9 * B243_WPT) * g0;
+    const uint32_t nw = ng * B243_INW;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        for (uint32_t i = tid; i < nw / 4; i += B243_TPB) {
+            uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+            v.x = mod27x4(v.x); v.y = mod27x4(v.y); v.z = mod27x4(v.z); v.w = mod27x4(v.w);
+            reinterpret_cast<uint4*>(s_in)[i] = v;
+        }
+        for (uint32_t i = (nw & ~3u) + tid; i < nw; i += B243_TPB) s_in[i] = mod27x4(__ldcs(reinterpret_cast<const uint32_t*>(src) + i));
+    } else
+        for (uint32_t i = tid; i < nw; i += B243_TPB) s_in[i] = mod27x4(__ldcs(reinterpret_cast<const uint32_t*>(src) + i));
+    __syncthreads();
+    uint32_t x[B243_INW];
+#pragma unroll
+    for (int i = 0; i < B243_INW; ++i) x[i] = tid < ng ? s_in[B243_INW * tid + i] : 0u;
+    __syncthreads();
+    if (tid < ng) {
+        uint32_t o[N];
+        b243_words<N, 0>(x, s_lut, o);
+#pragma unroll
+        for (int j = 0; j < N; ++j) s_out[PITCH * tid + j] = o[j];
+    }
+    __syncthreads();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + 4 + (size_t)(4 * N) * g0);
+    for (uint32_t i = tid; i < ng * N; i += B243_TPB) {
+        const uint32_t row = i / N;
+        __stcs(dst + i, s_out[row * PITCH + (i - row * N)]);
+    }
+}
+template <int N>
+void launch_b243_v2(const uint8_t* words, uint32_t n_groups, uint32_t total_trits, uint8_t* out, cudaStream_t st)
+{
+    k_words_to_base243_v2<N><<<(n_groups + B243_TPB - 1) / B243_TPB, B243_TPB, 0, st>>>(words, n_groups, total_trits, out);
+}
+
 // NEW-generation RAW path.  pack13_from_quant (:62-78): clamp(Yq,0,242) + 243 (clamp(Cbq+40,0,80) + 81 clamp(Crq+40,0,80)).
 // Thread = 4 pixels: 24 bytes in (three 64-bit loads), one 128-bit store.
 __device__ __forceinline__ uint32_t v6new_code(uint32_t yq, int cb, int cr)
@@ -255,7 +353,20 @@ int launch_words_to_base243(const uint8_t* words9, size_t n_words, int N, uint8_
 {
     const uint64_t n_trits = (uint64_t)n_words * (uint64_t)N;
     if (!n_words) { k_words_to_base243<<<1, TPB, 0, st>>>(words9, n_trits, (uint32_t)N, out); return 1; } // just the count
-    k_words_to_base243_tiled<<<blocks_for(n_words, SW_WORDS), SW_TPB, 0, st>>>(words9, n_words, (uint32_t)N, out);
+    const size_t groups = n_words / B243_WPT;
+    if (!groups || groups > 0xFFFFFFFFull || ((reinterpret_cast<uintptr_t>(words9) | reinterpret_cast<uintptr_t>(out)) & 3u) || N < 1 || N > 27) {
+        k_words_to_base243_tiled<<<blocks_for(n_words, SW_WORDS), SW_TPB, 0, st>>>(words9, n_words, (uint32_t)N, out);
+        return 1;
+    }
+    // 20 words per thread; the last n_words mod 20 words (and the zero padding of the last byte) by the one-byte-per-thread kernel
+    using Fn = void (*)(const uint8_t*, uint32_t, uint32_t, uint8_t*, cudaStream_t);
+    static const Fn fn[27] = {launch_b243_v2<1>, launch_b243_v2<2>, launch_b243_v2<3>, launch_b243_v2<4>, launch_b243_v2<5>, launch_b243_v2<6>, launch_b243_v2<7>,
+                              launch_b243_v2<8>, launch_b243_v2<9>, launch_b243_v2<10>, launch_b243_v2<11>, launch_b243_v2<12>, launch_b243_v2<13>, launch_b243_v2<14>,
+                              launch_b243_v2<15>, launch_b243_v2<16>, launch_b243_v2<17>, launch_b243_v2<18>, launch_b243_v2<19>, launch_b243_v2<20>, launch_b243_v2<21>,
+                              launch_b243_v2<22>, launch_b243_v2<23>, launch_b243_v2<24>, launch_b243_v2<25>, launch_b243_v2<26>, launch_b243_v2<27>};
+    fn[N - 1](words9, (uint32_t)groups, (uint32_t)n_trits, out, st);
+    const uint64_t j0 = (uint64_t)(4 * N) * groups, nb = (n_trits + 4) / 5;
+    if (j0 < nb) { k_words_to_base243<<<blocks_for(nb - j0, TPB), TPB, 0, st>>>(words9, n_trits, (uint32_t)N, out, j0); return 2; }
     return 1;
 }
 int launch_v6new_pack_pixels(const t3c_pixel* px, size_t n_px, uint32_t* words, cudaStream_t st)
@@ -329,7 +440,9 @@ __device__ __forceinline__ uint32_t mod27_word(uint32_t w)
 constexpr int CRC_SHIFT0 = 1024, CRC_NSHIFT = 9, CRC_POW0 = CRC_SHIFT0 + CRC_NSHIFT * 1024;
 // ... then, for the lane-strided tile kernel: sixteen 256-entry tables X_j[v] = (CRC state after byte v and 15 - j zero bytes, from state 0),
 // three shift tables for 16, 32 and 64 bytes, and the state after one tile of zero bytes from 0xFFFFFFFF
-constexpr int CRC_NPOW = 48, CRC_X0 = CRC_POW0 + CRC_NPOW, CRC_LANE0 = CRC_X0 + 16 * 256, CRC_K0 = CRC_LANE0 + 3 * 1024, CRC_WORDS = CRC_K0 + 1;
+constexpr int CRC_NPOW = 48, CRC_X0 = CRC_POW0 + CRC_NPOW, CRC_LANE0 = CRC_X0 + 16 * 256, CRC_K0 = CRC_LANE0 + 3 * 1024;
+// ... and the 32-entry heads of the X tables for the four 512-byte pieces of a 2048-byte step: P[p][j][v] = X_j[v] * x^(8 * 512 * (3 - p)), v < 32
+constexpr int CRC_P0 = CRC_K0 + 1, CRC_WORDS = CRC_P0 + 4 * 16 * 32;
 __device__ __forceinline__ uint32_t crc_shift(const uint32_t* __restrict__ t, uint32_t v) // t = one shift table (shared or global)
 {
     return t[v & 0xFFu] ^ t[256 + ((v >> 8) & 0xFFu)] ^ t[512 + ((v >> 16) & 0xFFu)] ^ t[768 + (v >> 24)];
@@ -404,31 +517,36 @@ __device__ __forceinline__ void t3v_tile_body(uint32_t* __restrict__ sm, uint32_
     }
     if (tid == nseg - 1) tile_crc[(uint64_t)f * tiles_per_frame + t] = crc_shift_bytes(tabs, red[0], last_len) ^ crc;
 }
-// Full tiles, lane-strided: a warp takes one 32 KiB tile in 64 steps of 512 bytes, lane l the 16 bytes at 512 k + 16 l: perfectly coalesced
-// loads and stores, no shared-memory tile.  A lane keeps the CRC state of "its" bytes as if the other lanes' bytes were zero:
-//   c <- c * x^(8*512) + X(16 bytes)     (CRC is linear over GF(2): X = sum_j X_j[byte j], sixteen small look-ups; the symbols are < 27, so the 32 lanes
-//   of one look-up hit at most 27 consecutive words: no bank conflicts; the shift by 512 bytes is eight nibble look-ups in a per-lane copy of the table)
-// and the 32 lane states are joined at the end of the tile: crc = sum_l c_l * x^(8*16*(31-l)), pairwise by shuffles.
+// Full tiles, lane-strided: a warp takes one 32 KiB tile in 16 steps of 2048 bytes, four pieces of 512 bytes each, lane l the 16 bytes at
+// 512 (4 k + p) + 16 l: perfectly coalesced loads and stores, no shared-memory tile.  A lane keeps the CRC state of "its" bytes as if the other
+// lanes' bytes were zero:
+//   c <- c * x^(8*2048) + sum_p P_p(16 bytes of piece p)
+// CRC is linear over GF(2): P_p = sum_j P[p][j][byte j], the byte's share of the state at the END of the step (its own 15 - j trailing bytes
+// and the 3 - p pieces behind it folded into the table), so one shift serves 64 bytes.  Stored symbols are < 27: the 32 lanes of one look-up
+// hit at most 27 consecutive words of a 32-entry table head -- no bank conflicts; a piece with a byte >= 32 (only when checking a foreign
+// file) takes the 256-entry tables from global memory.  The shift by 2048 bytes is eight nibble look-ups in a per-lane copy of its table.
+// 72 shared look-ups per 64 bytes (the 512-byte-step version took 96 and sat on the shared-memory pipe at 0.49 of the HBM roofline).
+// The 32 lane states are joined at the end of the tile: crc = sum_l c_l * x^(8*16*(31-l)), pairwise by shuffles.
 __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t* __restrict__ src, uint64_t src_pitch, uint32_t src_off, uint8_t* __restrict__ dst,
                                                                  uint64_t dst_pitch, uint32_t dst_off, uint32_t full_tiles, uint32_t tiles_per_frame, uint32_t n_frames,
                                                                  int reduce, const uint32_t* __restrict__ tabs, uint32_t* __restrict__ tile_crc, uint64_t n_bytes,
                                                                  uint32_t body_ctas)
 {
-    static_assert(T3V_BODY_WORDS >= 32 * 256 && 32 * T3V_SW == T3V_TPB, "one shared buffer, one CTA shape for both roles");
+    static_assert(T3V_BODY_WORDS >= 4 * 16 * 32 + 8 * 16 * 32 && 32 * T3V_SW == T3V_TPB, "one shared buffer, one CTA shape for both roles");
     __shared__ __align__(16) uint32_t sm[T3V_BODY_WORDS];
     if (blockIdx.x < body_ctas) {   // the partial last tile of frame blockIdx.x (first in the grid: it is the longest serial piece)
         t3v_tile_body(sm, blockIdx.x, full_tiles, src, src_pitch, src_off, dst, dst_pitch, dst_off, n_bytes, tiles_per_frame, reduce, tabs, tile_crc);
         return;
     }
-    uint32_t* sx = sm;
-    uint32_t* s512 = sm + 16 * 256;
+    uint32_t* sp4 = sm;                    // P[4][16][32]
+    uint32_t* s2k = sm + 4 * 16 * 32;      // the shift by 2048 bytes by nibbles, one copy per lane
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, cta = blockIdx.x - body_ctas, n_cta = gridDim.x - body_ctas;
-    for (uint32_t i = tid; i < 16 * 256; i += 32 * T3V_SW) sx[i] = __ldg(tabs + CRC_X0 + i);
-    // the shift by 512 bytes (table 2: 128 * 2^2 bytes) by nibbles, every entry once per lane (word 32 * (16 n + v) + lane): the eight look-ups of a
+    for (uint32_t i = tid; i < 4 * 16 * 32; i += 32 * T3V_SW) sp4[i] = __ldg(tabs + CRC_P0 + i);
+    // the shift by 2048 bytes (table 4: 128 * 2^4 bytes) by nibbles, every entry once per lane (word 32 * (16 n + v) + lane): the eight look-ups of a
     // step, with state-dependent (random) indices, stay inside the lane's own bank
     for (uint32_t i = tid; i < 8 * 16 * 32; i += 32 * T3V_SW) {
         const uint32_t n = i >> 9, v = (i >> 5) & 15u;
-        s512[i] = __ldg(tabs + CRC_SHIFT0 + 1024 * 2 + 256 * (n >> 1) + (v << (4 * (n & 1))));
+        s2k[i] = __ldg(tabs + CRC_SHIFT0 + 1024 * 4 + 256 * (n >> 1) + (v << (4 * (n & 1))));
     }
     __syncthreads();
     const uint32_t k0 = __ldg(tabs + CRC_K0);
@@ -437,22 +555,25 @@ __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t
         const uint32_t f = (uint32_t)(gw / full_tiles), t = (uint32_t)(gw - (uint64_t)f * full_tiles);
         const uint8_t* sp = src + f * src_pitch + src_off + (uint64_t)t * T3V_TILE + 16u * lane;
         uint8_t* dp = dst ? dst + f * dst_pitch + dst_off + (uint64_t)t * T3V_TILE + 16u * lane : nullptr;
-        const bool s16 = (reinterpret_cast<uintptr_t>(sp) & 15) == 0, d16 = (reinterpret_cast<uintptr_t>(dp) & 15) == 0;   // else 4-byte accesses (the
-        // record's payload sits at + 4; re-aligning through shuffles was measured slower)
+        const bool s16 = (reinterpret_cast<uintptr_t>(sp) & 15) == 0, d16 = (reinterpret_cast<uintptr_t>(dp) & 15) == 0;   // else 4-byte accesses (a
+        // record's payload sits 4 bytes in: t3c.h tells callers to place records at 12 mod 16)
         uint32_t c = 0;
-        constexpr int G = 4;   // steps per group: the group's loads are issued together
+        constexpr int G = 4;   // pieces per step: the step's loads are issued together
 #pragma unroll 1
         for (int k0g = 0; k0g < T3V_TILE / 512; k0g += G) {
             uint32_t w[G][4];
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 const uint8_t* a = sp + 512 * (k0g + g);
-                if (s16) { const uint4 q = __ldg(reinterpret_cast<const uint4*>(a)); w[g][0] = q.x; w[g][1] = q.y; w[g][2] = q.z; w[g][3] = q.w; }
+                if (s16) { const uint4 q = __ldcs(reinterpret_cast<const uint4*>(a)); w[g][0] = q.x; w[g][1] = q.y; w[g][2] = q.z; w[g][3] = q.w; }
                 else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) w[g][i] = __ldg(reinterpret_cast<const uint32_t*>(a) + i);
+                    for (int i = 0; i < 4; ++i) w[g][i] = __ldcs(reinterpret_cast<const uint32_t*>(a) + i);
                 }
             }
+            uint32_t x = 0;                // the state moves 2048 bytes on, then every piece adds its bytes' share at the step's end
+#pragma unroll
+            for (int n = 0; n < 8; ++n) x ^= s2k[512 * n + 32 * ((c >> (4 * n)) & 15u) + lane];
 #pragma unroll
             for (int g = 0; g < G; ++g) {
                 if (reduce) {   // symbols >= 27 are stored % 27 (rare: one test for the sixteen bytes)
@@ -466,21 +587,32 @@ __global__ void __launch_bounds__(32 * T3V_SW) k_t3v_tiles_strided(const uint8_t
                 }
                 if (dp) {
                     uint8_t* a = dp + 512 * (k0g + g);
-                    if (d16) *reinterpret_cast<uint4*>(a) = make_uint4(w[g][0], w[g][1], w[g][2], w[g][3]);
+                    if (d16) __stcs(reinterpret_cast<uint4*>(a), make_uint4(w[g][0], w[g][1], w[g][2], w[g][3]));
                     else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(a)[i] = w[g][i];
+                        for (int i = 0; i < 4; ++i) __stcs(reinterpret_cast<uint32_t*>(a) + i, w[g][i]);
                     }
                 }
-                uint32_t x = 0;
+                if (((w[g][0] | w[g][1] | w[g][2] | w[g][3]) & 0xE0E0E0E0u) == 0) {   // all sixteen bytes < 32: the 32-entry table heads (no bank conflicts)
+                    const uint8_t* pt = reinterpret_cast<const uint8_t*>(sp4 + 16 * 32 * g);
 #pragma unroll
-                for (int n = 0; n < 8; ++n) x ^= s512[512 * n + 32 * ((c >> (4 * n)) & 15u) + lane];
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t w4 = w[g][i] << 2;                              // byte offsets into a 32-entry table; no carries between bytes
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    x ^= sx[256 * (4 * i) + (w[g][i] & 0xFFu)] ^ sx[256 * (4 * i + 1) + ((w[g][i] >> 8) & 0xFFu)] ^ sx[256 * (4 * i + 2) + ((w[g][i] >> 16) & 0xFFu)] ^
-                         sx[256 * (4 * i + 3) + (w[g][i] >> 24)];
-                c = x;
+                        for (int q = 0; q < 4; ++q) x ^= *reinterpret_cast<const uint32_t*>(pt + 128 * (4 * i + q) + ((w4 >> (8 * q)) & 0xFFu));
+                    }
+                } else {                                                                   // a stored byte >= 32 (checking a foreign file): the full tables
+                    uint32_t y = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) y ^= __ldg(tabs + CRC_X0 + 256 * (4 * i + q) + ((w[g][i] >> (8 * q)) & 0xFFu));
+                    if (g < 3 && ((3 - g) & 1)) y = crc_shift(tabs + CRC_SHIFT0 + 1024 * 2, y);   // x^(8 * 512)
+                    if (g < 2) y = crc_shift(tabs + CRC_SHIFT0 + 1024 * 3, y);                     // x^(8 * 1024)
+                    x ^= y;
+                }
             }
+            c = x;
         }
         // join the lanes: lane l stands 16 (31 - l) bytes before the end of a step
 #pragma unroll
@@ -581,6 +713,11 @@ void build_crc_tables(uint32_t* h)
         for (int k = 0; k < 4; ++k) for (uint32_t u = 0; u < 256; ++u) h[CRC_LANE0 + 1024 * j + 256 * k + u] = crc_mul(m, u << (8 * k));
     }
     h[CRC_K0] = crc_mul(crc_xpow8(T3V_TILE), 0xFFFFFFFFu);
+    for (int p = 0; p < 4; ++p)
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t m = crc_xpow8((uint64_t)(15 - j) + 512ull * (3 - p));
+            for (uint32_t v = 0; v < 32; ++v) h[CRC_P0 + (16 * p + j) * 32 + v] = crc_mul(m, h[v]);
+        }
 }
 size_t crc_table_words() { return CRC_WORDS; }
 

@@ -771,14 +771,16 @@ int launch_init_status(uint32_t* d_status, size_t n_frames, cudaStream_t st)
 int launch_rgb_to_quant(const uint8_t* rgb, size_t n, t3c_pixel* out, cudaStream_t st)
 {
     if (!n) return 0;
-    k_rgb_to_quant<<<blocks_for(n, 256), 256, 0, st>>>(rgb, n, reinterpret_cast<uint16_t*>(out));
-    return 1;
+    const size_t done = launch_rgb_to_quant8(rgb, n, out, st);
+    if (done < n) k_rgb_to_quant<<<blocks_for(n - done, 256), 256, 0, st>>>(rgb + 3 * done, n - done, reinterpret_cast<uint16_t*>(out + done));
+    return (done ? 1 : 0) + (done < n ? 1 : 0);
 }
 int launch_quant_to_rgb(const t3c_pixel* px, size_t n, uint8_t* rgb, cudaStream_t st)
 {
     if (!n) return 0;
-    k_quant_to_rgb<<<blocks_for(n, 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(px), n, rgb);
-    return 1;
+    const size_t done = launch_quant_to_rgb8(px, n, rgb, st);
+    if (done < n) k_quant_to_rgb<<<blocks_for(n - done, 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(px + done), n - done, rgb + 3 * done);
+    return (done ? 1 : 0) + (done < n ? 1 : 0);
 }
 static int raw2_grid(uint32_t n_tiles)
 {

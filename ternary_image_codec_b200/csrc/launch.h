@@ -55,6 +55,8 @@ int launch_init_status(uint32_t* d_status, size_t n_frames, cudaStream_t st); //
 // K1
 int launch_rgb_to_quant(const uint8_t* rgb, size_t n_px, t3c_pixel* out, cudaStream_t st);
 int launch_quant_to_rgb(const t3c_pixel* px, size_t n_px, uint8_t* rgb, cudaStream_t st);
+size_t launch_rgb_to_quant8(const uint8_t* rgb, size_t n_px, t3c_pixel* out, cudaStream_t st);   // k_fast.cu: pixels covered (0: unaligned)
+size_t launch_quant_to_rgb8(const t3c_pixel* px, size_t n_px, uint8_t* rgb, cudaStream_t st);
 int launch_pack_pixels(const t3c_pixel* px, size_t n_px, uint8_t* words9, cudaStream_t st);
 int launch_unpack_pixels(const uint8_t* words9, size_t n_words, t3c_pixel* px, cudaStream_t st);
 int launch_mod27(const uint8_t* in, size_t n, uint8_t* out, cudaStream_t st);

@@ -686,6 +686,16 @@ def test_two_devices_in_one_process(oracle, t3):
 
 
 # ------------------------------------------------------------------ SURVEY 8(f).2 / 8(f).3
+def test_words_to_base243_every_subword_length(codec, oracle):
+    """the fused kernel is a template on N (20 words per thread, compile-time trit pieces): every N, sizes around the 20-word groups and
+    the 128-thread CTAs, bytes >= 27 (unpack3 reduces them mod 27, OLD:28-31)"""
+    r = rng(77)
+    for N in range(1, 28):
+        for nw in (19, 20, 21, 2559, 2560, 2561 + 20 * N):
+            words = r.integers(0, 256 if nw % 2 else 27, size=(nw, 9), dtype=np.uint8)
+            assert np.array_equal(codec.words_to_base243(words, N), oracle.base243_pack(oracle.subword_stream(words, N))), (N, nw)
+
+
 @pytest.mark.parametrize("N", (27, 24, 21, 18, 15, 1, 5))
 def test_subword_streams_and_base243(codec, oracle, N):
     r = rng(600 + N)

@@ -167,7 +167,9 @@ def t3v8k(ctx):
     pitch = (8 + 9 * wpf + 15) & ~15
     g = torch.Generator(device=dev); g.manual_seed(6)
     words = torch.randint(0, 27, (NB, stride * 9), dtype=torch.uint8, device=dev, generator=g)
-    rec = torch.zeros(NB, pitch, dtype=torch.uint8, device=dev)
+    # a record is n (4 bytes) | payload | CRC: its base sits at 12 mod 16 so that the payload -- all but 8 of its bytes -- moves in 16-byte accesses
+    rec_flat = torch.zeros(NB * pitch + 16, dtype=torch.uint8, device=dev)
+    rec = [rec_flat[12 + j * pitch:12 + (j + 1) * pitch] for j in range(NB)]
     back = torch.zeros_like(words)
     okf = torch.zeros(1, dtype=torch.uint8, device=dev)
     i = [0]
@@ -176,13 +178,13 @@ def t3v8k(ctx):
     tw = timeit(W)
     tr = timeit(R)
     import zlib
-    r0 = rec[0, :8 + 9 * wpf].cpu().numpy()
+    r0 = rec[0][:8 + 9 * wpf].cpu().numpy()
     want = zlib.crc32(r0[4:-4].tobytes()) ^ ((zlib.crc32(r0[:4].tobytes()) * 16777619) & 0xFFFFFFFF)
     assert int.from_bytes(r0[-4:].tobytes(), "little") == want and okf.item() == 1 and torch.equal(back[0, :9 * wpf], words[0, :9 * wpf])
     alg = 2 * 9 * wpf
-    return {"workload": "t3v8k: .t3v frame record of an 8K frame's 20.8 M profile words (payload % 27 + CRC-32), emit and check", "write_us": tw * 1e3,
+    return {"workload": "t3v8k: .t3v frame record of an 8K frame's 20.8 M profile words (payload % 27 + CRC-32), emit and check; record base at 12 mod 16", "write_us": tw * 1e3,
                       "read_check_us": tr * 1e3, "write_gbs": alg / tw / 1e6, "read_gbs": alg / tr / 1e6, "write_frac_of_measured_peak": alg / tw / 1e6 / PEAK,
-                      "algorithmic_bytes": alg}
+                      "read_frac_of_measured_peak": alg / tr / 1e6 / PEAK, "algorithmic_bytes": alg}
 
 
 def stream240(ctx, frames_per_call=8, n_frames=240):
