@@ -170,7 +170,9 @@ T3C_API t3c_status t3c_decode_profile_fixed(t3c_ctx*, const t3c_config* cfg, siz
 T3C_API t3c_status t3c_encode_frames_rgb8(t3c_ctx*, const t3c_config*, int arith, const uint8_t* rgb, size_t n_px,
                                           size_t n_frames, uint8_t* out9, size_t stride_words, size_t* words_per_frame);
 /* inverse (T3C_FIXED framing): per frame decode -> decode_raw_words_to_pixels -> quant_stream_to_rgb.
- * ok[f] per frame; pixels past the recovered prefix are left untouched; *px_recovered per frame. */
+ * ok[f] per frame; pixels past the recovered prefix are left untouched; *px_recovered per frame; *n_corrected summed over the frames.
+ * Any n_frames (batches above 32 frames are decoded in pieces of 32 inside the call).  Limits of the whole ABI: a frame's body below 2^32
+ * symbols on the tiled paths (an 8K frame has 1.9e8), .t3v record counts are uint32 (T3C_ERR_ARG beyond), sub-word N in 1..27. */
 T3C_API t3c_status t3c_decode_frames_rgb8(t3c_ctx*, const t3c_config*, const uint8_t* in9, size_t words_per_frame,
                                           size_t stride_words, size_t n_frames, size_t n_px, uint8_t* rgb,
                                           uint8_t* ok, size_t* px_recovered, size_t* n_corrected);

@@ -814,7 +814,7 @@ t3c_status t3c_encode_profile(t3c_ctx* ctx, const t3c_config* cfg, int arith, co
 t3c_status t3c_decode_profile(t3c_ctx* ctx, t3c_config* seen, const uint8_t* in, size_t n_words, uint8_t* out, size_t cap_words,
                               size_t* n_out, int* ok)
 {
-    if (!ctx || !seen || !n_out || !ok || (n_words && !in)) return fail(ctx, T3C_ERR_ARG, "decode_profile: null");
+    if (!ctx || !seen || !n_out || !ok || (n_words && !in) || (cap_words && !out)) return fail(ctx, T3C_ERR_ARG, "decode_profile: null");
     DeviceGuard guard(ctx->device);
     host_buffer(ctx, in, 9 * n_words); host_buffer(ctx, out, 9 * cap_words);
     *n_out = 0; *ok = 0;
@@ -961,8 +961,17 @@ t3c_status t3c_decode_frames_rgb8(t3c_ctx* ctx, const t3c_config* cfg, const uin
                                   size_t n_frames, size_t n_px, uint8_t* rgb, uint8_t* ok, size_t* px_recovered, size_t* n_corrected)
 {
     if (!ctx || !cfg || !in || !rgb || !ok) return fail(ctx, T3C_ERR_ARG, "decode_frames: null");
-    if (n_frames > 32) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: at most 32 frames per host-buffer call");
     if (cfg->profile == T3C_PROFILE_RAW) return fail(ctx, T3C_ERR_UNSUPPORTED, "decode_frames: RAW profile carries raw words, use unpack_pixels");
+    if (n_frames > 32) {   // the status mailbox holds 32 frames: longer batches go through in pieces (same result, same order)
+        size_t corrected = 0, part = 0;
+        for (size_t f = 0; f < n_frames; f += 32) {
+            const size_t nf = n_frames - f < 32 ? n_frames - f : 32;
+            TRY(t3c_decode_frames_rgb8(ctx, cfg, in + 9 * stride_words * f, words_per_frame, stride_words, nf, n_px, rgb + 3 * n_px * f, ok + f, px_recovered, &part));
+            corrected += part;
+        }
+        if (n_corrected) *n_corrected = corrected;
+        return T3C_OK;
+    }
     DeviceGuard guard(ctx->device);
     host_buffer(ctx, in, 9 * stride_words * n_frames); host_buffer(ctx, rgb, 3 * n_px * n_frames);
     if (n_corrected) *n_corrected = 0;
@@ -1193,6 +1202,7 @@ t3c_status t3c_t3v_frame_records_dev(t3c_ctx* ctx, const uint8_t* d_words, size_
                                      size_t record_pitch, void* st)
 {
     if (!ctx || !d_rec || (n_words && !d_words)) return fail(ctx, T3C_ERR_ARG, "t3v_frame_records: null");
+    if (n_words > 0xFFFFFFFFull) return fail(ctx, T3C_ERR_ARG, "t3v_frame_records: the count is a uint32");
     if (record_pitch < 8 + 9 * n_words || (record_pitch & 3) || ((uintptr_t)d_rec & 3) || ((uintptr_t)d_words & 3) || (n_frames > 1 && ((9 * stride_words) & 3)))
         return fail(ctx, T3C_ERR_ARG, "t3v_frame_records: pitch / alignment");
     DeviceGuard guard(ctx->device);
@@ -1204,6 +1214,7 @@ t3c_status t3c_t3v_read_frames_dev(t3c_ctx* ctx, const uint8_t* d_rec, size_t re
                                    size_t stride_words, uint8_t* d_ok, void* st)
 {
     if (!ctx || !d_rec || !d_ok) return fail(ctx, T3C_ERR_ARG, "t3v_read_frames: null");
+    if (n_words > 0xFFFFFFFFull) return fail(ctx, T3C_ERR_ARG, "t3v_read_frames: the count is a uint32");
     if (record_pitch < 8 + 9 * n_words || (record_pitch & 3) || ((uintptr_t)d_rec & 3) || ((uintptr_t)d_words & 3) || (n_frames > 1 && ((9 * stride_words) & 3)))
         return fail(ctx, T3C_ERR_ARG, "t3v_read_frames: pitch / alignment");
     DeviceGuard guard(ctx->device);

@@ -304,6 +304,24 @@ def test_fixed_roundtrip_with_errors(codec, oracle, t3, ci):
 
 
 # ------------------------------------------------------------------ fused frames
+def test_decode_frames_more_than_one_mailbox(codec, oracle, t3):
+    """the host-buffer decode call takes any number of frames (its status mailbox holds 32: longer batches go through in pieces)"""
+    oc, gc = both(CONFIGS[1])
+    shape, F = (40, 27), 70
+    n_px = shape[0] * shape[1]
+    frames = np.stack([T.synth_rgb(100 + f, n_px) for f in range(F)])
+    enc = codec.encode_frames_rgb8(frames, gc, t3.FIXED)
+    add = T.gf_add_table()
+    bad, tot = enc.copy(), 0
+    for f in (0, 31, 32, 33, 69):
+        bad[f], ne = T.inject_errors(enc[f], oc, (n_px + 1) // 2, seed=5 + f, gf_add=add)
+        tot += ne
+    ok, rgb, nc = codec.decode_frames_rgb8(bad, n_px, gc)
+    assert ok.all() and nc == tot
+    for f in range(F):
+        assert np.array_equal(rgb[f], oracle.decode_rgb_fixed(oc, enc[f], n_px)[1]), f
+
+
 @pytest.mark.parametrize("ci", [0, 1, 2, 3, 4, 5, 7, 9, 11, 12])
 @pytest.mark.parametrize("shape", [(64, 64), (512, 512), (130, 77)])
 def test_fused_frames_rgb8(codec, oracle, t3, ci, shape):

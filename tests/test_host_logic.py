@@ -197,7 +197,7 @@ def test_v5_fixed_point_colour_matrix_matches_float32_reference_on_all_values():
     K5 = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "k_fast5.cuh")).read()
     c = lambda n: _const(n, K5)
     CR, CB, G1, G2 = c("V5_CR"), c("V5_CB"), c("V5_G1"), c("V5_G2")
-    body = K5[K5.index("uint32_t value_to_rgb5"):]
+    body = K5[K5.index("uint32_t yuvq_to_rgb5"):]
     assert "32768 + 32 - 128 * V5_CB" in body and "2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22" in body
     assert "__umulhi(96u * ub + 15u, 143165577u)" in body and "__umulhi(96u * ur + 15u, 143165577u)" in body
     u64 = np.arange(81, dtype=np.int64)
