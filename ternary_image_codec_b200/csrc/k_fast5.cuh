@@ -14,8 +14,11 @@
 //     Cb = round(128 - 0.168736 R - 0.331264 G + 0.5 B) is floor((X + 15625) / 31250) + 128 with X = -5273 R - 10352 G + 15625 B
 //     (two 16x8-bit dot products, IDP.2A), and it agrees with the reference's float32 evaluation (IMG:47-56) for all 2^24 colours
 //     because no colour comes closer than 32e-6 to a rounding boundary other than exact ties, which float32 also hits exactly;
-//     the quantiser (IMG:69-78) follows as one mask-or and one multiply-high.  Luma keeps the float32 path: 824 of its 16782
-//     exact ties round down in float32.
+//     the quantiser (IMG:69-78) follows as one mask-or and one multiply-high.  Luma is computed the same way; 824 of its 16782
+//     exact ties round down in float32, so tie candidates are flagged (low nine bits of the scaled sum) and redone in float32;
+//   * decode: the nine band runs of a tile arrive by one 3-D tensor copy, YCbCr -> RGB is exact fixed-point arithmetic, dirty
+//     codewords go to an out-of-line bounded-distance decoder with uniform control flow (dev.cuh rs_bd_fix);
+//   * the CTA-shared tables are built once per configuration (FastImageCache) instead of by every CTA of every launch.
 #pragma once
 
 // ---- exact integer chroma (checked against the float path over all 2^24 colours by tests/test_gpu_parity.py) ------------------------
