@@ -69,7 +69,8 @@ def main():
             continue
         h = hs[0]
         iline, isrc, iaddr, isass = 0, 1, 2, 3
-        ie, iw, ii = h.index("Instructions Executed"), h.index("L1 Wavefronts Shared"), h.index("L1 Wavefronts Shared Ideal")
+        col = lambda name: h.index(name) if name in h else -1           # kernels without shared memory have no wavefront columns
+        ie, iw, ii = h.index("Instructions Executed"), col("L1 Wavefronts Shared"), col("L1 Wavefronts Shared Ideal")
         ismp = h.index("# Samples") if "# Samples" in h else -1
         stall_cols = [(i, c[6:]) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
         samples = collections.OrderedDict()   # (file, line) -> [n, Counter(reason)]
@@ -87,7 +88,7 @@ def main():
             if r[iline].isdigit() and r[ie].isdigit():
                 key = (fpath, int(r[iline]))
                 e = lines.setdefault(key, [0, 0, 0, r[isrc].strip()[:100]])
-                e[0] += int(r[ie]); e[1] += int(r[iw]) if r[iw].isdigit() else 0; e[2] += int(r[ii]) if r[ii].isdigit() else 0
+                e[0] += int(r[ie]); e[1] += int(r[iw]) if iw >= 0 and r[iw].isdigit() else 0; e[2] += int(r[ii]) if ii >= 0 and r[ii].isdigit() else 0
                 if ismp >= 0 and r[ismp].isdigit():
                     se = samples.setdefault(key, [0, collections.Counter(), r[isrc].strip()[:100]])
                     se[0] += int(r[ismp])
