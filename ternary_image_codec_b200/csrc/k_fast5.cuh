@@ -172,8 +172,8 @@ template <int K, bool WORDS = false> struct Cfg5 {
     static constexpr int ENC_WARP = ENC_REC + REC_BYTES;
     static constexpr int ENC_WARPS = (SMEM_MAX - ENC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - ENC_WARP) / WARP_BYTES : 32;
     static constexpr int TOTAL_ENC = ENC_WARP + ENC_WARPS * WARP_BYTES;
-    // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | GF(27) + Chien tables | records
-    static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 24 + 15) / 16 * 16;
+    // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | par[3][2] | GF(27) + Chien tables | records
+    static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 48 + 15) / 16 * 16;   // chk[3][2] | par[3][2]
     static constexpr int CHIEN_BYTES = ((26 - K) / 2) * 27 * 24;                // the locator has at most t coefficients besides sigma_0
     static constexpr int DEC_REC = DEC_GF + ((int)sizeof(GfTables) + CHIEN_BYTES + 15) / 16 * 16;
     static constexpr int DEC_IMAGE = DEC_REC + REC_BYTES;                       // what the image holds
@@ -362,6 +362,24 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables*
         }
         reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid] = c.nz;
         reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[2 * tid + 1] = c.two;
+        // the hot path sums the K data positions only and compares the parity it implies with the received parity symbols as bytes:
+        // sum_{i<K} T_i[r_i] = parity(c) + D with D = sum_{i<K} T_i[13*st_i], the received parity symbol j of a codeword is parity(c)_j (+)
+        // 13*st_{K+j}, so the constant to add is par = (scrambler pattern of the parity positions) - D
+        Planes e{0, 0};
+        for (int i = 0; i < K; ++i) {
+            const int idx = i * 32 + 13 * (int)st_of(g, tid, i);
+            gf3_add(e, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
+        }
+        e.two ^= e.nz;                                          // -D
+        uint32_t pn = 0, pt = 0;
+        for (int j = 0; j < 26 - K; ++j) {
+            const uint32_t st = st_of(g, tid, K + j);
+            if (st) pn |= 7u << plane_shift<K>(j);
+            if (st == 2) pt |= 7u << plane_shift<K>(j);
+        }
+        gf3_add(e, pn, pt);
+        reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[6 + 2 * tid] = e.nz;
+        reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[6 + 2 * tid + 1] = e.two;
     }
     __syncthreads();
     for (int i = tid; i < L5::DEC_IMAGE / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
@@ -490,24 +508,36 @@ static __device__ __noinline__ void dec_cw_mod27(uint8_t* src)
 {
     for (int i = 0; i < 26; ++i) src[i] = (uint8_t)(src[i] % 27u);   // in place in the staged run: the codeword belongs to this lane alone
 }
-// a codeword that fails the screen: the screen's sum minus the clean-codeword constant is the parity residual, from which the
-// bounded-distance decoder (dev.cuh rs_bd_fix) repairs the data symbols the hot path has already stored
+// a codeword whose received parity differs from the parity its data symbols imply: finish the syndrome screen with the R parity
+// positions (table rows K..25 hold -x in the planes), subtract the clean-codeword constant -- that is the parity residual, from which
+// the bounded-distance decoder (dev.cuh rs_bd_fix) repairs the data symbols the hot path has already stored
 template <int K>
-static __device__ __noinline__ void dec_cw_dirty(uint8_t* dst, uint32_t acc_nz, uint32_t acc_two, uint32_t chk_nz, uint32_t chk_two, const GfTables& sg, uint32_t* status)
+static __device__ __noinline__ void dec_cw_dirty5(const uint8_t* src, uint8_t* dst, uint32_t acc_nz, uint32_t acc_two, const uint8_t* tab_v, const uint32_t* chk_v,
+                                                  const GfTables& sg, uint32_t* status)
 {
+    constexpr int PLANE = 26 * 32;
     Planes d{acc_nz, acc_two};
-    gf3_add(d, chk_nz, chk_nz ^ chk_two);                      // minus the constant: -x keeps nz and flips two where nz is set
+#pragma unroll 1
+    for (int i = K; i < 26; ++i) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(tab_v) + 32 * i + src[i];   // src[i] < 32 here (dec_cw_mod27 ran if any byte was larger)
+        gf3_add(d, row[0], row[PLANE]);
+    }
+    const uint32_t cn = chk_v[0], ct = chk_v[1];
+    gf3_add(d, cn, cn ^ ct);                                   // minus the constant: -x keeps nz and flips two where nz is set
+    if (!(d.nz >> 8)) return;                                  // a parity byte 27..31 (alias of 0..4) in an otherwise clean codeword
     uint32_t lo, hi;
     planes_to_parity<K>(d.nz, d.two, lo, hi);
     rs_bd_fix<K>(sg, chien_of(&sg), dst, lo, hi, status, true);   // the image keeps the Chien tables behind the GF(27) tables, as HostTables does
 }
-// ---- one codeword of decode phase B (see dec_cw, PRESCALED = false): 26 received symbols at src (even address) -> screen -> K descrambled
-// data symbols scattered at byte stride 9 from dst
+// ---- one codeword of decode phase B: 26 received symbols at src (even address) -> K descrambled data symbols scattered at byte stride 9
+// from dst, and the screen: the parity the K data symbols imply (K table look-ups, plane sums), scrambled in the plane domain (par_*: see
+// k_v5_image_dec), converted to bytes and compared with the R received parity symbols as they lie in the run -- 6 look-ups, 18 LOP3 and
+// 6 PRMT fewer per codeword than the full 26-position syndrome sum, which only dirty codewords finish (dec_cw_dirty5)
 template <int K>
-__device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, uint32_t chk_nz, uint32_t chk_two,
+__device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, uint32_t par_nz, uint32_t par_two, const uint32_t* chk_v,
                                         const GfTables& sg, uint32_t* status)
 {
-    constexpr int PLANE = 4 * 26 * 32;
+    constexpr int PLANE = 4 * 26 * 32, W = K / 4, NW = (K + 3) / 4;
     asm volatile("" : "+r"(pa));   // the block address in a vector register: with a uniform one PRMT would need its selector in a register (a move per symbol)
     const uint32_t sa = smem_u32(src), sh = (sa & 2u) * 8u;
     uint32_t xw[7];
@@ -522,23 +552,36 @@ __device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32
     };
     load();
     if ((xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6]) & 0xE0E0E0E0u) { dec_cw_mod27(const_cast<uint8_t*>(src)); load(); }
+    // the received parity symbols K..25 as bytes of two words
+    uint32_t rx_lo, rx_hi = 0;
+    if constexpr (K % 4 == 0) {
+        rx_lo = xw[W];
+        if constexpr (W + 1 < 7) rx_hi = xw[W + 1];
+    } else {
+        rx_lo = __funnelshift_r(xw[W], xw[W + 1], 16);
+        if constexpr (W + 2 < 7) rx_hi = __funnelshift_r(xw[W + 1], xw[W + 2], 16);
+    }
 #pragma unroll
-    for (int j = 0; j < 7; ++j) xw[j] *= 4u;                       // table byte offsets; < 128 per byte: no carry between symbols
+    for (int j = 0; j < NW; ++j) xw[j] *= 4u;                      // table byte offsets; < 128 per byte: no carry between symbols
     Planes acc{0, 0}, acc2{0, 0};
     uint32_t ev[K];
-    static_for<0, 26>([&](auto ic) {
+    static_for<0, K>([&](auto ic) {
         constexpr int i = decltype(ic)::value;
         const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
         const uint32_t ea = lds_tab<128 * i>(ra);
         const uint32_t eb = lds_tab<128 * i + PLANE>(ra);
         if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
-        if (i < K) ev[i < K ? i : 0] = ea;
+        ev[i] = ea;
     });
 #pragma unroll
     for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
     gf3_add(acc, acc2.nz, acc2.two);
-    if (((acc.nz ^ chk_nz) | (acc.two ^ chk_two)) & ~0xFFu)        // the low bytes carry the embedded symbols
-        dec_cw_dirty<K>(dst, acc.nz, acc.two, chk_nz, chk_two, sg, status);
+    Planes s = acc;
+    gf3_add(s, par_nz, par_two);
+    uint32_t lo, hi;
+    planes_to_parity<K>(s.nz, s.two, lo, hi);
+    if ((26 - K > 4) ? (((lo ^ rx_lo) | (hi ^ rx_hi)) != 0u) : (lo != rx_lo))
+        dec_cw_dirty5<K>(src, dst, acc.nz, acc.two, tab_v, chk_v, sg, status);
 }
 
 // pixel value -> RGB8 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84) in integers.  The
@@ -624,7 +667,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
     __syncthreads();
     const uint32_t tabA32 = smem_u32(smem);
     const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L5::DEC_CHK);
-    const uint32_t chk0n = chk[0], chk0t = chk[1], chk1n = chk[2], chk1t = chk[3], chk2n = chk[4], chk2t = chk[5];
+    const uint32_t par0n = chk[6], par0t = chk[7], par1n = chk[8], par1t = chk[9], par2n = chk[10], par2t = chk[11];   // parity-compare constants (k_v5_image_dec)
     const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
     uint32_t mt_lo, mt_hi;
     warp_range_smsp((uint64_t)P.n_tiles * P.n_frames, blockIdx.x, gridDim.x, warp, NW, mt_lo, mt_hi);
@@ -685,14 +728,14 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
                 constexpr int p = decltype(pc)::value;
                 const uint2 r = rt[32 * p + lane];
                 const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFFu));
-                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, smem + p * L5::DEC_VAR, p == 0 ? chk0n : p == 1 ? chk1n : chk2n,
-                                 p == 0 ? chk0t : p == 1 ? chk1t : chk2t, sg, status);
+                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, smem + p * L5::DEC_VAR, p == 0 ? par0n : p == 1 ? par1n : par2n,
+                                 p == 0 ? par0t : p == 1 ? par1t : par2t, chk + 2 * p, sg, status);
             });
             const uint2 r = rt[96 + lane];
             const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFu));
             if (r.y != REC_IDLE) {
                 const uint32_t v = r.y >> 8;
-                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, smem + v * L5::DEC_VAR, chk[2 * v], chk[2 * v + 1], sg, status);
+                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, smem + v * L5::DEC_VAR, chk[6 + 2 * v], chk[7 + 2 * v], chk + 2 * v, sg, status);
             }
         }
         __syncwarp();

@@ -314,6 +314,68 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
     }
 }
 
+// ---- one codeword of decode phase B, parity-compare screen (k_fast5.cuh dec_cw5 has the reasoning): the K data symbols' look-ups give the
+// parity they imply; scrambled in the plane domain and converted to bytes it is compared with the R received parity symbols (x4 here: the
+// squeeze pass has scaled the runs).  Only codewords that differ finish the 26-position syndrome sum and go to the bounded-distance decoder.
+// c4 = {chk_nz, chk_two, par_nz, par_two} of the codeword's (k, variant)
+template <int K>
+static __device__ __noinline__ void dec_cw_dirty_s(const uint8_t* src, uint8_t* dst, uint32_t acc_nz, uint32_t acc_two, const uint8_t* tab_v, uint32_t chk_nz, uint32_t chk_two,
+                                                   const GfTables& sg, const uint32_t* chien, uint32_t* status)
+{
+    Planes d{acc_nz, acc_two};
+#pragma unroll 1
+    for (int i = K; i < 26; ++i) {
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(tab_v + 128 * i + src[i]);   // src holds symbols x4 (< 128)
+        gf3_add(d, row[0], row[26 * 32]);
+    }
+    gf3_add(d, chk_nz, chk_nz ^ chk_two);                      // minus the clean-codeword constant
+    if (!(d.nz >> 8)) return;
+    uint32_t lo, hi;
+    planes_to_parity<K>(d.nz, d.two, lo, hi);
+    rs_bd_fix<K>(sg, chien, dst, lo, hi, status, true);
+}
+template <int K>
+__device__ __forceinline__ void dec_cw_s(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, const uint4 c4, const GfTables& sg, const uint32_t* chien, uint32_t* status)
+{
+    constexpr int PLANE = 4 * 26 * 32, W = K / 4;
+    const uint32_t sa = smem_u32(src), sh = (sa & 2u) * 8u;
+    uint32_t xw[7];
+    static_for<0, 7>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(xw[j]) : "r"(sa & ~3u), "n"(4 * j) : "memory");
+    });
+#pragma unroll
+    for (int j = 0; j < 6; ++j) xw[j] = __funnelshift_r(xw[j], xw[j + 1], sh);
+    xw[6] = (xw[6] >> sh) & 0xFFFFu;
+    uint32_t rx_lo, rx_hi = 0;
+    if constexpr (K % 4 == 0) {
+        rx_lo = xw[W];
+        if constexpr (W + 1 < 7) rx_hi = xw[W + 1];
+    } else {
+        rx_lo = __funnelshift_r(xw[W], xw[W + 1], 16);
+        if constexpr (W + 2 < 7) rx_hi = __funnelshift_r(xw[W + 1], xw[W + 2], 16);
+    }
+    Planes acc{0, 0}, acc2{0, 0};
+    uint32_t ev[K];
+    static_for<0, K>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
+        const uint32_t ea = lds_tab<128 * i>(ra);
+        const uint32_t eb = lds_tab<128 * i + PLANE>(ra);
+        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        ev[i] = ea;
+    });
+#pragma unroll
+    for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];
+    gf3_add(acc, acc2.nz, acc2.two);
+    Planes s = acc;
+    gf3_add(s, c4.z, c4.w);
+    uint32_t lo, hi;
+    planes_to_parity<K>(s.nz, s.two, lo, hi);
+    if ((26 - K > 4) ? ((((lo << 2) ^ rx_lo) | ((hi << 2) ^ rx_hi)) != 0u) : ((lo << 2) != rx_lo))
+        dec_cw_dirty_s<K>(src, dst, acc.nz, acc.two, tab_v, c4.x, c4.y, sg, chien, status);
+}
+
 // =============================================================================================
 // decode
 // =============================================================================================
@@ -327,7 +389,7 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
     uint8_t* S = smem + P.off_S;                   // the runs as they lie in the frame, later the descrambled stream symbols
     uint8_t* R = smem + P.off_U;                   // the nine pre-beacon runs (x4), later the pixel-side bytes on their way out
     SuperMeta& meta = *reinterpret_cast<SuperMeta*>(smem + P.off_meta);
-    uint32_t* chk = reinterpret_cast<uint32_t*>(smem + P.off_aux); // [k slot][variant][2]
+    uint32_t* chk = reinterpret_cast<uint32_t*>(smem + P.off_aux); // [k slot][variant]{chk_nz, chk_two, par_nz, par_two}
     GfTables& sg = *reinterpret_cast<GfTables*>(smem + P.off_gf);
     for (uint32_t ks = 0; ks < P.nk; ++ks) {
         const int K = (int)P.kk[ks];
@@ -349,8 +411,26 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             const int idx = i * 32 + 13 * (int)st_of(g, v, i);
             gf3_add(c, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
         }
-        chk[2 * tid] = c.nz;
-        chk[2 * tid + 1] = c.two;
+        chk[4 * tid] = c.nz;
+        chk[4 * tid + 1] = c.two;
+        // the parity-compare constant of dec_cw_s (k_v5_image_dec derives it): (scrambler pattern of the parity positions) - sum_{i<K} T_i[13*st_i]
+        const int K = (int)P.kk[ks];
+        Planes e{0, 0};
+        for (int i = 0; i < K; ++i) {
+            const int idx = i * 32 + 13 * (int)st_of(g, v, i);
+            gf3_add(e, blk[idx] & ~0xFFu, blk[26 * 32 + idx]);
+        }
+        e.two ^= e.nz;
+        uint32_t pn = 0, pt = 0;
+        for (int j = 0; j < 26 - K; ++j) {
+            const uint32_t st = st_of(g, v, K + j);
+            const int sh = 26 - K <= 6 ? 8 + 4 * j : 8 + 3 * j;   // plane_shift<K>(j)
+            if (st) pn |= 7u << sh;
+            if (st == 2) pt |= 7u << sh;
+        }
+        gf3_add(e, pn, pt);
+        chk[4 * tid + 2] = e.nz;
+        chk[4 * tid + 3] = e.two;
     }
     const uint32_t smem32 = smem_u32(smem);
     const uint64_t in_limit = Q.in_stride * (Q.n_frames - 1) + 9 * g.n_out;
@@ -441,11 +521,11 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             const uint8_t* src = R + P.run_base[b] + 26u * cl;
             uint8_t* dst = S + 9u * K * cl + b;
             const uint32_t toff = P.off_tab[ks] + v * 6656u;
-            const uint32_t cnz = chk[6 * ks + 2 * v], ctw = chk[6 * ks + 2 * v + 1];
-            if (K == 20) dec_cw<20>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
-            else if (K == 22) dec_cw<22>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
-            else if (K == 24) dec_cw<24>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
-            else dec_cw<18>(src, dst, smem32 + toff, smem + toff, cnz, ctw, sg, chien_of(gf), Q.status + 2 * f);
+            const uint4 c4 = *reinterpret_cast<const uint4*>(chk + 4 * (3 * ks + v));
+            if (K == 20) dec_cw_s<20>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
+            else if (K == 22) dec_cw_s<22>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
+            else if (K == 24) dec_cw_s<24>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
+            else dec_cw_s<18>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
         }
         __syncthreads();                           // S complete, R dead
         SUP_TICK(6);
@@ -535,7 +615,7 @@ static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, b
         }
         if (M / 20u >= 4095u || n_cw / 32u + 3u * P.nk > SUP_MAX_PASS) continue;
         for (uint32_t s = 0; s < P.nk; ++s) { P.off_tab[s] = off; off += decode ? 3u * 6656u : up256(3u * 8u * P.kk[s] * 27u); }
-        P.off_aux = off; off += up16(4u * 6u * 4u + 16u);   // + the mbarrier of the encoder's input buffer
+        P.off_aux = off; off += up16(decode ? 4u * 3u * 16u : 4u * 6u * 4u + 16u);   // encoder: pat[4][3][2] + the mbarrier of its input buffer; decoder: [4][3]{chk, par}
         P.off_gf = off; off += decode ? up16((uint32_t)sizeof(GfTables)) : 0u;
         P.off_meta = off; off += 2u * up16((uint32_t)sizeof(SuperMeta));
         const uint32_t UN = 9u * M / 26u, pix = up16(pixb * UN + 48u);
