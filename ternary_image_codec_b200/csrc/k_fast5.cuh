@@ -147,10 +147,14 @@ template <int K, bool WORDS>
 __device__ __forceinline__ void enc_phase_a5(const uint8_t* IN, uint32_t pad, uint8_t* S, int lane)
 {
     using L = Cfg3<K>;
-    // units dealt even / odd over the first two passes: 36- and 52-byte lane strides (9 and 13 words, conflict-free)
+    static_assert(L::UNITS >= 64, "two full passes at least");
+    // units dealt even / odd over the first two passes: 36- and 52-byte lane strides (9 and 13 words, conflict-free), and the pass is the
+    // alignment of the unit's 26 symbols in S (compile-time store26)
+    enc_unit5<K, WORDS, 0>(IN, pad, S, 2 * lane);
+    enc_unit5<K, WORDS, 1>(IN, pad, S, 2 * lane + 1);
 #pragma unroll 1
-    for (int pass = 0; pass < L::PASS_A; ++pass) {
-        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+    for (int pass = 2; pass < L::PASS_A; ++pass) {
+        const int u = 32 * pass + lane;
         if (u < L::UNITS) enc_unit5<K, WORDS, 2>(IN, pad, S, u);
     }
 }
@@ -176,7 +180,8 @@ template <int K, bool WORDS = false> struct Cfg5 {
     static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 48 + 15) / 16 * 16;   // chk[3][2] | par[3][2]
     static constexpr int CHIEN_BYTES = ((26 - K) / 2) * 27 * 24;                // the locator has at most t coefficients besides sigma_0
     static constexpr int DEC_REC = DEC_GF + ((int)sizeof(GfTables) + CHIEN_BYTES + 15) / 16 * 16;
-    static constexpr int DEC_IMAGE = DEC_REC + REC_BYTES;                       // what the image holds
+    static constexpr int DEC_CLUT = DEC_REC + REC_BYTES;                        // dequantised chroma of the 81 quantised values, one byte each (dec_unit_rgb5)
+    static constexpr int DEC_IMAGE = DEC_CLUT + 96;                             // what the image holds
     static constexpr int DEC_WARP = (DEC_IMAGE + 127) / 128 * 128;              // per-warp blocks start 128-byte aligned (tensor copies land there)
     static constexpr int DEC_WARP_BYTES = (WARP_BYTES + 127) / 128 * 128;       // decode: R | OUT | S | carry | barrier
     static constexpr int DEC_WARPS = (SMEM_MAX - 256 - DEC_WARP) / DEC_WARP_BYTES < 32 ? (SMEM_MAX - 256 - DEC_WARP) / DEC_WARP_BYTES : 32;
@@ -205,9 +210,11 @@ constexpr int V5_G1 = 1443411, V5_G2 = 2995303;      // 0.344136, 0.714136 x 2^2
 constexpr uint32_t V5_FLAGS_DEFAULT = 1u | (9000u << 8);
 __device__ __forceinline__ void stagger_start(uint32_t flags, int warp, uint32_t n_tiles)
 {
-    if ((flags & 1u) && (warp & 4) && n_tiles >= 8) {   // short ranges (chunked host pipelines) would only lose the delay
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)(flags >> 8)) { }
+    // flags & 8: four groups (warp / 4 mod 4) a quarter period apart instead of two (experiment)
+    const uint32_t grp = (flags & 8u) ? ((uint32_t)warp >> 2) & 3u : ((uint32_t)warp >> 2) & 1u;
+    if ((flags & 1u) && grp && n_tiles >= 8) {   // short ranges (chunked host pipelines) would only lose the delay
+        const long long t0 = clock64(), d = (long long)grp * (long long)(flags >> 8);
+        while (clock64() - t0 < d) { }
     }
 }
 // position of a warp inside its contiguous tile range: everything phase A / B / C need, advanced by constants
@@ -351,6 +358,7 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables*
     load_gf(sg, gf);
     for (int i = tid; i < L5::CHIEN_BYTES / 4; i += TPB) reinterpret_cast<uint32_t*>(&sg + 1)[i] = chien_of(gf)[i];
     for (int t = tid; t < 3 * 128; t += TPB) build_pass_map(maps, g, t);
+    if (tid < 96) smem[L5::DEC_CLUT + tid] = (uint8_t)min((32u * (uint32_t)tid + 5u) / 10u, 255u);   // dequantize_ycbcr's chroma (IMG:79-84) of Cq + 40 = tid
     __syncthreads();
     for (int t = tid; t < 3 * 128; t += TPB) build_records<K, L5::RUN_PITCH>(reinterpret_cast<uint2*>(smem + L5::DEC_REC), maps, g, t);
     if (tid < 3) { // a received block r = c (+) 13*st is a codeword iff sum_i T_i[r_i] == sum_i T_i[13*st_i] (GF(3)-linear tables)
@@ -611,19 +619,50 @@ __device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
     return yuvq_to_rgb5(Yq, q - 81u * ur, ur);
 }
 // ---- decode phase A: 26 stream symbols at S + a (even) -> six pixels -> 18 RGB bytes at dst (even address): four 32-bit stores and one
-// 16-bit store, aligned per lane by funnel shifts (see store26)
-__device__ __forceinline__ void dec_unit_rgb5(const uint8_t* S, uint32_t a, uint8_t* dst)
+// 16-bit store, aligned per lane by funnel shifts (see store26).  PARU = 0 / 1: a is 0 / 2 mod 4, known at compile time (the alignment
+// shifts of the loads vanish or become immediates); PARU = 2: decided per lane.  clut: the 81 dequantised chroma values as bytes -- 21
+// consecutive words, so a look-up never meets a bank conflict -- instead of a multiply, a multiply-high and a min per component (the
+// multiply pipe bounds this phase: a multiply-high takes it for four cycles, tools/probe/pipe_rates.cu).  The 18 bytes are gathered
+// from the clamped sums (r and b in byte 2, g in byte 0) by 13 PRMT.
+template <int PARU>
+__device__ __forceinline__ void dec_unit_rgb5(const uint8_t* S, uint32_t a, uint8_t* dst, const uint8_t* __restrict__ clut)
 {
-    uint32_t y[7]; // the 26 symbols, word aligned
-    load_unit26<false>(S, a, y, false);
-    uint32_t A[6];
-    symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
-    symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
-    uint32_t p[6];
+    const uint32_t* mw = reinterpret_cast<const uint32_t*>(S + (a & ~3u));
+    uint32_t x[7];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) p[q] = value_to_rgb5(A[q]);
-    // 18 bytes as words: p0 | p1<<24, p1>>8 | p2<<16, p2>>16 | p3<<8, p4 | p5<<24, (p5>>8: two bytes)
-    const uint32_t w[5] = {p[0] | (p[1] << 24), (p[1] >> 8) | (p[2] << 16), (p[2] >> 16) | (p[3] << 8), p[4] | (p[5] << 24), p[5] >> 8};
+    for (int j = 0; j < 7; ++j) x[j] = mw[j];
+    uint32_t y0, y1, y2, s12, z0, z1, z2, t12;   // symbols 0..11, 12, 13..24, 25
+    if constexpr (PARU == 0) {
+        y0 = x[0]; y1 = x[1]; y2 = x[2]; s12 = x[3] & 0xFFu;
+        z0 = __funnelshift_r(x[3], x[4], 8); z1 = __funnelshift_r(x[4], x[5], 8); z2 = __funnelshift_r(x[5], x[6], 8); t12 = (x[6] >> 8) & 0xFFu;
+    } else if constexpr (PARU == 1) {
+        y0 = __funnelshift_r(x[0], x[1], 16); y1 = __funnelshift_r(x[1], x[2], 16); y2 = __funnelshift_r(x[2], x[3], 16); s12 = (x[3] >> 16) & 0xFFu;
+        z0 = __funnelshift_r(x[3], x[4], 24); z1 = __funnelshift_r(x[4], x[5], 24); z2 = __funnelshift_r(x[5], x[6], 24); t12 = x[6] >> 24;
+    } else {
+        const uint32_t sh = (a & 2u) * 8u, sh8 = sh + 8u;
+        y0 = __funnelshift_r(x[0], x[1], sh); y1 = __funnelshift_r(x[1], x[2], sh); y2 = __funnelshift_r(x[2], x[3], sh); s12 = (x[3] >> sh) & 0xFFu;
+        z0 = __funnelshift_r(x[3], x[4], sh8); z1 = __funnelshift_r(x[4], x[5], sh8); z2 = __funnelshift_r(x[5], x[6], sh8); t12 = (x[6] >> sh8) & 0xFFu;
+    }
+    uint32_t A[6];
+    symbols_to_triple(y0, y1, y2, s12, A[0], A[1], A[2]);
+    symbols_to_triple(z0, z1, z2, t12, A[3], A[4], A[5]);
+    uint32_t r[6], g[6], b[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const uint32_t qq = __umulhi(A[q], 17674763u);             // A / 243, exact for A < 3^13
+        const uint32_t Yq = A[q] - 243u * qq;
+        const uint32_t ur = __umulhi(qq, 53024288u);               // / 81, exact below 6561
+        const int Cb = clut[qq - 81u * ur], Cr = clut[ur];
+        const int Y = (int)__umulhi(Yq * 510u + 241u, 8873899u);
+        const int Y16 = Y << 16, Y22 = Y << 22;
+        r[q] = (uint32_t)__viaddmin_s32_relu(Cr * V5_CR + Y16, 32768 - 128 * V5_CR, 0xFFFFFF);
+        b[q] = (uint32_t)__viaddmin_s32_relu(Cb * V5_CB + Y16, 32768 + 32 - 128 * V5_CB, 0xFFFFFF);
+        g[q] = (uint32_t)__viaddmin_s32_relu(Cr * -V5_G2 + (Cb * -V5_G1 + Y22), 2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22;
+    }
+    auto rg = [&](int q) { return __byte_perm(r[q], g[q], 0x0042); };           // R | G << 8
+    auto gb = [&](int q) { return __byte_perm(g[q], b[q], 0x0060); };           // G | B << 8
+    auto br = [&](int q) { return __byte_perm(b[q], r[q + 1], 0x0062); };       // B | R' << 8
+    const uint32_t w[5] = {__byte_perm(rg(0), br(0), 0x5410), __byte_perm(gb(1), rg(2), 0x5410), __byte_perm(br(2), gb(3), 0x5410), __byte_perm(rg(4), br(4), 0x5410), gb(5)};
     const uint32_t da = smem_u32(dst), odd = da & 2u, sh = odd << 3;
     uint32_t* d = reinterpret_cast<uint32_t*>(dst + odd);
 #pragma unroll
@@ -631,14 +670,17 @@ __device__ __forceinline__ void dec_unit_rgb5(const uint8_t* S, uint32_t a, uint
     *reinterpret_cast<uint16_t*>(dst + (odd ? 0 : 16)) = (uint16_t)(odd ? w[0] : w[4]);
 }
 template <int K>
-__device__ __forceinline__ void dec_phase_a5(const uint8_t* S, uint8_t* OUT, uint32_t pad, int lane)
+__device__ __forceinline__ void dec_phase_a5(const uint8_t* S, uint8_t* OUT, uint32_t pad, int lane, const uint8_t* __restrict__ clut)
 {
     using L = Cfg3<K>;
+    static_assert(L::PASS_A >= 3, "two full passes at least");
+    // units dealt even / odd over the first two passes (S is 4-byte aligned and a unit has 26 bytes: the pass is the alignment)
+    dec_unit_rgb5<0>(S, 52u * (uint32_t)lane, OUT + pad + 36 * lane, clut);               // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
+    dec_unit_rgb5<1>(S, 52u * (uint32_t)lane + 26u, OUT + pad + 36 * lane + 18, clut);
 #pragma unroll 1
-    for (int pass = 0; pass < L::PASS_A; ++pass) {
-        const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
-        if (u >= L::UNITS) continue;
-        dec_unit_rgb5(S, 26u * (uint32_t)u, OUT + pad + 18 * u); // pad is even: every frame starts on a 16-byte boundary and 3*PX*tile is even
+    for (int pass = 2; pass < L::PASS_A; ++pass) {
+        const int u = 32 * pass + lane;
+        if (u < L::UNITS) dec_unit_rgb5<2>(S, 26u * (uint32_t)u, OUT + pad + 18 * u, clut);
     }
 }
 
@@ -747,7 +789,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
             if (!first) *reinterpret_cast<uint4*>(OUT) = carry[0];                   // bytes [0, pad): the previous tile's tail
         }
         __syncwarp();
-        if constexpr (WORDS) dec_phase_a_words<K>(S, OUT, pad, lane); else dec_phase_a5<K>(S, OUT, pad, lane);
+        if constexpr (WORDS) dec_phase_a_words<K>(S, OUT, pad, lane); else dec_phase_a5<K>(S, OUT, pad, lane, smem + L5::DEC_CLUT);
         fence_async_smem();
         __syncwarp();
         {   // the pixel side of the tile -> global: whole chunks by one bulk store, edge bytes of a stretch one by one
