@@ -1549,6 +1549,21 @@ static const uint8_t* v5_image(const DevTables& T, const Geom& g, bool dec, cuda
     C.e[slot].valid = true;
     return img;
 }
+typedef CUresult (*tensor_map_encode_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tensor_map_encode_t tensor_map_encode_fn()   // cuTensorMapEncodeTiled through the runtime (no link against libcuda)
+{
+    static tensor_map_encode_t enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) enc = (tensor_map_encode_t)fn;
+        else cudaGetLastError();
+    }
+    return enc;
+}
 // T3C_V5_FLAGS overrides both defaults.  The decoder runs without the staggered start since its screen sums the K data positions only
 // (r02q: 142.4 us against 144.4 us with it; the encoder still gains: 147.5 against 153.5 us)
 static uint32_t v5_flags(bool dec = false)
@@ -1569,8 +1584,29 @@ static int launch_v5_enc(const DevTables& T, FastParams P, const Geom& g, cudaSt
     uint64_t grid = (uint64_t)T.sm_count * occ;
     if (grid > need) grid = need;
     if (!grid) return n;
-    P.flags = v5_flags();
-    k_encode_v5<K, WORDS><<<(unsigned)grid, 32 * L5::ENC_WARPS, L5::TOTAL_ENC, st>>>(P, g, T.gf, img);
+    P.flags = v5_flags() & ~16u;
+    // One 3-D tensor store (TMA, SASS UTMASTG) per mini-tile instead of nine bulk stores when the nine runs of a tile form a regular box
+    // (the condition of launch_v5_dec's tensor copy, on the output buffer).  T3C_V5_FLAGS |= 32 turns it off.
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof tmap);
+    if (!(v5_flags() & 32u)) {
+        bool regular = P.out_stride % 16 == 0 || P.n_frames == 1;
+        for (int b = 1; b < 9; ++b) regular = regular && g.ncw[b] == g.ncw[0];
+        const uint64_t pitch = 26 * g.ncw[0];
+        regular = regular && pitch % 16 == 0 && pitch >= 4096 && ((uintptr_t)P.out & 15) == 0 && g.cw_base[0] == 0;
+        if (regular) {
+            const cuuint64_t frame_pitch = P.n_frames > 1 ? P.out_stride : (9 * pitch + 4096 + 15) / 16 * 16;
+            const cuuint64_t dims[3] = {pitch / 2, 9, P.n_frames}, strides[2] = {pitch, frame_pitch};
+            const cuuint32_t box[3] = {(cuuint32_t)L5::RUN_PITCH / 2, 9, 1}, estr[3] = {1, 1, 1};
+            if (tensor_map_encode_fn() && tensor_map_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, P.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+                P.flags |= 16u;
+                P.band_stride = pitch;
+            }
+        }
+    }
+    if (getenv("T3C_DEBUG")) std::fprintf(stderr, "t3c: k_encode_v5<%d,%d> grid %u, flags %#x (tensor store %s)\n", K, (int)WORDS, (unsigned)grid, P.flags, (P.flags & 16u) ? "on" : "off");
+    k_encode_v5<K, WORDS><<<(unsigned)grid, 32 * L5::ENC_WARPS, L5::TOTAL_ENC, st>>>(P, g, T.gf, img, tmap);
     return n + 1;
 }
 template <int K, bool WORDS>

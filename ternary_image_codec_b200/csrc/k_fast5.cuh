@@ -167,15 +167,17 @@ template <int K, bool WORDS = false> struct Cfg5 {
     static constexpr int RUN_PITCH = 368;                                              // >= 15 + 338, multiple of 16
     static constexpr int RUNS_BYTES = 9 * RUN_PITCH;
     static constexpr int CARRY_BYTES = 9 * 16, BAR_BYTES = 16;
-    static constexpr int WARP_BYTES = IN_BYTES + L::S_BYTES + RUNS_BYTES + CARRY_BYTES + BAR_BYTES; // encode: IN | S | U;  decode: OUT | S | R
+    static constexpr int WARP_BYTES = IN_BYTES + L::S_BYTES + RUNS_BYTES + CARRY_BYTES + BAR_BYTES;
     static constexpr int SMEM_MAX = 227 * 1024;
     // lane records of phase B: [tile mod 3][pass][lane] -> {source offset | destination offset << 16, band | variant << 8}
     static constexpr int REC_BYTES = 3 * 128 * 8;
     // encode, CTA-shared: per variant {A[K][27] | B[K][27]} | pat[3][2] | records
     static constexpr int ENC_PLANE = 4 * K * 27, ENC_VAR = 2 * ENC_PLANE, ENC_PAT = 3 * ENC_VAR, ENC_REC = (ENC_PAT + 24 + 15) / 16 * 16;
-    static constexpr int ENC_WARP = ENC_REC + REC_BYTES;
-    static constexpr int ENC_WARPS = (SMEM_MAX - ENC_WARP) / WARP_BYTES < 32 ? (SMEM_MAX - ENC_WARP) / WARP_BYTES : 32;
-    static constexpr int TOTAL_ENC = ENC_WARP + ENC_WARPS * WARP_BYTES;
+    static constexpr int ENC_IMAGE = ENC_REC + REC_BYTES;                       // what the image holds
+    static constexpr int ENC_WARP = (ENC_IMAGE + 127) / 128 * 128;              // per-warp blocks start 128-byte aligned (the tensor store reads U from there)
+    static constexpr int ENC_WARP_BYTES = (WARP_BYTES + 127) / 128 * 128;       // encode: U | IN | S | carry | barrier
+    static constexpr int ENC_WARPS = (SMEM_MAX - ENC_WARP) / ENC_WARP_BYTES < 32 ? (SMEM_MAX - ENC_WARP) / ENC_WARP_BYTES : 32;
+    static constexpr int TOTAL_ENC = ENC_WARP + ENC_WARPS * ENC_WARP_BYTES;
     // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | par[3][2] | GF(27) + Chien tables | records
     static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 48 + 15) / 16 * 16;   // chk[3][2] | par[3][2]
     static constexpr int CHIEN_BYTES = ((26 - K) / 2) * 27 * 24;                // the locator has at most t coefficients besides sigma_0
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_enc(Geom g, const GfTables*
     __syncthreads();
     for (int t = tid; t < 3 * 128; t += TPB) build_records<K, L5::RUN_PITCH>(reinterpret_cast<uint2*>(smem + L5::ENC_REC), maps, g, t);
     __syncthreads();
-    for (int i = tid; i < L5::ENC_WARP / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
+    for (int i = tid; i < L5::ENC_IMAGE / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
 }
 template <int K>
 __global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables* __restrict__ gf, const RsTables* __restrict__ rs, uint8_t* __restrict__ image)
@@ -394,23 +396,24 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables*
 }
 
 template <int K, bool WORDS>
-__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5(FastParams P, Geom g, const GfTables* __restrict__ gf, const uint8_t* __restrict__ image)
+__global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5(FastParams P, Geom g, const GfTables* __restrict__ gf, const uint8_t* __restrict__ image,
+                                                                                 const __grid_constant__ CUtensorMap tmap)
 {
     using L = Cfg3<K>;
     using L5 = Cfg5<K, WORDS>;
     constexpr int PIX = L5::PIX_BYTES, NW = L5::ENC_WARPS, TPB = 32 * NW, PITCH = L5::RUN_PITCH;
     extern __shared__ __align__(16) uint8_t smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t* IN = smem + L5::ENC_WARP + warp * L5::WARP_BYTES;  // the pixel side of the tile (bulk-loaded one tile ahead)
+    uint8_t* U = smem + L5::ENC_WARP + warp * L5::ENC_WARP_BYTES; // the nine body runs (128-byte aligned: the tensor store reads them from here)
+    uint8_t* IN = U + L5::RUNS_BYTES;                           // the pixel side of the tile (bulk-loaded one tile ahead)
     uint8_t* S = IN + L5::IN_BYTES;                             // stream symbols, pre-scaled by 4
-    uint8_t* U = S + L::S_BYTES;                                // the nine body runs
-    uint4* carry = reinterpret_cast<uint4*>(U + L5::RUNS_BYTES);
-    const uint32_t bar = smem_u32(U + L5::RUNS_BYTES + L5::CARRY_BYTES);
+    uint4* carry = reinterpret_cast<uint4*>(S + L::S_BYTES);
+    const uint32_t bar = smem_u32(S + L::S_BYTES + L5::CARRY_BYTES);
     const uint2* rec = reinterpret_cast<const uint2*>(smem + L5::ENC_REC);
     {   // the CTA-shared tables: a copy of the image v5_build_enc made once for this config (FastImageCache)
         const uint4* src = reinterpret_cast<const uint4*>(image);
         uint4* dst = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < L5::ENC_WARP / 16; i += TPB) dst[i] = __ldg(src + i);
+        for (int i = tid; i < L5::ENC_IMAGE / 16; i += TPB) dst[i] = __ldg(src + i);
         if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     }
     __syncthreads(); // tables, records and barriers ready; no block-level barrier after this one
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
         cursor_next<PIX>(nx, P, g, P.in_stride, P.out_stride, lane);
         if (left > 1 && lane == 0) fetch(nx.pix);                                  // IN is free again: next tile's pixels on their way
         if (lane < 9) {
-            bulk_wait_read();                                                        // the previous tile's bulk stores have read U
+            bulk_wait_all();                                                         // the previous tile's stores have read U and have landed (see phase C)
             if (!first) *reinterpret_cast<uint4*>(U + PITCH * lane) = carry[lane];   // bytes [0, padb) of each run: the previous tile's tail
         }
         __syncwarp();
@@ -482,10 +485,22 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
         fence_async_smem();                                                          // generic-proxy writes to U before the bulk engine reads it
         __syncwarp();
         // ---- phase C: nine band-major runs -> global as bulk stores of whole chunks; the partial last chunk is carried to the next tile
+        // Inside a stretch of a regular frame (launch_v5_enc: every band's run has the same 16-byte phase) the nine rows of U leave by ONE
+        // 3-D tensor store (SASS UTMASTG) of all 23 chunks per row: the chunks behind this tile's last whole one hold its tail and stale
+        // bytes, and the same warp's next tile stores over them (its row starts with this tile's tail, carried) -- after this store has
+        // landed: bulk_wait_all above.  The first and the last tile of a stretch store exactly their own chunks, run by run.
+        const bool ts = (P.flags & 16u) && !first && !last && ((52ull + 338ull * c.tile) & ~15ull) + PITCH <= P.band_stride;
         if (lane < 9) {
             const uint32_t cend = (padb + L::RUN) >> 4, c0 = (first && padb) ? 1u : 0u;
             if (!last) carry[lane] = *reinterpret_cast<const uint4*>(U + PITCH * lane + 16 * cend);
-            if (cend > c0) bulk_s2g(P.out + (c.run - padb) + 16 * c0, smem_u32(U + PITCH * lane + 16 * c0), 16 * (cend - c0));
+            if (!ts) {
+                if (cend > c0) bulk_s2g(P.out + (c.run - padb) + 16 * c0, smem_u32(U + PITCH * lane + 16 * c0), 16 * (cend - c0));
+                bulk_commit();
+            }
+        }
+        if (ts && lane == 0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(&tmap), "r"((int)(((52u + 338u * c.tile) & ~15u) >> 1)), "r"(0), "r"((int)c.f), "r"(smem_u32(U)) : "memory");   // x in 16-bit elements
             bulk_commit();
         }
         if (first || last) { // edge bytes of a contiguous stretch, one by one
