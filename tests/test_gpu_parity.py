@@ -543,6 +543,57 @@ def test_multi_frame_stream_device(codec, oracle, t3):
         assert np.array_equal(got[f], oracle.encode_rgb(oc, frames[f], 0))
 
 
+@pytest.mark.parametrize("stride_pad", [0, 16, 3])
+def test_fused_regular_frames_tensor_copies(codec, oracle, t3, stride_pad):
+    """1080p frames at k = 20 are `regular` (every band holds the same number of codewords, band pitch a multiple of 16 bytes): the v5
+    kernels then move the nine runs of a mini-tile by one 3-D tensor copy each way (UTMASTG / UTMALDG).  Three frames in one device
+    call -- frame strides that keep the batch regular (0, 16 words) and one that does not (3 words: the per-run bulk copies) -- and the
+    chunked host pipelines (tile ranges that start inside a frame): encode parity with the oracle, t errors per codeword corrected,
+    decode parity."""
+    import torch
+    kw = dict(profile=T.P3, uep=2)
+    oc, gc = both(kw)
+    n_px, F = 1920 * 1080, 3
+    frames = np.stack([T.synth_rgb(70 + f, n_px) for f in range(F)])
+    want = [oracle.encode_rgb(oc, frames[f], t3.FIXED) for f in range(F)]
+    wpf = t3.profile_words(gc, n_px // 2)
+    assert want[0].shape[0] == wpf
+    stride = ((wpf + 15) & ~15) + stride_pad
+    dev = torch.device("cuda", 0)
+    rgb = torch.from_numpy(frames.reshape(F, -1)).to(dev)
+    enc = torch.zeros(F, stride * 9, dtype=torch.uint8, device=dev)
+    back = torch.zeros(F, n_px * 3, dtype=torch.uint8, device=dev)
+    status = torch.zeros(2 * F, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    codec.encode_frames_rgb8_dev(rgb, n_px, F, enc, stride, gc, t3.FIXED, s)
+    torch.cuda.synchronize()
+    got = enc.cpu().numpy()
+    for f in range(F):
+        assert np.array_equal(got[f, :wpf * 9].reshape(wpf, 9), want[f]), (stride_pad, f)
+        assert not got[f, wpf * 9:].any()                       # nothing written between the frames
+    add = T.gf_add_table()
+    bad = got.copy()
+    tot = 0
+    for f in range(F):
+        b, ne = T.inject_errors(want[f], oc, n_px // 2, seed=3 + f, gf_add=add)
+        bad[f, :wpf * 9] = b.reshape(-1)
+        tot += ne
+    codec.decode_frames_rgb8_dev(torch.from_numpy(bad).to(dev), wpf, stride, F, n_px, back, status, gc, s)
+    torch.cuda.synchronize()
+    st = status.cpu().numpy()
+    assert all(st[2 * f] == 1 for f in range(F)) and int(st[1::2].sum()) == tot
+    rgb_back = back.cpu().numpy().reshape(F, n_px, 3)
+    for f in range(F):
+        ok_o, rgb_o, _ = oracle.decode_rgb_fixed(oc, want[f], n_px)
+        assert ok_o and np.array_equal(rgb_back[f], rgb_o), (stride_pad, f)
+    if stride_pad == 0:                                          # the host-buffer calls: chunked pipelines, tile ranges inside a frame
+        h = codec.encode_frames_rgb8(frames, gc, t3.FIXED)
+        for f in range(F):
+            assert np.array_equal(h[f], want[f]), f
+        ok, rgb_h, nc = codec.decode_frames_rgb8(h, n_px, gc)
+        assert ok.all() and nc == 0 and np.array_equal(rgb_h, rgb_back)
+
+
 @pytest.mark.parametrize("uep", [2, 1, 0])
 def test_fused_fast_path_all_2_24_colours_match_general_kernels(codec, t3, uep):
     """Every RGB colour once (a 4096x4096 frame) through the fused tiled kernels, against the stage-by-stage

@@ -225,6 +225,51 @@ def test_v5_fixed_point_colour_matrix_matches_float32_reference_on_all_values():
     assert np.array_equal(np.clip(full, 0, 0x3FFFFFFF) >> 22, rnd(gf))         # clamp first, then shift, as the kernel does
 
 
+def test_v5_decode_chroma_table_and_constants_in_source():
+    """k_fast5.cuh dec_unit_rgb5: the 81-byte chroma table holds dequantize_ycbcr's chroma (the formula yuvq_to_rgb5 evaluates with a
+    multiply-high), 81 bytes lie in 21 consecutive words (no bank conflict whatever the lanes look up), and the per-pixel sums of the
+    unit body are the ones test_v5_fixed_point_colour_matrix_* pins for yuvq_to_rgb5."""
+    K5 = open(os.path.join(ROOT, "ternary_image_codec_b200", "csrc", "k_fast5.cuh")).read()
+    assert "min((32u * (uint32_t)tid + 5u) / 10u, 255u)" in K5
+    u = np.arange(81, dtype=np.int64)
+    assert np.array_equal(np.minimum((32 * u + 5) // 10, 255), np.minimum((64 * u + 10) // 20, 255))
+    assert (81 + 3) // 4 <= 32
+    unit = K5[K5.index("void dec_unit_rgb5("):K5.index("void dec_phase_a5(")]
+    ref = K5[K5.index("uint32_t yuvq_to_rgb5"):K5.index("uint32_t value_to_rgb5")]
+    for piece in ("Cr * V5_CR + Y16, 32768 - 128 * V5_CR, 0xFFFFFF", "Cb * V5_CB + Y16, 32768 + 32 - 128 * V5_CB, 0xFFFFFF",
+                  "Cr * -V5_G2 + (Cb * -V5_G1 + Y22), 2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22", "__umulhi(Yq * 510u + 241u, 8873899u)"):
+        assert piece in unit and piece in ref, piece
+
+
+def test_parity_compare_screen_is_the_syndrome_screen():
+    """dec_cw5 / dec_cw_s: a received block passes the 26-position screen sum_i T_i[r_i] == chk iff the parity implied by its K data
+    positions, plus the constant par = (scrambler pattern of the parity positions) - sum_{i<K} T_i[13 st_i], equals the received
+    parity symbols -- checked on GF(27) vectors with a random linear systematic code standing in for the RS parity map (the identity
+    needs only linearity over GF(3) and the scrambler being the addition of st * (1,1,1) to every symbol)."""
+    rng = np.random.default_rng(5)
+    K, R = 20, 6
+    add = lambda a, b: (a + b) % 3                                # symbols as 3 trits: arrays [..., 3]
+    P = rng.integers(0, 3, size=(K, 3, R, 3))                     # GF(3)-linear map: data trit (i, t) -> parity trit (j, u)
+    def parity(d):                                                # d: [K, 3] trits -> [R, 3]
+        return np.einsum("it,itju->ju", d, P) % 3
+    st = rng.integers(0, 3, size=26)                              # scrambler state per position
+    pat = np.repeat(st[:, None], 3, axis=1)                       # 13 * st: st on every trit
+    for trial in range(200):
+        d = rng.integers(0, 3, size=(K, 3))
+        c = np.concatenate([d, parity(d)])                        # clean codeword, 26 x 3 trits
+        r = add(c, pat)                                           # as received
+        if trial % 2:                                             # corrupt one symbol
+            r[rng.integers(0, 26), rng.integers(0, 3)] += 1
+            r %= 3
+        # full screen: sum over data positions of parity(r_i e_i) minus the received parity, against the constant of the pattern alone
+        full = (parity(r[:K]) - r[K:]) % 3
+        chk = (parity(pat[:K]) - pat[K:]) % 3
+        clean = np.array_equal(full, chk)
+        # parity-compare: implied parity + par == received parity
+        par = (pat[K:] - parity(pat[:K])) % 3
+        assert np.array_equal(add(parity(r[:K]), par), r[K:]) == clean
+
+
 def test_v5_integer_bridge_matches_float32_reference_on_all_colours():
     """k_fast5.cuh: the integer Cb / Cr path equals the reference's float32 BT.601 + quantiser (IMG:47-56,69-78) for all 2^24
     colours; the integer luma path equals it wherever its tie flag (low nine bits of t) is clear -- flagged pixels take the float path."""

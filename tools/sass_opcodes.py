@@ -8,7 +8,7 @@ import collections, os, re, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ternary_image_codec_b200", "libt3c.so")
-WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "LDG.E.128", "STG.E.128", "LDG.E.64", "STG.E.64", "LDS", "STS", "LOP3", "IMAD", "IDP", "PRMT", "REDUX", "ATOMG", "REDG", "LDL", "STL"]
+WATCH = ["UBLKCP", "UTMALDG", "UTMASTG", "SYNCS", "LDG.E.128", "STG.E.128", "LDG.E.64", "STG.E.64", "LDS", "STS", "LOP3", "IMAD", "IDP", "PRMT", "REDUX", "ATOMG", "REDG", "LDL", "STL"]
 
 
 def main():
@@ -29,7 +29,7 @@ def main():
                 if op == w or op.startswith(w + "."):
                     cur[w] += 1
     print("# cuobjdump -sass ternary_image_codec_b200/libt3c.so (sm_100a), static counts per kernel: total instructions, then the watched opcodes that occur")
-    print("# UBLKCP = cp.async.bulk, UTMALDG = cp.async.bulk.tensor (TMA tile load), SYNCS = mbarrier operations, LDL/STL = local-memory (spill) traffic")
+    print("# UBLKCP = cp.async.bulk, UTMALDG / UTMASTG = cp.async.bulk.tensor (TMA tile load / store), SYNCS = mbarrier operations, LDL/STL = local-memory (spill) traffic")
     for name, c in sorted(per.items(), key=lambda kv: demangle(kv[0])):
         d = demangle(name)
         d = re.sub(r"\(anonymous namespace\)::|<unnamed>::|t3c::|\((?:int|bool|unsigned int)\)", "", d).replace("void ", "")
