@@ -20,6 +20,12 @@
 //     codewords go to an out-of-line bounded-distance decoder with uniform control flow (dev.cuh rs_bd_fix);
 //   * the CTA-shared tables are built once per configuration (FastImageCache) instead of by every CTA of every launch.
 #pragma once
+#ifndef T3C_ENC_WARPS_CAP
+#define T3C_ENC_WARPS_CAP 32   // experiments: fewer encoder warps per CTA
+#endif
+#ifndef T3C_ENC_ONE_LOOP
+#define T3C_ENC_ONE_LOOP 0
+#endif
 
 // ---- exact integer chroma (checked against the float path over all 2^24 colours by tests/test_gpu_parity.py) ------------------------
 constexpr uint32_t C5_M = 2251799814u;                         // ceil(2^46 / 31250): hi32(X * M) >> 14 == X / 31250 for X < 2^32
@@ -150,12 +156,20 @@ __device__ __forceinline__ void enc_phase_a5(const uint8_t* IN, uint32_t pad, ui
     static_assert(L::UNITS >= 64, "two full passes at least");
     // units dealt even / odd over the first two passes: 36- and 52-byte lane strides (9 and 13 words, conflict-free), and the pass is the
     // alignment of the unit's 26 symbols in S (compile-time store26)
-    enc_unit5<K, WORDS, 0>(IN, pad, S, 2 * lane);
-    enc_unit5<K, WORDS, 1>(IN, pad, S, 2 * lane + 1);
+    if constexpr (WORDS || T3C_ENC_ONE_LOOP) {   // the raw-word front end stores halfwords (no alignment to know) and is large: one copy of it
 #pragma unroll 1
-    for (int pass = 2; pass < L::PASS_A; ++pass) {
-        const int u = 32 * pass + lane;
-        if (u < L::UNITS) enc_unit5<K, WORDS, 2>(IN, pad, S, u);
+        for (int pass = 0; pass < L::PASS_A; ++pass) {
+            const int u = pass < 2 ? 2 * lane + pass : 32 * pass + lane;
+            if (u < L::UNITS) enc_unit5<K, WORDS, 2>(IN, pad, S, u);
+        }
+    } else {
+        enc_unit5<K, WORDS, 0>(IN, pad, S, 2 * lane);
+        enc_unit5<K, WORDS, 1>(IN, pad, S, 2 * lane + 1);
+#pragma unroll 1
+        for (int pass = 2; pass < L::PASS_A; ++pass) {
+            const int u = 32 * pass + lane;
+            if (u < L::UNITS) enc_unit5<K, WORDS, 2>(IN, pad, S, u);
+        }
     }
 }
 
@@ -176,7 +190,7 @@ template <int K, bool WORDS = false> struct Cfg5 {
     static constexpr int ENC_IMAGE = ENC_REC + REC_BYTES;                       // what the image holds
     static constexpr int ENC_WARP = (ENC_IMAGE + 127) / 128 * 128;              // per-warp blocks start 128-byte aligned (the tensor store reads U from there)
     static constexpr int ENC_WARP_BYTES = (WARP_BYTES + 127) / 128 * 128;       // encode: U | IN | S | carry | barrier
-    static constexpr int ENC_WARPS = (SMEM_MAX - ENC_WARP) / ENC_WARP_BYTES < 32 ? (SMEM_MAX - ENC_WARP) / ENC_WARP_BYTES : 32;
+    static constexpr int ENC_WARPS = (SMEM_MAX - ENC_WARP) / ENC_WARP_BYTES < T3C_ENC_WARPS_CAP ? (SMEM_MAX - ENC_WARP) / ENC_WARP_BYTES : T3C_ENC_WARPS_CAP;
     static constexpr int TOTAL_ENC = ENC_WARP + ENC_WARPS * ENC_WARP_BYTES;
     // decode, CTA-shared (from a 256-byte aligned base): per variant {A[26][32] | B[26][32]} | chk[3][2] | par[3][2] | GF(27) + Chien tables | records
     static constexpr int DEC_PLANE = 4 * 26 * 32, DEC_VAR = 2 * DEC_PLANE, DEC_CHK = 3 * DEC_VAR, DEC_GF = (DEC_CHK + 48 + 15) / 16 * 16;   // chk[3][2] | par[3][2]
