@@ -647,6 +647,29 @@ __device__ __forceinline__ uint32_t value_to_rgb5(uint32_t A)
     const uint32_t ur = __umulhi(q, 53024288u);                // q / 81, exact for q < 6561
     return yuvq_to_rgb5(Yq, q - 81u * ur, ur);
 }
+// six 13-trit pixel values -> their 18 RGB bytes as words (w[4]: two bytes): dequantised chroma from the 81-byte table, exact fixed-point
+// colour sums (yuvq_to_rgb5), 13 PRMT gather the bytes from the clamped sums (r and b in byte 2, g in byte 0)
+__device__ __forceinline__ void values_to_rgb18(const uint32_t (&A)[6], const uint8_t* __restrict__ clut, uint32_t (&w)[5])
+{
+    uint32_t r[6], g[6], b[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const uint32_t qq = __umulhi(A[q], 17674763u);             // A / 243, exact for A < 3^13
+        const uint32_t Yq = A[q] - 243u * qq;
+        const uint32_t ur = __umulhi(qq, 53024288u);               // / 81, exact below 6561
+        const int Cb = clut[qq - 81u * ur], Cr = clut[ur];
+        const int Y = (int)__umulhi(Yq * 510u + 241u, 8873899u);
+        const int Y16 = Y << 16, Y22 = Y << 22;
+        r[q] = (uint32_t)__viaddmin_s32_relu(Cr * V5_CR + Y16, 32768 - 128 * V5_CR, 0xFFFFFF);
+        b[q] = (uint32_t)__viaddmin_s32_relu(Cb * V5_CB + Y16, 32768 + 32 - 128 * V5_CB, 0xFFFFFF);
+        g[q] = (uint32_t)__viaddmin_s32_relu(Cr * -V5_G2 + (Cb * -V5_G1 + Y22), 2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22;
+    }
+    auto rg = [&](int q) { return __byte_perm(r[q], g[q], 0x0042); };           // R | G << 8
+    auto gb = [&](int q) { return __byte_perm(g[q], b[q], 0x0060); };           // G | B << 8
+    auto br = [&](int q) { return __byte_perm(b[q], r[q + 1], 0x0062); };       // B | R' << 8
+    w[0] = __byte_perm(rg(0), br(0), 0x5410); w[1] = __byte_perm(gb(1), rg(2), 0x5410); w[2] = __byte_perm(br(2), gb(3), 0x5410);
+    w[3] = __byte_perm(rg(4), br(4), 0x5410); w[4] = gb(5);
+}
 // ---- decode phase A: 26 stream symbols at S + a (even) -> six pixels -> 18 RGB bytes at dst (even address): four 32-bit stores and one
 // 16-bit store, aligned per lane by funnel shifts (see store26).  PARU = 0 / 1: a is 0 / 2 mod 4, known at compile time (the alignment
 // shifts of the loads vanish or become immediates); PARU = 2: decided per lane.  clut: the 81 dequantised chroma values as bytes -- 21
@@ -672,26 +695,10 @@ __device__ __forceinline__ void dec_unit_rgb5(const uint8_t* S, uint32_t a, uint
         y0 = __funnelshift_r(x[0], x[1], sh); y1 = __funnelshift_r(x[1], x[2], sh); y2 = __funnelshift_r(x[2], x[3], sh); s12 = (x[3] >> sh) & 0xFFu;
         z0 = __funnelshift_r(x[3], x[4], sh8); z1 = __funnelshift_r(x[4], x[5], sh8); z2 = __funnelshift_r(x[5], x[6], sh8); t12 = (x[6] >> sh8) & 0xFFu;
     }
-    uint32_t A[6];
+    uint32_t A[6], w[5];
     symbols_to_triple(y0, y1, y2, s12, A[0], A[1], A[2]);
     symbols_to_triple(z0, z1, z2, t12, A[3], A[4], A[5]);
-    uint32_t r[6], g[6], b[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        const uint32_t qq = __umulhi(A[q], 17674763u);             // A / 243, exact for A < 3^13
-        const uint32_t Yq = A[q] - 243u * qq;
-        const uint32_t ur = __umulhi(qq, 53024288u);               // / 81, exact below 6561
-        const int Cb = clut[qq - 81u * ur], Cr = clut[ur];
-        const int Y = (int)__umulhi(Yq * 510u + 241u, 8873899u);
-        const int Y16 = Y << 16, Y22 = Y << 22;
-        r[q] = (uint32_t)__viaddmin_s32_relu(Cr * V5_CR + Y16, 32768 - 128 * V5_CR, 0xFFFFFF);
-        b[q] = (uint32_t)__viaddmin_s32_relu(Cb * V5_CB + Y16, 32768 + 32 - 128 * V5_CB, 0xFFFFFF);
-        g[q] = (uint32_t)__viaddmin_s32_relu(Cr * -V5_G2 + (Cb * -V5_G1 + Y22), 2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22;
-    }
-    auto rg = [&](int q) { return __byte_perm(r[q], g[q], 0x0042); };           // R | G << 8
-    auto gb = [&](int q) { return __byte_perm(g[q], b[q], 0x0060); };           // G | B << 8
-    auto br = [&](int q) { return __byte_perm(b[q], r[q + 1], 0x0062); };       // B | R' << 8
-    const uint32_t w[5] = {__byte_perm(rg(0), br(0), 0x5410), __byte_perm(gb(1), rg(2), 0x5410), __byte_perm(br(2), gb(3), 0x5410), __byte_perm(rg(4), br(4), 0x5410), gb(5)};
+    values_to_rgb18(A, clut, w);
     const uint32_t da = smem_u32(dst), odd = da & 2u, sh = odd << 3;
     uint32_t* d = reinterpret_cast<uint32_t*>(dst + odd);
 #pragma unroll

@@ -376,6 +376,22 @@ __device__ __forceinline__ void dec_cw_s(const uint8_t* src, uint8_t* dst, uint3
         dec_cw_dirty_s<K>(src, dst, acc.nz, acc.two, tab_v, c4.x, c4.y, sg, chien, status);
 }
 
+// ---- decode phase A of the super-tile kernel: a unit (a row of a 26-wide 2D tile when rev) -> six pixels -> 18 RGB bytes, with the pixel
+// arithmetic of the v5 warp-tile decoder (values_to_rgb18: table chroma, fixed-point sums, PRMT gather)
+__device__ __forceinline__ void dec_unit_rgb_s(const uint8_t* S, uint32_t a, uint8_t* dst, bool rev, const uint8_t* __restrict__ clut)
+{
+    uint32_t y[7];
+    load_unit26<true>(S, a, y, rev);
+    uint32_t A[6], w[5];
+    symbols_to_triple(y[0], y[1], y[2], y[3] & 0xFF, A[0], A[1], A[2]);
+    symbols_to_triple(__funnelshift_r(y[3], y[4], 8), __funnelshift_r(y[4], y[5], 8), __funnelshift_r(y[5], y[6], 8), (y[6] >> 8) & 0xFF, A[3], A[4], A[5]);
+    values_to_rgb18(A, clut, w);
+    const uint32_t da = smem_u32(dst), odd = da & 2u, sh = odd << 3;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + odd);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = __funnelshift_r(w[j], w[j + 1], sh);
+    *reinterpret_cast<uint16_t*>(dst + (odd ? 0 : 16)) = (uint16_t)(odd ? w[0] : w[4]);
+}
 // =============================================================================================
 // decode
 // =============================================================================================
@@ -390,6 +406,8 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
     uint8_t* R = smem + P.off_U;                   // the nine pre-beacon runs (x4), later the pixel-side bytes on their way out
     SuperMeta& meta = *reinterpret_cast<SuperMeta*>(smem + P.off_meta);
     uint32_t* chk = reinterpret_cast<uint32_t*>(smem + P.off_aux); // [k slot][variant]{chk_nz, chk_two, par_nz, par_two}
+    uint8_t* clut = smem + P.off_aux + 192;        // dequantised chroma of the 81 quantised values (values_to_rgb18)
+    if (tid < 96) clut[tid] = (uint8_t)min((32u * (uint32_t)tid + 5u) / 10u, 255u);
     GfTables& sg = *reinterpret_cast<GfTables*>(smem + P.off_gf);
     for (uint32_t ks = 0; ks < P.nk; ++ks) {
         const int K = (int)P.kk[ks];
@@ -540,7 +558,7 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
                 if (u >= P.UN) continue;
                 const bool rev = super_row_odd(P, P.UN * T + u);                // 26-wide tiles: unit = row
                 if constexpr (WORDS) dec_unit_words<true>(S, 26u * u, R + pad + 27u * u, rev);
-                else dec_unit_rgb<true>(S, 26u * u, R + pad + 18u * u, rev);   // pad is even (frames start on even bytes, 18 UN T is even)
+                else dec_unit_rgb_s(S, 26u * u, R + pad + 18u * u, rev, clut);   // pad is even (frames start on even bytes, 18 UN T is even)
             }
         }
         __syncthreads();
@@ -615,7 +633,7 @@ static bool make_super_plan(const t3c_config& cfg, const Geom& g, bool decode, b
         }
         if (M / 20u >= 4095u || n_cw / 32u + 3u * P.nk > SUP_MAX_PASS) continue;
         for (uint32_t s = 0; s < P.nk; ++s) { P.off_tab[s] = off; off += decode ? 3u * 6656u : up256(3u * 8u * P.kk[s] * 27u); }
-        P.off_aux = off; off += up16(decode ? 4u * 3u * 16u : 4u * 6u * 4u + 16u);   // encoder: pat[4][3][2] + the mbarrier of its input buffer; decoder: [4][3]{chk, par}
+        P.off_aux = off; off += up16(decode ? 4u * 3u * 16u + 96u : 4u * 6u * 4u + 16u);   // encoder: pat[4][3][2] + the mbarrier of its input buffer; decoder: [4][3]{chk, par}
         P.off_gf = off; off += decode ? up16((uint32_t)sizeof(GfTables)) : 0u;
         P.off_meta = off; off += 2u * up16((uint32_t)sizeof(SuperMeta));
         const uint32_t UN = 9u * M / 26u, pix = up16(pixb * UN + 48u);

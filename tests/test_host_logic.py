@@ -234,7 +234,7 @@ def test_v5_decode_chroma_table_and_constants_in_source():
     u = np.arange(81, dtype=np.int64)
     assert np.array_equal(np.minimum((32 * u + 5) // 10, 255), np.minimum((64 * u + 10) // 20, 255))
     assert (81 + 3) // 4 <= 32
-    unit = K5[K5.index("void dec_unit_rgb5("):K5.index("void dec_phase_a5(")]
+    unit = K5[K5.index("void values_to_rgb18("):K5.index("void dec_phase_a5(")]
     ref = K5[K5.index("uint32_t yuvq_to_rgb5"):K5.index("uint32_t value_to_rgb5")]
     for piece in ("Cr * V5_CR + Y16, 32768 - 128 * V5_CR, 0xFFFFFF", "Cb * V5_CB + Y16, 32768 + 32 - 128 * V5_CB, 0xFFFFFF",
                   "Cr * -V5_G2 + (Cb * -V5_G1 + Y22), 2097152 + 128 * (V5_G1 + V5_G2), 0x3FFFFFFF) >> 22", "__umulhi(Yq * 510u + 241u, 8873899u)"):
