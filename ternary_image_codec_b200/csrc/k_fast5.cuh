@@ -23,6 +23,9 @@
 #ifndef T3C_ENC_WARPS_CAP
 #define T3C_ENC_WARPS_CAP 32   // experiments: fewer encoder warps per CTA
 #endif
+#ifndef T3C_ENC_WAIT_READ
+#define T3C_ENC_WAIT_READ 0      // experiment only: does not order the tensor store's trailing chunks
+#endif
 #ifndef T3C_ENC_ONE_LOOP
 #define T3C_ENC_ONE_LOOP 0
 #endif
@@ -470,7 +473,11 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
         cursor_next<PIX>(nx, P, g, P.in_stride, P.out_stride, lane);
         if (left > 1 && lane == 0) fetch(nx.pix);                                  // IN is free again: next tile's pixels on their way
         if (lane < 9) {
+#if T3C_ENC_WAIT_READ
+            bulk_wait_read();
+#else
             bulk_wait_all();                                                         // the previous tile's stores have read U and have landed (see phase C)
+#endif
             if (!first) *reinterpret_cast<uint4*>(U + PITCH * lane) = carry[lane];   // bytes [0, padb) of each run: the previous tile's tail
         }
         __syncwarp();
