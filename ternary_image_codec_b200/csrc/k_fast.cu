@@ -794,8 +794,8 @@ __device__ __forceinline__ void enc_cw(const uint8_t* src, uint8_t* dst, uint32_
         const uint32_t d4 = src[9 * i];
         const uint32_t ra = pa + d4;
         const uint32_t ea = lds_tab<108 * i>(ra), eb = lds_tab<108 * i + PLANE>(ra);
-        if (i & 1) { gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
-        else { gf3_add(acc, ea, eb); prev = ea; }
+        if (i & 1) { if (i == 1) acc2 = Planes{ea, eb}; else gf3_add(acc2, ea, eb); pk[i / 2] = __byte_perm(prev, ea, 0x0040); }
+        else { if (i == 0) acc = Planes{ea, eb}; else gf3_add(acc, ea, eb); prev = ea; }
     });
     gf3_add(acc, acc2.nz, acc2.two);
     gf3_add(acc, pat_nz, pat_two);
@@ -869,7 +869,8 @@ __device__ __forceinline__ void dec_cw(const uint8_t* src, uint8_t* dst, uint32_
         const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
         const uint32_t ea = lds_tab<128 * i>(ra);
         const uint32_t eb = lds_tab<128 * i + PLANE>(ra);
-        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        if (i == 0) acc = Planes{ea, eb}; else if (i == 1) acc2 = Planes{ea, eb};   // 0 + x = x: the first entry of an accumulator is a move
+        else if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
         if (i < K) ev[i < K ? i : 0] = ea;
     });
 #pragma unroll

@@ -303,7 +303,8 @@ __device__ __forceinline__ void enc_cw5(const uint8_t* src, uint8_t* dst, uint32
         const uint32_t ra = VAR >= 0 ? d4 : d4 + vb;
         // plane B is the same in every variant: the mixed pass reads it from block 0, where all its lanes meet in one 27-word row
         const uint32_t ea = lds_abs<BASE + 108 * i>(ra), eb = lds_abs<(VAR >= 0 ? BASE : SMEM_WINDOW_BASE + TAB0) + 108 * i + PLANE>(d4);
-        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        if (i == 0) acc = Planes{ea, eb}; else if (i == 1) acc2 = Planes{ea, eb};   // 0 + x = x: the first entry of an accumulator is a move
+        else if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
         e[i] = ea;
     });
     gf3_add(acc, acc2.nz, acc2.two);
@@ -614,7 +615,8 @@ __device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32
         const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
         const uint32_t ea = lds_tab<128 * i>(ra);
         const uint32_t eb = lds_tab<128 * i + PLANE>(ra);
-        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        if (i == 0) acc = Planes{ea, eb}; else if (i == 1) acc2 = Planes{ea, eb};   // 0 + x = x: the first entry of an accumulator is a move
+        else if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
         ev[i] = ea;
     });
 #pragma unroll

@@ -362,7 +362,8 @@ __device__ __forceinline__ void dec_cw_s(const uint8_t* src, uint8_t* dst, uint3
         const uint32_t ra = __byte_perm(xw[i >> 2], pa, 0x7650u | (uint32_t)(i & 3));
         const uint32_t ea = lds_tab<128 * i>(ra);
         const uint32_t eb = lds_tab<128 * i + PLANE>(ra);
-        if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
+        if (i == 0) acc = Planes{ea, eb}; else if (i == 1) acc2 = Planes{ea, eb};   // 0 + x = x: the first entry of an accumulator is a move
+        else if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
         ev[i] = ea;
     });
 #pragma unroll
