@@ -548,23 +548,30 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
 // =============================================================================================
 // The rare branches of a codeword's screen live out of line: inlined into the four unrolled passes they made the hot loop 100 KB of
 // code (6350 instructions), more than the instruction caches hold for 27 warps at different places of it.
-// bytes >= 27 in the received words (out-of-alphabet symbols read as their low three trits, unpack3, OLD:28-31)
-static __device__ __noinline__ void dec_cw_mod27(uint8_t* src)
+// bytes >= 27 in the received words (out-of-alphabet symbols read as their low three trits, unpack3, OLD:28-31).
+// The out-of-line paths take .shared addresses (32 bits), not pointers: the hot path then never forms the 64-bit generic addresses
+// that pointer arguments of a call it rarely makes would need before every branch (ten instructions per codeword pass).
+__device__ __forceinline__ uint8_t* smem_ptr(uint32_t a) { return reinterpret_cast<uint8_t*>(__cvta_shared_to_generic(a)); }
+static __device__ __noinline__ void dec_cw_mod27(uint32_t src_s)
 {
+    uint8_t* src = smem_ptr(src_s);
     for (int i = 0; i < 26; ++i) src[i] = (uint8_t)(src[i] % 27u);   // in place in the staged run: the codeword belongs to this lane alone
 }
 // a codeword whose received parity differs from the parity its data symbols imply: finish the syndrome screen with the R parity
 // positions (table rows K..25 hold -x in the planes), subtract the clean-codeword constant -- that is the parity residual, from which
 // the bounded-distance decoder (dev.cuh rs_bd_fix) repairs the data symbols the hot path has already stored
 template <int K>
-static __device__ __noinline__ void dec_cw_dirty5(const uint8_t* src, uint8_t* dst, uint32_t acc_nz, uint32_t acc_two, const uint8_t* tab_v, const uint32_t* chk_v,
-                                                  const GfTables& sg, uint32_t* status)
+static __device__ __noinline__ void dec_cw_dirty5(uint32_t src_s, uint32_t dst_s, uint32_t acc_nz, uint32_t acc_two, uint32_t tab_s, uint32_t chk_s, uint32_t sg_s, uint32_t* status)
 {
     constexpr int PLANE = 26 * 32;
+    const uint8_t* src = smem_ptr(src_s);
+    const uint32_t* tab_v = reinterpret_cast<const uint32_t*>(smem_ptr(tab_s));
+    const uint32_t* chk_v = reinterpret_cast<const uint32_t*>(smem_ptr(chk_s));
+    const GfTables& sg = *reinterpret_cast<const GfTables*>(smem_ptr(sg_s));
     Planes d{acc_nz, acc_two};
 #pragma unroll 1
     for (int i = K; i < 26; ++i) {
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(tab_v) + 32 * i + src[i];   // src[i] < 32 here (dec_cw_mod27 ran if any byte was larger)
+        const uint32_t* row = tab_v + 32 * i + src[i];             // src[i] < 32 here (dec_cw_mod27 ran if any byte was larger)
         gf3_add(d, row[0], row[PLANE]);
     }
     const uint32_t cn = chk_v[0], ct = chk_v[1];
@@ -572,19 +579,20 @@ static __device__ __noinline__ void dec_cw_dirty5(const uint8_t* src, uint8_t* d
     if (!(d.nz >> 8)) return;                                  // a parity byte 27..31 (alias of 0..4) in an otherwise clean codeword
     uint32_t lo, hi;
     planes_to_parity<K>(d.nz, d.two, lo, hi);
-    rs_bd_fix<K>(sg, chien_of(&sg), dst, lo, hi, status, true);   // the image keeps the Chien tables behind the GF(27) tables, as HostTables does
+    rs_bd_fix<K>(sg, chien_of(&sg), smem_ptr(dst_s), lo, hi, status, true);   // the image keeps the Chien tables behind the GF(27) tables, as HostTables does
 }
-// ---- one codeword of decode phase B: 26 received symbols at src (even address) -> K descrambled data symbols scattered at byte stride 9
-// from dst, and the screen: the parity the K data symbols imply (K table look-ups, plane sums), scrambled in the plane domain (par_*: see
-// k_v5_image_dec), converted to bytes and compared with the R received parity symbols as they lie in the run -- 6 look-ups, 18 LOP3 and
-// 6 PRMT fewer per codeword than the full 26-position syndrome sum, which only dirty codewords finish (dec_cw_dirty5)
+// ---- one codeword of decode phase B: 26 received symbols at .shared address sa (even) -> K descrambled data symbols scattered at byte
+// stride 9 from .shared address da, and the screen: the parity the K data symbols imply (K table look-ups, plane sums), scrambled in the
+// plane domain (par_*: see k_v5_image_dec), converted to bytes and compared with the R received parity symbols as they lie in the run --
+// 6 look-ups, 18 LOP3 and 6 PRMT fewer per codeword than the full 26-position syndrome sum, which only dirty codewords finish
+// (dec_cw_dirty5).  pa = .shared address of the variant's table block, chk_s / sg_s = .shared addresses of its clean-codeword constant
+// and of the GF(27) tables
 template <int K>
-__device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, uint32_t par_nz, uint32_t par_two, const uint32_t* chk_v,
-                                        const GfTables& sg, uint32_t* status)
+__device__ __forceinline__ void dec_cw5(uint32_t sa, uint32_t da, uint32_t pa, uint32_t par_nz, uint32_t par_two, uint32_t chk_s, uint32_t sg_s, uint32_t* status)
 {
     constexpr int PLANE = 4 * 26 * 32, W = K / 4, NW = (K + 3) / 4;
     asm volatile("" : "+r"(pa));   // the block address in a vector register: with a uniform one PRMT would need its selector in a register (a move per symbol)
-    const uint32_t sa = smem_u32(src), sh = (sa & 2u) * 8u;
+    const uint32_t sh = (sa & 2u) * 8u;
     uint32_t xw[7];
     auto load = [&]() {
         static_for<0, 7>([&](auto jc) {
@@ -596,7 +604,7 @@ __device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32
         xw[6] = (xw[6] >> sh) & 0xFFFFu;                           // symbols 24, 25 only
     };
     load();
-    if ((xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6]) & 0xE0E0E0E0u) { dec_cw_mod27(const_cast<uint8_t*>(src)); load(); }
+    if ((xw[0] | xw[1] | xw[2] | xw[3] | xw[4] | xw[5] | xw[6]) & 0xE0E0E0E0u) { dec_cw_mod27(sa); load(); }
     // the received parity symbols K..25 as bytes of two words
     uint32_t rx_lo, rx_hi = 0;
     if constexpr (K % 4 == 0) {
@@ -619,15 +627,17 @@ __device__ __forceinline__ void dec_cw5(const uint8_t* src, uint8_t* dst, uint32
         else if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
         ev[i] = ea;
     });
-#pragma unroll
-    for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];       // stores after all loads: nothing to order
+    static_for<0, K>([&](auto ic) {                                // stores after all loads: nothing to order
+        constexpr int i = decltype(ic)::value;
+        asm volatile("st.shared.u8 [%0+%1], %2;" ::"r"(da), "n"(9 * i), "r"(ev[i]) : "memory");
+    });
     gf3_add(acc, acc2.nz, acc2.two);
     Planes s = acc;
     gf3_add(s, par_nz, par_two);
     uint32_t lo, hi;
     planes_to_parity<K>(s.nz, s.two, lo, hi);
     if ((26 - K > 4) ? (((lo ^ rx_lo) | (hi ^ rx_hi)) != 0u) : (lo != rx_lo))
-        dec_cw_dirty5<K>(src, dst, acc.nz, acc.two, tab_v, chk_v, sg, status);
+        dec_cw_dirty5<K>(sa, da, acc.nz, acc.two, pa, chk_s, sg_s, status);
 }
 
 // pixel value -> RGB8 (decode_raw_words_to_pixels + dequantize_ycbcr + ycbcr_to_rgb, OLD:706-722, IMG:57-84) in integers.  The
@@ -752,7 +762,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
         if (lane == 0) { mbar_init(bar, 9); fence_mbar_init(); }
     }
     __syncthreads();
-    const uint32_t tabA32 = smem_u32(smem);
+    const uint32_t tabA32 = smem_u32(smem), R32 = smem_u32(R), S32 = smem_u32(S), chk32 = tabA32 + L5::DEC_CHK, sg32 = tabA32 + L5::DEC_GF;
     const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L5::DEC_CHK);
     const uint32_t par0n = chk[6], par0t = chk[7], par1n = chk[8], par1t = chk[9], par2n = chk[10], par2t = chk[11];   // parity-compare constants (k_v5_image_dec)
     const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
@@ -815,14 +825,14 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
                 constexpr int p = decltype(pc)::value;
                 const uint2 r = rt[32 * p + lane];
                 const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFFu));
-                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, smem + p * L5::DEC_VAR, p == 0 ? par0n : p == 1 ? par1n : par2n,
-                                 p == 0 ? par0t : p == 1 ? par1t : par2t, chk + 2 * p, sg, status);
+                dec_cw5<K>(R32 + (r.x >> 16) + pb, S32 + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, p == 0 ? par0n : p == 1 ? par1n : par2n,
+                                 p == 0 ? par0t : p == 1 ? par1t : par2t, chk32 + 8 * p, sg32, status);
             });
             const uint2 r = rt[96 + lane];
             const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFu));
             if (r.y != REC_IDLE) {
                 const uint32_t v = r.y >> 8;
-                dec_cw5<K>(R + (r.x >> 16) + pb, S + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, smem + v * L5::DEC_VAR, chk[6 + 2 * v], chk[7 + 2 * v], chk + 2 * v, sg, status);
+                dec_cw5<K>(R32 + (r.x >> 16) + pb, S32 + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, chk[6 + 2 * v], chk[7 + 2 * v], chk32 + 8 * v, sg32, status);
             }
         }
         __syncwarp();

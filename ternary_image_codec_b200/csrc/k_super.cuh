@@ -319,9 +319,11 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_encode_super(FastParams Q, Super
 // squeeze pass has scaled the runs).  Only codewords that differ finish the 26-position syndrome sum and go to the bounded-distance decoder.
 // c4 = {chk_nz, chk_two, par_nz, par_two} of the codeword's (k, variant)
 template <int K>
-static __device__ __noinline__ void dec_cw_dirty_s(const uint8_t* src, uint8_t* dst, uint32_t acc_nz, uint32_t acc_two, const uint8_t* tab_v, uint32_t chk_nz, uint32_t chk_two,
-                                                   const GfTables& sg, const uint32_t* chien, uint32_t* status)
+static __device__ __noinline__ void dec_cw_dirty_s(uint32_t src_s, uint32_t dst_s, uint32_t acc_nz, uint32_t acc_two, uint32_t tab_s, uint32_t chk_nz, uint32_t chk_two,
+                                                   uint32_t sg_s, const uint32_t* chien, uint32_t* status)
 {
+    const uint8_t* src = smem_ptr(src_s);
+    const uint8_t* tab_v = smem_ptr(tab_s);
     Planes d{acc_nz, acc_two};
 #pragma unroll 1
     for (int i = K; i < 26; ++i) {
@@ -332,13 +334,14 @@ static __device__ __noinline__ void dec_cw_dirty_s(const uint8_t* src, uint8_t* 
     if (!(d.nz >> 8)) return;
     uint32_t lo, hi;
     planes_to_parity<K>(d.nz, d.two, lo, hi);
-    rs_bd_fix<K>(sg, chien, dst, lo, hi, status, true);
+    rs_bd_fix<K>(*reinterpret_cast<const GfTables*>(smem_ptr(sg_s)), chien, smem_ptr(dst_s), lo, hi, status, true);
 }
+// sa / da / pa / sg_s: .shared addresses (the out-of-line path takes no pointers: k_fast5.cuh dec_cw_mod27)
 template <int K>
-__device__ __forceinline__ void dec_cw_s(const uint8_t* src, uint8_t* dst, uint32_t pa, const uint8_t* tab_v, const uint4 c4, const GfTables& sg, const uint32_t* chien, uint32_t* status)
+__device__ __forceinline__ void dec_cw_s(uint32_t sa, uint32_t da, uint32_t pa, const uint4 c4, uint32_t sg_s, const uint32_t* chien, uint32_t* status)
 {
     constexpr int PLANE = 4 * 26 * 32, W = K / 4;
-    const uint32_t sa = smem_u32(src), sh = (sa & 2u) * 8u;
+    const uint32_t sh = (sa & 2u) * 8u;
     uint32_t xw[7];
     static_for<0, 7>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
@@ -366,15 +369,17 @@ __device__ __forceinline__ void dec_cw_s(const uint8_t* src, uint8_t* dst, uint3
         else if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
         ev[i] = ea;
     });
-#pragma unroll
-    for (int i = 0; i < K; ++i) dst[9 * i] = (uint8_t)ev[i];
+    static_for<0, K>([&](auto ic) {
+        constexpr int i = decltype(ic)::value;
+        asm volatile("st.shared.u8 [%0+%1], %2;" ::"r"(da), "n"(9 * i), "r"(ev[i]) : "memory");
+    });
     gf3_add(acc, acc2.nz, acc2.two);
     Planes s = acc;
     gf3_add(s, c4.z, c4.w);
     uint32_t lo, hi;
     planes_to_parity<K>(s.nz, s.two, lo, hi);
     if ((26 - K > 4) ? ((((lo << 2) ^ rx_lo) | ((hi << 2) ^ rx_hi)) != 0u) : ((lo << 2) != rx_lo))
-        dec_cw_dirty_s<K>(src, dst, acc.nz, acc.two, tab_v, c4.x, c4.y, sg, chien, status);
+        dec_cw_dirty_s<K>(sa, da, acc.nz, acc.two, pa, c4.x, c4.y, sg_s, chien, status);
 }
 
 // ---- decode phase A of the super-tile kernel: a unit (a row of a 26-wide 2D tile when rev) -> six pixels -> 18 RGB bytes, with the pixel
@@ -537,14 +542,14 @@ __global__ void __launch_bounds__(SUP_TPB, 2) k_decode_super(FastParams Q, Super
             if (pass + SUP_WARPS < n_pass) { e_nx = __ldg(map + 32 * (pass + SUP_WARPS) + lane); kv_nx = __ldg(pkv + pass + SUP_WARPS); }
             if (e == SUP_IDLE) continue;
             const uint32_t ks = kv & 3u, v = kv >> 2, b = e & 15u, cl = e >> 4, K = P.kk[ks];
-            const uint8_t* src = R + P.run_base[b] + 26u * cl;
-            uint8_t* dst = S + 9u * K * cl + b;
-            const uint32_t toff = P.off_tab[ks] + v * 6656u;
+            const uint32_t src = smem32 + P.off_U + P.run_base[b] + 26u * cl;
+            const uint32_t dst = S32 + 9u * K * cl + b;
+            const uint32_t toff = P.off_tab[ks] + v * 6656u, sg32 = smem32 + P.off_gf;
             const uint4 c4 = *reinterpret_cast<const uint4*>(chk + 4 * (3 * ks + v));
-            if (K == 20) dec_cw_s<20>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
-            else if (K == 22) dec_cw_s<22>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
-            else if (K == 24) dec_cw_s<24>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
-            else dec_cw_s<18>(src, dst, smem32 + toff, smem + toff, c4, sg, chien_of(gf), Q.status + 2 * f);
+            if (K == 20) dec_cw_s<20>(src, dst, smem32 + toff, c4, sg32, chien_of(gf), Q.status + 2 * f);
+            else if (K == 22) dec_cw_s<22>(src, dst, smem32 + toff, c4, sg32, chien_of(gf), Q.status + 2 * f);
+            else if (K == 24) dec_cw_s<24>(src, dst, smem32 + toff, c4, sg32, chien_of(gf), Q.status + 2 * f);
+            else dec_cw_s<18>(src, dst, smem32 + toff, c4, sg32, chien_of(gf), Q.status + 2 * f);
         }
         __syncthreads();                           // S complete, R dead
         SUP_TICK(6);
