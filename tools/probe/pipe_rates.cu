@@ -87,7 +87,7 @@ static void run(const char* name, F launch, int per_iter, int warps_per_smsp)
 int main()
 {
     const char* names[16] = {"IMAD r,r,r", "IMAD.HI (mul.hi) r,r", "LOP3", "PRMT r,r,r", "SHF.R.W", "IDP.2A", "IDP.4A", "IADD", "IMAD.HI (mad.hi) r,r,r", "VIMNMX (min)",
-                             "IMAD r,imm,r", "SHL imm", "IMAD.HI r,imm", "LOP3 + IMAD pair", "FFMA r,r,r", "VIADDMNMX"};
+                             "IMAD r,imm,r", "SHL imm", "IMAD.HI r,imm", "LOP3 + IMAD pair", "FFMA r,r,r", "vadd.min (PTX video op: emulated)"};
 #define RUN(OP, PER) run(names[OP], [](uint32_t* o, long long* c) { k<OP><<<1, 1024>>>(o, 12345u, c); }, PER, 8);
     RUN(0, 1) RUN(10, 1) RUN(1, 1) RUN(12, 1) RUN(8, 1) RUN(2, 1) RUN(3, 1) RUN(4, 1) RUN(11, 1) RUN(5, 1) RUN(6, 1) RUN(7, 1) RUN(9, 1) RUN(15, 1) RUN(14, 1) RUN(13, 2)
     run("LDS.32 27-entry rows", [](uint32_t* o, long long* c) { ks<0><<<1, 1024>>>(o, 12345u, c); }, 1, 8);
