@@ -543,17 +543,17 @@ def test_multi_frame_stream_device(codec, oracle, t3):
         assert np.array_equal(got[f], oracle.encode_rgb(oc, frames[f], 0))
 
 
-@pytest.mark.parametrize("stride_pad", [0, 16, 3])
-def test_fused_regular_frames_tensor_copies(codec, oracle, t3, stride_pad):
-    """1080p frames at k = 20 are `regular` (every band holds the same number of codewords, band pitch a multiple of 16 bytes): the v5
+@pytest.mark.parametrize("stride_pad,kw,shape,F", [(0, dict(profile=T.P3, uep=2), (1920, 1080), 3), (16, dict(profile=T.P3, uep=2), (1920, 1080), 3),
+                                                   (3, dict(profile=T.P3, uep=2), (1920, 1080), 3), (0, dict(profile=T.P1, uep=0), (3840, 2160), 2)])
+def test_fused_regular_frames_tensor_copies(codec, oracle, t3, stride_pad, kw, shape, F):
+    """1080p frames at k = 20 and 4K frames at k = 24 are `regular` (every band holds the same number of codewords, band pitch a multiple of 16 bytes): the v5
     kernels then move the nine runs of a mini-tile by one 3-D tensor copy each way (UTMASTG / UTMALDG).  Three frames in one device
     call -- frame strides that keep the batch regular (0, 16 words) and one that does not (3 words: the per-run bulk copies) -- and the
     chunked host pipelines (tile ranges that start inside a frame): encode parity with the oracle, t errors per codeword corrected,
     decode parity."""
     import torch
-    kw = dict(profile=T.P3, uep=2)
     oc, gc = both(kw)
-    n_px, F = 1920 * 1080, 3
+    n_px = shape[0] * shape[1]
     frames = np.stack([T.synth_rgb(70 + f, n_px) for f in range(F)])
     want = [oracle.encode_rgb(oc, frames[f], t3.FIXED) for f in range(F)]
     wpf = t3.profile_words(gc, n_px // 2)
