@@ -46,6 +46,7 @@ struct FastParams {
     uint32_t* status;       // decode: {ok, n_corrected} per frame
     uint32_t chk_nz[7], chk_two[7]; // decode: sum of T_i[13*st_i] per scrambler phase (6) and for p0==0
     uint32_t flags;         // v5: 1 | delay << 8 = staggered start of every other warp (k_fast5.cuh, T3C_V5_FLAGS); 2 = decode: runs arrive by one 3-D tensor copy
+    uint32_t ts_tiles;      // v5 encode with the tensor store: mini-tiles of a frame whose 23-chunk box stays inside a band's row (0: no tensor store)
     uint64_t band_stride;   // v5 decode with the tensor copy: bytes between the runs of neighbouring bands (26 * codewords per band, a multiple of 16)
 };
 
@@ -1603,6 +1604,11 @@ static int launch_v5_enc(const DevTables& T, FastParams P, const Geom& g, cudaSt
                                                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
                 P.flags |= 16u;
                 P.band_stride = pitch;
+                // ((52 + 338 t) & ~15) + RUN_PITCH <= pitch  for every t < ts_tiles
+                uint64_t t = pitch >= (uint64_t)L5::RUN_PITCH + 52 ? (pitch - L5::RUN_PITCH - 52) / 338 + 1 : 0;
+                while (t && ((52ull + 338ull * (t - 1)) & ~15ull) + L5::RUN_PITCH > pitch) --t;
+                while (((52ull + 338ull * t) & ~15ull) + L5::RUN_PITCH <= pitch) ++t;
+                P.ts_tiles = (uint32_t)(t > 0xFFFFFFFFull ? 0xFFFFFFFFull : t);
             }
         }
     }

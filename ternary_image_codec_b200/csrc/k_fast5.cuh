@@ -300,7 +300,7 @@ __global__ void k_smem_window_probe(uint32_t* out)
 // pass, vb unused); VAR < 0: vb = variant * ENC_VAR, per lane.  TAB0 = offset of the variant-0 table block {A[K][27] | B[K][27]} from
 // the start of dynamic shared memory
 template <int K, int VAR, uint32_t TAB0, uint32_t ENC_VAR>
-__device__ __forceinline__ void enc_cw5(const uint8_t* src, uint8_t* dst, uint32_t vb, uint32_t pat_nz, uint32_t pat_two)
+__device__ __forceinline__ void enc_cw5(const uint8_t* src, uint8_t* dst, uint32_t vb)
 {
     constexpr int R = 26 - K;
     constexpr uint32_t PLANE = 4 * K * 27, BASE = SMEM_WINDOW_BASE + TAB0 + (VAR >= 0 ? VAR * ENC_VAR : 0u);
@@ -310,14 +310,14 @@ __device__ __forceinline__ void enc_cw5(const uint8_t* src, uint8_t* dst, uint32
         constexpr int i = decltype(ic)::value;
         const uint32_t d4 = src[9 * i];
         const uint32_t ra = VAR >= 0 ? d4 : d4 + vb;
-        // plane B is the same in every variant: the mixed pass reads it from block 0, where all its lanes meet in one 27-word row
-        const uint32_t ea = lds_abs<BASE + 108 * i>(ra), eb = lds_abs<(VAR >= 0 ? BASE : SMEM_WINDOW_BASE + TAB0) + 108 * i + PLANE>(d4);
+        // plane B is the same in every variant but for position 0 (which carries the variant's parity scramble pattern): the mixed pass
+        // reads the others from block 0, where all its lanes meet in one 27-word row
+        const uint32_t ea = lds_abs<BASE + 108 * i>(ra), eb = lds_abs<(VAR >= 0 ? BASE : SMEM_WINDOW_BASE + TAB0) + 108 * i + PLANE>(i == 0 ? ra : d4);
         if (i == 0) acc = Planes{ea, eb}; else if (i == 1) acc2 = Planes{ea, eb};   // 0 + x = x: the first entry of an accumulator is a move
         else if (i & 1) gf3_add(acc2, ea, eb); else gf3_add(acc, ea, eb);
         e[i] = ea;
     });
-    gf3_add(acc, acc2.nz, acc2.two);
-    gf3_add(acc, pat_nz, pat_two);
+    gf3_add(acc, acc2.nz, acc2.two);          // (the scramble pattern of the parity symbols came in with position 0's table entry)
     uint32_t lo, hi;
     planes_to_parity<K>(acc.nz, acc.two, lo, hi);
     // the codeword's 26 bytes as words: data symbols are the low bytes of the A entries
@@ -350,8 +350,18 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_enc(Geom g, const GfTables*
     for (int idx = tid; idx < 3 * K * 27; idx += TPB) {
         const int v = idx / (K * 27), rem = idx - v * (K * 27), i = rem / 27, d = rem - 27 * i;
         uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::ENC_VAR);
-        blk[rem] = pl[i][d][0] | gf->scr[st_of(g, v, i)][d];
-        blk[K * 27 + rem] = pl[i][d][1];
+        Planes e{pl[i][d][0], pl[i][d][1]};
+        if (i == 0) {   // the scrambler as seen by the parity symbols of a variant-v codeword rides on position 0: every codeword adds it exactly once
+            uint32_t nz = 0, two = 0;
+            for (int j = 0; j < L::R; ++j) {
+                const uint32_t st = st_of(g, v, K + j);
+                if (st) nz |= 7u << plane_shift<K>(j);
+                if (st == 2) two |= 7u << plane_shift<K>(j);
+            }
+            gf3_add(e, nz, two);
+        }
+        blk[rem] = e.nz | gf->scr[st_of(g, v, i)][d];
+        blk[K * 27 + rem] = e.two;
     }
     if (tid < 3) { // the scrambler as seen by the parity symbols of a variant-tid codeword, in the plane domain
         uint32_t nz = 0, two = 0;
@@ -444,8 +454,6 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
         if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
     }
     __syncthreads(); // tables, records and barriers ready; no block-level barrier after this one
-    const uint32_t* patp = reinterpret_cast<const uint32_t*>(smem + L5::ENC_PAT);
-    const uint32_t pat0n = patp[0], pat0t = patp[1], pat1n = patp[2], pat1t = patp[3], pat2n = patp[4], pat2t = patp[5];
     const uint64_t in_limit = P.in_stride * P.n_frames;
     uint32_t mt_lo, mt_hi;
     warp_range_smsp((uint64_t)P.n_tiles * P.n_frames, blockIdx.x, gridDim.x, warp, NW, mt_lo, mt_hi);
@@ -498,13 +506,13 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
                 constexpr int p = decltype(pc)::value;
                 const uint2 r = rt[32 * p + lane];
                 const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFFu));
-                enc_cw5<K, p, 0u, (uint32_t)L5::ENC_VAR>(S + (r.x & 0xFFFFu), U + (r.x >> 16) + pb, 0u, p == 0 ? pat0n : p == 1 ? pat1n : pat2n, p == 0 ? pat0t : p == 1 ? pat1t : pat2t);
+                enc_cw5<K, p, 0u, (uint32_t)L5::ENC_VAR>(S + (r.x & 0xFFFFu), U + (r.x >> 16) + pb, 0u);
             });
             const uint2 r = rt[96 + lane];
             const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFu));
             if (r.y != REC_IDLE) {
                 const uint32_t v = r.y >> 8;
-                enc_cw5<K, -1, 0u, (uint32_t)L5::ENC_VAR>(S + (r.x & 0xFFFFu), U + (r.x >> 16) + pb, v * L5::ENC_VAR, patp[2 * v], patp[2 * v + 1]);
+                enc_cw5<K, -1, 0u, (uint32_t)L5::ENC_VAR>(S + (r.x & 0xFFFFu), U + (r.x >> 16) + pb, v * L5::ENC_VAR);
             }
         }
         __syncwarp();
@@ -520,7 +528,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
         // 3-D tensor store (SASS UTMASTG) of all 23 chunks per row: the chunks behind this tile's last whole one hold its tail and stale
         // bytes, and the same warp's next tile stores over them (its row starts with this tile's tail, carried) -- after this store has
         // landed: bulk_wait_all above.  The first and the last tile of a stretch store exactly their own chunks, run by run.
-        const bool ts = (P.flags & 16u) && !first && !last && ((52ull + 338ull * c.tile) & ~15ull) + PITCH <= P.band_stride;
+        const bool ts = !first && !last && c.tile < P.ts_tiles;     // ts_tiles: 0 without the tensor store, else the tiles whose box stays inside a band's row
         if (lane < 9) {
             const uint32_t cend = (padb + L::RUN) >> 4, c0 = (first && padb) ? 1u : 0u;
             if (!last) carry[lane] = *reinterpret_cast<const uint4*>(U + PITCH * lane + 16 * cend);
