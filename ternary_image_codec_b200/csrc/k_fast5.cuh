@@ -429,6 +429,18 @@ __global__ void __launch_bounds__(256, 1) k_v5_image_dec(Geom g, const GfTables*
         reinterpret_cast<uint32_t*>(smem + L5::DEC_CHK)[6 + 2 * tid + 1] = e.two;
     }
     __syncthreads();
+    // par rides on position 0's table entries: every codeword's data sum then already holds it (no add in the hot path, six registers
+    // free); the out-of-line path, which needs the plain 26-position sum, takes it off again (dec_cw_dirty5)
+    if (tid < 3 * 32) {
+        const int v = tid >> 5, x = tid & 31;
+        uint32_t* blk = reinterpret_cast<uint32_t*>(smem + v * L5::DEC_VAR);
+        const uint32_t* par = reinterpret_cast<const uint32_t*>(smem + L5::DEC_CHK) + 6 + 2 * v;
+        Planes e{blk[x], blk[26 * 32 + x]};
+        gf3_add(e, par[0], par[1]);
+        blk[x] = e.nz;
+        blk[26 * 32 + x] = e.two;
+    }
+    __syncthreads();
     for (int i = tid; i < L5::DEC_IMAGE / 16; i += TPB) reinterpret_cast<uint4*>(image)[i] = reinterpret_cast<const uint4*>(smem)[i];
 }
 
@@ -591,8 +603,9 @@ static __device__ __noinline__ void dec_cw_dirty5(uint32_t src_s, uint32_t dst_s
         const uint32_t* row = tab_v + 32 * i + src[i];             // src[i] < 32 here (dec_cw_mod27 ran if any byte was larger)
         gf3_add(d, row[0], row[PLANE]);
     }
-    const uint32_t cn = chk_v[0], ct = chk_v[1];
+    const uint32_t cn = chk_v[0], ct = chk_v[1], pn = chk_v[6], pt = chk_v[7];   // par of this variant lies 24 bytes behind its chk
     gf3_add(d, cn, cn ^ ct);                                   // minus the constant: -x keeps nz and flips two where nz is set
+    gf3_add(d, pn, pn ^ pt);                                   // minus par, which the data sum brought along from position 0's entries
     if (!(d.nz >> 8)) return;                                  // a parity byte 27..31 (alias of 0..4) in an otherwise clean codeword
     uint32_t lo, hi;
     planes_to_parity<K>(d.nz, d.two, lo, hi);
@@ -605,7 +618,7 @@ static __device__ __noinline__ void dec_cw_dirty5(uint32_t src_s, uint32_t dst_s
 // (dec_cw_dirty5).  pa = .shared address of the variant's table block, chk_s / sg_s = .shared addresses of its clean-codeword constant
 // and of the GF(27) tables
 template <int K>
-__device__ __forceinline__ void dec_cw5(uint32_t sa, uint32_t da, uint32_t pa, uint32_t par_nz, uint32_t par_two, uint32_t chk_s, uint32_t sg_s, uint32_t* status)
+__device__ __forceinline__ void dec_cw5(uint32_t sa, uint32_t da, uint32_t pa, uint32_t chk_s, uint32_t sg_s, uint32_t* status)
 {
     constexpr int PLANE = 4 * 26 * 32, W = K / 4, NW = (K + 3) / 4;
     asm volatile("" : "+r"(pa));   // the block address in a vector register: with a uniform one PRMT would need its selector in a register (a move per symbol)
@@ -648,11 +661,9 @@ __device__ __forceinline__ void dec_cw5(uint32_t sa, uint32_t da, uint32_t pa, u
         constexpr int i = decltype(ic)::value;
         asm volatile("st.shared.u8 [%0+%1], %2;" ::"r"(da), "n"(9 * i), "r"(ev[i]) : "memory");
     });
-    gf3_add(acc, acc2.nz, acc2.two);
-    Planes s = acc;
-    gf3_add(s, par_nz, par_two);
+    gf3_add(acc, acc2.nz, acc2.two);          // (par came in with position 0's table entry)
     uint32_t lo, hi;
-    planes_to_parity<K>(s.nz, s.two, lo, hi);
+    planes_to_parity<K>(acc.nz, acc.two, lo, hi);
     if ((26 - K > 4) ? (((lo ^ rx_lo) | (hi ^ rx_hi)) != 0u) : (lo != rx_lo))
         dec_cw_dirty5<K>(sa, da, acc.nz, acc.two, pa, chk_s, sg_s, status);
 }
@@ -781,7 +792,6 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
     __syncthreads();
     const uint32_t tabA32 = smem_u32(smem), R32 = smem_u32(R), S32 = smem_u32(S), chk32 = tabA32 + L5::DEC_CHK, sg32 = tabA32 + L5::DEC_GF;
     const uint32_t* chk = reinterpret_cast<const uint32_t*>(smem + L5::DEC_CHK);
-    const uint32_t par0n = chk[6], par0t = chk[7], par1n = chk[8], par1t = chk[9], par2n = chk[10], par2t = chk[11];   // parity-compare constants (k_v5_image_dec)
     const uint64_t in_limit = P.in_stride * (P.n_frames - 1) + 9 * g.n_out;
     uint32_t mt_lo, mt_hi;
     warp_range_smsp((uint64_t)P.n_tiles * P.n_frames, blockIdx.x, gridDim.x, warp, NW, mt_lo, mt_hi);
@@ -842,14 +852,13 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
                 constexpr int p = decltype(pc)::value;
                 const uint2 r = rt[32 * p + lane];
                 const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFFu));
-                dec_cw5<K>(R32 + (r.x >> 16) + pb, S32 + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, p == 0 ? par0n : p == 1 ? par1n : par2n,
-                                 p == 0 ? par0t : p == 1 ? par1t : par2t, chk32 + 8 * p, sg32, status);
+                dec_cw5<K>(R32 + (r.x >> 16) + pb, S32 + (r.x & 0xFFFFu), tabA32 + p * L5::DEC_VAR, chk32 + 8 * p, sg32, status);
             });
             const uint2 r = rt[96 + lane];
             const uint32_t pb = __shfl_sync(0xFFFFFFFFu, padb, (int)(r.y & 0xFu));
             if (r.y != REC_IDLE) {
                 const uint32_t v = r.y >> 8;
-                dec_cw5<K>(R32 + (r.x >> 16) + pb, S32 + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, chk[6 + 2 * v], chk[7 + 2 * v], chk32 + 8 * v, sg32, status);
+                dec_cw5<K>(R32 + (r.x >> 16) + pb, S32 + (r.x & 0xFFFFu), tabA32 + v * L5::DEC_VAR, chk32 + 8 * v, sg32, status);
             }
         }
         __syncwarp();
