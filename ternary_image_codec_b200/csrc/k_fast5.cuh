@@ -502,6 +502,8 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::ENC_WARPS, 1) k_encode_v5
         TileCursor nx = c;
         cursor_next<PIX>(nx, P, g, P.in_stride, P.out_stride, lane);
         if (left > 1 && lane == 0) fetch(nx.pix);                                  // IN is free again: next tile's pixels on their way
+        // (advancing the cursor in place at the end of the loop, as the decoder does, frees seven registers across phase B -- the kernel
+        // then compiles to 64 registers -- and was measured slower: 140.2 us against 138.3 us)
         if (lane < 9) {
 #if T3C_ENC_WAIT_READ
             bulk_wait_read();
@@ -862,9 +864,12 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
             }
         }
         __syncwarp();
-        TileCursor nx = c;
-        cursor_next<PIX>(nx, P, g, P.out_stride, P.in_stride, lane);
-        if (left > 1 && lane < 9) { if (tensor_tile(nx.tile)) fetch_tensor(nx.f, nx.tile); else fetch(nx.run); }  // R is free again: next tile's runs on their way
+        if (left > 1 && lane < 9) {   // R is free again: next tile's runs on their way (the cursor itself advances at the end of the loop)
+            const bool wrap = c.tile + 1 == P.tile0 + P.n_tiles;
+            const uint32_t nf = wrap ? c.f + 1 : c.f, nt = wrap ? P.tile0 : c.tile + 1;
+            if (tensor_tile(nt)) fetch_tensor(nf, nt);
+            else fetch(wrap ? P.in_stride * nf + 52 + 26 * (g.cw_base[lane] + (uint64_t)C_MINI * nt) : c.run + 26 * C_MINI);
+        }
         if (lane == 0) {
             bulk_wait_read();                                                        // the previous tile's bulk store has read OUT
             if (!first) *reinterpret_cast<uint4*>(OUT) = carry[0];                   // bytes [0, pad): the previous tile's tail
@@ -886,7 +891,7 @@ __global__ void __launch_bounds__(32 * Cfg5<K, WORDS>::DEC_WARPS, 1) k_decode_v5
         }
         __syncwarp();
         first = last;
-        c = nx;
+        cursor_next<PIX>(c, P, g, P.out_stride, P.in_stride, lane);
     }
     if (lane == 0) bulk_wait_all();
 }
