@@ -197,7 +197,7 @@ template <int K, bool WORDS = false> struct Cfg5 {
     static constexpr int SMEM_MAX = 227 * 1024;
     // lane records of phase B: [tile mod 3][pass][lane] -> {source offset | destination offset << 16, band | variant << 8}
     static constexpr int REC_BYTES = 3 * 128 * 8;
-    // encode, CTA-shared: per variant {A[K][27] | B[K][27]} | pat[3][2] | records
+    // encode, CTA-shared: per variant {A[K][27] | B[K][27]} | pat[3][2] (kept for reference: the kernel finds the pattern in position 0's entries) | records
     static constexpr int ENC_PLANE = 4 * K * 27, ENC_VAR = 2 * ENC_PLANE, ENC_PAT = 3 * ENC_VAR, ENC_REC = (ENC_PAT + 24 + 15) / 16 * 16;
     static constexpr int ENC_IMAGE = ENC_REC + REC_BYTES;                       // what the image holds
     static constexpr int ENC_WARP = (ENC_IMAGE + 127) / 128 * 128;              // per-warp blocks start 128-byte aligned (the tensor store reads U from there)
@@ -615,7 +615,7 @@ static __device__ __noinline__ void dec_cw_dirty5(uint32_t src_s, uint32_t dst_s
 }
 // ---- one codeword of decode phase B: 26 received symbols at .shared address sa (even) -> K descrambled data symbols scattered at byte
 // stride 9 from .shared address da, and the screen: the parity the K data symbols imply (K table look-ups, plane sums), scrambled in the
-// plane domain (par_*: see k_v5_image_dec), converted to bytes and compared with the R received parity symbols as they lie in the run --
+// plane domain (the constant par of k_v5_image_dec, which rides on position 0's table entries), converted to bytes and compared with the R received parity symbols as they lie in the run --
 // 6 look-ups, 18 LOP3 and 6 PRMT fewer per codeword than the full 26-position syndrome sum, which only dirty codewords finish
 // (dec_cw_dirty5).  pa = .shared address of the variant's table block, chk_s / sg_s = .shared addresses of its clean-codeword constant
 // and of the GF(27) tables
